@@ -1,0 +1,169 @@
+"""ctypes binding of oracle/_ref/libmmref.so (the UNMODIFIED reference modules behind oracle/ref_harness.cpp)
+and of oracle/_ref/libmmplug.so (our drop-in modules in the same graph).
+
+TEST INFRASTRUCTURE: only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may import this.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+REF_LIB = os.path.join(_HERE, "_ref", "libmmref.so")
+PLUG_LIB = os.path.join(_HERE, "_ref", "libmmplug.so")
+
+# SimpleSphericalParticles.h:27-50
+VERT_NONE, VERT_FLOAT_XYZ, VERT_FLOAT_XYZR, VERT_SHORT_XYZ, VERT_DOUBLE_XYZ = range(5)
+(COL_NONE, COL_UINT8_RGB, COL_UINT8_RGBA, COL_FLOAT_RGB, COL_FLOAT_RGBA, COL_FLOAT_I, COL_USHORT_RGBA,
+ COL_DOUBLE_I) = range(8)
+
+
+class MmhList(C.Structure):
+    _fields_ = [("vtx", C.c_void_p), ("col", C.c_void_p), ("count", C.c_uint64), ("vtx_type", C.c_int32),
+                ("vtx_stride", C.c_uint32), ("col_type", C.c_int32), ("col_stride", C.c_uint32),
+                ("global_radius", C.c_float), ("global_rgba", C.c_uint8 * 4), ("irange", C.c_float * 2)]
+
+
+def available(path: str = REF_LIB) -> bool:
+    return os.path.exists(path)
+
+
+class Harness:
+    """source -> ParticlesToDensity -> IsoSurface -> sink, driven through the reference's Call/Slot API."""
+
+    def __init__(self, lib_path: str = REF_LIB, preload: str | None = None):
+        if preload:
+            C.CDLL(preload, mode=C.RTLD_GLOBAL)
+        self.lib = C.CDLL(lib_path)
+        L = self.lib
+        L.mmh_create.restype = C.c_void_p
+        L.mmh_destroy.argtypes = [C.c_void_p]
+        L.mmh_set_particles.argtypes = [C.c_void_p, C.c_int, C.POINTER(MmhList), C.POINTER(C.c_float), C.c_uint]
+        L.mmh_set_p2d_params.argtypes = [C.c_void_p] + [C.c_int] * 8 + [C.c_float, C.c_int]
+        L.mmh_set_param_int.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int]
+        L.mmh_set_param_float.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_float]
+        L.mmh_pull_volume.argtypes = [C.c_void_p, C.c_uint, C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_double),
+                                      C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_double)]
+        L.mmh_pull_mesh.argtypes = [C.c_void_p, C.c_uint, C.c_float, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
+                                    C.POINTER(C.c_double)]
+        L.mmh_copy_mesh.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.mmh_mc_tables.argtypes = [C.c_void_p] * 5
+        self.h = L.mmh_create()
+        if not self.h:
+            raise RuntimeError("mmh_create failed")
+        self._keep = []
+        self.res = (16, 16, 16)
+        self.frame = 0
+
+    def close(self):
+        if self.h:
+            self.lib.mmh_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def threads(self) -> int:
+        return self.lib.mmh_threads()
+
+    def set_threads(self, n: int):
+        self.lib.mmh_set_threads(int(n))
+
+    def set_particles(self, lists, bbox, frame_id: int = 0):
+        """lists: iterable of dicts with keys vtx (np array, raw bytes), vtx_type, vtx_stride, optional col/col_type/
+        col_stride, global_radius, global_rgba, irange. bbox = (minx,miny,minz,maxx,maxy,maxz)."""
+        arr = (MmhList * len(lists))()
+        self._keep = []
+        for i, l in enumerate(lists):
+            vtx = np.ascontiguousarray(l["vtx"])
+            self._keep.append(vtx)
+            arr[i].vtx = vtx.ctypes.data
+            arr[i].vtx_type = l["vtx_type"]
+            arr[i].vtx_stride = l.get("vtx_stride", 0)
+            arr[i].count = l["count"]
+            col = l.get("col")
+            if col is not None:
+                col = np.ascontiguousarray(col) if not isinstance(col, int) else col
+                if isinstance(col, int):
+                    arr[i].col = col
+                else:
+                    self._keep.append(col)
+                    arr[i].col = col.ctypes.data
+            arr[i].col_type = l.get("col_type", COL_NONE)
+            arr[i].col_stride = l.get("col_stride", 0)
+            arr[i].global_radius = l.get("global_radius", 0.5)
+            rgba = l.get("global_rgba", (255, 255, 255, 255))
+            for k in range(4):
+                arr[i].global_rgba[k] = rgba[k]
+            ir = l.get("irange", (0.0, 1.0))
+            arr[i].irange[0], arr[i].irange[1] = ir
+        bb = (C.c_float * 6)(*[float(b) for b in bbox])
+        self.frame = frame_id
+        rc = self.lib.mmh_set_particles(self.h, len(lists), arr, bb, frame_id)
+        if rc:
+            raise RuntimeError(f"mmh_set_particles rc={rc}")
+
+    def set_p2d_params(self, res, cyclic=(True, True, True), normalize=True, sigma=1.0, aggregator=0,
+                       for_surface=False):
+        self.res = tuple(int(r) for r in res)
+        rc = self.lib.mmh_set_p2d_params(self.h, aggregator, *self.res, *[int(bool(c)) for c in cyclic],
+                                         int(bool(normalize)), float(sigma), int(bool(for_surface)))
+        if rc:
+            raise RuntimeError(f"mmh_set_p2d_params rc={rc}")
+
+    def set_param(self, module: int, name: str, value):
+        if isinstance(value, float):
+            rc = self.lib.mmh_set_param_float(self.h, module, name.encode(), value)
+        else:
+            rc = self.lib.mmh_set_param_int(self.h, module, name.encode(), int(value))
+        if rc:
+            raise RuntimeError(f"no parameter {name!r} on module {module}")
+
+    def pull_volume(self, copy: bool = True):
+        sx, sy, sz = self.res
+        info = (C.c_uint64 * 5)()
+        mm = (C.c_double * 2)()
+        org = (C.c_float * 3)()
+        sd = (C.c_float * 3)()
+        ms = C.c_double()
+        out = np.empty((sz, sy, sx), dtype=np.float32) if copy else None
+        rc = self.lib.mmh_pull_volume(self.h, self.frame, out.ctypes.data if copy else None, info, mm, org, sd,
+                                      C.byref(ms))
+        if rc:
+            raise RuntimeError(f"mmh_pull_volume rc={rc}")
+        meta = {"resolution": tuple(info[:3]), "components": info[3], "datahash": info[4], "min": mm[0], "max": mm[1],
+                "origin": tuple(org), "slicedist": tuple(sd), "ms": ms.value}
+        return out, meta
+
+    def pull_mesh(self, isoval: float, copy: bool = True, colours: bool = False):
+        nv = C.c_uint64()
+        nt = C.c_uint64()
+        ms = C.c_double()
+        rc = self.lib.mmh_pull_mesh(self.h, self.frame, float(isoval), C.byref(nv), C.byref(nt), C.byref(ms))
+        if rc:
+            raise RuntimeError(f"mmh_pull_mesh rc={rc}")
+        res = {"nverts": nv.value, "ntris": nt.value, "ms": ms.value}
+        if copy and nv.value:
+            pos = np.empty((nv.value, 3), np.float32)
+            nrm = np.empty((nv.value, 3), np.float32)
+            col = np.empty((nv.value, 3), np.float32) if colours else None
+            rc = self.lib.mmh_copy_mesh(self.h, pos.ctypes.data, nrm.ctypes.data, col.ctypes.data if colours else None)
+            if rc:
+                raise RuntimeError(f"mmh_copy_mesh rc={rc}")
+            res.update(pos=pos, nrm=nrm, col=col)
+        return res
+
+    def mc_tables(self):
+        tri = np.empty((256, 16), np.int32)
+        cnt = np.empty(256, np.uint8)
+        ef = np.empty(256, np.uint32)
+        vo = np.empty((8, 3), np.uint32)
+        ec = np.empty((12, 2), np.uint32)
+        self.lib.mmh_mc_tables(tri.ctypes.data, cnt.ctypes.data, ef.ctypes.data, vo.ctypes.data, ec.ctypes.data)
+        return {"tri": tri, "count": cnt, "edgeflags": ef, "vertoff": vo, "edgeconn": ec}

@@ -1,0 +1,368 @@
+// oracle/ref_harness.cpp -- TEST INFRASTRUCTURE, not product code.
+//
+// Drives MegaMol modules through the reference's real Module / CallerSlot / CalleeSlot / Call
+// machinery, the way MegaMolGraph::add_module / add_call do (core/src/MegaMolGraph.cpp:567-790),
+// and exposes the result over a small C interface that the pytest suite and bench.py load with
+// ctypes.  It is compiled twice by oracle/Makefile.ref:
+//   * oracle/_ref/libmmref.so       P2D = datatools::ParticlesToDensity (plugins/datatools/src/
+//                                   ParticlesToDensity.cpp), ISO = trisoup_gl::volumetrics::IsoSurface
+//                                   (plugins/trisoup_gl/src/volumetrics/IsoSurface.cpp): the UNMODIFIED
+//                                   reference translation units == the parity anchor and CPU baseline.
+//   * oracle/_ref/libmmplug.so      -DMMH_B200: the same graph with our drop-in modules
+//                                   (plugin/b200surf/src) in place of the reference ones.
+// The file includes reference headers but copies no reference code.
+#include <chrono>
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include <omp.h>
+
+#include "geometry_calls/MultiParticleDataCall.h"
+#include "geometry_calls/VolumetricDataCall.h"
+#include "geometry_calls_gl/CallTriMeshDataGL.h"
+#include "mmcore/Call.h"
+#include "mmcore/CalleeSlot.h"
+#include "mmcore/CallerSlot.h"
+#include "mmcore/Module.h"
+#include "mmcore/RootModuleNamespace.h"
+#include "mmcore/factories/CallAutoDescription.h"
+#include "mmcore/param/BoolParam.h"
+#include "mmcore/param/EnumParam.h"
+#include "mmcore/param/FloatParam.h"
+#include "mmcore/param/IntParam.h"
+#include "mmcore/param/ParamSlot.h"
+#include "mmcore/utility/log/Log.h"
+#include "trisoup/volumetrics/MarchingCubeTables.h"
+
+#ifdef MMH_B200
+#include "IsoSurfaceB200.h"
+#include "ParticlesToDensityB200.h"
+using P2DModule = megamol::b200surf::ParticlesToDensityB200;
+using IsoModule = megamol::b200surf::IsoSurfaceB200;
+#else
+#include "ParticlesToDensity.h"
+#include "volumetrics/IsoSurface.h"
+using P2DModule = megamol::datatools::ParticlesToDensity;
+using IsoModule = megamol::trisoup_gl::volumetrics::IsoSurface;
+#endif
+
+using namespace megamol;
+
+extern "C" {
+/** One particle list as a MultiParticleDataCall carries it (enums numerically equal to
+ *  SimpleSphericalParticles::VertexDataType / ColourDataType, SimpleSphericalParticles.h:27-50). */
+struct mmh_list {
+    const void* vtx;
+    const void* col;
+    uint64_t count;
+    int32_t vtx_type;
+    uint32_t vtx_stride;
+    int32_t col_type;
+    uint32_t col_stride;
+    float global_radius;
+    uint8_t global_rgba[4];
+    float irange[2];
+};
+}
+
+namespace {
+
+/** Answers MultiParticleDataCall GetData/GetExtent from caller-supplied arrays (stands in for MMPLDDataSource). */
+class ParticleSource : public core::Module {
+public:
+    ParticleSource() : outSlot("outData", "particles") {
+        outSlot.SetCallback(geocalls::MultiParticleDataCall::ClassName(), "GetData", &ParticleSource::getData);
+        outSlot.SetCallback(geocalls::MultiParticleDataCall::ClassName(), "GetExtent", &ParticleSource::getExtent);
+        MakeSlotAvailable(&outSlot);
+    }
+    ~ParticleSource() override { Release(); }
+    std::vector<mmh_list> lists;
+    float bbox[6] = {0, 0, 0, 1, 1, 1};
+    unsigned frameCount = 1;
+    unsigned frameID = 0;
+    size_t hash = 1;
+
+protected:
+    bool create() override { return true; }
+    void release() override {}
+
+private:
+    bool getExtent(core::Call& c) {
+        auto* m = dynamic_cast<geocalls::MultiParticleDataCall*>(&c);
+        if (!m) return false;
+        m->SetFrameCount(frameCount);
+        m->AccessBoundingBoxes().Clear();
+        m->AccessBoundingBoxes().SetObjectSpaceBBox(bbox[0], bbox[1], bbox[2], bbox[3], bbox[4], bbox[5]);
+        m->AccessBoundingBoxes().SetObjectSpaceClipBox(bbox[0], bbox[1], bbox[2], bbox[3], bbox[4], bbox[5]);
+        m->SetFrameID(frameID);
+        m->SetDataHash(hash);
+        m->SetUnlocker(nullptr);
+        return true;
+    }
+    bool getData(core::Call& c) {
+        auto* m = dynamic_cast<geocalls::MultiParticleDataCall*>(&c);
+        if (!m) return false;
+        m->SetFrameID(frameID);
+        m->SetDataHash(hash);
+        m->SetParticleListCount(static_cast<unsigned>(lists.size()));
+        for (size_t i = 0; i < lists.size(); ++i) {
+            auto& p = m->AccessParticles(static_cast<unsigned>(i));
+            const auto& l = lists[i];
+            p.SetCount(l.count);
+            p.SetGlobalRadius(l.global_radius);
+            p.SetGlobalColour(l.global_rgba[0], l.global_rgba[1], l.global_rgba[2], l.global_rgba[3]);
+            p.SetColourMapIndexValues(l.irange[0], l.irange[1]);
+            p.SetVertexData(static_cast<geocalls::SimpleSphericalParticles::VertexDataType>(l.vtx_type), l.vtx,
+                l.vtx_stride);
+            p.SetColourData(static_cast<geocalls::SimpleSphericalParticles::ColourDataType>(l.col_type), l.col,
+                l.col_stride);
+        }
+        m->SetUnlocker(nullptr);
+        return true;
+    }
+    core::CalleeSlot outSlot;
+};
+
+/** The consumer end: what a renderer would be. */
+class Sink : public core::Module {
+public:
+    Sink() : volSlot("inVolume", "volume"), meshSlot("inMesh", "mesh") {
+        volSlot.SetCompatibleCall<geocalls::VolumetricDataCallDescription>();
+        MakeSlotAvailable(&volSlot);
+        meshSlot.SetCompatibleCall<geocalls_gl::CallTriMeshDataGLDescription>();
+        MakeSlotAvailable(&meshSlot);
+    }
+    ~Sink() override { Release(); }
+    core::CallerSlot volSlot, meshSlot;
+
+protected:
+    bool create() override { return true; }
+    void release() override {}
+};
+
+template<class Desc>
+bool connect(core::Module& from, const char* fromSlot, core::Module& to, const char* toSlot,
+    std::vector<std::unique_ptr<core::Call>>& keep) {
+    auto desc = std::make_shared<Desc>();
+    auto* caller = dynamic_cast<core::CallerSlot*>(from.FindSlot(fromSlot));
+    auto* callee = dynamic_cast<core::CalleeSlot*>(to.FindSlot(toSlot));
+    if (!caller || !callee) return false;
+    core::Call* call = desc->CreateCall();
+    keep.emplace_back(call);
+    if (!callee->ConnectCall(call, desc)) return false;
+    return caller->ConnectCall(call);
+}
+
+struct Harness {
+    std::shared_ptr<core::RootModuleNamespace> root = std::make_shared<core::RootModuleNamespace>();
+    std::shared_ptr<ParticleSource> src = std::make_shared<ParticleSource>();
+    std::shared_ptr<P2DModule> p2d = std::make_shared<P2DModule>();
+    std::shared_ptr<IsoModule> iso = std::make_shared<IsoModule>();
+    std::shared_ptr<Sink> sink = std::make_shared<Sink>();
+    std::vector<std::unique_ptr<core::Call>> calls;
+    const geocalls_gl::CallTriMeshDataGL::Mesh* mesh = nullptr;
+    bool ok = false;
+
+    Harness() {
+        core::utility::log::Log::DefaultLog.SetLevel(core::utility::log::Log::log_level::error);
+        core::utility::log::Log::DefaultLog.SetEchoLevel(core::utility::log::Log::log_level::error);
+        src->setName("src");
+        p2d->setName("p2d");
+        iso->setName("iso");
+        sink->setName("sink");
+        root->AddChild(src);
+        root->AddChild(p2d);
+        root->AddChild(iso);
+        root->AddChild(sink);
+        ok = src->Create() && p2d->Create() && iso->Create() && sink->Create();
+        ok = ok && connect<geocalls::MultiParticleDataCallDescription>(*p2d, "inData", *src, "outData", calls);
+        ok = ok && connect<geocalls::VolumetricDataCallDescription>(*iso, "inData", *p2d, "outData", calls);
+        ok = ok && connect<geocalls::VolumetricDataCallDescription>(*sink, "inVolume", *p2d, "outData", calls);
+        ok = ok && connect<geocalls_gl::CallTriMeshDataGLDescription>(*sink, "inMesh", *iso, "outData", calls);
+    }
+    ~Harness() {
+        // callers first, so that no slot is left pointing at a destroyed call
+        sink->volSlot.ConnectCall(nullptr);
+        sink->meshSlot.ConnectCall(nullptr);
+    }
+};
+
+template<class P, class V>
+bool setParam(core::Module& m, const char* name, V v) {
+    auto* s = dynamic_cast<core::param::ParamSlot*>(m.FindSlot(name));
+    if (!s) return false;
+    auto* p = s->Param<P>();
+    if (!p) return false;
+    p->SetValue(v);
+    return true;
+}
+
+double nowMs() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+} // namespace
+
+extern "C" {
+
+/** 0 = reference modules, 1 = B200 drop-in modules. */
+int mmh_flavour() {
+#ifdef MMH_B200
+    return 1;
+#else
+    return 0;
+#endif
+}
+
+int mmh_threads() { return omp_get_max_threads(); }
+void mmh_set_threads(int n) { omp_set_num_threads(n); }
+
+void* mmh_create() {
+    auto* h = new Harness();
+    if (!h->ok) {
+        delete h;
+        return nullptr;
+    }
+    return h;
+}
+
+void mmh_destroy(void* hv) { delete static_cast<Harness*>(hv); }
+
+/** Replaces the source's particle lists; bumps the data hash so that consumers recompute. */
+int mmh_set_particles(void* hv, int nlists, const mmh_list* lists, const float bbox[6], unsigned frame_id) {
+    auto* h = static_cast<Harness*>(hv);
+    h->src->lists.assign(lists, lists + nlists);
+    std::memcpy(h->src->bbox, bbox, sizeof(float) * 6);
+    h->src->frameID = frame_id;
+    h->src->frameCount = frame_id + 1;
+    ++h->src->hash;
+    return 0;
+}
+
+/** Parameters of ParticlesToDensity by their slot names (ParticlesToDensity.cpp:59-152). */
+int mmh_set_p2d_params(void* hv, int aggregator, int sx, int sy, int sz, int cyclx, int cycly, int cyclz,
+    int normalize, float sigma, int for_surface) {
+    auto* h = static_cast<Harness*>(hv);
+    using namespace core::param;
+    bool ok = setParam<EnumParam>(*h->p2d, "aggregator", aggregator);
+    ok = ok && setParam<IntParam>(*h->p2d, "sizex", sx) && setParam<IntParam>(*h->p2d, "sizey", sy) &&
+         setParam<IntParam>(*h->p2d, "sizez", sz);
+    ok = ok && setParam<BoolParam>(*h->p2d, "cyclX", cyclx != 0) && setParam<BoolParam>(*h->p2d, "cyclY", cycly != 0) &&
+         setParam<BoolParam>(*h->p2d, "cyclZ", cyclz != 0);
+    ok = ok && setParam<BoolParam>(*h->p2d, "normalize", normalize != 0) && setParam<FloatParam>(*h->p2d, "sigma", sigma);
+    ok = ok && setParam<BoolParam>(*h->p2d, "forSurfaceReconstruction", for_surface != 0);
+    return ok ? 0 : -1;
+}
+
+/** Generic parameter setters (for the extra parameters of the B200 modules). */
+int mmh_set_param_int(void* hv, int module, const char* name, int v) {
+    auto* h = static_cast<Harness*>(hv);
+    core::Module& m = module == 0 ? static_cast<core::Module&>(*h->p2d) : static_cast<core::Module&>(*h->iso);
+    if (setParam<core::param::IntParam>(m, name, v)) return 0;
+    if (setParam<core::param::EnumParam>(m, name, v)) return 0;
+    if (setParam<core::param::BoolParam>(m, name, v != 0)) return 0;
+    return -1;
+}
+int mmh_set_param_float(void* hv, int module, const char* name, float v) {
+    auto* h = static_cast<Harness*>(hv);
+    core::Module& m = module == 0 ? static_cast<core::Module&>(*h->p2d) : static_cast<core::Module&>(*h->iso);
+    return setParam<core::param::FloatParam>(m, name, v) ? 0 : -1;
+}
+
+/**
+ * Pulls the volume like a consumer would: VolumetricDataCall GetExtents(0), GetMetadata(2), GetData(1)
+ * (the order IsoSurface.cpp:114-117 uses).  out_vol may be NULL (timing only).
+ * info[0..2] = resolution, info[3] = components, info[4] = data hash; minmax = metadata Min/MaxValues[0].
+ */
+int mmh_pull_volume(void* hv, unsigned frame_id, float* out_vol, uint64_t info[5], double minmax[2],
+    float origin[3], float slicedist[3], double* ms) {
+    auto* h = static_cast<Harness*>(hv);
+    auto* v = h->sink->volSlot.CallAs<geocalls::VolumetricDataCall>();
+    if (!v) return -1;
+    v->SetFrameID(frame_id, true);
+    const double t0 = nowMs();
+    if (!(*v)(geocalls::VolumetricDataCall::IDX_GET_EXTENTS)) return -2;
+    if (!(*v)(geocalls::VolumetricDataCall::IDX_GET_METADATA)) return -3;
+    if (!(*v)(geocalls::VolumetricDataCall::IDX_GET_DATA)) return -4;
+    if (ms) *ms = nowMs() - t0;
+    const auto* md = v->GetMetadata();
+    if (!md) return -5;
+    for (int i = 0; i < 3; ++i) {
+        info[i] = md->Resolution[i];
+        origin[i] = md->Origin[i];
+        slicedist[i] = md->SliceDists[i] ? md->SliceDists[i][0] : 0.0f;
+    }
+    info[3] = md->Components;
+    info[4] = v->DataHash();
+    minmax[0] = md->MinValues ? md->MinValues[0] : 0.0;
+    minmax[1] = md->MaxValues ? md->MaxValues[0] : 0.0;
+    const void* data = v->GetData();
+    if (out_vol) {
+        if (!data) return -6;
+        std::memcpy(out_vol, data, sizeof(float) * md->Resolution[0] * md->Resolution[1] * md->Resolution[2] * md->Components);
+    }
+    return 0;
+}
+
+/** Pulls the mesh like TriSoupRenderer would: CallTriMeshData GetExtent(1) then GetData(0). */
+int mmh_pull_mesh(void* hv, unsigned frame_id, float isoval, uint64_t* nverts, uint64_t* ntris, double* ms) {
+    auto* h = static_cast<Harness*>(hv);
+    if (!setParam<core::param::FloatParam>(*h->iso, "isoval", isoval)) return -1;
+    auto* t = h->sink->meshSlot.CallAs<geocalls_gl::CallTriMeshDataGL>();
+    if (!t) return -2;
+    t->SetFrameID(frame_id, true);
+    const double t0 = nowMs();
+    if (!(*t)(1)) return -3;
+    if (!(*t)(0)) return -4;
+    if (ms) *ms = nowMs() - t0;
+    h->mesh = nullptr;
+    *nverts = 0;
+    *ntris = 0;
+    if (t->Count() >= 1 && t->Objects()) {
+        h->mesh = &t->Objects()[0];
+        *nverts = h->mesh->GetVertexCount();
+        *ntris = h->mesh->GetTriCount();
+    }
+    return 0;
+}
+
+/** Copies the last pulled mesh (float positions / normals / colours, 3 per vertex); NULL outputs are skipped. */
+int mmh_copy_mesh(void* hv, float* pos, float* nrm, float* col) {
+    auto* h = static_cast<Harness*>(hv);
+    if (!h->mesh) return -1;
+    using Mesh = geocalls_gl::CallTriMeshDataGL::Mesh;
+    const size_t n = h->mesh->GetVertexCount();
+    if (pos) {
+        if (h->mesh->GetVertexDataType() != Mesh::DT_FLOAT) return -2;
+        std::memcpy(pos, h->mesh->GetVertexPointerFloat(), n * 3 * sizeof(float));
+    }
+    if (nrm) {
+        if (h->mesh->GetNormalDataType() != Mesh::DT_FLOAT) return -3;
+        std::memcpy(nrm, h->mesh->GetNormalPointerFloat(), n * 3 * sizeof(float));
+    }
+    if (col) {
+        if (h->mesh->GetColourDataType() != Mesh::DT_FLOAT) return -4;
+        std::memcpy(col, h->mesh->GetColourPointerFloat(), n * 3 * sizeof(float));
+    }
+    return 0;
+}
+
+/** The reference's marching-cubes tables (plugins/trisoup/src/volumetrics/MarchingCubeTables.cpp:11-285). */
+void mmh_mc_tables(int32_t tri[256 * 16], uint8_t count[256], uint32_t edgeflags[256], uint32_t vertoff[8 * 3],
+    uint32_t edgeconn[12 * 2]) {
+    using T = trisoup::volumetrics::MarchingCubeTables;
+    for (int i = 0; i < 256; ++i) {
+        for (int j = 0; j < 16; ++j) tri[i * 16 + j] = T::a2iTriangleConnectionTable[i][j];
+        count[i] = T::a2ucTriangleConnectionCount[i];
+        edgeflags[i] = T::aiCubeEdgeFlags[i];
+    }
+    for (int i = 0; i < 8; ++i)
+        for (int j = 0; j < 3; ++j) vertoff[i * 3 + j] = T::a2fVertexOffset[i][j];
+    for (int i = 0; i < 12; ++i)
+        for (int j = 0; j < 2; ++j) edgeconn[i * 2 + j] = T::a2iEdgeConnection[i][j];
+}
+
+} // extern "C"
