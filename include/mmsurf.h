@@ -1,0 +1,159 @@
+/*
+ * mmsurf.h -- C ABI of libmmsurf: the B200-native particle -> density volume -> isosurface path of MegaMol.
+ *
+ * This is the drop-in boundary.  A MegaMol module (plugin/b200surf/src/*.cpp), the pytest suite (ctypes) and
+ * bench.py all go through these entry points; signatures carry plain pointers and sizes only.
+ *
+ * What each entry point replaces in the reference (paths relative to the MegaMol checkout):
+ *   mms_set_grid / mms_set_params   the parameter + bounding-box reads at the top of
+ *                                   datatools::ParticlesToDensity::createVolumeCPU
+ *                                   (plugins/datatools/src/ParticlesToDensity.cpp:395-434, params :78-147)
+ *   mms_push_particles              the per-list accessor set-up and particle loop input
+ *                                   (ParticlesToDensity.cpp:458-486; SimpleSphericalParticles.h:27-50 enums,
+ *                                   :86-178 type -> float conversion)
+ *   mms_compute_density             createVolumeCPU's binning + scatter + reduction + range + normalise
+ *                                   (ParticlesToDensity.cpp:561-626, :669-682)
+ *   mms_get_density / _range        what getDataCallback hands to VolumetricDataCall::SetData / metadata
+ *                                   Min/MaxValues (ParticlesToDensity.cpp:249-295)
+ *   mms_extract_isosurface          trisoup_gl::volumetrics::IsoSurface::buildMesh
+ *                                   (plugins/trisoup_gl/src/volumetrics/IsoSurface.cpp:229-309), with the classic
+ *                                   marching-cubes table of plugins/trisoup/src/volumetrics/MarchingCubeTables.cpp:58
+ *                                   instead of marching tetrahedra, and smooth (gradient) normals
+ *   mms_get_mesh                    what outDataCallback passes to Mesh::SetVertexData (IsoSurface.cpp:171-181):
+ *                                   unindexed triangle soup, 3 floats position + 3 floats normal per vertex
+ *   mms_get_home_voxels, mms_get_cell_tricounts   test hooks for the bit-exact claims (no reference counterpart)
+ *
+ * Conventions: every function returns MMS_OK (0) or a negative error code and never throws or aborts;
+ * mms_last_error() gives the message.  A context is NOT re-entrant; use one per module instance/thread.
+ * All pointers returned by mms_get_* stay owned by the library and valid until the next compute on that context.
+ * There is no CPU fallback: without a CUDA device mms_create fails with MMS_ERR_CUDA.
+ */
+#ifndef MMSURF_H
+#define MMSURF_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMS_OK 0
+#define MMS_ERR_INVALID (-1)     /* bad argument / call order */
+#define MMS_ERR_CUDA (-2)        /* CUDA runtime error (message has the CUDA string) */
+#define MMS_ERR_NOMEM (-3)       /* device or pinned allocation failed */
+#define MMS_ERR_UNSUPPORTED (-4) /* valid MegaMol configuration that this path does not implement (yet) */
+
+/* Numerically equal to geocalls::SimpleSphericalParticles::VertexDataType / ColourDataType. */
+enum mms_vertex_type { MMS_VERT_NONE = 0, MMS_VERT_FLOAT_XYZ = 1, MMS_VERT_FLOAT_XYZR = 2, MMS_VERT_SHORT_XYZ = 3, MMS_VERT_DOUBLE_XYZ = 4 };
+enum mms_colour_type {
+    MMS_COL_NONE = 0, MMS_COL_UINT8_RGB = 1, MMS_COL_UINT8_RGBA = 2, MMS_COL_FLOAT_RGB = 3, MMS_COL_FLOAT_RGBA = 4,
+    MMS_COL_FLOAT_I = 5, MMS_COL_USHORT_RGBA = 6, MMS_COL_DOUBLE_I = 7
+};
+
+/* Density semantics. */
+enum mms_mode {
+    MMS_MODE_P2D_BUMP = 0, /* datatools::ParticlesToDensity: compact bump RBF, support box from the home voxel */
+    MMS_MODE_QS_GAUSS = 1  /* QuickSurf: Gaussian exp2(d^2 w), radial cut-off gausslim*radscale*r, optional colour */
+};
+
+typedef struct mms_ctx mms_ctx;
+
+typedef struct mms_config {
+    int32_t device;   /* CUDA device ordinal */
+    int32_t reserved; /* must be 0 */
+} mms_config;
+
+/* One particle list exactly as a MultiParticleDataCall carries it (borrowed pointers, arbitrary stride;
+ * stride 0 = tightly packed).  The pointers may be pageable host, pinned host or device memory. */
+typedef struct mms_list {
+    const void* vtx;
+    const void* col;
+    uint64_t count;
+    int32_t vtx_type;
+    uint32_t vtx_stride;
+    int32_t col_type;
+    uint32_t col_stride;
+    float global_radius;
+    uint8_t global_rgba[4];
+    float irange[2];
+} mms_list;
+
+/* Node-centred grid: voxel (i,j,k) sits at min + (i,j,k) * extent/(res-1)   (docs/volumes.md:14-16). */
+typedef struct mms_grid {
+    float min[3];      /* object-space bbox Left/Bottom/Back */
+    float extent[3];   /* bbox Width/Height/Depth */
+    int32_t res[3];    /* sizex/sizey/sizez */
+    int32_t cyclic[3]; /* cyclX/cyclY/cyclZ */
+} mms_grid;
+
+typedef struct mms_params {
+    int32_t mode;            /* mms_mode */
+    int32_t aggregator;      /* ParticlesToDensity "aggregator": 0 position, 1 intensity-weighted; 2 -> MMS_ERR_UNSUPPORTED */
+    int32_t normalize;       /* ParticlesToDensity "normalize" */
+    int32_t defer_normalize; /* 1: compute_density leaves the raw sums; caller normalises with mms_normalize (slabs) */
+    float sigma;             /* ParticlesToDensity "sigma" */
+    float radscale;          /* QuickSurf "radiusScale" */
+    float gausslim;          /* QuickSurf quality -> 2.0/2.5/3.0/4.0 */
+    int32_t colour;          /* QS mode: also build the density-weighted RGB volume and coloured mesh */
+    int32_t want_home_voxels;   /* test hook: keep per-particle home voxels */
+    int32_t want_cell_tricounts;/* test hook: keep per-cell triangle counts */
+} mms_params;
+
+typedef struct mms_timings { /* milliseconds, CUDA events on the context's stream, last call of each stage */
+    float h2d, bin, density, normalize, mc, d2h_volume, d2h_mesh;
+} mms_timings;
+
+int mms_create(mms_ctx** out, const mms_config* cfg);
+int mms_destroy(mms_ctx* ctx);
+const char* mms_last_error(const mms_ctx* ctx); /* ctx may be NULL: error of the last failed mms_create */
+
+int mms_set_grid(mms_ctx* ctx, const mms_grid* grid);
+/* z-slab sharding: this context computes density planes [z0, z0+nz) and marching-cubes cell layers
+ * [cell_z0, cell_z0+cell_nz) (cell layer k spans planes k and k+1, so cell_z0 >= z0 and cell_z0+cell_nz < z0+nz).
+ * Give a slab one extra plane on each interior side of its cell range and its gradient normals are identical to
+ * the unsharded ones.  Default (and after every mms_set_grid) = all planes, all cell layers. */
+int mms_set_slab(mms_ctx* ctx, int32_t z0, int32_t nz, int32_t cell_z0, int32_t cell_nz);
+int mms_set_params(mms_ctx* ctx, const mms_params* params);
+
+int mms_clear_particles(mms_ctx* ctx);
+/* Appends lists; data is copied (H2D, asynchronously for pinned memory) unless it already lives on the device. */
+int mms_push_particles(mms_ctx* ctx, int32_t nlists, const mms_list* lists);
+
+int mms_compute_density(mms_ctx* ctx);
+/* Range of the (un-normalised) sums of the last compute_density: the reference's minDens/maxDens. */
+int mms_get_density_range(mms_ctx* ctx, float minmax[2]);
+/* v = (v - mn) * (1/(mx - mn)) on the device volume (ParticlesToDensity.cpp:676-682). */
+int mms_normalize(mms_ctx* ctx, float mn, float mx);
+/* Host copy (library-owned pinned memory) of the slab: nz*res[1]*res[0] floats, x fastest. rgb may be NULL. */
+int mms_get_density(mms_ctx* ctx, const float** host_volume, const float** host_rgb);
+int mms_get_density_device(mms_ctx* ctx, const float** dev_volume, const float** dev_rgb);
+/* Use a caller-supplied volume instead of computing one (IsoSurface fed by another VolumetricDataCall source).
+ * `volume` may be host or device memory, res-shaped for the current slab. */
+int mms_set_density(mms_ctx* ctx, const float* volume);
+
+int mms_extract_isosurface(mms_ctx* ctx, float isovalue);
+/* Triangle soup: nverts = 3 * triangles; pos/nrm/col = 3 floats per vertex (col NULL unless colour mode). */
+int mms_get_mesh(mms_ctx* ctx, uint64_t* nverts, const float** pos, const float** nrm, const float** col);
+int mms_get_mesh_device(mms_ctx* ctx, uint64_t* nverts, const float** pos, const float** nrm, const float** col);
+
+/* Test hooks (host pointers). home: 3 int32 per particle, list-major input order. tricounts: one byte per
+ * cell, x fastest, (res0-1)*(res1-1)*cell_nz entries. */
+int mms_get_home_voxels(mms_ctx* ctx, const int32_t** home, uint64_t* nparticles);
+int mms_get_cell_tricounts(mms_ctx* ctx, const uint8_t** counts, uint64_t* ncells);
+
+int mms_get_timings(mms_ctx* ctx, mms_timings* out);
+int mms_synchronize(mms_ctx* ctx);
+/* Number of kernel launches issued by this context so far (for bench.py's gpu_launches). */
+uint64_t mms_launch_count(const mms_ctx* ctx);
+
+/* Pinned host memory for callers that want zero-staging H2D (e.g. an MMPLD reader). */
+void* mms_alloc_pinned(size_t bytes);
+void mms_free_pinned(void* p);
+
+int mms_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMSURF_H */

@@ -1,0 +1,274 @@
+"""ctypes binding of libmmsurf.so (include/mmsurf.h).  No CPU fallback: if the library or a CUDA device is
+missing, every entry point raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+VERT_NONE, VERT_FLOAT_XYZ, VERT_FLOAT_XYZR, VERT_SHORT_XYZ, VERT_DOUBLE_XYZ = range(5)
+(COL_NONE, COL_UINT8_RGB, COL_UINT8_RGBA, COL_FLOAT_RGB, COL_FLOAT_RGBA, COL_FLOAT_I, COL_USHORT_RGBA,
+ COL_DOUBLE_I) = range(8)
+MODE_P2D_BUMP, MODE_QS_GAUSS = 0, 1
+
+EXPORTS = ["mms_create", "mms_destroy", "mms_last_error", "mms_set_grid", "mms_set_slab", "mms_set_params",
+           "mms_clear_particles", "mms_push_particles", "mms_compute_density", "mms_get_density_range", "mms_normalize",
+           "mms_get_density", "mms_get_density_device", "mms_set_density", "mms_extract_isosurface", "mms_get_mesh",
+           "mms_get_mesh_device", "mms_get_home_voxels", "mms_get_cell_tricounts", "mms_get_timings", "mms_synchronize",
+           "mms_launch_count", "mms_alloc_pinned", "mms_free_pinned", "mms_version"]
+
+
+class MmsError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libmmsurf error {code}: {msg}")
+        self.code = code
+
+
+class MmsConfig(C.Structure):
+    _fields_ = [("device", C.c_int32), ("reserved", C.c_int32)]
+
+
+class MmsList(C.Structure):
+    _fields_ = [("vtx", C.c_void_p), ("col", C.c_void_p), ("count", C.c_uint64), ("vtx_type", C.c_int32),
+                ("vtx_stride", C.c_uint32), ("col_type", C.c_int32), ("col_stride", C.c_uint32),
+                ("global_radius", C.c_float), ("global_rgba", C.c_uint8 * 4), ("irange", C.c_float * 2)]
+
+
+class MmsGrid(C.Structure):
+    _fields_ = [("min", C.c_float * 3), ("extent", C.c_float * 3), ("res", C.c_int32 * 3), ("cyclic", C.c_int32 * 3)]
+
+
+class MmsParams(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("aggregator", C.c_int32), ("normalize", C.c_int32), ("defer_normalize", C.c_int32),
+                ("sigma", C.c_float), ("radscale", C.c_float), ("gausslim", C.c_float), ("colour", C.c_int32),
+                ("want_home_voxels", C.c_int32), ("want_cell_tricounts", C.c_int32)]
+
+
+class MmsTimings(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("h2d", "bin", "density", "normalize", "mc", "d2h_volume", "d2h_mesh")]
+
+
+def lib_path() -> str:
+    return os.path.join(_HERE, "libmmsurf.so")
+
+
+_LIB = None
+
+
+def load_library():
+    """Loads the in-tree libmmsurf.so.  Raises if it has not been built (python -m megamol_b200.build)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    p = lib_path()
+    if not os.path.exists(p):
+        raise FileNotFoundError(f"{p} is missing: build it with `python -m megamol_b200.build` (nvcc, sm_100a); "
+                                "there is no fallback implementation")
+    L = C.CDLL(p)
+    vp = C.c_void_p
+    L.mms_create.argtypes = [C.POINTER(vp), C.POINTER(MmsConfig)]
+    L.mms_destroy.argtypes = [vp]
+    L.mms_last_error.argtypes = [vp]
+    L.mms_last_error.restype = C.c_char_p
+    L.mms_set_grid.argtypes = [vp, C.POINTER(MmsGrid)]
+    L.mms_set_slab.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32]
+    L.mms_set_params.argtypes = [vp, C.POINTER(MmsParams)]
+    L.mms_clear_particles.argtypes = [vp]
+    L.mms_push_particles.argtypes = [vp, C.c_int32, C.POINTER(MmsList)]
+    L.mms_compute_density.argtypes = [vp]
+    L.mms_get_density_range.argtypes = [vp, C.POINTER(C.c_float)]
+    L.mms_normalize.argtypes = [vp, C.c_float, C.c_float]
+    L.mms_get_density.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
+    L.mms_get_density_device.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
+    L.mms_set_density.argtypes = [vp, vp]
+    L.mms_extract_isosurface.argtypes = [vp, C.c_float]
+    L.mms_get_mesh.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    L.mms_get_mesh_device.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    L.mms_get_home_voxels.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_uint64)]
+    L.mms_get_cell_tricounts.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_uint64)]
+    L.mms_get_timings.argtypes = [vp, C.POINTER(MmsTimings)]
+    L.mms_synchronize.argtypes = [vp]
+    L.mms_launch_count.argtypes = [vp]
+    L.mms_launch_count.restype = C.c_uint64
+    L.mms_alloc_pinned.argtypes = [C.c_size_t]
+    L.mms_alloc_pinned.restype = vp
+    L.mms_free_pinned.argtypes = [vp]
+    _LIB = L
+    return L
+
+
+def _np_view(ptr, shape, dtype):
+    n = int(np.prod(shape))
+    if n == 0 or not ptr:
+        return np.empty(shape, dtype)
+    buf = (C.c_char * (n * np.dtype(dtype).itemsize)).from_address(ptr)
+    return np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+
+class Surf:
+    """One libmmsurf context (= one module instance on one GPU)."""
+
+    def __init__(self, device: int = 0):
+        self.L = load_library()
+        self.h = C.c_void_p()
+        cfg = MmsConfig(device, 0)
+        rc = self.L.mms_create(C.byref(self.h), C.byref(cfg))
+        if rc:
+            raise MmsError(rc, self.L.mms_last_error(None).decode())
+        self.res = None
+        self.z0 = 0
+        self.nz = 0
+        self.cell_z0 = 0
+        self.cell_nz = 0
+        self._keep = []
+        self.params = MmsParams(MODE_P2D_BUMP, 0, 1, 0, 1.0, 1.0, 3.0, 0, 0, 0)
+
+    def close(self):
+        if self.h:
+            self.L.mms_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc):
+        if rc:
+            raise MmsError(rc, self.L.mms_last_error(self.h).decode())
+
+    def set_grid(self, bbox_min, bbox_extent, res, cyclic=(True, True, True)):
+        g = MmsGrid()
+        for a in range(3):
+            g.min[a] = float(bbox_min[a])
+            g.extent[a] = float(bbox_extent[a])
+            g.res[a] = int(res[a])
+            g.cyclic[a] = int(bool(cyclic[a]))
+        self._chk(self.L.mms_set_grid(self.h, C.byref(g)))
+        self.res = tuple(int(r) for r in res)
+        self.z0, self.nz = 0, self.res[2]
+        self.cell_z0, self.cell_nz = 0, self.res[2] - 1
+
+    def set_slab(self, z0, nz, cell_z0, cell_nz):
+        self._chk(self.L.mms_set_slab(self.h, int(z0), int(nz), int(cell_z0), int(cell_nz)))
+        self.z0, self.nz, self.cell_z0, self.cell_nz = int(z0), int(nz), int(cell_z0), int(cell_nz)
+
+    def set_params(self, **kw):
+        for k, v in kw.items():
+            if not hasattr(self.params, k):
+                raise KeyError(k)
+            setattr(self.params, k, v)
+        self._chk(self.L.mms_set_params(self.h, C.byref(self.params)))
+
+    def clear_particles(self):
+        self._chk(self.L.mms_clear_particles(self.h))
+        self._keep = []
+
+    def push_particles(self, lists):
+        """lists: dicts {vtx: ndarray | int address (host or device), vtx_type, count, [vtx_stride], [col], [col_type],
+        [col_stride], [global_radius], [global_rgba], [irange]}"""
+        arr = (MmsList * len(lists))()
+        for i, l in enumerate(lists):
+            for key, fld in (("vtx", "vtx"), ("col", "col")):
+                v = l.get(key)
+                if v is None:
+                    continue
+                if isinstance(v, np.ndarray):
+                    v = np.ascontiguousarray(v)
+                    self._keep.append(v)
+                    setattr(arr[i], fld, v.ctypes.data)
+                else:
+                    setattr(arr[i], fld, int(v))
+            arr[i].vtx_type = l["vtx_type"]
+            arr[i].vtx_stride = l.get("vtx_stride", 0)
+            arr[i].count = l["count"]
+            arr[i].col_type = l.get("col_type", COL_NONE)
+            arr[i].col_stride = l.get("col_stride", 0)
+            arr[i].global_radius = l.get("global_radius", 0.5)
+            rgba = l.get("global_rgba", (255, 255, 255, 255))
+            for k in range(4):
+                arr[i].global_rgba[k] = rgba[k]
+            ir = l.get("irange", (0.0, 1.0))
+            arr[i].irange[0], arr[i].irange[1] = ir
+        self._chk(self.L.mms_push_particles(self.h, len(lists), arr))
+
+    def compute_density(self):
+        self._chk(self.L.mms_compute_density(self.h))
+
+    def density_range(self):
+        mm = (C.c_float * 2)()
+        self._chk(self.L.mms_get_density_range(self.h, mm))
+        return float(mm[0]), float(mm[1])
+
+    def normalize(self, mn, mx):
+        self._chk(self.L.mms_normalize(self.h, float(mn), float(mx)))
+
+    def get_density(self, copy=True):
+        p = C.c_void_p()
+        q = C.c_void_p()
+        self._chk(self.L.mms_get_density(self.h, C.byref(p), C.byref(q)))
+        v = _np_view(p.value, (self.nz, self.res[1], self.res[0]), np.float32)
+        return v.copy() if copy else v
+
+    def density_device_ptr(self):
+        p = C.c_void_p()
+        q = C.c_void_p()
+        self._chk(self.L.mms_get_density_device(self.h, C.byref(p), C.byref(q)))
+        return p.value
+
+    def set_density(self, vol):
+        if isinstance(vol, np.ndarray):
+            vol = np.ascontiguousarray(vol, np.float32)
+            self._keep.append(vol)
+            self._chk(self.L.mms_set_density(self.h, vol.ctypes.data))
+            self._chk(self.L.mms_synchronize(self.h))
+        else:
+            self._chk(self.L.mms_set_density(self.h, int(vol)))
+
+    def extract_isosurface(self, iso):
+        self._chk(self.L.mms_extract_isosurface(self.h, float(iso)))
+
+    def get_mesh(self, copy=True, normals=True):
+        n = C.c_uint64()
+        p, q, r = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self._chk(self.L.mms_get_mesh(self.h, C.byref(n), C.byref(p), C.byref(q) if normals else None, C.byref(r)))
+        nt = n.value // 3
+        pos = _np_view(p.value, (nt, 3, 3), np.float32)
+        nrm = _np_view(q.value, (nt, 3, 3), np.float32) if normals else None
+        if copy:
+            pos = pos.copy()
+            nrm = nrm.copy() if nrm is not None else None
+        return pos, nrm
+
+    def mesh_device(self):
+        n = C.c_uint64()
+        p, q, r = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self._chk(self.L.mms_get_mesh_device(self.h, C.byref(n), C.byref(p), C.byref(q), C.byref(r)))
+        return n.value, p.value, q.value
+
+    def home_voxels(self):
+        p = C.c_void_p()
+        n = C.c_uint64()
+        self._chk(self.L.mms_get_home_voxels(self.h, C.byref(p), C.byref(n)))
+        return _np_view(p.value, (n.value, 3), np.int32).copy()
+
+    def cell_tricounts(self):
+        p = C.c_void_p()
+        n = C.c_uint64()
+        self._chk(self.L.mms_get_cell_tricounts(self.h, C.byref(p), C.byref(n)))
+        return _np_view(p.value, (self.cell_nz, self.res[1] - 1, self.res[0] - 1), np.uint8).copy()
+
+    def timings(self):
+        t = MmsTimings()
+        self._chk(self.L.mms_get_timings(self.h, C.byref(t)))
+        return {n: getattr(t, n) for n, _ in MmsTimings._fields_}
+
+    def synchronize(self):
+        self._chk(self.L.mms_synchronize(self.h))
+
+    def launch_count(self):
+        return int(self.L.mms_launch_count(self.h))

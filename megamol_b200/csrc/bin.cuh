@@ -1,0 +1,143 @@
+// bin.cuh -- counting sort of particles into the uniform cell grid.
+//
+//   bin_count_kernel    home voxel (bit-exact vs ParticlesToDensity.cpp:563-568) -> cell id -> histogram
+//   (exclusive scan of the histogram: scan.cuh)
+//   bin_scatter_kernel  recompute the cell id, claim a slot in the cell's segment, write the 16-byte record
+//   cell_order_kernel   canonical order INSIDE each cell (lexicographic on the record's bit pattern), so that
+//                       the density kernel's summation order does not depend on which thread claimed which
+//                       slot: results are bit-reproducible run to run and across slab decompositions.
+// Integer atomics only (histogram / slot claim); no floating-point atomics anywhere.
+#pragma once
+#include "common.cuh"
+
+namespace mms {
+
+struct Binned {
+    float4 p;   // x y z r
+    int X, Y, Z; // home voxel (un-wrapped, as the reference computes it)
+    int cell;   // linear cell id, -1 = does not contribute to this slab
+};
+
+__device__ __forceinline__ bool axisReaches(int X, int f, int lo, int hi, int s, bool cyc) {
+    // does the support box [X-f, X+f] (periodic images if cyc) touch voxel range [lo, hi]?
+    if (!cyc) return X + f >= lo && X - f <= hi;
+    if (2 * f + 1 >= s) return true;
+    const int xw = floorMod(X, s);
+    const int a = xw - f, b = xw + f;
+    return (b >= lo && a <= hi) || (b - s >= lo && a - s <= hi) || (b + s >= lo && a + s <= hi);
+}
+
+__device__ __forceinline__ Binned binParticle(const Geo& g, const ListDev& l, unsigned long long j) {
+    Binned q;
+    q.p = fetchParticle(l, j);
+    q.X = homeVoxel(q.p.x, g.mn[0], g.sd[0]);
+    q.Y = homeVoxel(q.p.y, g.mn[1], g.sd[1]);
+    q.Z = homeVoxel(q.p.z, g.mn[2], g.sd[2]);
+    q.cell = -1;
+    const float r = q.p.w;
+    if (!(r > 0.0f) || !isfinite(r)) return q; // rad == 0 early-out (:523); r < 0 or NaN never contributes
+    if (!isfinite(q.p.x) || !isfinite(q.p.y) || !isfinite(q.p.z)) return q;
+    int fx, fy, fz;
+    if (g.mode == 0) {
+        fx = filterSize(r, g.sd[0]), fy = filterSize(r, g.sd[1]), fz = filterSize(r, g.sd[2]);
+    } else {
+        const float cut = g.gausslim * g.radscale * r;
+        fx = filterSize(cut, g.sd[0]) + 1, fy = filterSize(cut, g.sd[1]) + 1, fz = filterSize(cut, g.sd[2]) + 1;
+    }
+    if (!axisReaches(q.X, fx, 0, g.s[0] - 1, g.s[0], g.cyc[0])) return q;
+    if (!axisReaches(q.Y, fy, 0, g.s[1] - 1, g.s[1], g.cyc[1])) return q;
+    if (!axisReaches(q.Z, fz, g.z0, g.z0 + g.nz - 1, g.s[2], g.cyc[2])) return q;
+    const int xw = g.cyc[0] ? floorMod(q.X, g.s[0]) : min(max(q.X, 0), g.s[0] - 1);
+    const int yw = g.cyc[1] ? floorMod(q.Y, g.s[1]) : min(max(q.Y, 0), g.s[1] - 1);
+    const int zw = g.cyc[2] ? floorMod(q.Z, g.s[2]) : min(max(q.Z, 0), g.s[2] - 1);
+    q.cell = (xw >> g.cshift) + g.nc[0] * ((yw >> g.cshift) + g.nc[1] * (zw >> g.cshift));
+    return q;
+}
+
+__global__ void __launch_bounds__(256) bin_count_kernel(Geo g, ListDev l, unsigned* __restrict__ cellCount,
+    DevState* __restrict__ st, int* __restrict__ homeOut) {
+    const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
+    float rmax = 0.0f;
+    unsigned kept = 0;
+    for (unsigned long long j = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; j < l.count; j += stride) {
+        const Binned q = binParticle(g, l, j);
+        if (homeOut) {
+            int* h = homeOut + 3 * (l.base + j);
+            h[0] = q.X, h[1] = q.Y, h[2] = q.Z;
+        }
+        if (q.cell >= 0) {
+            atomicAdd(&cellCount[q.cell], 1u);
+            rmax = fmaxf(rmax, q.p.w);
+            ++kept;
+        }
+    }
+    rmax = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(rmax))); // positive floats order like uints
+    kept = __reduce_add_sync(0xffffffffu, kept);
+    if ((threadIdx.x & 31) == 0 && kept) {
+        atomicMax(&st->rmaxBits, __float_as_uint(rmax));
+        atomicAdd(&st->kept, kept);
+    }
+}
+
+/** aux: 0 floats (plain), 1 float (aggregator 1: intensity) or 4 floats (QuickSurf colour) per record. */
+__global__ void __launch_bounds__(256) bin_scatter_kernel(Geo g, ListDev l, unsigned* __restrict__ cursor,
+    float4* __restrict__ recs, float* __restrict__ aux, int auxN) {
+    const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
+    for (unsigned long long j = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; j < l.count; j += stride) {
+        const Binned q = binParticle(g, l, j);
+        if (q.cell < 0) continue;
+        const unsigned slot = atomicAdd(&cursor[q.cell], 1u);
+        recs[slot] = q.p;
+        if (auxN == 1) {
+            aux[slot] = fetchColourRaw(l, j).x; // iAcc->Get_f (ParticlesToDensity.cpp:483,515)
+        } else if (auxN == 4) {
+            reinterpret_cast<float4*>(aux)[slot] = quicksurfColour(l, fetchColourRaw(l, j));
+        }
+    }
+}
+
+__device__ __forceinline__ bool recLess(const float4& a, const float* aa, const float4& b, const float* ab, int auxN) {
+    const unsigned ka[4] = {__float_as_uint(a.x), __float_as_uint(a.y), __float_as_uint(a.z), __float_as_uint(a.w)};
+    const unsigned kb[4] = {__float_as_uint(b.x), __float_as_uint(b.y), __float_as_uint(b.z), __float_as_uint(b.w)};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        if (ka[i] != kb[i]) return ka[i] < kb[i];
+    for (int i = 0; i < auxN; ++i) {
+        const unsigned x = __float_as_uint(aa[i]), y = __float_as_uint(ab[i]);
+        if (x != y) return x < y;
+    }
+    return false;
+}
+
+/**
+ * One thread per sorted slot: rank of my record among the records of my cell (ties: slot order, the tied
+ * records are bit-identical so their order cannot change any sum), written to the second buffer.
+ */
+__global__ void __launch_bounds__(256) cell_order_kernel(Geo g, const unsigned* __restrict__ cellStart,
+    const float4* __restrict__ in, const float* __restrict__ auxIn, float4* __restrict__ out, float* __restrict__ auxOut,
+    int auxN, const DevState* __restrict__ st) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= st->kept) return;
+    const float4 me = in[i];
+    // my cell (records only exist for contributing particles, so the clamped/wrapped home is in range)
+    const int X = homeVoxel(me.x, g.mn[0], g.sd[0]), Y = homeVoxel(me.y, g.mn[1], g.sd[1]), Z = homeVoxel(me.z, g.mn[2], g.sd[2]);
+    const int xw = g.cyc[0] ? floorMod(X, g.s[0]) : min(max(X, 0), g.s[0] - 1);
+    const int yw = g.cyc[1] ? floorMod(Y, g.s[1]) : min(max(Y, 0), g.s[1] - 1);
+    const int zw = g.cyc[2] ? floorMod(Z, g.s[2]) : min(max(Z, 0), g.s[2] - 1);
+    const int cell = (xw >> g.cshift) + g.nc[0] * ((yw >> g.cshift) + g.nc[1] * (zw >> g.cshift));
+    const unsigned b = cellStart[cell], e = cellStart[cell + 1];
+    float myAux[4] = {0, 0, 0, 0};
+    for (int k = 0; k < auxN; ++k) myAux[k] = auxIn[static_cast<size_t>(i) * auxN + k];
+    unsigned rank = 0;
+    for (unsigned k = b; k < e; ++k) {
+        if (k == i) continue;
+        const float4 o = in[k];
+        float oa[4] = {0, 0, 0, 0};
+        for (int q = 0; q < auxN; ++q) oa[q] = auxIn[static_cast<size_t>(k) * auxN + q];
+        if (recLess(o, oa, me, myAux, auxN) || (!recLess(me, myAux, o, oa, auxN) && k < i)) ++rank;
+    }
+    out[b + rank] = me;
+    for (int k = 0; k < auxN; ++k) auxOut[static_cast<size_t>(b + rank) * auxN + k] = myAux[k];
+}
+
+} // namespace mms

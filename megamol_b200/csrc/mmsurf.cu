@@ -1,0 +1,711 @@
+// mmsurf.cu -- context management and the C ABI of libmmsurf (see include/mmsurf.h).
+// Built for sm_100a only; there is no CPU path in this library.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/mmsurf.h"
+#include "common.cuh"
+#include "scan.cuh"
+#include "bin.cuh"
+#include "density.cuh"
+#include "mc.cuh"
+
+using namespace mms;
+
+namespace {
+
+std::string g_createError;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    bool ensure(size_t bytes) {
+        if (bytes <= cap) return true;
+        if (p) cudaFree(p);
+        p = nullptr;
+        size_t want = std::max(bytes, cap + cap / 2);
+        if (cudaMalloc(&p, want) != cudaSuccess) {
+            cudaGetLastError();
+            want = bytes;
+            if (cudaMalloc(&p, want) != cudaSuccess) {
+                cudaGetLastError();
+                cap = 0;
+                p = nullptr;
+                return false;
+            }
+        }
+        cap = want;
+        return true;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template<class T> T* as() { return static_cast<T*>(p); }
+};
+
+struct PinBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    bool ensure(size_t bytes) {
+        if (bytes <= cap) return true;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        const size_t want = std::max(bytes, cap + cap / 2);
+        if (cudaHostAlloc(&p, want, cudaHostAllocDefault) != cudaSuccess) {
+            cudaGetLastError();
+            cap = 0;
+            p = nullptr;
+            return false;
+        }
+        cap = want;
+        return true;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template<class T> T* as() { return static_cast<T*>(p); }
+};
+
+enum Ev { EV_H2D0, EV_H2D1, EV_BIN0, EV_BIN1, EV_DEN1, EV_NRM0, EV_NRM1, EV_MC0, EV_MC1, EV_DV0, EV_DV1, EV_DM0, EV_DM1, EV_COUNT };
+
+} // namespace
+
+struct mms_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    mms_grid grid{};
+    bool haveGrid = false;
+    int z0 = 0, nz = 0, cellZ0 = 0, cellNz = 0;
+    mms_params params{};
+    std::vector<ListDev> lists;
+    std::vector<void*> listBufs; // device copies we own
+    unsigned long long nparticles = 0;
+    bool haveDensity = false, haveMesh = false, normalized = false;
+    unsigned long long ntris = 0;
+    unsigned long long launches = 0;
+
+    DevBuf cellCount, cellStart, cursor, tileSums, recsA, recsB, auxA, auxB, vol, rgb, segCount, segOffset, meshPos, meshNrm,
+        meshCol, triCount, home, dstate;
+    PinBuf hState, hVol, hRgb, hPos, hNrm, hCol, hHome, hTri;
+    cudaEvent_t ev[EV_COUNT]{};
+    bool evSet[EV_COUNT]{};
+    int smCount = 148;
+
+    int fail(int code, const char* fmt, ...) {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof(buf), fmt, ap);
+        va_end(ap);
+        err = buf;
+        return code;
+    }
+    void rec(Ev e) {
+        cudaEventRecord(ev[e], stream);
+        evSet[e] = true;
+    }
+};
+
+namespace {
+
+struct DeviceGuard { // the host application may have another device current (SURVEY 8b threading)
+    int prev = 0;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+    }
+    ~DeviceGuard() {
+        int cur = 0;
+        cudaGetDevice(&cur);
+        if (cur != prev) cudaSetDevice(prev);
+    }
+};
+
+#define MMS_CUDA(ctx, call)                                                                      \
+    do {                                                                                         \
+        cudaError_t e_ = (call);                                                                 \
+        if (e_ != cudaSuccess) return (ctx)->fail(MMS_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+const unsigned kVertSize[5] = {0, 12, 16, 6, 24};
+const unsigned kColSize[8] = {0, 3, 4, 12, 16, 4, 8, 8};
+
+bool isDevicePointer(const void* p) {
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+int alignOf(const void* p, unsigned stride, int want) {
+    const uintptr_t u = reinterpret_cast<uintptr_t>(p);
+    for (int a = want; a > 1; a >>= 1)
+        if (u % a == 0 && stride % a == 0) return a;
+    return 1;
+}
+
+Geo makeGeo(const mms_ctx* c) {
+    Geo g{};
+    for (int a = 0; a < 3; ++a) {
+        g.mn[a] = c->grid.min[a];
+        g.s[a] = c->grid.res[a];
+        // sliceDist = rangeOS / static_cast<float>(s - 1)  (ParticlesToDensity.cpp:430-432), fp32 division on the host
+        volatile float range = c->grid.extent[a];
+        volatile float denom = static_cast<float>(c->grid.res[a] - 1);
+        volatile float sd = range / denom;
+        g.sd[a] = sd;
+        g.cyc[a] = c->grid.cyclic[a] != 0;
+    }
+    g.z0 = c->z0, g.nz = c->nz;
+    g.cshift = 2;
+    for (int a = 0; a < 3; ++a) g.nc[a] = (g.s[a] + (1 << g.cshift) - 1) >> g.cshift;
+    g.sigma = c->params.sigma;
+    g.agg = c->params.aggregator;
+    g.mode = c->params.mode;
+    g.radscale = c->params.radscale;
+    g.gausslim = c->params.gausslim;
+    g.colour = c->params.colour;
+    return g;
+}
+
+int gridFor(unsigned long long n, int threads, int cap) {
+    unsigned long long b = (n + threads - 1) / threads;
+    if (b < 1) b = 1;
+    return static_cast<int>(std::min<unsigned long long>(b, static_cast<unsigned long long>(cap)));
+}
+
+__global__ void init_state_kernel(DevState* st) {
+    st->rmaxBits = 0u;
+    st->kept = 0u;
+    st->minKey = 0xffffffffu;
+    st->maxKey = 0u;
+    st->totalTris = 0ull;
+    st->pad[0] = 0u; // error flag
+    st->pad[1] = 0u;
+}
+
+__global__ void normalize_state_kernel(float* __restrict__ vol, size_t n, const DevState* __restrict__ st) {
+    const float mn = keyFloat(st->minKey), mx = keyFloat(st->maxKey);
+    const float rcp = __fdiv_rn(1.0f, __fsub_rn(mx, mn)); // 1.0f / (maxDens - minDens) (:677)
+    const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+        vol[i] = __fmul_rn(__fsub_rn(vol[i], mn), rcp);
+}
+
+} // namespace
+
+extern "C" {
+
+int mms_version(void) { return 1; }
+
+const char* mms_last_error(const mms_ctx* ctx) { return ctx ? ctx->err.c_str() : g_createError.c_str(); }
+
+int mms_create(mms_ctx** out, const mms_config* cfg) {
+    if (!out) return MMS_ERR_INVALID;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_createError = std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                        " (libmmsurf has no CPU fallback)";
+        cudaGetLastError();
+        return MMS_ERR_CUDA;
+    }
+    const int dev = cfg ? cfg->device : 0;
+    if (dev < 0 || dev >= ndev) {
+        g_createError = "device ordinal out of range";
+        return MMS_ERR_INVALID;
+    }
+    DeviceGuard guard(dev);
+    cudaDeviceProp prop{};
+    cudaGetDeviceProperties(&prop, dev);
+    if (prop.major < 10) {
+        g_createError = std::string("device '") + prop.name + "' is not sm_100+; libmmsurf ships sm_100a code only";
+        return MMS_ERR_CUDA;
+    }
+    auto* c = new mms_ctx();
+    c->device = dev;
+    c->smCount = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        g_createError = "cudaStreamCreate failed";
+        delete c;
+        return MMS_ERR_CUDA;
+    }
+    for (auto& ev : c->ev) cudaEventCreate(&ev);
+    c->params.mode = MMS_MODE_P2D_BUMP;
+    c->params.sigma = 1.0f;
+    c->params.normalize = 1;
+    c->params.radscale = 1.0f;
+    c->params.gausslim = 3.0f;
+    cudaFuncSetAttribute(density_tile_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileShared));
+    cudaFuncSetAttribute(density_tile_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileShared));
+    cudaFuncSetAttribute(mc_emit_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(McEmitShared));
+    if (!c->dstate.ensure(sizeof(DevState)) || !c->hState.ensure(sizeof(DevState))) {
+        g_createError = "allocation of the state block failed";
+        delete c;
+        return MMS_ERR_NOMEM;
+    }
+    if (cudaGetLastError() != cudaSuccess) {
+        g_createError = "kernel attribute set-up failed (is this an sm_100a build on an sm_100 device?)";
+        delete c;
+        return MMS_ERR_CUDA;
+    }
+    *out = c;
+    return MMS_OK;
+}
+
+int mms_clear_particles(mms_ctx* c) {
+    if (!c) return MMS_ERR_INVALID;
+    DeviceGuard guard(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (void* p : c->listBufs) cudaFree(p);
+    c->listBufs.clear();
+    c->lists.clear();
+    c->nparticles = 0;
+    return MMS_OK;
+}
+
+int mms_destroy(mms_ctx* c) {
+    if (!c) return MMS_ERR_INVALID;
+    {
+        DeviceGuard guard(c->device);
+        mms_clear_particles(c);
+        for (DevBuf* b : {&c->cellCount, &c->cellStart, &c->cursor, &c->tileSums, &c->recsA, &c->recsB, &c->auxA, &c->auxB, &c->vol,
+                 &c->rgb, &c->segCount, &c->segOffset, &c->meshPos, &c->meshNrm, &c->meshCol, &c->triCount, &c->home, &c->dstate})
+            b->release();
+        for (PinBuf* b : {&c->hState, &c->hVol, &c->hRgb, &c->hPos, &c->hNrm, &c->hCol, &c->hHome, &c->hTri}) b->release();
+        for (auto& ev : c->ev) cudaEventDestroy(ev);
+        cudaStreamDestroy(c->stream);
+    }
+    delete c;
+    return MMS_OK;
+}
+
+int mms_set_grid(mms_ctx* c, const mms_grid* g) {
+    if (!c || !g) return MMS_ERR_INVALID;
+    for (int a = 0; a < 3; ++a) {
+        if (g->res[a] < 2) return c->fail(MMS_ERR_INVALID, "resolution must be >= 2 per axis (sliceDist = extent/(res-1))");
+        if (!(g->extent[a] > 0.0f) || !std::isfinite(g->extent[a]) || !std::isfinite(g->min[a]))
+            return c->fail(MMS_ERR_INVALID, "bounding box extent must be positive and finite");
+    }
+    if (static_cast<unsigned long long>(g->res[0]) * g->res[1] * g->res[2] >= (1ull << 32))
+        return c->fail(MMS_ERR_UNSUPPORTED, "volumes of 2^32 voxels or more are not supported");
+    c->grid = *g;
+    c->haveGrid = true;
+    c->z0 = 0, c->nz = g->res[2];
+    c->cellZ0 = 0, c->cellNz = g->res[2] - 1;
+    c->haveDensity = c->haveMesh = false;
+    return MMS_OK;
+}
+
+int mms_set_slab(mms_ctx* c, int32_t z0, int32_t nz, int32_t cell_z0, int32_t cell_nz) {
+    if (!c || !c->haveGrid) return MMS_ERR_INVALID;
+    if (z0 < 0 || nz < 1 || z0 + nz > c->grid.res[2]) return c->fail(MMS_ERR_INVALID, "slab planes out of range");
+    if (cell_nz < 0 || cell_z0 < z0 || (cell_nz > 0 && cell_z0 + cell_nz + 1 > z0 + nz))
+        return c->fail(MMS_ERR_INVALID, "cell layers must lie inside the slab's planes");
+    c->z0 = z0, c->nz = nz, c->cellZ0 = cell_z0, c->cellNz = cell_nz;
+    c->haveDensity = c->haveMesh = false;
+    return MMS_OK;
+}
+
+int mms_set_params(mms_ctx* c, const mms_params* p) {
+    if (!c || !p) return MMS_ERR_INVALID;
+    if (p->mode != MMS_MODE_P2D_BUMP && p->mode != MMS_MODE_QS_GAUSS) return c->fail(MMS_ERR_INVALID, "unknown mode %d", p->mode);
+    if (p->mode == MMS_MODE_P2D_BUMP) {
+        if (p->aggregator == 2)
+            return c->fail(MMS_ERR_UNSUPPORTED, "aggregator 2 (IVecToSingleCell_Volume, vector field) is not implemented on this path");
+        if (p->aggregator != 0 && p->aggregator != 1) return c->fail(MMS_ERR_INVALID, "unknown aggregator %d", p->aggregator);
+        if (!(p->sigma > 0.0f)) return c->fail(MMS_ERR_INVALID, "sigma must be > 0");
+    } else {
+        if (!(p->radscale > 0.0f) || !(p->gausslim > 0.0f)) return c->fail(MMS_ERR_INVALID, "radscale and gausslim must be > 0");
+        if (p->colour) return c->fail(MMS_ERR_UNSUPPORTED, "QuickSurf colour volume is not implemented yet");
+    }
+    c->params = *p;
+    return MMS_OK;
+}
+
+int mms_push_particles(mms_ctx* c, int32_t nlists, const mms_list* lists) {
+    if (!c || nlists < 0 || (nlists > 0 && !lists)) return MMS_ERR_INVALID;
+    DeviceGuard guard(c->device);
+    if (c->lists.size() + nlists > static_cast<size_t>(kMaxLists)) return c->fail(MMS_ERR_UNSUPPORTED, "more than %d particle lists", kMaxLists);
+    c->rec(EV_H2D0);
+    for (int i = 0; i < nlists; ++i) {
+        const mms_list& l = lists[i];
+        if (l.vtx_type == MMS_VERT_NONE || l.count == 0) continue; // lists with VERTDATA_NONE are skipped (:464-466)
+        if (l.vtx_type < 0 || l.vtx_type > 4 || l.col_type < 0 || l.col_type > 7) return c->fail(MMS_ERR_INVALID, "bad data type in list %d", i);
+        if (!l.vtx) return c->fail(MMS_ERR_INVALID, "list %d has no vertex pointer", i);
+        ListDev d{};
+        d.count = l.count;
+        d.base = c->nparticles;
+        d.vtype = l.vtx_type;
+        d.vstride = l.vtx_stride ? l.vtx_stride : kVertSize[l.vtx_type];
+        d.ctype = l.col ? l.col_type : MMS_COL_NONE;
+        d.cstride = l.col_stride ? l.col_stride : kColSize[d.ctype];
+        d.grad = l.global_radius;
+        for (int k = 0; k < 4; ++k) d.gcol[k] = static_cast<float>(l.global_rgba[k]) / 255.0f;
+        d.irange[0] = l.irange[0], d.irange[1] = l.irange[1];
+        const size_t vbytes = (l.count - 1) * static_cast<size_t>(d.vstride) + kVertSize[l.vtx_type];
+        const size_t cbytes = d.ctype ? (l.count - 1) * static_cast<size_t>(d.cstride) + kColSize[d.ctype] : 0;
+        const char* hv = static_cast<const char*>(l.vtx);
+        const char* hc = static_cast<const char*>(l.col);
+        if (isDevicePointer(l.vtx)) {
+            d.vtx = hv;
+            d.col = hc; // a device-resident list carries device colour pointers too
+        } else {
+            // one copy for interleaved vertex+colour (the MMPLD layout, MMPLDDataSource.cpp:160,197-198), else two
+            const char* lo = hv;
+            const char* hi = hv + vbytes;
+            const uintptr_t uv = reinterpret_cast<uintptr_t>(hv), uc = reinterpret_cast<uintptr_t>(hc);
+            const bool interleaved = d.ctype && uc + d.vstride >= uv && uc < uv + vbytes + d.vstride;
+            if (interleaved) lo = std::min(lo, hc), hi = std::max(hi, hc + cbytes);
+            void* dv = nullptr;
+            // keep the source's alignment modulo 16 so that aligned host data stays aligned on the device
+            const size_t mis = reinterpret_cast<uintptr_t>(lo) & 15u;
+            if (cudaMalloc(&dv, static_cast<size_t>(hi - lo) + mis + 16) != cudaSuccess) {
+                cudaGetLastError();
+                return c->fail(MMS_ERR_NOMEM, "device allocation of %zu bytes for list %d failed", static_cast<size_t>(hi - lo), i);
+            }
+            c->listBufs.push_back(dv);
+            char* dbase = static_cast<char*>(dv) + mis;
+            MMS_CUDA(c, cudaMemcpyAsync(dbase, lo, static_cast<size_t>(hi - lo), cudaMemcpyHostToDevice, c->stream));
+            d.vtx = dbase + (hv - lo);
+            if (d.ctype) {
+                if (interleaved) {
+                    d.col = dbase + (hc - lo);
+                } else {
+                    void* dc = nullptr;
+                    if (cudaMalloc(&dc, cbytes + 16) != cudaSuccess) {
+                        cudaGetLastError();
+                        return c->fail(MMS_ERR_NOMEM, "device allocation of %zu bytes for colours of list %d failed", cbytes, i);
+                    }
+                    c->listBufs.push_back(dc);
+                    MMS_CUDA(c, cudaMemcpyAsync(dc, hc, cbytes, cudaMemcpyHostToDevice, c->stream));
+                    d.col = static_cast<const char*>(dc);
+                }
+            }
+        }
+        d.valign = alignOf(d.vtx, d.vstride, l.vtx_type == MMS_VERT_DOUBLE_XYZ ? 8 : (l.vtx_type == MMS_VERT_FLOAT_XYZR ? 16 : 4));
+        if (l.vtx_type == MMS_VERT_DOUBLE_XYZ && d.valign < 8) d.valign = 1;
+        if ((l.vtx_type == MMS_VERT_FLOAT_XYZ || l.vtx_type == MMS_VERT_FLOAT_XYZR) && d.valign < 4) d.valign = 1;
+        d.calign = d.ctype ? alignOf(d.col, d.cstride, d.ctype == MMS_COL_DOUBLE_I ? 8 : 4) : 4;
+        if (d.ctype == MMS_COL_DOUBLE_I && d.calign < 8) d.calign = 1;
+        if (d.calign < 4) d.calign = 1;
+        c->lists.push_back(d);
+        c->nparticles += l.count;
+    }
+    c->rec(EV_H2D1);
+    c->haveDensity = c->haveMesh = false;
+    return MMS_OK;
+}
+
+int mms_compute_density(mms_ctx* c) {
+    if (!c || !c->haveGrid) return c ? c->fail(MMS_ERR_INVALID, "mms_set_grid has not been called") : MMS_ERR_INVALID;
+    if (c->nparticles >= (1ull << 32) - 1) return c->fail(MMS_ERR_UNSUPPORTED, "2^32 or more particles per context");
+    DeviceGuard guard(c->device);
+    const Geo g = makeGeo(c);
+    const size_t ncells = static_cast<size_t>(g.nc[0]) * g.nc[1] * g.nc[2];
+    const size_t nvox = static_cast<size_t>(g.s[0]) * g.s[1] * g.nz;
+    const int auxN = (g.mode == 0 && g.agg == 1) ? 1 : 0;
+    const size_t n = static_cast<size_t>(c->nparticles);
+    const unsigned ntiles = static_cast<unsigned>((ncells + kScanTile - 1) / kScanTile);
+    if (!c->cellCount.ensure(ncells * 4) || !c->cellStart.ensure((ncells + 1) * 4) || !c->cursor.ensure(ncells * 4) ||
+        !c->tileSums.ensure(std::max<size_t>(ntiles, 1) * 4) || !c->recsA.ensure(std::max<size_t>(n, 1) * 16) ||
+        !c->recsB.ensure(std::max<size_t>(n, 1) * 16) || !c->vol.ensure(nvox * 4))
+        return c->fail(MMS_ERR_NOMEM, "device allocation failed (cells %zu, particles %zu, voxels %zu)", ncells, n, nvox);
+    if (auxN && (!c->auxA.ensure(std::max<size_t>(n, 1) * 4 * auxN) || !c->auxB.ensure(std::max<size_t>(n, 1) * 4 * auxN)))
+        return c->fail(MMS_ERR_NOMEM, "device allocation failed (aux)");
+    int* homeOut = nullptr;
+    if (c->params.want_home_voxels) {
+        if (!c->home.ensure(std::max<size_t>(n, 1) * 12)) return c->fail(MMS_ERR_NOMEM, "device allocation failed (home voxels)");
+        homeOut = c->home.as<int>();
+    }
+    cudaStream_t st = c->stream;
+    c->rec(EV_BIN0);
+    init_state_kernel<<<1, 1, 0, st>>>(c->dstate.as<DevState>());
+    ++c->launches;
+    MMS_CUDA(c, cudaMemsetAsync(c->cellCount.p, 0, ncells * 4, st));
+    const int cap = c->smCount * 16;
+    for (const ListDev& l : c->lists) {
+        bin_count_kernel<<<gridFor(l.count, 256, cap), 256, 0, st>>>(g, l, c->cellCount.as<unsigned>(), c->dstate.as<DevState>(), homeOut);
+        ++c->launches;
+    }
+    exclusiveScan(c->cellCount.as<unsigned>(), c->cellStart.as<unsigned>(), c->cursor.as<unsigned>(), c->tileSums.as<unsigned>(),
+        static_cast<unsigned>(ncells), nullptr, st, c->launches);
+    for (const ListDev& l : c->lists) {
+        bin_scatter_kernel<<<gridFor(l.count, 256, cap), 256, 0, st>>>(g, l, c->cursor.as<unsigned>(), c->recsA.as<float4>(),
+            c->auxA.as<float>(), auxN);
+        ++c->launches;
+    }
+    if (n > 0) {
+        // upper bound n threads; slots >= kept are never claimed, the kernel reads the segment table only
+        cell_order_kernel<<<gridFor(n, 256, 1 << 30), 256, 0, st>>>(g, c->cellStart.as<unsigned>(), c->recsA.as<float4>(), c->auxA.as<float>(),
+            c->recsB.as<float4>(), c->auxB.as<float>(), auxN, c->dstate.as<DevState>());
+        ++c->launches;
+    }
+    c->rec(EV_BIN1);
+    dim3 grid((g.s[0] + BTX - 1) / BTX, (g.s[1] + BTY - 1) / BTY, (g.nz + BTZ - 1) / BTZ);
+    if (g.mode == 0)
+        density_tile_kernel<0, false><<<grid, DT_THREADS, sizeof(TileShared), st>>>(g, c->dstate.as<DevState>(), c->recsB.as<float4>(),
+            c->auxB.as<float>(), auxN, c->cellStart.as<unsigned>(), c->vol.as<float>(), nullptr);
+    else
+        density_tile_kernel<1, false><<<grid, DT_THREADS, sizeof(TileShared), st>>>(g, c->dstate.as<DevState>(), c->recsB.as<float4>(),
+            c->auxB.as<float>(), auxN, c->cellStart.as<unsigned>(), c->vol.as<float>(), nullptr);
+    ++c->launches;
+    c->rec(EV_DEN1);
+    c->normalized = false;
+    if (c->params.mode == MMS_MODE_P2D_BUMP && c->params.normalize && !c->params.defer_normalize) {
+        c->rec(EV_NRM0);
+        normalize_state_kernel<<<c->smCount * 8, 256, 0, st>>>(c->vol.as<float>(), nvox, c->dstate.as<DevState>());
+        ++c->launches;
+        c->rec(EV_NRM1);
+        c->normalized = true;
+    }
+    MMS_CUDA(c, cudaMemcpyAsync(c->hState.p, c->dstate.p, sizeof(DevState), cudaMemcpyDeviceToHost, st));
+    MMS_CUDA(c, cudaGetLastError());
+    c->haveDensity = true;
+    c->haveMesh = false;
+    return MMS_OK;
+}
+
+static int checkDeviceError(mms_ctx* c) {
+    MMS_CUDA(c, cudaStreamSynchronize(c->stream));
+    const DevState* hs = c->hState.as<DevState>();
+    if (hs->pad[0] != 0)
+        return c->fail(MMS_ERR_UNSUPPORTED, "support radius too large for the tile kernel's neighbourhood list (reach > %d cells per axis)", DT_MAXAXIS);
+    return MMS_OK;
+}
+
+int mms_get_density_range(mms_ctx* c, float minmax[2]) {
+    if (!c || !minmax) return MMS_ERR_INVALID;
+    if (!c->haveDensity) return c->fail(MMS_ERR_INVALID, "no density has been computed");
+    DeviceGuard guard(c->device);
+    if (int rc = checkDeviceError(c)) return rc;
+    const DevState* hs = c->hState.as<DevState>();
+    minmax[0] = keyFloat(hs->minKey);
+    minmax[1] = keyFloat(hs->maxKey);
+    return MMS_OK;
+}
+
+int mms_normalize(mms_ctx* c, float mn, float mx) {
+    if (!c) return MMS_ERR_INVALID;
+    if (!c->haveDensity) return c->fail(MMS_ERR_INVALID, "no density has been computed");
+    DeviceGuard guard(c->device);
+    const size_t nvox = static_cast<size_t>(c->grid.res[0]) * c->grid.res[1] * c->nz;
+    volatile float range = mx - mn;
+    volatile float rcp = 1.0f / range;
+    c->rec(EV_NRM0);
+    normalize_kernel<<<c->smCount * 8, 256, 0, c->stream>>>(c->vol.as<float>(), nvox, mn, rcp);
+    ++c->launches;
+    c->rec(EV_NRM1);
+    MMS_CUDA(c, cudaGetLastError());
+    c->normalized = true;
+    c->haveMesh = false;
+    return MMS_OK;
+}
+
+int mms_get_density_device(mms_ctx* c, const float** dv, const float** drgb) {
+    if (!c || !dv) return MMS_ERR_INVALID;
+    if (!c->haveDensity) return c->fail(MMS_ERR_INVALID, "no density has been computed");
+    *dv = c->vol.as<float>();
+    if (drgb) *drgb = nullptr;
+    return MMS_OK;
+}
+
+int mms_get_density(mms_ctx* c, const float** hv, const float** hrgb) {
+    if (!c || !hv) return MMS_ERR_INVALID;
+    if (!c->haveDensity) return c->fail(MMS_ERR_INVALID, "no density has been computed");
+    DeviceGuard guard(c->device);
+    const size_t bytes = static_cast<size_t>(c->grid.res[0]) * c->grid.res[1] * c->nz * 4;
+    if (!c->hVol.ensure(bytes)) return c->fail(MMS_ERR_NOMEM, "pinned allocation of %zu bytes failed", bytes);
+    c->rec(EV_DV0);
+    MMS_CUDA(c, cudaMemcpyAsync(c->hVol.p, c->vol.p, bytes, cudaMemcpyDeviceToHost, c->stream));
+    c->rec(EV_DV1);
+    if (int rc = checkDeviceError(c)) return rc;
+    *hv = c->hVol.as<float>();
+    if (hrgb) *hrgb = nullptr;
+    return MMS_OK;
+}
+
+int mms_set_density(mms_ctx* c, const float* volume) {
+    if (!c || !volume || !c->haveGrid) return MMS_ERR_INVALID;
+    DeviceGuard guard(c->device);
+    const size_t bytes = static_cast<size_t>(c->grid.res[0]) * c->grid.res[1] * c->nz * 4;
+    if (!c->vol.ensure(bytes)) return c->fail(MMS_ERR_NOMEM, "device allocation of %zu bytes failed", bytes);
+    MMS_CUDA(c, cudaMemcpyAsync(c->vol.p, volume, bytes, cudaMemcpyDefault, c->stream));
+    init_state_kernel<<<1, 1, 0, c->stream>>>(c->dstate.as<DevState>());
+    ++c->launches;
+    MMS_CUDA(c, cudaMemcpyAsync(c->hState.p, c->dstate.p, sizeof(DevState), cudaMemcpyDeviceToHost, c->stream));
+    c->haveDensity = true;
+    c->haveMesh = false;
+    return MMS_OK;
+}
+
+int mms_extract_isosurface(mms_ctx* c, float iso) {
+    if (!c) return MMS_ERR_INVALID;
+    if (!c->haveDensity) return c->fail(MMS_ERR_INVALID, "no density has been computed");
+    DeviceGuard guard(c->device);
+    McGeo m{};
+    m.sx = c->grid.res[0], m.sy = c->grid.res[1];
+    m.nzPlanes = c->nz, m.zPlane0 = c->z0, m.szGlobal = c->grid.res[2];
+    m.cx = m.sx - 1, m.cy = m.sy - 1, m.cz0 = c->cellZ0, m.cnz = c->cellNz;
+    m.nsegx = (m.cx + MCX - 1) / MCX;
+    const Geo g = makeGeo(c);
+    for (int a = 0; a < 3; ++a) m.org[a] = g.mn[a], m.sd[a] = g.sd[a];
+    m.iso = iso;
+    c->ntris = 0;
+    c->haveMesh = true;
+    if (m.cnz <= 0) return MMS_OK;
+    const size_t nseg = static_cast<size_t>(m.nsegx) * m.cy * m.cnz;
+    if (nseg >= (1ull << 32) - 1) return c->fail(MMS_ERR_UNSUPPORTED, "too many cell segments");
+    const unsigned ntiles = static_cast<unsigned>((nseg + kScanTile - 1) / kScanTile);
+    if (!c->segCount.ensure(nseg * 4) || !c->segOffset.ensure((nseg + 1) * 4) || !c->tileSums.ensure(std::max<size_t>(ntiles, 1) * 4))
+        return c->fail(MMS_ERR_NOMEM, "device allocation failed (marching-cubes segments)");
+    unsigned char* tri = nullptr;
+    if (c->params.want_cell_tricounts) {
+        const size_t ncell = static_cast<size_t>(m.cx) * m.cy * m.cnz;
+        if (!c->triCount.ensure(ncell)) return c->fail(MMS_ERR_NOMEM, "device allocation failed (cell counts)");
+        tri = c->triCount.as<unsigned char>();
+    }
+    cudaStream_t st = c->stream;
+    c->rec(EV_MC0);
+    dim3 grid(m.nsegx, (m.cy + MCY - 1) / MCY, (m.cnz + MCZ - 1) / MCZ);
+    mc_count_kernel<<<grid, MC_THREADS, 0, st>>>(m, c->vol.as<float>(), c->segCount.as<unsigned>(), tri);
+    ++c->launches;
+    DevState* ds = c->dstate.as<DevState>();
+    exclusiveScan(c->segCount.as<unsigned>(), c->segOffset.as<unsigned>(), nullptr, c->tileSums.as<unsigned>(), static_cast<unsigned>(nseg),
+        &ds->totalTris, st, c->launches);
+    MMS_CUDA(c, cudaMemcpyAsync(c->hState.p, c->dstate.p, sizeof(DevState), cudaMemcpyDeviceToHost, st));
+    MMS_CUDA(c, cudaStreamSynchronize(st)); // the one host round trip: the mesh size decides the allocation
+    const unsigned long long T = c->hState.as<DevState>()->totalTris;
+    c->ntris = T;
+    if (T > 0) {
+        if (!c->meshPos.ensure(T * 36) || !c->meshNrm.ensure(T * 36))
+            return c->fail(MMS_ERR_NOMEM, "device allocation of the mesh (%llu triangles, %llu bytes) failed", T, T * 72ull);
+        mc_emit_kernel<false><<<grid, MC_THREADS, sizeof(McEmitShared), st>>>(m, c->vol.as<float>(), nullptr, c->segOffset.as<unsigned>(),
+            c->meshPos.as<float>(), c->meshNrm.as<float>(), nullptr);
+        ++c->launches;
+    }
+    c->rec(EV_MC1);
+    MMS_CUDA(c, cudaGetLastError());
+    return MMS_OK;
+}
+
+int mms_get_mesh_device(mms_ctx* c, uint64_t* nverts, const float** pos, const float** nrm, const float** col) {
+    if (!c || !nverts) return MMS_ERR_INVALID;
+    if (!c->haveMesh) return c->fail(MMS_ERR_INVALID, "no isosurface has been extracted");
+    *nverts = c->ntris * 3;
+    if (pos) *pos = c->ntris ? c->meshPos.as<float>() : nullptr;
+    if (nrm) *nrm = c->ntris ? c->meshNrm.as<float>() : nullptr;
+    if (col) *col = nullptr;
+    return MMS_OK;
+}
+
+int mms_get_mesh(mms_ctx* c, uint64_t* nverts, const float** pos, const float** nrm, const float** col) {
+    if (!c || !nverts) return MMS_ERR_INVALID;
+    if (!c->haveMesh) return c->fail(MMS_ERR_INVALID, "no isosurface has been extracted");
+    DeviceGuard guard(c->device);
+    const size_t bytes = static_cast<size_t>(c->ntris) * 36;
+    *nverts = c->ntris * 3;
+    if (pos) *pos = nullptr;
+    if (nrm) *nrm = nullptr;
+    if (col) *col = nullptr;
+    if (bytes) {
+        if ((pos && !c->hPos.ensure(bytes)) || (nrm && !c->hNrm.ensure(bytes)))
+            return c->fail(MMS_ERR_NOMEM, "pinned allocation of %zu bytes failed", bytes);
+        c->rec(EV_DM0);
+        if (pos) MMS_CUDA(c, cudaMemcpyAsync(c->hPos.p, c->meshPos.p, bytes, cudaMemcpyDeviceToHost, c->stream));
+        if (nrm) MMS_CUDA(c, cudaMemcpyAsync(c->hNrm.p, c->meshNrm.p, bytes, cudaMemcpyDeviceToHost, c->stream));
+        c->rec(EV_DM1);
+        MMS_CUDA(c, cudaStreamSynchronize(c->stream));
+        if (pos) *pos = c->hPos.as<float>();
+        if (nrm) *nrm = c->hNrm.as<float>();
+    }
+    return MMS_OK;
+}
+
+int mms_get_home_voxels(mms_ctx* c, const int32_t** home, uint64_t* nparticles) {
+    if (!c || !home || !nparticles) return MMS_ERR_INVALID;
+    if (!c->haveDensity || !c->params.want_home_voxels) return c->fail(MMS_ERR_INVALID, "home voxels were not requested (params.want_home_voxels)");
+    DeviceGuard guard(c->device);
+    const size_t bytes = static_cast<size_t>(c->nparticles) * 12;
+    *nparticles = c->nparticles;
+    *home = nullptr;
+    if (!bytes) return MMS_OK;
+    if (!c->hHome.ensure(bytes)) return c->fail(MMS_ERR_NOMEM, "pinned allocation failed");
+    MMS_CUDA(c, cudaMemcpyAsync(c->hHome.p, c->home.p, bytes, cudaMemcpyDeviceToHost, c->stream));
+    MMS_CUDA(c, cudaStreamSynchronize(c->stream));
+    *home = c->hHome.as<int32_t>();
+    return MMS_OK;
+}
+
+int mms_get_cell_tricounts(mms_ctx* c, const uint8_t** counts, uint64_t* ncells) {
+    if (!c || !counts || !ncells) return MMS_ERR_INVALID;
+    if (!c->haveMesh || !c->params.want_cell_tricounts) return c->fail(MMS_ERR_INVALID, "cell counts were not requested (params.want_cell_tricounts)");
+    DeviceGuard guard(c->device);
+    const size_t n = static_cast<size_t>(c->grid.res[0] - 1) * (c->grid.res[1] - 1) * std::max(c->cellNz, 0);
+    *ncells = n;
+    *counts = nullptr;
+    if (!n) return MMS_OK;
+    if (!c->hTri.ensure(n)) return c->fail(MMS_ERR_NOMEM, "pinned allocation failed");
+    MMS_CUDA(c, cudaMemcpyAsync(c->hTri.p, c->triCount.p, n, cudaMemcpyDeviceToHost, c->stream));
+    MMS_CUDA(c, cudaStreamSynchronize(c->stream));
+    *counts = c->hTri.as<uint8_t>();
+    return MMS_OK;
+}
+
+int mms_synchronize(mms_ctx* c) {
+    if (!c) return MMS_ERR_INVALID;
+    DeviceGuard guard(c->device);
+    MMS_CUDA(c, cudaStreamSynchronize(c->stream));
+    return MMS_OK;
+}
+
+int mms_get_timings(mms_ctx* c, mms_timings* t) {
+    if (!c || !t) return MMS_ERR_INVALID;
+    DeviceGuard guard(c->device);
+    MMS_CUDA(c, cudaStreamSynchronize(c->stream));
+    auto el = [&](Ev a, Ev b) -> float {
+        float ms = 0.0f;
+        if (c->evSet[a] && c->evSet[b] && cudaEventElapsedTime(&ms, c->ev[a], c->ev[b]) == cudaSuccess) return ms;
+        cudaGetLastError();
+        return 0.0f;
+    };
+    t->h2d = el(EV_H2D0, EV_H2D1);
+    t->bin = el(EV_BIN0, EV_BIN1);
+    t->density = el(EV_BIN1, EV_DEN1);
+    t->normalize = el(EV_NRM0, EV_NRM1);
+    t->mc = el(EV_MC0, EV_MC1);
+    t->d2h_volume = el(EV_DV0, EV_DV1);
+    t->d2h_mesh = el(EV_DM0, EV_DM1);
+    return MMS_OK;
+}
+
+uint64_t mms_launch_count(const mms_ctx* c) { return c ? c->launches : 0; }
+
+void* mms_alloc_pinned(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+void mms_free_pinned(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+} // extern "C"

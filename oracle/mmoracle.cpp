@@ -1,0 +1,488 @@
+// oracle/mmoracle.cpp -- CPU ORACLE.  TEST INFRASTRUCTURE ONLY.
+//
+// An independent restatement, in plain C++, of the algorithm on MegaMol's particle -> density -> isosurface
+// path.  Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may load it; the product
+// (libmmsurf.so) never links, loads or calls anything in this directory.
+//
+// What each function follows (paths relative to the reference checkout):
+//   home voxel / support box / bump kernel / aggregators 0,1 / reduction order / normalise
+//        plugins/datatools/src/ParticlesToDensity.cpp:416-434 (geometry), :458-476 (radius, kernel),
+//        :490-529 (aggregators), :561-620 (binning + scatter loop), :669-682 (range, normalise)
+//   particle accessors (type -> float conversion, global radius, colour-R as intensity)
+//        plugins/geometry_calls/include/geometry_calls/SimpleSphericalParticles.h:86-178,
+//        plugins/geometry_calls/include/geometry_calls/Accessor.h:54-146
+//   marching-cubes classification + table (bit i <=> value < iso, corner order a2fVertexOffset)
+//        plugins/trisoup/src/volumetrics/MarchingCubeTables.cpp:11-16,58,278 and
+//        plugins/trisoup_gl/src/volumetrics/IsoSurface.cpp:254-276 (comparison sense)
+//   vertex interpolation t=(iso-f0)/(f1-f0), p0+t(p1-p0)
+//        plugins/protein_cuda/src/quicksurf/CUDAMarchingCubes.cu:224-227 (semantics reference only)
+//   Gaussian (QuickSurf) mode   rho = sum exp2(d^2 * -log2(e)/(2 (r*radscale)^2)), colour = sum w*rgb
+//        plugins/protein_cuda/src/quicksurf/CUDAQuickSurf.cu:303-315,1325-1334; QuickSurf.cpp:511-590
+//
+// PINNING: the reference ships no tests or golden vectors for this path, so this oracle is
+// pinned against the compiled reference translation units themselves (oracle/_ref/libmmref.so): see
+// tests/test_oracle_vs_reference.py (runs where /root/reference exists) and the fixtures it wrote to
+// tests/golden/ with oracle/tools/gen_golden.py (checked everywhere).
+//
+// Built with -ffp-contract=off: the reference is built for baseline x86-64 without FMA, every fp32
+// operation below is individually rounded.
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <limits>
+#include <vector>
+
+#include <omp.h>
+
+namespace {
+
+const uint64_t kCaseWords[256] = {
+#include "mc_case_words.inc"
+};
+
+// Corner offsets and edge end points of the classic table (MarchingCubeTables.cpp:11-16).
+const int kCorner[8][3] = {{0, 0, 0}, {1, 0, 0}, {1, 1, 0}, {0, 1, 0}, {0, 0, 1}, {1, 0, 1}, {1, 1, 1}, {0, 1, 1}};
+const int kEdge[12][2] = {{0, 1}, {1, 2}, {2, 3}, {3, 0}, {4, 5}, {5, 6}, {6, 7}, {7, 4}, {0, 4}, {1, 5}, {2, 6}, {3, 7}};
+
+enum { VERT_NONE = 0, VERT_FLOAT_XYZ = 1, VERT_FLOAT_XYZR = 2, VERT_SHORT_XYZ = 3, VERT_DOUBLE_XYZ = 4 };
+enum {
+    COL_NONE = 0, COL_UINT8_RGB = 1, COL_UINT8_RGBA = 2, COL_FLOAT_RGB = 3, COL_FLOAT_RGBA = 4, COL_FLOAT_I = 5,
+    COL_USHORT_RGBA = 6, COL_DOUBLE_I = 7
+};
+const unsigned kVertSize[5] = {0, 12, 16, 6, 24};
+const unsigned kColSize[8] = {0, 3, 4, 12, 16, 4, 8, 8};
+
+} // namespace
+
+extern "C" {
+
+struct mmo_list {
+    const void* vtx;
+    const void* col;
+    uint64_t count;
+    int32_t vtx_type;
+    uint32_t vtx_stride;
+    int32_t col_type;
+    uint32_t col_stride;
+    float global_radius;
+    uint8_t global_rgba[4];
+    float irange[2];
+};
+
+struct mmo_grid {
+    float min[3];    // bbox Left/Bottom/Back
+    float extent[3]; // bbox Width/Height/Depth
+    int32_t res[3];
+    int32_t cyclic[3];
+};
+
+} // extern "C"
+
+namespace {
+
+struct Particle {
+    float x, y, z, r;
+};
+
+inline Particle fetch(const mmo_list& l, uint64_t j) {
+    const unsigned stride = l.vtx_stride ? l.vtx_stride : kVertSize[l.vtx_type];
+    const char* p = static_cast<const char*>(l.vtx) + j * stride;
+    Particle q{0, 0, 0, l.global_radius};
+    switch (l.vtx_type) {
+    case VERT_FLOAT_XYZ: {
+        float f[3];
+        std::memcpy(f, p, 12);
+        q.x = f[0], q.y = f[1], q.z = f[2];
+    } break;
+    case VERT_FLOAT_XYZR: {
+        float f[4];
+        std::memcpy(f, p, 16);
+        q.x = f[0], q.y = f[1], q.z = f[2], q.r = f[3];
+    } break;
+    case VERT_SHORT_XYZ: { // raw unsigned short values cast to float, no de-quantisation (SURVEY 8a traps)
+        unsigned short s[3];
+        std::memcpy(s, p, 6);
+        q.x = static_cast<float>(s[0]), q.y = static_cast<float>(s[1]), q.z = static_cast<float>(s[2]);
+    } break;
+    case VERT_DOUBLE_XYZ: {
+        double d[3];
+        std::memcpy(d, p, 24);
+        q.x = static_cast<float>(d[0]), q.y = static_cast<float>(d[1]), q.z = static_cast<float>(d[2]);
+    } break;
+    default: break;
+    }
+    return q;
+}
+
+/** Colour accessors as floats (Get_f of cr/cg/cb/ca accessors); out[0] is what aggregator 1 multiplies by. */
+inline void fetchColour(const mmo_list& l, uint64_t j, float out[4]) {
+    const unsigned stride = l.col_stride ? l.col_stride : kColSize[l.col_type];
+    const char* p = l.col ? static_cast<const char*>(l.col) + j * stride : nullptr;
+    switch (l.col_type) {
+    case COL_UINT8_RGB:
+    case COL_UINT8_RGBA: {
+        unsigned char c[4] = {0, 0, 0, 255};
+        std::memcpy(c, p, l.col_type == COL_UINT8_RGB ? 3 : 4);
+        for (int k = 0; k < 4; ++k) out[k] = static_cast<float>(c[k]);
+    } break;
+    case COL_FLOAT_RGB: {
+        std::memcpy(out, p, 12);
+        out[3] = 1.0f;
+    } break;
+    case COL_FLOAT_RGBA: std::memcpy(out, p, 16); break;
+    case COL_FLOAT_I: {
+        std::memcpy(out, p, 4);
+        out[1] = out[2] = out[3] = 0.0f;
+    } break;
+    case COL_USHORT_RGBA: {
+        unsigned short c[4];
+        std::memcpy(c, p, 8);
+        for (int k = 0; k < 4; ++k) out[k] = static_cast<float>(c[k]);
+    } break;
+    case COL_DOUBLE_I: {
+        double d;
+        std::memcpy(&d, p, 8);
+        out[0] = static_cast<float>(d);
+        out[1] = out[2] = out[3] = 0.0f;
+    } break;
+    default:
+        for (int k = 0; k < 4; ++k) out[k] = static_cast<float>(l.global_rgba[k]) / 255.0f;
+    }
+}
+
+struct Geometry {
+    float min[3], sd[3];
+    int s[3];
+    bool cyc[3];
+};
+
+inline Geometry geometry(const mmo_grid& g) {
+    Geometry q;
+    for (int a = 0; a < 3; ++a) {
+        q.min[a] = g.min[a];
+        q.s[a] = g.res[a];
+        q.sd[a] = g.extent[a] / static_cast<float>(g.res[a] - 1); // ParticlesToDensity.cpp:430-432
+        q.cyc[a] = g.cyclic[a] != 0;
+    }
+    return q;
+}
+
+inline int homeVoxel(float p, float mn, float sd) { // ParticlesToDensity.cpp:564
+    return static_cast<int>((p - mn) / sd);
+}
+
+inline float bump(float dist, float eps) { // ParticlesToDensity.cpp:472-476
+    if (dist >= eps) return 0.0f;
+    return std::exp(-1.0f / (1.0f - std::pow((1.0f / eps) * dist, 2.0f)));
+}
+
+inline long floorMod(long a, long m) {
+    long r = a % m;
+    return r < 0 ? r + m : r;
+}
+
+} // namespace
+
+extern "C" {
+
+int mmo_version() { return 1; }
+
+/** Home voxel of every particle, list-major: out[3*i + axis].  Bit-exact restatement of :563-568. */
+int mmo_home_voxels(int nlists, const mmo_list* lists, const mmo_grid* grid, int32_t* out) {
+    const Geometry g = geometry(*grid);
+    uint64_t base = 0;
+    for (int li = 0; li < nlists; ++li) {
+        const mmo_list& l = lists[li];
+        if (l.vtx_type == VERT_NONE) continue;
+#pragma omp parallel for
+        for (int64_t j = 0; j < static_cast<int64_t>(l.count); ++j) {
+            const Particle p = fetch(l, j);
+            out[3 * (base + j) + 0] = homeVoxel(p.x, g.min[0], g.sd[0]);
+            out[3 * (base + j) + 1] = homeVoxel(p.y, g.min[1], g.sd[1]);
+            out[3 * (base + j) + 2] = homeVoxel(p.z, g.min[2], g.sd[2]);
+        }
+        base += l.count;
+    }
+    return 0;
+}
+
+/**
+ * ParticlesToDensity density volume, aggregator 0 (sum of bumps) or 1 (bump * colour-R).
+ * Accumulation order per voxel = particle order (list-major), i.e. exactly the reference at ONE OpenMP
+ * thread; threads here partition the z axis, which leaves every voxel's order untouched, so the result
+ * is independent of the thread count.  [z0, z0+nz) restricts the output to a slab (vol has nz planes).
+ * minmax (optional) receives min/max BEFORE normalisation; normalize applies (v-min)*(1/(max-min)) (:676-682).
+ */
+int mmo_density_p2d(int nlists, const mmo_list* lists, const mmo_grid* grid, float sigma, int aggregator,
+    int normalize, int z0, int nz, float* vol, float minmax[2]) {
+    if (aggregator != 0 && aggregator != 1) return -1;
+    const Geometry g = geometry(*grid);
+    const int sx = g.s[0], sy = g.s[1], sz = g.s[2];
+    if (z0 < 0 || nz < 0 || z0 + nz > sz) return -2;
+    const size_t nvox = static_cast<size_t>(sx) * sy * nz;
+    std::fill(vol, vol + nvox, 0.0f);
+    for (int li = 0; li < nlists; ++li) {
+        const mmo_list& l = lists[li];
+        if (l.vtx_type == VERT_NONE) continue;
+#pragma omp parallel
+        {
+            const int nt = omp_get_num_threads(), tid = omp_get_thread_num();
+            const int zlo = z0 + static_cast<int>(static_cast<long>(nz) * tid / nt);
+            const int zhi = z0 + static_cast<int>(static_cast<long>(nz) * (tid + 1) / nt); // exclusive
+            for (uint64_t j = 0; j < l.count && zlo < zhi; ++j) {
+                const Particle p = fetch(l, j);
+                const float rad = p.r;
+                if (rad == 0.0f) continue; // volOp early-out (:523)
+                const int x = homeVoxel(p.x, g.min[0], g.sd[0]);
+                const int y = homeVoxel(p.y, g.min[1], g.sd[1]);
+                const int z = homeVoxel(p.z, g.min[2], g.sd[2]);
+                const int fx = static_cast<int>(std::ceil(rad / g.sd[0]));
+                const int fy = static_cast<int>(std::ceil(rad / g.sd[1]));
+                const int fz = static_cast<int>(std::ceil(rad / g.sd[2]));
+                float weight = 1.0f;
+                if (aggregator == 1) {
+                    float c[4];
+                    fetchColour(l, j, c);
+                    weight = c[0];
+                }
+                const float eps = sigma * rad;
+                for (int hz = z - fz; hz <= z + fz; ++hz) {
+                    long tz = hz;
+                    if (g.cyc[2]) tz = floorMod(hz, sz); // == (hz + 2*sz) % sz wherever the reference is defined
+                    else if (hz < 0 || hz > sz - 1) continue;
+                    if (tz < zlo || tz >= zhi) continue;
+                    float zd = static_cast<float>(hz) * g.sd[2] + g.min[2];
+                    zd = std::fabs(zd - p.z);
+                    for (int hy = y - fy; hy <= y + fy; ++hy) {
+                        long ty = hy;
+                        if (g.cyc[1]) ty = floorMod(hy, sy);
+                        else if (hy < 0 || hy > sy - 1) continue;
+                        float yd = static_cast<float>(hy) * g.sd[1] + g.min[1];
+                        yd = std::fabs(yd - p.y);
+                        for (int hx = x - fx; hx <= x + fx; ++hx) {
+                            long tx = hx;
+                            if (g.cyc[0]) tx = floorMod(hx, sx);
+                            else if (hx < 0 || hx > sx - 1) continue;
+                            float xd = static_cast<float>(hx) * g.sd[0] + g.min[0];
+                            xd = std::fabs(xd - p.x);
+                            const float dis = std::sqrt(xd * xd + yd * yd + zd * zd);
+                            const float w = bump(dis, eps);
+                            float& v = vol[tx + (ty + (tz - z0) * sy) * static_cast<size_t>(sx)];
+                            v += (aggregator == 1) ? w * weight : w;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (nvox == 0) return 0;
+    float mx = *std::max_element(vol, vol + nvox), mn = *std::min_element(vol, vol + nvox);
+    if (minmax) minmax[0] = mn, minmax[1] = mx;
+    if (normalize) {
+        const float rcp = 1.0f / (mx - mn);
+#pragma omp parallel for
+        for (int64_t i = 0; i < static_cast<int64_t>(nvox); ++i) vol[i] = (vol[i] - mn) * rcp;
+    }
+    return 0;
+}
+
+/** (v - mn) * (1/(mx-mn)) with caller-supplied range (multi-slab normalisation uses the GLOBAL range). */
+int mmo_normalize(float* vol, uint64_t n, float mn, float mx) {
+    const float rcp = 1.0f / (mx - mn);
+#pragma omp parallel for
+    for (int64_t i = 0; i < static_cast<int64_t>(n); ++i) vol[i] = (vol[i] - mn) * rcp;
+    return 0;
+}
+
+/**
+ * QuickSurf-style Gaussian density (+ optional density-weighted RGB volume, 3 floats per voxel, x fastest).
+ * Node (i,j,k) sits at origin + (i,j,k)*spacing.  Candidate set = clean radial cutoff
+ * d < gausslim*radscale*r_p per particle (spec choice); weight exp2f(d^2 * w_p),
+ * w_p = -log2(e) / (2 (r_p*radscale)^2).  Per-voxel order = particle order.  Non-periodic.
+ */
+int mmo_density_gauss(int nlists, const mmo_list* lists, const float origin[3], const float spacing[3],
+    const int32_t res[3], float radscale, float gausslim, int z0, int nz, float* vol, float* rgb) {
+    const int sx = res[0], sy = res[1];
+    const size_t nvox = static_cast<size_t>(sx) * sy * nz;
+    std::fill(vol, vol + nvox, 0.0f);
+    if (rgb) std::fill(rgb, rgb + 3 * nvox, 0.0f);
+    const float log2e = 1.4426950408889634f;
+    for (int li = 0; li < nlists; ++li) {
+        const mmo_list& l = lists[li];
+        if (l.vtx_type == VERT_NONE) continue;
+#pragma omp parallel
+        {
+            const int nt = omp_get_num_threads(), tid = omp_get_thread_num();
+            const int zlo = z0 + static_cast<int>(static_cast<long>(nz) * tid / nt);
+            const int zhi = z0 + static_cast<int>(static_cast<long>(nz) * (tid + 1) / nt);
+            for (uint64_t j = 0; j < l.count && zlo < zhi; ++j) {
+                const Particle p = fetch(l, j);
+                const float sr = p.r * radscale;
+                if (!(sr > 0.0f)) continue;
+                const float w = -log2e / (2.0f * sr * sr);
+                const float cut = gausslim * sr;
+                const float cut2 = cut * cut;
+                float c[4] = {1, 1, 1, 1};
+                if (rgb) {
+                    fetchColour(l, j, c);
+                    if (l.col_type == COL_UINT8_RGB || l.col_type == COL_UINT8_RGBA || l.col_type == COL_USHORT_RGBA)
+                        for (int k = 0; k < 3; ++k) c[k] = c[k] / 255.0f; // QuickSurf.cpp:545-577 (USHORT /255 sic)
+                    if (l.col_type == COL_FLOAT_I || l.col_type == COL_DOUBLE_I) { // grey, min-max normalised per list
+                        const float v = (c[0] - l.irange[0]) / (l.irange[1] - l.irange[0]);
+                        c[0] = c[1] = c[2] = v;
+                    }
+                }
+                int lo[3], hi[3];
+                const float pp[3] = {p.x, p.y, p.z};
+                for (int a = 0; a < 3; ++a) {
+                    lo[a] = static_cast<int>(std::floor((pp[a] - cut - origin[a]) / spacing[a])) - 1;
+                    hi[a] = static_cast<int>(std::ceil((pp[a] + cut - origin[a]) / spacing[a])) + 1;
+                }
+                lo[0] = std::max(lo[0], 0), lo[1] = std::max(lo[1], 0), lo[2] = std::max(lo[2], zlo);
+                hi[0] = std::min(hi[0], sx - 1), hi[1] = std::min(hi[1], sy - 1), hi[2] = std::min(hi[2], zhi - 1);
+                for (int k = lo[2]; k <= hi[2]; ++k) {
+                    const float dz = (static_cast<float>(k) * spacing[2] + origin[2]) - p.z;
+                    for (int jy = lo[1]; jy <= hi[1]; ++jy) {
+                        const float dy = (static_cast<float>(jy) * spacing[1] + origin[1]) - p.y;
+                        for (int i = lo[0]; i <= hi[0]; ++i) {
+                            const float dx = (static_cast<float>(i) * spacing[0] + origin[0]) - p.x;
+                            const float d2 = dx * dx + dy * dy + dz * dz;
+                            if (!(d2 < cut2)) continue;
+                            const float g = std::exp2(d2 * w);
+                            const size_t o = i + (jy + static_cast<size_t>(k - z0) * sy) * sx;
+                            vol[o] += g;
+                            if (rgb) {
+                                rgb[3 * o + 0] += g * c[0];
+                                rgb[3 * o + 1] += g * c[1];
+                                rgb[3 * o + 2] += g * c[2];
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+    return 0;
+}
+
+/** Cube index of cell (x,y,z): bit i set iff corner i < iso. */
+static inline int cubeIndex(const float* vol, int sx, int sy, int x, int y, int z, float iso) {
+    int ci = 0;
+    for (int c = 0; c < 8; ++c) {
+        const float v = vol[(x + kCorner[c][0]) + static_cast<size_t>(sx) * ((y + kCorner[c][1]) + static_cast<size_t>(sy) * (z + kCorner[c][2]))];
+        if (v < iso) ci |= 1 << c;
+    }
+    return ci;
+}
+
+/**
+ * Per-cell triangle counts, cells x-fastest: out[x + (sx-1)*(y + (sy-1)*z)], (sx-1)(sy-1)(sz-1) entries.
+ * cubeidx (optional) receives the 8-bit case.  Returns the total number of triangles.
+ */
+int64_t mmo_mc_count(const float* vol, const int32_t res[3], float iso, uint8_t* tricount, uint8_t* cubeidx) {
+    const int sx = res[0], sy = res[1], sz = res[2];
+    const int cx = sx - 1, cy = sy - 1, cz = sz - 1;
+    if (cx <= 0 || cy <= 0 || cz <= 0) return 0;
+    int64_t total = 0;
+#pragma omp parallel for reduction(+ : total)
+    for (int z = 0; z < cz; ++z)
+        for (int y = 0; y < cy; ++y)
+            for (int x = 0; x < cx; ++x) {
+                const int ci = cubeIndex(vol, sx, sy, x, y, z, iso);
+                const int n = static_cast<int>(kCaseWords[ci] & 15);
+                const size_t o = x + static_cast<size_t>(cx) * (y + static_cast<size_t>(cy) * z);
+                if (tricount) tricount[o] = static_cast<uint8_t>(n);
+                if (cubeidx) cubeidx[o] = static_cast<uint8_t>(ci);
+                total += n;
+            }
+    return total;
+}
+
+namespace {
+struct Node {
+    float f, gx, gy, gz;
+};
+} // namespace
+
+/**
+ * Triangle soup in cell-linear order (x fastest, then y, then z); within a cell the table's order.
+ * pos/nrm (and col, if rgb != NULL): 9 floats per triangle.  Node (i,j,k) sits at origin + idx*sd
+ * (float(idx)*sd + origin, two roundings, the reference's voxel-position formula :605).
+ * Vertex on an edge: always interpolated from the LOWER node to the HIGHER node of the edge's axis
+ * (t = (iso - f_lo)/(f_hi - f_lo), p = p_lo + t*(p_hi - p_lo)) so that neighbouring cells produce
+ * bit-identical shared vertices.  Normal = -grad(rho) interpolated with the same t and normalised;
+ * grad at a node by central differences (one-sided at the border), divided by the actual node distance.
+ * Colour = lerp of the per-node colour rgb/rho (rho == 0 -> 0), same t.
+ * z_offset: index of plane 0 of `vol` in the global grid (slabs); positions use global indices.
+ * Returns the number of triangles written (<= max_tris), or -1 if max_tris was too small.
+ */
+int64_t mmo_mc_emit(const float* vol, const float* rgb, const int32_t res[3], const float origin[3], const float sd[3],
+    float iso, int z_offset, int64_t max_tris, float* pos, float* nrm, float* col) {
+    const int sx = res[0], sy = res[1], sz = res[2];
+    const int cx = sx - 1, cy = sy - 1, cz = sz - 1;
+    if (cx <= 0 || cy <= 0 || cz <= 0) return 0;
+    auto at = [&](int x, int y, int z) -> float { return vol[x + static_cast<size_t>(sx) * (y + static_cast<size_t>(sy) * z)]; };
+    auto node = [&](int x, int y, int z) -> Node {
+        Node n;
+        n.f = at(x, y, z);
+        const int xm = std::max(x - 1, 0), xp = std::min(x + 1, sx - 1);
+        const int ym = std::max(y - 1, 0), yp = std::min(y + 1, sy - 1);
+        const int zm = std::max(z - 1, 0), zp = std::min(z + 1, sz - 1);
+        n.gx = (at(xp, y, z) - at(xm, y, z)) / (static_cast<float>(xp - xm) * sd[0]);
+        n.gy = (at(x, yp, z) - at(x, ym, z)) / (static_cast<float>(yp - ym) * sd[1]);
+        n.gz = (at(x, y, zp) - at(x, y, zm)) / (static_cast<float>(zp - zm) * sd[2]);
+        return n;
+    };
+    int64_t ntri = 0;
+    for (int z = 0; z < cz; ++z)
+        for (int y = 0; y < cy; ++y)
+            for (int x = 0; x < cx; ++x) {
+                const int ci = cubeIndex(vol, sx, sy, x, y, z, iso);
+                const uint64_t word = kCaseWords[ci];
+                const int n = static_cast<int>(word & 15);
+                if (n == 0) continue;
+                if (ntri + n > max_tris) return -1;
+                for (int k = 0; k < 3 * n; ++k) {
+                    const int e = static_cast<int>((word >> (4 + 4 * k)) & 15);
+                    int a = kEdge[e][0], b = kEdge[e][1];
+                    // canonical direction: lower node first
+                    if (kCorner[a][0] + kCorner[a][1] + kCorner[a][2] > kCorner[b][0] + kCorner[b][1] + kCorner[b][2]) std::swap(a, b);
+                    const int ax = x + kCorner[a][0], ay = y + kCorner[a][1], az = z + kCorner[a][2];
+                    const int bx = x + kCorner[b][0], by = y + kCorner[b][1], bz = z + kCorner[b][2];
+                    const Node na = node(ax, ay, az), nb = node(bx, by, bz);
+                    const float t = (iso - na.f) / (nb.f - na.f);
+                    const float pa[3] = {static_cast<float>(ax) * sd[0] + origin[0], static_cast<float>(ay) * sd[1] + origin[1],
+                        static_cast<float>(az + z_offset) * sd[2] + origin[2]};
+                    const float pb[3] = {static_cast<float>(bx) * sd[0] + origin[0], static_cast<float>(by) * sd[1] + origin[1],
+                        static_cast<float>(bz + z_offset) * sd[2] + origin[2]};
+                    float* P = pos + 9 * ntri + 3 * k;
+                    for (int c = 0; c < 3; ++c) P[c] = pa[c] + t * (pb[c] - pa[c]);
+                    if (nrm) {
+                        const float gx = na.gx + t * (nb.gx - na.gx), gy = na.gy + t * (nb.gy - na.gy), gz = na.gz + t * (nb.gz - na.gz);
+                        const float len2 = gx * gx + gy * gy + gz * gz;
+                        float inv = 0.0f;
+                        if (len2 > 0.0f) inv = -1.0f / std::sqrt(len2);
+                        float* N = nrm + 9 * ntri + 3 * k;
+                        N[0] = gx * inv, N[1] = gy * inv, N[2] = gz * inv;
+                    }
+                    if (col && rgb) {
+                        const size_t oa = ax + static_cast<size_t>(sx) * (ay + static_cast<size_t>(sy) * az);
+                        const size_t ob = bx + static_cast<size_t>(sx) * (by + static_cast<size_t>(sy) * bz);
+                        float* Cc = col + 9 * ntri + 3 * k;
+                        for (int c = 0; c < 3; ++c) {
+                            const float ca = na.f > 0.0f ? rgb[3 * oa + c] / na.f : 0.0f;
+                            const float cb = nb.f > 0.0f ? rgb[3 * ob + c] / nb.f : 0.0f;
+                            Cc[c] = ca + t * (cb - ca);
+                        }
+                    }
+                }
+                ntri += n;
+            }
+    return ntri;
+}
+
+/** The packed case words (for table tests). */
+void mmo_case_words(uint64_t out[256]) { std::memcpy(out, kCaseWords, sizeof(kCaseWords)); }
+
+} // extern "C"
