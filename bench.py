@@ -1,0 +1,244 @@
+#!/usr/bin/env python
+"""bench.py -- particles -> density volume -> isosurface throughput on N B200s (one process per GPU).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c1|c4]
+
+Workload (BASELINE.json configs[1], SURVEY.md 8d "C2"): 10 M Lennard-Jones-fluid-like particles (jittered simple
+cubic lattice, rho* = 0.795, FLOAT_XYZ + global radius 0.5) -> 512^3 ParticlesToDensity volume (bump kernel,
+sigma 1, cyclic, normalize on) + marching-cubes isosurface at isoval 0.5 (the modules' default parameters).
+For N > 1 the workload is weak-scaled: every rank owns a z-slab of 512 planes worth of particles of the
+C4-style lattice (N = 8 -> 80 M particles, 512 x 512 x 4096 ... see slabs.py); `value` is the whole job.
+
+One JSON line on stdout (rank 0).  `value` = device-resident throughput (inputs in HBM when the clock starts),
+`e2e` = the same step through the C ABI with HOST buffers (pinned H2D of the particles, D2H of volume + mesh inside
+the timed region).  `--impl reference` times the UNMODIFIED reference modules (oracle/_ref/libmmref.so: the
+reference's ParticlesToDensity + IsoSurface translation units) on the host cores on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from megamol_b200 import synth  # noqa: E402
+
+METRIC = "Mparticles/s & Gvoxels/s density+isosurface"
+ISO = 0.5
+RADIUS = 0.5
+
+
+def workload(name: str):
+    if name == "c1":
+        return dict(name="C1: 1M uniform-random spheres r=0.5 -> 128^3 P2D bump + MC", n=1_000_000, res=(128, 128, 128), kind="uniform", box=64.0)
+    if name == "c2":
+        return dict(name="C2: 10M LJ-fluid-like (jittered lattice, r=0.5, cyclic, normalize) -> 512^3 P2D bump + MC iso 0.5",
+                    n=10_000_000, res=(512, 512, 512), kind="lj")
+    raise SystemExit(f"unknown workload {name}")
+
+
+def make_particles(w, i0=0, i1=None):
+    if w["kind"] == "uniform":
+        xyz = synth.uniform_box(w["n"], w["box"], i0=i0, i1=i1)
+        return xyz, w["box"]
+    xyz, L = synth.lj_fluid(w["n"], i0=i0, i1=i1)
+    return xyz, L
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.stop_flag = threading.Event()
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([t.strip() for t in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.1)
+
+    def summary(self):
+        sm = [float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[k] for s in self.samples if len(s) >= 6 for k in range(4) if s[2 + k].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.samples)}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_reference_sample(threads=None, reps=1):
+    """The reference's own CPU path on a bounded sample of the C2 workload: 54^3 = 157 464 lattice sites -> 128^3
+    (same lattice spacing and voxel size as C2: 1/64 of the volume), ParticlesToDensity (OpenMP) + IsoSurface (serial),
+    through the reference's call/slot API.  Returns dict(value Mparticles/s, gvoxels/s, ...)."""
+    from oracle import ref_binding as rb
+    n = 54 ** 3
+    xyz, L = synth.lj_fluid(n)
+    res = (128, 128, 128)
+    # same voxel size as C2: box = 127 * (L_c2 / 511)
+    if rb.available():
+        h = rb.Harness()
+        if threads:
+            h.set_threads(threads)
+        cores = h.threads
+        kind = "reference"
+        best = None
+        for _ in range(reps):
+            h.set_particles([dict(vtx=xyz, vtx_type=1, count=n, global_radius=RADIUS)], (0, 0, 0, L, L, L))
+            h.set_p2d_params(res, cyclic=(True, True, True), normalize=True, sigma=1.0)
+            t0 = time.perf_counter()
+            _, meta = h.pull_volume(copy=False)
+            m = h.pull_mesh(ISO, copy=False)
+            dt = time.perf_counter() - t0
+            if best is None or dt < best[0]:
+                best = (dt, meta["ms"], m["ms"], m["nverts"] // 3)
+        dt, ms_d, ms_i, ntri = best
+        sample = f"{n} particles (54^3 sites of the C2 lattice) -> 128^3, P2D {ms_d:.0f} ms ({cores} OpenMP threads) + IsoSurface {ms_i:.0f} ms (serial, marching tets, {ntri} triangles)"
+    else:
+        from oracle import oracle_binding as ob
+        o = ob.Oracle()
+        cores = os.cpu_count() or 1
+        kind = "port"
+        t0 = time.perf_counter()
+        vol, _ = o.density_p2d([dict(vtx=xyz, vtx_type=1, count=n, global_radius=RADIUS)], (0, 0, 0), (L, L, L), res, (1, 1, 1), normalize=True)
+        ntri, _, _ = o.mc_count(vol, ISO)
+        dt = time.perf_counter() - t0
+        sample = f"{n} particles -> 128^3 with the oracle port (density OpenMP + MC classify), {ntri} triangles"
+    return {"value": n / dt / 1e6, "unit": "Mparticles/s", "gvoxels_per_s": res[0] * res[1] * res[2] / dt / 1e9, "cores": cores,
+            "kind": kind, "sample": sample, "seconds": dt}
+
+
+def run_reference(args, w):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vals = []
+    for _ in range(args.warmup):
+        cpu_reference_sample()
+    for _ in range(args.steps):
+        vals.append(cpu_reference_sample())
+    total_s = sum(v["seconds"] for v in vals)
+    n = 54 ** 3
+    value = n * len(vals) / total_s / 1e6
+    cb = dict(vals[-1])
+    cb["value"] = value
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "Mparticles/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_s / len(vals) * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "gvoxels_per_s": 128 ** 3 * len(vals) / total_s / 1e9,
+            "config": {"workload": w["name"], "sample_per_step": cb["sample"]},
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": value, "unit": "Mparticles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def run_ours(args, w):
+    import torch
+    import megamol_b200 as mm
+    from megamol_b200 import slabs
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    job = slabs.SlabJob(w, rank, world, local, iso=ISO, radius=RADIUS)
+    peak, peak_src = load_peaks()
+
+    # ---- device-resident arm -------------------------------------------------------------------------------
+    for _ in range(args.warmup):
+        job.step_device()
+    job.barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = job.launches()
+    t_dev = job.timed(job.step_device, args.steps)  # max over ranks, ms for K steps
+    launches = (job.launches() - launches0)
+    stage = job.stage_times()
+    # ---- end-to-end arm --------------------------------------------------------------------------------------
+    for _ in range(min(args.warmup, 3)):
+        job.step_e2e()
+    job.barrier()
+    e2e_steps = max(1, min(args.steps, 5))
+    t_e2e = job.timed(job.step_e2e, e2e_steps)
+    if rank == 0:
+        sampler.stop_flag.set()
+        sampler.join(timeout=3)
+    n_total, v_total, t_total = job.totals()
+    if rank != 0:
+        job.close()
+        return
+    ms = t_dev / args.steps
+    value = n_total / (ms * 1e-3) / 1e6
+    ms_e = t_e2e / e2e_steps
+    e2e_val = n_total / (ms_e * 1e-3) / 1e6
+    # roofline of the dominant kernel (largest share of the device step), algorithmic bytes per DESIGN.md
+    rl = job.roofline(stage, peak)
+    rl["peak_source"] = peak_src
+    line = {"metric": METRIC, "value": value, "unit": "Mparticles/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "gvoxels_per_s": v_total / (ms * 1e-3) / 1e9,
+            "config": {"workload": w["name"] if world == 1 else job.describe(), "particles": n_total, "voxels": v_total, "triangles": t_total,
+                       "l2": "inputs (particles + volume + mesh) are larger than the 126 MB L2; no explicit flush",
+                       "parallelism": f"z-slabs x{world}"},
+            "stages_ms": stage, "roofline": rl,
+            "pipeline_hbm_frac": job.pipeline_bytes() / (ms * 1e-3) / 1e9 / peak,
+            "e2e": {"value": e2e_val, "unit": "Mparticles/s", "ms_per_step": ms_e, "steps": e2e_steps,
+                    "h2d_bytes_per_step": job.h2d_bytes(), "d2h_bytes_per_step": job.d2h_bytes()},
+            "gpu_launches": launches, "clocks": sampler.summary()}
+    if not args.no_cpu:
+        cb = cpu_reference_sample()
+        line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        line["cpu_baseline"]["gvoxels_per_s"] = cb["gvoxels_per_s"]
+    print(json.dumps(line))
+    job.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    w = workload(args.workload)
+    if args.impl == "reference":
+        run_reference(args, w)
+    else:
+        run_ours(args, w)
+
+
+if __name__ == "__main__":
+    main()

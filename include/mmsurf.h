@@ -143,6 +143,9 @@ int mms_get_home_voxels(mms_ctx* ctx, const int32_t** home, uint64_t* nparticles
 int mms_get_cell_tricounts(mms_ctx* ctx, const uint8_t** counts, uint64_t* ncells);
 
 int mms_get_timings(mms_ctx* ctx, mms_timings* out);
+/* Stopwatch on the context's own stream (CUDA events): start records, stop records + synchronises. */
+int mms_timer_start(mms_ctx* ctx);
+int mms_timer_stop(mms_ctx* ctx, float* elapsed_ms);
 int mms_synchronize(mms_ctx* ctx);
 /* Number of kernel launches issued by this context so far (for bench.py's gpu_launches). */
 uint64_t mms_launch_count(const mms_ctx* ctx);

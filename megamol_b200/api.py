@@ -18,7 +18,7 @@ EXPORTS = ["mms_create", "mms_destroy", "mms_last_error", "mms_set_grid", "mms_s
            "mms_clear_particles", "mms_push_particles", "mms_compute_density", "mms_get_density_range", "mms_normalize",
            "mms_get_density", "mms_get_density_device", "mms_set_density", "mms_extract_isosurface", "mms_get_mesh",
            "mms_get_mesh_device", "mms_get_home_voxels", "mms_get_cell_tricounts", "mms_get_timings", "mms_synchronize",
-           "mms_launch_count", "mms_alloc_pinned", "mms_free_pinned", "mms_version"]
+           "mms_timer_start", "mms_timer_stop", "mms_launch_count", "mms_alloc_pinned", "mms_free_pinned", "mms_version"]
 
 
 class MmsError(RuntimeError):
@@ -91,6 +91,8 @@ def load_library():
     L.mms_get_cell_tricounts.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_uint64)]
     L.mms_get_timings.argtypes = [vp, C.POINTER(MmsTimings)]
     L.mms_synchronize.argtypes = [vp]
+    L.mms_timer_start.argtypes = [vp]
+    L.mms_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
     L.mms_launch_count.argtypes = [vp]
     L.mms_launch_count.restype = C.c_uint64
     L.mms_alloc_pinned.argtypes = [C.c_size_t]
@@ -266,6 +268,14 @@ class Surf:
         t = MmsTimings()
         self._chk(self.L.mms_get_timings(self.h, C.byref(t)))
         return {n: getattr(t, n) for n, _ in MmsTimings._fields_}
+
+    def timer_start(self):
+        self._chk(self.L.mms_timer_start(self.h))
+
+    def timer_stop(self) -> float:
+        ms = C.c_float()
+        self._chk(self.L.mms_timer_stop(self.h, C.byref(ms)))
+        return float(ms.value)
 
     def synchronize(self):
         self._chk(self.L.mms_synchronize(self.h))

@@ -77,7 +77,7 @@ struct PinBuf {
     template<class T> T* as() { return static_cast<T*>(p); }
 };
 
-enum Ev { EV_H2D0, EV_H2D1, EV_BIN0, EV_BIN1, EV_DEN1, EV_NRM0, EV_NRM1, EV_MC0, EV_MC1, EV_DV0, EV_DV1, EV_DM0, EV_DM1, EV_COUNT };
+enum Ev { EV_H2D0, EV_H2D1, EV_BIN0, EV_BIN1, EV_DEN1, EV_NRM0, EV_NRM1, EV_MC0, EV_MC1, EV_DV0, EV_DV1, EV_DM0, EV_DM1, EV_T0, EV_T1, EV_COUNT };
 
 } // namespace
 
@@ -691,6 +691,22 @@ int mms_get_timings(mms_ctx* c, mms_timings* t) {
     t->mc = el(EV_MC0, EV_MC1);
     t->d2h_volume = el(EV_DV0, EV_DV1);
     t->d2h_mesh = el(EV_DM0, EV_DM1);
+    return MMS_OK;
+}
+
+int mms_timer_start(mms_ctx* c) {
+    if (!c) return MMS_ERR_INVALID;
+    DeviceGuard guard(c->device);
+    c->rec(EV_T0);
+    return MMS_OK;
+}
+
+int mms_timer_stop(mms_ctx* c, float* ms) {
+    if (!c || !ms) return MMS_ERR_INVALID;
+    DeviceGuard guard(c->device);
+    c->rec(EV_T1);
+    MMS_CUDA(c, cudaEventSynchronize(c->ev[EV_T1]));
+    MMS_CUDA(c, cudaEventElapsedTime(ms, c->ev[EV_T0], c->ev[EV_T1]));
     return MMS_OK;
 }
 

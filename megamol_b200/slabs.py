@@ -1,0 +1,347 @@
+"""Multi-GPU driver: z-slab sharding with halo, one process per GPU.
+
+Rank g owns marching-cubes cell layers [c_g, c_{g+1}), c_g = floor(g * (sz-1) / G), and computes the density planes
+those cells need: [c_g - 1, c_{g+1} + 1] clipped to the grid (one extra plane on each interior side so that the
+gradient normals equal the unsharded ones).  A particle is needed by every slab its support box [Z-f, Z+f] touches
+(periodic images in cyclic mode).  The ONLY data-path exchanges are
+
+  1. particles:  all-to-all-v of 16-byte xyzr records (each rank starts with a contiguous chunk of the frame);
+                 receivers concatenate in source-rank order, so the global particle order is preserved,
+  2. normalise:  one all-reduce of (min, max)  -- instead of the reference's whole-volume MPI_Allreduce
+                 (plugins/datatools/src/MPIVolumeAggregator.cpp:129),
+  3. mesh:       all-gather of triangle counts + send/recv of the per-slab vertex arrays to rank 0.
+
+torch.distributed is plumbing only (NCCL on the GPUs, gloo in the CPU tests); the compute is libmmsurf.
+The planning functions are pure and are what tests/test_slabs_cpu.py exercises under gloo with world_size 2.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def plan_slabs(sz: int, world: int):
+    """-> list of dicts(cell_z0, cell_nz, z0, nz) per rank."""
+    out = []
+    ncell = sz - 1
+    for g in range(world):
+        c0 = (g * ncell) // world
+        c1 = ((g + 1) * ncell) // world
+        p0 = max(c0 - 1, 0)
+        p1 = min(c1 + 1, sz - 1)  # inclusive
+        if c1 <= c0:  # more ranks than cell layers: this rank idles on an (empty) one-plane slab
+            p0, p1 = min(c0, sz - 1), min(c0, sz - 1)
+        out.append(dict(cell_z0=c0, cell_nz=c1 - c0, z0=p0, nz=p1 - p0 + 1))
+    return out
+
+
+def home_and_filter_z(z, r, zmin, sdz, xp):
+    """Bit-exact fp32 restatement of static_cast<int>((z - minOS)/sliceDist) and (int)ceil(rad/sliceDist)
+    (ParticlesToDensity.cpp:567,575) with array ops (xp = numpy or torch)."""
+    if xp is np:
+        Z = np.trunc((z.astype(np.float32) - np.float32(zmin)) / np.float32(sdz)).astype(np.int64)
+        f = np.ceil(r.astype(np.float32) / np.float32(sdz)).astype(np.int64)
+    else:
+        import torch
+        Z = torch.trunc((z - zmin) / sdz).to(torch.int64)
+        f = torch.ceil(r / sdz).to(torch.int64)
+    return Z, f
+
+
+def destination_masks(Z, f, slabs, sz: int, cyclic_z: bool, xp):
+    """mask[g][i] = particle i is needed by slab g."""
+    masks = []
+    if cyclic_z:
+        Zw = Z % sz  # floor-mod for numpy and torch
+    for s in slabs:
+        lo, hi = s["z0"], s["z0"] + s["nz"] - 1
+        if not cyclic_z:
+            m = (Z + f >= lo) & (Z - f <= hi)
+        else:
+            a, b = Zw - f, Zw + f
+            m = ((b >= lo) & (a <= hi)) | ((b - sz >= lo) & (a - sz <= hi)) | ((b + sz >= lo) & (a + sz <= hi)) | (2 * f + 1 >= sz)
+        masks.append(m)
+    return masks
+
+
+class SlabJob:
+    """The bench/test driver: generates this rank's chunk of the synthetic frame and runs full steps."""
+
+    def __init__(self, w, rank, world, local, iso, radius, sigma=1.0, cyclic=(True, True, True), normalize=True):
+        import torch
+        import megamol_b200 as mm
+        from megamol_b200 import synth
+        self.torch = torch
+        self.w, self.rank, self.world, self.iso, self.radius = w, rank, world, iso, radius
+        self.dev = torch.device("cuda", local)
+        self.normalize = normalize
+        self.cyclic = cyclic
+        # weak scaling: the lattice (and the grid) grows along z with the number of ranks
+        n1 = w["n"]
+        res = list(w["res"])
+        if w["kind"] == "lj":
+            L1 = int(np.ceil(n1 ** (1 / 3) - 1e-9))
+            self.n_total = n1 * world
+            a = np.float32(1.0794)
+            self.lat = (L1, L1, -(-self.n_total // (L1 * L1)))
+            self.box = (float(np.float32(L1) * a), float(np.float32(L1) * a), float(np.float32(self.lat[2]) * a))
+            res[2] = res[2] * world
+        else:
+            self.n_total = n1 * world
+            self.box = (w["box"], w["box"], w["box"] * world)
+            res[2] = res[2] * world
+        self.res = tuple(res)
+        i0 = (self.n_total * rank) // world
+        i1 = (self.n_total * (rank + 1)) // world
+        if w["kind"] == "lj":
+            xyz = self._lj_chunk(i0, i1)
+        else:
+            xyz = synth.uniform_box(self.n_total, 1.0, i0=i0, i1=i1) * np.asarray(self.box, np.float32)
+        self.n_local = i1 - i0
+        # host copy in pinned memory (what an MMPLD reader would fill), device copy for the resident arm
+        self.h_xyz = torch.empty((self.n_local, 3), dtype=torch.float32, pin_memory=True)
+        self.h_xyz.numpy()[:] = xyz
+        self.d_xyz = self.h_xyz.to(self.dev)
+        self.slabs = plan_slabs(self.res[2], world)
+        self.me = self.slabs[rank]
+        self.surf = mm.Surf(local)
+        self.surf.set_grid((0, 0, 0), self.box, self.res, cyclic)
+        if world > 1:
+            self.surf.set_slab(self.me["z0"], self.me["nz"], self.me["cell_z0"], self.me["cell_nz"])
+        self.surf.set_params(mode=0, aggregator=0, normalize=int(normalize), defer_normalize=int(world > 1), sigma=sigma)
+        self.sdz = float(np.float32(self.box[2]) / np.float32(self.res[2] - 1))
+        self._keep = []
+        self.last = {}
+        self.gather_ms = 0.0
+        self.exchange_ms = 0.0
+
+    def _lj_chunk(self, i0, i1):
+        from megamol_b200 import synth
+        Lx, Ly, Lz = self.lat
+        idx = np.arange(i0, i1, dtype=np.int64)
+        lat = (idx % Lx, (idx // Lx) % Ly, idx // (Lx * Ly))
+        out = np.empty((i1 - i0, 3), np.float32)
+        a = np.float32(1.0794)
+        for k in range(3):
+            u = synth.uniform(synth.SEED + 2, i0, i1, k)
+            out[:, k] = (lat[k].astype(np.float32) + np.float32(0.5) + (u * np.float32(2) - np.float32(1)) * np.float32(0.15)) * a
+        return out
+
+    # ---- plumbing ---------------------------------------------------------------------------------------------
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def timed(self, fn, steps):
+        """K steps between barriers; device time (CUDA events on the current torch stream AND the library stream are
+        both drained by the trailing synchronize); returns max over ranks in ms."""
+        torch = self.torch
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        self.surf.timer_start()
+        for _ in range(steps):
+            fn()
+        lib_ms = self.surf.timer_stop()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = max(lib_ms, e0.elapsed_time(e1))
+        if self.world > 1:
+            import torch.distributed as dist
+            t = torch.tensor([ms], device=self.dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        self.barrier()
+        return ms
+
+    def _exchange(self, xyz_dev):
+        """all-to-all-v of the particles by destination slab; returns this rank's [n,3] tensor (source-rank order)."""
+        torch = self.torch
+        import torch.distributed as dist
+        t0 = torch.cuda.Event(enable_timing=True)
+        t1 = torch.cuda.Event(enable_timing=True)
+        t0.record()
+        r = torch.full((xyz_dev.shape[0],), self.radius, device=xyz_dev.device, dtype=torch.float32)
+        Z, f = home_and_filter_z(xyz_dev[:, 2], r, 0.0, self.sdz, torch)
+        masks = destination_masks(Z, f, self.slabs, self.res[2], bool(self.cyclic[2]), torch)
+        parts = [xyz_dev[m] for m in masks]
+        send_counts = torch.tensor([p.shape[0] for p in parts], device=xyz_dev.device, dtype=torch.int64)
+        recv_counts = torch.empty_like(send_counts)
+        dist.all_to_all_single(recv_counts, send_counts)
+        sc, rc = send_counts.tolist(), recv_counts.tolist()
+        send = torch.cat(parts, 0).contiguous()
+        recv = torch.empty((sum(rc), 3), device=xyz_dev.device, dtype=torch.float32)
+        dist.all_to_all_single(recv, send, output_split_sizes=rc, input_split_sizes=sc)
+        t1.record()
+        self._ex_events = (t0, t1)
+        return recv
+
+    def _gather_mesh(self):
+        """all-gather of triangle counts, then the per-slab vertex/normal arrays travel to rank 0 over NCCL."""
+        torch = self.torch
+        import torch.distributed as dist
+        nverts, ppos, pnrm = self.surf.mesh_device()
+        cnt = torch.tensor([nverts], device=self.dev, dtype=torch.int64)
+        allc = [torch.empty_like(cnt) for _ in range(self.world)]
+        dist.all_gather(allc, cnt)
+        counts = [int(c.item()) for c in allc]
+        self.last["tri_counts"] = [c // 3 for c in counts]
+
+        def view(ptr, n):
+            if n == 0:
+                return torch.empty((0,), device=self.dev, dtype=torch.float32)
+            return _tensor_from_ptr(torch, ptr, n * 3, self.dev)
+        mine_p, mine_n = view(ppos, nverts), view(pnrm, nverts)
+        if self.rank == 0:
+            total = sum(counts)
+            if getattr(self, "_gpos", None) is None or self._gpos.numel() < total * 3:
+                self._gpos = torch.empty((total * 3,), device=self.dev, dtype=torch.float32)
+                self._gnrm = torch.empty((total * 3,), device=self.dev, dtype=torch.float32)
+            off = 0
+            ops = []
+            for g, c in enumerate(counts):
+                if g == 0:
+                    self._gpos[:c * 3].copy_(mine_p)
+                    self._gnrm[:c * 3].copy_(mine_n)
+                elif c:
+                    ops.append(dist.P2POp(dist.irecv, self._gpos[off * 3:(off + c) * 3], g))
+                    ops.append(dist.P2POp(dist.irecv, self._gnrm[off * 3:(off + c) * 3], g))
+                off += c
+            if ops:
+                for req in dist.batch_isend_irecv(ops):
+                    req.wait()
+            self.last["gathered_verts"] = total
+        elif nverts:
+            ops = [dist.P2POp(dist.isend, mine_p, 0), dist.P2POp(dist.isend, mine_n, 0)]
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+
+    # ---- steps ------------------------------------------------------------------------------------------------
+    def _compute(self, xyz_ptr, n):
+        s = self.surf
+        s.clear_particles()
+        s.push_particles([dict(vtx=xyz_ptr, vtx_type=1, count=n, global_radius=self.radius)])
+        s.compute_density()
+        if self.world > 1 and self.normalize:
+            import torch.distributed as dist
+            torch = self.torch
+            mn, mx = s.density_range()
+            t = torch.tensor([-mn, mx], device=self.dev, dtype=torch.float32)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            mn, mx = -float(t[0].item()), float(t[1].item())
+            s.normalize(mn, mx)
+        s.extract_isosurface(self.iso)
+
+    def step_device(self):
+        """inputs resident in HBM: (exchange) -> bin -> density -> (range all-reduce, normalise) -> MC -> (mesh gather)"""
+        torch = self.torch
+        if self.world == 1:
+            self._compute(self.d_xyz.data_ptr(), self.n_local)
+            self.surf.synchronize()
+        else:
+            recv = self._exchange(self.d_xyz)
+            torch.cuda.current_stream().synchronize()
+            self._keep = [recv]
+            self._compute(recv.data_ptr(), recv.shape[0])
+            self.surf.synchronize()
+            self._gather_mesh()
+            torch.cuda.current_stream().synchronize()
+        self.last["n_in"] = self.n_local
+
+    def step_e2e(self):
+        """the same through HOST buffers: pinned H2D of this rank's chunk, D2H of its volume slab and of the mesh"""
+        torch = self.torch
+        if self.world == 1:
+            self._compute(self.h_xyz.data_ptr(), self.n_local)
+            self.surf.get_density(copy=False)
+            self.surf.get_mesh(copy=False)
+        else:
+            d = self.h_xyz.to(self.dev, non_blocking=True)
+            recv = self._exchange(d)
+            torch.cuda.current_stream().synchronize()
+            self._keep = [recv, d]
+            self._compute(recv.data_ptr(), recv.shape[0])
+            self.surf.get_density(copy=False)
+            self._gather_mesh()
+            if self.rank == 0:
+                tot = self.last["gathered_verts"] * 3
+                if getattr(self, "_hpos", None) is None or self._hpos.numel() < tot:
+                    self._hpos = torch.empty((tot,), dtype=torch.float32, pin_memory=True)
+                    self._hnrm = torch.empty((tot,), dtype=torch.float32, pin_memory=True)
+                self._hpos[:tot].copy_(self._gpos[:tot], non_blocking=True)
+                self._hnrm[:tot].copy_(self._gnrm[:tot], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+    # ---- accounting -------------------------------------------------------------------------------------------
+    def launches(self):
+        return self.surf.launch_count()
+
+    def stage_times(self):
+        t = self.surf.timings()
+        return {k: round(v, 4) for k, v in t.items()}
+
+    def local_tris(self):
+        n, _, _ = self.surf.mesh_device()
+        return n // 3
+
+    def totals(self):
+        """(particles, voxels, triangles) of the whole job"""
+        tris = self.local_tris()
+        if self.world > 1:
+            import torch.distributed as dist
+            t = self.torch.tensor([tris], device=self.dev, dtype=torch.int64)
+            dist.all_reduce(t)
+            tris = int(t.item())
+        self._tris_total = tris
+        return self.n_total, self.res[0] * self.res[1] * self.res[2], tris
+
+    def _local_alg_bytes(self):
+        """Algorithmic HBM bytes of this rank's step: particles read (12 B xyz) + sorted records written and
+        read (16 B each) + density written and read by MC (4 B each) + 72 B per triangle."""
+        n = self.n_local
+        v = self.res[0] * self.res[1] * self.me["nz"] if self.world > 1 else self.res[0] * self.res[1] * self.res[2]
+        return dict(bin=n * 12 + n * 16, density=n * 16 + v * 4, mc=v * 4 + self.local_tris() * 72, n=n, v=v)
+
+    def pipeline_bytes(self):
+        b = self._local_alg_bytes()
+        return (b["bin"] + b["density"] + b["mc"]) * self.world
+
+    def roofline(self, stage, peak):
+        b = self._local_alg_bytes()
+        cand = {"bin (count+scan+scatter+order)": (stage["bin"], b["bin"]), "density_tile_kernel": (stage["density"], b["density"]),
+                "marching cubes (count+scan+emit)": (stage["mc"], b["mc"])}
+        name = max(cand, key=lambda k: cand[k][0])
+        ms, by = cand[name]
+        ach = by / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+        return {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                "algorithmic_bytes": by, "ms": ms,
+                "per_stage_frac": {k: (v[1] / (v[0] * 1e-3) / 1e9 / peak if v[0] > 0 else None) for k, v in cand.items()}}
+
+    def h2d_bytes(self):
+        return self.n_local * 12 * self.world
+
+    def d2h_bytes(self):
+        v = self.res[0] * self.res[1] * self.res[2]
+        return v * 4 + getattr(self, "_tris_total", 0) * 72
+
+    def describe(self):
+        return (f"{self.w['name']} weak-scaled x{self.world} along z: {self.n_total} particles -> "
+                f"{self.res[0]}x{self.res[1]}x{self.res[2]}, z-slabs with halo, mesh gathered to rank 0 over NCCL")
+
+    def close(self):
+        self.surf.close()
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+            dist.destroy_process_group()
+
+
+def _tensor_from_ptr(torch, ptr, nfloats, device):
+    """Zero-copy float32 view of library-owned device memory (CUDA array interface)."""
+    class _Wrap:
+        pass
+    w = _Wrap()
+    w.__cuda_array_interface__ = {"shape": (nfloats,), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+    return torch.as_tensor(w, device=device)
