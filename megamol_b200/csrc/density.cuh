@@ -1,317 +1,352 @@
-// density.cuh -- density volume from cell-sorted particles, no floating-point atomics, fixed summation order.
+// density.cuh -- density volume from cell-sorted particles: no floating-point atomics, one fixed summation order.
 //
-// density_tile_kernel ("owner-warp splat"): a block owns a 32x16x16-voxel tile kept in shared memory, each
-// of its 8 warps owns a private 16x8x8 sub-tile.  The block streams the particles of all cells whose support
-// can reach the tile (cell rows are contiguous in the sorted array, so this is a handful of coalesced
-// segments) through shared memory in chunks; every warp culls the chunk against its sub-tile (one candidate
-// per lane + ballot) and then walks the survivors IN ORDER, the 32 lanes covering the voxels of the
-// particle's tight support box.  A voxel is only ever touched by its owner warp and candidates are visited
-// in (cell z, cell y, cell x, canonical in-cell) order, so every voxel's sum has one fixed order -- the
-// same for every launch, tile decomposition and z-slab decomposition.
+// density_splat_kernel ("coloured cell splat").  A block owns a 32x16x16-voxel tile in shared memory.  The
+// particles that can reach the tile live in the tile's cells plus one ring of neighbour cells (the cell edge C
+// is chosen on the host so that every support box reaches at most C/2 voxels beyond its home cell).  Cells are
+// coloured 2x2x2 by the parity of their GLOBAL cell coordinates: two different cells of one colour have
+// disjoint footprints, so during one colour phase every warp can splat a different cell with plain
+// load-add-store on shared memory and no two warps ever touch the same voxel.  Inside a cell the particles
+// are walked in their canonical order by ONE warp, the 32 lanes covering the voxels of the particle's tight
+// support box.  Every voxel therefore receives its contributions in the order
+//        (colour phase, canonical in-cell order)
+// which depends on nothing but the data: bit-identical run to run and for every tile / z-slab decomposition.
+// Cells of one phase are handed to warps dynamically (integer counter in shared memory) -- the assignment
+// does not influence any sum.
 //
-// Arithmetic of the P2D-bump mode follows ParticlesToDensity.cpp:577-620 and :472-476 operation by
-// operation with round-to-nearest intrinsics (no FMA contraction):
-//   pos = float(h)*sliceDist + minOS;  d = |pos - p|;  dis = sqrt(dx*dx + dy*dy + dz*dz)
-//   dis >= sigma*rad ? 0 : exp(-1 / (1 - ((1/eps)*dis)^2))
+// Arithmetic of the P2D-bump mode follows ParticlesToDensity.cpp:577-620 and :472-476 with individually
+// rounded operations:   pos = float(h)*sliceDist + minOS;  d = |pos - p|;  dis = sqrt(dx*dx + dy*dy + dz*dz);
+//                       q = (1/eps)*dis;  den = 1 - q*q        -- bit-identical to the reference up to here --
+//                       w = exp(-1/den)  evaluated as ex2(-log2(e) * rcp(den)) on the SFU (|rel err| < 3e-6).
 // h is the UN-wrapped voxel index, so periodic images get the true distance (:605-613).
 #pragma once
 #include "common.cuh"
 
 namespace mms {
 
-constexpr int WTX = 16, WTY = 8, WTZ = 8;       // warp sub-tile
-constexpr int BWX = 2, BWY = 2, BWZ = 2;        // warps per block tile
-constexpr int BTX = WTX * BWX, BTY = WTY * BWY, BTZ = WTZ * BWZ;
-constexpr int DT_WARPS = BWX * BWY * BWZ;
-constexpr int DT_THREADS = DT_WARPS * 32;
-constexpr int WT_SY = 18, WT_SZ = 171;          // padded strides: 3x3x3 lane pattern is bank-conflict free
-constexpr int WT_FLOATS = WT_SZ * WTZ;
-constexpr int DT_CHUNK = DT_THREADS;            // candidates staged per round (one per thread)
-constexpr int DT_MAXSEG = 512;                  // cell-row segments per batch
-constexpr int DT_MAXAXIS = 64;                  // cells per axis in a tile's neighbourhood list
+constexpr int CT_X = 32, CT_Y = 16, CT_Z = 16;       // block tile (voxels)
+constexpr int CT_SY = 35, CT_SZ = 585;               // padded strides (= 3 and 9 mod 32): a 3x3x3 lane pattern hits 27 banks
+constexpr int CT_FLOATS = CT_SZ * CT_Z;
+constexpr int CT_WARPS = 8;
+constexpr int CT_THREADS = CT_WARPS * 32;
+constexpr int CT_MAXAXIS = 16;                       // cells per axis in a tile's neighbourhood (<= 32/4 + 3)
+constexpr int CT_MAXCELLS = 12 * 8 * 8;              // neighbourhood cells (C = 4: at most 11 x 7 x 7)
 
-/** A staged candidate, pre-digested once per block. 16 words. */
-struct Cand {
-    float x, y, z, eps;       // position, kernel radius (P2D: sigma*rad, QS: cut-off)
-    float k0, weight;         // P2D: 1/eps; QS: w_p = -log2(e)/(2 (r*radscale)^2) | aggregator-1 intensity
-    int lox, loy;             // tight support box, lower corner, un-wrapped but shifted into [-s, 2s)
-    int loz;
-    unsigned dims;            // bx | by<<10 | bz<<20   (0 = empty)
-    int offx, offy, offz;     // true un-wrapped voxel index = shifted index + off  (non-zero only for homes outside [0,s))
-    float cr, cg, cb;         // QS colour
+/** A digested particle (per-warp staging, read back with broadcast LDS.128). 16 words. */
+struct Dig {
+    float x, y, z, eps;
+    float k0, weight, f0x, f0y; // k0: P2D 1/eps, QS w_p;  f0*: float(true un-wrapped index of the box's first voxel)
+    float f0z;
+    int base;                   // shared-memory offset of the box's first voxel
+    unsigned dims;              // bx | by<<8 | bz<<16  (0 = nothing to do)
+    unsigned mask27;            // fast path (all dims <= 3): valid lanes of the fixed 3x3x3 lane pattern
+    int l0x, l0y, l0z, pad;     // tile-local index of the box's first voxel (per-voxel-wrap mode: before wrapping)
 };
 
-struct TileShared {
-    float tile[DT_WARPS][WT_FLOATS];
-    Cand cand[DT_CHUNK];
-    unsigned segBegin[DT_MAXSEG];
-    unsigned segPrefix[DT_MAXSEG + 1];
-    int axisCells[3][DT_MAXAXIS];
+struct SplatShared {
+    float tile[CT_FLOATS];
+    Dig dig[CT_WARPS][32];
+    unsigned cellB[CT_MAXCELLS], cellE[CT_MAXCELLS];
+    int axisCells[3][CT_MAXAXIS];
     int axisCount[3];
-    unsigned scanTmp[33];
+    int colList[3][4][CT_MAXAXIS]; // per axis, per colour: positions in axisCells
+    int colCount[3][4];
+    int ncol[3];
+    int phaseCounter[64];
+    int tl0[3], tl1[3];            // tile voxel range (inclusive), clipped to the grid / slab
+    int perVoxelWrap[3];           // degenerate cyclic axis: wrap every voxel instead of choosing one image per particle
 };
 
 /** Ordered, duplicate-free list of the cells along one axis whose particles can reach voxels [t0, t1]. */
-__device__ inline int buildAxisCells(int t0, int t1, int reach, int s, bool cyc, int sh, int nc, int* out) {
+__device__ inline int buildAxisCells(int t0, int t1, int reach, int s, bool cyc, int sh, int nc, int* out, int cap) {
     int a = t0 - reach, b = t1 + reach;
+    int n = 0;
     if (!cyc) {
         a = max(a, 0), b = min(b, s - 1);
-        int n = 0;
-        for (int c = a >> sh; c <= (b >> sh) && n < DT_MAXAXIS; ++c) out[n++] = c;
-        return (b >> sh) - (a >> sh) + 1 > DT_MAXAXIS ? -1 : n;
+        for (int c = a >> sh; c <= (b >> sh); ++c) {
+            if (n >= cap) return -1;
+            out[n++] = c;
+        }
+        return n;
     }
     if (b - a + 1 >= s) { // whole axis, each cell once
-        if (nc > DT_MAXAXIS) return -1;
+        if (nc > cap) return -1;
         for (int c = 0; c < nc; ++c) out[c] = c;
         return nc;
     }
-    // un-wrapped order: high-end image first, then the main piece, then the low-end image
-    int n = 0;
-    int lastAdded = -1; // cells are added in pieces; keep every cell once
+    bool overflow = false;
     auto addRange = [&](int v0, int v1) {
         for (int c = v0 >> sh; c <= (v1 >> sh); ++c) {
             bool dup = false;
             for (int k = 0; k < n; ++k) dup |= (out[k] == c);
-            if (!dup) {
-                if (n >= DT_MAXAXIS) { n = DT_MAXAXIS + 1; return; }
-                out[n++] = c;
-            }
+            if (dup) continue;
+            if (n >= cap) { overflow = true; return; }
+            out[n++] = c;
         }
-        (void)lastAdded;
     };
     if (a < 0) addRange(a + s, s - 1);
-    if (n <= DT_MAXAXIS) addRange(max(a, 0), min(b, s - 1));
-    if (n <= DT_MAXAXIS && b >= s) addRange(0, b - s);
-    return n > DT_MAXAXIS ? -1 : n;
+    addRange(max(a, 0), min(b, s - 1));
+    if (b >= s) addRange(0, b - s);
+    return overflow ? -1 : n;
+}
+
+/** Colour of cell c along one axis: parity, except that an irregular periodic axis (odd cell count or a partial
+ *  last cell) gives its last two cells private colours so that same-coloured cells stay >= one full cell apart
+ *  across the wrap. */
+__device__ __forceinline__ int axisColour(int c, int nc, bool irregular) {
+    if (nc < 3) return min(c, 3);
+    if (!irregular) return c & 1;
+    if (c == nc - 2) return 2;
+    if (c == nc - 1) return 3;
+    return c & 1;
+}
+
+__device__ __forceinline__ float ex2Approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcpApprox(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+/** Contribution of one voxel; returns false if the voxel is outside the kernel support. */
+template<int MODE>
+__device__ __forceinline__ bool kernelValue(float d2, float eps, float k0, float& w) {
+    if (MODE == 0) {
+        const float dis = __fsqrt_rn(d2);
+        if (dis >= eps) return false;
+        const float q = __fmul_rn(k0, dis);
+        const float den = __fsub_rn(1.0f, __fmul_rn(q, q));
+        w = ex2Approx(-1.4426950408889634f * rcpApprox(den));
+        return true;
+    } else {
+        if (!(d2 < __fmul_rn(eps, eps))) return false;
+        w = ex2Approx(__fmul_rn(d2, k0));
+        return true;
+    }
 }
 
 template<int MODE>
-__device__ __forceinline__ void digest(const Geo& g, const float4 p, float auxI, const float4 auxC, Cand& c) {
-    c.x = p.x, c.y = p.y, c.z = p.z;
-    c.weight = auxI;
-    c.cr = auxC.x, c.cg = auxC.y, c.cb = auxC.z;
-    const int H[3] = {homeVoxel(p.x, g.mn[0], g.sd[0]), homeVoxel(p.y, g.mn[1], g.sd[1]), homeVoxel(p.z, g.mn[2], g.sd[2])};
-    const float pos[3] = {p.x, p.y, p.z};
-    float eps;
-    if (MODE == 0) {
-        eps = __fmul_rn(g.sigma, p.w);       // sigma * rad (:526)
-        c.k0 = __fdiv_rn(1.0f, eps);         // (1.0f / epsilon) (:475)
-    } else {
-        const float sr = __fmul_rn(p.w, g.radscale);
-        eps = __fmul_rn(g.gausslim, sr);
-        c.k0 = __fdiv_rn(-1.4426950408889634f, __fmul_rn(__fmul_rn(2.0f, sr), sr));
-    }
-    c.eps = eps;
-    int lo[3], hi[3], off[3];
-    bool empty = false;
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-        // tight bounds: a voxel further than eps along one axis cannot be inside the kernel support.
-        // The slop only has to beat fp32 rounding of this bound; contributions within 0.48% of the
-        // support radius are exactly 0.0f anyway (exp(-x) underflows for x > 104).
-        const float vlo = __fdiv_rn(__fsub_rn(__fsub_rn(pos[a], eps), g.mn[a]), g.sd[a]);
-        const float vhi = __fdiv_rn(__fsub_rn(__fadd_rn(pos[a], eps), g.mn[a]), g.sd[a]);
-        const float slop = fmaxf(fmaxf(fabsf(vlo), fabsf(vhi)), 1.0f) * 2e-6f;
-        int l = __float2int_ru(vlo - slop), h = __float2int_rd(vhi + slop);
-        if (MODE == 0) { // the reference's support box around the home voxel (:573-579)
-            const int f = filterSize(p.w, g.sd[a]);
-            l = max(l, H[a] - f), h = min(h, H[a] + f);
-        }
-        off[a] = 0;
-        if (g.cyc[a]) {
-            if (h - l + 1 > g.s[a]) h = l + g.s[a] - 1; // cannot happen for f <= (s-1)/2; keeps images unique
-            const int k = (H[a] >= 0 && H[a] < g.s[a]) ? 0 : (H[a] - floorMod(H[a], g.s[a]));
-            off[a] = k, l -= k, h -= k;
-        } else {
-            l = max(l, 0), h = min(h, g.s[a] - 1);
-        }
-        if (h < l) empty = true;
-        lo[a] = l, hi[a] = h;
-    }
-    c.lox = lo[0], c.loy = lo[1], c.loz = lo[2];
-    c.offx = off[0], c.offy = off[1], c.offz = off[2];
-    const int bx = hi[0] - lo[0] + 1, by = hi[1] - lo[1] + 1, bz = hi[2] - lo[2] + 1;
-    c.dims = (empty || bx > 1023 || by > 1023 || bz > 1023) ? 0u : (unsigned)bx | ((unsigned)by << 10) | ((unsigned)bz << 20);
-    // boxes wider than 1023 voxels per axis are rejected on the host (MMS_ERR_UNSUPPORTED)
-}
-
-__device__ __forceinline__ bool axisHits(int lo, int n, int w0, int wn, int s, bool cyc) {
-    // does [lo, lo+n) (periodic if cyc; lo in [-s, 2s)) touch [w0, w0+wn)?
-    const int hi = lo + n - 1, w1 = w0 + wn - 1;
-    bool r = hi >= w0 && lo <= w1;
-    if (cyc) r = r || (hi - s >= w0 && lo - s <= w1) || (hi + s >= w0 && lo + s <= w1);
-    return r;
-}
-
-template<int MODE, bool COLOUR>
-__global__ void __launch_bounds__(DT_THREADS) density_tile_kernel(Geo g, DevState* st,
-    const float4* __restrict__ recs, const float* __restrict__ aux, int auxN, const unsigned* __restrict__ cellStart,
-    float* __restrict__ vol, float* __restrict__ rgb) {
+__global__ void __launch_bounds__(CT_THREADS, 3) density_splat_kernel(Geo g, DevState* st, const float4* __restrict__ recs,
+    const float* __restrict__ aux, int auxN, const unsigned* __restrict__ cellStart, float* __restrict__ vol, int reach) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
-    TileShared& sh = *reinterpret_cast<TileShared*>(smemRaw);
+    SplatShared& sh = *reinterpret_cast<SplatShared*>(smemRaw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int bt0[3] = {(int)blockIdx.x * BTX, (int)blockIdx.y * BTY, g.z0 + (int)blockIdx.z * BTZ};
-    const int w0x = bt0[0] + (warp % BWX) * WTX, w0y = bt0[1] + ((warp / BWX) % BWY) * WTY, w0z = bt0[2] + (warp / (BWX * BWY)) * WTZ;
-    float* mine = sh.tile[warp];
-    for (int i = lane; i < WT_FLOATS; i += 32) mine[i] = 0.0f;
-
-    // neighbourhood of the block tile in cell space
+    const int C = 1 << g.cshift;
+    for (int i = tid; i < CT_FLOATS; i += CT_THREADS) sh.tile[i] = 0.0f;
+    if (tid < 64) sh.phaseCounter[tid] = 0;
     if (tid < 3) {
-        const float rmax = __uint_as_float(st->rmaxBits);
-        int reach;
-        if (MODE == 0) {
-            const int f = filterSize(rmax, g.sd[tid]);
-            const int t = __float2int_ru(__fdiv_rn(__fmul_rn(g.sigma, rmax), g.sd[tid])) + 1;
-            reach = min(f, t);
-        } else {
-            reach = __float2int_ru(__fdiv_rn(g.gausslim * g.radscale * rmax, g.sd[tid])) + 2;
+        const int a = tid;
+        const int t0 = (a == 0 ? (int)blockIdx.x * CT_X : a == 1 ? (int)blockIdx.y * CT_Y : g.z0 + (int)blockIdx.z * CT_Z);
+        const int lim = (a == 2) ? g.z0 + g.nz : g.s[a];
+        const int t1 = min(t0 + (a == 0 ? CT_X : a == 1 ? CT_Y : CT_Z), lim) - 1;
+        sh.tl0[a] = t0, sh.tl1[a] = t1;
+        const bool cyc = g.cyc[a] != 0;
+        // one periodic image per particle is enough unless the axis is so short that two images can hit the tile
+        sh.perVoxelWrap[a] = (cyc && g.s[a] < (t1 - t0 + 1) + 2 * reach + 2) ? 1 : 0;
+        const int n = buildAxisCells(t0, t1, reach, g.s[a], cyc, g.cshift, g.nc[a], sh.axisCells[a], CT_MAXAXIS);
+        sh.axisCount[a] = n;
+        const bool irregular = cyc && ((g.nc[a] & 1) || (g.s[a] & (C - 1)));
+        sh.ncol[a] = (g.nc[a] < 3) ? min(g.nc[a], 4) : (irregular ? 4 : 2);
+        for (int c = 0; c < 4; ++c) sh.colCount[a][c] = 0;
+        for (int k = 0; k < n; ++k) {
+            const int col = axisColour(sh.axisCells[a][k], g.nc[a], irregular);
+            sh.colList[a][col][sh.colCount[a][col]++] = k;
         }
-        reach = max(reach, 0);
-        const int hiV = (tid == 2) ? min(bt0[2] + BTZ, g.z0 + g.nz) - 1 : min(bt0[tid] + (tid == 0 ? BTX : BTY), g.s[tid]) - 1;
-        sh.axisCount[tid] = buildAxisCells(bt0[tid], hiV, reach, g.s[tid], g.cyc[tid] != 0, g.cshift, g.nc[tid], sh.axisCells[tid]);
     }
     __syncthreads();
-    const int ncx = sh.axisCount[0], ncy = sh.axisCount[1], ncz = sh.axisCount[2];
-    if ((ncx < 0 || ncy < 0 || ncz < 0) && tid == 0) st->pad[0] = 1u; // neighbourhood list overflow -> host reports it
-    // x cells form at most a few runs of consecutive cell ids; a (y,z) row contributes one segment per run.
-    // Rows are enumerated z-major, then y, then x-run: the canonical candidate order.
-    // (axisCount < 0 -> neighbourhood too large for the list: host guards against it.)
-    int nruns = 0;
-    int runStart[4], runEnd[4];
-    for (int k = 0; k < ncx && nruns < 4; ++k) {
-        const int c = sh.axisCells[0][k];
-        if (nruns > 0 && c == runEnd[nruns - 1] + 1) runEnd[nruns - 1] = c;
-        else { runStart[nruns] = c; runEnd[nruns] = c; ++nruns; }
+    const int nax = sh.axisCount[0], nay = sh.axisCount[1], naz = sh.axisCount[2];
+    if (nax < 0 || nay < 0 || naz < 0 || nax * nay * naz > CT_MAXCELLS) {
+        if (tid == 0) st->pad[0] = 1u; // cannot happen when the host picked the cell size from the reach
+        return;
     }
-    const int nrows = (ncx > 0 && ncy > 0 && ncz > 0) ? ncy * ncz : 0;
-    const int nsegTotal = nrows * nruns;
+    // segment table of the neighbourhood cells
+    for (int i = tid; i < nax * nay * naz; i += CT_THREADS) {
+        const int kx = i % nax, ky = (i / nax) % nay, kz = i / (nax * nay);
+        const size_t cell = sh.axisCells[0][kx] + static_cast<size_t>(g.nc[0]) * (sh.axisCells[1][ky] + static_cast<size_t>(g.nc[1]) * sh.axisCells[2][kz]);
+        sh.cellB[i] = cellStart[cell];
+        sh.cellE[i] = cellStart[cell + 1];
+    }
+    __syncthreads();
 
-    for (int segBase = 0; segBase < nsegTotal; segBase += DT_MAXSEG) {
-        const int nseg = min(DT_MAXSEG, nsegTotal - segBase);
-        __syncthreads();
-        // segment table + prefix sums
-        unsigned carry = 0;
-        for (int b0 = 0; b0 < nseg; b0 += DT_THREADS) {
-            const int sI = b0 + tid;
-            unsigned len = 0, beg = 0;
-            if (sI < nseg) {
-                const int gs = segBase + sI;
-                const int row = gs / nruns, run = gs - row * nruns;
-                const int cz = sh.axisCells[2][row / ncy], cy = sh.axisCells[1][row % ncy];
-                const size_t rowBase = (static_cast<size_t>(cz) * g.nc[1] + cy) * g.nc[0];
-                beg = cellStart[rowBase + runStart[run]];
-                len = cellStart[rowBase + runEnd[run] + 1] - beg;
-                sh.segBegin[sI] = beg;
-            }
-            unsigned total;
-            const unsigned ex = blockExclusiveScan(len, &total, sh.scanTmp);
-            if (sI < nseg) sh.segPrefix[sI] = carry + ex;
-            carry += total;
-        }
-        if (tid == 0) sh.segPrefix[nseg] = carry;
-        __syncthreads();
-        const unsigned ncand = sh.segPrefix[nseg];
+    // per-lane constants of the fixed 3x3x3 pattern
+    const int pix = lane % 3, piy = (lane / 3) % 3, piz = lane / 9;
+    const int plin = pix + piy * CT_SY + piz * CT_SZ;
+    const float pfx = (float)pix, pfy = (float)piy, pfz = (float)piz;
+    const int t0x = sh.tl0[0], t0y = sh.tl0[1], t0z = sh.tl0[2];
+    const int t1x = sh.tl1[0], t1y = sh.tl1[1], t1z = sh.tl1[2];
+    const bool pvx = sh.perVoxelWrap[0] != 0, pvy = sh.perVoxelWrap[1] != 0, pvz = sh.perVoxelWrap[2] != 0;
+    const bool anyPv = pvx | pvy | pvz;
+    const float isdx = __frcp_rn(g.sd[0]), isdy = __frcp_rn(g.sd[1]), isdz = __frcp_rn(g.sd[2]);
+    Dig* myDig = sh.dig[warp];
 
-        for (unsigned chunk = 0; chunk < ncand; chunk += DT_CHUNK) {
-            const unsigned nin = min((unsigned)DT_CHUNK, ncand - chunk);
-            __syncthreads(); // previous chunk fully consumed
-            if ((unsigned)tid < nin) {
-                const unsigned pos = chunk + tid;
-                int lo = 0, hi = nseg; // last segment with prefix <= pos
-                while (hi - lo > 1) {
-                    const int mid = (lo + hi) >> 1;
-                    if (sh.segPrefix[mid] <= pos) lo = mid; else hi = mid;
-                }
-                const unsigned idx = sh.segBegin[lo] + (pos - sh.segPrefix[lo]);
-                const float4 p = recs[idx];
-                float aI = 1.0f;
-                float4 aC = make_float4(1.f, 1.f, 1.f, 1.f);
-                if (auxN == 1) aI = aux[idx];
-                else if (auxN == 4) aC = reinterpret_cast<const float4*>(aux)[idx];
-                digest<MODE>(g, p, aI, aC, sh.cand[tid]);
-            }
-            __syncthreads();
-
-            for (unsigned base = 0; base < nin; base += 32) {
-                const unsigned ci = base + lane;
-                bool hit = false;
-                if (ci < nin) {
-                    const Cand& c = sh.cand[ci];
-                    const unsigned d = c.dims;
-                    hit = d != 0 && axisHits(c.lox, d & 1023, w0x, WTX, g.s[0], g.cyc[0] != 0) &&
-                          axisHits(c.loy, (d >> 10) & 1023, w0y, WTY, g.s[1], g.cyc[1] != 0) &&
-                          axisHits(c.loz, (d >> 20) & 1023, w0z, WTZ, g.s[2], g.cyc[2] != 0);
-                }
-                unsigned mask = __ballot_sync(0xffffffffu, hit);
-                while (mask) {
-                    const int j = __ffs(mask) - 1;
-                    mask &= mask - 1;
-                    const Cand& c = sh.cand[base + j];
-                    const int bx = c.dims & 1023, by = (c.dims >> 10) & 1023, bz = (c.dims >> 20) & 1023;
-                    const int bxy = bx * by, nvox = bxy * bz;
-                    const float rbx = __frcp_rn((float)bx), rbxy = __frcp_rn((float)bxy);
-                    const bool smallBox = nvox <= 4096;
-                    for (int i = lane; i < nvox; i += 32) {
-                        int iz, iy, ix;
-                        if (smallBox) { // exact for these ranges: (i+0.5)/n is never within rounding of an integer
-                            iz = __float2int_rz(((float)i + 0.5f) * rbxy);
-                            const int rem = i - iz * bxy;
-                            iy = __float2int_rz(((float)rem + 0.5f) * rbx);
-                            ix = rem - iy * bx;
-                        } else {
-                            iz = i / bxy;
-                            const int rem = i - iz * bxy;
-                            iy = rem / bx;
-                            ix = rem - iy * bx;
+    const int ncx = sh.ncol[0], ncy = sh.ncol[1], ncz = sh.ncol[2];
+    const int nphase = ncx * ncy * ncz;
+    for (int phase = 0; phase < nphase; ++phase) {
+        const int px = phase % ncx, py = (phase / ncx) % ncy, pz = phase / (ncx * ncy);
+        const int nx = sh.colCount[0][px], ny = sh.colCount[1][py], nz = sh.colCount[2][pz];
+        const int ncell = nx * ny * nz;
+        while (ncell > 0) {
+            int k = 0;
+            if (lane == 0) k = atomicAdd(&sh.phaseCounter[phase], 1);
+            k = __shfl_sync(0xffffffffu, k, 0);
+            if (k >= ncell) break;
+            const int kx = k % nx, ky = (k / nx) % ny, kz = k / (nx * ny);
+            const int ci = sh.colList[0][px][kx] + nax * (sh.colList[1][py][ky] + nay * sh.colList[2][pz][kz]);
+            const unsigned b = sh.cellB[ci], e = sh.cellE[ci];
+            for (unsigned base = b; base < e; base += 32) {
+                const int cnt = min(32u, e - base);
+                if (lane < cnt) {
+                    // ---- digest my particle -------------------------------------------------------------------
+                    const float4 p = recs[base + lane];
+                    Dig d;
+                    d.x = p.x, d.y = p.y, d.z = p.z;
+                    d.weight = (auxN == 1) ? aux[base + lane] : 1.0f;
+                    float eps;
+                    if (MODE == 0) {
+                        eps = __fmul_rn(g.sigma, p.w);   // sigma * rad (:526)
+                        d.k0 = __fdiv_rn(1.0f, eps);     // (1.0f / epsilon) (:475)
+                    } else {
+                        const float sr = __fmul_rn(p.w, g.radscale);
+                        eps = __fmul_rn(g.gausslim, sr);
+                        d.k0 = __fdiv_rn(-1.4426950408889634f, __fmul_rn(__fmul_rn(2.0f, sr), sr));
+                    }
+                    d.eps = eps;
+                    const float pos[3] = {p.x, p.y, p.z};
+                    const float isd[3] = {isdx, isdy, isdz};
+                    const int tl0[3] = {t0x, t0y, t0z}, tl1[3] = {t1x, t1y, t1z};
+                    const bool pv[3] = {pvx, pvy, pvz};
+                    int l0[3], bd[3], tru[3];
+                    bool empty = false;
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) {
+                        // tight bounds of the support along this axis.  The slop only has to beat fp32 rounding of the
+                        // bound itself: contributions within 0.48% of the support radius are exactly 0 (exp(-x), x > 104).
+                        const float aa = pos[a] - g.mn[a];
+                        const float vlo = (aa - eps) * isd[a], vhi = (aa + eps) * isd[a];
+                        const float slop = fmaxf(fmaxf(fabsf(vlo), fabsf(vhi)), 1.0f) * 4e-6f;
+                        int lo = __float2int_ru(vlo - slop), hi = __float2int_rd(vhi + slop);
+                        if (MODE == 0 && g.sigma > 1.0f) { // the reference's box around the home voxel clips the kernel (:573-579)
+                            const int H = homeVoxel(pos[a], g.mn[a], g.sd[a]);
+                            const int f = filterSize(p.w, g.sd[a]);
+                            lo = max(lo, H - f), hi = min(hi, H + f);
                         }
-                        int hx = c.lox + ix, hy = c.loy + iy, hz = c.loz + iz; // shifted un-wrapped index
-                        int tx = hx, ty = hy, tz = hz;
-                        if (g.cyc[0]) tx = hx < 0 ? hx + g.s[0] : (hx >= g.s[0] ? hx - g.s[0] : hx);
-                        if (g.cyc[1]) ty = hy < 0 ? hy + g.s[1] : (hy >= g.s[1] ? hy - g.s[1] : hy);
-                        if (g.cyc[2]) tz = hz < 0 ? hz + g.s[2] : (hz >= g.s[2] ? hz - g.s[2] : hz);
-                        const unsigned lx = tx - w0x, ly = ty - w0y, lz = tz - w0z;
-                        if (lx >= (unsigned)WTX || ly >= (unsigned)WTY || lz >= (unsigned)WTZ) continue;
-                        hx += c.offx, hy += c.offy, hz += c.offz; // the reference's hx/hy/hz
-                        const float px = __fadd_rn(__fmul_rn((float)hx, g.sd[0]), g.mn[0]);
-                        const float py = __fadd_rn(__fmul_rn((float)hy, g.sd[1]), g.mn[1]);
-                        const float pz = __fadd_rn(__fmul_rn((float)hz, g.sd[2]), g.mn[2]);
-                        const float dx = fabsf(__fsub_rn(px, c.x)), dy = fabsf(__fsub_rn(py, c.y)), dz = fabsf(__fsub_rn(pz, c.z));
-                        const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-                        float* cell = mine + lx + ly * WT_SY + lz * WT_SZ;
-                        if (MODE == 0) {
-                            const float dis = __fsqrt_rn(d2);
-                            if (dis >= c.eps) continue;
-                            const float q = __fmul_rn(c.k0, dis);
-                            const float w = expf(__fdiv_rn(-1.0f, __fsub_rn(1.0f, __fmul_rn(q, q))));
-                            *cell = __fadd_rn(*cell, g.agg == 1 ? __fmul_rn(w, c.weight) : w);
+                        hi = min(hi, lo + 2 * reach); // footprint bound the colouring relies on (never binds for sane input)
+                        int off = 0;                  // true index = normalised index + off
+                        if (g.cyc[a]) {
+                            if (lo < 0 || lo >= g.s[a]) {
+                                const int m = floorMod(lo, g.s[a]);
+                                off = lo - m, hi -= off, lo = m;
+                            }
+                            if (pv[a]) { // every voxel wraps individually
+                                l0[a] = lo - tl0[a], bd[a] = hi - lo + 1, tru[a] = lo + off;
+                            } else {
+                                int kk = 0;
+                                if (!(hi >= tl0[a] && lo <= tl1[a])) kk = -g.s[a]; // the image one period below
+                                const int l = max(lo + kk, tl0[a]), h = min(hi + kk, tl1[a]);
+                                l0[a] = l - tl0[a], bd[a] = h - l + 1, tru[a] = l - kk + off;
+                            }
                         } else {
-                            if (!(d2 < __fmul_rn(c.eps, c.eps))) continue;
-                            const float w = exp2f(__fmul_rn(d2, c.k0));
-                            *cell = __fadd_rn(*cell, w);
-                            // colour volume handled by the gather kernel variant (QS mode): see density_gather_kernel
+                            const int l = max(lo, tl0[a]), h = min(hi, tl1[a]);
+                            l0[a] = l - tl0[a], bd[a] = h - l + 1, tru[a] = l;
+                        }
+                        if (bd[a] <= 0) empty = true;
+                    }
+                    d.f0x = (float)tru[0], d.f0y = (float)tru[1], d.f0z = (float)tru[2];
+                    d.base = l0[0] + l0[1] * CT_SY + l0[2] * CT_SZ;
+                    d.l0x = l0[0], d.l0y = l0[1], d.l0z = l0[2], d.pad = 0;
+                    if (empty || bd[0] > 255 || bd[1] > 255 || bd[2] > 255) {
+                        d.dims = 0u, d.mask27 = 0u;
+                    } else {
+                        d.dims = (unsigned)bd[0] | ((unsigned)bd[1] << 8) | ((unsigned)bd[2] << 16);
+                        unsigned m = 0u;
+                        if (bd[0] <= 3 && bd[1] <= 3 && bd[2] <= 3) {
+                            const unsigned mx = bd[0] == 1 ? 0x1249249u : (bd[0] == 2 ? 0x36DB6DBu : 0x7FFFFFFu);
+                            const unsigned my = bd[1] == 1 ? 0x01C0E07u : (bd[1] == 2 ? 0x0FC7E3Fu : 0x7FFFFFFu);
+                            const unsigned mz = bd[2] == 1 ? 0x00001FFu : (bd[2] == 2 ? 0x003FFFFu : 0x7FFFFFFu);
+                            m = mx & my & mz;
+                        }
+                        d.mask27 = m;
+                    }
+                    myDig[lane] = d;
+                }
+                __syncwarp();
+                for (int j = 0; j < cnt; ++j) {
+                    const float4 A = reinterpret_cast<const float4*>(&myDig[j])[0];
+                    const float4 B = reinterpret_cast<const float4*>(&myDig[j])[1];
+                    const float4 Cc = reinterpret_cast<const float4*>(&myDig[j])[2];
+                    const unsigned dims = __float_as_uint(Cc.z), mask27 = __float_as_uint(Cc.w);
+                    if (dims == 0u) continue;
+                    const int sbase = __float_as_int(Cc.y);
+                    if (mask27 != 0u && !anyPv) {
+                        // ---- fast path: box <= 3x3x3, one pass, fixed lane pattern ------------------------------------
+                        if ((mask27 >> lane) & 1u) {
+                            const float vx = __fadd_rn(__fmul_rn(B.z + pfx, g.sd[0]), g.mn[0]);
+                            const float vy = __fadd_rn(__fmul_rn(B.w + pfy, g.sd[1]), g.mn[1]);
+                            const float vz = __fadd_rn(__fmul_rn(Cc.x + pfz, g.sd[2]), g.mn[2]);
+                            const float dx = __fsub_rn(vx, A.x), dy = __fsub_rn(vy, A.y), dz = __fsub_rn(vz, A.z);
+                            const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+                            float w;
+                            if (kernelValue<MODE>(d2, A.w, B.x, w)) {
+                                float* cell = sh.tile + sbase + plin;
+                                *cell = __fadd_rn(*cell, (MODE == 0 && g.agg == 1) ? __fmul_rn(w, B.y) : w);
+                            }
+                        }
+                    } else {
+                        // ---- general path: any box, optional per-voxel wrap ------------------------------------------
+                        const int4 L0 = reinterpret_cast<const int4*>(&myDig[j])[3];
+                        const int bx = dims & 255, by = (dims >> 8) & 255, bz = dims >> 16;
+                        const int bxy = bx * by, nvox = bxy * bz;
+                        const float rbx = __frcp_rn((float)bx), rbxy = __frcp_rn((float)bxy);
+                        for (int i = lane; i < nvox; i += 32) {
+                            // exact for these ranges: (i+0.5)/n is never within rounding of an integer
+                            const int iz = __float2int_rz(((float)i + 0.5f) * rbxy);
+                            const int rem = i - iz * bxy;
+                            const int iy = __float2int_rz(((float)rem + 0.5f) * rbx);
+                            const int ix = rem - iy * bx;
+                            int sidx = sbase + ix + iy * CT_SY + iz * CT_SZ;
+                            if (anyPv) {
+                                int lx = L0.x + ix, ly = L0.y + iy, lz = L0.z + iz;
+                                if (pvx && lx + t0x >= g.s[0]) lx -= g.s[0];
+                                if (pvy && ly + t0y >= g.s[1]) ly -= g.s[1];
+                                if (pvz && lz + t0z >= g.s[2]) lz -= g.s[2];
+                                if ((unsigned)lx > (unsigned)(t1x - t0x) || (unsigned)ly > (unsigned)(t1y - t0y) || (unsigned)lz > (unsigned)(t1z - t0z)) continue;
+                                sidx = lx + ly * CT_SY + lz * CT_SZ;
+                            }
+                            const float vx = __fadd_rn(__fmul_rn(B.z + (float)ix, g.sd[0]), g.mn[0]);
+                            const float vy = __fadd_rn(__fmul_rn(B.w + (float)iy, g.sd[1]), g.mn[1]);
+                            const float vz = __fadd_rn(__fmul_rn(Cc.x + (float)iz, g.sd[2]), g.mn[2]);
+                            const float dx = __fsub_rn(vx, A.x), dy = __fsub_rn(vy, A.y), dz = __fsub_rn(vz, A.z);
+                            const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+                            float w;
+                            if (kernelValue<MODE>(d2, A.w, B.x, w)) {
+                                float* cell = sh.tile + sidx;
+                                *cell = __fadd_rn(*cell, (MODE == 0 && g.agg == 1) ? __fmul_rn(w, B.y) : w);
+                            }
                         }
                     }
-                    __syncwarp(); // the next candidate may touch voxels this one wrote from other lanes
+                    __syncwarp(); // the next particle of this cell may touch the same voxels from other lanes
                 }
+                __syncwarp();
             }
         }
+        __syncthreads(); // colour phases are ordered
     }
-    __syncthreads();
 
     // write-out: rows of 32 consecutive voxels (128 B), plus the block's min/max
     float vmin = INFINITY, vmax = -INFINITY;
-    const int zEnd = g.z0 + g.nz;
-    for (int r = warp; r < BTY * BTZ; r += DT_WARPS) {
-        const int ly = r % BTY, lz = r / BTY;
-        const int x = bt0[0] + lane, y = bt0[1] + ly, z = bt0[2] + lz;
-        if (x < g.s[0] && y < g.s[1] && z < zEnd) {
-            const int w = (lane / WTX) + BWX * ((ly / WTY) + BWY * (lz / WTZ));
-            const float v = sh.tile[w][(lane % WTX) + (ly % WTY) * WT_SY + (lz % WTZ) * WT_SZ];
+    for (int r = warp; r < CT_Y * CT_Z; r += CT_WARPS) {
+        const int ly = r % CT_Y, lz = r / CT_Y;
+        const int x = t0x + lane, y = t0y + ly, z = t0z + lz;
+        if (x <= t1x && y <= t1y && z <= t1z) {
+            const float v = sh.tile[lane + ly * CT_SY + lz * CT_SZ];
             vol[x + static_cast<size_t>(g.s[0]) * (y + static_cast<size_t>(g.s[1]) * (z - g.z0))] = v;
             vmin = fminf(vmin, v), vmax = fmaxf(vmax, v);
         }
     }
-    unsigned kmin = __reduce_min_sync(0xffffffffu, floatKey(vmin)), kmax = __reduce_max_sync(0xffffffffu, floatKey(vmax));
+    const unsigned kmin = __reduce_min_sync(0xffffffffu, floatKey(vmin)), kmax = __reduce_max_sync(0xffffffffu, floatKey(vmax));
     if (lane == 0 && kmin <= kmax) {
         atomicMin(&st->minKey, kmin);
         atomicMax(&st->maxKey, kmax);
@@ -322,6 +357,18 @@ __global__ void __launch_bounds__(256) normalize_kernel(float* __restrict__ vol,
     const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
     for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
         vol[i] = __fmul_rn(__fsub_rn(vol[i], mn), rcp);
+}
+
+/** Largest radius over a list with per-particle radii (decides the cell size on the host). */
+__global__ void __launch_bounds__(256) radius_max_kernel(ListDev l, DevState* st) {
+    const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
+    float rmax = 0.0f;
+    for (unsigned long long j = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; j < l.count; j += stride) {
+        const float r = fetchParticle(l, j).w;
+        if (r > 0.0f && isfinite(r)) rmax = fmaxf(rmax, r);
+    }
+    rmax = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(rmax)));
+    if ((threadIdx.x & 31) == 0 && rmax > 0.0f) atomicMax(&st->rmaxBits, __float_as_uint(rmax));
 }
 
 } // namespace mms

@@ -95,6 +95,7 @@ struct mms_ctx {
     bool haveDensity = false, haveMesh = false, normalized = false;
     unsigned long long ntris = 0;
     unsigned long long launches = 0;
+    int cshift = 2, reach = 2;
 
     DevBuf cellCount, cellStart, cursor, tileSums, recsA, recsB, auxA, auxB, vol, rgb, segCount, segOffset, meshPos, meshNrm,
         meshCol, triCount, home, dstate;
@@ -171,7 +172,7 @@ Geo makeGeo(const mms_ctx* c) {
         g.cyc[a] = c->grid.cyclic[a] != 0;
     }
     g.z0 = c->z0, g.nz = c->nz;
-    g.cshift = 2;
+    g.cshift = c->cshift;
     for (int a = 0; a < 3; ++a) g.nc[a] = (g.s[a] + (1 << g.cshift) - 1) >> g.cshift;
     g.sigma = c->params.sigma;
     g.agg = c->params.aggregator;
@@ -251,8 +252,8 @@ int mms_create(mms_ctx** out, const mms_config* cfg) {
     c->params.normalize = 1;
     c->params.radscale = 1.0f;
     c->params.gausslim = 3.0f;
-    cudaFuncSetAttribute(density_tile_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileShared));
-    cudaFuncSetAttribute(density_tile_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileShared));
+    cudaFuncSetAttribute(density_splat_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SplatShared));
+    cudaFuncSetAttribute(density_splat_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SplatShared));
     cudaFuncSetAttribute(mc_emit_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(McEmitShared));
     if (!c->dstate.ensure(sizeof(DevState)) || !c->hState.ensure(sizeof(DevState))) {
         g_createError = "allocation of the state block failed";
@@ -416,6 +417,42 @@ int mms_compute_density(mms_ctx* c) {
     if (!c || !c->haveGrid) return c ? c->fail(MMS_ERR_INVALID, "mms_set_grid has not been called") : MMS_ERR_INVALID;
     if (c->nparticles >= (1ull << 32) - 1) return c->fail(MMS_ERR_UNSUPPORTED, "2^32 or more particles per context");
     DeviceGuard guard(c->device);
+    cudaStream_t st = c->stream;
+    c->rec(EV_BIN0);
+    init_state_kernel<<<1, 1, 0, st>>>(c->dstate.as<DevState>());
+    ++c->launches;
+    // ---- largest support radius -> reach in voxels -> cell size (the colouring needs reach <= cell/2) ----------
+    {
+        float rmax = 0.0f;
+        bool perParticle = false;
+        for (const ListDev& l : c->lists) {
+            if (l.vtype == MMS_VERT_FLOAT_XYZR) perParticle = true;
+            else if (l.grad > rmax && std::isfinite(l.grad)) rmax = l.grad;
+        }
+        if (perParticle) {
+            for (const ListDev& l : c->lists)
+                if (l.vtype == MMS_VERT_FLOAT_XYZR) {
+                    radius_max_kernel<<<gridFor(l.count, 256, c->smCount * 16), 256, 0, st>>>(l, c->dstate.as<DevState>());
+                    ++c->launches;
+                }
+            MMS_CUDA(c, cudaMemcpyAsync(c->hState.p, c->dstate.p, sizeof(DevState), cudaMemcpyDeviceToHost, st));
+            MMS_CUDA(c, cudaStreamSynchronize(st));
+            float r = 0.0f;
+            const unsigned bits = c->hState.as<DevState>()->rmaxBits;
+            std::memcpy(&r, &bits, 4);
+            rmax = std::max(rmax, r);
+        }
+        const Geo g0 = makeGeo(c);
+        const float epsMax = (c->params.mode == MMS_MODE_P2D_BUMP) ? c->params.sigma * rmax : c->params.gausslim * c->params.radscale * rmax;
+        int need = 1;
+        for (int a = 0; a < 3; ++a) need = std::max(need, static_cast<int>(std::ceil(epsMax / g0.sd[a] + 0.02f)));
+        if (need <= 2) c->cshift = 2;
+        else if (need <= 4) c->cshift = 3;
+        else if (need <= 8) c->cshift = 4;
+        else
+            return c->fail(MMS_ERR_UNSUPPORTED, "kernel support of %d voxels exceeds what the splat kernel handles (8); the wide-support gather kernel is not built yet", need);
+        c->reach = need;
+    }
     const Geo g = makeGeo(c);
     const size_t ncells = static_cast<size_t>(g.nc[0]) * g.nc[1] * g.nc[2];
     const size_t nvox = static_cast<size_t>(g.s[0]) * g.s[1] * g.nz;
@@ -433,10 +470,6 @@ int mms_compute_density(mms_ctx* c) {
         if (!c->home.ensure(std::max<size_t>(n, 1) * 12)) return c->fail(MMS_ERR_NOMEM, "device allocation failed (home voxels)");
         homeOut = c->home.as<int>();
     }
-    cudaStream_t st = c->stream;
-    c->rec(EV_BIN0);
-    init_state_kernel<<<1, 1, 0, st>>>(c->dstate.as<DevState>());
-    ++c->launches;
     MMS_CUDA(c, cudaMemsetAsync(c->cellCount.p, 0, ncells * 4, st));
     const int cap = c->smCount * 16;
     for (const ListDev& l : c->lists) {
@@ -457,13 +490,13 @@ int mms_compute_density(mms_ctx* c) {
         ++c->launches;
     }
     c->rec(EV_BIN1);
-    dim3 grid((g.s[0] + BTX - 1) / BTX, (g.s[1] + BTY - 1) / BTY, (g.nz + BTZ - 1) / BTZ);
+    dim3 grid((g.s[0] + CT_X - 1) / CT_X, (g.s[1] + CT_Y - 1) / CT_Y, (g.nz + CT_Z - 1) / CT_Z);
     if (g.mode == 0)
-        density_tile_kernel<0, false><<<grid, DT_THREADS, sizeof(TileShared), st>>>(g, c->dstate.as<DevState>(), c->recsB.as<float4>(),
-            c->auxB.as<float>(), auxN, c->cellStart.as<unsigned>(), c->vol.as<float>(), nullptr);
+        density_splat_kernel<0><<<grid, CT_THREADS, sizeof(SplatShared), st>>>(g, c->dstate.as<DevState>(), c->recsB.as<float4>(),
+            c->auxB.as<float>(), auxN, c->cellStart.as<unsigned>(), c->vol.as<float>(), c->reach);
     else
-        density_tile_kernel<1, false><<<grid, DT_THREADS, sizeof(TileShared), st>>>(g, c->dstate.as<DevState>(), c->recsB.as<float4>(),
-            c->auxB.as<float>(), auxN, c->cellStart.as<unsigned>(), c->vol.as<float>(), nullptr);
+        density_splat_kernel<1><<<grid, CT_THREADS, sizeof(SplatShared), st>>>(g, c->dstate.as<DevState>(), c->recsB.as<float4>(),
+            c->auxB.as<float>(), auxN, c->cellStart.as<unsigned>(), c->vol.as<float>(), c->reach);
     ++c->launches;
     c->rec(EV_DEN1);
     c->normalized = false;
@@ -485,7 +518,7 @@ static int checkDeviceError(mms_ctx* c) {
     MMS_CUDA(c, cudaStreamSynchronize(c->stream));
     const DevState* hs = c->hState.as<DevState>();
     if (hs->pad[0] != 0)
-        return c->fail(MMS_ERR_UNSUPPORTED, "support radius too large for the tile kernel's neighbourhood list (reach > %d cells per axis)", DT_MAXAXIS);
+        return c->fail(MMS_ERR_UNSUPPORTED, "internal error: the splat kernel's neighbourhood list overflowed (%d cells per axis)", CT_MAXAXIS);
     return MMS_OK;
 }
 
