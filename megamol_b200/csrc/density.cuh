@@ -51,7 +51,9 @@ struct SplatShared {
     int colList[3][4][CT_MAXAXIS]; // per axis, per colour: positions in axisCells
     int colCount[3][4];
     int ncol[3];
-    int phaseCounter[64];
+    int phaseCount[64];            // non-empty cells per colour phase
+    int phaseStart[65];
+    unsigned short phaseCells[CT_MAXCELLS];
     int tl0[3], tl1[3];            // tile voxel range (inclusive), clipped to the grid / slab
     int perVoxelWrap[3];           // degenerate cyclic axis: wrap every voxel instead of choosing one image per particle
 };
@@ -136,7 +138,7 @@ __global__ void __launch_bounds__(CT_THREADS, 3) density_splat_kernel(Geo g, Dev
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int C = 1 << g.cshift;
     for (int i = tid; i < CT_FLOATS; i += CT_THREADS) sh.tile[i] = 0.0f;
-    if (tid < 64) sh.phaseCounter[tid] = 0;
+    if (tid < 64) sh.phaseCount[tid] = 0;
     if (tid < 3) {
         const int a = tid;
         const int t0 = (a == 0 ? (int)blockIdx.x * CT_X : a == 1 ? (int)blockIdx.y * CT_Y : g.z0 + (int)blockIdx.z * CT_Z);
@@ -162,12 +164,46 @@ __global__ void __launch_bounds__(CT_THREADS, 3) density_splat_kernel(Geo g, Dev
         if (tid == 0) st->pad[0] = 1u; // cannot happen when the host picked the cell size from the reach
         return;
     }
-    // segment table of the neighbourhood cells
-    for (int i = tid; i < nax * nay * naz; i += CT_THREADS) {
+    // segment table of the neighbourhood cells + per-phase lists of the non-empty ones (order inside a phase is free:
+    // same-coloured cells never touch the same voxel)
+    const int ncx = sh.ncol[0], ncy = sh.ncol[1], ncz = sh.ncol[2];
+    const int nphase = ncx * ncy * ncz;
+    const int nneigh = nax * nay * naz;
+    for (int i = tid; i < nneigh; i += CT_THREADS) {
         const int kx = i % nax, ky = (i / nax) % nay, kz = i / (nax * nay);
-        const size_t cell = sh.axisCells[0][kx] + static_cast<size_t>(g.nc[0]) * (sh.axisCells[1][ky] + static_cast<size_t>(g.nc[1]) * sh.axisCells[2][kz]);
-        sh.cellB[i] = cellStart[cell];
-        sh.cellE[i] = cellStart[cell + 1];
+        const int cxg = sh.axisCells[0][kx], cyg = sh.axisCells[1][ky], czg = sh.axisCells[2][kz];
+        const size_t cell = cxg + static_cast<size_t>(g.nc[0]) * (cyg + static_cast<size_t>(g.nc[1]) * czg);
+        const unsigned b = cellStart[cell], e = cellStart[cell + 1];
+        sh.cellB[i] = b;
+        sh.cellE[i] = e;
+        if (e > b) {
+            const bool irx = g.cyc[0] && ((g.nc[0] & 1) || (g.s[0] & (C - 1))), iry = g.cyc[1] && ((g.nc[1] & 1) || (g.s[1] & (C - 1))),
+                       irz = g.cyc[2] && ((g.nc[2] & 1) || (g.s[2] & (C - 1)));
+            const int ph = axisColour(cxg, g.nc[0], irx) + ncx * (axisColour(cyg, g.nc[1], iry) + ncy * axisColour(czg, g.nc[2], irz));
+            atomicAdd(&sh.phaseCount[ph], 1);
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int acc = 0;
+        for (int p = 0; p < nphase; ++p) {
+            sh.phaseStart[p] = acc;
+            acc += sh.phaseCount[p];
+            sh.phaseCount[p] = 0;
+        }
+        sh.phaseStart[nphase] = acc;
+    }
+    __syncthreads();
+    for (int i = tid; i < nneigh; i += CT_THREADS) {
+        if (sh.cellE[i] > sh.cellB[i]) {
+            const int kx = i % nax, ky = (i / nax) % nay, kz = i / (nax * nay);
+            const int cxg = sh.axisCells[0][kx], cyg = sh.axisCells[1][ky], czg = sh.axisCells[2][kz];
+            const bool irx = g.cyc[0] && ((g.nc[0] & 1) || (g.s[0] & (C - 1))), iry = g.cyc[1] && ((g.nc[1] & 1) || (g.s[1] & (C - 1))),
+                       irz = g.cyc[2] && ((g.nc[2] & 1) || (g.s[2] & (C - 1)));
+            const int ph = axisColour(cxg, g.nc[0], irx) + ncx * (axisColour(cyg, g.nc[1], iry) + ncy * axisColour(czg, g.nc[2], irz));
+            const int slot = atomicAdd(&sh.phaseCount[ph], 1);
+            sh.phaseCells[sh.phaseStart[ph] + slot] = static_cast<unsigned short>(i);
+        }
     }
     __syncthreads();
 
@@ -182,28 +218,32 @@ __global__ void __launch_bounds__(CT_THREADS, 3) density_splat_kernel(Geo g, Dev
     const float isdx = __frcp_rn(g.sd[0]), isdy = __frcp_rn(g.sd[1]), isdz = __frcp_rn(g.sd[2]);
     Dig* myDig = sh.dig[warp];
 
-    const int ncx = sh.ncol[0], ncy = sh.ncol[1], ncz = sh.ncol[2];
-    const int nphase = ncx * ncy * ncz;
     for (int phase = 0; phase < nphase; ++phase) {
-        const int px = phase % ncx, py = (phase / ncx) % ncy, pz = phase / (ncx * ncy);
-        const int nx = sh.colCount[0][px], ny = sh.colCount[1][py], nz = sh.colCount[2][pz];
-        const int ncell = nx * ny * nz;
-        while (ncell > 0) {
-            int k = 0;
-            if (lane == 0) k = atomicAdd(&sh.phaseCounter[phase], 1);
-            k = __shfl_sync(0xffffffffu, k, 0);
-            if (k >= ncell) break;
-            const int kx = k % nx, ky = (k / nx) % ny, kz = k / (nx * ny);
-            const int ci = sh.colList[0][px][kx] + nax * (sh.colList[1][py][ky] + nay * sh.colList[2][pz][kz]);
-            const unsigned b = sh.cellB[ci], e = sh.cellE[ci];
-            for (unsigned base = b; base < e; base += 32) {
-                const int cnt = min(32u, e - base);
+        const int pBeg = sh.phaseStart[phase], pEnd = sh.phaseStart[phase + 1];
+        // this warp's cells of the phase: pBeg + warp, + CT_WARPS, ...  A chunk = up to 32 particles from consecutive
+        // cells of that sequence (a cell may continue in the next chunk); particles are then walked in sequence order.
+        int cur = pBeg + warp;
+        unsigned curOff = 0;
+        while (cur < pEnd) {
+            int filled = 0;
+            unsigned src = 0xffffffffu;
+            while (filled < 32 && cur < pEnd) {
+                const int ci = sh.phaseCells[cur];
+                const unsigned b = sh.cellB[ci] + curOff, e = sh.cellE[ci];
+                const int take = min(32 - filled, (int)(e - b));
+                if (lane >= filled && lane < filled + take) src = b + (lane - filled);
+                filled += take;
+                if (b + take == e) { cur += CT_WARPS; curOff = 0; }
+                else curOff += take;
+            }
+            {
+                const int cnt = filled;
                 if (lane < cnt) {
                     // ---- digest my particle -------------------------------------------------------------------
-                    const float4 p = recs[base + lane];
+                    const float4 p = recs[src];
                     Dig d;
                     d.x = p.x, d.y = p.y, d.z = p.z;
-                    d.weight = (auxN == 1) ? aux[base + lane] : 1.0f;
+                    d.weight = (auxN == 1) ? aux[src] : 1.0f;
                     float eps;
                     if (MODE == 0) {
                         eps = __fmul_rn(g.sigma, p.w);   // sigma * rad (:526)
