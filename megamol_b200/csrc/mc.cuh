@@ -4,10 +4,15 @@
 //                     trisoup::volumetrics::MarchingCubeTables, MarchingCubeTables.cpp:11-16,58,278) and sum the
 //                     triangle counts of each 32-cell x-segment with a warp reduction
 //   (exclusive scan of the segment counts: scan.cuh -> triangle offsets in CELL-LINEAR order)
-//   mc_emit_kernel    active tiles only: stage density (+1 halo for gradients) in shared memory, build
-//                     {f, grad} per node once, classify again, warp-level prefix scan of the per-cell counts,
-//                     interpolate vertices/normals, compact them in shared memory and stream them out with
-//                     fully coalesced stores.
+//   mc_emit_kernel    active tiles only (32x8x2 cells):
+//                       A  stage density + one-node halo in shared memory (coalesced rows)
+//                       B  find the crossed grid edges of the tile, compact them (ballot), and compute each crossed
+//                          edge's vertex ONCE with full lanes: interpolation parameter, position coordinate,
+//                          gradient normal -> one float4 record per edge in shared memory
+//                       C  per 32-cell row: classify, warp-level prefix scan of the per-cell triangle counts, then the
+//                          row's triangle corners are FLATTENED over the lanes (corner j of the row -> lane j mod 32):
+//                          each lane looks up the edge record and writes 3+3 floats; consecutive lanes write
+//                          consecutive 12-byte pieces, so every warp store covers one contiguous span of the output.
 // Output order = cell-linear (x fastest, then y, then z), inside a cell the table's order: independent of the
 // tile shape and of the z-slab decomposition.
 #pragma once
@@ -19,12 +24,6 @@ __constant__ unsigned long long kCaseWords[256] = {
 #include "mc_case_words.inc"
 };
 
-constexpr int MCX = 32, MCY = 8, MCZ = 4; // cells per block tile; one warp per (y,z) row of 32 cells
-constexpr int MC_THREADS = 256;
-constexpr int MC_NX = MCX + 1, MC_NY = MCY + 1, MC_NZ = MCZ + 1;       // nodes of the tile's cells
-constexpr int MC_HX = MCX + 3, MC_HY = MCY + 3, MC_HZ = MCZ + 3;       // + gradient halo
-constexpr int MC_STAGE = 64;                                            // triangles staged per warp round
-
 struct McGeo {
     int sx, sy;        // volume resolution in x, y
     int nzPlanes;      // planes in the slab volume
@@ -34,17 +33,16 @@ struct McGeo {
     int cz0, cnz;      // cell layers [cz0, cz0+cnz) in GLOBAL z handled by this context
     int nsegx;         // ceil(cx / 32)
     float org[3], sd[3];
+    float rinv[3][3];  // rinv[a][n] = 1/(n*sd[a]), n = 1, 2 (gradient: one-sided / central)
     float iso;
 };
 
-// per edge: low corner (dx,dy,dz) and axis, 5 bits each: dx | dy<<1 | dz<<2 | axis<<3
-//  e0 (0,0,0)x  e1 (1,0,0)y  e2 (0,1,0)x  e3 (0,0,0)y  e4 (0,0,1)x  e5 (1,0,1)y  e6 (0,1,1)x  e7 (0,0,1)y
-//  e8 (0,0,0)z  e9 (1,0,0)z  e10 (1,1,0)z e11 (0,1,0)z           (MarchingCubeTables.cpp:15-16, low node first)
-__device__ __forceinline__ unsigned edgeCode(int e) {
-    const unsigned long long codes = (0ull) | (9ull << 5) | (2ull << 10) | (8ull << 15) | (4ull << 20) | (13ull << 25) |
-                                     (6ull << 30) | (12ull << 35) | (16ull << 40) | (17ull << 45) | (19ull << 50) | (18ull << 55);
-    return static_cast<unsigned>(codes >> (5 * e)) & 31u;
-}
+// ---------------------------------------------------------------------------------------------------------------
+// count
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int MCX = 32, MCY = 8, MCZ = 4; // cells per block tile of the count kernel
+constexpr int MC_THREADS = 256;
+constexpr int MC_NX = MCX + 1, MC_NY = MCY + 1, MC_NZ = MCZ + 1;
 
 __device__ __forceinline__ int cubeIndexSmem(const float* f, int strideY, int strideZ, float iso) {
     // f points at corner 0; corners: (0,0,0) (1,0,0) (1,1,0) (0,1,0) (0,0,1) (1,0,1) (1,1,1) (0,1,1)
@@ -64,15 +62,17 @@ __global__ void __launch_bounds__(MC_THREADS) mc_count_kernel(McGeo m, const flo
     unsigned char* __restrict__ triCount) {
     __shared__ float f[MC_NZ][MC_NY][MC_NX + 1];
     const int x0 = blockIdx.x * MCX, y0 = blockIdx.y * MCY, zc0 = m.cz0 + blockIdx.z * MCZ; // global cell coords
-    // load nodes (clamped; clamped duplicates only feed cells that are masked out below)
-    for (int i = threadIdx.x; i < MC_NZ * MC_NY * MC_NX; i += MC_THREADS) {
-        const int ix = i % MC_NX, iy = (i / MC_NX) % MC_NY, iz = i / (MC_NX * MC_NY);
-        const int x = min(x0 + ix, m.sx - 1), y = min(y0 + iy, m.sy - 1);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // rows of 33 nodes, one warp per row (clamped; clamped duplicates only feed cells that are masked out below)
+    for (int r = warp; r < MC_NZ * MC_NY; r += MC_THREADS / 32) {
+        const int iy = r % MC_NY, iz = r / MC_NY;
+        const int y = min(y0 + iy, m.sy - 1);
         const int zl = min(zc0 + iz - m.zPlane0, m.nzPlanes - 1);
-        f[iz][iy][ix] = vol[x + static_cast<size_t>(m.sx) * (y + static_cast<size_t>(m.sy) * zl)];
+        const float* row = vol + static_cast<size_t>(m.sx) * (y + static_cast<size_t>(m.sy) * zl);
+        f[iz][iy][lane] = row[min(x0 + lane, m.sx - 1)];
+        if (lane == 0) f[iz][iy][32] = row[min(x0 + 32, m.sx - 1)];
     }
     __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int r = warp; r < MCY * MCZ; r += MC_THREADS / 32) {
         const int ly = r % MCY, lz = r / MCY;
         const int cxi = x0 + lane, cyi = y0 + ly, czi = zc0 + lz;
@@ -88,27 +88,57 @@ __global__ void __launch_bounds__(MC_THREADS) mc_count_kernel(McGeo m, const flo
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// emit
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int EX = 32, EY = 8, EZ = 2;                      // cells per block tile
+constexpr int ENX = EX + 1, ENY = EY + 1, ENZ = EZ + 1;     // nodes
+constexpr int EHX = EX + 3, EHY = EY + 3, EHZ = EZ + 3;     // nodes + gradient halo
+constexpr int EHXP = EHX + 1;                               // padded row
+constexpr int E_XEDGES = ENZ * ENY * EX;                    // 864  x-edges: ix < 32
+constexpr int E_YEDGES = ENZ * EY * ENX;                    // 792  y-edges: iy < 8
+constexpr int E_ZEDGES = EZ * ENY * ENX;                    // 594  z-edges: iz < 2
+constexpr int E_YBASE = E_XEDGES, E_ZBASE = E_XEDGES + E_YEDGES, E_EDGES = E_XEDGES + E_YEDGES + E_ZEDGES;
+constexpr int E_MAXROWTRIS = 160;
+
 struct McEmitShared {
-    float4 node[MC_NZ][MC_NY][MC_NX];            // f, gx, gy, gz
-    float halo[MC_HZ][MC_HY][MC_HX + 1];
-    float stagePos[MC_THREADS / 32][MC_STAGE * 9];
-    float stageNrm[MC_THREADS / 32][MC_STAGE * 9];
+    float4 edge[E_EDGES];               // {interpolated coordinate along the edge's axis, nx, ny, nz}
+    float halo[EHZ][EHY][EHXP];
+    unsigned short crossList[E_EDGES];
+    unsigned char triOwner[MC_THREADS / 32][E_MAXROWTRIS];
+    float tabX[ENX], tabY[ENY], tabZ[ENZ]; // node positions float(idx)*sd + origin (ParticlesToDensity.cpp:605)
     int anyActive;
+    int ncross;
 };
+
+// per cube edge: low corner (dx,dy,dz) and axis: dx | dy<<1 | dz<<2 | axis<<3   (MarchingCubeTables.cpp:15-16, low node first)
+//  e0 (0,0,0)x  e1 (1,0,0)y  e2 (0,1,0)x  e3 (0,0,0)y  e4 (0,0,1)x  e5 (1,0,1)y  e6 (0,1,1)x  e7 (0,0,1)y
+//  e8 (0,0,0)z  e9 (1,0,0)z  e10 (1,1,0)z e11 (0,1,0)z
+__device__ __forceinline__ unsigned edgeCode(int e) {
+    const unsigned long long codes = (0ull) | (9ull << 5) | (2ull << 10) | (8ull << 15) | (4ull << 20) | (13ull << 25) |
+                                     (6ull << 30) | (12ull << 35) | (16ull << 40) | (17ull << 45) | (19ull << 50) | (18ull << 55);
+    return static_cast<unsigned>(codes >> (5 * e)) & 31u;
+}
+
+__device__ __forceinline__ int edgeIndex(int axis, int ix, int iy, int iz) {
+    if (axis == 0) return (iz * ENY + iy) * EX + ix;
+    if (axis == 1) return E_YBASE + (iz * EY + iy) * ENX + ix;
+    return E_ZBASE + (iz * ENY + iy) * ENX + ix;
+}
 
 template<bool COLOUR>
 __global__ void __launch_bounds__(MC_THREADS) mc_emit_kernel(McGeo m, const float* __restrict__ vol, const float* __restrict__ rgb,
     const unsigned* __restrict__ segOffset, float* __restrict__ outPos, float* __restrict__ outNrm, float* __restrict__ outCol) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     McEmitShared& sh = *reinterpret_cast<McEmitShared*>(smemRaw);
-    const int x0 = blockIdx.x * MCX, y0 = blockIdx.y * MCY, zc0 = m.cz0 + blockIdx.z * MCZ;
+    const int x0 = blockIdx.x * EX, y0 = blockIdx.y * EY, zc0 = m.cz0 + blockIdx.z * EZ;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-    // skip tiles without triangles
-    if (threadIdx.x == 0) sh.anyActive = 0;
+    // ---- skip tiles without triangles -----------------------------------------------------------------------------
+    if (threadIdx.x == 0) sh.anyActive = 0, sh.ncross = 0;
     __syncthreads();
-    if (threadIdx.x < MCY * MCZ) {
-        const int ly = threadIdx.x % MCY, lz = threadIdx.x / MCY;
+    if (threadIdx.x < EY * EZ) {
+        const int ly = threadIdx.x % EY, lz = threadIdx.x / EY;
         const int cyi = y0 + ly, czi = zc0 + lz;
         if (cyi < m.cy && czi < m.cz0 + m.cnz) {
             const size_t seg = blockIdx.x + static_cast<size_t>(m.nsegx) * (cyi + static_cast<size_t>(m.cy) * (czi - m.cz0));
@@ -118,111 +148,134 @@ __global__ void __launch_bounds__(MC_THREADS) mc_emit_kernel(McGeo m, const floa
     __syncthreads();
     if (!sh.anyActive) return;
 
-    // density with a one-node halo; indices clamped to the GLOBAL grid (one-sided differences at the border)
-    for (int i = threadIdx.x; i < MC_HZ * MC_HY * MC_HX; i += MC_THREADS) {
-        const int ix = i % MC_HX, iy = (i / MC_HX) % MC_HY, iz = i / (MC_HX * MC_HY);
-        const int x = min(max(x0 + ix - 1, 0), m.sx - 1), y = min(max(y0 + iy - 1, 0), m.sy - 1);
+    // ---- A: density with a one-node halo; indices clamped to the GLOBAL grid ----------------------------------------
+    for (int r = warp; r < EHZ * EHY; r += MC_THREADS / 32) {
+        const int iy = r % EHY, iz = r / EHY;
+        const int y = min(max(y0 + iy - 1, 0), m.sy - 1);
         const int zg = min(max(zc0 + iz - 1, 0), m.szGlobal - 1);
         const int zl = min(max(zg - m.zPlane0, 0), m.nzPlanes - 1);
-        sh.halo[iz][iy][ix] = vol[x + static_cast<size_t>(m.sx) * (y + static_cast<size_t>(m.sy) * zl)];
+        const float* row = vol + static_cast<size_t>(m.sx) * (y + static_cast<size_t>(m.sy) * zl);
+        sh.halo[iz][iy][lane] = row[min(max(x0 + lane - 1, 0), m.sx - 1)];
+        if (lane < EHX - 32) sh.halo[iz][iy][32 + lane] = row[min(max(x0 + 32 + lane - 1, 0), m.sx - 1)];
     }
+    if (threadIdx.x < ENX) sh.tabX[threadIdx.x] = __fadd_rn(__fmul_rn((float)(x0 + threadIdx.x), m.sd[0]), m.org[0]);
+    else if (threadIdx.x < ENX + ENY) sh.tabY[threadIdx.x - ENX] = __fadd_rn(__fmul_rn((float)(y0 + threadIdx.x - ENX), m.sd[1]), m.org[1]);
+    else if (threadIdx.x < ENX + ENY + ENZ)
+        sh.tabZ[threadIdx.x - ENX - ENY] = __fadd_rn(__fmul_rn((float)(zc0 + threadIdx.x - ENX - ENY), m.sd[2]), m.org[2]);
     __syncthreads();
-    for (int i = threadIdx.x; i < MC_NZ * MC_NY * MC_NX; i += MC_THREADS) {
-        const int ix = i % MC_NX, iy = (i / MC_NX) % MC_NY, iz = i / (MC_NX * MC_NY);
-        const int x = x0 + ix, y = y0 + iy, z = zc0 + iz; // global node index (may exceed the grid for masked cells)
-        // distance between the two samples actually used (clamped at the global border)
-        const int xm = max(x - 1, 0), xp = min(x + 1, m.sx - 1), ym = max(y - 1, 0), yp = min(y + 1, m.sy - 1);
-        const int zm = max(z - 1, 0), zp = min(z + 1, m.szGlobal - 1);
-        const float f = sh.halo[iz + 1][iy + 1][ix + 1];
-        // halo index of a clamped global coordinate c along x is (c - x0 + 1); out-of-grid nodes are never used
-        auto H = [&](int gx, int gy, int gz) -> float {
-            const int hx = min(max(gx - x0 + 1, 0), MC_HX - 1), hy = min(max(gy - y0 + 1, 0), MC_HY - 1), hz = min(max(gz - zc0 + 1, 0), MC_HZ - 1);
-            return sh.halo[hz][hy][hx];
-        };
-        float4 n;
-        n.x = f;
-        n.y = __fdiv_rn(__fsub_rn(H(xp, y, z), H(xm, y, z)), __fmul_rn((float)(xp - xm), m.sd[0]));
-        n.z = __fdiv_rn(__fsub_rn(H(x, yp, z), H(x, ym, z)), __fmul_rn((float)(yp - ym), m.sd[1]));
-        n.w = __fdiv_rn(__fsub_rn(H(x, y, zp), H(x, y, zm)), __fmul_rn((float)(zp - zm), m.sd[2]));
-        sh.node[iz][iy][ix] = n;
+
+    // ---- B1: crossed edges -> crossList (order is irrelevant) ----------------------------------------------------
+    // one warp per node row (33 nodes: lanes 0..31 + one extra pass for node 32)
+    for (int r = warp; r < ENZ * ENY; r += MC_THREADS / 32) {
+        const int iy = r % ENY, iz = r / ENY;
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass) {
+            const int ix = pass == 0 ? lane : 32;
+            const bool active = pass == 0 || lane == 0;
+            bool cx = false, cy = false, cz = false;
+            if (active) {
+                const bool b0 = sh.halo[iz + 1][iy + 1][ix + 1] < m.iso;
+                if (ix < EX) cx = b0 != (sh.halo[iz + 1][iy + 1][ix + 2] < m.iso);
+                if (iy < EY) cy = b0 != (sh.halo[iz + 1][iy + 2][ix + 1] < m.iso);
+                if (iz < EZ) cz = b0 != (sh.halo[iz + 2][iy + 1][ix + 1] < m.iso);
+            }
+            const unsigned bx = __ballot_sync(0xffffffffu, cx), by = __ballot_sync(0xffffffffu, cy), bz = __ballot_sync(0xffffffffu, cz);
+            const int nx = __popc(bx), ny = __popc(by), nz = __popc(bz);
+            if (nx + ny + nz == 0) continue;
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&sh.ncross, nx + ny + nz);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            const unsigned lt = (1u << lane) - 1u;
+            if (cx) sh.crossList[base + __popc(bx & lt)] = static_cast<unsigned short>(edgeIndex(0, ix, iy, iz));
+            if (cy) sh.crossList[base + nx + __popc(by & lt)] = static_cast<unsigned short>(edgeIndex(1, ix, iy, iz));
+            if (cz) sh.crossList[base + nx + ny + __popc(bz & lt)] = static_cast<unsigned short>(edgeIndex(2, ix, iy, iz));
+        }
     }
     __syncthreads();
 
-    float* sPos = sh.stagePos[warp];
-    float* sNrm = sh.stageNrm[warp];
-    for (int r = warp; r < MCY * MCZ; r += MC_THREADS / 32) {
-        const int ly = r % MCY, lz = r / MCY;
+    // ---- B2: one vertex per crossed edge ------------------------------------------------------------------------
+    const int ncross = sh.ncross;
+    for (int c = threadIdx.x; c < ncross; c += MC_THREADS) {
+        const int id = sh.crossList[c];
+        int axis, ix, iy, iz;
+        if (id < E_YBASE) { axis = 0; ix = id % EX; const int t = id / EX; iy = t % ENY; iz = t / ENY; }
+        else if (id < E_ZBASE) { axis = 1; const int q = id - E_YBASE; ix = q % ENX; const int t = q / ENX; iy = t % EY; iz = t / EY; }
+        else { axis = 2; const int q = id - E_ZBASE; ix = q % ENX; const int t = q / ENX; iy = t % ENY; iz = t / ENY; }
+        const int jx = ix + (axis == 0), jy = iy + (axis == 1), jz = iz + (axis == 2);
+        // gradient at a node: (f(+) - f(-)) * 1/(n*sd), samples clamped at the GLOBAL grid border
+        auto grad = [&](int nx_, int ny_, int nz_, float& gx, float& gy, float& gz) {
+            const int gxi = x0 + nx_, gyi = y0 + ny_, gzi = zc0 + nz_;
+            const int xm = gxi > 0 ? -1 : 0, xp = gxi < m.sx - 1 ? 1 : 0;
+            const int ym = gyi > 0 ? -1 : 0, yp = gyi < m.sy - 1 ? 1 : 0;
+            const int zm = gzi > 0 ? -1 : 0, zp = gzi < m.szGlobal - 1 ? 1 : 0;
+            const float* h = &sh.halo[nz_ + 1][ny_ + 1][nx_ + 1];
+            gx = xp > xm ? __fmul_rn(__fsub_rn(h[xp], h[xm]), m.rinv[0][xp - xm]) : 0.0f;
+            gy = yp > ym ? __fmul_rn(__fsub_rn(h[yp * EHXP], h[ym * EHXP]), m.rinv[1][yp - ym]) : 0.0f;
+            gz = zp > zm ? __fmul_rn(__fsub_rn(h[zp * EHXP * EHY], h[zm * EHXP * EHY]), m.rinv[2][zp - zm]) : 0.0f;
+        };
+        const float fa = sh.halo[iz + 1][iy + 1][ix + 1], fb = sh.halo[jz + 1][jy + 1][jx + 1];
+        const float t01 = __fdiv_rn(__fsub_rn(m.iso, fa), __fsub_rn(fb, fa));
+        const float pa = axis == 0 ? sh.tabX[ix] : (axis == 1 ? sh.tabY[iy] : sh.tabZ[iz]);
+        const float pb = axis == 0 ? sh.tabX[jx] : (axis == 1 ? sh.tabY[jy] : sh.tabZ[jz]);
+        float gax, gay, gaz, gbx, gby, gbz;
+        grad(ix, iy, iz, gax, gay, gaz);
+        grad(jx, jy, jz, gbx, gby, gbz);
+        const float gx = __fadd_rn(gax, __fmul_rn(t01, __fsub_rn(gbx, gax)));
+        const float gy = __fadd_rn(gay, __fmul_rn(t01, __fsub_rn(gby, gay)));
+        const float gz = __fadd_rn(gaz, __fmul_rn(t01, __fsub_rn(gbz, gaz)));
+        const float len2 = __fadd_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)), __fmul_rn(gz, gz));
+        const float inv = len2 > 0.0f ? __fdiv_rn(-1.0f, __fsqrt_rn(len2)) : 0.0f;
+        sh.edge[id] = make_float4(__fadd_rn(pa, __fmul_rn(t01, __fsub_rn(pb, pa))), __fmul_rn(gx, inv), __fmul_rn(gy, inv), __fmul_rn(gz, inv));
+    }
+    __syncthreads();
+
+    // ---- C: triangles, one warp per 32-cell row ---------------------------------------------------------------------
+    unsigned char* owner = sh.triOwner[warp];
+    for (int r = warp; r < EY * EZ; r += MC_THREADS / 32) {
+        const int ly = r % EY, lz = r / EY;
         const int cxi = x0 + lane, cyi = y0 + ly, czi = zc0 + lz;
         if (cyi >= m.cy || czi >= m.cz0 + m.cnz) continue;
         const size_t seg = blockIdx.x + static_cast<size_t>(m.nsegx) * (cyi + static_cast<size_t>(m.cy) * (czi - m.cz0));
         const unsigned segOff = segOffset[seg], segTris = segOffset[seg + 1] - segOff;
         if (segTris == 0) continue;
         unsigned long long word = 0;
-        if (cxi < m.cx) {
-            int ci = 0;
-            ci |= (sh.node[lz][ly][lane].x < m.iso) ? 1 : 0;
-            ci |= (sh.node[lz][ly][lane + 1].x < m.iso) ? 2 : 0;
-            ci |= (sh.node[lz][ly + 1][lane + 1].x < m.iso) ? 4 : 0;
-            ci |= (sh.node[lz][ly + 1][lane].x < m.iso) ? 8 : 0;
-            ci |= (sh.node[lz + 1][ly][lane].x < m.iso) ? 16 : 0;
-            ci |= (sh.node[lz + 1][ly][lane + 1].x < m.iso) ? 32 : 0;
-            ci |= (sh.node[lz + 1][ly + 1][lane + 1].x < m.iso) ? 64 : 0;
-            ci |= (sh.node[lz + 1][ly + 1][lane].x < m.iso) ? 128 : 0;
-            word = kCaseWords[ci];
-        }
+        if (cxi < m.cx) word = kCaseWords[cubeIndexSmem(&sh.halo[lz + 1][ly + 1][lane + 1], EHXP, EHXP * EHY, m.iso)];
         const unsigned n = static_cast<unsigned>(word & 15ull);
-        // warp-level exclusive prefix of the triangle counts
         unsigned inc = n;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const unsigned t = __shfl_up_sync(0xffffffffu, inc, d);
             if (lane >= d) inc += t;
         }
-        const unsigned first = inc - n; // my first triangle within the segment
-        for (unsigned win = 0; win < segTris; win += MC_STAGE) {
-            // my triangles that fall into [win, win + MC_STAGE)
-            for (unsigned k = 0; k < n; ++k) {
-                const unsigned t = first + k;
-                if (t < win || t >= win + MC_STAGE) continue;
-                const unsigned slot = (t - win) * 9;
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    const int e = static_cast<int>((word >> (4 + 4 * (3 * k + c))) & 15ull);
-                    const unsigned code = edgeCode(e);
-                    const int ax = lane + (code & 1), ay = ly + ((code >> 1) & 1), az = lz + ((code >> 2) & 1);
-                    const int axis = code >> 3;
-                    const int bx = ax + (axis == 0), by = ay + (axis == 1), bz = az + (axis == 2);
-                    const float4 na = sh.node[az][ay][ax], nb = sh.node[bz][by][bx];
-                    const float t01 = __fdiv_rn(__fsub_rn(m.iso, na.x), __fsub_rn(nb.x, na.x));
-                    // node positions: float(idx)*sd + origin (ParticlesToDensity.cpp:605)
-                    const float pax = __fadd_rn(__fmul_rn((float)(x0 + ax), m.sd[0]), m.org[0]);
-                    const float pay = __fadd_rn(__fmul_rn((float)(y0 + ay), m.sd[1]), m.org[1]);
-                    const float paz = __fadd_rn(__fmul_rn((float)(zc0 + az), m.sd[2]), m.org[2]);
-                    const float pbx = __fadd_rn(__fmul_rn((float)(x0 + bx), m.sd[0]), m.org[0]);
-                    const float pby = __fadd_rn(__fmul_rn((float)(y0 + by), m.sd[1]), m.org[1]);
-                    const float pbz = __fadd_rn(__fmul_rn((float)(zc0 + bz), m.sd[2]), m.org[2]);
-                    sPos[slot + 3 * c + 0] = __fadd_rn(pax, __fmul_rn(t01, __fsub_rn(pbx, pax)));
-                    sPos[slot + 3 * c + 1] = __fadd_rn(pay, __fmul_rn(t01, __fsub_rn(pby, pay)));
-                    sPos[slot + 3 * c + 2] = __fadd_rn(paz, __fmul_rn(t01, __fsub_rn(pbz, paz)));
-                    const float gx = __fadd_rn(na.y, __fmul_rn(t01, __fsub_rn(nb.y, na.y)));
-                    const float gy = __fadd_rn(na.z, __fmul_rn(t01, __fsub_rn(nb.z, na.z)));
-                    const float gz = __fadd_rn(na.w, __fmul_rn(t01, __fsub_rn(nb.w, na.w)));
-                    const float len2 = __fadd_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)), __fmul_rn(gz, gz));
-                    const float inv = len2 > 0.0f ? __fdiv_rn(-1.0f, __fsqrt_rn(len2)) : 0.0f;
-                    sNrm[slot + 3 * c + 0] = __fmul_rn(gx, inv);
-                    sNrm[slot + 3 * c + 1] = __fmul_rn(gy, inv);
-                    sNrm[slot + 3 * c + 2] = __fmul_rn(gz, inv);
-                }
-            }
-            __syncwarp();
-            const unsigned cnt = min((unsigned)MC_STAGE, segTris - win) * 9;
-            const size_t gbase = (static_cast<size_t>(segOff) + win) * 9;
-            for (unsigned j = lane; j < cnt; j += 32) {
-                outPos[gbase + j] = sPos[j];
-                outNrm[gbase + j] = sNrm[j];
-            }
-            __syncwarp();
+        const unsigned first = inc - n; // my first triangle within the row
+        for (unsigned k = 0; k < n; ++k) owner[first + k] = static_cast<unsigned char>(lane);
+        __syncwarp();
+        const unsigned wlo = static_cast<unsigned>(word >> 4), whi = static_cast<unsigned>(word >> 36); // 15 nibbles of edge ids
+        const unsigned ncorn = segTris * 3;
+        const size_t gbase = static_cast<size_t>(segOff) * 9;
+        for (unsigned j0 = 0; j0 < ncorn; j0 += 32) {
+            const unsigned j = j0 + lane;
+            const bool act = j < ncorn;
+            const unsigned t = act ? j / 3 : 0;
+            const unsigned L = owner[t];
+            const unsigned oFirst = __shfl_sync(0xffffffffu, first, L);
+            const unsigned oLo = __shfl_sync(0xffffffffu, wlo, L), oHi = __shfl_sync(0xffffffffu, whi, L);
+            if (!act) continue;
+            const unsigned slot = 3 * (t - oFirst) + (j - 3 * t); // corner number inside the owner cell (0..14)
+            const int e = static_cast<int>(slot < 8 ? (oLo >> (4 * slot)) & 15u : (oHi >> (4 * (slot - 8))) & 15u);
+            const unsigned code = edgeCode(e);
+            const int ix = (int)L + (code & 1), iy = ly + ((code >> 1) & 1), iz = lz + ((code >> 2) & 1);
+            const int axis = code >> 3;
+            const float4 v = sh.edge[edgeIndex(axis, ix, iy, iz)];
+            const float px = axis == 0 ? v.x : sh.tabX[ix];
+            const float py = axis == 1 ? v.x : sh.tabY[iy];
+            const float pz = axis == 2 ? v.x : sh.tabZ[iz];
+            float* op = outPos + gbase + static_cast<size_t>(j) * 3;
+            float* on = outNrm + gbase + static_cast<size_t>(j) * 3;
+            op[0] = px, op[1] = py, op[2] = pz;
+            on[0] = v.y, on[1] = v.z, on[2] = v.w;
         }
+        __syncwarp();
     }
 }
 

@@ -597,7 +597,15 @@ int mms_extract_isosurface(mms_ctx* c, float iso) {
     m.cx = m.sx - 1, m.cy = m.sy - 1, m.cz0 = c->cellZ0, m.cnz = c->cellNz;
     m.nsegx = (m.cx + MCX - 1) / MCX;
     const Geo g = makeGeo(c);
-    for (int a = 0; a < 3; ++a) m.org[a] = g.mn[a], m.sd[a] = g.sd[a];
+    for (int a = 0; a < 3; ++a) {
+        m.org[a] = g.mn[a], m.sd[a] = g.sd[a];
+        for (int n = 1; n <= 2; ++n) {
+            volatile float den = static_cast<float>(n) * g.sd[a];
+            volatile float r = 1.0f / den;
+            m.rinv[a][n] = r;
+        }
+        m.rinv[a][0] = 0.0f;
+    }
     m.iso = iso;
     c->ntris = 0;
     c->haveMesh = true;
@@ -628,7 +636,8 @@ int mms_extract_isosurface(mms_ctx* c, float iso) {
     if (T > 0) {
         if (!c->meshPos.ensure(T * 36) || !c->meshNrm.ensure(T * 36))
             return c->fail(MMS_ERR_NOMEM, "device allocation of the mesh (%llu triangles, %llu bytes) failed", T, T * 72ull);
-        mc_emit_kernel<false><<<grid, MC_THREADS, sizeof(McEmitShared), st>>>(m, c->vol.as<float>(), nullptr, c->segOffset.as<unsigned>(),
+        dim3 gridE(m.nsegx, (m.cy + EY - 1) / EY, (m.cnz + EZ - 1) / EZ);
+        mc_emit_kernel<false><<<gridE, MC_THREADS, sizeof(McEmitShared), st>>>(m, c->vol.as<float>(), nullptr, c->segOffset.as<unsigned>(),
             c->meshPos.as<float>(), c->meshNrm.as<float>(), nullptr);
         ++c->launches;
     }

@@ -412,7 +412,7 @@ struct Node {
  * Vertex on an edge: always interpolated from the LOWER node to the HIGHER node of the edge's axis
  * (t = (iso - f_lo)/(f_hi - f_lo), p = p_lo + t*(p_hi - p_lo)) so that neighbouring cells produce
  * bit-identical shared vertices.  Normal = -grad(rho) interpolated with the same t and normalised;
- * grad at a node by central differences (one-sided at the border), divided by the actual node distance.
+ * grad at a node by central differences (one-sided at the border) times 1/(actual node distance).
  * Colour = lerp of the per-node colour rgb/rho (rho == 0 -> 0), same t.
  * z_offset: index of plane 0 of `vol` in the global grid (slabs); positions use global indices.
  * Returns the number of triangles written (<= max_tris), or -1 if max_tris was too small.
@@ -423,15 +423,20 @@ int64_t mmo_mc_emit(const float* vol, const float* rgb, const int32_t res[3], co
     const int cx = sx - 1, cy = sy - 1, cz = sz - 1;
     if (cx <= 0 || cy <= 0 || cz <= 0) return 0;
     auto at = [&](int x, int y, int z) -> float { return vol[x + static_cast<size_t>(sx) * (y + static_cast<size_t>(sy) * z)]; };
+    // gradient = (f(+) - f(-)) * (1 / (n * sd)) with n = number of grid steps between the two samples (2 inside,
+    // 1 at the border); the reciprocal is formed once per axis and n, the product is one rounded multiply
+    float rinv[3][3];
+    for (int a = 0; a < 3; ++a)
+        for (int n = 1; n <= 2; ++n) rinv[a][n] = 1.0f / (static_cast<float>(n) * sd[a]);
     auto node = [&](int x, int y, int z) -> Node {
         Node n;
         n.f = at(x, y, z);
         const int xm = std::max(x - 1, 0), xp = std::min(x + 1, sx - 1);
         const int ym = std::max(y - 1, 0), yp = std::min(y + 1, sy - 1);
         const int zm = std::max(z - 1, 0), zp = std::min(z + 1, sz - 1);
-        n.gx = (at(xp, y, z) - at(xm, y, z)) / (static_cast<float>(xp - xm) * sd[0]);
-        n.gy = (at(x, yp, z) - at(x, ym, z)) / (static_cast<float>(yp - ym) * sd[1]);
-        n.gz = (at(x, y, zp) - at(x, y, zm)) / (static_cast<float>(zp - zm) * sd[2]);
+        n.gx = xp > xm ? (at(xp, y, z) - at(xm, y, z)) * rinv[0][xp - xm] : 0.0f;
+        n.gy = yp > ym ? (at(x, yp, z) - at(x, ym, z)) * rinv[1][yp - ym] : 0.0f;
+        n.gz = zp > zm ? (at(x, y, zp) - at(x, y, zm)) * rinv[2][zp - zm] : 0.0f;
         return n;
     };
     int64_t ntri = 0;
