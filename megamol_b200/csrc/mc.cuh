@@ -165,36 +165,38 @@ __global__ void __launch_bounds__(MC_THREADS) mc_emit_kernel(McGeo m, const floa
     __syncthreads();
 
     // ---- B1: crossed edges -> crossList (order is irrelevant) ----------------------------------------------------
-    // one warp per node row (33 nodes: lanes 0..31 + one extra pass for node 32)
-    for (int r = warp; r < ENZ * ENY; r += MC_THREADS / 32) {
-        const int iy = r % ENY, iz = r / ENY;
-#pragma unroll
-        for (int pass = 0; pass < 2; ++pass) {
-            const int ix = pass == 0 ? lane : 32;
-            const bool active = pass == 0 || lane == 0;
-            bool cx = false, cy = false, cz = false;
-            if (active) {
-                const bool b0 = sh.halo[iz + 1][iy + 1][ix + 1] < m.iso;
-                if (ix < EX) cx = b0 != (sh.halo[iz + 1][iy + 1][ix + 2] < m.iso);
-                if (iy < EY) cy = b0 != (sh.halo[iz + 1][iy + 2][ix + 1] < m.iso);
-                if (iz < EZ) cz = b0 != (sh.halo[iz + 2][iy + 1][ix + 1] < m.iso);
-            }
-            const unsigned bx = __ballot_sync(0xffffffffu, cx), by = __ballot_sync(0xffffffffu, cy), bz = __ballot_sync(0xffffffffu, cz);
-            const int nx = __popc(bx), ny = __popc(by), nz = __popc(bz);
-            if (nx + ny + nz == 0) continue;
-            int base = 0;
-            if (lane == 0) base = atomicAdd(&sh.ncross, nx + ny + nz);
-            base = __shfl_sync(0xffffffffu, base, 0);
-            const unsigned lt = (1u << lane) - 1u;
-            if (cx) sh.crossList[base + __popc(bx & lt)] = static_cast<unsigned short>(edgeIndex(0, ix, iy, iz));
-            if (cy) sh.crossList[base + nx + __popc(by & lt)] = static_cast<unsigned short>(edgeIndex(1, ix, iy, iz));
-            if (cz) sh.crossList[base + nx + ny + __popc(bz & lt)] = static_cast<unsigned short>(edgeIndex(2, ix, iy, iz));
+    // rounds 0..26: one warp per node row, lanes = nodes 0..31; round 27: the 27 nodes of column 32, one per lane
+    for (int r = warp; r < ENZ * ENY + 1; r += MC_THREADS / 32) {
+        const bool lastCol = r == ENZ * ENY;
+        const int rr = lastCol ? lane : r;
+        const bool active = !lastCol || lane < ENZ * ENY;
+        const int iy = rr % ENY, iz = (rr / ENY) % ENZ;
+        const int ix = lastCol ? EX : lane;
+        bool cx = false, cy = false, cz = false;
+        if (active) {
+            const bool b0 = sh.halo[iz + 1][iy + 1][ix + 1] < m.iso;
+            if (ix < EX) cx = b0 != (sh.halo[iz + 1][iy + 1][ix + 2] < m.iso);
+            if (iy < EY) cy = b0 != (sh.halo[iz + 1][iy + 2][ix + 1] < m.iso);
+            if (iz < EZ) cz = b0 != (sh.halo[iz + 2][iy + 1][ix + 1] < m.iso);
         }
+        const unsigned bx = __ballot_sync(0xffffffffu, cx), by = __ballot_sync(0xffffffffu, cy), bz = __ballot_sync(0xffffffffu, cz);
+        const int nx = __popc(bx), ny = __popc(by), nz = __popc(bz);
+        if (nx + ny + nz == 0) continue;
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&sh.ncross, nx + ny + nz);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        const unsigned lt = (1u << lane) - 1u;
+        if (cx) sh.crossList[base + __popc(bx & lt)] = static_cast<unsigned short>(edgeIndex(0, ix, iy, iz));
+        if (cy) sh.crossList[base + nx + __popc(by & lt)] = static_cast<unsigned short>(edgeIndex(1, ix, iy, iz));
+        if (cz) sh.crossList[base + nx + ny + __popc(bz & lt)] = static_cast<unsigned short>(edgeIndex(2, ix, iy, iz));
     }
     __syncthreads();
 
     // ---- B2: one vertex per crossed edge ------------------------------------------------------------------------
     const int ncross = sh.ncross;
+    const float r1x = m.rinv[0][1], r2x = m.rinv[0][2], r1y = m.rinv[1][1], r2y = m.rinv[1][2], r1z = m.rinv[2][1], r2z = m.rinv[2][2];
+    // no node of this tile touches the global border -> plain central differences
+    const bool interior = x0 > 0 && x0 + EX < m.sx - 1 && y0 > 0 && y0 + EY < m.sy - 1 && zc0 > 0 && zc0 + EZ < m.szGlobal - 1;
     for (int c = threadIdx.x; c < ncross; c += MC_THREADS) {
         const int id = sh.crossList[c];
         int axis, ix, iy, iz;
@@ -204,14 +206,20 @@ __global__ void __launch_bounds__(MC_THREADS) mc_emit_kernel(McGeo m, const floa
         const int jx = ix + (axis == 0), jy = iy + (axis == 1), jz = iz + (axis == 2);
         // gradient at a node: (f(+) - f(-)) * 1/(n*sd), samples clamped at the GLOBAL grid border
         auto grad = [&](int nx_, int ny_, int nz_, float& gx, float& gy, float& gz) {
-            const int gxi = x0 + nx_, gyi = y0 + ny_, gzi = zc0 + nz_;
-            const int xm = gxi > 0 ? -1 : 0, xp = gxi < m.sx - 1 ? 1 : 0;
-            const int ym = gyi > 0 ? -1 : 0, yp = gyi < m.sy - 1 ? 1 : 0;
-            const int zm = gzi > 0 ? -1 : 0, zp = gzi < m.szGlobal - 1 ? 1 : 0;
             const float* h = &sh.halo[nz_ + 1][ny_ + 1][nx_ + 1];
-            gx = xp > xm ? __fmul_rn(__fsub_rn(h[xp], h[xm]), m.rinv[0][xp - xm]) : 0.0f;
-            gy = yp > ym ? __fmul_rn(__fsub_rn(h[yp * EHXP], h[ym * EHXP]), m.rinv[1][yp - ym]) : 0.0f;
-            gz = zp > zm ? __fmul_rn(__fsub_rn(h[zp * EHXP * EHY], h[zm * EHXP * EHY]), m.rinv[2][zp - zm]) : 0.0f;
+            if (interior) {
+                gx = __fmul_rn(__fsub_rn(h[1], h[-1]), r2x);
+                gy = __fmul_rn(__fsub_rn(h[EHXP], h[-EHXP]), r2y);
+                gz = __fmul_rn(__fsub_rn(h[EHXP * EHY], h[-EHXP * EHY]), r2z);
+            } else {
+                const int gxi = x0 + nx_, gyi = y0 + ny_, gzi = zc0 + nz_;
+                const int xm = gxi > 0 ? -1 : 0, xp = gxi < m.sx - 1 ? 1 : 0;
+                const int ym = gyi > 0 ? -1 : 0, yp = gyi < m.sy - 1 ? 1 : 0;
+                const int zm = gzi > 0 ? -1 : 0, zp = gzi < m.szGlobal - 1 ? 1 : 0;
+                gx = xp > xm ? __fmul_rn(__fsub_rn(h[xp], h[xm]), xp - xm == 2 ? r2x : r1x) : 0.0f;
+                gy = yp > ym ? __fmul_rn(__fsub_rn(h[yp * EHXP], h[ym * EHXP]), yp - ym == 2 ? r2y : r1y) : 0.0f;
+                gz = zp > zm ? __fmul_rn(__fsub_rn(h[zp * EHXP * EHY], h[zm * EHXP * EHY]), zp - zm == 2 ? r2z : r1z) : 0.0f;
+            }
         };
         const float fa = sh.halo[iz + 1][iy + 1][ix + 1], fb = sh.halo[jz + 1][jy + 1][jx + 1];
         const float t01 = __fdiv_rn(__fsub_rn(m.iso, fa), __fsub_rn(fb, fa));
@@ -224,7 +232,7 @@ __global__ void __launch_bounds__(MC_THREADS) mc_emit_kernel(McGeo m, const floa
         const float gy = __fadd_rn(gay, __fmul_rn(t01, __fsub_rn(gby, gay)));
         const float gz = __fadd_rn(gaz, __fmul_rn(t01, __fsub_rn(gbz, gaz)));
         const float len2 = __fadd_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)), __fmul_rn(gz, gz));
-        const float inv = len2 > 0.0f ? __fdiv_rn(-1.0f, __fsqrt_rn(len2)) : 0.0f;
+        const float inv = len2 > 0.0f ? -rsqrtf(len2) : 0.0f; // SFU rsqrt: 2 ulp, normals are compared at 1e-4
         sh.edge[id] = make_float4(__fadd_rn(pa, __fmul_rn(t01, __fsub_rn(pb, pa))), __fmul_rn(gx, inv), __fmul_rn(gy, inv), __fmul_rn(gz, inv));
     }
     __syncthreads();
