@@ -19,6 +19,9 @@
 
 using namespace mms;
 
+static_assert(sizeof(mms_list) == 56 && sizeof(mms_grid) == 48 && sizeof(mms_params) == 40 && sizeof(mms_timings) == 28,
+    "C ABI struct layout changed: update include/mmsurf.h users (megamol_b200/api.py, plugin/b200surf)");
+
 namespace {
 
 std::string g_createError;

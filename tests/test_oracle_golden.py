@@ -1,0 +1,91 @@
+"""CPU suite: the oracle against the golden vectors produced by the UNMODIFIED reference translation units
+(tests/golden/*, generator oracle/tools/gen_golden.py).  This is what pins the oracle."""
+import os
+
+import numpy as np
+import pytest
+
+from tests import golden_util as G
+
+
+@pytest.mark.parametrize("path", G.p2d_cases(), ids=lambda p: os.path.basename(p)[9:-4])
+def test_density_bit_identical_to_reference(oracle, path):
+    c = G.load_p2d(path)
+    vol, (mn, mx) = oracle.density_p2d(c["lists"], c["bmin"], c["bext"], c["res"], c["cyclic"], sigma=c["sigma"],
+                                       aggregator=c["aggregator"], normalize=c["normalize"])
+    # reference at one OpenMP thread accumulates in particle order, exactly like the oracle: every bit must match
+    assert np.array_equal(vol.view(np.uint32), c["volume"].view(np.uint32))
+    if not c["normalize"]:
+        assert (mn, mx) == c["minmax"]
+    else:
+        assert c["minmax"] == (0.0, 1.0)
+    sd = np.array(c["bext"], np.float32) / (np.array(c["res"], np.float32) - np.float32(1))
+    assert np.array_equal(sd, c["slicedist"])
+
+
+def test_home_voxels_match_reference_kat(oracle):
+    z = np.load(os.path.join(G.GOLDEN, "home_voxel_kat.npz"))
+    pts = np.ascontiguousarray(z["points"])
+    lists = [dict(vtx=pts, vtx_type=1, count=len(pts), global_radius=float(z["radius"]))]
+    home = oracle.home_voxels(lists, z["bmin"], z["bext"], z["res"])
+    assert np.array_equal(home, z["home"])
+    # the KAT is not trivial: a float64 evaluation of (p-min)/sd disagrees for a good part of the particles
+    sd = z["bext"].astype(np.float64) / (z["res"] - 1)
+    naive = np.trunc((pts.astype(np.float64) - z["bmin"]) / sd).astype(np.int32)
+    assert (naive != z["home"]).any()
+
+
+def test_mc_tables_equal_reference(oracle):
+    z = np.load(os.path.join(G.GOLDEN, "mc_tables_ref.npz"))
+    words = oracle.case_words()
+    assert np.array_equal(words, z["words"])
+    tri, cnt = z["tri"].astype(np.int64), z["count"]
+    for c in range(256):
+        w = int(words[c])
+        assert (w & 15) == int(cnt[c])
+        for k in range(15):
+            e = (w >> (4 + 4 * k)) & 15
+            assert e == (int(tri[c, k]) if tri[c, k] >= 0 else 0)
+    # the product's copy of the table is the same text
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    a = open(os.path.join(here, "oracle", "mc_case_words.inc")).read()
+    b = open(os.path.join(here, "megamol_b200", "csrc", "mc_case_words.inc")).read()
+    assert a == b
+    # classic table facts: 820 triangles over the 256 cases, empty at both ends, at most 5 per cell
+    assert int(cnt.sum()) == 820 and cnt[0] == 0 and cnt[255] == 0 and cnt.max() == 5
+
+
+def test_marching_cubes_oracle_properties(oracle):
+    """Closed surface of a sphere: watertight (every edge shared by exactly two triangles), outward normals,
+    vertices on the iso-level of the trilinear field along grid edges."""
+    z, y, x = np.mgrid[0:24, 0:26, 0:28].astype(np.float32)
+    vol = (10.0 - np.sqrt((x - 13.2) ** 2 + (y - 12.1) ** 2 + (z - 11.7) ** 2)).astype(np.float32)
+    pos, nrm, _ = oracle.mc_emit(vol, (0, 0, 0), (1, 1, 1), 2.5)
+    total, counts, cub = oracle.mc_count(vol, 2.5, want_cubeidx=True)
+    assert pos.shape[0] == total == counts.sum()
+    v = pos.reshape(-1, 3)
+    keys = [tuple(np.round(p * 4096).astype(np.int64)) for p in v]
+    from collections import Counter
+    edges = Counter()
+    for t in range(total):
+        a, b, c = keys[3 * t], keys[3 * t + 1], keys[3 * t + 2]
+        for e in ((a, b), (b, c), (c, a)):
+            if e[0] != e[1]:
+                edges[tuple(sorted(e))] += 1
+    assert set(edges.values()) == {2}
+    r = np.linalg.norm(v - np.array([13.2, 12.1, 11.7]), axis=1)
+    assert np.abs(r - 7.5).max() < 0.05
+    # density falls outwards, so -grad points outwards
+    out = (v - np.array([13.2, 12.1, 11.7])) / r[:, None]
+    assert (out * nrm.reshape(-1, 3)).sum(1).min() > 0.98
+
+
+def test_reference_isosurface_is_a_different_algorithm(oracle):
+    """Informational pin (SURVEY 8c iv): the reference's IsoSurface is marching TETRAHEDRA; on the same volume our
+    marching cubes yields fewer triangles, the same bounding box to within a cell."""
+    z = np.load(os.path.join(G.GOLDEN, "isosurface_ref.npz"))
+    vol, iso = z["volume"], float(z["iso"])
+    total, _, _ = oracle.mc_count(vol, iso)
+    ref_tris = int(z["nverts"]) // 3
+    assert int(z["ntris"]) == 0            # the reference never fills its index buffer (IsoSurface.cpp:180)
+    assert 0 < total < ref_tris < 3 * total
