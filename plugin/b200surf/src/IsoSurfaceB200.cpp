@@ -1,0 +1,187 @@
+/*
+ * IsoSurfaceB200.cpp
+ *
+ * Call protocol of trisoup_gl::volumetrics::IsoSurface (plugins/trisoup_gl/src/volumetrics/IsoSurface.cpp:94-223).
+ * If the volume comes from a ParticlesToDensityB200 the density never leaves the GPU: the isosurface is extracted
+ * on that module's context.  Any other VolumetricDataCall source is uploaded through mms_set_density.
+ * Vertex positions use the node-centred frame of the metadata (Origin + idx * SliceDist, docs/volumes.md:14-16),
+ * not the reference IsoSurface's half-voxel-shifted frame (IsoSurface.cpp:238-252; SURVEY.md 8a traps).
+ */
+#include "IsoSurfaceB200.h"
+
+#include <chrono>
+
+#include "ParticlesToDensityB200.h"
+#include "mmcore/param/FloatParam.h"
+#include "mmcore/param/IntParam.h"
+#include "mmcore/param/StringParam.h"
+#include "mmcore/utility/log/Log.h"
+
+using namespace megamol;
+using namespace megamol::b200surf;
+using megamol::core::utility::log::Log;
+using geocalls::VolumetricDataCall;
+using geocalls_gl::CallTriMeshDataGL;
+
+bool IsoSurfaceB200::IsAvailable() {
+    return ParticlesToDensityB200::IsAvailable();
+}
+
+IsoSurfaceB200::IsoSurfaceB200()
+        : inDataSlot("inData", "The slot for requesting input data")
+        , outDataSlot("outData", "Gets the data")
+        , attributeSlot("attr", "The attribute to show")
+        , isoValueSlot("isoval", "The iso value")
+        , deviceSlot("device", "CUDA device ordinal used for volumes that are not already device resident") {
+
+    this->inDataSlot.SetCompatibleCall<geocalls::VolumetricDataCallDescription>();
+    this->MakeSlotAvailable(&this->inDataSlot);
+
+    this->outDataSlot.SetCallback("CallTriMeshData", "GetData", &IsoSurfaceB200::outDataCallback);
+    this->outDataSlot.SetCallback("CallTriMeshData", "GetExtent", &IsoSurfaceB200::outExtentCallback);
+    this->MakeSlotAvailable(&this->outDataSlot);
+
+    this->attributeSlot << new core::param::StringParam("0");
+    this->MakeSlotAvailable(&this->attributeSlot);
+
+    this->isoValueSlot << new core::param::FloatParam(0.5f);
+    this->MakeSlotAvailable(&this->isoValueSlot);
+
+    this->deviceSlot << new core::param::IntParam(0, 0);
+    this->MakeSlotAvailable(&this->deviceSlot);
+}
+
+IsoSurfaceB200::~IsoSurfaceB200() {
+    this->Release();
+}
+
+bool IsoSurfaceB200::create() {
+    return true;
+}
+
+void IsoSurfaceB200::release() {
+    if (this->ctx != nullptr) {
+        mms_destroy(this->ctx);
+        this->ctx = nullptr;
+    }
+}
+
+bool IsoSurfaceB200::outExtentCallback(core::Call& caller) {
+    auto* tmd = dynamic_cast<CallTriMeshDataGL*>(&caller);
+    if (tmd == nullptr)
+        return false;
+    tmd->AccessBoundingBoxes().Clear();
+    auto* cvd = this->inDataSlot.CallAs<VolumetricDataCall>();
+    if (cvd != nullptr)
+        cvd->SetFrameID(tmd->FrameID(), tmd->IsFrameForced());
+    if (cvd == nullptr || !(*cvd)(VolumetricDataCall::IDX_GET_EXTENTS) || !(*cvd)(VolumetricDataCall::IDX_GET_METADATA)) {
+        tmd->SetDataHash(0);
+        tmd->SetFrameCount(1);
+    } else {
+        tmd->SetDataHash(cvd->DataHash());
+        tmd->SetExtent(cvd->FrameCount(), cvd->AccessBoundingBoxes());
+    }
+    tmd->SetUnlocker(nullptr);
+    return true;
+}
+
+bool IsoSurfaceB200::buildMesh(VolumetricDataCall* cvd, float iso) {
+    const auto t0 = std::chrono::high_resolution_clock::now();
+    mms_ctx* use = nullptr;
+    // device-resident hand-off: is the callee a ParticlesToDensityB200 whose context holds exactly this volume?
+    const core::CalleeSlot* callee = cvd->PeekCalleeSlot();
+    if (callee != nullptr) {
+        auto parent = callee->Parent();
+        auto* p2d = dynamic_cast<const ParticlesToDensityB200*>(parent.get());
+        if (p2d != nullptr && p2d->Context() != nullptr && p2d->VolumeHash() == cvd->DataHash())
+            use = p2d->Context();
+    }
+    if (use == nullptr) {
+        const auto* md = cvd->GetMetadata();
+        if (md == nullptr || cvd->GetData() == nullptr || md->Components != 1 || md->GridType != geocalls::GridType_t::CARTESIAN) {
+            Log::DefaultLog.WriteError("IsoSurfaceB200: need a host-resident single-component cartesian float volume");
+            return false;
+        }
+        const int device = this->deviceSlot.Param<core::param::IntParam>()->Value();
+        if (this->ctx == nullptr || this->ctxDevice != device) {
+            if (this->ctx != nullptr)
+                mms_destroy(this->ctx);
+            this->ctx = nullptr;
+            mms_config cfg{device, 0};
+            if (mms_create(&this->ctx, &cfg) != MMS_OK) {
+                Log::DefaultLog.WriteError("IsoSurfaceB200: %s", mms_last_error(nullptr));
+                return false;
+            }
+            this->ctxDevice = device;
+        }
+        mms_grid grid{};
+        for (int a = 0; a < 3; ++a) {
+            grid.min[a] = md->Origin[a];
+            grid.extent[a] = md->Extents[a];
+            grid.res[a] = static_cast<int32_t>(md->Resolution[a]);
+            grid.cyclic[a] = 0;
+        }
+        if (mms_set_grid(this->ctx, &grid) != MMS_OK || mms_set_density(this->ctx, static_cast<const float*>(cvd->GetData())) != MMS_OK) {
+            Log::DefaultLog.WriteError("IsoSurfaceB200: %s", mms_last_error(this->ctx));
+            return false;
+        }
+        use = this->ctx;
+    }
+    uint64_t nverts = 0;
+    const float *pos = nullptr, *nrm = nullptr;
+    if (mms_extract_isosurface(use, iso) != MMS_OK || mms_get_mesh(use, &nverts, &pos, &nrm, nullptr) != MMS_OK) {
+        Log::DefaultLog.WriteError("IsoSurfaceB200: %s", mms_last_error(use));
+        return false;
+    }
+    this->mesh.SetMaterial(nullptr);
+    // the reference's contract (IsoSurface.cpp:171-181): unindexed soup, float positions + normals, no colours, 0 "triangles"
+    // (the Mesh setters are overloaded on NON-const pointers; a const float* would select the catch-all "no data" overload)
+    this->mesh.SetVertexData(static_cast<unsigned int>(nverts), const_cast<float*>(pos), const_cast<float*>(nrm), static_cast<float*>(nullptr),
+        static_cast<float*>(nullptr), false);
+    this->mesh.SetTriangleData(0, static_cast<unsigned int*>(nullptr), false);
+    const std::chrono::duration<float, std::milli> ms = std::chrono::high_resolution_clock::now() - t0;
+    Log::DefaultLog.WriteInfo("IsoSurfaceB200: %llu triangles at iso %f took %f ms (%s volume).", static_cast<unsigned long long>(nverts / 3), iso,
+        ms.count(), use == this->ctx ? "uploaded" : "device-resident");
+    return true;
+}
+
+bool IsoSurfaceB200::outDataCallback(core::Call& caller) {
+    auto* tmd = dynamic_cast<CallTriMeshDataGL*>(&caller);
+    if (tmd == nullptr)
+        return false;
+    auto* cvd = this->inDataSlot.CallAs<VolumetricDataCall>();
+    if (cvd != nullptr) {
+        bool recalc = false;
+        if (this->isoValueSlot.IsDirty()) {
+            this->isoValueSlot.ResetDirty();
+            recalc = true;
+        }
+        if (this->attributeSlot.IsDirty()) {
+            this->attributeSlot.ResetDirty();
+            recalc = true;
+        }
+        cvd->SetFrameID(tmd->FrameID(), tmd->IsFrameForced());
+        if (!(*cvd)(VolumetricDataCall::IDX_GET_EXTENTS) || !(*cvd)(VolumetricDataCall::IDX_GET_METADATA) ||
+            !(*cvd)(VolumetricDataCall::IDX_GET_DATA)) {
+            recalc = false;
+        } else if (this->dataHash != cvd->DataHash() || this->frameIdx != cvd->FrameID() || !this->has_mesh) {
+            recalc = true;
+        }
+        if (recalc && cvd->GetScalarType() != VolumetricDataCall::ScalarType::FLOATING_POINT) {
+            Log::DefaultLog.WriteError("IsoSurfaceB200: Only float volumes are supported ATM");
+            recalc = false;
+        }
+        if (recalc) {
+            if (!this->buildMesh(cvd, this->isoValueSlot.Param<core::param::FloatParam>()->Value()))
+                return false;
+            this->dataHash = cvd->DataHash();
+            this->frameIdx = cvd->FrameID();
+            this->has_mesh = true;
+        }
+    }
+    tmd->SetDataHash(this->dataHash);
+    tmd->SetFrameID(this->frameIdx);
+    tmd->SetObjects(1, &this->mesh);
+    tmd->SetUnlocker(nullptr);
+    return true;
+}

@@ -1,0 +1,56 @@
+/*
+ * IsoSurfaceB200.h -- drop-in for trisoup_gl::volumetrics::IsoSurface (plugins/trisoup_gl/src/volumetrics/IsoSurface.h):
+ * slots inData (VolumetricDataCall) / outData ("CallTriMeshData": GetData, GetExtent), parameters attr, isoval.
+ * Marching cubes with the classic table instead of marching tetrahedra, smooth normals; the mesh contract is the
+ * reference's: one Mesh, unindexed triangle soup, float positions + float normals.
+ */
+#pragma once
+
+#include <cstddef>
+
+#include "geometry_calls/VolumetricDataCall.h"
+#include "geometry_calls_gl/CallTriMeshDataGL.h"
+#include "mmcore/CalleeSlot.h"
+#include "mmcore/CallerSlot.h"
+#include "mmcore/Module.h"
+#include "mmcore/param/ParamSlot.h"
+
+#include "mmsurf.h"
+
+namespace megamol::b200surf {
+
+class IsoSurfaceB200 : public core::Module {
+public:
+    static const char* ClassName() {
+        return "IsoSurfaceB200";
+    }
+    static const char* Description() {
+        return "Extracts an iso-surface mesh from a volume on a B200 (drop-in for IsoSurface)";
+    }
+    static bool IsAvailable();
+
+    IsoSurfaceB200();
+    ~IsoSurfaceB200() override;
+
+protected:
+    bool create() override;
+    void release() override;
+
+private:
+    bool outDataCallback(core::Call& caller);
+    bool outExtentCallback(core::Call& caller);
+    bool buildMesh(geocalls::VolumetricDataCall* cvd, float iso);
+
+    core::CallerSlot inDataSlot;
+    core::CalleeSlot outDataSlot;
+    core::param::ParamSlot attributeSlot, isoValueSlot, deviceSlot;
+
+    mms_ctx* ctx = nullptr; // own context, used when the volume comes from a foreign (host) source
+    int ctxDevice = -1;
+    std::size_t dataHash = 0;
+    unsigned int frameIdx = 0;
+    bool has_mesh = false;
+    geocalls_gl::CallTriMeshDataGL::Mesh mesh;
+};
+
+} // namespace megamol::b200surf

@@ -1,0 +1,374 @@
+/*
+ * ParticlesToDensityB200.cpp
+ *
+ * Host side of the B200 density path.  Mirrors the call protocol of datatools::ParticlesToDensity
+ * (plugins/datatools/src/ParticlesToDensity.cpp:163-383) and hands the particle lists of the incoming
+ * MultiParticleDataCall to libmmsurf as raw (pointer, type, stride) triples -- no per-particle virtual accessors.
+ */
+#include "ParticlesToDensityB200.h"
+
+#include <cfloat>
+#include <chrono>
+#include <vector>
+
+#include "datatools/table/TableDataCall.h"
+#include "mmcore/param/BoolParam.h"
+#include "mmcore/param/EnumParam.h"
+#include "mmcore/param/FloatParam.h"
+#include "mmcore/param/IntParam.h"
+#include "mmcore/utility/log/Log.h"
+
+using namespace megamol;
+using namespace megamol::b200surf;
+using megamol::core::utility::log::Log;
+using geocalls::MultiParticleDataCall;
+using geocalls::VolumetricDataCall;
+
+bool ParticlesToDensityB200::IsAvailable() {
+    mms_ctx* probe = nullptr;
+    mms_config cfg{0, 0};
+    if (mms_create(&probe, &cfg) != MMS_OK)
+        return false;
+    mms_destroy(probe);
+    return true;
+}
+
+ParticlesToDensityB200::ParticlesToDensityB200()
+        : aggregatorSlot("aggregator", "algorithm for the aggregation")
+        , xResSlot("sizex", "The size of the volume in numbers of voxels")
+        , yResSlot("sizey", "The size of the volume in numbers of voxels")
+        , zResSlot("sizez", "The size of the volume in numbers of voxels")
+        , cyclXSlot("cyclX", "Considers cyclic boundary conditions in X direction")
+        , cyclYSlot("cyclY", "Considers cyclic boundary conditions in Y direction")
+        , cyclZSlot("cyclZ", "Considers cyclic boundary conditions in Z direction")
+        , normalizeSlot("normalize", "Normalize the output volume")
+        , sigmaSlot("sigma", "Sigma for Gauss in multiple of rad")
+        , surfaceSlot("forSurfaceReconstruction", "Set true if this volume is used for surface reconstruction")
+        , deviceSlot("device", "CUDA device ordinal the volume is computed on")
+        , outDataSlot("outData", "Provides a density volume for the particles")
+        , outParticlesSlot("outParticles", "Provides the particles in grid form (vector aggregator only)")
+        , outInfoSlot("outInfo", "Provides information about the grid (vector aggregator only)")
+        , inDataSlot("inData", "takes the particle data") {
+
+    auto* ep = new core::param::EnumParam(0);
+    ep->SetTypePair(0, "PosToSingleCell_Volume");
+    ep->SetTypePair(1, "IColToSingleCell_Volume");
+    ep->SetTypePair(2, "IVecToSingleCell_Volume");
+    this->aggregatorSlot << ep;
+    this->MakeSlotAvailable(&this->aggregatorSlot);
+
+    using VDC = VolumetricDataCall;
+    this->outDataSlot.SetCallback(VDC::ClassName(), VDC::FunctionName(VDC::IDX_GET_DATA), &ParticlesToDensityB200::getDataCallback);
+    this->outDataSlot.SetCallback(VDC::ClassName(), VDC::FunctionName(VDC::IDX_GET_EXTENTS), &ParticlesToDensityB200::getExtentCallback);
+    this->outDataSlot.SetCallback(VDC::ClassName(), VDC::FunctionName(VDC::IDX_GET_METADATA), &ParticlesToDensityB200::getMetadataCallback);
+    this->outDataSlot.SetCallback(VDC::ClassName(), VDC::FunctionName(VDC::IDX_START_ASYNC), &ParticlesToDensityB200::dummyCallback);
+    this->outDataSlot.SetCallback(VDC::ClassName(), VDC::FunctionName(VDC::IDX_STOP_ASYNC), &ParticlesToDensityB200::dummyCallback);
+    this->outDataSlot.SetCallback(VDC::ClassName(), VDC::FunctionName(VDC::IDX_TRY_GET_DATA), &ParticlesToDensityB200::dummyCallback);
+    this->MakeSlotAvailable(&this->outDataSlot);
+
+    this->outParticlesSlot.SetCallback(MultiParticleDataCall::ClassName(), MultiParticleDataCall::FunctionName(0), &ParticlesToDensityB200::getDataCallback);
+    this->outParticlesSlot.SetCallback(MultiParticleDataCall::ClassName(), MultiParticleDataCall::FunctionName(1), &ParticlesToDensityB200::getExtentCallback);
+    this->MakeSlotAvailable(&this->outParticlesSlot);
+
+    using TDC = datatools::table::TableDataCall;
+    this->outInfoSlot.SetCallback(TDC::ClassName(), TDC::FunctionName(0), &ParticlesToDensityB200::getDataCallback);
+    this->outInfoSlot.SetCallback(TDC::ClassName(), TDC::FunctionName(1), &ParticlesToDensityB200::getExtentCallback);
+    this->MakeSlotAvailable(&this->outInfoSlot);
+
+    this->xResSlot << new core::param::IntParam(16);
+    this->MakeSlotAvailable(&this->xResSlot);
+    this->yResSlot << new core::param::IntParam(16);
+    this->MakeSlotAvailable(&this->yResSlot);
+    this->zResSlot << new core::param::IntParam(16);
+    this->MakeSlotAvailable(&this->zResSlot);
+
+    this->cyclXSlot << new core::param::BoolParam(true);
+    this->MakeSlotAvailable(&this->cyclXSlot);
+    this->cyclYSlot << new core::param::BoolParam(true);
+    this->MakeSlotAvailable(&this->cyclYSlot);
+    this->cyclZSlot << new core::param::BoolParam(true);
+    this->MakeSlotAvailable(&this->cyclZSlot);
+
+    this->normalizeSlot << new core::param::BoolParam(true);
+    this->MakeSlotAvailable(&this->normalizeSlot);
+
+    this->sigmaSlot << new core::param::FloatParam(1.0f, FLT_MIN);
+    this->MakeSlotAvailable(&this->sigmaSlot);
+
+    this->surfaceSlot << new core::param::BoolParam(false);
+    this->MakeSlotAvailable(&this->surfaceSlot);
+
+    this->deviceSlot << new core::param::IntParam(0, 0);
+    this->MakeSlotAvailable(&this->deviceSlot);
+
+    this->inDataSlot.SetCompatibleCall<geocalls::MultiParticleDataCallDescription>();
+    this->MakeSlotAvailable(&this->inDataSlot);
+}
+
+ParticlesToDensityB200::~ParticlesToDensityB200() {
+    this->Release();
+}
+
+bool ParticlesToDensityB200::create() {
+    return true; // the context is created lazily on the device selected by the "device" parameter
+}
+
+void ParticlesToDensityB200::release() {
+    if (this->ctx != nullptr) {
+        mms_destroy(this->ctx);
+        this->ctx = nullptr;
+    }
+    this->metadata.MinValues = nullptr;
+    this->metadata.MaxValues = nullptr;
+    for (auto& s : this->metadata.SliceDists)
+        s = nullptr;
+}
+
+bool ParticlesToDensityB200::dummyCallback(core::Call&) {
+    return true;
+}
+
+bool ParticlesToDensityB200::anythingDirty() const {
+    return this->aggregatorSlot.IsDirty() || this->xResSlot.IsDirty() || this->yResSlot.IsDirty() || this->zResSlot.IsDirty() ||
+           this->cyclXSlot.IsDirty() || this->cyclYSlot.IsDirty() || this->cyclZSlot.IsDirty() || this->normalizeSlot.IsDirty() ||
+           this->sigmaSlot.IsDirty() || this->deviceSlot.IsDirty();
+}
+
+void ParticlesToDensityB200::resetDirty() {
+    for (auto* s : {&aggregatorSlot, &xResSlot, &yResSlot, &zResSlot, &cyclXSlot, &cyclYSlot, &cyclZSlot, &normalizeSlot, &sigmaSlot, &deviceSlot})
+        s->ResetDirty();
+}
+
+bool ParticlesToDensityB200::getExtentCallback(core::Call& c) {
+    auto* out = dynamic_cast<VolumetricDataCall*>(&c);
+    auto* outGrid = dynamic_cast<MultiParticleDataCall*>(&c);
+    auto* outInfo = dynamic_cast<datatools::table::TableDataCall*>(&c);
+    auto* in = this->inDataSlot.CallAs<MultiParticleDataCall>();
+    if (in == nullptr)
+        return false;
+    const unsigned int frameID = out != nullptr ? out->FrameID() : (outGrid != nullptr ? outGrid->FrameID() : 0);
+    in->SetFrameID(frameID, true);
+    if (!(*in)(1)) {
+        Log::DefaultLog.WriteError("ParticlesToDensityB200: could not get current frame extents (%u)", frameID);
+        return false;
+    }
+    core::AbstractGetData3DCall* o3 = out != nullptr ? static_cast<core::AbstractGetData3DCall*>(out) : static_cast<core::AbstractGetData3DCall*>(outGrid);
+    if (o3 != nullptr) {
+        o3->AccessBoundingBoxes().SetObjectSpaceBBox(in->GetBoundingBoxes().ObjectSpaceBBox());
+        o3->AccessBoundingBoxes().SetObjectSpaceClipBox(in->GetBoundingBoxes().ObjectSpaceClipBox());
+        o3->AccessBoundingBoxes().MakeScaledWorld(1.0f);
+        o3->SetFrameCount(in->FrameCount());
+    }
+    if (outInfo != nullptr) {
+        outInfo->SetDataHash(this->datahash);
+        outInfo->SetUnlocker(nullptr);
+        outInfo->SetFrameCount(in->FrameCount());
+    }
+    return true;
+}
+
+bool ParticlesToDensityB200::getMetadataCallback(core::Call& c) {
+    // the reference answers GET_METADATA with its extent callback and only fills the metadata in GET_DATA
+    // (ParticlesToDensity.cpp:100-102,249-293); we additionally publish what is already known
+    if (!this->getExtentCallback(c))
+        return false;
+    auto* out = dynamic_cast<VolumetricDataCall*>(&c);
+    auto* in = this->inDataSlot.CallAs<MultiParticleDataCall>();
+    if (out != nullptr && in != nullptr) {
+        this->fillMetadata(in);
+        out->SetMetadata(&this->metadata);
+    }
+    return true;
+}
+
+void ParticlesToDensityB200::fillMetadata(MultiParticleDataCall* in) {
+    auto& md = this->metadata;
+    md.Components = 1;
+    md.GridType = geocalls::GridType_t::CARTESIAN;
+    md.Resolution[0] = static_cast<size_t>(this->xResSlot.Param<core::param::IntParam>()->Value());
+    md.Resolution[1] = static_cast<size_t>(this->yResSlot.Param<core::param::IntParam>()->Value());
+    md.Resolution[2] = static_cast<size_t>(this->zResSlot.Param<core::param::IntParam>()->Value());
+    md.ScalarType = geocalls::ScalarType_t::FLOATING_POINT;
+    md.ScalarLength = sizeof(float);
+    this->minValue = this->minDens;
+    this->maxValue = this->maxDens;
+    md.MinValues = &this->minValue; // owned by the module, allocated once (the reference leaks a new[] per call)
+    md.MaxValues = &this->maxValue;
+    const auto bbox = in->AccessBoundingBoxes().ObjectSpaceBBox();
+    md.Extents[0] = bbox.Width();
+    md.Extents[1] = bbox.Height();
+    md.Extents[2] = bbox.Depth();
+    md.NumberOfFrames = 1;
+    for (int a = 0; a < 3; ++a) {
+        this->sliceDists[a] = md.Extents[a] / static_cast<float>(md.Resolution[a] - 1);
+        md.SliceDists[a] = &this->sliceDists[a];
+        md.IsUniform[a] = true;
+    }
+    md.Origin[0] = bbox.Left();
+    md.Origin[1] = bbox.Bottom();
+    md.Origin[2] = bbox.Back();
+    md.MemLoc = geocalls::MemoryLocation::RAM;
+}
+
+void ParticlesToDensityB200::surfaceBBox(MultiParticleDataCall* in) {
+    // "forSurfaceReconstruction" (ParticlesToDensity.cpp:749-799): grow the box by 10 % plus a two-voxel margin and make
+    // the voxels cubic by CHANGING sizex / sizey; the modified box only lives in the incoming call for this request.
+    const int sz = this->zResSlot.Param<core::param::IntParam>()->Value();
+    auto bb = in->AccessBoundingBoxes().ObjectSpaceBBox();
+    const float scale = 1.1f;
+    float w = bb.Width(), hgt = bb.Height(), d = bb.Depth();
+    float spacing = (d * scale) / sz;
+    const float newDepth = (d * scale) + 2 * spacing;
+    spacing = newDepth / sz;
+    auto fit = [&](float range, core::param::ParamSlot& slot) {
+        float n = (range * scale) + 2 * spacing;
+        int res = static_cast<int>(n / spacing);
+        const float rest = n / spacing - static_cast<float>(res);
+        n += (1 - rest) * spacing;
+        res += 1;
+        slot.Param<core::param::IntParam>()->SetValue(res);
+        return n;
+    };
+    const float newWidth = fit(w, this->xResSlot);
+    const float newHeight = fit(hgt, this->yResSlot);
+    const float l = bb.Left() - (newWidth - w) / 2, b = bb.Bottom() - (newHeight - hgt) / 2, k = bb.Back() - (newDepth - d) / 2;
+    const float r = bb.Right() + (newWidth - w) / 2, t = bb.Top() + (newHeight - hgt) / 2, f = bb.Front() + (newDepth - d) / 2;
+    in->AccessBoundingBoxes().SetObjectSpaceBBox(l, b, k, r, t, f);
+    in->AccessBoundingBoxes().SetObjectSpaceClipBox(l, b, k, r, t, f);
+}
+
+bool ParticlesToDensityB200::computeVolume(MultiParticleDataCall* in) {
+    const auto t0 = std::chrono::high_resolution_clock::now();
+    const int device = this->deviceSlot.Param<core::param::IntParam>()->Value();
+    if (this->ctx == nullptr || this->ctxDevice != device) {
+        if (this->ctx != nullptr)
+            mms_destroy(this->ctx);
+        this->ctx = nullptr;
+        mms_config cfg{device, 0};
+        if (mms_create(&this->ctx, &cfg) != MMS_OK) {
+            Log::DefaultLog.WriteError("ParticlesToDensityB200: %s", mms_last_error(nullptr));
+            return false;
+        }
+        this->ctxDevice = device;
+    }
+    const auto bbox = in->AccessBoundingBoxes().ObjectSpaceBBox();
+    mms_grid grid{};
+    grid.min[0] = bbox.Left(), grid.min[1] = bbox.Bottom(), grid.min[2] = bbox.Back();
+    grid.extent[0] = bbox.Width(), grid.extent[1] = bbox.Height(), grid.extent[2] = bbox.Depth();
+    grid.res[0] = this->xResSlot.Param<core::param::IntParam>()->Value();
+    grid.res[1] = this->yResSlot.Param<core::param::IntParam>()->Value();
+    grid.res[2] = this->zResSlot.Param<core::param::IntParam>()->Value();
+    grid.cyclic[0] = this->cyclXSlot.Param<core::param::BoolParam>()->Value();
+    grid.cyclic[1] = this->cyclYSlot.Param<core::param::BoolParam>()->Value();
+    grid.cyclic[2] = this->cyclZSlot.Param<core::param::BoolParam>()->Value();
+    mms_params p{};
+    p.mode = MMS_MODE_P2D_BUMP;
+    p.aggregator = this->aggregatorSlot.Param<core::param::EnumParam>()->Value();
+    p.normalize = this->normalizeSlot.Param<core::param::BoolParam>()->Value();
+    p.sigma = this->sigmaSlot.Param<core::param::FloatParam>()->Value();
+    p.radscale = 1.0f, p.gausslim = 3.0f;
+
+    std::vector<mms_list> lists;
+    size_t total = 0;
+    for (unsigned int i = 0; i < in->GetParticleListCount(); ++i) {
+        const auto& parts = in->AccessParticles(i);
+        if (parts.GetVertexDataType() == MultiParticleDataCall::Particles::VERTDATA_NONE)
+            continue;
+        mms_list l{};
+        l.vtx = parts.GetVertexData();
+        l.vtx_type = static_cast<int32_t>(parts.GetVertexDataType());
+        l.vtx_stride = parts.GetVertexDataStride();
+        l.col = parts.GetColourData();
+        l.col_type = static_cast<int32_t>(parts.GetColourDataType());
+        l.col_stride = parts.GetColourDataStride();
+        l.count = parts.GetCount();
+        l.global_radius = parts.GetGlobalRadius();
+        for (int k = 0; k < 4; ++k)
+            l.global_rgba[k] = parts.GetGlobalColour()[k];
+        l.irange[0] = parts.GetMinColourIndexValue();
+        l.irange[1] = parts.GetMaxColourIndexValue();
+        total += l.count;
+        lists.push_back(l);
+    }
+    auto fail = [&](const char* what) {
+        Log::DefaultLog.WriteError("ParticlesToDensityB200: %s: %s", what, mms_last_error(this->ctx));
+        return false;
+    };
+    if (mms_set_grid(this->ctx, &grid) != MMS_OK)
+        return fail("set_grid");
+    if (mms_set_params(this->ctx, &p) != MMS_OK)
+        return fail("set_params");
+    if (mms_clear_particles(this->ctx) != MMS_OK)
+        return fail("clear_particles");
+    if (mms_push_particles(this->ctx, static_cast<int32_t>(lists.size()), lists.data()) != MMS_OK)
+        return fail("push_particles");
+    if (mms_compute_density(this->ctx) != MMS_OK)
+        return fail("compute_density");
+    float mm[2] = {0, 0};
+    if (mms_get_density_range(this->ctx, mm) != MMS_OK)
+        return fail("get_density_range");
+    if (mms_get_density(this->ctx, &this->hostVolume, nullptr) != MMS_OK) // RAM contract of VolumetricDataCall::GetData()
+        return fail("get_density");
+    this->minDens = mm[0], this->maxDens = mm[1];
+    Log::DefaultLog.WriteInfo("ParticlesToDensityB200: Captured density %f -> %f", this->minDens, this->maxDens);
+    if (p.normalize) {
+        this->minDens = 0.0f;
+        this->maxDens = 1.0f;
+    }
+    const std::chrono::duration<float, std::milli> ms = std::chrono::high_resolution_clock::now() - t0;
+    Log::DefaultLog.WriteInfo("ParticlesToDensityB200: creation of %u x %u x %u volume from %llu particles took %f ms.", grid.res[0],
+        grid.res[1], grid.res[2], static_cast<unsigned long long>(total), ms.count());
+    return true;
+}
+
+bool ParticlesToDensityB200::getDataCallback(core::Call& c) {
+    auto* in = this->inDataSlot.CallAs<MultiParticleDataCall>();
+    if (in == nullptr)
+        return false;
+    auto* outVol = dynamic_cast<VolumetricDataCall*>(&c);
+    auto* outGrid = dynamic_cast<MultiParticleDataCall*>(&c);
+
+    if (outVol != nullptr || outGrid != nullptr) {
+        const unsigned int frameID = outVol != nullptr ? outVol->FrameID() : outGrid->FrameID();
+        do {
+            in->SetFrameID(frameID, true);
+            if (!(*in)(1)) {
+                Log::DefaultLog.WriteError("ParticlesToDensityB200: Unable to get extents.");
+                return false;
+            }
+            if (!(*in)(0)) {
+                Log::DefaultLog.WriteError("ParticlesToDensityB200: Unable to get data.");
+                return false;
+            }
+        } while (in->FrameID() != frameID);
+        if (this->time != in->FrameID() || this->in_datahash != in->DataHash() || this->anythingDirty() || !this->has_data) {
+            if (this->surfaceSlot.Param<core::param::BoolParam>()->Value())
+                this->surfaceBBox(in);
+            if (!this->computeVolume(in))
+                return false;
+            this->time = in->FrameID();
+            this->in_datahash = in->DataHash();
+            ++this->datahash;
+            this->resetDirty();
+            this->has_data = true;
+        }
+    }
+    if (outVol != nullptr) {
+        outVol->SetFrameID(this->time);
+        outVol->SetData(const_cast<float*>(this->hostVolume));
+        this->fillMetadata(in);
+        outVol->SetMetadata(&this->metadata);
+        outVol->SetDataHash(this->datahash);
+    }
+    if (auto* outInfo = dynamic_cast<datatools::table::TableDataCall*>(&c)) { // table rows exist only for the vector aggregator
+        outInfo->SetDataHash(this->datahash);
+        outInfo->Set(0, 0, nullptr, nullptr);
+    }
+    if (outGrid != nullptr) { // grid particles exist only for the vector aggregator, which this path does not implement
+        outGrid->SetFrameID(this->time);
+        outGrid->SetDataHash(this->datahash);
+        outGrid->SetParticleListCount(0);
+    }
+    in->Unlock();
+    return true;
+}

@@ -1,0 +1,79 @@
+/*
+ * ParticlesToDensityB200.h -- drop-in for datatools::ParticlesToDensity (plugins/datatools/src/ParticlesToDensity.h):
+ * same slots (inData / outData / outParticles / outInfo), same parameters with the same defaults, same call protocol;
+ * the volume is computed by libmmsurf on a B200 instead of createVolumeCPU.
+ */
+#pragma once
+
+#include <cstddef>
+#include <limits>
+
+#include "geometry_calls/MultiParticleDataCall.h"
+#include "geometry_calls/VolumetricDataCall.h"
+#include "mmcore/CalleeSlot.h"
+#include "mmcore/CallerSlot.h"
+#include "mmcore/Module.h"
+#include "mmcore/param/ParamSlot.h"
+
+#include "mmsurf.h"
+
+namespace megamol::b200surf {
+
+class ParticlesToDensityB200 : public core::Module {
+public:
+    static const char* ClassName() {
+        return "ParticlesToDensityB200";
+    }
+    static const char* Description() {
+        return "Computes a density volume from particles on a B200 (drop-in for ParticlesToDensity)";
+    }
+    /** No CPU fallback: the module is only available where libmmsurf finds an sm_100 device. */
+    static bool IsAvailable();
+
+    ParticlesToDensityB200();
+    ~ParticlesToDensityB200() override;
+
+    /** Device-resident hand-off for IsoSurfaceB200: the context holding the volume of the last GetData. */
+    mms_ctx* Context() const {
+        return this->ctx;
+    }
+    std::size_t VolumeHash() const {
+        return this->datahash;
+    }
+
+protected:
+    bool create() override;
+    void release() override;
+
+private:
+    bool getExtentCallback(core::Call& c);
+    bool getMetadataCallback(core::Call& c);
+    bool getDataCallback(core::Call& c);
+    bool dummyCallback(core::Call& c);
+
+    bool anythingDirty() const;
+    void resetDirty();
+    bool computeVolume(geocalls::MultiParticleDataCall* in);
+    void fillMetadata(geocalls::MultiParticleDataCall* in);
+    void surfaceBBox(geocalls::MultiParticleDataCall* in);
+
+    core::param::ParamSlot aggregatorSlot, xResSlot, yResSlot, zResSlot, cyclXSlot, cyclYSlot, cyclZSlot, normalizeSlot,
+        sigmaSlot, surfaceSlot;
+    core::param::ParamSlot deviceSlot; // extra: CUDA device ordinal
+    core::CalleeSlot outDataSlot, outParticlesSlot, outInfoSlot;
+    core::CallerSlot inDataSlot;
+
+    mms_ctx* ctx = nullptr;
+    int ctxDevice = -1;
+    const float* hostVolume = nullptr;
+    std::size_t in_datahash = std::numeric_limits<std::size_t>::max();
+    std::size_t datahash = 0;
+    unsigned int time = 0;
+    float minDens = 0.0f, maxDens = 0.0f;
+    bool has_data = false;
+    geocalls::VolumetricDataCall::Metadata metadata;
+    double minValue = 0.0, maxValue = 0.0;
+    float sliceDists[3] = {0, 0, 0};
+};
+
+} // namespace megamol::b200surf

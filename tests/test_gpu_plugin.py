@@ -1,0 +1,116 @@
+"""GPU suite: the MegaMol drop-in modules (plugin/b200surf, compiled against the reference headers into
+oracle/_ref/libmmplug.so) next to the UNMODIFIED reference modules (oracle/_ref/libmmref.so), both driven through the
+reference's own Module / CallerSlot / CalleeSlot / Call machinery by the same harness code."""
+import numpy as np
+import pytest
+
+from megamol_b200 import synth
+from tests import helpers as H
+
+rb = pytest.importorskip("oracle.ref_binding")
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(not (rb.available(rb.REF_LIB) and rb.available(rb.PLUG_LIB)), reason="oracle/_ref libraries not built")]
+
+
+@pytest.fixture(scope="module")
+def ref():
+    h = rb.Harness(rb.REF_LIB)
+    h.set_threads(4)
+    return h
+
+
+@pytest.fixture(scope="module")
+def plug():
+    return rb.Harness(rb.PLUG_LIB)
+
+
+def feed(h, lists, bbox, res, **kw):
+    h.set_particles(lists, bbox)
+    h.set_p2d_params(res, **kw)
+
+
+@pytest.mark.parametrize("cyc,norm", [(True, True), (False, False), (True, False)])
+def test_volume_call_matches_reference(ref, plug, cyc, norm):
+    n, box, res = 6000, 12.0, (28, 24, 20)
+    xyz = synth.uniform_box(n, box, seed=321)
+    lists = [dict(vtx=xyz, vtx_type=rb.VERT_FLOAT_XYZ, count=n, global_radius=0.8)]
+    outs = []
+    for h in (ref, plug):
+        feed(h, lists, (0, 0, 0, box, box, box), res, cyclic=(cyc,) * 3, normalize=norm, sigma=1.0)
+        outs.append(h.pull_volume())
+    (rv, rm), (pv, pm) = outs
+    for k in ("resolution", "components", "origin", "slicedist"):
+        assert rm[k] == pm[k], k
+    assert H.density_close(pv, rv) < H.DENSITY_RTOL
+    assert abs(pm["min"] - rm["min"]) <= 1e-5 and abs(pm["max"] - rm["max"]) <= 1e-5 * max(1.0, abs(rm["max"]))
+
+
+def test_interleaved_xyzr_rgba_and_intensity(ref, plug):
+    """MMPLD-style interleaved list (x y z r | R G B A floats, stride 32), aggregator 1 uses the colour's R channel."""
+    n = 3000
+    buf = np.zeros((n, 8), np.float32)
+    buf[:, :3] = synth.uniform_box(n, 9.0, seed=99)
+    buf[:, 3] = 0.4 + 0.5 * synth.uniform(5, 0, n, 0)
+    buf[:, 4] = 0.2 + synth.uniform(6, 0, n, 0)
+    buf[:, 7] = 1.0
+    lists = [dict(vtx=buf, vtx_type=rb.VERT_FLOAT_XYZR, vtx_stride=32, count=n, col=buf.ctypes.data + 16, col_type=rb.COL_FLOAT_RGBA,
+                  col_stride=32)]
+    vols = []
+    for h in (ref, plug):
+        feed(h, lists, (0, 0, 0, 9, 9, 9), (18, 18, 18), cyclic=(True,) * 3, normalize=False, sigma=1.0, aggregator=1)
+        vols.append(h.pull_volume()[0])
+    assert H.density_close(vols[1], vols[0]) < H.DENSITY_RTOL
+
+
+def test_datahash_protocol_matches_reference(ref, plug):
+    xyz = synth.uniform_box(800, 4.0, seed=5)
+    lists = [dict(vtx=xyz, vtx_type=rb.VERT_FLOAT_XYZ, count=800, global_radius=0.5)]
+    deltas = []
+    for h in (ref, plug):
+        feed(h, lists, (0, 0, 0, 4, 4, 4), (8, 8, 8))
+        _, a = h.pull_volume()
+        _, b = h.pull_volume()                       # nothing changed -> no recompute, same hash
+        h.set_p2d_params((8, 8, 8), sigma=0.9)       # parameter dirty -> recompute, hash + 1
+        _, c = h.pull_volume()
+        h.set_particles(lists, (0, 0, 0, 4, 4, 4))   # new input data hash -> recompute, hash + 1
+        _, d = h.pull_volume()
+        deltas.append((b["datahash"] - a["datahash"], c["datahash"] - b["datahash"], d["datahash"] - c["datahash"]))
+    assert deltas[0] == deltas[1] == (0, 1, 1)
+
+
+def test_mesh_call_contract(ref, plug, oracle):
+    """CallTriMeshData from IsoSurfaceB200: same contract as the reference (one unindexed soup, GetTriCount()==0), vertices =
+    marching cubes of the very volume the VolumetricDataCall delivers."""
+    n, box, res = 5000, 10.0, (24, 24, 24)
+    xyz = synth.uniform_box(n, box, seed=11)
+    lists = [dict(vtx=xyz, vtx_type=rb.VERT_FLOAT_XYZ, count=n, global_radius=1.0)]
+    feed(plug, lists, (0, 0, 0, box, box, box), res, cyclic=(False,) * 3, normalize=True)
+    vol, meta = plug.pull_volume()
+    m = plug.pull_mesh(0.5)
+    feed(ref, lists, (0, 0, 0, box, box, box), res, cyclic=(False,) * 3, normalize=True)
+    ref.pull_volume()
+    rmesh = ref.pull_mesh(0.5, copy=False)
+    assert m["ntris"] == rmesh["ntris"] == 0 and m["nverts"] % 3 == 0 and m["nverts"] > 0
+    total, _, _ = oracle.mc_count(vol, 0.5)
+    assert m["nverts"] == 3 * total
+    pos, nrm, _ = oracle.mc_emit(vol, meta["origin"], np.array(meta["slicedist"], np.float32), 0.5)
+    cell = np.array(meta["slicedist"], np.float64)
+    assert np.abs((m["pos"].reshape(-1, 3, 3) - pos) / cell).max() <= H.VERTEX_TOL_CELLS
+    assert np.abs(m["nrm"].reshape(-1, 3, 3) - nrm).max() < 1e-4
+    # a second pull without changes must not recompute and must hand out the same data
+    m2 = plug.pull_mesh(0.5)
+    assert m2["nverts"] == m["nverts"] and np.array_equal(m2["pos"], m["pos"])
+    # changing isoval recomputes
+    m3 = plug.pull_mesh(0.3)
+    assert m3["nverts"] != m["nverts"]
+
+
+def test_for_surface_reconstruction_bbox(ref, plug):
+    xyz = synth.uniform_box(2000, 6.0, seed=17)
+    lists = [dict(vtx=xyz, vtx_type=rb.VERT_FLOAT_XYZ, count=2000, global_radius=0.7)]
+    outs = []
+    for h in (ref, plug):
+        feed(h, lists, (0, 0, 0, 6, 5, 4), (16, 16, 16), cyclic=(False,) * 3, normalize=False, for_surface=True)
+        outs.append(h.pull_volume(copy=False)[1])
+    assert outs[0]["resolution"] == outs[1]["resolution"]
+    assert np.allclose(outs[0]["origin"], outs[1]["origin"]) and np.allclose(outs[0]["slicedist"], outs[1]["slicedist"])
