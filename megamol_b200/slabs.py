@@ -63,6 +63,56 @@ def destination_masks(Z, f, slabs, sz: int, cyclic_z: bool, xp):
     return masks
 
 
+def route_and_exchange(xyz, radius, slabs, sz, zmin, sdz, cyclic_z):
+    """All-to-all-v of particle records by destination slab (torch tensors on any device; NCCL or gloo).
+    xyz: [n, k] float32 rows whose column 2 is z; radius: float (global radius) or [n] tensor.
+    Returns the rows this rank needs (own slab + halo), concatenated in SOURCE-RANK order = global particle order."""
+    import torch
+    import torch.distributed as dist
+    r = radius if torch.is_tensor(radius) else torch.full((xyz.shape[0],), float(radius), device=xyz.device, dtype=torch.float32)
+    Z, f = home_and_filter_z(xyz[:, 2], r, zmin, sdz, torch)
+    masks = destination_masks(Z, f, slabs, sz, cyclic_z, torch)
+    parts = [xyz[m] for m in masks]
+    send_counts = torch.tensor([p.shape[0] for p in parts], device=xyz.device, dtype=torch.int64)
+    recv_counts = torch.empty_like(send_counts)
+    dist.all_to_all_single(recv_counts, send_counts)
+    sc, rc = send_counts.tolist(), recv_counts.tolist()
+    send = torch.cat(parts, 0).contiguous()
+    recv = torch.empty((sum(rc), xyz.shape[1]), device=xyz.device, dtype=xyz.dtype)
+    dist.all_to_all_single(recv, send, output_split_sizes=rc, input_split_sizes=sc)
+    return recv
+
+
+def gather_rows_to_root(local, rank, world, out=None):
+    """all-gather of row counts, then every rank's [n_g, k] tensor travels to rank 0 (send/recv), concatenated in rank
+    (= slab = cell-linear) order.  Returns (tensor on rank 0 | None, counts)."""
+    import torch
+    import torch.distributed as dist
+    cnt = torch.tensor([local.shape[0]], device=local.device, dtype=torch.int64)
+    allc = [torch.empty_like(cnt) for _ in range(world)]
+    dist.all_gather(allc, cnt)
+    counts = [int(c.item()) for c in allc]
+    if rank == 0:
+        total = sum(counts)
+        if out is None or out.shape[0] < total:
+            out = torch.empty((total,) + tuple(local.shape[1:]), device=local.device, dtype=local.dtype)
+        out[:counts[0]].copy_(local)
+        off = counts[0]
+        ops = []
+        for g in range(1, world):
+            if counts[g]:
+                ops.append(dist.P2POp(dist.irecv, out[off:off + counts[g]], g))
+            off += counts[g]
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        return out, counts
+    if local.shape[0]:
+        for req in dist.batch_isend_irecv([dist.P2POp(dist.isend, local.contiguous(), 0)]):
+            req.wait()
+    return None, counts
+
+
 class SlabJob:
     """The bench/test driver: generates this rank's chunk of the synthetic frame and runs full steps."""
 
@@ -158,65 +208,21 @@ class SlabJob:
 
     def _exchange(self, xyz_dev):
         """all-to-all-v of the particles by destination slab; returns this rank's [n,3] tensor (source-rank order)."""
-        torch = self.torch
-        import torch.distributed as dist
-        t0 = torch.cuda.Event(enable_timing=True)
-        t1 = torch.cuda.Event(enable_timing=True)
-        t0.record()
-        r = torch.full((xyz_dev.shape[0],), self.radius, device=xyz_dev.device, dtype=torch.float32)
-        Z, f = home_and_filter_z(xyz_dev[:, 2], r, 0.0, self.sdz, torch)
-        masks = destination_masks(Z, f, self.slabs, self.res[2], bool(self.cyclic[2]), torch)
-        parts = [xyz_dev[m] for m in masks]
-        send_counts = torch.tensor([p.shape[0] for p in parts], device=xyz_dev.device, dtype=torch.int64)
-        recv_counts = torch.empty_like(send_counts)
-        dist.all_to_all_single(recv_counts, send_counts)
-        sc, rc = send_counts.tolist(), recv_counts.tolist()
-        send = torch.cat(parts, 0).contiguous()
-        recv = torch.empty((sum(rc), 3), device=xyz_dev.device, dtype=torch.float32)
-        dist.all_to_all_single(recv, send, output_split_sizes=rc, input_split_sizes=sc)
-        t1.record()
-        self._ex_events = (t0, t1)
-        return recv
+        return route_and_exchange(xyz_dev, self.radius, self.slabs, self.res[2], 0.0, self.sdz, bool(self.cyclic[2]))
 
     def _gather_mesh(self):
         """all-gather of triangle counts, then the per-slab vertex/normal arrays travel to rank 0 over NCCL."""
         torch = self.torch
-        import torch.distributed as dist
         nverts, ppos, pnrm = self.surf.mesh_device()
-        cnt = torch.tensor([nverts], device=self.dev, dtype=torch.int64)
-        allc = [torch.empty_like(cnt) for _ in range(self.world)]
-        dist.all_gather(allc, cnt)
-        counts = [int(c.item()) for c in allc]
-        self.last["tri_counts"] = [c // 3 for c in counts]
 
         def view(ptr, n):
             if n == 0:
-                return torch.empty((0,), device=self.dev, dtype=torch.float32)
-            return _tensor_from_ptr(torch, ptr, n * 3, self.dev)
-        mine_p, mine_n = view(ppos, nverts), view(pnrm, nverts)
-        if self.rank == 0:
-            total = sum(counts)
-            if getattr(self, "_gpos", None) is None or self._gpos.numel() < total * 3:
-                self._gpos = torch.empty((total * 3,), device=self.dev, dtype=torch.float32)
-                self._gnrm = torch.empty((total * 3,), device=self.dev, dtype=torch.float32)
-            off = 0
-            ops = []
-            for g, c in enumerate(counts):
-                if g == 0:
-                    self._gpos[:c * 3].copy_(mine_p)
-                    self._gnrm[:c * 3].copy_(mine_n)
-                elif c:
-                    ops.append(dist.P2POp(dist.irecv, self._gpos[off * 3:(off + c) * 3], g))
-                    ops.append(dist.P2POp(dist.irecv, self._gnrm[off * 3:(off + c) * 3], g))
-                off += c
-            if ops:
-                for req in dist.batch_isend_irecv(ops):
-                    req.wait()
-            self.last["gathered_verts"] = total
-        elif nverts:
-            ops = [dist.P2POp(dist.isend, mine_p, 0), dist.P2POp(dist.isend, mine_n, 0)]
-            for req in dist.batch_isend_irecv(ops):
-                req.wait()
+                return torch.empty((0, 3), device=self.dev, dtype=torch.float32)
+            return _tensor_from_ptr(torch, ptr, n * 3, self.dev).view(n, 3)
+        self._gpos, counts = gather_rows_to_root(view(ppos, nverts), self.rank, self.world, getattr(self, "_gpos", None))
+        self._gnrm, _ = gather_rows_to_root(view(pnrm, nverts), self.rank, self.world, getattr(self, "_gnrm", None))
+        self.last["tri_counts"] = [c // 3 for c in counts]
+        self.last["gathered_verts"] = sum(counts)
 
     # ---- steps ------------------------------------------------------------------------------------------------
     def _compute(self, xyz_ptr, n):
@@ -270,8 +276,8 @@ class SlabJob:
                 if getattr(self, "_hpos", None) is None or self._hpos.numel() < tot:
                     self._hpos = torch.empty((tot,), dtype=torch.float32, pin_memory=True)
                     self._hnrm = torch.empty((tot,), dtype=torch.float32, pin_memory=True)
-                self._hpos[:tot].copy_(self._gpos[:tot], non_blocking=True)
-                self._hnrm[:tot].copy_(self._gnrm[:tot], non_blocking=True)
+                self._hpos[:tot].copy_(self._gpos.view(-1)[:tot], non_blocking=True)
+                self._hnrm[:tot].copy_(self._gnrm.view(-1)[:tot], non_blocking=True)
             torch.cuda.current_stream().synchronize()
 
     # ---- accounting -------------------------------------------------------------------------------------------
