@@ -297,7 +297,7 @@ class SlabJob:
         tris = self.local_tris()
         if self.world > 1:
             import torch.distributed as dist
-            t = self.torch.tensor([tris], device=self.dev, dtype=torch.int64)
+            t = self.torch.tensor([tris], device=self.dev, dtype=self.torch.int64)
             dist.all_reduce(t)
             tris = int(t.item())
         self._tris_total = tris
