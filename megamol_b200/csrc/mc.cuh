@@ -35,6 +35,7 @@ struct McGeo {
     float org[3], sd[3];
     float rinv[3][3];  // rinv[a][n] = 1/(n*sd[a]), n = 1, 2 (gradient: one-sided / central)
     float iso;
+    int debug;         // profiling experiments only (MMS_DEBUG_MC): 1 no stores, 2 skip phase C, 4 skip B2, 8 skip B1
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -61,8 +62,10 @@ __device__ __forceinline__ int cubeIndexSmem(const float* f, int strideY, int st
 __global__ void __launch_bounds__(MC_THREADS) mc_count_kernel(McGeo m, const float* __restrict__ vol, unsigned* __restrict__ segCount,
     unsigned char* __restrict__ triCount) {
     __shared__ float f[MC_NZ][MC_NY][MC_NX + 1];
+    __shared__ unsigned char sCount[256]; // per-lane indexed lookups: shared memory, not the (serialising) constant cache
     const int x0 = blockIdx.x * MCX, y0 = blockIdx.y * MCY, zc0 = m.cz0 + blockIdx.z * MCZ; // global cell coords
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    sCount[threadIdx.x] = static_cast<unsigned char>(kCaseWords[threadIdx.x] & 15ull);
     // rows of 33 nodes, one warp per row (clamped; clamped duplicates only feed cells that are masked out below)
     for (int r = warp; r < MC_NZ * MC_NY; r += MC_THREADS / 32) {
         const int iy = r % MC_NY, iz = r / MC_NY;
@@ -80,7 +83,7 @@ __global__ void __launch_bounds__(MC_THREADS) mc_count_kernel(McGeo m, const flo
         unsigned n = 0;
         if (cxi < m.cx) {
             const int ci = cubeIndexSmem(&f[lz][ly][lane], MC_NX + 1, (MC_NX + 1) * MC_NY, m.iso);
-            n = static_cast<unsigned>(kCaseWords[ci] & 15ull);
+            n = sCount[ci];
             if (triCount) triCount[cxi + static_cast<size_t>(m.cx) * (cyi + static_cast<size_t>(m.cy) * (czi - m.cz0))] = static_cast<unsigned char>(n);
         }
         const unsigned tot = __reduce_add_sync(0xffffffffu, n);
@@ -89,12 +92,18 @@ __global__ void __launch_bounds__(MC_THREADS) mc_count_kernel(McGeo m, const flo
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// emit
+// emit: z-marching, software-pipelined
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int EX = 32, EY = 8, EZ = 2;                      // cells per block tile
-constexpr int ENX = EX + 1, ENY = EY + 1, ENZ = EZ + 1;     // nodes
+// A block owns a 32x8-cell column and marches through EM_STEPS steps of EZ = 2 cell layers.  The density planes live
+// in a 7-slot ring in shared memory (5 planes of the current step incl. the gradient halo + the 2 planes the next
+// step adds); the next step's planes are fetched with cp.async while the current step computes, so the global-load
+// latency is paid once per block instead of once per tile, and no plane is loaded twice inside a column chunk.
+constexpr int EX = 32, EY = 8, EZ = 2;                      // cells per step
+constexpr int ENX = EX + 1, ENY = EY + 1, ENZ = EZ + 1;     // nodes per step
 constexpr int EHX = EX + 3, EHY = EY + 3, EHZ = EZ + 3;     // nodes + gradient halo
 constexpr int EHXP = EHX + 1;                               // padded row
+constexpr int ERING = EHZ + EZ;                             // plane slots
+constexpr int EM_STEPS = 16;                                // steps per block (32 cell layers)
 constexpr int E_XEDGES = ENZ * ENY * EX;                    // 864  x-edges: ix < 32
 constexpr int E_YEDGES = ENZ * EY * ENX;                    // 792  y-edges: iy < 8
 constexpr int E_ZEDGES = EZ * ENY * ENX;                    // 594  z-edges: iz < 2
@@ -103,10 +112,12 @@ constexpr int E_MAXROWTRIS = 160;
 
 struct McEmitShared {
     float4 edge[E_EDGES];               // {interpolated coordinate along the edge's axis, nx, ny, nz}
-    float halo[EHZ][EHY][EHXP];
+    float ring[ERING][EHY][EHXP];       // plane with global node index z sits in slot (z + 1) mod ERING
     unsigned short crossList[E_EDGES];
     unsigned char triOwner[MC_THREADS / 32][E_MAXROWTRIS];
-    float tabX[ENX], tabY[ENY], tabZ[ENZ]; // node positions float(idx)*sd + origin (ParticlesToDensity.cpp:605)
+    float tabX[ENX], tabY[ENY];         // node positions float(idx)*sd + origin (ParticlesToDensity.cpp:605)
+    unsigned segOff[EM_STEPS * EZ * EY + 1][2]; // per row of the chunk: first triangle, triangle count
+    int stepActive[EM_STEPS];
     int anyActive;
     int ncross;
 };
@@ -126,165 +137,231 @@ __device__ __forceinline__ int edgeIndex(int axis, int ix, int iy, int iz) {
     return E_ZBASE + (iz * ENY + iy) * ENX + ix;
 }
 
+__device__ __forceinline__ int ringSlot(int zNode) { // zNode >= -1
+    return (zNode + 1) % ERING;
+}
+
+__device__ __forceinline__ void cpAsync4(float* smemDst, const float* gmemSrc) {
+    const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smemDst));
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gmemSrc));
+}
+
 template<bool COLOUR>
 __global__ void __launch_bounds__(MC_THREADS) mc_emit_kernel(McGeo m, const float* __restrict__ vol, const float* __restrict__ rgb,
     const unsigned* __restrict__ segOffset, float* __restrict__ outPos, float* __restrict__ outNrm, float* __restrict__ outCol) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     McEmitShared& sh = *reinterpret_cast<McEmitShared*>(smemRaw);
-    const int x0 = blockIdx.x * EX, y0 = blockIdx.y * EY, zc0 = m.cz0 + blockIdx.z * EZ;
+    const int x0 = blockIdx.x * EX, y0 = blockIdx.y * EY;
+    const int zcBeg = m.cz0 + blockIdx.z * (EM_STEPS * EZ);           // first global cell layer of this block
+    const int zcEnd = min(zcBeg + EM_STEPS * EZ, m.cz0 + m.cnz);      // exclusive
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-    // ---- skip tiles without triangles -----------------------------------------------------------------------------
-    if (threadIdx.x == 0) sh.anyActive = 0, sh.ncross = 0;
+    // ---- which rows / steps have triangles (one global read per row of the chunk) -----------------------------------
+    if (threadIdx.x < EM_STEPS) sh.stepActive[threadIdx.x] = 0;
+    if (threadIdx.x == 0) sh.anyActive = 0;
     __syncthreads();
-    if (threadIdx.x < EY * EZ) {
-        const int ly = threadIdx.x % EY, lz = threadIdx.x / EY;
-        const int cyi = y0 + ly, czi = zc0 + lz;
-        if (cyi < m.cy && czi < m.cz0 + m.cnz) {
+    for (int r = threadIdx.x; r < EM_STEPS * EZ * EY; r += MC_THREADS) {
+        const int ly = r % EY, lzc = r / EY;
+        const int cyi = y0 + ly, czi = zcBeg + lzc;
+        unsigned off = 0, cnt = 0;
+        if (cyi < m.cy && czi < zcEnd) {
             const size_t seg = blockIdx.x + static_cast<size_t>(m.nsegx) * (cyi + static_cast<size_t>(m.cy) * (czi - m.cz0));
-            if (segOffset[seg + 1] != segOffset[seg]) sh.anyActive = 1;
+            off = segOffset[seg];
+            cnt = segOffset[seg + 1] - off;
         }
+        sh.segOff[r][0] = off, sh.segOff[r][1] = cnt;
+        if (cnt) sh.stepActive[lzc / EZ] = 1, sh.anyActive = 1;
     }
     __syncthreads();
     if (!sh.anyActive) return;
 
-    // ---- A: density with a one-node halo; indices clamped to the GLOBAL grid ----------------------------------------
-    for (int r = warp; r < EHZ * EHY; r += MC_THREADS / 32) {
-        const int iy = r % EHY, iz = r / EHY;
-        const int y = min(max(y0 + iy - 1, 0), m.sy - 1);
-        const int zg = min(max(zc0 + iz - 1, 0), m.szGlobal - 1);
+    // ---- plane loader: rows of one plane, clamped to the GLOBAL grid and to the slab -------------------------------------
+    auto loadPlane = [&](int zNode) { // all threads; asynchronous
+        const int zg = min(max(zNode, 0), m.szGlobal - 1);
         const int zl = min(max(zg - m.zPlane0, 0), m.nzPlanes - 1);
-        const float* row = vol + static_cast<size_t>(m.sx) * (y + static_cast<size_t>(m.sy) * zl);
-        sh.halo[iz][iy][lane] = row[min(max(x0 + lane - 1, 0), m.sx - 1)];
-        if (lane < EHX - 32) sh.halo[iz][iy][32 + lane] = row[min(max(x0 + 32 + lane - 1, 0), m.sx - 1)];
-    }
+        float* dst = &sh.ring[ringSlot(zNode)][0][0];
+        for (int i = threadIdx.x; i < EHY * EHXP; i += MC_THREADS) {
+            const int ix = i % EHXP, iy = i / EHXP;
+            if (ix >= EHX) continue;
+            const int x = min(max(x0 + ix - 1, 0), m.sx - 1), y = min(max(y0 + iy - 1, 0), m.sy - 1);
+            cpAsync4(dst + iy * EHXP + ix, vol + x + static_cast<size_t>(m.sx) * (y + static_cast<size_t>(m.sy) * zl));
+        }
+    };
+    // first active step: its five planes; later steps add two planes each
+    int step = 0;
+    while (step < EM_STEPS && !sh.stepActive[step]) ++step;
+    int loadedUpTo = zcBeg + step * EZ - 2; // highest node plane present in the ring (none yet)
     if (threadIdx.x < ENX) sh.tabX[threadIdx.x] = __fadd_rn(__fmul_rn((float)(x0 + threadIdx.x), m.sd[0]), m.org[0]);
     else if (threadIdx.x < ENX + ENY) sh.tabY[threadIdx.x - ENX] = __fadd_rn(__fmul_rn((float)(y0 + threadIdx.x - ENX), m.sd[1]), m.org[1]);
-    else if (threadIdx.x < ENX + ENY + ENZ)
-        sh.tabZ[threadIdx.x - ENX - ENY] = __fadd_rn(__fmul_rn((float)(zc0 + threadIdx.x - ENX - ENY), m.sd[2]), m.org[2]);
-    __syncthreads();
 
-    // ---- B1: crossed edges -> crossList (order is irrelevant) ----------------------------------------------------
-    // rounds 0..26: one warp per node row, lanes = nodes 0..31; round 27: the 27 nodes of column 32, one per lane
-    for (int r = warp; r < ENZ * ENY + 1; r += MC_THREADS / 32) {
-        const bool lastCol = r == ENZ * ENY;
-        const int rr = lastCol ? lane : r;
-        const bool active = !lastCol || lane < ENZ * ENY;
-        const int iy = rr % ENY, iz = (rr / ENY) % ENZ;
-        const int ix = lastCol ? EX : lane;
-        bool cx = false, cy = false, cz = false;
-        if (active) {
-            const bool b0 = sh.halo[iz + 1][iy + 1][ix + 1] < m.iso;
-            if (ix < EX) cx = b0 != (sh.halo[iz + 1][iy + 1][ix + 2] < m.iso);
-            if (iy < EY) cy = b0 != (sh.halo[iz + 1][iy + 2][ix + 1] < m.iso);
-            if (iz < EZ) cz = b0 != (sh.halo[iz + 2][iy + 1][ix + 1] < m.iso);
-        }
-        const unsigned bx = __ballot_sync(0xffffffffu, cx), by = __ballot_sync(0xffffffffu, cy), bz = __ballot_sync(0xffffffffu, cz);
-        const int nx = __popc(bx), ny = __popc(by), nz = __popc(bz);
-        if (nx + ny + nz == 0) continue;
-        int base = 0;
-        if (lane == 0) base = atomicAdd(&sh.ncross, nx + ny + nz);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        const unsigned lt = (1u << lane) - 1u;
-        if (cx) sh.crossList[base + __popc(bx & lt)] = static_cast<unsigned short>(edgeIndex(0, ix, iy, iz));
-        if (cy) sh.crossList[base + nx + __popc(by & lt)] = static_cast<unsigned short>(edgeIndex(1, ix, iy, iz));
-        if (cz) sh.crossList[base + nx + ny + __popc(bz & lt)] = static_cast<unsigned short>(edgeIndex(2, ix, iy, iz));
-    }
-    __syncthreads();
-
-    // ---- B2: one vertex per crossed edge ------------------------------------------------------------------------
-    const int ncross = sh.ncross;
     const float r1x = m.rinv[0][1], r2x = m.rinv[0][2], r1y = m.rinv[1][1], r2y = m.rinv[1][2], r1z = m.rinv[2][1], r2z = m.rinv[2][2];
-    // no node of this tile touches the global border -> plain central differences
-    const bool interior = x0 > 0 && x0 + EX < m.sx - 1 && y0 > 0 && y0 + EY < m.sy - 1 && zc0 > 0 && zc0 + EZ < m.szGlobal - 1;
-    for (int c = threadIdx.x; c < ncross; c += MC_THREADS) {
-        const int id = sh.crossList[c];
-        int axis, ix, iy, iz;
-        if (id < E_YBASE) { axis = 0; ix = id % EX; const int t = id / EX; iy = t % ENY; iz = t / ENY; }
-        else if (id < E_ZBASE) { axis = 1; const int q = id - E_YBASE; ix = q % ENX; const int t = q / ENX; iy = t % EY; iz = t / EY; }
-        else { axis = 2; const int q = id - E_ZBASE; ix = q % ENX; const int t = q / ENX; iy = t % ENY; iz = t / ENY; }
-        const int jx = ix + (axis == 0), jy = iy + (axis == 1), jz = iz + (axis == 2);
-        // gradient at a node: (f(+) - f(-)) * 1/(n*sd), samples clamped at the GLOBAL grid border
-        auto grad = [&](int nx_, int ny_, int nz_, float& gx, float& gy, float& gz) {
-            const float* h = &sh.halo[nz_ + 1][ny_ + 1][nx_ + 1];
-            if (interior) {
-                gx = __fmul_rn(__fsub_rn(h[1], h[-1]), r2x);
-                gy = __fmul_rn(__fsub_rn(h[EHXP], h[-EHXP]), r2y);
-                gz = __fmul_rn(__fsub_rn(h[EHXP * EHY], h[-EHXP * EHY]), r2z);
-            } else {
-                const int gxi = x0 + nx_, gyi = y0 + ny_, gzi = zc0 + nz_;
-                const int xm = gxi > 0 ? -1 : 0, xp = gxi < m.sx - 1 ? 1 : 0;
-                const int ym = gyi > 0 ? -1 : 0, yp = gyi < m.sy - 1 ? 1 : 0;
-                const int zm = gzi > 0 ? -1 : 0, zp = gzi < m.szGlobal - 1 ? 1 : 0;
-                gx = xp > xm ? __fmul_rn(__fsub_rn(h[xp], h[xm]), xp - xm == 2 ? r2x : r1x) : 0.0f;
-                gy = yp > ym ? __fmul_rn(__fsub_rn(h[yp * EHXP], h[ym * EHXP]), yp - ym == 2 ? r2y : r1y) : 0.0f;
-                gz = zp > zm ? __fmul_rn(__fsub_rn(h[zp * EHXP * EHY], h[zm * EHXP * EHY]), zp - zm == 2 ? r2z : r1z) : 0.0f;
-            }
-        };
-        const float fa = sh.halo[iz + 1][iy + 1][ix + 1], fb = sh.halo[jz + 1][jy + 1][jx + 1];
-        const float t01 = __fdiv_rn(__fsub_rn(m.iso, fa), __fsub_rn(fb, fa));
-        const float pa = axis == 0 ? sh.tabX[ix] : (axis == 1 ? sh.tabY[iy] : sh.tabZ[iz]);
-        const float pb = axis == 0 ? sh.tabX[jx] : (axis == 1 ? sh.tabY[jy] : sh.tabZ[jz]);
-        float gax, gay, gaz, gbx, gby, gbz;
-        grad(ix, iy, iz, gax, gay, gaz);
-        grad(jx, jy, jz, gbx, gby, gbz);
-        const float gx = __fadd_rn(gax, __fmul_rn(t01, __fsub_rn(gbx, gax)));
-        const float gy = __fadd_rn(gay, __fmul_rn(t01, __fsub_rn(gby, gay)));
-        const float gz = __fadd_rn(gaz, __fmul_rn(t01, __fsub_rn(gbz, gaz)));
-        const float len2 = __fadd_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)), __fmul_rn(gz, gz));
-        const float inv = len2 > 0.0f ? -rsqrtf(len2) : 0.0f; // SFU rsqrt: 2 ulp, normals are compared at 1e-4
-        sh.edge[id] = make_float4(__fadd_rn(pa, __fmul_rn(t01, __fsub_rn(pb, pa))), __fmul_rn(gx, inv), __fmul_rn(gy, inv), __fmul_rn(gz, inv));
-    }
-    __syncthreads();
-
-    // ---- C: triangles, one warp per 32-cell row ---------------------------------------------------------------------
     unsigned char* owner = sh.triOwner[warp];
-    for (int r = warp; r < EY * EZ; r += MC_THREADS / 32) {
-        const int ly = r % EY, lz = r / EY;
-        const int cxi = x0 + lane, cyi = y0 + ly, czi = zc0 + lz;
-        if (cyi >= m.cy || czi >= m.cz0 + m.cnz) continue;
-        const size_t seg = blockIdx.x + static_cast<size_t>(m.nsegx) * (cyi + static_cast<size_t>(m.cy) * (czi - m.cz0));
-        const unsigned segOff = segOffset[seg], segTris = segOffset[seg + 1] - segOff;
-        if (segTris == 0) continue;
-        unsigned long long word = 0;
-        if (cxi < m.cx) word = kCaseWords[cubeIndexSmem(&sh.halo[lz + 1][ly + 1][lane + 1], EHXP, EHXP * EHY, m.iso)];
-        const unsigned n = static_cast<unsigned>(word & 15ull);
-        unsigned inc = n;
+
+    for (; step < EM_STEPS; ++step) {
+        const int zc0 = zcBeg + step * EZ; // global cell layer = global node plane of the step's lowest cells
+        if (zc0 >= zcEnd) break;
+        if (!sh.stepActive[step]) continue;
+        // planes zc0-1 .. zc0+3 must be in the ring
+        for (int z = max(loadedUpTo + 1, zc0 - 1); z <= zc0 + EZ + 1; ++z) loadPlane(z);
+        loadedUpTo = zc0 + EZ + 1;
+        asm volatile("cp.async.commit_group;");
+        asm volatile("cp.async.wait_group 0;");
+        if (threadIdx.x == 0) sh.ncross = 0;
+        __syncthreads();
+        // prefetch the two planes the next step adds (if that step is active) while this one computes
+        const bool nextActive = step + 1 < EM_STEPS && sh.stepActive[step + 1] && zc0 + EZ < zcEnd;
+        if (nextActive) {
+            loadPlane(zc0 + EZ + 2);
+            loadPlane(zc0 + EZ + 3);
+            loadedUpTo = zc0 + EZ + 3;
+            asm volatile("cp.async.commit_group;");
+        }
+        // halo coordinates (node + 1): plane iz of the step = node plane zc0 - 1 + iz = ring slot (slot0 + iz) mod ERING
+        const int slot0 = ringSlot(zc0 - 1);
+        auto H = [&](int iz, int iy, int ix) -> float {
+            int sl = slot0 + iz;
+            if (sl >= ERING) sl -= ERING;
+            return sh.ring[sl][iy][ix];
+        };
+
+        // ---- B1: crossed edges -> crossList (order is irrelevant) ------------------------------------------------
+        // rounds 0..26: one warp per node row, lanes = nodes 0..31; round 27: the 27 nodes of column 32, one per lane
+        for (int r = warp; r < ENZ * ENY + 1; r += MC_THREADS / 32) {
+            const bool lastCol = r == ENZ * ENY;
+            const int rr = lastCol ? lane : r;
+            const bool active = !lastCol || lane < ENZ * ENY;
+            const int iy = rr % ENY, iz = (rr / ENY) % ENZ;
+            const int ix = lastCol ? EX : lane;
+            bool cx = false, cy = false, cz = false;
+            if (active) {
+                const bool b0 = H(iz + 1, iy + 1, ix + 1) < m.iso;
+                if (ix < EX) cx = b0 != (H(iz + 1, iy + 1, ix + 2) < m.iso);
+                if (iy < EY) cy = b0 != (H(iz + 1, iy + 2, ix + 1) < m.iso);
+                if (iz < EZ) cz = b0 != (H(iz + 2, iy + 1, ix + 1) < m.iso);
+            }
+            const unsigned bx = __ballot_sync(0xffffffffu, cx), by = __ballot_sync(0xffffffffu, cy), bz = __ballot_sync(0xffffffffu, cz);
+            const int nx = __popc(bx), ny = __popc(by), nz = __popc(bz);
+            if (nx + ny + nz == 0) continue;
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&sh.ncross, nx + ny + nz);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            const unsigned lt = (1u << lane) - 1u;
+            if (cx) sh.crossList[base + __popc(bx & lt)] = static_cast<unsigned short>(edgeIndex(0, ix, iy, iz));
+            if (cy) sh.crossList[base + nx + __popc(by & lt)] = static_cast<unsigned short>(edgeIndex(1, ix, iy, iz));
+            if (cz) sh.crossList[base + nx + ny + __popc(bz & lt)] = static_cast<unsigned short>(edgeIndex(2, ix, iy, iz));
+        }
+        __syncthreads();
+
+        // ---- B2: one vertex per crossed edge ------------------------------------------------------------------------
+        const int ncross = sh.ncross;
+        // no node of this step touches the global border -> plain central differences
+        const bool interior = x0 > 0 && x0 + EX < m.sx - 1 && y0 > 0 && y0 + EY < m.sy - 1 && zc0 > 0 && zc0 + EZ < m.szGlobal - 1;
+        for (int c = threadIdx.x; c < ncross; c += MC_THREADS) {
+            const int id = sh.crossList[c];
+            int axis, ix, iy, iz;
+            if (id < E_YBASE) { axis = 0; ix = id % EX; const int t = id / EX; iy = t % ENY; iz = t / ENY; }
+            else if (id < E_ZBASE) { axis = 1; const int q = id - E_YBASE; ix = q % ENX; const int t = q / ENX; iy = t % EY; iz = t / EY; }
+            else { axis = 2; const int q = id - E_ZBASE; ix = q % ENX; const int t = q / ENX; iy = t % ENY; iz = t / ENY; }
+            const int jx = ix + (axis == 0), jy = iy + (axis == 1), jz = iz + (axis == 2);
+            // gradient at a node: (f(+) - f(-)) * 1/(n*sd), samples clamped at the GLOBAL grid border
+            auto grad = [&](int nx_, int ny_, int nz_, float& gx, float& gy, float& gz) {
+                const int hx = nx_ + 1, hy = ny_ + 1, hz = nz_ + 1;
+                if (interior) {
+                    gx = __fmul_rn(__fsub_rn(H(hz, hy, hx + 1), H(hz, hy, hx - 1)), r2x);
+                    gy = __fmul_rn(__fsub_rn(H(hz, hy + 1, hx), H(hz, hy - 1, hx)), r2y);
+                    gz = __fmul_rn(__fsub_rn(H(hz + 1, hy, hx), H(hz - 1, hy, hx)), r2z);
+                } else {
+                    const int gxi = x0 + nx_, gyi = y0 + ny_, gzi = zc0 + nz_;
+                    const int xm = gxi > 0 ? -1 : 0, xp = gxi < m.sx - 1 ? 1 : 0;
+                    const int ym = gyi > 0 ? -1 : 0, yp = gyi < m.sy - 1 ? 1 : 0;
+                    const int zm = gzi > 0 ? -1 : 0, zp = gzi < m.szGlobal - 1 ? 1 : 0;
+                    gx = xp > xm ? __fmul_rn(__fsub_rn(H(hz, hy, hx + xp), H(hz, hy, hx + xm)), xp - xm == 2 ? r2x : r1x) : 0.0f;
+                    gy = yp > ym ? __fmul_rn(__fsub_rn(H(hz, hy + yp, hx), H(hz, hy + ym, hx)), yp - ym == 2 ? r2y : r1y) : 0.0f;
+                    gz = zp > zm ? __fmul_rn(__fsub_rn(H(hz + zp, hy, hx), H(hz + zm, hy, hx)), zp - zm == 2 ? r2z : r1z) : 0.0f;
+                }
+            };
+            const float fa = H(iz + 1, iy + 1, ix + 1), fb = H(jz + 1, jy + 1, jx + 1);
+            const float t01 = __fdiv_rn(__fsub_rn(m.iso, fa), __fsub_rn(fb, fa));
+            const float pza = __fadd_rn(__fmul_rn((float)(zc0 + iz), m.sd[2]), m.org[2]);
+            const float pzb = __fadd_rn(__fmul_rn((float)(zc0 + jz), m.sd[2]), m.org[2]);
+            const float pa = axis == 0 ? sh.tabX[ix] : (axis == 1 ? sh.tabY[iy] : pza);
+            const float pb = axis == 0 ? sh.tabX[jx] : (axis == 1 ? sh.tabY[jy] : pzb);
+            float gax, gay, gaz, gbx, gby, gbz;
+            grad(ix, iy, iz, gax, gay, gaz);
+            grad(jx, jy, jz, gbx, gby, gbz);
+            const float gx = __fadd_rn(gax, __fmul_rn(t01, __fsub_rn(gbx, gax)));
+            const float gy = __fadd_rn(gay, __fmul_rn(t01, __fsub_rn(gby, gay)));
+            const float gz = __fadd_rn(gaz, __fmul_rn(t01, __fsub_rn(gbz, gaz)));
+            const float len2 = __fadd_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)), __fmul_rn(gz, gz));
+            const float inv = len2 > 0.0f ? -rsqrtf(len2) : 0.0f; // SFU rsqrt: 2 ulp, normals are compared at 1e-4
+            sh.edge[id] = make_float4(__fadd_rn(pa, __fmul_rn(t01, __fsub_rn(pb, pa))), __fmul_rn(gx, inv), __fmul_rn(gy, inv), __fmul_rn(gz, inv));
+        }
+        __syncthreads();
+
+        // ---- C: triangles, one warp per 32-cell row ---------------------------------------------------------------------
+        for (int r = warp; r < EY * EZ && !(m.debug & 2); r += MC_THREADS / 32) {
+            const int ly = r % EY, lz = r / EY;
+            const int cxi = x0 + lane;
+            const int row = (step * EZ + lz) * EY + ly;
+            const unsigned segOff = sh.segOff[row][0], segTris = sh.segOff[row][1];
+            if (segTris == 0) continue;
+            unsigned long long word = 0;
+            if (cxi < m.cx) {
+                int ci = 0;
+                ci |= (H(lz + 1, ly + 1, lane + 1) < m.iso) ? 1 : 0;
+                ci |= (H(lz + 1, ly + 1, lane + 2) < m.iso) ? 2 : 0;
+                ci |= (H(lz + 1, ly + 2, lane + 2) < m.iso) ? 4 : 0;
+                ci |= (H(lz + 1, ly + 2, lane + 1) < m.iso) ? 8 : 0;
+                ci |= (H(lz + 2, ly + 1, lane + 1) < m.iso) ? 16 : 0;
+                ci |= (H(lz + 2, ly + 1, lane + 2) < m.iso) ? 32 : 0;
+                ci |= (H(lz + 2, ly + 2, lane + 2) < m.iso) ? 64 : 0;
+                ci |= (H(lz + 2, ly + 2, lane + 1) < m.iso) ? 128 : 0;
+                word = kCaseWords[ci];
+            }
+            const unsigned n = static_cast<unsigned>(word & 15ull);
+            unsigned inc = n;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const unsigned t = __shfl_up_sync(0xffffffffu, inc, d);
-            if (lane >= d) inc += t;
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned t = __shfl_up_sync(0xffffffffu, inc, d);
+                if (lane >= d) inc += t;
+            }
+            const unsigned first = inc - n; // my first triangle within the row
+            for (unsigned k = 0; k < n; ++k) owner[first + k] = static_cast<unsigned char>(lane);
+            __syncwarp();
+            const unsigned wlo = static_cast<unsigned>(word >> 4), whi = static_cast<unsigned>(word >> 36); // 15 nibbles of edge ids
+            const unsigned ncorn = segTris * 3;
+            const size_t gbase = static_cast<size_t>(segOff) * 9;
+            const float tz0 = __fadd_rn(__fmul_rn((float)(zc0 + lz), m.sd[2]), m.org[2]);
+            const float tz1 = __fadd_rn(__fmul_rn((float)(zc0 + lz + 1), m.sd[2]), m.org[2]);
+            for (unsigned j0 = 0; j0 < ncorn; j0 += 32) {
+                const unsigned j = j0 + lane;
+                const bool act = j < ncorn;
+                const unsigned t = act ? j / 3 : 0;
+                const unsigned L = owner[t];
+                const unsigned oFirst = __shfl_sync(0xffffffffu, first, L);
+                const unsigned oLo = __shfl_sync(0xffffffffu, wlo, L), oHi = __shfl_sync(0xffffffffu, whi, L);
+                if (!act) continue;
+                const unsigned slotc = 3 * (t - oFirst) + (j - 3 * t); // corner number inside the owner cell (0..14)
+                const int e = static_cast<int>(slotc < 8 ? (oLo >> (4 * slotc)) & 15u : (oHi >> (4 * (slotc - 8))) & 15u);
+                const unsigned code = edgeCode(e);
+                const int dz = (code >> 2) & 1;
+                const int ix = (int)L + (code & 1), iy = ly + ((code >> 1) & 1), iz = lz + dz;
+                const int axis = code >> 3;
+                const float4 v = sh.edge[edgeIndex(axis, ix, iy, iz)];
+                const float px = axis == 0 ? v.x : sh.tabX[ix];
+                const float py = axis == 1 ? v.x : sh.tabY[iy];
+                const float pz = axis == 2 ? v.x : (dz ? tz1 : tz0);
+                float* op = outPos + gbase + static_cast<size_t>(j) * 3;
+                float* on = outNrm + gbase + static_cast<size_t>(j) * 3;
+                if ((m.debug & 1) && px != -12345.678f) continue;
+                op[0] = px, op[1] = py, op[2] = pz;
+                on[0] = v.y, on[1] = v.z, on[2] = v.w;
+            }
+            __syncwarp();
         }
-        const unsigned first = inc - n; // my first triangle within the row
-        for (unsigned k = 0; k < n; ++k) owner[first + k] = static_cast<unsigned char>(lane);
-        __syncwarp();
-        const unsigned wlo = static_cast<unsigned>(word >> 4), whi = static_cast<unsigned>(word >> 36); // 15 nibbles of edge ids
-        const unsigned ncorn = segTris * 3;
-        const size_t gbase = static_cast<size_t>(segOff) * 9;
-        for (unsigned j0 = 0; j0 < ncorn; j0 += 32) {
-            const unsigned j = j0 + lane;
-            const bool act = j < ncorn;
-            const unsigned t = act ? j / 3 : 0;
-            const unsigned L = owner[t];
-            const unsigned oFirst = __shfl_sync(0xffffffffu, first, L);
-            const unsigned oLo = __shfl_sync(0xffffffffu, wlo, L), oHi = __shfl_sync(0xffffffffu, whi, L);
-            if (!act) continue;
-            const unsigned slot = 3 * (t - oFirst) + (j - 3 * t); // corner number inside the owner cell (0..14)
-            const int e = static_cast<int>(slot < 8 ? (oLo >> (4 * slot)) & 15u : (oHi >> (4 * (slot - 8))) & 15u);
-            const unsigned code = edgeCode(e);
-            const int ix = (int)L + (code & 1), iy = ly + ((code >> 1) & 1), iz = lz + ((code >> 2) & 1);
-            const int axis = code >> 3;
-            const float4 v = sh.edge[edgeIndex(axis, ix, iy, iz)];
-            const float px = axis == 0 ? v.x : sh.tabX[ix];
-            const float py = axis == 1 ? v.x : sh.tabY[iy];
-            const float pz = axis == 2 ? v.x : sh.tabZ[iz];
-            float* op = outPos + gbase + static_cast<size_t>(j) * 3;
-            float* on = outNrm + gbase + static_cast<size_t>(j) * 3;
-            op[0] = px, op[1] = py, op[2] = pz;
-            on[0] = v.y, on[1] = v.z, on[2] = v.w;
-        }
-        __syncwarp();
+        __syncthreads(); // the next step overwrites edge[] / crossList and the ring slots this step no longer needs
     }
+    asm volatile("cp.async.wait_group 0;");
 }
 
 } // namespace mms

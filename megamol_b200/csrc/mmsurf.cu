@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -610,6 +611,7 @@ int mms_extract_isosurface(mms_ctx* c, float iso) {
         m.rinv[a][0] = 0.0f;
     }
     m.iso = iso;
+    m.debug = getenv("MMS_DEBUG_MC") ? atoi(getenv("MMS_DEBUG_MC")) : 0;
     c->ntris = 0;
     c->haveMesh = true;
     if (m.cnz <= 0) return MMS_OK;
@@ -639,7 +641,7 @@ int mms_extract_isosurface(mms_ctx* c, float iso) {
     if (T > 0) {
         if (!c->meshPos.ensure(T * 36) || !c->meshNrm.ensure(T * 36))
             return c->fail(MMS_ERR_NOMEM, "device allocation of the mesh (%llu triangles, %llu bytes) failed", T, T * 72ull);
-        dim3 gridE(m.nsegx, (m.cy + EY - 1) / EY, (m.cnz + EZ - 1) / EZ);
+        dim3 gridE(m.nsegx, (m.cy + EY - 1) / EY, (m.cnz + EM_STEPS * EZ - 1) / (EM_STEPS * EZ));
         mc_emit_kernel<false><<<gridE, MC_THREADS, sizeof(McEmitShared), st>>>(m, c->vol.as<float>(), nullptr, c->segOffset.as<unsigned>(),
             c->meshPos.as<float>(), c->meshNrm.as<float>(), nullptr);
         ++c->launches;
