@@ -102,7 +102,7 @@ constexpr int EX = 32, EY = 8, EZ = 2;                      // cells per step
 constexpr int ENX = EX + 1, ENY = EY + 1, ENZ = EZ + 1;     // nodes per step
 constexpr int EHX = EX + 3, EHY = EY + 3, EHZ = EZ + 3;     // nodes + gradient halo
 constexpr int EHXP = EHX + 1;                               // padded row
-constexpr int ERING = EHZ + EZ;                             // plane slots
+constexpr int ERING = 8;                                    // plane slots (>= EHZ + EZ = 7; power of two: slot = (z+1) & 7)
 constexpr int EM_STEPS = 16;                                // steps per block (32 cell layers)
 constexpr int E_XEDGES = ENZ * ENY * EX;                    // 864  x-edges: ix < 32
 constexpr int E_YEDGES = ENZ * EY * ENX;                    // 792  y-edges: iy < 8
@@ -138,7 +138,7 @@ __device__ __forceinline__ int edgeIndex(int axis, int ix, int iy, int iz) {
 }
 
 __device__ __forceinline__ int ringSlot(int zNode) { // zNode >= -1
-    return (zNode + 1) % ERING;
+    return (zNode + 1) & (ERING - 1);
 }
 
 __device__ __forceinline__ void cpAsync4(float* smemDst, const float* gmemSrc) {
@@ -219,9 +219,7 @@ __global__ void __launch_bounds__(MC_THREADS) mc_emit_kernel(McGeo m, const floa
         // halo coordinates (node + 1): plane iz of the step = node plane zc0 - 1 + iz = ring slot (slot0 + iz) mod ERING
         const int slot0 = ringSlot(zc0 - 1);
         auto H = [&](int iz, int iy, int ix) -> float {
-            int sl = slot0 + iz;
-            if (sl >= ERING) sl -= ERING;
-            return sh.ring[sl][iy][ix];
+            return sh.ring[(slot0 + iz) & (ERING - 1)][iy][ix];
         };
 
         // ---- B1: crossed edges -> crossList (order is irrelevant) ------------------------------------------------
