@@ -1,1 +1,1 @@
-python -m pytest tests/test_gpu_slabs.py -m gpu -x -q 2>&1 | tail -15
+python -m pytest tests/test_gpu_quicksurf.py -m gpu -x -q 2>&1 | tail -25

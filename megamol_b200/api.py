@@ -209,12 +209,16 @@ class Surf:
     def normalize(self, mn, mx):
         self._chk(self.L.mms_normalize(self.h, float(mn), float(mx)))
 
-    def get_density(self, copy=True):
+    def get_density(self, copy=True, with_rgb=False):
         p = C.c_void_p()
         q = C.c_void_p()
-        self._chk(self.L.mms_get_density(self.h, C.byref(p), C.byref(q)))
+        self._chk(self.L.mms_get_density(self.h, C.byref(p), C.byref(q) if with_rgb else None))
         v = _np_view(p.value, (self.nz, self.res[1], self.res[0]), np.float32)
-        return v.copy() if copy else v
+        v = v.copy() if copy else v
+        if not with_rgb:
+            return v
+        c = _np_view(q.value, (self.nz, self.res[1], self.res[0], 3), np.float32) if q.value else None
+        return v, (c.copy() if (copy and c is not None) else c)
 
     def density_device_ptr(self):
         p = C.c_void_p()
@@ -234,17 +238,19 @@ class Surf:
     def extract_isosurface(self, iso):
         self._chk(self.L.mms_extract_isosurface(self.h, float(iso)))
 
-    def get_mesh(self, copy=True, normals=True):
+    def get_mesh(self, copy=True, normals=True, colours=False):
         n = C.c_uint64()
         p, q, r = C.c_void_p(), C.c_void_p(), C.c_void_p()
-        self._chk(self.L.mms_get_mesh(self.h, C.byref(n), C.byref(p), C.byref(q) if normals else None, C.byref(r)))
+        self._chk(self.L.mms_get_mesh(self.h, C.byref(n), C.byref(p), C.byref(q) if normals else None, C.byref(r) if colours else None))
         nt = n.value // 3
         pos = _np_view(p.value, (nt, 3, 3), np.float32)
         nrm = _np_view(q.value, (nt, 3, 3), np.float32) if normals else None
+        col = _np_view(r.value, (nt, 3, 3), np.float32) if (colours and r.value) else None
         if copy:
             pos = pos.copy()
             nrm = nrm.copy() if nrm is not None else None
-        return pos, nrm
+            col = col.copy() if col is not None else None
+        return (pos, nrm, col) if colours else (pos, nrm)
 
     def mesh_device(self):
         n = C.c_uint64()

@@ -20,6 +20,7 @@
 // h is the UN-wrapped voxel index, so periodic images get the true distance (:605-613).
 #pragma once
 #include "common.cuh"
+#include "scan.cuh"
 
 namespace mms {
 
@@ -115,7 +116,7 @@ __device__ __forceinline__ float rcpApprox(float x) {
 
 /** Contribution of one voxel; returns false if the voxel is outside the kernel support. */
 template<int MODE>
-__device__ __forceinline__ bool kernelValue(float d2, float eps, float k0, float& w) {
+__device__ __forceinline__ bool kernelValue(float d2, float eps, float k0, float& w, float lim2 = -1.0f) {
     if (MODE == 0) {
         const float dis = __fsqrt_rn(d2);
         if (dis >= eps) return false;
@@ -124,7 +125,7 @@ __device__ __forceinline__ bool kernelValue(float d2, float eps, float k0, float
         w = ex2Approx(-1.4426950408889634f * rcpApprox(den));
         return true;
     } else {
-        if (!(d2 < __fmul_rn(eps, eps))) return false;
+        if (!(d2 < (lim2 >= 0.0f ? lim2 : __fmul_rn(eps, eps)))) return false;
         w = ex2Approx(__fmul_rn(d2, k0));
         return true;
     }
@@ -384,6 +385,205 @@ __global__ void __launch_bounds__(CT_THREADS, 3) density_splat_kernel(Geo g, Dev
             const float v = sh.tile[lane + ly * CT_SY + lz * CT_SZ];
             vol[x + static_cast<size_t>(g.s[0]) * (y + static_cast<size_t>(g.s[1]) * (z - g.z0))] = v;
             vmin = fminf(vmin, v), vmax = fmaxf(vmax, v);
+        }
+    }
+    const unsigned kmin = __reduce_min_sync(0xffffffffu, floatKey(vmin)), kmax = __reduce_max_sync(0xffffffffu, floatKey(vmax));
+    if (lane == 0 && kmin <= kmax) {
+        atomicMin(&st->minKey, kmin);
+        atomicMax(&st->maxKey, kmax);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Wide supports: voxel gather
+// ---------------------------------------------------------------------------------------------------------------
+// density_gather_kernel: QuickSurf-Gaussian mode (supports of ~10 voxels, optional density-weighted RGB volume) and
+// P2D supports wider than 8 voxels.  A block owns a 32x8x8-voxel tile; each thread keeps a column of 8 voxels (+ RGB)
+// in registers.  The particles of every cell the tile's neighbourhood touches are streamed through shared memory in
+// (cell z, cell y, cell x, canonical in-cell) order, 256 at a time; every thread walks the staged candidates in that
+// order, rejects on the xy distance first, and accumulates in registers -- no atomics, one fixed order per voxel.
+constexpr int GT_X = 32, GT_Y = 8, GT_Z = 8;
+constexpr int GT_THREADS = 256;
+constexpr int GT_CHUNK = 256;
+constexpr int GT_MAXSEG = 512;
+
+struct GCand {          // 48 bytes
+    float x, y, z, k0;  // k0: QS w_p = -log2e/(2 (r radscale)^2); P2D 1/eps
+    float lim, cr, cg, cb; // lim: QS cut-off^2, P2D eps;  colour (QS) / intensity in cr (P2D aggregator 1)
+    int kx, ky, kz, pad;   // periodic image: the voxel index seen by this particle is t + k (k in {-s, 0, +s})
+};
+
+struct GatherShared {
+    GCand cand[GT_CHUNK];
+    unsigned segBegin[GT_MAXSEG];
+    unsigned segPrefix[GT_MAXSEG + 1];
+    int axisCells[3][CT_MAXAXIS];
+    int axisCount[3];
+    unsigned scanTmp[33];
+};
+
+template<int MODE, bool COLOUR>
+__global__ void __launch_bounds__(GT_THREADS, 2) density_gather_kernel(Geo g, DevState* st, const float4* __restrict__ recs,
+    const float* __restrict__ aux, int auxN, const unsigned* __restrict__ cellStart, float* __restrict__ vol, float* __restrict__ rgb,
+    int reach) {
+    __shared__ GatherShared sh;
+    const int tid = threadIdx.x, lane = tid & 31, ty = tid >> 5;
+    const int t0x = (int)blockIdx.x * GT_X, t0y = (int)blockIdx.y * GT_Y, t0z = g.z0 + (int)blockIdx.z * GT_Z;
+    const int t1x = min(t0x + GT_X, g.s[0]) - 1, t1y = min(t0y + GT_Y, g.s[1]) - 1, t1z = min(t0z + GT_Z, g.z0 + g.nz) - 1;
+    if (tid < 3) {
+        const int a = tid;
+        const int t0 = a == 0 ? t0x : (a == 1 ? t0y : t0z), t1 = a == 0 ? t1x : (a == 1 ? t1y : t1z);
+        sh.axisCount[a] = buildAxisCells(t0, t1, reach, g.s[a], g.cyc[a] != 0, g.cshift, g.nc[a], sh.axisCells[a], CT_MAXAXIS);
+        // two periodic images of one particle reaching the same tile is not handled by this kernel
+        if (g.cyc[a] && g.s[a] < (t1 - t0 + 1) + 2 * reach + 2) st->pad[0] = 2u;
+    }
+    __syncthreads();
+    const int ncx = sh.axisCount[0], ncy = sh.axisCount[1], ncz = sh.axisCount[2];
+    if (ncx < 0 || ncy < 0 || ncz < 0) {
+        if (tid == 0) st->pad[0] = 1u;
+        return;
+    }
+    int nruns = 0;
+    int runStart[4], runEnd[4];
+    for (int k = 0; k < ncx && nruns < 4; ++k) {
+        const int c = sh.axisCells[0][k];
+        if (nruns > 0 && c == runEnd[nruns - 1] + 1) runEnd[nruns - 1] = c;
+        else { runStart[nruns] = c; runEnd[nruns] = c; ++nruns; }
+    }
+    const int nrows = ncy * ncz, nsegTotal = nrows * nruns;
+
+    const int vxI = t0x + lane, vyI = t0y + ty;
+    const float vx = __fadd_rn(__fmul_rn((float)vxI, g.sd[0]), g.mn[0]);
+    const float vy = __fadd_rn(__fmul_rn((float)vyI, g.sd[1]), g.mn[1]);
+    float vz[GT_Z], acc[GT_Z], accR[GT_Z], accG[GT_Z], accB[GT_Z];
+#pragma unroll
+    for (int k = 0; k < GT_Z; ++k) {
+        vz[k] = __fadd_rn(__fmul_rn((float)(t0z + k), g.sd[2]), g.mn[2]);
+        acc[k] = 0.0f, accR[k] = 0.0f, accG[k] = 0.0f, accB[k] = 0.0f;
+    }
+
+    for (int segBase = 0; segBase < nsegTotal; segBase += GT_MAXSEG) {
+        const int nseg = min(GT_MAXSEG, nsegTotal - segBase);
+        __syncthreads();
+        unsigned carry = 0;
+        for (int b0 = 0; b0 < nseg; b0 += GT_THREADS) {
+            const int sI = b0 + tid;
+            unsigned len = 0;
+            if (sI < nseg) {
+                const int gs = segBase + sI;
+                const int row = gs / nruns, run = gs - row * nruns;
+                const int cz = sh.axisCells[2][row / ncy], cy = sh.axisCells[1][row % ncy];
+                const size_t rowBase = (static_cast<size_t>(cz) * g.nc[1] + cy) * g.nc[0];
+                const unsigned beg = cellStart[rowBase + runStart[run]];
+                len = cellStart[rowBase + runEnd[run] + 1] - beg;
+                sh.segBegin[sI] = beg;
+            }
+            unsigned total;
+            const unsigned ex = blockExclusiveScan(len, &total, sh.scanTmp);
+            if (sI < nseg) sh.segPrefix[sI] = carry + ex;
+            carry += total;
+        }
+        if (tid == 0) sh.segPrefix[nseg] = carry;
+        __syncthreads();
+        const unsigned ncand = sh.segPrefix[nseg];
+        for (unsigned chunk = 0; chunk < ncand; chunk += GT_CHUNK) {
+            const unsigned nin = min((unsigned)GT_CHUNK, ncand - chunk);
+            __syncthreads();
+            if ((unsigned)tid < nin) {
+                const unsigned pos = chunk + tid;
+                int lo = 0, hi = nseg;
+                while (hi - lo > 1) {
+                    const int mid = (lo + hi) >> 1;
+                    if (sh.segPrefix[mid] <= pos) lo = mid; else hi = mid;
+                }
+                const unsigned idx = sh.segBegin[lo] + (pos - sh.segPrefix[lo]);
+                const float4 p = recs[idx];
+                GCand c;
+                c.x = p.x, c.y = p.y, c.z = p.z;
+                c.cr = c.cg = c.cb = 1.0f;
+                float eps;
+                if (MODE == 0) {
+                    eps = __fmul_rn(g.sigma, p.w);
+                    c.k0 = __fdiv_rn(1.0f, eps);
+                    c.lim = eps;
+                    if (auxN == 1) c.cr = aux[idx];
+                } else {
+                    const float sr = __fmul_rn(p.w, g.radscale);
+                    eps = __fmul_rn(g.gausslim, sr);
+                    c.k0 = __fdiv_rn(-1.4426950408889634f, __fmul_rn(__fmul_rn(2.0f, sr), sr));
+                    c.lim = __fmul_rn(eps, eps);
+                    if (auxN == 4) {
+                        const float4 col = reinterpret_cast<const float4*>(aux)[idx];
+                        c.cr = col.x, c.cg = col.y, c.cb = col.z;
+                    }
+                }
+                // periodic image that can reach this tile (at most one: checked above)
+                const float pp[3] = {p.x, p.y, p.z};
+                const int tl0[3] = {t0x, t0y, t0z}, tl1[3] = {t1x, t1y, t1z};
+                int kk[3] = {0, 0, 0};
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    if (!g.cyc[a]) continue;
+                    const int H = homeVoxel(pp[a], g.mn[a], g.sd[a]);
+                    // voxel index seen by the particle = t + k, k a multiple of s, must meet [H - R, H + R], R = reach + 1:
+                    // the smallest such k is ceil((H - R - t1) / s) * s (at most one k works: checked per block above)
+                    const int R = reach + 1;
+                    const int a0 = H - R - tl1[a];
+                    const int q = -((-a0 - floorMod(-a0, g.s[a])) / g.s[a]); // ceil(a0 / s)
+                    int k = q * g.s[a];
+                    if (tl0[a] + k > H + R) k = 0; // no image reaches this tile
+                    kk[a] = k;
+                }
+                c.kx = kk[0], c.ky = kk[1], c.kz = kk[2], c.pad = 0;
+                sh.cand[tid] = c;
+            }
+            __syncthreads();
+            for (unsigned j = 0; j < nin; ++j) {
+                const float4 A = reinterpret_cast<const float4*>(&sh.cand[j])[0];
+                const float4 B = reinterpret_cast<const float4*>(&sh.cand[j])[1];
+                const int4 K = reinterpret_cast<const int4*>(&sh.cand[j])[2];
+                float px = vx, py = vy;
+                if (K.x | K.y | K.z) { // periodic image: the reference's un-wrapped voxel index (ParticlesToDensity.cpp:605-613)
+                    px = __fadd_rn(__fmul_rn((float)(vxI + K.x), g.sd[0]), g.mn[0]);
+                    py = __fadd_rn(__fmul_rn((float)(vyI + K.y), g.sd[1]), g.mn[1]);
+                }
+                const float dx = __fsub_rn(px, A.x), dy = __fsub_rn(py, A.y);
+                const float dxy2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+                const float lim2 = MODE == 0 ? B.x * B.x * 1.0001f : B.x;
+                if (!(dxy2 < lim2)) continue;
+#pragma unroll
+                for (int k = 0; k < GT_Z; ++k) {
+                    float pz = vz[k];
+                    if (K.z) pz = __fadd_rn(__fmul_rn((float)(t0z + k + K.z), g.sd[2]), g.mn[2]);
+                    const float dz = __fsub_rn(pz, A.z);
+                    const float d2 = __fadd_rn(dxy2, __fmul_rn(dz, dz));
+                    float w;
+                    if (kernelValue<MODE>(d2, MODE == 0 ? B.x : 0.0f, A.w, w, B.x)) {
+                        if (MODE == 0) {
+                            acc[k] = __fadd_rn(acc[k], g.agg == 1 ? __fmul_rn(w, B.y) : w);
+                        } else {
+                            acc[k] = __fadd_rn(acc[k], w);
+                            if (COLOUR) {
+                                accR[k] = __fadd_rn(accR[k], __fmul_rn(w, B.y));
+                                accG[k] = __fadd_rn(accG[k], __fmul_rn(w, B.z));
+                                accB[k] = __fadd_rn(accB[k], __fmul_rn(w, B.w));
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+    float vmin = INFINITY, vmax = -INFINITY;
+    if (vxI <= t1x && vyI <= t1y) {
+#pragma unroll
+        for (int k = 0; k < GT_Z; ++k) {
+            const int z = t0z + k;
+            if (z > t1z) break;
+            const size_t o = vxI + static_cast<size_t>(g.s[0]) * (vyI + static_cast<size_t>(g.s[1]) * (z - g.z0));
+            vol[o] = acc[k];
+            if (COLOUR) rgb[3 * o + 0] = accR[k], rgb[3 * o + 1] = accG[k], rgb[3 * o + 2] = accB[k];
+            vmin = fminf(vmin, acc[k]), vmax = fmaxf(vmax, acc[k]);
         }
     }
     const unsigned kmin = __reduce_min_sync(0xffffffffu, floatKey(vmin)), kmax = __reduce_max_sync(0xffffffffu, floatKey(vmax));

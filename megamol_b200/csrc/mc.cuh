@@ -151,6 +151,7 @@ __global__ void __launch_bounds__(MC_THREADS) mc_emit_kernel(McGeo m, const floa
     const unsigned* __restrict__ segOffset, float* __restrict__ outPos, float* __restrict__ outNrm, float* __restrict__ outCol) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     McEmitShared& sh = *reinterpret_cast<McEmitShared*>(smemRaw);
+    float4* edgeCol = reinterpret_cast<float4*>(smemRaw + ((sizeof(McEmitShared) + 15) & ~size_t(15))); // COLOUR only
     const int x0 = blockIdx.x * EX, y0 = blockIdx.y * EY;
     const int zcBeg = m.cz0 + blockIdx.z * (EM_STEPS * EZ);           // first global cell layer of this block
     const int zcEnd = min(zcBeg + EM_STEPS * EZ, m.cz0 + m.cnz);      // exclusive
@@ -293,6 +294,20 @@ __global__ void __launch_bounds__(MC_THREADS) mc_emit_kernel(McGeo m, const floa
             const float len2 = __fadd_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)), __fmul_rn(gz, gz));
             const float inv = len2 > 0.0f ? -rsqrtf(len2) : 0.0f; // SFU rsqrt: 2 ulp, normals are compared at 1e-4
             sh.edge[id] = make_float4(__fadd_rn(pa, __fmul_rn(t01, __fsub_rn(pb, pa))), __fmul_rn(gx, inv), __fmul_rn(gy, inv), __fmul_rn(gz, inv));
+            if (COLOUR) { // node colour = rgb / rho (0 where rho == 0), interpolated with the same t
+                auto nodeColour = [&](int nx_, int ny_, int nz_, float f, float& r, float& gg, float& b) {
+                    const int x = min(x0 + nx_, m.sx - 1), y = min(y0 + ny_, m.sy - 1);
+                    const int zl = min(max(zc0 + nz_ - m.zPlane0, 0), m.nzPlanes - 1);
+                    const float* c = rgb + 3 * (x + static_cast<size_t>(m.sx) * (y + static_cast<size_t>(m.sy) * zl));
+                    if (f > 0.0f) r = __fdiv_rn(c[0], f), gg = __fdiv_rn(c[1], f), b = __fdiv_rn(c[2], f);
+                    else r = gg = b = 0.0f;
+                };
+                float ar, ag, ab, br, bg, bb;
+                nodeColour(ix, iy, iz, fa, ar, ag, ab);
+                nodeColour(jx, jy, jz, fb, br, bg, bb);
+                edgeCol[id] = make_float4(__fadd_rn(ar, __fmul_rn(t01, __fsub_rn(br, ar))), __fadd_rn(ag, __fmul_rn(t01, __fsub_rn(bg, ag))),
+                    __fadd_rn(ab, __fmul_rn(t01, __fsub_rn(bb, ab))), 0.0f);
+            }
         }
         __syncthreads();
 
@@ -345,7 +360,8 @@ __global__ void __launch_bounds__(MC_THREADS) mc_emit_kernel(McGeo m, const floa
                 const int dz = (code >> 2) & 1;
                 const int ix = (int)L + (code & 1), iy = ly + ((code >> 1) & 1), iz = lz + dz;
                 const int axis = code >> 3;
-                const float4 v = sh.edge[edgeIndex(axis, ix, iy, iz)];
+                const int eidx = edgeIndex(axis, ix, iy, iz);
+                const float4 v = sh.edge[eidx];
                 const float px = axis == 0 ? v.x : sh.tabX[ix];
                 const float py = axis == 1 ? v.x : sh.tabY[iy];
                 const float pz = axis == 2 ? v.x : (dz ? tz1 : tz0);
@@ -354,6 +370,11 @@ __global__ void __launch_bounds__(MC_THREADS) mc_emit_kernel(McGeo m, const floa
                 if ((m.debug & 1) && px != -12345.678f) continue;
                 op[0] = px, op[1] = py, op[2] = pz;
                 on[0] = v.y, on[1] = v.z, on[2] = v.w;
+                if (COLOUR) {
+                    const float4 cc = edgeCol[eidx];
+                    float* oc = outCol + gbase + static_cast<size_t>(j) * 3;
+                    oc[0] = cc.x, oc[1] = cc.y, oc[2] = cc.z;
+                }
             }
             __syncwarp();
         }

@@ -100,6 +100,7 @@ struct mms_ctx {
     unsigned long long ntris = 0;
     unsigned long long launches = 0;
     int cshift = 2, reach = 2;
+    bool useGather = false, haveColour = false;
 
     DevBuf cellCount, cellStart, cursor, tileSums, recsA, recsB, auxA, auxB, vol, rgb, segCount, segOffset, meshPos, meshNrm,
         meshCol, triCount, home, dstate;
@@ -258,7 +259,8 @@ int mms_create(mms_ctx** out, const mms_config* cfg) {
     c->params.gausslim = 3.0f;
     cudaFuncSetAttribute(density_splat_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SplatShared));
     cudaFuncSetAttribute(density_splat_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SplatShared));
-    cudaFuncSetAttribute(mc_emit_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(McEmitShared));
+    cudaFuncSetAttribute(mc_emit_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(McEmitShared) + 16);
+    cudaFuncSetAttribute(mc_emit_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(McEmitShared) + 16 + E_EDGES * sizeof(float4)));
     if (!c->dstate.ensure(sizeof(DevState)) || !c->hState.ensure(sizeof(DevState))) {
         g_createError = "allocation of the state block failed";
         delete c;
@@ -337,7 +339,6 @@ int mms_set_params(mms_ctx* c, const mms_params* p) {
         if (!(p->sigma > 0.0f)) return c->fail(MMS_ERR_INVALID, "sigma must be > 0");
     } else {
         if (!(p->radscale > 0.0f) || !(p->gausslim > 0.0f)) return c->fail(MMS_ERR_INVALID, "radscale and gausslim must be > 0");
-        if (p->colour) return c->fail(MMS_ERR_UNSUPPORTED, "QuickSurf colour volume is not implemented yet");
     }
     c->params = *p;
     return MMS_OK;
@@ -450,17 +451,23 @@ int mms_compute_density(mms_ctx* c) {
         const float epsMax = (c->params.mode == MMS_MODE_P2D_BUMP) ? c->params.sigma * rmax : c->params.gausslim * c->params.radscale * rmax;
         int need = 1;
         for (int a = 0; a < 3; ++a) need = std::max(need, static_cast<int>(std::ceil(epsMax / g0.sd[a] + 0.02f)));
-        if (need <= 2) c->cshift = 2;
+        c->useGather = c->params.mode == MMS_MODE_QS_GAUSS || need > 8;
+        if (c->useGather) {
+            if (need > 96) return c->fail(MMS_ERR_UNSUPPORTED, "kernel support of %d voxels per side is not supported", need);
+            if (c->params.mode == MMS_MODE_P2D_BUMP && c->params.sigma > 1.0f)
+                return c->fail(MMS_ERR_UNSUPPORTED, "sigma > 1 with supports wider than 8 voxels is not implemented");
+            c->cshift = need <= 16 ? 3 : 4; // gather: cells only organise the candidate stream
+        } else if (need <= 2) c->cshift = 2;
         else if (need <= 4) c->cshift = 3;
-        else if (need <= 8) c->cshift = 4;
-        else
-            return c->fail(MMS_ERR_UNSUPPORTED, "kernel support of %d voxels exceeds what the splat kernel handles (8); the wide-support gather kernel is not built yet", need);
+        else c->cshift = 4;
         c->reach = need;
     }
     const Geo g = makeGeo(c);
     const size_t ncells = static_cast<size_t>(g.nc[0]) * g.nc[1] * g.nc[2];
     const size_t nvox = static_cast<size_t>(g.s[0]) * g.s[1] * g.nz;
-    const int auxN = (g.mode == 0 && g.agg == 1) ? 1 : 0;
+    const bool colour = g.mode == 1 && c->params.colour != 0;
+    const int auxN = (g.mode == 0 && g.agg == 1) ? 1 : (colour ? 4 : 0);
+    if (colour && !c->rgb.ensure(nvox * 12)) return c->fail(MMS_ERR_NOMEM, "device allocation failed (colour volume)");
     const size_t n = static_cast<size_t>(c->nparticles);
     const unsigned ntiles = static_cast<unsigned>((ncells + kScanTile - 1) / kScanTile);
     if (!c->cellCount.ensure(ncells * 4) || !c->cellStart.ensure((ncells + 1) * 4) || !c->cursor.ensure(ncells * 4) ||
@@ -494,13 +501,25 @@ int mms_compute_density(mms_ctx* c) {
         ++c->launches;
     }
     c->rec(EV_BIN1);
-    dim3 grid((g.s[0] + CT_X - 1) / CT_X, (g.s[1] + CT_Y - 1) / CT_Y, (g.nz + CT_Z - 1) / CT_Z);
-    if (g.mode == 0)
-        density_splat_kernel<0><<<grid, CT_THREADS, sizeof(SplatShared), st>>>(g, c->dstate.as<DevState>(), c->recsB.as<float4>(),
-            c->auxB.as<float>(), auxN, c->cellStart.as<unsigned>(), c->vol.as<float>(), c->reach);
-    else
-        density_splat_kernel<1><<<grid, CT_THREADS, sizeof(SplatShared), st>>>(g, c->dstate.as<DevState>(), c->recsB.as<float4>(),
-            c->auxB.as<float>(), auxN, c->cellStart.as<unsigned>(), c->vol.as<float>(), c->reach);
+    if (c->useGather) {
+        dim3 grid((g.s[0] + GT_X - 1) / GT_X, (g.s[1] + GT_Y - 1) / GT_Y, (g.nz + GT_Z - 1) / GT_Z);
+        const float4* R = c->recsB.as<float4>();
+        const float* A = c->auxB.as<float>();
+        const unsigned* CS = c->cellStart.as<unsigned>();
+        DevState* DS = c->dstate.as<DevState>();
+        if (g.mode == 0) density_gather_kernel<0, false><<<grid, GT_THREADS, 0, st>>>(g, DS, R, A, auxN, CS, c->vol.as<float>(), nullptr, c->reach);
+        else if (colour) density_gather_kernel<1, true><<<grid, GT_THREADS, 0, st>>>(g, DS, R, A, auxN, CS, c->vol.as<float>(), c->rgb.as<float>(), c->reach);
+        else density_gather_kernel<1, false><<<grid, GT_THREADS, 0, st>>>(g, DS, R, A, auxN, CS, c->vol.as<float>(), nullptr, c->reach);
+    } else {
+        dim3 grid((g.s[0] + CT_X - 1) / CT_X, (g.s[1] + CT_Y - 1) / CT_Y, (g.nz + CT_Z - 1) / CT_Z);
+        if (g.mode == 0)
+            density_splat_kernel<0><<<grid, CT_THREADS, sizeof(SplatShared), st>>>(g, c->dstate.as<DevState>(), c->recsB.as<float4>(),
+                c->auxB.as<float>(), auxN, c->cellStart.as<unsigned>(), c->vol.as<float>(), c->reach);
+        else
+            density_splat_kernel<1><<<grid, CT_THREADS, sizeof(SplatShared), st>>>(g, c->dstate.as<DevState>(), c->recsB.as<float4>(),
+                c->auxB.as<float>(), auxN, c->cellStart.as<unsigned>(), c->vol.as<float>(), c->reach);
+    }
+    c->haveColour = colour;
     ++c->launches;
     c->rec(EV_DEN1);
     c->normalized = false;
@@ -521,6 +540,8 @@ int mms_compute_density(mms_ctx* c) {
 static int checkDeviceError(mms_ctx* c) {
     MMS_CUDA(c, cudaStreamSynchronize(c->stream));
     const DevState* hs = c->hState.as<DevState>();
+    if (hs->pad[0] == 2)
+        return c->fail(MMS_ERR_UNSUPPORTED, "wide kernel support on a periodic axis shorter than tile + 2*support is not implemented");
     if (hs->pad[0] != 0)
         return c->fail(MMS_ERR_UNSUPPORTED, "internal error: the splat kernel's neighbourhood list overflowed (%d cells per axis)", CT_MAXAXIS);
     return MMS_OK;
@@ -558,7 +579,7 @@ int mms_get_density_device(mms_ctx* c, const float** dv, const float** drgb) {
     if (!c || !dv) return MMS_ERR_INVALID;
     if (!c->haveDensity) return c->fail(MMS_ERR_INVALID, "no density has been computed");
     *dv = c->vol.as<float>();
-    if (drgb) *drgb = nullptr;
+    if (drgb) *drgb = c->haveColour ? c->rgb.as<float>() : nullptr;
     return MMS_OK;
 }
 
@@ -568,12 +589,15 @@ int mms_get_density(mms_ctx* c, const float** hv, const float** hrgb) {
     DeviceGuard guard(c->device);
     const size_t bytes = static_cast<size_t>(c->grid.res[0]) * c->grid.res[1] * c->nz * 4;
     if (!c->hVol.ensure(bytes)) return c->fail(MMS_ERR_NOMEM, "pinned allocation of %zu bytes failed", bytes);
+    const bool wantRgb = hrgb && c->haveColour;
+    if (wantRgb && !c->hRgb.ensure(bytes * 3)) return c->fail(MMS_ERR_NOMEM, "pinned allocation of %zu bytes failed", bytes * 3);
     c->rec(EV_DV0);
     MMS_CUDA(c, cudaMemcpyAsync(c->hVol.p, c->vol.p, bytes, cudaMemcpyDeviceToHost, c->stream));
+    if (wantRgb) MMS_CUDA(c, cudaMemcpyAsync(c->hRgb.p, c->rgb.p, bytes * 3, cudaMemcpyDeviceToHost, c->stream));
     c->rec(EV_DV1);
     if (int rc = checkDeviceError(c)) return rc;
     *hv = c->hVol.as<float>();
-    if (hrgb) *hrgb = nullptr;
+    if (hrgb) *hrgb = wantRgb ? c->hRgb.as<float>() : nullptr;
     return MMS_OK;
 }
 
@@ -587,6 +611,7 @@ int mms_set_density(mms_ctx* c, const float* volume) {
     ++c->launches;
     MMS_CUDA(c, cudaMemcpyAsync(c->hState.p, c->dstate.p, sizeof(DevState), cudaMemcpyDeviceToHost, c->stream));
     c->haveDensity = true;
+    c->haveColour = false;
     c->haveMesh = false;
     return MMS_OK;
 }
@@ -639,11 +664,15 @@ int mms_extract_isosurface(mms_ctx* c, float iso) {
     const unsigned long long T = c->hState.as<DevState>()->totalTris;
     c->ntris = T;
     if (T > 0) {
-        if (!c->meshPos.ensure(T * 36) || !c->meshNrm.ensure(T * 36))
+        if (!c->meshPos.ensure(T * 36) || !c->meshNrm.ensure(T * 36) || (c->haveColour && !c->meshCol.ensure(T * 36)))
             return c->fail(MMS_ERR_NOMEM, "device allocation of the mesh (%llu triangles, %llu bytes) failed", T, T * 72ull);
         dim3 gridE(m.nsegx, (m.cy + EY - 1) / EY, (m.cnz + EM_STEPS * EZ - 1) / (EM_STEPS * EZ));
-        mc_emit_kernel<false><<<gridE, MC_THREADS, sizeof(McEmitShared), st>>>(m, c->vol.as<float>(), nullptr, c->segOffset.as<unsigned>(),
-            c->meshPos.as<float>(), c->meshNrm.as<float>(), nullptr);
+        if (c->haveColour)
+            mc_emit_kernel<true><<<gridE, MC_THREADS, sizeof(McEmitShared) + 16 + E_EDGES * sizeof(float4), st>>>(m, c->vol.as<float>(),
+                c->rgb.as<float>(), c->segOffset.as<unsigned>(), c->meshPos.as<float>(), c->meshNrm.as<float>(), c->meshCol.as<float>());
+        else
+            mc_emit_kernel<false><<<gridE, MC_THREADS, sizeof(McEmitShared) + 16, st>>>(m, c->vol.as<float>(), nullptr,
+                c->segOffset.as<unsigned>(), c->meshPos.as<float>(), c->meshNrm.as<float>(), nullptr);
         ++c->launches;
     }
     c->rec(EV_MC1);
@@ -657,7 +686,7 @@ int mms_get_mesh_device(mms_ctx* c, uint64_t* nverts, const float** pos, const f
     *nverts = c->ntris * 3;
     if (pos) *pos = c->ntris ? c->meshPos.as<float>() : nullptr;
     if (nrm) *nrm = c->ntris ? c->meshNrm.as<float>() : nullptr;
-    if (col) *col = nullptr;
+    if (col) *col = (c->ntris && c->haveColour) ? c->meshCol.as<float>() : nullptr;
     return MMS_OK;
 }
 
@@ -671,15 +700,18 @@ int mms_get_mesh(mms_ctx* c, uint64_t* nverts, const float** pos, const float** 
     if (nrm) *nrm = nullptr;
     if (col) *col = nullptr;
     if (bytes) {
-        if ((pos && !c->hPos.ensure(bytes)) || (nrm && !c->hNrm.ensure(bytes)))
+        const bool wantCol = col && c->haveColour;
+        if ((pos && !c->hPos.ensure(bytes)) || (nrm && !c->hNrm.ensure(bytes)) || (wantCol && !c->hCol.ensure(bytes)))
             return c->fail(MMS_ERR_NOMEM, "pinned allocation of %zu bytes failed", bytes);
         c->rec(EV_DM0);
         if (pos) MMS_CUDA(c, cudaMemcpyAsync(c->hPos.p, c->meshPos.p, bytes, cudaMemcpyDeviceToHost, c->stream));
         if (nrm) MMS_CUDA(c, cudaMemcpyAsync(c->hNrm.p, c->meshNrm.p, bytes, cudaMemcpyDeviceToHost, c->stream));
+        if (wantCol) MMS_CUDA(c, cudaMemcpyAsync(c->hCol.p, c->meshCol.p, bytes, cudaMemcpyDeviceToHost, c->stream));
         c->rec(EV_DM1);
         MMS_CUDA(c, cudaStreamSynchronize(c->stream));
         if (pos) *pos = c->hPos.as<float>();
         if (nrm) *nrm = c->hNrm.as<float>();
+        if (wantCol) *col = c->hCol.as<float>();
     }
     return MMS_OK;
 }
