@@ -42,6 +42,9 @@ def workload(name: str):
     if name == "c2":
         return dict(name="C2: 10M LJ-fluid-like (jittered lattice, r=0.5, cyclic, normalize) -> 512^3 P2D bump + MC iso 0.5",
                     n=10_000_000, res=(512, 512, 512), kind="lj")
+    if name == "c3":
+        return dict(name="C3: 1M protein-like atoms (FLOAT_XYZR + FLOAT_RGBA, stride 32) -> 512^3 QuickSurf-Gaussian density + RGB volume "
+                         "+ coloured MC surface (radscale 1, quality 2, iso 0.5)", n=1_000_000, res=(512, 512, 512), kind="protein")
     raise SystemExit(f"unknown workload {name}")
 
 

@@ -128,7 +128,19 @@ class SlabJob:
         # weak scaling: the lattice (and the grid) grows along z with the number of ranks
         n1 = w["n"]
         res = list(w["res"])
-        if w["kind"] == "lj":
+        self.protein = w["kind"] == "protein"
+        if self.protein:
+            if world != 1:
+                raise SystemExit("the protein / QuickSurf workload (C3) is a single-GPU configuration")
+            from megamol_b200 import quicksurf
+            data, _, _ = synth.protein_like(n1)
+            self.n_total = n1
+            org, ext, _ = quicksurf.grid_from_particles(data[:, :3], data[:, 3], 1.0, 1.0)
+            # fixed 512^3 grid: gridspacing = padded extent / 512
+            self.origin = tuple(float(v) for v in org)
+            pad_ext = ext + 1.0
+            self.box = tuple(float(v) for v in pad_ext)
+        elif w["kind"] == "lj":
             L1 = int(np.ceil(n1 ** (1 / 3) - 1e-9))
             self.n_total = n1 * world
             a = np.float32(1.0794)
@@ -142,22 +154,30 @@ class SlabJob:
         self.res = tuple(res)
         i0 = (self.n_total * rank) // world
         i1 = (self.n_total * (rank + 1)) // world
-        if w["kind"] == "lj":
+        if self.protein:
+            xyz = data
+        elif w["kind"] == "lj":
             xyz = self._lj_chunk(i0, i1)
         else:
             xyz = synth.uniform_box(self.n_total, 1.0, i0=i0, i1=i1) * np.asarray(self.box, np.float32)
         self.n_local = i1 - i0
         # host copy in pinned memory (what an MMPLD reader would fill), device copy for the resident arm
-        self.h_xyz = torch.empty((self.n_local, 3), dtype=torch.float32, pin_memory=True)
+        self.h_xyz = torch.empty((self.n_local, xyz.shape[1]), dtype=torch.float32, pin_memory=True)
         self.h_xyz.numpy()[:] = xyz
         self.d_xyz = self.h_xyz.to(self.dev)
         self.slabs = plan_slabs(self.res[2], world)
         self.me = self.slabs[rank]
         self.surf = mm.Surf(local)
-        self.surf.set_grid((0, 0, 0), self.box, self.res, cyclic)
-        if world > 1:
-            self.surf.set_slab(self.me["z0"], self.me["nz"], self.me["cell_z0"], self.me["cell_nz"])
-        self.surf.set_params(mode=0, aggregator=0, normalize=int(normalize), defer_normalize=int(world > 1), sigma=sigma)
+        if self.protein:
+            self.cyclic = cyclic = (False, False, False)
+            self.normalize = False
+            self.surf.set_grid(self.origin, self.box, self.res, cyclic)
+            self.surf.set_params(mode=1, aggregator=0, normalize=0, radscale=1.0, gausslim=3.0, colour=1)
+        else:
+            self.surf.set_grid((0, 0, 0), self.box, self.res, cyclic)
+            if world > 1:
+                self.surf.set_slab(self.me["z0"], self.me["nz"], self.me["cell_z0"], self.me["cell_nz"])
+            self.surf.set_params(mode=0, aggregator=0, normalize=int(normalize), defer_normalize=int(world > 1), sigma=sigma)
         self.sdz = float(np.float32(self.box[2]) / np.float32(self.res[2] - 1))
         self._keep = []
         self.last = {}
@@ -228,7 +248,10 @@ class SlabJob:
     def _compute(self, xyz_ptr, n):
         s = self.surf
         s.clear_particles()
-        s.push_particles([dict(vtx=xyz_ptr, vtx_type=1, count=n, global_radius=self.radius)])
+        if self.protein:  # x y z r | R G B A interleaved, stride 32 (FLOAT_XYZR + FLOAT_RGBA)
+            s.push_particles([dict(vtx=xyz_ptr, vtx_type=2, vtx_stride=32, count=n, col=xyz_ptr + 16, col_type=4, col_stride=32)])
+        else:
+            s.push_particles([dict(vtx=xyz_ptr, vtx_type=1, count=n, global_radius=self.radius)])
         s.compute_density()
         if self.world > 1 and self.normalize:
             import torch.distributed as dist
@@ -261,8 +284,8 @@ class SlabJob:
         torch = self.torch
         if self.world == 1:
             self._compute(self.h_xyz.data_ptr(), self.n_local)
-            self.surf.get_density(copy=False)
-            self.surf.get_mesh(copy=False)
+            self.surf.get_density(copy=False, with_rgb=self.protein)
+            self.surf.get_mesh(copy=False, colours=self.protein)
         else:
             d = self.h_xyz.to(self.dev, non_blocking=True)
             recv = self._exchange(d)
@@ -308,6 +331,8 @@ class SlabJob:
         read (16 B each) + density written and read by MC (4 B each) + 72 B per triangle."""
         n = self.n_local
         v = self.res[0] * self.res[1] * self.me["nz"] if self.world > 1 else self.res[0] * self.res[1] * self.res[2]
+        if self.protein:  # 32 B records in, 16 + 16 B sorted (xyzr + rgba), density + RGB3F volume, coloured mesh (108 B / triangle)
+            return dict(bin=n * 32 + n * 32, density=n * 32 + v * 16, mc=v * 4 + self.local_tris() * 108, n=n, v=v)
         return dict(bin=n * 12 + n * 16, density=n * 16 + v * 4, mc=v * 4 + self.local_tris() * 72, n=n, v=v)
 
     def pipeline_bytes(self):
@@ -316,7 +341,8 @@ class SlabJob:
 
     def roofline(self, stage, peak):
         b = self._local_alg_bytes()
-        cand = {"bin (count+scan+scatter+order)": (stage["bin"], b["bin"]), "density_tile_kernel": (stage["density"], b["density"]),
+        cand = {"bin (count+scan+scatter+order)": (stage["bin"], b["bin"]),
+                ("density_gather_kernel" if self.protein else "density_splat_kernel"): (stage["density"], b["density"]),
                 "marching cubes (count+scan+emit)": (stage["mc"], b["mc"])}
         name = max(cand, key=lambda k: cand[k][0])
         ms, by = cand[name]
@@ -326,10 +352,12 @@ class SlabJob:
                 "per_stage_frac": {k: (v[1] / (v[0] * 1e-3) / 1e9 / peak if v[0] > 0 else None) for k, v in cand.items()}}
 
     def h2d_bytes(self):
-        return self.n_local * 12 * self.world
+        return self.n_local * (32 if self.protein else 12) * self.world
 
     def d2h_bytes(self):
         v = self.res[0] * self.res[1] * self.res[2]
+        if self.protein:
+            return v * 16 + getattr(self, "_tris_total", 0) * 108
         return v * 4 + getattr(self, "_tris_total", 0) * 72
 
     def describe(self):
