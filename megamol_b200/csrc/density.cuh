@@ -489,6 +489,8 @@ __global__ void __launch_bounds__(GT_THREADS, 2) density_gather_kernel(Geo g, De
         for (unsigned chunk = 0; chunk < ncand; chunk += GT_CHUNK) {
             const unsigned nin = min((unsigned)GT_CHUNK, ncand - chunk);
             __syncthreads();
+            GCand c;
+            bool keep = false;
             if ((unsigned)tid < nin) {
                 const unsigned pos = chunk + tid;
                 int lo = 0, hi = nseg;
@@ -498,7 +500,6 @@ __global__ void __launch_bounds__(GT_THREADS, 2) density_gather_kernel(Geo g, De
                 }
                 const unsigned idx = sh.segBegin[lo] + (pos - sh.segPrefix[lo]);
                 const float4 p = recs[idx];
-                GCand c;
                 c.x = p.x, c.y = p.y, c.z = p.z;
                 c.cr = c.cg = c.cb = 1.0f;
                 float eps;
@@ -521,24 +522,36 @@ __global__ void __launch_bounds__(GT_THREADS, 2) density_gather_kernel(Geo g, De
                 const float pp[3] = {p.x, p.y, p.z};
                 const int tl0[3] = {t0x, t0y, t0z}, tl1[3] = {t1x, t1y, t1z};
                 int kk[3] = {0, 0, 0};
+                float gap2 = 0.0f; // squared distance from the particle to the tile's box (in the particle's image frame)
 #pragma unroll
                 for (int a = 0; a < 3; ++a) {
-                    if (!g.cyc[a]) continue;
-                    const int H = homeVoxel(pp[a], g.mn[a], g.sd[a]);
-                    // voxel index seen by the particle = t + k, k a multiple of s, must meet [H - R, H + R], R = reach + 1:
-                    // the smallest such k is ceil((H - R - t1) / s) * s (at most one k works: checked per block above)
-                    const int R = reach + 1;
-                    const int a0 = H - R - tl1[a];
-                    const int q = -((-a0 - floorMod(-a0, g.s[a])) / g.s[a]); // ceil(a0 / s)
-                    int k = q * g.s[a];
-                    if (tl0[a] + k > H + R) k = 0; // no image reaches this tile
+                    int k = 0;
+                    if (g.cyc[a]) {
+                        const int H = homeVoxel(pp[a], g.mn[a], g.sd[a]);
+                        // voxel index seen by the particle = t + k, k a multiple of s, must meet [H - R, H + R], R = reach + 1:
+                        // the smallest such k is ceil((H - R - t1) / s) * s (at most one k works: checked per block above)
+                        const int R = reach + 1;
+                        const int a0 = H - R - tl1[a];
+                        const int q = -((-a0 - floorMod(-a0, g.s[a])) / g.s[a]); // ceil(a0 / s)
+                        k = q * g.s[a];
+                        if (tl0[a] + k > H + R) k = 0; // no image reaches this tile
+                    }
                     kk[a] = k;
+                    const float lo_ = (float)(tl0[a] + k) * g.sd[a] + g.mn[a], hi_ = (float)(tl1[a] + k) * g.sd[a] + g.mn[a];
+                    const float d = fmaxf(fmaxf(lo_ - pp[a], pp[a] - hi_), 0.0f);
+                    gap2 += d * d;
                 }
                 c.kx = kk[0], c.ky = kk[1], c.kz = kk[2], c.pad = 0;
-                sh.cand[tid] = c;
+                // sphere / tile-box rejection (1 % slack for the rounding of this test; the exact test is per voxel)
+                keep = gap2 <= eps * eps * 1.01f;
             }
+            // order-preserving compaction of the survivors
+            unsigned nkeep;
+            const unsigned slot = blockExclusiveScan(keep ? 1u : 0u, &nkeep, sh.scanTmp);
+            if (keep) sh.cand[slot] = c;
             __syncthreads();
-            for (unsigned j = 0; j < nin; ++j) {
+            const unsigned nstaged = nkeep;
+            for (unsigned j = 0; j < nstaged; ++j) {
                 const float4 A = reinterpret_cast<const float4*>(&sh.cand[j])[0];
                 const float4 B = reinterpret_cast<const float4*>(&sh.cand[j])[1];
                 const int4 K = reinterpret_cast<const int4*>(&sh.cand[j])[2];
