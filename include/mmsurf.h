@@ -154,6 +154,17 @@ uint64_t mms_launch_count(const mms_ctx* ctx);
 void* mms_alloc_pinned(size_t bytes);
 void mms_free_pinned(void* p);
 
+/* MMPLD frame ingest (replaces the loader of moldyn::MMPLDDataSource, plugins/moldyn/src/io/MMPLDDataSource.cpp:61-217,375-401,
+ * for this path): frames are read into pinned, double-buffered host memory and described as mms_list arrays (file colour types
+ * are translated to the in-memory enum).  Lists returned by read_frame stay valid until the second-next read_frame. */
+typedef struct mms_mmpld mms_mmpld;
+int mms_mmpld_open(mms_mmpld** out, const char* path);
+int mms_mmpld_close(mms_mmpld* reader);
+const char* mms_mmpld_last_error(const mms_mmpld* reader);
+int mms_mmpld_info(const mms_mmpld* reader, uint32_t* frames, uint32_t* version, float bbox[6], float clipbox[6]);
+int mms_mmpld_prefetch(mms_mmpld* reader, uint32_t frame); /* background thread, into the other buffer */
+int mms_mmpld_read_frame(mms_mmpld* reader, uint32_t frame, int32_t* nlists, const mms_list** lists, float* timestamp);
+
 int mms_version(void);
 
 #ifdef __cplusplus

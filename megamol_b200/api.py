@@ -18,7 +18,8 @@ EXPORTS = ["mms_create", "mms_destroy", "mms_last_error", "mms_set_grid", "mms_s
            "mms_clear_particles", "mms_push_particles", "mms_compute_density", "mms_get_density_range", "mms_normalize",
            "mms_get_density", "mms_get_density_device", "mms_set_density", "mms_extract_isosurface", "mms_get_mesh",
            "mms_get_mesh_device", "mms_get_home_voxels", "mms_get_cell_tricounts", "mms_get_timings", "mms_synchronize",
-           "mms_timer_start", "mms_timer_stop", "mms_launch_count", "mms_alloc_pinned", "mms_free_pinned", "mms_version"]
+           "mms_timer_start", "mms_timer_stop", "mms_launch_count", "mms_alloc_pinned", "mms_free_pinned", "mms_version", "mms_mmpld_open", "mms_mmpld_close",
+           "mms_mmpld_last_error", "mms_mmpld_info", "mms_mmpld_prefetch", "mms_mmpld_read_frame"]
 
 
 class MmsError(RuntimeError):
@@ -98,6 +99,13 @@ def load_library():
     L.mms_alloc_pinned.argtypes = [C.c_size_t]
     L.mms_alloc_pinned.restype = vp
     L.mms_free_pinned.argtypes = [vp]
+    L.mms_mmpld_open.argtypes = [C.POINTER(vp), C.c_char_p]
+    L.mms_mmpld_close.argtypes = [vp]
+    L.mms_mmpld_last_error.argtypes = [vp]
+    L.mms_mmpld_last_error.restype = C.c_char_p
+    L.mms_mmpld_info.argtypes = [vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    L.mms_mmpld_prefetch.argtypes = [vp, C.c_uint32]
+    L.mms_mmpld_read_frame.argtypes = [vp, C.c_uint32, C.POINTER(C.c_int32), C.POINTER(C.POINTER(MmsList)), C.POINTER(C.c_float)]
     _LIB = L
     return L
 
@@ -169,6 +177,10 @@ class Surf:
     def clear_particles(self):
         self._chk(self.L.mms_clear_particles(self.h))
         self._keep = []
+
+    def push_raw_lists(self, nlists, lists_ptr):
+        """lists_ptr: ctypes POINTER(MmsList) as returned by the MMPLD reader (no Python-side repacking)."""
+        self._chk(self.L.mms_push_particles(self.h, int(nlists), lists_ptr))
 
     def push_particles(self, lists):
         """lists: dicts {vtx: ndarray | int address (host or device), vtx_type, count, [vtx_stride], [col], [col_type],

@@ -9,10 +9,10 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmmsurf.so")
-SOURCES = ["mmsurf.cu"]
+SOURCES = ["mmsurf.cu", "mmpld.cpp"]
 HEADERS = ["common.cuh", "scan.cuh", "bin.cuh", "density.cuh", "mc.cuh", "mc_case_words.inc", "../../include/mmsurf.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
-              "-Xptxas", "-v", "--fmad=true", "-shared", "-cudart", "shared"]
+              "-Xptxas", "-v", "--fmad=true", "-shared", "-cudart", "shared", "-Xcompiler", "-pthread"]
 
 
 def nvcc() -> str:
