@@ -117,7 +117,10 @@ int mms_set_slab(mms_ctx* ctx, int32_t z0, int32_t nz, int32_t cell_z0, int32_t 
 int mms_set_params(mms_ctx* ctx, const mms_params* params);
 
 int mms_clear_particles(mms_ctx* ctx);
-/* Appends lists; data is copied (H2D, asynchronously for pinned memory) unless it already lives on the device. */
+/* Appends lists; data is copied (H2D on a dedicated copy stream, asynchronously for pinned memory, into one of two
+ * persistent upload arenas) unless it already lives on the device.  Pinned source buffers must stay valid until the next
+ * mms_compute_density returned.  Results of the previous compute stay readable, so frame k+1 can be pushed while frame k
+ * is still being read back (streaming). */
 int mms_push_particles(mms_ctx* ctx, int32_t nlists, const mms_list* lists);
 
 int mms_compute_density(mms_ctx* ctx);

@@ -81,6 +81,48 @@ struct PinBuf {
     template<class T> T* as() { return static_cast<T*>(p); }
 };
 
+/** Upload arena: device chunks that persist across frames (no cudaMalloc / cudaFree in steady state). Two arenas
+ *  alternate so that the H2D copy of frame k+1 (copy stream) overlaps the kernels of frame k. */
+struct Arena {
+    struct Chunk {
+        char* p;
+        size_t cap, used;
+    };
+    std::vector<Chunk> chunks;
+    cudaEvent_t consumed = nullptr; // recorded on the compute stream once the raw input has been re-written into cell order
+    bool consumedSet = false;
+    bool waited = true;             // the copy stream already waits for `consumed` in this frame
+    char* alloc(size_t bytes, size_t mis) {
+        for (auto& ch : chunks) {
+            const size_t off = (ch.used + 255) & ~size_t(255);
+            if (off + mis + bytes + 16 <= ch.cap) {
+                ch.used = off + mis + bytes;
+                return ch.p + off + mis;
+            }
+        }
+        size_t want = std::max<size_t>(bytes + mis + 512, size_t(32) << 20);
+        if (!chunks.empty()) want = std::max(want, chunks.back().cap + chunks.back().cap / 2);
+        void* p = nullptr;
+        if (cudaMalloc(&p, want) != cudaSuccess) {
+            cudaGetLastError();
+            want = bytes + mis + 512;
+            if (cudaMalloc(&p, want) != cudaSuccess) {
+                cudaGetLastError();
+                return nullptr;
+            }
+        }
+        chunks.push_back({static_cast<char*>(p), want, mis + bytes});
+        return static_cast<char*>(p) + mis;
+    }
+    void reset() {
+        for (auto& ch : chunks) ch.used = 0;
+    }
+    void release() {
+        for (auto& ch : chunks) cudaFree(ch.p);
+        chunks.clear();
+    }
+};
+
 enum Ev { EV_H2D0, EV_H2D1, EV_BIN0, EV_BIN1, EV_DEN1, EV_NRM0, EV_NRM1, EV_MC0, EV_MC1, EV_DV0, EV_DV1, EV_DM0, EV_DM1, EV_T0, EV_T1, EV_COUNT };
 
 } // namespace
@@ -94,7 +136,11 @@ struct mms_ctx {
     int z0 = 0, nz = 0, cellZ0 = 0, cellNz = 0;
     mms_params params{};
     std::vector<ListDev> lists;
-    std::vector<void*> listBufs; // device copies we own
+    Arena arena[2];
+    int arenaCur = 0;
+    cudaStream_t copyStream = nullptr;
+    cudaEvent_t uploadDone = nullptr;
+    bool uploadPending = false;
     unsigned long long nparticles = 0;
     bool haveDensity = false, haveMesh = false, normalized = false;
     unsigned long long ntris = 0;
@@ -252,6 +298,9 @@ int mms_create(mms_ctx** out, const mms_config* cfg) {
         return MMS_ERR_CUDA;
     }
     for (auto& ev : c->ev) cudaEventCreate(&ev);
+    cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&c->uploadDone, cudaEventDisableTiming);
+    for (auto& a : c->arena) cudaEventCreateWithFlags(&a.consumed, cudaEventDisableTiming);
     c->params.mode = MMS_MODE_P2D_BUMP;
     c->params.sigma = 1.0f;
     c->params.normalize = 1;
@@ -277,12 +326,13 @@ int mms_create(mms_ctx** out, const mms_config* cfg) {
 
 int mms_clear_particles(mms_ctx* c) {
     if (!c) return MMS_ERR_INVALID;
-    DeviceGuard guard(c->device);
-    cudaStreamSynchronize(c->stream);
-    for (void* p : c->listBufs) cudaFree(p);
-    c->listBufs.clear();
+    // no synchronisation, no frees: kernels already launched hold their pointers by value; the next pushes go to the OTHER
+    // arena, whose previous contents were consumed two frames ago (guarded by its `consumed` event)
     c->lists.clear();
     c->nparticles = 0;
+    c->arenaCur ^= 1;
+    c->arena[c->arenaCur].reset();
+    c->arena[c->arenaCur].waited = false;
     return MMS_OK;
 }
 
@@ -295,6 +345,14 @@ int mms_destroy(mms_ctx* c) {
                  &c->rgb, &c->segCount, &c->segOffset, &c->meshPos, &c->meshNrm, &c->meshCol, &c->triCount, &c->home, &c->dstate})
             b->release();
         for (PinBuf* b : {&c->hState, &c->hVol, &c->hRgb, &c->hPos, &c->hNrm, &c->hCol, &c->hHome, &c->hTri}) b->release();
+        cudaStreamSynchronize(c->stream);
+        cudaStreamSynchronize(c->copyStream);
+        for (auto& a : c->arena) {
+            a.release();
+            cudaEventDestroy(a.consumed);
+        }
+        cudaEventDestroy(c->uploadDone);
+        cudaStreamDestroy(c->copyStream);
         for (auto& ev : c->ev) cudaEventDestroy(ev);
         cudaStreamDestroy(c->stream);
     }
@@ -348,7 +406,9 @@ int mms_push_particles(mms_ctx* c, int32_t nlists, const mms_list* lists) {
     if (!c || nlists < 0 || (nlists > 0 && !lists)) return MMS_ERR_INVALID;
     DeviceGuard guard(c->device);
     if (c->lists.size() + nlists > static_cast<size_t>(kMaxLists)) return c->fail(MMS_ERR_UNSUPPORTED, "more than %d particle lists", kMaxLists);
-    c->rec(EV_H2D0);
+    Arena& arena = c->arena[c->arenaCur];
+    cudaEventRecord(c->ev[EV_H2D0], c->copyStream);
+    c->evSet[EV_H2D0] = true;
     for (int i = 0; i < nlists; ++i) {
         const mms_list& l = lists[i];
         if (l.vtx_type == MMS_VERT_NONE || l.count == 0) continue; // lists with VERTDATA_NONE are skipped (:464-466)
@@ -378,31 +438,27 @@ int mms_push_particles(mms_ctx* c, int32_t nlists, const mms_list* lists) {
             const uintptr_t uv = reinterpret_cast<uintptr_t>(hv), uc = reinterpret_cast<uintptr_t>(hc);
             const bool interleaved = d.ctype && uc + d.vstride >= uv && uc < uv + vbytes + d.vstride;
             if (interleaved) lo = std::min(lo, hc), hi = std::max(hi, hc + cbytes);
-            void* dv = nullptr;
             // keep the source's alignment modulo 16 so that aligned host data stays aligned on the device
             const size_t mis = reinterpret_cast<uintptr_t>(lo) & 15u;
-            if (cudaMalloc(&dv, static_cast<size_t>(hi - lo) + mis + 16) != cudaSuccess) {
-                cudaGetLastError();
-                return c->fail(MMS_ERR_NOMEM, "device allocation of %zu bytes for list %d failed", static_cast<size_t>(hi - lo), i);
+            if (!arena.waited) { // first upload into this arena for the new frame: its old contents must have been consumed
+                if (arena.consumedSet) MMS_CUDA(c, cudaStreamWaitEvent(c->copyStream, arena.consumed, 0));
+                arena.waited = true;
             }
-            c->listBufs.push_back(dv);
-            char* dbase = static_cast<char*>(dv) + mis;
-            MMS_CUDA(c, cudaMemcpyAsync(dbase, lo, static_cast<size_t>(hi - lo), cudaMemcpyHostToDevice, c->stream));
+            char* dbase = arena.alloc(static_cast<size_t>(hi - lo), mis);
+            if (!dbase) return c->fail(MMS_ERR_NOMEM, "device allocation of %zu bytes for list %d failed", static_cast<size_t>(hi - lo), i);
+            MMS_CUDA(c, cudaMemcpyAsync(dbase, lo, static_cast<size_t>(hi - lo), cudaMemcpyHostToDevice, c->copyStream));
             d.vtx = dbase + (hv - lo);
             if (d.ctype) {
                 if (interleaved) {
                     d.col = dbase + (hc - lo);
                 } else {
-                    void* dc = nullptr;
-                    if (cudaMalloc(&dc, cbytes + 16) != cudaSuccess) {
-                        cudaGetLastError();
-                        return c->fail(MMS_ERR_NOMEM, "device allocation of %zu bytes for colours of list %d failed", cbytes, i);
-                    }
-                    c->listBufs.push_back(dc);
-                    MMS_CUDA(c, cudaMemcpyAsync(dc, hc, cbytes, cudaMemcpyHostToDevice, c->stream));
-                    d.col = static_cast<const char*>(dc);
+                    char* dc = arena.alloc(cbytes, reinterpret_cast<uintptr_t>(hc) & 15u);
+                    if (!dc) return c->fail(MMS_ERR_NOMEM, "device allocation of %zu bytes for colours of list %d failed", cbytes, i);
+                    MMS_CUDA(c, cudaMemcpyAsync(dc, hc, cbytes, cudaMemcpyHostToDevice, c->copyStream));
+                    d.col = dc;
                 }
             }
+            c->uploadPending = true;
         }
         d.valign = alignOf(d.vtx, d.vstride, l.vtx_type == MMS_VERT_DOUBLE_XYZ ? 8 : (l.vtx_type == MMS_VERT_FLOAT_XYZR ? 16 : 4));
         if (l.vtx_type == MMS_VERT_DOUBLE_XYZ && d.valign < 8) d.valign = 1;
@@ -413,8 +469,10 @@ int mms_push_particles(mms_ctx* c, int32_t nlists, const mms_list* lists) {
         c->lists.push_back(d);
         c->nparticles += l.count;
     }
-    c->rec(EV_H2D1);
-    c->haveDensity = c->haveMesh = false;
+    cudaEventRecord(c->ev[EV_H2D1], c->copyStream);
+    c->evSet[EV_H2D1] = true;
+    if (c->uploadPending) MMS_CUDA(c, cudaEventRecord(c->uploadDone, c->copyStream));
+    // results of the previous compute stay readable: pushing frame k+1 while frame k is being read back is the streaming pattern
     return MMS_OK;
 }
 
@@ -423,6 +481,10 @@ int mms_compute_density(mms_ctx* c) {
     if (c->nparticles >= (1ull << 32) - 1) return c->fail(MMS_ERR_UNSUPPORTED, "2^32 or more particles per context");
     DeviceGuard guard(c->device);
     cudaStream_t st = c->stream;
+    if (c->uploadPending) {
+        MMS_CUDA(c, cudaStreamWaitEvent(st, c->uploadDone, 0));
+        c->uploadPending = false;
+    }
     c->rec(EV_BIN0);
     init_state_kernel<<<1, 1, 0, st>>>(c->dstate.as<DevState>());
     ++c->launches;
@@ -494,6 +556,9 @@ int mms_compute_density(mms_ctx* c) {
             c->auxA.as<float>(), auxN);
         ++c->launches;
     }
+    // the raw input is not needed any more: its arena may be overwritten by the upload of the frame after next
+    MMS_CUDA(c, cudaEventRecord(c->arena[c->arenaCur].consumed, st));
+    c->arena[c->arenaCur].consumedSet = true;
     if (n > 0) {
         // upper bound n threads; slots >= kept are never claimed, the kernel reads the segment table only
         cell_order_kernel<<<gridFor(n, 256, 1 << 30), 256, 0, st>>>(g, c->cellStart.as<unsigned>(), c->recsA.as<float4>(), c->auxA.as<float>(),
@@ -749,6 +814,7 @@ int mms_get_cell_tricounts(mms_ctx* c, const uint8_t** counts, uint64_t* ncells)
 int mms_synchronize(mms_ctx* c) {
     if (!c) return MMS_ERR_INVALID;
     DeviceGuard guard(c->device);
+    MMS_CUDA(c, cudaStreamSynchronize(c->copyStream));
     MMS_CUDA(c, cudaStreamSynchronize(c->stream));
     return MMS_OK;
 }
@@ -756,6 +822,7 @@ int mms_synchronize(mms_ctx* c) {
 int mms_get_timings(mms_ctx* c, mms_timings* t) {
     if (!c || !t) return MMS_ERR_INVALID;
     DeviceGuard guard(c->device);
+    MMS_CUDA(c, cudaStreamSynchronize(c->copyStream));
     MMS_CUDA(c, cudaStreamSynchronize(c->stream));
     auto el = [&](Ev a, Ev b) -> float {
         float ms = 0.0f;
