@@ -729,7 +729,10 @@ int mms_extract_isosurface(mms_ctx* c, float iso) {
     const unsigned long long T = c->hState.as<DevState>()->totalTris;
     c->ntris = T;
     if (T > 0) {
-        if (!c->meshPos.ensure(T * 36) || !c->meshNrm.ensure(T * 36) || (c->haveColour && !c->meshCol.ensure(T * 36)))
+        // 1/8 headroom: the triangle count of a time series wobbles from frame to frame; growing a multi-GB buffer is a stall
+        const size_t mbytes = static_cast<size_t>(T) * 36, mwant = mbytes + mbytes / 8;
+        auto grow = [&](DevBuf& b) { return b.cap >= mbytes || b.ensure(mwant) || b.ensure(mbytes); };
+        if (!grow(c->meshPos) || !grow(c->meshNrm) || (c->haveColour && !grow(c->meshCol)))
             return c->fail(MMS_ERR_NOMEM, "device allocation of the mesh (%llu triangles, %llu bytes) failed", T, T * 72ull);
         dim3 gridE(m.nsegx, (m.cy + EY - 1) / EY, (m.cnz + EM_STEPS * EZ - 1) / (EM_STEPS * EZ));
         if (c->haveColour)
@@ -766,7 +769,8 @@ int mms_get_mesh(mms_ctx* c, uint64_t* nverts, const float** pos, const float** 
     if (col) *col = nullptr;
     if (bytes) {
         const bool wantCol = col && c->haveColour;
-        if ((pos && !c->hPos.ensure(bytes)) || (nrm && !c->hNrm.ensure(bytes)) || (wantCol && !c->hCol.ensure(bytes)))
+        auto growPin = [&](PinBuf& b) { return b.cap >= bytes || b.ensure(bytes + bytes / 8) || b.ensure(bytes); };
+        if ((pos && !growPin(c->hPos)) || (nrm && !growPin(c->hNrm)) || (wantCol && !growPin(c->hCol)))
             return c->fail(MMS_ERR_NOMEM, "pinned allocation of %zu bytes failed", bytes);
         c->rec(EV_DM0);
         if (pos) MMS_CUDA(c, cudaMemcpyAsync(c->hPos.p, c->meshPos.p, bytes, cudaMemcpyDeviceToHost, c->stream));
