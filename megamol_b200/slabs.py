@@ -270,13 +270,21 @@ class SlabJob:
             self._compute(self.d_xyz.data_ptr(), self.n_local)
             self.surf.synchronize()
         else:
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            ev[0].record()
             recv = self._exchange(self.d_xyz)
+            ev[1].record()
             torch.cuda.current_stream().synchronize()
             self._keep = [recv]
             self._compute(recv.data_ptr(), recv.shape[0])
             self.surf.synchronize()
+            ev[2].record()
             self._gather_mesh()
+            ev[3].record()
             torch.cuda.current_stream().synchronize()
+            self.last["exchange_ms"] = ev[0].elapsed_time(ev[1])
+            self.last["gather_ms"] = ev[2].elapsed_time(ev[3])
+            self.last["n_recv"] = int(recv.shape[0])
         self.last["n_in"] = self.n_local
 
     def step_e2e(self):
@@ -309,7 +317,11 @@ class SlabJob:
 
     def stage_times(self):
         t = self.surf.timings()
-        return {k: round(v, 4) for k, v in t.items()}
+        out = {k: round(v, 4) for k, v in t.items()}
+        for k in ("exchange_ms", "gather_ms"):
+            if k in self.last:
+                out[k[:-3]] = round(self.last[k], 4)
+        return out
 
     def local_tris(self):
         n, _, _ = self.surf.mesh_device()
