@@ -1,4 +1,2 @@
 mkdir -p gpurun_out
-ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches_r1a.csv python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/b_ncu.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:'density_tile|mc_emit|mc_count|bin_scatter|cell_order|bin_count' -s 12 -c 6 -o gpurun_out/prof_r1a python bench.py --steps 1 --warmup 3 --no-cpu > gpurun_out/b_ncu2.log 2>&1
-ls -la gpurun_out
+ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches_r1e.csv python bench.py --steps 1 --warmup 3 --no-cpu > gpurun_out/b_ncu.log 2>&1

@@ -41,9 +41,8 @@ struct McGeo {
 // ---------------------------------------------------------------------------------------------------------------
 // count
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int MCX = 32, MCY = 8, MCZ = 4; // cells per block tile of the count kernel
 constexpr int MC_THREADS = 256;
-constexpr int MC_NX = MCX + 1, MC_NY = MCY + 1, MC_NZ = MCZ + 1;
+constexpr int MCC_ROWS = 16; // cell rows (y) per warp of the count kernel
 
 __device__ __forceinline__ int cubeIndexSmem(const float* f, int strideY, int strideZ, float iso) {
     // f points at corner 0; corners: (0,0,0) (1,0,0) (1,1,0) (0,1,0) (0,0,1) (1,0,1) (1,1,1) (0,1,1)
@@ -59,35 +58,69 @@ __device__ __forceinline__ int cubeIndexSmem(const float* f, int strideY, int st
     return ci;
 }
 
+/**
+ * Count kernel, register-rolling: a warp owns one 32-cell x-segment of one cell layer and walks MCC_ROWS rows in y.
+ * Per row it loads two node rows (planes z and z+1, 128 contiguous bytes each) -- the previous row's "below iso" bits are
+ * kept in registers, the x+1 neighbour comes from a shuffle -- so a cell costs two coalesced loads and ~25 instructions.
+ * Per-cell lookups go to a shared copy of the count table (the constant cache would serialise per-lane indices).
+ */
 __global__ void __launch_bounds__(MC_THREADS) mc_count_kernel(McGeo m, const float* __restrict__ vol, unsigned* __restrict__ segCount,
     unsigned char* __restrict__ triCount) {
-    __shared__ float f[MC_NZ][MC_NY][MC_NX + 1];
-    __shared__ unsigned char sCount[256]; // per-lane indexed lookups: shared memory, not the (serialising) constant cache
-    const int x0 = blockIdx.x * MCX, y0 = blockIdx.y * MCY, zc0 = m.cz0 + blockIdx.z * MCZ; // global cell coords
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __shared__ unsigned char sCount[256];
     sCount[threadIdx.x] = static_cast<unsigned char>(kCaseWords[threadIdx.x] & 15ull);
-    // rows of 33 nodes, one warp per row (clamped; clamped duplicates only feed cells that are masked out below)
-    for (int r = warp; r < MC_NZ * MC_NY; r += MC_THREADS / 32) {
-        const int iy = r % MC_NY, iz = r / MC_NY;
-        const int y = min(y0 + iy, m.sy - 1);
-        const int zl = min(zc0 + iz - m.zPlane0, m.nzPlanes - 1);
-        const float* row = vol + static_cast<size_t>(m.sx) * (y + static_cast<size_t>(m.sy) * zl);
-        f[iz][iy][lane] = row[min(x0 + lane, m.sx - 1)];
-        if (lane == 0) f[iz][iy][32] = row[min(x0 + 32, m.sx - 1)];
-    }
     __syncthreads();
-    for (int r = warp; r < MCY * MCZ; r += MC_THREADS / 32) {
-        const int ly = r % MCY, lz = r / MCY;
-        const int cxi = x0 + lane, cyi = y0 + ly, czi = zc0 + lz;
-        if (cyi >= m.cy || czi >= m.cz0 + m.cnz) continue; // warp-uniform
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int xseg = blockIdx.x;
+    const int yBeg = (blockIdx.y * (MC_THREADS / 32) + warp) * MCC_ROWS;
+    const int czi = m.cz0 + blockIdx.z; // global cell layer
+    if (yBeg >= m.cy || czi >= m.cz0 + m.cnz) return;
+    const int yEnd = min(yBeg + MCC_ROWS, m.cy);
+    const int x = xseg * 32 + lane;
+    const int xa = min(x, m.sx - 1), xb = min(xseg * 32 + 32, m.sx - 1); // lane 31's right neighbour is node 32 of the segment
+    const int zl = czi - m.zPlane0;
+    const float* p0 = vol + static_cast<size_t>(m.sx) * m.sy * zl;
+    const float* p1 = p0 + static_cast<size_t>(m.sx) * m.sy;
+    // all loads of the strip first (2 x 17 independent 128-byte requests per warp in flight), then the arithmetic
+    unsigned bits[MCC_ROWS + 1];
+    {
+        float a[MCC_ROWS + 1], b[MCC_ROWS + 1];
+#pragma unroll
+        for (int r = 0; r <= MCC_ROWS; ++r) {
+            const size_t o = static_cast<size_t>(m.sx) * min(yBeg + r, m.sy - 1);
+            a[r] = p0[o + (lane == 31 ? xb : xa)]; // placeholder for lane 31's neighbour, fixed below
+            b[r] = p1[o + (lane == 31 ? xb : xa)];
+        }
+        float a31[MCC_ROWS + 1], b31[MCC_ROWS + 1];
+#pragma unroll
+        for (int r = 0; r <= MCC_ROWS; ++r) { // lane 31's own node (x = 32*xseg + 31): loaded by every lane's slot? no: one extra request
+            const size_t o = static_cast<size_t>(m.sx) * min(yBeg + r, m.sy - 1);
+            a31[r] = p0[o + xa];
+            b31[r] = p1[o + xa];
+        }
+#pragma unroll
+        for (int r = 0; r <= MCC_ROWS; ++r) {
+            // me: my own node; nb: node x+1 (lane 31: node 32 of the segment, loaded above into a/b)
+            const unsigned me = (a31[r] < m.iso ? 1u : 0u) | (b31[r] < m.iso ? 2u : 0u);
+            unsigned nb = __shfl_down_sync(0xffffffffu, me, 1);
+            if (lane == 31) nb = (a[r] < m.iso ? 1u : 0u) | (b[r] < m.iso ? 2u : 0u);
+            bits[r] = me | (nb << 2);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < MCC_ROWS; ++r) {
+        const int y = yBeg + r;
+        if (y >= yEnd) break;
+        const unsigned prev = bits[r], cur = bits[r + 1];
+        // corners: 0 (x,y,z) 1 (x+1,y,z) 2 (x+1,y+1,z) 3 (x,y+1,z) 4 (x,y,z+1) 5 (x+1,y,z+1) 6 (x+1,y+1,z+1) 7 (x,y+1,z+1)
+        const unsigned ci = (prev & 1u) | ((prev >> 2) & 1u) << 1 | ((cur >> 2) & 1u) << 2 | (cur & 1u) << 3 | ((prev >> 1) & 1u) << 4 |
+                            ((prev >> 3) & 1u) << 5 | ((cur >> 3) & 1u) << 6 | ((cur >> 1) & 1u) << 7;
         unsigned n = 0;
-        if (cxi < m.cx) {
-            const int ci = cubeIndexSmem(&f[lz][ly][lane], MC_NX + 1, (MC_NX + 1) * MC_NY, m.iso);
+        if (x < m.cx) {
             n = sCount[ci];
-            if (triCount) triCount[cxi + static_cast<size_t>(m.cx) * (cyi + static_cast<size_t>(m.cy) * (czi - m.cz0))] = static_cast<unsigned char>(n);
+            if (triCount) triCount[x + static_cast<size_t>(m.cx) * (y + static_cast<size_t>(m.cy) * (czi - m.cz0))] = static_cast<unsigned char>(n);
         }
         const unsigned tot = __reduce_add_sync(0xffffffffu, n);
-        if (lane == 0) segCount[blockIdx.x + static_cast<size_t>(m.nsegx) * (cyi + static_cast<size_t>(m.cy) * (czi - m.cz0))] = tot;
+        if (lane == 0) segCount[xseg + static_cast<size_t>(m.nsegx) * (y + static_cast<size_t>(m.cy) * (czi - m.cz0))] = tot;
     }
 }
 

@@ -689,7 +689,7 @@ int mms_extract_isosurface(mms_ctx* c, float iso) {
     m.sx = c->grid.res[0], m.sy = c->grid.res[1];
     m.nzPlanes = c->nz, m.zPlane0 = c->z0, m.szGlobal = c->grid.res[2];
     m.cx = m.sx - 1, m.cy = m.sy - 1, m.cz0 = c->cellZ0, m.cnz = c->cellNz;
-    m.nsegx = (m.cx + MCX - 1) / MCX;
+    m.nsegx = (m.cx + 31) / 32;
     const Geo g = makeGeo(c);
     for (int a = 0; a < 3; ++a) {
         m.org[a] = g.mn[a], m.sd[a] = g.sd[a];
@@ -718,7 +718,7 @@ int mms_extract_isosurface(mms_ctx* c, float iso) {
     }
     cudaStream_t st = c->stream;
     c->rec(EV_MC0);
-    dim3 grid(m.nsegx, (m.cy + MCY - 1) / MCY, (m.cnz + MCZ - 1) / MCZ);
+    dim3 grid(m.nsegx, (m.cy + (MC_THREADS / 32) * MCC_ROWS - 1) / ((MC_THREADS / 32) * MCC_ROWS), m.cnz);
     mc_count_kernel<<<grid, MC_THREADS, 0, st>>>(m, c->vol.as<float>(), c->segCount.as<unsigned>(), tri);
     ++c->launches;
     DevState* ds = c->dstate.as<DevState>();
