@@ -173,7 +173,7 @@ def run_ours(args, w):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    job = slabs.SlabJob(w, rank, world, local, iso=ISO, radius=RADIUS)
+    job = slabs.SlabJob(w, rank, world, local, iso=ISO, radius=RADIUS, gather=args.gather)
     peak, peak_src = load_peaks()
 
     # ---- device-resident arm -------------------------------------------------------------------------------
@@ -284,6 +284,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--gather", default="fused", choices=["fused", "nccl"], help="multi-GPU mesh gather: fused peer-store emit or NCCL send/recv")
     ap.add_argument("--frames", type=int, default=12, help="frames of the C5 time series")
     ap.add_argument("--tmpdir", default="/tmp")
     args = ap.parse_args()

@@ -135,7 +135,14 @@ int mms_get_density_device(mms_ctx* ctx, const float** dev_volume, const float**
  * `volume` may be host or device memory, res-shaped for the current slab. */
 int mms_set_density(mms_ctx* ctx, const float* volume);
 
-int mms_extract_isosurface(mms_ctx* ctx, float isovalue);
+int mms_extract_isosurface(mms_ctx* ctx, float isovalue); /* = count + emit into library-owned buffers */
+/* The two halves of extract, for callers that own the destination: count (classify + scan, one host round trip for the size),
+ * then emit into caller-supplied DEVICE memory starting at triangle `first_triangle` (9 floats per triangle and array).
+ * The destination may be this GPU's memory, a CUDA-IPC / peer mapping of another GPU's buffer (the z-slab driver lets every
+ * rank write its slab's triangles straight into rank 0's mesh over NVLink: compute and gather in ONE kernel), or a
+ * graphics-interop mapping of a vertex buffer.  pos == NULL emits into the library's own buffers. */
+int mms_count_isosurface(mms_ctx* ctx, float isovalue, uint64_t* ntriangles);
+int mms_emit_isosurface(mms_ctx* ctx, float* pos, float* nrm, float* col, uint64_t first_triangle);
 /* Triangle soup: nverts = 3 * triangles; pos/nrm/col = 3 floats per vertex (col NULL unless colour mode). */
 int mms_get_mesh(mms_ctx* ctx, uint64_t* nverts, const float** pos, const float** nrm, const float** col);
 int mms_get_mesh_device(mms_ctx* ctx, uint64_t* nverts, const float** pos, const float** nrm, const float** col);
@@ -152,6 +159,13 @@ int mms_timer_stop(mms_ctx* ctx, float* elapsed_ms);
 int mms_synchronize(mms_ctx* ctx);
 /* Number of kernel launches issued by this context so far (for bench.py's gpu_launches). */
 uint64_t mms_launch_count(const mms_ctx* ctx);
+
+/* Device buffers that can be shared between the per-GPU processes of one node (CUDA IPC over NVLink / PCIe P2P). */
+int mms_device_alloc(int32_t device, size_t bytes, void** ptr);
+int mms_device_free(int32_t device, void* ptr);
+int mms_ipc_export(int32_t device, const void* devptr, unsigned char handle[64]);
+int mms_ipc_open(int32_t device, const unsigned char handle[64], void** ptr);
+int mms_ipc_close(int32_t device, void* ptr);
 
 /* Pinned host memory for callers that want zero-staging H2D (e.g. an MMPLD reader). */
 void* mms_alloc_pinned(size_t bytes);

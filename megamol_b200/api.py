@@ -16,7 +16,8 @@ MODE_P2D_BUMP, MODE_QS_GAUSS = 0, 1
 
 EXPORTS = ["mms_create", "mms_destroy", "mms_last_error", "mms_set_grid", "mms_set_slab", "mms_set_params",
            "mms_clear_particles", "mms_push_particles", "mms_compute_density", "mms_get_density_range", "mms_normalize",
-           "mms_get_density", "mms_get_density_device", "mms_set_density", "mms_extract_isosurface", "mms_get_mesh",
+           "mms_get_density", "mms_get_density_device", "mms_set_density", "mms_extract_isosurface", "mms_count_isosurface", "mms_emit_isosurface", "mms_device_alloc",
+           "mms_device_free", "mms_ipc_export", "mms_ipc_open", "mms_ipc_close", "mms_get_mesh",
            "mms_get_mesh_device", "mms_get_home_voxels", "mms_get_cell_tricounts", "mms_get_timings", "mms_synchronize",
            "mms_timer_start", "mms_timer_stop", "mms_launch_count", "mms_alloc_pinned", "mms_free_pinned", "mms_version", "mms_mmpld_open", "mms_mmpld_close",
            "mms_mmpld_last_error", "mms_mmpld_info", "mms_mmpld_prefetch", "mms_mmpld_read_frame"]
@@ -86,6 +87,13 @@ def load_library():
     L.mms_get_density_device.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
     L.mms_set_density.argtypes = [vp, vp]
     L.mms_extract_isosurface.argtypes = [vp, C.c_float]
+    L.mms_count_isosurface.argtypes = [vp, C.c_float, C.POINTER(C.c_uint64)]
+    L.mms_emit_isosurface.argtypes = [vp, vp, vp, vp, C.c_uint64]
+    L.mms_device_alloc.argtypes = [C.c_int32, C.c_size_t, C.POINTER(vp)]
+    L.mms_device_free.argtypes = [C.c_int32, vp]
+    L.mms_ipc_export.argtypes = [C.c_int32, vp, C.POINTER(C.c_ubyte)]
+    L.mms_ipc_open.argtypes = [C.c_int32, C.POINTER(C.c_ubyte), C.POINTER(vp)]
+    L.mms_ipc_close.argtypes = [C.c_int32, vp]
     L.mms_get_mesh.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     L.mms_get_mesh_device.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     L.mms_get_home_voxels.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_uint64)]
@@ -249,6 +257,15 @@ class Surf:
 
     def extract_isosurface(self, iso):
         self._chk(self.L.mms_extract_isosurface(self.h, float(iso)))
+
+    def count_isosurface(self, iso) -> int:
+        n = C.c_uint64()
+        self._chk(self.L.mms_count_isosurface(self.h, float(iso), C.byref(n)))
+        return int(n.value)
+
+    def emit_isosurface(self, pos=None, nrm=None, col=None, first_triangle=0):
+        """pos/nrm/col: device addresses (ints) of caller-owned buffers, or None for the library's own buffers."""
+        self._chk(self.L.mms_emit_isosurface(self.h, pos, nrm, col, int(first_triangle)))
 
     def get_mesh(self, copy=True, normals=True, colours=False):
         n = C.c_uint64()

@@ -147,6 +147,8 @@ struct mms_ctx {
     unsigned long long launches = 0;
     int cshift = 2, reach = 2;
     bool useGather = false, haveColour = false;
+    McGeo mcGeo{};
+    bool haveCount = false, meshExternal = false;
 
     DevBuf cellCount, cellStart, cursor, tileSums, recsA, recsB, auxA, auxB, vol, rgb, segCount, segOffset, meshPos, meshNrm,
         meshCol, triCount, home, dstate;
@@ -681,7 +683,7 @@ int mms_set_density(mms_ctx* c, const float* volume) {
     return MMS_OK;
 }
 
-int mms_extract_isosurface(mms_ctx* c, float iso) {
+int mms_count_isosurface(mms_ctx* c, float iso, uint64_t* ntris) {
     if (!c) return MMS_ERR_INVALID;
     if (!c->haveDensity) return c->fail(MMS_ERR_INVALID, "no density has been computed");
     DeviceGuard guard(c->device);
@@ -701,9 +703,13 @@ int mms_extract_isosurface(mms_ctx* c, float iso) {
         m.rinv[a][0] = 0.0f;
     }
     m.iso = iso;
-    m.debug = getenv("MMS_DEBUG_MC") ? atoi(getenv("MMS_DEBUG_MC")) : 0;
+    m.debug = 0;
+    c->mcGeo = m;
     c->ntris = 0;
-    c->haveMesh = true;
+    c->haveCount = true;
+    c->haveMesh = false;
+    if (ntris) *ntris = 0;
+    c->rec(EV_MC0);
     if (m.cnz <= 0) return MMS_OK;
     const size_t nseg = static_cast<size_t>(m.nsegx) * m.cy * m.cnz;
     if (nseg >= (1ull << 32) - 1) return c->fail(MMS_ERR_UNSUPPORTED, "too many cell segments");
@@ -717,7 +723,6 @@ int mms_extract_isosurface(mms_ctx* c, float iso) {
         tri = c->triCount.as<unsigned char>();
     }
     cudaStream_t st = c->stream;
-    c->rec(EV_MC0);
     dim3 grid(m.nsegx, (m.cy + (MC_THREADS / 32) * MCC_ROWS - 1) / ((MC_THREADS / 32) * MCC_ROWS), m.cnz);
     mc_count_kernel<<<grid, MC_THREADS, 0, st>>>(m, c->vol.as<float>(), c->segCount.as<unsigned>(), tri);
     ++c->launches;
@@ -726,31 +731,58 @@ int mms_extract_isosurface(mms_ctx* c, float iso) {
         &ds->totalTris, st, c->launches);
     MMS_CUDA(c, cudaMemcpyAsync(c->hState.p, c->dstate.p, sizeof(DevState), cudaMemcpyDeviceToHost, st));
     MMS_CUDA(c, cudaStreamSynchronize(st)); // the one host round trip: the mesh size decides the allocation
-    const unsigned long long T = c->hState.as<DevState>()->totalTris;
-    c->ntris = T;
-    if (T > 0) {
-        // 1/8 headroom: the triangle count of a time series wobbles from frame to frame; growing a multi-GB buffer is a stall
-        const size_t mbytes = static_cast<size_t>(T) * 36, mwant = mbytes + mbytes / 8;
-        auto grow = [&](DevBuf& b) { return b.cap >= mbytes || b.ensure(mwant) || b.ensure(mbytes); };
-        if (!grow(c->meshPos) || !grow(c->meshNrm) || (c->haveColour && !grow(c->meshCol)))
-            return c->fail(MMS_ERR_NOMEM, "device allocation of the mesh (%llu triangles, %llu bytes) failed", T, T * 72ull);
+    c->ntris = c->hState.as<DevState>()->totalTris;
+    if (ntris) *ntris = c->ntris;
+    return MMS_OK;
+}
+
+int mms_emit_isosurface(mms_ctx* c, float* pos, float* nrm, float* col, uint64_t first_triangle) {
+    if (!c) return MMS_ERR_INVALID;
+    if (!c->haveCount) return c->fail(MMS_ERR_INVALID, "mms_count_isosurface has not been called");
+    DeviceGuard guard(c->device);
+    const McGeo& m = c->mcGeo;
+    cudaStream_t st = c->stream;
+    const bool own = pos == nullptr;
+    if (c->ntris > 0) {
+        float *P = pos, *N = nrm, *C = col;
+        if (own) {
+            // 1/8 headroom: the triangle count of a time series wobbles from frame to frame; growing a multi-GB buffer is a stall
+            const size_t mbytes = static_cast<size_t>(c->ntris) * 36, mwant = mbytes + mbytes / 8;
+            auto grow = [&](DevBuf& b) { return b.cap >= mbytes || b.ensure(mwant) || b.ensure(mbytes); };
+            if (!grow(c->meshPos) || !grow(c->meshNrm) || (c->haveColour && !grow(c->meshCol)))
+                return c->fail(MMS_ERR_NOMEM, "device allocation of the mesh (%llu triangles, %llu bytes) failed", c->ntris, c->ntris * 72ull);
+            P = c->meshPos.as<float>(), N = c->meshNrm.as<float>(), C = c->haveColour ? c->meshCol.as<float>() : nullptr;
+        } else {
+            if (!nrm) return c->fail(MMS_ERR_INVALID, "a normal buffer is required");
+            if (c->haveColour && !col) return c->fail(MMS_ERR_INVALID, "colour mode needs a colour buffer");
+            P += first_triangle * 9, N += first_triangle * 9;
+            if (C) C += first_triangle * 9;
+        }
         dim3 gridE(m.nsegx, (m.cy + EY - 1) / EY, (m.cnz + EM_STEPS * EZ - 1) / (EM_STEPS * EZ));
         if (c->haveColour)
             mc_emit_kernel<true><<<gridE, MC_THREADS, sizeof(McEmitShared) + 16 + E_EDGES * sizeof(float4), st>>>(m, c->vol.as<float>(),
-                c->rgb.as<float>(), c->segOffset.as<unsigned>(), c->meshPos.as<float>(), c->meshNrm.as<float>(), c->meshCol.as<float>());
+                c->rgb.as<float>(), c->segOffset.as<unsigned>(), P, N, C);
         else
             mc_emit_kernel<false><<<gridE, MC_THREADS, sizeof(McEmitShared) + 16, st>>>(m, c->vol.as<float>(), nullptr,
-                c->segOffset.as<unsigned>(), c->meshPos.as<float>(), c->meshNrm.as<float>(), nullptr);
+                c->segOffset.as<unsigned>(), P, N, nullptr);
         ++c->launches;
     }
     c->rec(EV_MC1);
     MMS_CUDA(c, cudaGetLastError());
+    c->haveMesh = true;
+    c->meshExternal = !own;
     return MMS_OK;
+}
+
+int mms_extract_isosurface(mms_ctx* c, float iso) {
+    if (int rc = mms_count_isosurface(c, iso, nullptr)) return rc;
+    return mms_emit_isosurface(c, nullptr, nullptr, nullptr, 0);
 }
 
 int mms_get_mesh_device(mms_ctx* c, uint64_t* nverts, const float** pos, const float** nrm, const float** col) {
     if (!c || !nverts) return MMS_ERR_INVALID;
     if (!c->haveMesh) return c->fail(MMS_ERR_INVALID, "no isosurface has been extracted");
+    if (c->meshExternal) return c->fail(MMS_ERR_INVALID, "the mesh was emitted into caller-supplied memory");
     *nverts = c->ntris * 3;
     if (pos) *pos = c->ntris ? c->meshPos.as<float>() : nullptr;
     if (nrm) *nrm = c->ntris ? c->meshNrm.as<float>() : nullptr;
@@ -761,6 +793,7 @@ int mms_get_mesh_device(mms_ctx* c, uint64_t* nverts, const float** pos, const f
 int mms_get_mesh(mms_ctx* c, uint64_t* nverts, const float** pos, const float** nrm, const float** col) {
     if (!c || !nverts) return MMS_ERR_INVALID;
     if (!c->haveMesh) return c->fail(MMS_ERR_INVALID, "no isosurface has been extracted");
+    if (c->meshExternal) return c->fail(MMS_ERR_INVALID, "the mesh was emitted into caller-supplied memory");
     DeviceGuard guard(c->device);
     const size_t bytes = static_cast<size_t>(c->ntris) * 36;
     *nverts = c->ntris * 3;
@@ -861,6 +894,53 @@ int mms_timer_stop(mms_ctx* c, float* ms) {
 }
 
 uint64_t mms_launch_count(const mms_ctx* c) { return c ? c->launches : 0; }
+
+int mms_device_alloc(int32_t device, size_t bytes, void** ptr) {
+    if (!ptr) return MMS_ERR_INVALID;
+    DeviceGuard guard(device);
+    if (cudaMalloc(ptr, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        *ptr = nullptr;
+        return MMS_ERR_NOMEM;
+    }
+    return MMS_OK;
+}
+
+int mms_device_free(int32_t device, void* ptr) {
+    DeviceGuard guard(device);
+    return cudaFree(ptr) == cudaSuccess ? MMS_OK : MMS_ERR_CUDA;
+}
+
+int mms_ipc_export(int32_t device, const void* devptr, unsigned char handle[64]) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    if (!devptr || !handle) return MMS_ERR_INVALID;
+    DeviceGuard guard(device);
+    cudaIpcMemHandle_t h;
+    if (cudaIpcGetMemHandle(&h, const_cast<void*>(devptr)) != cudaSuccess) {
+        cudaGetLastError();
+        return MMS_ERR_CUDA;
+    }
+    std::memcpy(handle, &h, 64);
+    return MMS_OK;
+}
+
+int mms_ipc_open(int32_t device, const unsigned char handle[64], void** ptr) {
+    if (!handle || !ptr) return MMS_ERR_INVALID;
+    DeviceGuard guard(device);
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, 64);
+    if (cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError();
+        *ptr = nullptr;
+        return MMS_ERR_CUDA;
+    }
+    return MMS_OK;
+}
+
+int mms_ipc_close(int32_t device, void* ptr) {
+    DeviceGuard guard(device);
+    return cudaIpcCloseMemHandle(ptr) == cudaSuccess ? MMS_OK : MMS_ERR_CUDA;
+}
 
 void* mms_alloc_pinned(size_t bytes) {
     void* p = nullptr;

@@ -116,12 +116,15 @@ def gather_rows_to_root(local, rank, world, out=None):
 class SlabJob:
     """The bench/test driver: generates this rank's chunk of the synthetic frame and runs full steps."""
 
-    def __init__(self, w, rank, world, local, iso, radius, sigma=1.0, cyclic=(True, True, True), normalize=True):
+    def __init__(self, w, rank, world, local, iso, radius, sigma=1.0, cyclic=(True, True, True), normalize=True, gather="fused"):
         import torch
         import megamol_b200 as mm
         from megamol_b200 import synth
         self.torch = torch
         self.w, self.rank, self.world, self.iso, self.radius = w, rank, world, iso, radius
+        self.local = local
+        self.gather = gather          # "fused": emit straight into rank 0's buffers over NVLink (CUDA IPC); "nccl": emit locally, then send/recv
+        self._root = dict(gen=0, cap=0, pos=None, nrm=None)   # rank 0: owned buffers; others: IPC mappings
         self.dev = torch.device("cuda", local)
         self.normalize = normalize
         self.cyclic = cyclic
@@ -244,8 +247,71 @@ class SlabJob:
         self.last["tri_counts"] = [c // 3 for c in counts]
         self.last["gathered_verts"] = sum(counts)
 
+    # ---- fused emit + gather -------------------------------------------------------------------------------------
+    def _emit_to_root(self):
+        """Marching-cubes emission and mesh gather in ONE kernel: every rank's mc_emit_kernel writes its slab's triangles
+        at their final offset of rank 0's mesh buffers (CUDA-IPC mapping, stores travel over NVLink).  The only collectives
+        left are the all-gather of the triangle counts and a 144-byte broadcast of (generation, IPC handles)."""
+        import ctypes as C
+        torch = self.torch
+        import torch.distributed as dist
+        L = self.surf.L
+        T = self.surf.count_isosurface(self.iso)
+        cnt = torch.tensor([T], device=self.dev, dtype=torch.int64)
+        allc = [torch.empty_like(cnt) for _ in range(self.world)]
+        dist.all_gather(allc, cnt)
+        counts = [int(c.item()) for c in allc]
+        total, first = sum(counts), sum(counts[:self.rank])
+        R = self._root
+        msg = torch.zeros(144, dtype=torch.uint8, device=self.dev)
+        if self.rank == 0:
+            need = total * 36
+            if R["cap"] < need:
+                for k in ("pos", "nrm"):
+                    if R[k]:
+                        L.mms_device_free(self.local, R[k])
+                cap = need + need // 8 + 256
+                hb = bytearray(144)
+                for i, k in enumerate(("pos", "nrm")):
+                    p = C.c_void_p()
+                    if L.mms_device_alloc(self.local, cap, C.byref(p)):
+                        raise MemoryError(f"gather buffer of {cap} bytes")
+                    R[k] = p.value
+                    h = (C.c_ubyte * 64)()
+                    if L.mms_ipc_export(self.local, p, h):
+                        raise RuntimeError("cudaIpcGetMemHandle failed")
+                    hb[16 + 64 * i:16 + 64 * (i + 1)] = bytes(h)
+                R["cap"], R["gen"] = cap, R["gen"] + 1
+                hb[0:8] = int(R["gen"]).to_bytes(8, "little")
+                hb[8:16] = int(cap).to_bytes(8, "little")
+                R["msg"] = bytes(hb)
+            msg = torch.frombuffer(bytearray(R["msg"]), dtype=torch.uint8).to(self.dev)
+        dist.broadcast(msg, 0)
+        if self.rank != 0:
+            raw = bytes(msg.cpu().numpy())
+            gen = int.from_bytes(raw[0:8], "little")
+            if gen != R["gen"]:
+                for k in ("pos", "nrm"):
+                    if R[k]:
+                        L.mms_ipc_close(self.local, R[k])
+                for i, k in enumerate(("pos", "nrm")):
+                    h = (C.c_ubyte * 64).from_buffer_copy(raw[16 + 64 * i:16 + 64 * (i + 1)])
+                    p = C.c_void_p()
+                    if L.mms_ipc_open(self.local, h, C.byref(p)):
+                        raise RuntimeError("cudaIpcOpenMemHandle failed (is peer access available between the GPUs?)")
+                    R[k] = p.value
+                R["gen"], R["cap"] = gen, int.from_bytes(raw[8:16], "little")
+        self.surf.emit_isosurface(R["pos"], R["nrm"], None, first)
+        self.surf.synchronize()
+        dist.barrier()   # rank 0 may read the mesh once every rank's stores have landed
+        self.last["tri_counts"] = counts
+        self.last["gathered_verts"] = total * 3
+        if self.rank == 0:
+            self._gpos = _tensor_from_ptr(torch, R["pos"], total * 9, self.dev)
+            self._gnrm = _tensor_from_ptr(torch, R["nrm"], total * 9, self.dev)
+
     # ---- steps ------------------------------------------------------------------------------------------------
-    def _compute(self, xyz_ptr, n):
+    def _compute(self, xyz_ptr, n, extract=True):
         s = self.surf
         s.clear_particles()
         if self.protein:  # x y z r | R G B A interleaved, stride 32 (FLOAT_XYZR + FLOAT_RGBA)
@@ -261,7 +327,8 @@ class SlabJob:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             mn, mx = -float(t[0].item()), float(t[1].item())
             s.normalize(mn, mx)
-        s.extract_isosurface(self.iso)
+        if extract:
+            s.extract_isosurface(self.iso)
 
     def step_device(self):
         """inputs resident in HBM: (exchange) -> bin -> density -> (range all-reduce, normalise) -> MC -> (mesh gather)"""
@@ -276,10 +343,14 @@ class SlabJob:
             ev[1].record()
             torch.cuda.current_stream().synchronize()
             self._keep = [recv]
-            self._compute(recv.data_ptr(), recv.shape[0])
+            fused = self.gather == "fused"
+            self._compute(recv.data_ptr(), recv.shape[0], extract=not fused)
             self.surf.synchronize()
             ev[2].record()
-            self._gather_mesh()
+            if fused:
+                self._emit_to_root()
+            else:
+                self._gather_mesh()
             ev[3].record()
             torch.cuda.current_stream().synchronize()
             self.last["exchange_ms"] = ev[0].elapsed_time(ev[1])
@@ -299,9 +370,13 @@ class SlabJob:
             recv = self._exchange(d)
             torch.cuda.current_stream().synchronize()
             self._keep = [recv, d]
-            self._compute(recv.data_ptr(), recv.shape[0])
+            fused = self.gather == "fused"
+            self._compute(recv.data_ptr(), recv.shape[0], extract=not fused)
             self.surf.get_density(copy=False)
-            self._gather_mesh()
+            if fused:
+                self._emit_to_root()
+            else:
+                self._gather_mesh()
             if self.rank == 0:
                 tot = self.last["gathered_verts"] * 3
                 if getattr(self, "_hpos", None) is None or self._hpos.numel() < tot:
@@ -324,6 +399,8 @@ class SlabJob:
         return out
 
     def local_tris(self):
+        if self.world > 1 and self.gather == "fused":
+            return int(self.last.get("tri_counts", [0] * self.world)[self.rank])
         n, _, _ = self.surf.mesh_device()
         return n // 3
 
@@ -373,10 +450,21 @@ class SlabJob:
         return v * 4 + getattr(self, "_tris_total", 0) * 72
 
     def describe(self):
+        how = ("marching-cubes kernels write straight into rank 0's mesh over NVLink (CUDA IPC): emit + gather fused"
+               if self.gather == "fused" else "mesh gathered to rank 0 with NCCL send/recv")
         return (f"{self.w['name']} weak-scaled x{self.world} along z: {self.n_total} particles -> "
-                f"{self.res[0]}x{self.res[1]}x{self.res[2]}, z-slabs with halo, mesh gathered to rank 0 over NCCL")
+                f"{self.res[0]}x{self.res[1]}x{self.res[2]}, z-slabs with halo, particles exchanged with NCCL all-to-all-v, {how}")
 
     def close(self):
+        R = self._root
+        if self.world > 1:
+            self.torch.cuda.synchronize()
+            import torch.distributed as dist
+            dist.barrier()
+            for k in ("pos", "nrm"):
+                if R[k]:
+                    (self.surf.L.mms_device_free if self.rank == 0 else self.surf.L.mms_ipc_close)(self.local, R[k])
+                    R[k] = None
         self.surf.close()
         if self.world > 1:
             import torch.distributed as dist

@@ -170,3 +170,26 @@ def test_external_volume_isosurface(surf, oracle):
     d = pos.reshape(-1, 3) - c
     cosang = -(d * nrm.reshape(-1, 3)).sum(1) / np.linalg.norm(d, axis=1)
     assert cosang.min() > 0.97
+
+
+def test_emit_into_caller_buffers(surf, oracle):
+    """mms_count_isosurface + mms_emit_isosurface: the mesh lands at an offset of caller-owned device memory (the hook the
+    z-slab driver uses to let every rank write into rank 0's mesh, and the hook for GL-interop vertex buffers)."""
+    import torch
+    lists, bmin, bext = H.uniform_case(8000, 10.0, 0.8)
+    run_density(surf, lists, bmin, bext, (30, 30, 30), (False,) * 3)
+    n = surf.count_isosurface(0.4)
+    assert n > 500
+    off = 37
+    pos = torch.full(((n + off) * 9 + 5,), -7.0, device="cuda")
+    nrm = torch.full(((n + off) * 9 + 5,), -7.0, device="cuda")
+    surf.emit_isosurface(pos.data_ptr(), nrm.data_ptr(), None, off)
+    surf.synchronize()
+    with pytest.raises(Exception):
+        surf.get_mesh()                      # the mesh lives in caller memory
+    surf.extract_isosurface(0.4)
+    rpos, rnrm = surf.get_mesh()
+    p = pos.cpu().numpy()
+    assert (p[:off * 9] == -7.0).all() and (p[(n + off) * 9:] == -7.0).all()
+    assert np.array_equal(p[off * 9:(n + off) * 9].reshape(-1, 3, 3), rpos)
+    assert np.array_equal(nrm.cpu().numpy()[off * 9:(n + off) * 9].reshape(-1, 3, 3), rnrm)
