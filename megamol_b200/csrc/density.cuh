@@ -30,9 +30,10 @@ constexpr int CT_FLOATS = CT_SZ * CT_Z;
 constexpr int CT_WARPS = 8;
 constexpr int CT_THREADS = CT_WARPS * 32;
 constexpr int CT_MAXAXIS = 16;                       // cells per axis in a tile's neighbourhood (<= 32/4 + 3)
-constexpr int CT_MAXCELLS = 12 * 8 * 8;              // neighbourhood cells (C = 4: at most 11 x 7 x 7)
+constexpr int CT_MAXCELLS = 640;                     // neighbourhood cells (C = 4: at most 11 x 7 x 7 = 539)
 
-/** A digested particle (per-warp staging, read back with broadcast LDS.128). 16 words. */
+/** A digested particle (per-warp staging, read back with broadcast LDS.128). 12 words; the shared-memory budget
+ *  (tile 36.6 KB + 12 KB of these + tables) is trimmed to 56 KB so that FOUR blocks fit one SM. */
 struct Dig {
     float x, y, z, eps;
     float k0, weight, f0x, f0y; // k0: P2D 1/eps, QS w_p;  f0*: float(true un-wrapped index of the box's first voxel)
@@ -40,13 +41,13 @@ struct Dig {
     int base;                   // shared-memory offset of the box's first voxel
     unsigned dims;              // bx | by<<8 | bz<<16  (0 = nothing to do)
     unsigned mask27;            // fast path (all dims <= 3): valid lanes of the fixed 3x3x3 lane pattern
-    int l0x, l0y, l0z, pad;     // tile-local index of the box's first voxel (per-voxel-wrap mode: before wrapping)
 };
 
 struct SplatShared {
     float tile[CT_FLOATS];
     Dig dig[CT_WARPS][32];
-    unsigned cellB[CT_MAXCELLS], cellE[CT_MAXCELLS];
+    unsigned cellB[CT_MAXCELLS];
+    unsigned short cellN[CT_MAXCELLS]; // particles in the cell (a cell with more than 65535 particles is split by the host guard)
     int axisCells[3][CT_MAXAXIS];
     int axisCount[3];
     int colList[3][4][CT_MAXAXIS]; // per axis, per colour: positions in axisCells
@@ -132,7 +133,7 @@ __device__ __forceinline__ bool kernelValue(float d2, float eps, float k0, float
 }
 
 template<int MODE>
-__global__ void __launch_bounds__(CT_THREADS, 3) density_splat_kernel(Geo g, DevState* st, const float4* __restrict__ recs,
+__global__ void __launch_bounds__(CT_THREADS, 4) density_splat_kernel(Geo g, DevState* st, const float4* __restrict__ recs,
     const float* __restrict__ aux, int auxN, const unsigned* __restrict__ cellStart, float* __restrict__ vol, int reach) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     SplatShared& sh = *reinterpret_cast<SplatShared*>(smemRaw);
@@ -176,7 +177,8 @@ __global__ void __launch_bounds__(CT_THREADS, 3) density_splat_kernel(Geo g, Dev
         const size_t cell = cxg + static_cast<size_t>(g.nc[0]) * (cyg + static_cast<size_t>(g.nc[1]) * czg);
         const unsigned b = cellStart[cell], e = cellStart[cell + 1];
         sh.cellB[i] = b;
-        sh.cellE[i] = e;
+        sh.cellN[i] = static_cast<unsigned short>(min(e - b, 65535u));
+        if (e - b > 65535u) st->pad[0] = 3u; // a cell this crowded needs the (not yet written) split path
         if (e > b) {
             const bool irx = g.cyc[0] && ((g.nc[0] & 1) || (g.s[0] & (C - 1))), iry = g.cyc[1] && ((g.nc[1] & 1) || (g.s[1] & (C - 1))),
                        irz = g.cyc[2] && ((g.nc[2] & 1) || (g.s[2] & (C - 1)));
@@ -196,7 +198,7 @@ __global__ void __launch_bounds__(CT_THREADS, 3) density_splat_kernel(Geo g, Dev
     }
     __syncthreads();
     for (int i = tid; i < nneigh; i += CT_THREADS) {
-        if (sh.cellE[i] > sh.cellB[i]) {
+        if (sh.cellN[i] > 0) {
             const int kx = i % nax, ky = (i / nax) % nay, kz = i / (nax * nay);
             const int cxg = sh.axisCells[0][kx], cyg = sh.axisCells[1][ky], czg = sh.axisCells[2][kz];
             const bool irx = g.cyc[0] && ((g.nc[0] & 1) || (g.s[0] & (C - 1))), iry = g.cyc[1] && ((g.nc[1] & 1) || (g.s[1] & (C - 1))),
@@ -230,7 +232,7 @@ __global__ void __launch_bounds__(CT_THREADS, 3) density_splat_kernel(Geo g, Dev
             unsigned src = 0xffffffffu;
             while (filled < 32 && cur < pEnd) {
                 const int ci = sh.phaseCells[cur];
-                const unsigned b = sh.cellB[ci] + curOff, e = sh.cellE[ci];
+                const unsigned b = sh.cellB[ci] + curOff, e = sh.cellB[ci] + sh.cellN[ci];
                 const int take = min(32 - filled, (int)(e - b));
                 if (lane >= filled && lane < filled + take) src = b + (lane - filled);
                 filled += take;
@@ -239,6 +241,7 @@ __global__ void __launch_bounds__(CT_THREADS, 3) density_splat_kernel(Geo g, Dev
             }
             {
                 const int cnt = filled;
+                int myL0x = 0, myL0y = 0, myL0z = 0; // per-voxel-wrap mode only: tile-local box origin before wrapping
                 if (lane < cnt) {
                     // ---- digest my particle -------------------------------------------------------------------
                     const float4 p = recs[src];
@@ -297,7 +300,7 @@ __global__ void __launch_bounds__(CT_THREADS, 3) density_splat_kernel(Geo g, Dev
                     }
                     d.f0x = (float)tru[0], d.f0y = (float)tru[1], d.f0z = (float)tru[2];
                     d.base = l0[0] + l0[1] * CT_SY + l0[2] * CT_SZ;
-                    d.l0x = l0[0], d.l0y = l0[1], d.l0z = l0[2], d.pad = 0;
+                    myL0x = l0[0], myL0y = l0[1], myL0z = l0[2];
                     if (empty || bd[0] > 255 || bd[1] > 255 || bd[2] > 255) {
                         d.dims = 0u, d.mask27 = 0u;
                     } else {
@@ -337,7 +340,8 @@ __global__ void __launch_bounds__(CT_THREADS, 3) density_splat_kernel(Geo g, Dev
                         }
                     } else {
                         // ---- general path: any box, optional per-voxel wrap ------------------------------------------
-                        const int4 L0 = reinterpret_cast<const int4*>(&myDig[j])[3];
+                        int4 L0 = make_int4(0, 0, 0, 0);
+                        if (anyPv) L0 = make_int4(__shfl_sync(0xffffffffu, myL0x, j), __shfl_sync(0xffffffffu, myL0y, j), __shfl_sync(0xffffffffu, myL0z, j), 0);
                         const int bx = dims & 255, by = (dims >> 8) & 255, bz = dims >> 16;
                         const int bxy = bx * by, nvox = bxy * bz;
                         const float rbx = __frcp_rn((float)bx), rbxy = __frcp_rn((float)bxy);

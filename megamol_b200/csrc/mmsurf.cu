@@ -607,6 +607,8 @@ int mms_compute_density(mms_ctx* c) {
 static int checkDeviceError(mms_ctx* c) {
     MMS_CUDA(c, cudaStreamSynchronize(c->stream));
     const DevState* hs = c->hState.as<DevState>();
+    if (hs->pad[0] == 3)
+        return c->fail(MMS_ERR_UNSUPPORTED, "more than 65535 particles in one cell of the sort grid (extremely clustered input)");
     if (hs->pad[0] == 2)
         return c->fail(MMS_ERR_UNSUPPORTED, "wide kernel support on a periodic axis shorter than tile + 2*support is not implemented");
     if (hs->pad[0] != 0)
