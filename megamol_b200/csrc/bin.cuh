@@ -18,11 +18,16 @@ struct Binned {
     int cell;   // linear cell id, -1 = does not contribute to this slab
 };
 
+__device__ __forceinline__ int wrapIndex(int X, int s) { // floor-mod, without the integer division in the common case
+    return (static_cast<unsigned>(X) < static_cast<unsigned>(s)) ? X : floorMod(X, s);
+}
+
 __device__ __forceinline__ bool axisReaches(int X, int f, int lo, int hi, int s, bool cyc) {
     // does the support box [X-f, X+f] (periodic images if cyc) touch voxel range [lo, hi]?
     if (!cyc) return X + f >= lo && X - f <= hi;
+    if (lo == 0 && hi == s - 1) return true; // the whole periodic axis
     if (2 * f + 1 >= s) return true;
-    const int xw = floorMod(X, s);
+    const int xw = wrapIndex(X, s);
     const int a = xw - f, b = xw + f;
     return (b >= lo && a <= hi) || (b - s >= lo && a - s <= hi) || (b + s >= lo && a + s <= hi);
 }
@@ -38,7 +43,9 @@ __device__ __forceinline__ Binned binParticle(const Geo& g, const ListDev& l, un
     if (!(r > 0.0f) || !isfinite(r)) return q; // rad == 0 early-out (:523); r < 0 or NaN never contributes
     if (!isfinite(q.p.x) || !isfinite(q.p.y) || !isfinite(q.p.z)) return q;
     int fx, fy, fz;
-    if (g.mode == 0) {
+    if (l.vtype != 2) { // global radius: the host computed the filter sizes once with the same IEEE operations
+        fx = l.gf[0], fy = l.gf[1], fz = l.gf[2];
+    } else if (g.mode == 0) {
         fx = filterSize(r, g.sd[0]), fy = filterSize(r, g.sd[1]), fz = filterSize(r, g.sd[2]);
     } else {
         const float cut = g.gausslim * g.radscale * r;
@@ -47,9 +54,9 @@ __device__ __forceinline__ Binned binParticle(const Geo& g, const ListDev& l, un
     if (!axisReaches(q.X, fx, 0, g.s[0] - 1, g.s[0], g.cyc[0])) return q;
     if (!axisReaches(q.Y, fy, 0, g.s[1] - 1, g.s[1], g.cyc[1])) return q;
     if (!axisReaches(q.Z, fz, g.z0, g.z0 + g.nz - 1, g.s[2], g.cyc[2])) return q;
-    const int xw = g.cyc[0] ? floorMod(q.X, g.s[0]) : min(max(q.X, 0), g.s[0] - 1);
-    const int yw = g.cyc[1] ? floorMod(q.Y, g.s[1]) : min(max(q.Y, 0), g.s[1] - 1);
-    const int zw = g.cyc[2] ? floorMod(q.Z, g.s[2]) : min(max(q.Z, 0), g.s[2] - 1);
+    const int xw = g.cyc[0] ? wrapIndex(q.X, g.s[0]) : min(max(q.X, 0), g.s[0] - 1);
+    const int yw = g.cyc[1] ? wrapIndex(q.Y, g.s[1]) : min(max(q.Y, 0), g.s[1] - 1);
+    const int zw = g.cyc[2] ? wrapIndex(q.Z, g.s[2]) : min(max(q.Z, 0), g.s[2] - 1);
     q.cell = (xw >> g.cshift) + g.nc[0] * ((yw >> g.cshift) + g.nc[1] * (zw >> g.cshift));
     return q;
 }

@@ -38,6 +38,7 @@ struct ListDev {
     float irange[2];
     int valign; // 16: float4 loads ok, 4: scalar float loads ok, 1: bytewise
     int calign;
+    int gf[3];  // lists with a global radius: support half-width per axis (filter size / Gaussian cut-off), set per compute
 };
 
 /** Values produced on the device and consumed by later kernels without a host round trip. */

@@ -527,6 +527,13 @@ int mms_compute_density(mms_ctx* c) {
         c->reach = need;
     }
     const Geo g = makeGeo(c);
+    for (ListDev& l : c->lists) { // global-radius lists: (int)ceil(rad / sliceDist) once on the host, same fp32 operations (:573-575)
+        for (int a = 0; a < 3; ++a) {
+            volatile float rad = (g.mode == 0) ? l.grad : g.gausslim * g.radscale * l.grad;
+            volatile float q = rad / g.sd[a];
+            l.gf[a] = static_cast<int>(std::ceil(q)) + (g.mode == 0 ? 0 : 1);
+        }
+    }
     const size_t ncells = static_cast<size_t>(g.nc[0]) * g.nc[1] * g.nc[2];
     const size_t nvox = static_cast<size_t>(g.s[0]) * g.s[1] * g.nz;
     const bool colour = g.mode == 1 && c->params.colour != 0;
