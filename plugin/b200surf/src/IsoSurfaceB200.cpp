@@ -128,15 +128,15 @@ bool IsoSurfaceB200::buildMesh(VolumetricDataCall* cvd, float iso) {
         use = this->ctx;
     }
     uint64_t nverts = 0;
-    const float *pos = nullptr, *nrm = nullptr;
-    if (mms_extract_isosurface(use, iso) != MMS_OK || mms_get_mesh(use, &nverts, &pos, &nrm, nullptr) != MMS_OK) {
+    const float *pos = nullptr, *nrm = nullptr, *col = nullptr; // col stays NULL unless the volume carries colours (QuickSurf mode)
+    if (mms_extract_isosurface(use, iso) != MMS_OK || mms_get_mesh(use, &nverts, &pos, &nrm, &col) != MMS_OK) {
         Log::DefaultLog.WriteError("IsoSurfaceB200: %s", mms_last_error(use));
         return false;
     }
     this->mesh.SetMaterial(nullptr);
     // the reference's contract (IsoSurface.cpp:171-181): unindexed soup, float positions + normals, no colours, 0 "triangles"
     // (the Mesh setters are overloaded on NON-const pointers; a const float* would select the catch-all "no data" overload)
-    this->mesh.SetVertexData(static_cast<unsigned int>(nverts), const_cast<float*>(pos), const_cast<float*>(nrm), static_cast<float*>(nullptr),
+    this->mesh.SetVertexData(static_cast<unsigned int>(nverts), const_cast<float*>(pos), const_cast<float*>(nrm), const_cast<float*>(col),
         static_cast<float*>(nullptr), false);
     this->mesh.SetTriangleData(0, static_cast<unsigned int*>(nullptr), false);
     const std::chrono::duration<float, std::milli> ms = std::chrono::high_resolution_clock::now() - t0;

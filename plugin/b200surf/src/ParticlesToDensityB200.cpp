@@ -45,6 +45,10 @@ ParticlesToDensityB200::ParticlesToDensityB200()
         , sigmaSlot("sigma", "Sigma for Gauss in multiple of rad")
         , surfaceSlot("forSurfaceReconstruction", "Set true if this volume is used for surface reconstruction")
         , deviceSlot("device", "CUDA device ordinal the volume is computed on")
+        , modeSlot("mode", "Density semantics: ParticlesToDensity bump kernel or QuickSurf Gaussian")
+        , qsQualitySlot("quicksurf::quality", "Quality: 0 low .. 3 ultra (Gaussian cut-off 2.0/2.5/3.0/4.0 sigma)")
+        , qsRadScaleSlot("quicksurf::radiusScale", "Radius scale")
+        , qsColourSlot("quicksurf::colour", "Also build the density-weighted colour volume (coloured isosurface)")
         , outDataSlot("outData", "Provides a density volume for the particles")
         , outParticlesSlot("outParticles", "Provides the particles in grid form (vector aggregator only)")
         , outInfoSlot("outInfo", "Provides information about the grid (vector aggregator only)")
@@ -101,6 +105,18 @@ ParticlesToDensityB200::ParticlesToDensityB200()
     this->deviceSlot << new core::param::IntParam(0, 0);
     this->MakeSlotAvailable(&this->deviceSlot);
 
+    auto* mp = new core::param::EnumParam(0);
+    mp->SetTypePair(0, "ParticlesToDensity_Bump");
+    mp->SetTypePair(1, "QuickSurf_Gaussian");
+    this->modeSlot << mp;
+    this->MakeSlotAvailable(&this->modeSlot);
+    this->qsQualitySlot << new core::param::IntParam(2, 0, 3);
+    this->MakeSlotAvailable(&this->qsQualitySlot);
+    this->qsRadScaleSlot << new core::param::FloatParam(1.0f, 0.0f);
+    this->MakeSlotAvailable(&this->qsRadScaleSlot);
+    this->qsColourSlot << new core::param::BoolParam(false);
+    this->MakeSlotAvailable(&this->qsColourSlot);
+
     this->inDataSlot.SetCompatibleCall<geocalls::MultiParticleDataCallDescription>();
     this->MakeSlotAvailable(&this->inDataSlot);
 }
@@ -131,11 +147,13 @@ bool ParticlesToDensityB200::dummyCallback(core::Call&) {
 bool ParticlesToDensityB200::anythingDirty() const {
     return this->aggregatorSlot.IsDirty() || this->xResSlot.IsDirty() || this->yResSlot.IsDirty() || this->zResSlot.IsDirty() ||
            this->cyclXSlot.IsDirty() || this->cyclYSlot.IsDirty() || this->cyclZSlot.IsDirty() || this->normalizeSlot.IsDirty() ||
-           this->sigmaSlot.IsDirty() || this->deviceSlot.IsDirty();
+           this->sigmaSlot.IsDirty() || this->deviceSlot.IsDirty() || this->modeSlot.IsDirty() || this->qsQualitySlot.IsDirty() ||
+           this->qsRadScaleSlot.IsDirty() || this->qsColourSlot.IsDirty();
 }
 
 void ParticlesToDensityB200::resetDirty() {
-    for (auto* s : {&aggregatorSlot, &xResSlot, &yResSlot, &zResSlot, &cyclXSlot, &cyclYSlot, &cyclZSlot, &normalizeSlot, &sigmaSlot, &deviceSlot})
+    for (auto* s : {&aggregatorSlot, &xResSlot, &yResSlot, &zResSlot, &cyclXSlot, &cyclYSlot, &cyclZSlot, &normalizeSlot, &sigmaSlot, &deviceSlot, &modeSlot,
+             &qsQualitySlot, &qsRadScaleSlot, &qsColourSlot})
         s->ResetDirty();
 }
 
@@ -262,11 +280,16 @@ bool ParticlesToDensityB200::computeVolume(MultiParticleDataCall* in) {
     grid.cyclic[1] = this->cyclYSlot.Param<core::param::BoolParam>()->Value();
     grid.cyclic[2] = this->cyclZSlot.Param<core::param::BoolParam>()->Value();
     mms_params p{};
-    p.mode = MMS_MODE_P2D_BUMP;
+    p.mode = this->modeSlot.Param<core::param::EnumParam>()->Value() == 1 ? MMS_MODE_QS_GAUSS : MMS_MODE_P2D_BUMP;
     p.aggregator = this->aggregatorSlot.Param<core::param::EnumParam>()->Value();
-    p.normalize = this->normalizeSlot.Param<core::param::BoolParam>()->Value();
+    p.normalize = p.mode == MMS_MODE_P2D_BUMP && this->normalizeSlot.Param<core::param::BoolParam>()->Value();
     p.sigma = this->sigmaSlot.Param<core::param::FloatParam>()->Value();
-    p.radscale = 1.0f, p.gausslim = 3.0f;
+    static const float kGaussLim[4] = {2.0f, 2.5f, 3.0f, 4.0f}; // QuickSurf.cpp:580-587
+    p.radscale = this->qsRadScaleSlot.Param<core::param::FloatParam>()->Value();
+    p.gausslim = kGaussLim[this->qsQualitySlot.Param<core::param::IntParam>()->Value() & 3];
+    p.colour = p.mode == MMS_MODE_QS_GAUSS && this->qsColourSlot.Param<core::param::BoolParam>()->Value();
+    if (p.mode == MMS_MODE_QS_GAUSS)
+        grid.cyclic[0] = grid.cyclic[1] = grid.cyclic[2] = 0; // QuickSurf has no periodic images
 
     std::vector<mms_list> lists;
     size_t total = 0;
@@ -310,6 +333,7 @@ bool ParticlesToDensityB200::computeVolume(MultiParticleDataCall* in) {
     if (mms_get_density(this->ctx, &this->hostVolume, nullptr) != MMS_OK) // RAM contract of VolumetricDataCall::GetData()
         return fail("get_density");
     this->minDens = mm[0], this->maxDens = mm[1];
+    this->hasColour = p.colour != 0;
     Log::DefaultLog.WriteInfo("ParticlesToDensityB200: Captured density %f -> %f", this->minDens, this->maxDens);
     if (p.normalize) {
         this->minDens = 0.0f;

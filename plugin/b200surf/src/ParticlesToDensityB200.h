@@ -40,6 +40,10 @@ public:
     std::size_t VolumeHash() const {
         return this->datahash;
     }
+    /** true if the context also holds a density-weighted RGB volume (QuickSurf mode with colour). */
+    bool HasColour() const {
+        return this->hasColour;
+    }
 
 protected:
     bool create() override;
@@ -60,6 +64,8 @@ private:
     core::param::ParamSlot aggregatorSlot, xResSlot, yResSlot, zResSlot, cyclXSlot, cyclYSlot, cyclZSlot, normalizeSlot,
         sigmaSlot, surfaceSlot;
     core::param::ParamSlot deviceSlot; // extra: CUDA device ordinal
+    // extra: QuickSurf semantics as a kernel mode (names and defaults of protein_cuda::QuickSurf, QuickSurf.cpp:18-31,62-72)
+    core::param::ParamSlot modeSlot, qsQualitySlot, qsRadScaleSlot, qsColourSlot;
     core::CalleeSlot outDataSlot, outParticlesSlot, outInfoSlot;
     core::CallerSlot inDataSlot;
 
@@ -71,6 +77,7 @@ private:
     unsigned int time = 0;
     float minDens = 0.0f, maxDens = 0.0f;
     bool has_data = false;
+    bool hasColour = false;
     geocalls::VolumetricDataCall::Metadata metadata;
     double minValue = 0.0, maxValue = 0.0;
     float sliceDists[3] = {0, 0, 0};

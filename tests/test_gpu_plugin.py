@@ -114,3 +114,31 @@ def test_for_surface_reconstruction_bbox(ref, plug):
         outs.append(h.pull_volume(copy=False)[1])
     assert outs[0]["resolution"] == outs[1]["resolution"]
     assert np.allclose(outs[0]["origin"], outs[1]["origin"]) and np.allclose(outs[0]["slicedist"], outs[1]["slicedist"])
+
+
+def test_quicksurf_mode_through_the_modules(plug, oracle):
+    """The drop-in modules' extra `mode` parameter: QuickSurf-Gaussian density + colour volume -> coloured CallTriMeshData."""
+    n = 3000
+    data, _, _ = synth.protein_like(n, seed=3, nballs=5, extent=36.0)
+    data = np.ascontiguousarray(data)
+    lists = [dict(vtx=data, vtx_type=rb.VERT_FLOAT_XYZR, vtx_stride=32, count=n, col=data.ctypes.data + 16, col_type=rb.COL_FLOAT_RGBA,
+                  col_stride=32)]
+    res = (46, 46, 46)
+    feed(plug, lists, (0, 0, 0, 36, 36, 36), res, cyclic=(True,) * 3, normalize=True)
+    plug.set_param(0, "mode", 1)
+    plug.set_param(0, "quicksurf::quality", 1)
+    plug.set_param(0, "quicksurf::colour", 1)
+    try:
+        vol, meta = plug.pull_volume()
+        sd = np.array(meta["slicedist"], np.float32)
+        rvol, rrgb = oracle.density_gauss(lists, meta["origin"], sd, res, radscale=1.0, gausslim=2.5, colour=True)
+        assert (np.abs(vol - rvol) / np.maximum(rvol, 1e-5 * rvol.max())).max() < 2e-5
+        m = plug.pull_mesh(0.5, colours=True)
+        assert m["nverts"] > 1000 and m["col"] is not None
+        rpos, rnrm, rcol = oracle.mc_emit(vol, meta["origin"], sd, 0.5, rgb=rrgb)
+        assert m["nverts"] == 3 * rpos.shape[0]
+        assert np.abs(m["pos"].reshape(-1, 3, 3) - rpos).max() <= 1e-4 * float(sd.max())
+        assert np.abs(m["col"].reshape(-1, 3, 3) - rcol).max() < 2e-4
+    finally:
+        plug.set_param(0, "mode", 0)
+        plug.set_param(0, "quicksurf::colour", 0)
