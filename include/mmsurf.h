@@ -102,6 +102,7 @@ typedef struct mms_params {
 
 typedef struct mms_timings { /* milliseconds, CUDA events on the context's stream, last call of each stage */
     float h2d, bin, density, normalize, mc, d2h_volume, d2h_mesh;
+    float mc_emit; /* the emit kernel alone (part of mc) */
 } mms_timings;
 
 int mms_create(mms_ctx** out, const mms_config* cfg);

@@ -50,7 +50,7 @@ class MmsParams(C.Structure):
 
 
 class MmsTimings(C.Structure):
-    _fields_ = [(n, C.c_float) for n in ("h2d", "bin", "density", "normalize", "mc", "d2h_volume", "d2h_mesh")]
+    _fields_ = [(n, C.c_float) for n in ("h2d", "bin", "density", "normalize", "mc", "d2h_volume", "d2h_mesh", "mc_emit")]
 
 
 def lib_path() -> str:

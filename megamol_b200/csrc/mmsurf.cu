@@ -20,7 +20,7 @@
 
 using namespace mms;
 
-static_assert(sizeof(mms_list) == 56 && sizeof(mms_grid) == 48 && sizeof(mms_params) == 40 && sizeof(mms_timings) == 28,
+static_assert(sizeof(mms_list) == 56 && sizeof(mms_grid) == 48 && sizeof(mms_params) == 40 && sizeof(mms_timings) == 32,
     "C ABI struct layout changed: update include/mmsurf.h users (megamol_b200/api.py, plugin/b200surf)");
 
 namespace {
@@ -123,7 +123,7 @@ struct Arena {
     }
 };
 
-enum Ev { EV_H2D0, EV_H2D1, EV_BIN0, EV_BIN1, EV_DEN1, EV_NRM0, EV_NRM1, EV_MC0, EV_MC1, EV_DV0, EV_DV1, EV_DM0, EV_DM1, EV_T0, EV_T1, EV_COUNT };
+enum Ev { EV_H2D0, EV_H2D1, EV_BIN0, EV_BIN1, EV_DEN1, EV_NRM0, EV_NRM1, EV_MC0, EV_MC1, EV_DV0, EV_DV1, EV_DM0, EV_DM1, EV_T0, EV_T1, EV_EMIT0, EV_COUNT };
 
 } // namespace
 
@@ -768,6 +768,7 @@ int mms_emit_isosurface(mms_ctx* c, float* pos, float* nrm, float* col, uint64_t
             if (C) C += first_triangle * 9;
         }
         dim3 gridE(m.nsegx, (m.cy + EY - 1) / EY, (m.cnz + EM_STEPS * EZ - 1) / (EM_STEPS * EZ));
+        c->rec(EV_EMIT0);
         if (c->haveColour)
             mc_emit_kernel<true><<<gridE, MC_THREADS, sizeof(McEmitShared) + 16 + E_EDGES * sizeof(float4), st>>>(m, c->vol.as<float>(),
                 c->rgb.as<float>(), c->segOffset.as<unsigned>(), P, N, C);
@@ -883,6 +884,7 @@ int mms_get_timings(mms_ctx* c, mms_timings* t) {
     t->mc = el(EV_MC0, EV_MC1);
     t->d2h_volume = el(EV_DV0, EV_DV1);
     t->d2h_mesh = el(EV_DM0, EV_DM1);
+    t->mc_emit = el(EV_EMIT0, EV_MC1);
     return MMS_OK;
 }
 

@@ -429,16 +429,29 @@ class SlabJob:
         return (b["bin"] + b["density"] + b["mc"]) * self.world
 
     def roofline(self, stage, peak):
+        """Roofline of the dominant KERNEL: algorithmic bytes of one launch / its CUDA-event time (library stream)."""
         b = self._local_alg_bytes()
-        cand = {"bin (count+scan+scatter+order)": (stage["bin"], b["bin"]),
-                ("density_gather_kernel" if self.protein else "density_splat_kernel"): (stage["density"], b["density"]),
-                "marching cubes (count+scan+emit)": (stage["mc"], b["mc"])}
+        dens = "density_gather_kernel" if self.protein else "density_splat_kernel"
+        # mc_emit: reads the density once more, writes the mesh; mc_count reads the density once
+        emit_bytes = b["mc"]
+        cand = {dens: (stage["density"], b["density"]), "mc_emit_kernel": (stage.get("mc_emit", 0.0), emit_bytes)}
         name = max(cand, key=lambda k: cand[k][0])
         ms, by = cand[name]
         ach = by / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
-        return {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+        traffic = None
+        try:
+            import json, os
+            with open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "traffic.json")) as f:
+                t = json.load(f)
+            if self.w.get("kind") == "lj" and self.world == 1:
+                traffic = t["c2"].get(name)
+        except Exception:
+            pass
+        stages = {"bin (count+scan+scatter+order)": (stage["bin"], b["bin"]), dens: (stage["density"], b["density"]),
+                  "marching cubes (count+scan+emit)": (stage["mc"], b["mc"] + b["v"] * 4)}
+        return {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                 "algorithmic_bytes": by, "ms": ms,
-                "per_stage_frac": {k: (v[1] / (v[0] * 1e-3) / 1e9 / peak if v[0] > 0 else None) for k, v in cand.items()}}
+                "per_stage_frac": {k: (v[1] / (v[0] * 1e-3) / 1e9 / peak if v[0] > 0 else None) for k, v in stages.items()}}
 
     def h2d_bytes(self):
         return self.n_local * (32 if self.protein else 12) * self.world

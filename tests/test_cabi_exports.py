@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_header():
     from megamol_b200 import api
     assert ctypes.sizeof(api.MmsList) == 56 and ctypes.sizeof(api.MmsGrid) == 48
-    assert ctypes.sizeof(api.MmsParams) == 40 and ctypes.sizeof(api.MmsTimings) == 28
+    assert ctypes.sizeof(api.MmsParams) == 40 and ctypes.sizeof(api.MmsTimings) == 32
     assert api.MmsList.count.offset == 16 and api.MmsList.global_radius.offset == 40
 
 
