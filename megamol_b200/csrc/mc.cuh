@@ -42,7 +42,7 @@ struct McGeo {
 // count
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int MC_THREADS = 256;
-constexpr int MCC_ROWS = 16; // cell rows (y) per warp of the count kernel
+constexpr int MCC_ROWS = 8;  // cell rows (y) per warp of the count kernel (more rows = fewer redundant row loads but more registers)
 
 __device__ __forceinline__ int cubeIndexSmem(const float* f, int strideY, int strideZ, float iso) {
     // f points at corner 0; corners: (0,0,0) (1,0,0) (1,1,0) (0,1,0) (0,0,1) (1,0,1) (1,1,1) (0,1,1)
