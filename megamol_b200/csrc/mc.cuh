@@ -35,7 +35,6 @@ struct McGeo {
     float org[3], sd[3];
     float rinv[3][3];  // rinv[a][n] = 1/(n*sd[a]), n = 1, 2 (gradient: one-sided / central)
     float iso;
-    int debug;         // profiling experiments only (MMS_DEBUG_MC): 1 no stores, 2 skip phase C, 4 skip B2, 8 skip B1
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -58,10 +57,13 @@ __device__ __forceinline__ int cubeIndexSmem(const float* f, int strideY, int st
     return ci;
 }
 
+constexpr int MCC_LAYERS = 16; // cell layers (z) a warp marches through
+
 /**
- * Count kernel, register-rolling: a warp owns one 32-cell x-segment of one cell layer and walks MCC_ROWS rows in y.
- * Per row it loads two node rows (planes z and z+1, 128 contiguous bytes each) -- the previous row's "below iso" bits are
- * kept in registers, the x+1 neighbour comes from a shuffle -- so a cell costs two coalesced loads and ~25 instructions.
+ * Count kernel, register-rolling in z: a warp owns a strip of 32 cells (x) by MCC_ROWS rows (y) and marches through
+ * MCC_LAYERS cell layers.  Per layer it loads ONE new node plane of the strip (MCC_ROWS+1 rows of 128 contiguous bytes, node
+ * 32 of the segment by lane 0) and turns it into "below iso" bits; the bits of the previous plane stay in registers and the
+ * x+1 neighbour comes from a shuffle -- so every density value is loaded ~1.1 times and a cell costs ~20 instructions.
  * Per-cell lookups go to a shared copy of the count table (the constant cache would serialise per-lane indices).
  */
 __global__ void __launch_bounds__(MC_THREADS) mc_count_kernel(McGeo m, const float* __restrict__ vol, unsigned* __restrict__ segCount,
@@ -72,55 +74,53 @@ __global__ void __launch_bounds__(MC_THREADS) mc_count_kernel(McGeo m, const flo
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int xseg = blockIdx.x;
     const int yBeg = (blockIdx.y * (MC_THREADS / 32) + warp) * MCC_ROWS;
-    const int czi = m.cz0 + blockIdx.z; // global cell layer
-    if (yBeg >= m.cy || czi >= m.cz0 + m.cnz) return;
-    const int yEnd = min(yBeg + MCC_ROWS, m.cy);
+    const int czBeg = m.cz0 + blockIdx.z * MCC_LAYERS;
+    if (yBeg >= m.cy || czBeg >= m.cz0 + m.cnz) return;
+    const int yEnd = min(yBeg + MCC_ROWS, m.cy), czEnd = min(czBeg + MCC_LAYERS, m.cz0 + m.cnz);
     const int x = xseg * 32 + lane;
-    const int xa = min(x, m.sx - 1), xb = min(xseg * 32 + 32, m.sx - 1); // lane 31's right neighbour is node 32 of the segment
-    const int zl = czi - m.zPlane0;
-    const float* p0 = vol + static_cast<size_t>(m.sx) * m.sy * zl;
-    const float* p1 = p0 + static_cast<size_t>(m.sx) * m.sy;
-    // all loads of the strip first (2 x 17 independent 128-byte requests per warp in flight), then the arithmetic
-    unsigned bits[MCC_ROWS + 1];
-    {
-        float a[MCC_ROWS + 1], b[MCC_ROWS + 1];
+    const int xa = min(x, m.sx - 1), xb = min(xseg * 32 + 32, m.sx - 1);
+    const size_t plane = static_cast<size_t>(m.sx) * m.sy;
+    // bits of one node plane of the strip: bit0 = my node below iso, bit1 = node x+1 below iso
+    auto planeBits = [&](int zNode, unsigned (&out)[MCC_ROWS + 1]) {
+        const float* p = vol + plane * (zNode - m.zPlane0);
+        float v[MCC_ROWS + 1], e[MCC_ROWS + 1];
 #pragma unroll
         for (int r = 0; r <= MCC_ROWS; ++r) {
             const size_t o = static_cast<size_t>(m.sx) * min(yBeg + r, m.sy - 1);
-            a[r] = p0[o + (lane == 31 ? xb : xa)]; // placeholder for lane 31's neighbour, fixed below
-            b[r] = p1[o + (lane == 31 ? xb : xa)];
-        }
-        float a31[MCC_ROWS + 1], b31[MCC_ROWS + 1];
-#pragma unroll
-        for (int r = 0; r <= MCC_ROWS; ++r) { // lane 31's own node (x = 32*xseg + 31): loaded by every lane's slot? no: one extra request
-            const size_t o = static_cast<size_t>(m.sx) * min(yBeg + r, m.sy - 1);
-            a31[r] = p0[o + xa];
-            b31[r] = p1[o + xa];
+            v[r] = p[o + xa];
+            e[r] = lane == 0 ? p[o + xb] : 0.0f;
         }
 #pragma unroll
         for (int r = 0; r <= MCC_ROWS; ++r) {
-            // me: my own node; nb: node x+1 (lane 31: node 32 of the segment, loaded above into a/b)
-            const unsigned me = (a31[r] < m.iso ? 1u : 0u) | (b31[r] < m.iso ? 2u : 0u);
+            const unsigned me = v[r] < m.iso ? 1u : 0u;
             unsigned nb = __shfl_down_sync(0xffffffffu, me, 1);
-            if (lane == 31) nb = (a[r] < m.iso ? 1u : 0u) | (b[r] < m.iso ? 2u : 0u);
-            bits[r] = me | (nb << 2);
+            const unsigned last = __shfl_sync(0xffffffffu, e[r] < m.iso ? 1u : 0u, 0);
+            if (lane == 31) nb = last;
+            out[r] = me | (nb << 1);
         }
-    }
+    };
+    unsigned lo[MCC_ROWS + 1], hi[MCC_ROWS + 1];
+    planeBits(czBeg, lo);
+    for (int cz = czBeg; cz < czEnd; ++cz) {
+        planeBits(cz + 1, hi);
 #pragma unroll
-    for (int r = 0; r < MCC_ROWS; ++r) {
-        const int y = yBeg + r;
-        if (y >= yEnd) break;
-        const unsigned prev = bits[r], cur = bits[r + 1];
-        // corners: 0 (x,y,z) 1 (x+1,y,z) 2 (x+1,y+1,z) 3 (x,y+1,z) 4 (x,y,z+1) 5 (x+1,y,z+1) 6 (x+1,y+1,z+1) 7 (x,y+1,z+1)
-        const unsigned ci = (prev & 1u) | ((prev >> 2) & 1u) << 1 | ((cur >> 2) & 1u) << 2 | (cur & 1u) << 3 | ((prev >> 1) & 1u) << 4 |
-                            ((prev >> 3) & 1u) << 5 | ((cur >> 3) & 1u) << 6 | ((cur >> 1) & 1u) << 7;
-        unsigned n = 0;
-        if (x < m.cx) {
-            n = sCount[ci];
-            if (triCount) triCount[x + static_cast<size_t>(m.cx) * (y + static_cast<size_t>(m.cy) * (czi - m.cz0))] = static_cast<unsigned char>(n);
+        for (int r = 0; r < MCC_ROWS; ++r) {
+            const int y = yBeg + r;
+            if (y < yEnd) {
+                // corners: 0 (x,y,z) 1 (x+1,y,z) 2 (x+1,y+1,z) 3 (x,y+1,z) 4 (x,y,z+1) 5 (x+1,y,z+1) 6 (x+1,y+1,z+1) 7 (x,y+1,z+1)
+                const unsigned ci = (lo[r] & 1u) | (lo[r] & 2u) | ((lo[r + 1] >> 1) & 1u) << 2 | (lo[r + 1] & 1u) << 3 | (hi[r] & 1u) << 4 |
+                                    ((hi[r] >> 1) & 1u) << 5 | ((hi[r + 1] >> 1) & 1u) << 6 | (hi[r + 1] & 1u) << 7;
+                unsigned n = 0;
+                if (x < m.cx) {
+                    n = sCount[ci];
+                    if (triCount) triCount[x + static_cast<size_t>(m.cx) * (y + static_cast<size_t>(m.cy) * (cz - m.cz0))] = static_cast<unsigned char>(n);
+                }
+                const unsigned tot = __reduce_add_sync(0xffffffffu, n);
+                if (lane == 0) segCount[xseg + static_cast<size_t>(m.nsegx) * (y + static_cast<size_t>(m.cy) * (cz - m.cz0))] = tot;
+            }
         }
-        const unsigned tot = __reduce_add_sync(0xffffffffu, n);
-        if (lane == 0) segCount[xseg + static_cast<size_t>(m.nsegx) * (y + static_cast<size_t>(m.cy) * (czi - m.cz0))] = tot;
+#pragma unroll
+        for (int r = 0; r <= MCC_ROWS; ++r) lo[r] = hi[r];
     }
 }
 
@@ -345,7 +345,7 @@ __global__ void __launch_bounds__(MC_THREADS) mc_emit_kernel(McGeo m, const floa
         __syncthreads();
 
         // ---- C: triangles, one warp per 32-cell row ---------------------------------------------------------------------
-        for (int r = warp; r < EY * EZ && !(m.debug & 2); r += MC_THREADS / 32) {
+        for (int r = warp; r < EY * EZ; r += MC_THREADS / 32) {
             const int ly = r % EY, lz = r / EY;
             const int cxi = x0 + lane;
             const int row = (step * EZ + lz) * EY + ly;
@@ -400,7 +400,6 @@ __global__ void __launch_bounds__(MC_THREADS) mc_emit_kernel(McGeo m, const floa
                 const float pz = axis == 2 ? v.x : (dz ? tz1 : tz0);
                 float* op = outPos + gbase + static_cast<size_t>(j) * 3;
                 float* on = outNrm + gbase + static_cast<size_t>(j) * 3;
-                if ((m.debug & 1) && px != -12345.678f) continue;
                 op[0] = px, op[1] = py, op[2] = pz;
                 on[0] = v.y, on[1] = v.z, on[2] = v.w;
                 if (COLOUR) {

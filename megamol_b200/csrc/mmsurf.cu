@@ -720,7 +720,6 @@ int mms_count_isosurface(mms_ctx* c, float iso, uint64_t* ntris) {
         m.rinv[a][0] = 0.0f;
     }
     m.iso = iso;
-    m.debug = 0;
     c->mcGeo = m;
     c->ntris = 0;
     c->haveCount = true;
@@ -740,7 +739,7 @@ int mms_count_isosurface(mms_ctx* c, float iso, uint64_t* ntris) {
         tri = c->triCount.as<unsigned char>();
     }
     cudaStream_t st = c->stream;
-    dim3 grid(m.nsegx, (m.cy + (MC_THREADS / 32) * MCC_ROWS - 1) / ((MC_THREADS / 32) * MCC_ROWS), m.cnz);
+    dim3 grid(m.nsegx, (m.cy + (MC_THREADS / 32) * MCC_ROWS - 1) / ((MC_THREADS / 32) * MCC_ROWS), (m.cnz + MCC_LAYERS - 1) / MCC_LAYERS);
     mc_count_kernel<<<grid, MC_THREADS, 0, st>>>(m, c->vol.as<float>(), c->segCount.as<unsigned>(), tri);
     ++c->launches;
     DevState* ds = c->dstate.as<DevState>();
