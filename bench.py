@@ -284,7 +284,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--gather", default="fused", choices=["fused", "nccl"], help="multi-GPU mesh gather: fused peer-store emit or NCCL send/recv")
+    ap.add_argument("--gather", default="host", choices=["host", "fused", "nccl"],
+                    help="multi-GPU: where the per-slab meshes go: host (default; stay sharded in HBM, counts all-gathered, e2e copies each slab over its "
+                         "own PCIe link), fused (mc_emit stores into rank 0's mesh over NVLink), nccl (send/recv to rank 0)")
     ap.add_argument("--frames", type=int, default=12, help="frames of the C5 time series")
     ap.add_argument("--tmpdir", default="/tmp")
     args = ap.parse_args()

@@ -116,14 +116,20 @@ def gather_rows_to_root(local, rank, world, out=None):
 class SlabJob:
     """The bench/test driver: generates this rank's chunk of the synthetic frame and runs full steps."""
 
-    def __init__(self, w, rank, world, local, iso, radius, sigma=1.0, cyclic=(True, True, True), normalize=True, gather="fused"):
+    def __init__(self, w, rank, world, local, iso, radius, sigma=1.0, cyclic=(True, True, True), normalize=True, gather="host"):
         import torch
         import megamol_b200 as mm
         from megamol_b200 import synth
         self.torch = torch
         self.w, self.rank, self.world, self.iso, self.radius = w, rank, world, iso, radius
         self.local = local
-        self.gather = gather          # "fused": emit straight into rank 0's buffers over NVLink (CUDA IPC); "nccl": emit locally, then send/recv
+        # where the per-slab meshes end up:
+        #   "host"  (default) they stay in their slab's HBM; the triangle counts are all-gathered so that every rank knows its offset
+        #           in the frame's mesh, and (e2e) every rank copies its slab over ITS OWN PCIe link to that offset of the host mesh
+        #           -- CallTriMeshData is a host-memory contract, the mesh never has to sit on one GPU (SURVEY 8e)
+        #   "fused" every rank's mc_emit_kernel stores straight into rank 0's buffers over NVLink (CUDA IPC): emit + gather in one kernel
+        #   "nccl"  emit locally, then NCCL send/recv to rank 0 (the baseline the fused kernel is compared with)
+        self.gather = gather
         self._root = dict(gen=0, cap=0, pos=None, nrm=None)   # rank 0: owned buffers; others: IPC mappings
         self.dev = torch.device("cuda", local)
         self.normalize = normalize
@@ -247,6 +253,19 @@ class SlabJob:
         self.last["tri_counts"] = [c // 3 for c in counts]
         self.last["gathered_verts"] = sum(counts)
 
+    def _allgather_counts(self):
+        """mesh stays sharded: all-gather of the per-slab triangle counts -> every rank knows its offset in the frame's mesh"""
+        torch = self.torch
+        import torch.distributed as dist
+        nverts, _, _ = self.surf.mesh_device()
+        cnt = torch.tensor([nverts // 3], device=self.dev, dtype=torch.int64)
+        allc = [torch.empty_like(cnt) for _ in range(self.world)]
+        dist.all_gather(allc, cnt)
+        counts = [int(c.item()) for c in allc]
+        self.last["tri_counts"] = counts
+        self.last["tri_offset"] = sum(counts[:self.rank])
+        self.last["gathered_verts"] = 0
+
     # ---- fused emit + gather -------------------------------------------------------------------------------------
     def _emit_to_root(self):
         """Marching-cubes emission and mesh gather in ONE kernel: every rank's mc_emit_kernel writes its slab's triangles
@@ -349,8 +368,10 @@ class SlabJob:
             ev[2].record()
             if fused:
                 self._emit_to_root()
-            else:
+            elif self.gather == "nccl":
                 self._gather_mesh()
+            else:
+                self._allgather_counts()
             ev[3].record()
             torch.cuda.current_stream().synchronize()
             self.last["exchange_ms"] = ev[0].elapsed_time(ev[1])
@@ -375,15 +396,23 @@ class SlabJob:
             self.surf.get_density(copy=False)
             if fused:
                 self._emit_to_root()
-            else:
+            elif self.gather == "nccl":
                 self._gather_mesh()
-            if self.rank == 0:
+            else:
+                self._allgather_counts()
+                self.surf.get_mesh(copy=False)   # this rank's slab over this GPU's own PCIe link
+            if self.rank == 0 and self.gather != "host":
+                # D2H of the gathered mesh through a fixed 1 GiB pinned window (a consumer would map its own buffer; pinning
+                # 8 x 8.4 GB on the host just for the measurement is not reasonable): the PCIe time is what is measured
                 tot = self.last["gathered_verts"] * 3
-                if getattr(self, "_hpos", None) is None or self._hpos.numel() < tot:
-                    self._hpos = torch.empty((tot,), dtype=torch.float32, pin_memory=True)
-                    self._hnrm = torch.empty((tot,), dtype=torch.float32, pin_memory=True)
-                self._hpos[:tot].copy_(self._gpos.view(-1)[:tot], non_blocking=True)
-                self._hnrm[:tot].copy_(self._gnrm.view(-1)[:tot], non_blocking=True)
+                win = 256 * 1024 * 1024
+                if getattr(self, "_hwin", None) is None:
+                    self._hwin = torch.empty((win,), dtype=torch.float32, pin_memory=True)
+                for src in (self._gpos, self._gnrm):
+                    flat = src.view(-1)
+                    for o in range(0, tot, win):
+                        n = min(win, tot - o)
+                        self._hwin[:n].copy_(flat[o:o + n], non_blocking=True)
             torch.cuda.current_stream().synchronize()
 
     # ---- accounting -------------------------------------------------------------------------------------------
@@ -399,7 +428,7 @@ class SlabJob:
         return out
 
     def local_tris(self):
-        if self.world > 1 and self.gather == "fused":
+        if self.world > 1 and self.gather in ("fused",):
             return int(self.last.get("tri_counts", [0] * self.world)[self.rank])
         n, _, _ = self.surf.mesh_device()
         return n // 3
@@ -463,8 +492,10 @@ class SlabJob:
         return v * 4 + getattr(self, "_tris_total", 0) * 72
 
     def describe(self):
-        how = ("marching-cubes kernels write straight into rank 0's mesh over NVLink (CUDA IPC): emit + gather fused"
-               if self.gather == "fused" else "mesh gathered to rank 0 with NCCL send/recv")
+        how = {"fused": "marching-cubes kernels write straight into rank 0's mesh over NVLink (CUDA IPC): emit + gather fused",
+               "nccl": "mesh gathered to rank 0 with NCCL send/recv",
+               "host": "per-slab meshes stay in their GPU's HBM (counts all-gathered -> global offsets); e2e: every rank copies its slab "
+                       "over its own PCIe link"}[self.gather]
         return (f"{self.w['name']} weak-scaled x{self.world} along z: {self.n_total} particles -> "
                 f"{self.res[0]}x{self.res[1]}x{self.res[2]}, z-slabs with halo, particles exchanged with NCCL all-to-all-v, {how}")
 
