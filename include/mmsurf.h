@@ -161,6 +161,14 @@ int mms_synchronize(mms_ctx* ctx);
 /* Number of kernel launches issued by this context so far (for bench.py's gpu_launches). */
 uint64_t mms_launch_count(const mms_ctx* ctx);
 
+/* Multi-GPU exchange, sender side: stable partition of one DEVICE-resident FLOAT_XYZ/XYZR list by destination z-slab.  Slab i
+ * computes density planes [plane_lo[i], plane_hi[i]] (inclusive, halo planes included); a particle is copied to every slab its
+ * support box touches (the reference's home voxel +- filter size, periodic images in cyclic z).  send_buf (device) receives the
+ * raw records (list stride bytes each) grouped by slab, original order inside a group; counts[i] = records for slab i (host).
+ * Uses the grid and parameters of the context.  Synchronises once (the counts decide the all-to-all split sizes). */
+int mms_route_particles(mms_ctx* ctx, const mms_list* list, int32_t nslabs, const int32_t* plane_lo, const int32_t* plane_hi, void* send_buf,
+    uint64_t capacity_records, uint64_t* counts);
+
 /* Device buffers that can be shared between the per-GPU processes of one node (CUDA IPC over NVLink / PCIe P2P). */
 int mms_device_alloc(int32_t device, size_t bytes, void** ptr);
 int mms_device_free(int32_t device, void* ptr);

@@ -17,7 +17,7 @@ MODE_P2D_BUMP, MODE_QS_GAUSS = 0, 1
 EXPORTS = ["mms_create", "mms_destroy", "mms_last_error", "mms_set_grid", "mms_set_slab", "mms_set_params",
            "mms_clear_particles", "mms_push_particles", "mms_compute_density", "mms_get_density_range", "mms_normalize",
            "mms_get_density", "mms_get_density_device", "mms_set_density", "mms_extract_isosurface", "mms_count_isosurface", "mms_emit_isosurface", "mms_device_alloc",
-           "mms_device_free", "mms_ipc_export", "mms_ipc_open", "mms_ipc_close", "mms_get_mesh",
+           "mms_device_free", "mms_route_particles", "mms_ipc_export", "mms_ipc_open", "mms_ipc_close", "mms_get_mesh",
            "mms_get_mesh_device", "mms_get_home_voxels", "mms_get_cell_tricounts", "mms_get_timings", "mms_synchronize",
            "mms_timer_start", "mms_timer_stop", "mms_launch_count", "mms_alloc_pinned", "mms_free_pinned", "mms_version", "mms_mmpld_open", "mms_mmpld_close",
            "mms_mmpld_last_error", "mms_mmpld_info", "mms_mmpld_prefetch", "mms_mmpld_read_frame"]
@@ -89,6 +89,8 @@ def load_library():
     L.mms_extract_isosurface.argtypes = [vp, C.c_float]
     L.mms_count_isosurface.argtypes = [vp, C.c_float, C.POINTER(C.c_uint64)]
     L.mms_emit_isosurface.argtypes = [vp, vp, vp, vp, C.c_uint64]
+    L.mms_route_particles.argtypes = [vp, C.POINTER(MmsList), C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), vp, C.c_uint64,
+                                      C.POINTER(C.c_uint64)]
     L.mms_device_alloc.argtypes = [C.c_int32, C.c_size_t, C.POINTER(vp)]
     L.mms_device_free.argtypes = [C.c_int32, vp]
     L.mms_ipc_export.argtypes = [C.c_int32, vp, C.POINTER(C.c_ubyte)]
@@ -257,6 +259,17 @@ class Surf:
 
     def extract_isosurface(self, iso):
         self._chk(self.L.mms_extract_isosurface(self.h, float(iso)))
+
+    def route_particles(self, ptr, count, slabs, send_ptr, capacity, vtx_type=VERT_FLOAT_XYZ, stride=0, global_radius=0.5):
+        """Stable partition of a device-resident list by destination slab (mms_route_particles) -> per-slab record counts."""
+        l = MmsList()
+        l.vtx, l.count, l.vtx_type, l.vtx_stride, l.global_radius = int(ptr), int(count), vtx_type, stride, global_radius
+        n = len(slabs)
+        lo = (C.c_int32 * n)(*[s["z0"] for s in slabs])
+        hi = (C.c_int32 * n)(*[s["z0"] + s["nz"] - 1 for s in slabs])
+        cnt = (C.c_uint64 * n)()
+        self._chk(self.L.mms_route_particles(self.h, C.byref(l), n, lo, hi, int(send_ptr), int(capacity), cnt))
+        return [int(c) for c in cnt]
 
     def count_isosurface(self, iso) -> int:
         n = C.c_uint64()

@@ -17,6 +17,7 @@
 #include "bin.cuh"
 #include "density.cuh"
 #include "mc.cuh"
+#include "route.cuh"
 
 using namespace mms;
 
@@ -150,6 +151,8 @@ struct mms_ctx {
     McGeo mcGeo{};
     bool haveCount = false, meshExternal = false;
 
+    DevBuf routeCounts, routeOffsets, routeTile;
+    PinBuf hRoute;
     DevBuf cellCount, cellStart, cursor, tileSums, recsA, recsB, auxA, auxB, vol, rgb, segCount, segOffset, meshPos, meshNrm,
         meshCol, triCount, home, dstate;
     PinBuf hState, hVol, hRgb, hPos, hNrm, hCol, hHome, hTri;
@@ -352,9 +355,9 @@ int mms_destroy(mms_ctx* c) {
         DeviceGuard guard(c->device);
         mms_clear_particles(c);
         for (DevBuf* b : {&c->cellCount, &c->cellStart, &c->cursor, &c->tileSums, &c->recsA, &c->recsB, &c->auxA, &c->auxB, &c->vol,
-                 &c->rgb, &c->segCount, &c->segOffset, &c->meshPos, &c->meshNrm, &c->meshCol, &c->triCount, &c->home, &c->dstate})
+                 &c->rgb, &c->segCount, &c->segOffset, &c->meshPos, &c->meshNrm, &c->meshCol, &c->triCount, &c->home, &c->dstate, &c->routeCounts, &c->routeOffsets, &c->routeTile})
             b->release();
-        for (PinBuf* b : {&c->hState, &c->hVol, &c->hRgb, &c->hPos, &c->hNrm, &c->hCol, &c->hHome, &c->hTri}) b->release();
+        for (PinBuf* b : {&c->hState, &c->hVol, &c->hRgb, &c->hPos, &c->hNrm, &c->hCol, &c->hHome, &c->hTri, &c->hRoute}) b->release();
         cudaStreamSynchronize(c->stream);
         cudaStreamSynchronize(c->copyStream);
         for (auto& a : c->arena) {
@@ -892,6 +895,56 @@ int mms_get_timings(mms_ctx* c, mms_timings* t) {
     t->d2h_volume = el(EV_DV0, EV_DV1);
     t->d2h_mesh = el(EV_DM0, EV_DM1);
     t->mc_emit = el(EV_EMIT0, EV_MC1);
+    return MMS_OK;
+}
+
+int mms_route_particles(mms_ctx* c, const mms_list* list, int32_t nslabs, const int32_t* plane_lo, const int32_t* plane_hi, void* send_buf,
+    uint64_t capacity_records, uint64_t* counts) {
+    if (!c || !list || !plane_lo || !plane_hi || !counts || nslabs < 1) return MMS_ERR_INVALID;
+    if (!c->haveGrid) return c->fail(MMS_ERR_INVALID, "mms_set_grid has not been called");
+    if (nslabs > kMaxSlabs) return c->fail(MMS_ERR_UNSUPPORTED, "more than %d slabs", kMaxSlabs);
+    if (list->vtx_type != MMS_VERT_FLOAT_XYZ && list->vtx_type != MMS_VERT_FLOAT_XYZR)
+        return c->fail(MMS_ERR_UNSUPPORTED, "routing handles FLOAT_XYZ / FLOAT_XYZR lists");
+    DeviceGuard guard(c->device);
+    if (!isDevicePointer(list->vtx)) return c->fail(MMS_ERR_INVALID, "mms_route_particles needs a device-resident list");
+    ListDev d{};
+    d.vtx = static_cast<const char*>(list->vtx);
+    d.count = list->count;
+    d.vtype = list->vtx_type;
+    d.vstride = list->vtx_stride ? list->vtx_stride : kVertSize[list->vtx_type];
+    d.grad = list->global_radius;
+    d.valign = alignOf(d.vtx, d.vstride, list->vtx_type == MMS_VERT_FLOAT_XYZR ? 16 : 4);
+    if (d.valign < 4 || d.vstride % 4) return c->fail(MMS_ERR_UNSUPPORTED, "routing needs 4-byte aligned records");
+    const Geo g = makeGeo(c);
+    RouteGeo r{};
+    r.zmin = g.mn[2], r.sdz = g.sd[2], r.sz = g.s[2], r.cyc = g.cyc[2], r.nslabs = nslabs;
+    for (int i = 0; i < nslabs; ++i) r.lo[i] = plane_lo[i], r.hi[i] = plane_hi[i];
+    r.sigma = g.sigma, r.radscale = g.radscale, r.gausslim = g.gausslim, r.mode = g.mode;
+    for (int i = 0; i < nslabs; ++i) counts[i] = 0;
+    if (d.count == 0) return MMS_OK;
+    const unsigned nwarps = static_cast<unsigned>(std::min<unsigned long long>((d.count + 255) / 256, static_cast<unsigned long long>(c->smCount) * 64));
+    const unsigned long long chunk = ((d.count + nwarps - 1) / nwarps + 31) / 32 * 32;
+    const unsigned nent = nwarps * static_cast<unsigned>(nslabs);
+    const unsigned ntiles = (nent + kScanTile - 1) / kScanTile;
+    if (!c->routeCounts.ensure(nent * 4) || !c->routeOffsets.ensure((nent + 1) * 4) || !c->routeTile.ensure(std::max(ntiles, 1u) * 4) ||
+        !c->hRoute.ensure((nslabs + 1) * 4))
+        return c->fail(MMS_ERR_NOMEM, "allocation failed (routing tables)");
+    cudaStream_t st = c->stream;
+    const int blocks = static_cast<int>((static_cast<size_t>(nwarps) * 32 + 255) / 256);
+    route_count_kernel<<<blocks, 256, 0, st>>>(r, d, chunk, c->routeCounts.as<unsigned>(), nwarps);
+    ++c->launches;
+    exclusiveScan(c->routeCounts.as<unsigned>(), c->routeOffsets.as<unsigned>(), nullptr, c->routeTile.as<unsigned>(), nent, nullptr, st, c->launches);
+    // slab d starts at offsets[d * nwarps]; the grand total sits at offsets[nent]
+    unsigned* h = c->hRoute.as<unsigned>();
+    for (int i = 0; i <= nslabs; ++i)
+        MMS_CUDA(c, cudaMemcpyAsync(h + i, c->routeOffsets.as<unsigned>() + static_cast<size_t>(i) * nwarps, 4, cudaMemcpyDeviceToHost, st));
+    MMS_CUDA(c, cudaStreamSynchronize(st));
+    for (int i = 0; i < nslabs; ++i) counts[i] = h[i + 1] - h[i];
+    if (h[nslabs] > capacity_records)
+        return c->fail(MMS_ERR_NOMEM, "send buffer too small: %u records needed, %llu available", h[nslabs], static_cast<unsigned long long>(capacity_records));
+    route_scatter_kernel<<<blocks, 256, 0, st>>>(r, d, chunk, c->routeOffsets.as<unsigned>(), nwarps, static_cast<unsigned*>(send_buf), static_cast<int>(d.vstride / 4));
+    ++c->launches;
+    MMS_CUDA(c, cudaGetLastError());
     return MMS_OK;
 }
 

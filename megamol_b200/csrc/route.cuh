@@ -1,0 +1,96 @@
+// route.cuh -- stable partition of a device-resident particle list by destination z-slab (multi-GPU exchange).
+//
+// A particle goes to every slab its support box [Z-f, Z+f] touches (periodic images in cyclic mode); Z and f are the
+// reference's home voxel / filter size (ParticlesToDensity.cpp:567,575), computed with the same individually rounded fp32
+// operations as the binning kernels.  Each warp owns one contiguous chunk of the list:
+//   route_count_kernel    per (slab, warp) record counts
+//   (exclusive scan over the slab-major count matrix: scan.cuh)
+//   route_scatter_kernel  re-walks the chunk 32 particles at a time; a ballot per destination gives every record its
+//                         position -> the send buffer holds, per destination, the records in their original order
+// so that after the all-to-all-v (receivers concatenate in source-rank order) the global particle order is preserved.
+#pragma once
+#include "common.cuh"
+
+namespace mms {
+
+constexpr int kMaxSlabs = 16;
+
+struct RouteGeo {
+    float zmin, sdz;
+    int sz, cyc;
+    int nslabs;
+    int lo[kMaxSlabs], hi[kMaxSlabs]; // plane range [lo, hi] each slab computes (incl. its halo planes)
+    float sigma, radscale, gausslim;
+    int mode;
+};
+
+__device__ __forceinline__ unsigned routeMask(const RouteGeo& r, const ListDev& l, unsigned long long j) {
+    const float4 p = fetchParticle(l, j);
+    const int Z = homeVoxel(p.z, r.zmin, r.sdz);
+    int f;
+    if (r.mode == 0) f = filterSize(p.w, r.sdz);
+    else f = filterSize(r.gausslim * r.radscale * p.w, r.sdz) + 1;
+    unsigned m = 0;
+    if (!r.cyc) {
+        for (int d = 0; d < r.nslabs; ++d)
+            if (Z + f >= r.lo[d] && Z - f <= r.hi[d]) m |= 1u << d;
+    } else if (2 * f + 1 >= r.sz) {
+        m = (1u << r.nslabs) - 1u;
+    } else {
+        const int zw = (static_cast<unsigned>(Z) < static_cast<unsigned>(r.sz)) ? Z : floorMod(Z, r.sz);
+        const int a = zw - f, b = zw + f;
+        for (int d = 0; d < r.nslabs; ++d) {
+            const int lo = r.lo[d], hi = r.hi[d];
+            if ((b >= lo && a <= hi) || (b - r.sz >= lo && a - r.sz <= hi) || (b + r.sz >= lo && a + r.sz <= hi)) m |= 1u << d;
+        }
+    }
+    return m;
+}
+
+__global__ void __launch_bounds__(256) route_count_kernel(RouteGeo r, ListDev l, unsigned long long chunk, unsigned* __restrict__ counts,
+    unsigned nwarps) {
+    const unsigned w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= nwarps) return;
+    const unsigned long long beg = static_cast<unsigned long long>(w) * chunk, end = min(beg + chunk, l.count);
+    unsigned cnt[kMaxSlabs];
+#pragma unroll
+    for (int d = 0; d < kMaxSlabs; ++d) cnt[d] = 0;
+    for (unsigned long long j0 = beg; j0 < end; j0 += 32) {
+        const unsigned long long j = j0 + lane;
+        const unsigned m = j < end ? routeMask(r, l, j) : 0u;
+#pragma unroll
+        for (int d = 0; d < kMaxSlabs; ++d)
+            if (d < r.nslabs) cnt[d] += __popc(__ballot_sync(0xffffffffu, (m >> d) & 1u));
+    }
+    if (lane == 0)
+        for (int d = 0; d < r.nslabs; ++d) counts[static_cast<size_t>(d) * nwarps + w] = cnt[d];
+}
+
+/** recWords = record size in 4-byte words (the list's stride): records travel as they are (vertex + interleaved colour). */
+__global__ void __launch_bounds__(256) route_scatter_kernel(RouteGeo r, ListDev l, unsigned long long chunk, const unsigned* __restrict__ offsets,
+    unsigned nwarps, unsigned* __restrict__ out, int recWords) {
+    const unsigned w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= nwarps) return;
+    const unsigned long long beg = static_cast<unsigned long long>(w) * chunk, end = min(beg + chunk, l.count);
+    unsigned base[kMaxSlabs];
+#pragma unroll
+    for (int d = 0; d < kMaxSlabs; ++d) base[d] = d < r.nslabs ? offsets[static_cast<size_t>(d) * nwarps + w] : 0u;
+    const unsigned lt = (1u << lane) - 1u;
+    for (unsigned long long j0 = beg; j0 < end; j0 += 32) {
+        const unsigned long long j = j0 + lane;
+        const unsigned m = j < end ? routeMask(r, l, j) : 0u;
+        const unsigned* src = reinterpret_cast<const unsigned*>(l.vtx + j * l.vstride);
+#pragma unroll
+        for (int d = 0; d < kMaxSlabs; ++d) {
+            if (d >= r.nslabs) break;
+            const unsigned b = __ballot_sync(0xffffffffu, (m >> d) & 1u);
+            if ((m >> d) & 1u) {
+                unsigned* dst = out + static_cast<size_t>(base[d] + __popc(b & lt)) * recWords;
+                for (int k = 0; k < recWords; ++k) dst[k] = src[k];
+            }
+            base[d] += __popc(b);
+        }
+    }
+}
+
+} // namespace mms

@@ -236,8 +236,23 @@ class SlabJob:
         return ms
 
     def _exchange(self, xyz_dev):
-        """all-to-all-v of the particles by destination slab; returns this rank's [n,3] tensor (source-rank order)."""
-        return route_and_exchange(xyz_dev, self.radius, self.slabs, self.res[2], 0.0, self.sdz, bool(self.cyclic[2]))
+        """all-to-all-v of the particles by destination slab; returns this rank's [n,3] tensor (source-rank order).
+        The stable partition by destination is libmmsurf's routing kernel (mms_route_particles); torch only carries the bytes."""
+        torch = self.torch
+        import torch.distributed as dist
+        n = xyz_dev.shape[0]
+        cap = n + n // 2 + 4096
+        if getattr(self, "_send", None) is None or self._send.shape[0] < cap:
+            self._send = torch.empty((cap, xyz_dev.shape[1]), device=self.dev, dtype=torch.float32)
+        sc = self.surf.route_particles(xyz_dev.data_ptr(), n, self.slabs, self._send.data_ptr(), cap, global_radius=self.radius)
+        self.surf.synchronize()  # the scatter kernel ran on the library's stream
+        send_counts = torch.tensor(sc, device=self.dev, dtype=torch.int64)
+        recv_counts = torch.empty_like(send_counts)
+        dist.all_to_all_single(recv_counts, send_counts)
+        rc = recv_counts.tolist()
+        recv = torch.empty((sum(rc), xyz_dev.shape[1]), device=self.dev, dtype=torch.float32)
+        dist.all_to_all_single(recv, self._send[:sum(sc)], output_split_sizes=rc, input_split_sizes=sc)
+        return recv
 
     def _gather_mesh(self):
         """all-gather of triangle counts, then the per-slab vertex/normal arrays travel to rank 0 over NCCL."""
