@@ -403,6 +403,7 @@ class SlabJob:
             self.surf.get_mesh(copy=False, colours=self.protein)
         else:
             d = self.h_xyz.to(self.dev, non_blocking=True)
+            torch.cuda.current_stream().synchronize()  # the routing kernel runs on the library's stream
             recv = self._exchange(d)
             torch.cuda.current_stream().synchronize()
             self._keep = [recv, d]
