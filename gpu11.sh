@@ -1,1 +1,1 @@
-python -m pytest tests/test_gpu_plugin.py -m gpu -x -q 2>&1 | tail -12
+python -m pytest tests -m gpu -x -q 2>&1 | tail -4

@@ -235,13 +235,18 @@ __global__ void __launch_bounds__(MC_THREADS) mc_emit_kernel(McGeo m, const floa
         const int zc0 = zcBeg + step * EZ; // global cell layer = global node plane of the step's lowest cells
         if (zc0 >= zcEnd) break;
         if (!sh.stepActive[step]) continue;
-        // planes zc0-1 .. zc0+3 must be in the ring
-        for (int z = max(loadedUpTo + 1, zc0 - 1); z <= zc0 + EZ + 1; ++z) loadPlane(z);
-        loadedUpTo = zc0 + EZ + 1;
-        asm volatile("cp.async.commit_group;");
+        // planes zc0-1 .. zc0+3 must be in the ring.  In the dense case the previous step prefetched them and nothing is issued
+        // here; otherwise the ring slots about to be overwritten may still be read by warps finishing the previous step.
+        if (loadedUpTo < zc0 + EZ + 1) {
+            __syncthreads();
+            for (int z = max(loadedUpTo + 1, zc0 - 1); z <= zc0 + EZ + 1; ++z) loadPlane(z);
+            loadedUpTo = zc0 + EZ + 1;
+            asm volatile("cp.async.commit_group;");
+        }
         asm volatile("cp.async.wait_group 0;");
         if (threadIdx.x == 0) sh.ncross = 0;
-        __syncthreads();
+        __syncthreads(); // (a) the planes have landed for everybody, (b) every warp has left the previous step: edge[], crossList and
+                         //     the ring slots the prefetch below overwrites are free
         // prefetch the two planes the next step adds (if that step is active) while this one computes
         const bool nextActive = step + 1 < EM_STEPS && sh.stepActive[step + 1] && zc0 + EZ < zcEnd;
         if (nextActive) {
@@ -410,7 +415,6 @@ __global__ void __launch_bounds__(MC_THREADS) mc_emit_kernel(McGeo m, const floa
             }
             __syncwarp();
         }
-        __syncthreads(); // the next step overwrites edge[] / crossList and the ring slots this step no longer needs
     }
     asm volatile("cp.async.wait_group 0;");
 }
