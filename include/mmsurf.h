@@ -129,6 +129,14 @@ int mms_compute_density(mms_ctx* ctx);
 int mms_get_density_range(mms_ctx* ctx, float minmax[2]);
 /* v = (v - mn) * (1/(mx - mn)) on the device volume (ParticlesToDensity.cpp:676-682). */
 int mms_normalize(mms_ctx* ctx, float mn, float mx);
+/* The same without a host round trip (z-slab sharding): the range as two device floats {-min, max} (so that ONE max-all-reduce
+ * over the ranks yields the global range in place), and a normalise that reads it from device memory. */
+int mms_density_range_device(mms_ctx* ctx, float** dev_negmin_max);
+int mms_normalize_device(mms_ctx* ctx, const float* dev_negmin_max);
+/* Run all kernels of this context on the caller's CUDA stream (cudaStream_t; NULL = back to the context's own stream), e.g. the
+ * stream the caller's collectives are ordered on.  The default stream is named by cudaStreamLegacy ((cudaStream_t)0x1) or
+ * cudaStreamPerThread ((cudaStream_t)0x2), never by NULL. */
+int mms_set_stream(mms_ctx* ctx, void* cuda_stream);
 /* Host copy (library-owned pinned memory) of the slab: nz*res[1]*res[0] floats, x fastest. rgb may be NULL. */
 int mms_get_density(mms_ctx* ctx, const float** host_volume, const float** host_rgb);
 int mms_get_density_device(mms_ctx* ctx, const float** dev_volume, const float** dev_rgb);

@@ -15,7 +15,7 @@ VERT_NONE, VERT_FLOAT_XYZ, VERT_FLOAT_XYZR, VERT_SHORT_XYZ, VERT_DOUBLE_XYZ = ra
 MODE_P2D_BUMP, MODE_QS_GAUSS = 0, 1
 
 EXPORTS = ["mms_create", "mms_destroy", "mms_last_error", "mms_set_grid", "mms_set_slab", "mms_set_params",
-           "mms_clear_particles", "mms_push_particles", "mms_compute_density", "mms_get_density_range", "mms_normalize",
+           "mms_clear_particles", "mms_push_particles", "mms_compute_density", "mms_get_density_range", "mms_normalize", "mms_density_range_device", "mms_normalize_device", "mms_set_stream",
            "mms_get_density", "mms_get_density_device", "mms_set_density", "mms_extract_isosurface", "mms_count_isosurface", "mms_emit_isosurface", "mms_device_alloc",
            "mms_device_free", "mms_route_particles", "mms_ipc_export", "mms_ipc_open", "mms_ipc_close", "mms_get_mesh",
            "mms_get_mesh_device", "mms_get_home_voxels", "mms_get_cell_tricounts", "mms_get_timings", "mms_synchronize",
@@ -83,6 +83,9 @@ def load_library():
     L.mms_compute_density.argtypes = [vp]
     L.mms_get_density_range.argtypes = [vp, C.POINTER(C.c_float)]
     L.mms_normalize.argtypes = [vp, C.c_float, C.c_float]
+    L.mms_density_range_device.argtypes = [vp, C.POINTER(vp)]
+    L.mms_normalize_device.argtypes = [vp, vp]
+    L.mms_set_stream.argtypes = [vp, vp]
     L.mms_get_density.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
     L.mms_get_density_device.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
     L.mms_set_density.argtypes = [vp, vp]
@@ -227,6 +230,22 @@ class Surf:
         mm = (C.c_float * 2)()
         self._chk(self.L.mms_get_density_range(self.h, mm))
         return float(mm[0]), float(mm[1])
+
+    def density_range_device(self) -> int:
+        p = C.c_void_p()
+        self._chk(self.L.mms_density_range_device(self.h, C.byref(p)))
+        return p.value
+
+    def normalize_device(self, ptr):
+        self._chk(self.L.mms_normalize_device(self.h, int(ptr)))
+
+    def set_stream(self, cuda_stream):
+        """cuda_stream: a cudaStream_t handle as int; 0 (torch's default stream) is passed as cudaStreamLegacy (0x1) because NULL
+        means 'back to the context's own stream' in the C ABI; None restores the context's own stream."""
+        if cuda_stream is None:
+            self._chk(self.L.mms_set_stream(self.h, None))
+        else:
+            self._chk(self.L.mms_set_stream(self.h, int(cuda_stream) or 1))
 
     def normalize(self, mn, mx):
         self._chk(self.L.mms_normalize(self.h, float(mn), float(mx)))

@@ -149,6 +149,8 @@ struct mms_ctx {
     int cshift = 2, reach = 2;
     bool useGather = false, haveColour = false;
     McGeo mcGeo{};
+    cudaStream_t ownStream = nullptr;
+    DevBuf rangeBuf; // {-min, max} as floats for device-side all-reduce + normalise
     bool haveCount = false, meshExternal = false;
 
     DevBuf routeCounts, routeOffsets, routeTile;
@@ -255,6 +257,27 @@ __global__ void init_state_kernel(DevState* st) {
     st->pad[1] = 0u;
 }
 
+__global__ void range_to_float_kernel(const DevState* __restrict__ st, float* __restrict__ out) {
+    out[0] = -keyFloat(st->minKey);
+    out[1] = keyFloat(st->maxKey);
+}
+
+__global__ void __launch_bounds__(256) normalize_ptr_kernel(float* __restrict__ vol, size_t n, const float* __restrict__ negminMax) {
+    const float mn = -negminMax[0], mx = negminMax[1];
+    const float rcp = __fdiv_rn(1.0f, __fsub_rn(mx, mn));
+    const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+    const size_t n4 = n / 4;
+    float4* v4 = reinterpret_cast<float4*>(vol);
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        float4 v = v4[i];
+        v.x = __fmul_rn(__fsub_rn(v.x, mn), rcp), v.y = __fmul_rn(__fsub_rn(v.y, mn), rcp);
+        v.z = __fmul_rn(__fsub_rn(v.z, mn), rcp), v.w = __fmul_rn(__fsub_rn(v.w, mn), rcp);
+        v4[i] = v;
+    }
+    for (size_t i = n4 * 4 + static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+        vol[i] = __fmul_rn(__fsub_rn(vol[i], mn), rcp);
+}
+
 __global__ void __launch_bounds__(256) normalize_state_kernel(float* __restrict__ vol, size_t n, const DevState* __restrict__ st) {
     const float mn = keyFloat(st->minKey), mx = keyFloat(st->maxKey);
     const float rcp = __fdiv_rn(1.0f, __fsub_rn(mx, mn)); // 1.0f / (maxDens - minDens) (:677)
@@ -355,7 +378,7 @@ int mms_destroy(mms_ctx* c) {
         DeviceGuard guard(c->device);
         mms_clear_particles(c);
         for (DevBuf* b : {&c->cellCount, &c->cellStart, &c->cursor, &c->tileSums, &c->recsA, &c->recsB, &c->auxA, &c->auxB, &c->vol,
-                 &c->rgb, &c->segCount, &c->segOffset, &c->meshPos, &c->meshNrm, &c->meshCol, &c->triCount, &c->home, &c->dstate, &c->routeCounts, &c->routeOffsets, &c->routeTile})
+                 &c->rgb, &c->segCount, &c->segOffset, &c->meshPos, &c->meshNrm, &c->meshCol, &c->triCount, &c->home, &c->dstate, &c->routeCounts, &c->routeOffsets, &c->routeTile, &c->rangeBuf})
             b->release();
         for (PinBuf* b : {&c->hState, &c->hVol, &c->hRgb, &c->hPos, &c->hNrm, &c->hCol, &c->hHome, &c->hTri, &c->hRoute}) b->release();
         cudaStreamSynchronize(c->stream);
@@ -367,7 +390,7 @@ int mms_destroy(mms_ctx* c) {
         cudaEventDestroy(c->uploadDone);
         cudaStreamDestroy(c->copyStream);
         for (auto& ev : c->ev) cudaEventDestroy(ev);
-        cudaStreamDestroy(c->stream);
+        cudaStreamDestroy(c->ownStream ? c->ownStream : c->stream);
     }
     delete c;
     return MMS_OK;
@@ -654,6 +677,41 @@ int mms_normalize(mms_ctx* c, float mn, float mx) {
     volatile float rcp = 1.0f / range;
     c->rec(EV_NRM0);
     normalize_kernel<<<c->smCount * 8, 256, 0, c->stream>>>(c->vol.as<float>(), nvox, mn, rcp);
+    ++c->launches;
+    c->rec(EV_NRM1);
+    MMS_CUDA(c, cudaGetLastError());
+    c->normalized = true;
+    c->haveMesh = false;
+    return MMS_OK;
+}
+
+int mms_set_stream(mms_ctx* c, void* stream) {
+    if (!c) return MMS_ERR_INVALID;
+    DeviceGuard guard(c->device);
+    cudaStreamSynchronize(c->stream);
+    if (!c->ownStream) c->ownStream = c->stream;
+    c->stream = stream ? static_cast<cudaStream_t>(stream) : c->ownStream;
+    return MMS_OK;
+}
+
+int mms_density_range_device(mms_ctx* c, float** dev_negmin_max) {
+    if (!c || !dev_negmin_max) return MMS_ERR_INVALID;
+    if (!c->haveDensity) return c->fail(MMS_ERR_INVALID, "no density has been computed");
+    DeviceGuard guard(c->device);
+    if (!c->rangeBuf.ensure(16)) return c->fail(MMS_ERR_NOMEM, "allocation failed");
+    range_to_float_kernel<<<1, 1, 0, c->stream>>>(c->dstate.as<DevState>(), c->rangeBuf.as<float>());
+    ++c->launches;
+    *dev_negmin_max = c->rangeBuf.as<float>();
+    return MMS_OK;
+}
+
+int mms_normalize_device(mms_ctx* c, const float* dev_negmin_max) {
+    if (!c || !dev_negmin_max) return MMS_ERR_INVALID;
+    if (!c->haveDensity) return c->fail(MMS_ERR_INVALID, "no density has been computed");
+    DeviceGuard guard(c->device);
+    const size_t nvox = static_cast<size_t>(c->grid.res[0]) * c->grid.res[1] * c->nz;
+    c->rec(EV_NRM0);
+    normalize_ptr_kernel<<<c->smCount * 16, 256, 0, c->stream>>>(c->vol.as<float>(), nvox, dev_negmin_max);
     ++c->launches;
     c->rec(EV_NRM1);
     MMS_CUDA(c, cudaGetLastError());

@@ -177,6 +177,8 @@ class SlabJob:
         self.slabs = plan_slabs(self.res[2], world)
         self.me = self.slabs[rank]
         self.surf = mm.Surf(local)
+        if world > 1:  # one stream for the library's kernels and torch's collectives: ordering without host synchronisation
+            self.surf.set_stream(torch.cuda.current_stream().cuda_stream)
         if self.protein:
             self.cyclic = cyclic = (False, False, False)
             self.normalize = False
@@ -354,13 +356,12 @@ class SlabJob:
             s.push_particles([dict(vtx=xyz_ptr, vtx_type=1, count=n, global_radius=self.radius)])
         s.compute_density()
         if self.world > 1 and self.normalize:
+            # global range with ONE max-all-reduce of {-min, max}, in place on the library's device buffer: no host round trip
             import torch.distributed as dist
-            torch = self.torch
-            mn, mx = s.density_range()
-            t = torch.tensor([-mn, mx], device=self.dev, dtype=torch.float32)
+            ptr = s.density_range_device()
+            t = _tensor_from_ptr(self.torch, ptr, 2, self.dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            mn, mx = -float(t[0].item()), float(t[1].item())
-            s.normalize(mn, mx)
+            s.normalize_device(ptr)
         if extract:
             s.extract_isosurface(self.iso)
 
@@ -515,7 +516,7 @@ class SlabJob:
         return (f"{self.w['name']} weak-scaled x{self.world} along z: {self.n_total} particles -> "
                 f"{self.res[0]}x{self.res[1]}x{self.res[2]}, z-slabs with halo, particles exchanged with NCCL all-to-all-v, {how}")
 
-    def close(self):
+    def close(self, destroy_group=True):
         R = self._root
         if self.world > 1:
             self.torch.cuda.synchronize()
@@ -526,10 +527,13 @@ class SlabJob:
                     (self.surf.L.mms_device_free if self.rank == 0 else self.surf.L.mms_ipc_close)(self.local, R[k])
                     R[k] = None
         self.surf.close()
-        if self.world > 1:
+        if self.world > 1 and destroy_group:
             import torch.distributed as dist
             dist.barrier()
             dist.destroy_process_group()
+
+    def close_keep_group(self):
+        self.close(destroy_group=False)
 
 
 def _tensor_from_ptr(torch, ptr, nfloats, device):

@@ -1,0 +1,20 @@
+"""GPU suite, needs >= 2 GPUs (skipped on a single-GPU box): real NCCL run of the z-slab driver against the single-GPU result."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_two_rank_pipeline_bit_identical():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29577", os.path.join(here, "multi_gpu_check.py")], capture_output=True, text=True, timeout=600)
+    out = r.stdout + r.stderr
+    assert r.returncode == 0, out[-3000:]
+    assert out.count("-> OK") == 3, out[-3000:]
