@@ -1,28 +1,50 @@
 // mc.cuh -- marching cubes on the device-resident density slab.
 //
-//   mc_count_kernel   classify every cell (cube index bit i <=> corner i < iso, corner order and case table of
-//                     trisoup::volumetrics::MarchingCubeTables, MarchingCubeTables.cpp:11-16,58,278) and sum the
-//                     triangle counts of each 32-cell x-segment with a warp reduction
+//   mc_count_kernel   "below iso" BIT MASKS: a warp turns a row of 32 nodes into one 32-bit word (coalesced 128-byte load,
+//                     compare, ballot).  A thread then owns a whole 32-cell x-segment: the cells that produce triangles are
+//                     found with a dozen bitwise operations on the 8 words of the segment's four node rows, and only those
+//                     cells look up their triangle count (case table of trisoup::volumetrics::MarchingCubeTables,
+//                     MarchingCubeTables.cpp:11-16,58,278; cube index bit i <=> corner i < iso).
 //   (exclusive scan of the segment counts: scan.cuh -> triangle offsets in CELL-LINEAR order)
-//   mc_emit_kernel    active tiles only (32x8x2 cells):
-//                       A  stage density + one-node halo in shared memory (coalesced rows)
-//                       B  find the crossed grid edges of the tile, compact them (ballot), and compute each crossed
-//                          edge's vertex ONCE with full lanes: interpolation parameter, position coordinate,
-//                          gradient normal -> one float4 record per edge in shared memory
-//                       C  per 32-cell row: classify, warp-level prefix scan of the per-cell triangle counts, then the
-//                          row's triangle corners are FLATTENED over the lanes (corner j of the row -> lane j mod 32):
-//                          each lane looks up the edge record and writes 3+3 floats; consecutive lanes write
+//   mc_emit_kernel    a block owns a 32x8-cell column and marches in z, two cell layers per step; the density planes live in
+//                     a ring in shared memory that TMA (cp.async.bulk.tensor, one 40x11 box per plane, mbarrier completion)
+//                     fills one step ahead.  Per step:
+//                       M  bit masks of the step's 27 node rows (ballot)
+//                       X  crossed grid edges = XOR of neighbouring masks; one thread per (row, axis) group, warp scan of the
+//                          pop-counts, the set bits are expanded into a compact list
+//                       V  one vertex per crossed edge, full lanes: interpolation parameter, coordinate, gradient normal
+//                          -> one float4 record per edge in shared memory
+//                       C  per 32-cell row: cube indices from the masks, warp prefix scan of the per-cell triangle counts,
+//                          then the row's triangle corners are FLATTENED over the lanes (corner j -> lane j mod 32): a lane
+//                          looks up its edge record through a 12-entry table and writes 3+3 floats; consecutive lanes write
 //                          consecutive 12-byte pieces, so every warp store covers one contiguous span of the output.
 // Output order = cell-linear (x fastest, then y, then z), inside a cell the table's order: independent of the
 // tile shape and of the z-slab decomposition.
 #pragma once
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace mms {
 
-__constant__ unsigned long long kCaseWords[256] = {
-#include "mc_case_words.inc"
+// word = ntri | edge0<<4 | edge1<<8 | ... (generated from the compiled reference table, oracle/tools/gen_mc_tables.py)
+struct McCaseTable {
+    unsigned long long w[256];
 };
+constexpr McCaseTable kCaseHost = {{
+#include "mc_case_words.inc"
+}};
+// The kernels assemble the cube index from (x, x+1) bit pairs of four node rows, i.e. in the order
+// c0 c1 | c3 c2 | c4 c5 | c7 c6; the table is stored under that permuted index.
+constexpr int mcPermutedToCubeIndex(int i) {
+    return (i & 0x33) | ((i & 0x44) << 1) | ((i & 0x88) >> 1);
+}
+constexpr McCaseTable mcMakePermuted() {
+    McCaseTable t{};
+    for (int i = 0; i < 256; ++i) t.w[i] = kCaseHost.w[mcPermutedToCubeIndex(i)];
+    return t;
+}
+__device__ const McCaseTable kCasePerm = mcMakePermuted();
 
 struct McGeo {
     int sx, sy;        // volume resolution in x, y
@@ -37,165 +59,190 @@ struct McGeo {
     float iso;
 };
 
+constexpr int MC_THREADS = 256;
+
 // ---------------------------------------------------------------------------------------------------------------
 // count
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int MC_THREADS = 256;
-constexpr int MCC_ROWS = 8;  // cell rows (y) per warp of the count kernel (more rows = fewer redundant row loads but more registers)
+constexpr int CN_SEGS = 16;                 // x-segments (32 cells each) per block
+constexpr int CN_ROWS = 16;                 // cell rows (y) per block
+constexpr int CN_LAYERS = 16;               // cell layers (z) a block marches through
+constexpr int CN_WORDS = CN_SEGS + 1;       // mask words per node row: 16 segments + the first node of the next segment
+constexpr int CN_NROWS = CN_ROWS + 1;       // node rows per plane
 
-__device__ __forceinline__ int cubeIndexSmem(const float* f, int strideY, int strideZ, float iso) {
-    // f points at corner 0; corners: (0,0,0) (1,0,0) (1,1,0) (0,1,0) (0,0,1) (1,0,1) (1,1,1) (0,1,1)
-    int ci = 0;
-    ci |= (f[0] < iso) ? 1 : 0;
-    ci |= (f[1] < iso) ? 2 : 0;
-    ci |= (f[1 + strideY] < iso) ? 4 : 0;
-    ci |= (f[strideY] < iso) ? 8 : 0;
-    ci |= (f[strideZ] < iso) ? 16 : 0;
-    ci |= (f[1 + strideZ] < iso) ? 32 : 0;
-    ci |= (f[1 + strideY + strideZ] < iso) ? 64 : 0;
-    ci |= (f[strideY + strideZ] < iso) ? 128 : 0;
-    return ci;
-}
-
-constexpr int MCC_LAYERS = 16; // cell layers (z) a warp marches through
-
-/**
- * Count kernel, register-rolling in z: a warp owns a strip of 32 cells (x) by MCC_ROWS rows (y) and marches through
- * MCC_LAYERS cell layers.  Per layer it loads ONE new node plane of the strip (MCC_ROWS+1 rows of 128 contiguous bytes, node
- * 32 of the segment by lane 0) and turns it into "below iso" bits; the bits of the previous plane stay in registers and the
- * x+1 neighbour comes from a shuffle -- so every density value is loaded ~1.1 times and a cell costs ~20 instructions.
- * Per-cell lookups go to a shared copy of the count table (the constant cache would serialise per-lane indices).
- */
 __global__ void __launch_bounds__(MC_THREADS) mc_count_kernel(McGeo m, const float* __restrict__ vol, unsigned* __restrict__ segCount,
     unsigned char* __restrict__ triCount) {
+    __shared__ unsigned sMask[3][CN_NROWS][CN_WORDS];
     __shared__ unsigned char sCount[256];
-    sCount[threadIdx.x] = static_cast<unsigned char>(kCaseWords[threadIdx.x] & 15ull);
-    __syncthreads();
+    sCount[threadIdx.x] = static_cast<unsigned char>(kCasePerm.w[threadIdx.x] & 15ull);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int xseg = blockIdx.x;
-    const int yBeg = (blockIdx.y * (MC_THREADS / 32) + warp) * MCC_ROWS;
-    const int czBeg = m.cz0 + blockIdx.z * MCC_LAYERS;
-    if (yBeg >= m.cy || czBeg >= m.cz0 + m.cnz) return;
-    const int yEnd = min(yBeg + MCC_ROWS, m.cy), czEnd = min(czBeg + MCC_LAYERS, m.cz0 + m.cnz);
-    const int x = xseg * 32 + lane;
-    const int xa = min(x, m.sx - 1), xb = min(xseg * 32 + 32, m.sx - 1);
+    const int seg0 = blockIdx.x * CN_SEGS, yBeg = blockIdx.y * CN_ROWS;
+    const int czBeg = m.cz0 + blockIdx.z * CN_LAYERS, czEnd = min(czBeg + CN_LAYERS, m.cz0 + m.cnz);
+    if (czBeg >= czEnd) return;
     const size_t plane = static_cast<size_t>(m.sx) * m.sy;
-    // bits of one node plane of the strip: bit0 = my node below iso, bit1 = node x+1 below iso
-    auto planeBits = [&](int zNode, unsigned (&out)[MCC_ROWS + 1]) {
+    const int nsegHere = min(CN_SEGS, m.nsegx - seg0);
+
+    // one node plane -> mask words (nodes beyond the grid are clamped copies: they never make a valid cell look different)
+    auto planeMasks = [&](int zNode, int buf) {
         const float* p = vol + plane * (zNode - m.zPlane0);
-        float v[MCC_ROWS + 1], e[MCC_ROWS + 1];
+        constexpr int ITEMS = CN_NROWS * CN_SEGS; // 272 (row, segment) words
+        constexpr int U = 8;                      // loads in flight per lane
+        for (int it0 = warp; it0 < ITEMS; it0 += U * (MC_THREADS / 32)) {
+            float v[U];
 #pragma unroll
-        for (int r = 0; r <= MCC_ROWS; ++r) {
-            const size_t o = static_cast<size_t>(m.sx) * min(yBeg + r, m.sy - 1);
-            v[r] = p[o + xa];
-            e[r] = lane == 0 ? p[o + xb] : 0.0f;
-        }
+            for (int u = 0; u < U; ++u) {
+                const int it = it0 + u * (MC_THREADS / 32);
+                const int r = it / CN_SEGS, s = it % CN_SEGS;
+                const int y = min(yBeg + r, m.sy - 1), x = min((seg0 + s) * 32 + lane, m.sx - 1);
+                v[u] = it < ITEMS ? p[static_cast<size_t>(m.sx) * y + x] : 0.0f;
+            }
 #pragma unroll
-        for (int r = 0; r <= MCC_ROWS; ++r) {
-            const unsigned me = v[r] < m.iso ? 1u : 0u;
-            unsigned nb = __shfl_down_sync(0xffffffffu, me, 1);
-            const unsigned last = __shfl_sync(0xffffffffu, e[r] < m.iso ? 1u : 0u, 0);
-            if (lane == 31) nb = last;
-            out[r] = me | (nb << 1);
-        }
-    };
-    unsigned lo[MCC_ROWS + 1], hi[MCC_ROWS + 1];
-    planeBits(czBeg, lo);
-    for (int cz = czBeg; cz < czEnd; ++cz) {
-        planeBits(cz + 1, hi);
-#pragma unroll
-        for (int r = 0; r < MCC_ROWS; ++r) {
-            const int y = yBeg + r;
-            if (y < yEnd) {
-                // corners: 0 (x,y,z) 1 (x+1,y,z) 2 (x+1,y+1,z) 3 (x,y+1,z) 4 (x,y,z+1) 5 (x+1,y,z+1) 6 (x+1,y+1,z+1) 7 (x,y+1,z+1)
-                const unsigned ci = (lo[r] & 1u) | (lo[r] & 2u) | ((lo[r + 1] >> 1) & 1u) << 2 | (lo[r + 1] & 1u) << 3 | (hi[r] & 1u) << 4 |
-                                    ((hi[r] >> 1) & 1u) << 5 | ((hi[r + 1] >> 1) & 1u) << 6 | (hi[r + 1] & 1u) << 7;
-                unsigned n = 0;
-                if (x < m.cx) {
-                    n = sCount[ci];
-                    if (triCount) triCount[x + static_cast<size_t>(m.cx) * (y + static_cast<size_t>(m.cy) * (cz - m.cz0))] = static_cast<unsigned char>(n);
-                }
-                const unsigned tot = __reduce_add_sync(0xffffffffu, n);
-                if (lane == 0) segCount[xseg + static_cast<size_t>(m.nsegx) * (y + static_cast<size_t>(m.cy) * (cz - m.cz0))] = tot;
+            for (int u = 0; u < U; ++u) {
+                const int it = it0 + u * (MC_THREADS / 32);
+                const unsigned b = __ballot_sync(0xffffffffu, v[u] < m.iso);
+                if (lane == 0 && it < ITEMS) sMask[buf][it / CN_SEGS][it % CN_SEGS] = b;
             }
         }
-#pragma unroll
-        for (int r = 0; r <= MCC_ROWS; ++r) lo[r] = hi[r];
+        // the node column after the block's last segment (bit 0 of word CN_SEGS)
+        if (warp == (zNode & 7) && lane < CN_NROWS) {
+            const int y = min(yBeg + lane, m.sy - 1), x = min((seg0 + CN_SEGS) * 32, m.sx - 1);
+            sMask[buf][lane][CN_SEGS] = p[static_cast<size_t>(m.sx) * y + x] < m.iso ? 1u : 0u;
+        }
+    };
+
+    planeMasks(czBeg, czBeg % 3);
+    const int s = threadIdx.x & (CN_SEGS - 1), r = threadIdx.x >> 4; // this thread's segment and cell row
+    const int xseg = seg0 + s, y = yBeg + r;
+    const bool mine = s < nsegHere && y < m.cy;
+    const int ncellsX = m.cx - xseg * 32; // valid cells of my segment
+    const unsigned validCells = ncellsX >= 32 ? 0xffffffffu : (ncellsX > 0 ? (1u << ncellsX) - 1u : 0u);
+    for (int cz = czBeg; cz < czEnd; ++cz) {
+        planeMasks(cz + 1, (cz + 1) % 3);
+        __syncthreads();
+        if (mine) {
+            const unsigned(*lo)[CN_WORDS] = sMask[cz % 3];
+            const unsigned(*hi)[CN_WORDS] = sMask[(cz + 1) % 3];
+            // (x, x+1) pairs live in the 33-bit value hiWord:loWord
+            const unsigned a0 = lo[r][s], a1 = lo[r][s + 1], b0 = lo[r + 1][s], b1 = lo[r + 1][s + 1];
+            const unsigned c0 = hi[r][s], c1 = hi[r][s + 1], d0 = hi[r + 1][s], d1 = hi[r + 1][s + 1];
+            const unsigned a0s = __funnelshift_r(a0, a1, 1), b0s = __funnelshift_r(b0, b1, 1);
+            const unsigned c0s = __funnelshift_r(c0, c1, 1), d0s = __funnelshift_r(d0, d1, 1);
+            const unsigned all = a0 & a0s & b0 & b0s & c0 & c0s & d0 & d0s;
+            const unsigned any = a0 | a0s | b0 | b0s | c0 | c0s | d0 | d0s;
+            unsigned active = any & ~all & validCells;
+            unsigned n = 0;
+            unsigned char* tc = triCount ? triCount + (static_cast<size_t>(m.cx) * (y + static_cast<size_t>(m.cy) * (cz - m.cz0)) + xseg * 32) : nullptr;
+            while (active) {
+                const int b = __ffs(active) - 1;
+                active &= active - 1;
+                const unsigned ci = (__funnelshift_r(a0, a1, b) & 3u) | (__funnelshift_r(b0, b1, b) & 3u) << 2 |
+                                    (__funnelshift_r(c0, c1, b) & 3u) << 4 | (__funnelshift_r(d0, d1, b) & 3u) << 6;
+                const unsigned k = sCount[ci];
+                n += k;
+                if (tc) tc[b] = static_cast<unsigned char>(k);
+            }
+            segCount[xseg + static_cast<size_t>(m.nsegx) * (y + static_cast<size_t>(m.cy) * (cz - m.cz0))] = n;
+        }
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // emit: z-marching, software-pipelined
 // ---------------------------------------------------------------------------------------------------------------
-// A block owns a 32x8-cell column and marches through EM_STEPS steps of EZ = 2 cell layers.  The density planes live
-// in a 7-slot ring in shared memory (5 planes of the current step incl. the gradient halo + the 2 planes the next
-// step adds); the next step's planes are fetched with cp.async while the current step computes, so the global-load
-// latency is paid once per block instead of once per tile, and no plane is loaded twice inside a column chunk.
 constexpr int EX = 32, EY = 8, EZ = 2;                      // cells per step
 constexpr int ENX = EX + 1, ENY = EY + 1, ENZ = EZ + 1;     // nodes per step
-constexpr int EHX = EX + 3, EHY = EY + 3, EHZ = EZ + 3;     // nodes + gradient halo
-constexpr int EHXP = EHX + 1;                               // padded row
-constexpr int ERING = 8;                                    // plane slots (>= EHZ + EZ = 7; power of two: slot = (z+1) & 7)
+constexpr int EHY = EY + 3;                                 // node rows + gradient halo (y0-1 .. y0+9)
+constexpr int EPITCH = 40;                                  // x0-4 .. x0+35 (x0-1 .. x0+33 are needed): TMA wants the box start and width in
+                                                            // multiples of 16 bytes (an unaligned start coordinate is an illegal instruction)
+constexpr int EHX0 = 4;                                     // ring column of node 0
+constexpr int EPLANE = 448;                                 // floats per ring slot: 11*40 = 440, padded to 14*128 bytes
+constexpr int ERING = 8;                                    // plane slots (5 of the current step + 2 prefetched; power of two)
 constexpr int EM_STEPS = 16;                                // steps per block (32 cell layers)
-constexpr int E_XEDGES = ENZ * ENY * EX;                    // 864  x-edges: ix < 32
-constexpr int E_YEDGES = ENZ * EY * ENX;                    // 792  y-edges: iy < 8
-constexpr int E_ZEDGES = EZ * ENY * ENX;                    // 594  z-edges: iz < 2
+constexpr int E_XEDGES = ENZ * ENY * EX;                    // 864  x-edges: (plane*9 + row)*32 + ix,      ix < 32
+constexpr int E_YEDGES = ENZ * EY * ENX;                    // 792  y-edges: (plane*8 + row)*33 + ix,      row < 8
+constexpr int E_ZEDGES = EZ * ENY * ENX;                    // 594  z-edges: (plane*9 + row)*33 + ix,      plane < 2
 constexpr int E_YBASE = E_XEDGES, E_ZBASE = E_XEDGES + E_YEDGES, E_EDGES = E_XEDGES + E_YEDGES + E_ZEDGES;
 constexpr int E_MAXROWTRIS = 160;
+constexpr int E_ROWS = EM_STEPS * EZ * EY;                  // 256 cell rows per block chunk
+constexpr int E_TAB_Y = ENX, E_TAB_Z = ENX + ENY;           // node position table: 33 x, 9 y, 3 z (z per step)
+constexpr unsigned E_PLANE_BYTES = EHY * EPITCH * 4;        // 1584
 
-struct McEmitShared {
-    float4 edge[E_EDGES];               // {interpolated coordinate along the edge's axis, nx, ny, nz}
-    float ring[ERING][EHY][EHXP];       // plane with global node index z sits in slot (z + 1) mod ERING
-    unsigned short crossList[E_EDGES];
-    unsigned char triOwner[MC_THREADS / 32][E_MAXROWTRIS];
-    float tabX[ENX], tabY[ENY];         // node positions float(idx)*sd + origin (ParticlesToDensity.cpp:605)
-    unsigned segOff[EM_STEPS * EZ * EY + 1][2]; // per row of the chunk: first triangle, triangle count
-    int stepActive[EM_STEPS];
-    int anyActive;
+struct __align__(128) McEmitShared {
+    float ring[ERING * EPLANE];                 // plane with node index z sits in slot (z - zcBeg + 1) mod ERING      14336 B
+    float4 edge[E_EDGES];                       // {interpolated coordinate along the edge's axis, nx, ny, nz}          36000 B
+    union {
+        unsigned short crossList[E_EDGES];      // phases X, V
+        unsigned char triOwner[MC_THREADS / 32][E_MAXROWTRIS]; // phase C: (owner lane << 3) | triangle number inside the owner cell
+    };
+    unsigned char segCnt[E_ROWS];               // its triangle count (<= 160)
+    unsigned edgeTab[EZ * EY][12];              // per (layer, row) of a step and cube edge: edge slot of cell 0 | flags
+    float tab[E_TAB_Z + ENZ + 3];               // node positions float(idx)*sd + origin (ParticlesToDensity.cpp:605)
+    unsigned below[ENZ * ENY];                  // "below iso" bits of the step's node rows, nodes 0..31
+    unsigned col32;                             // ... of node 32 of every row (bit plane*9 + row)
+    unsigned stepAct[MC_THREADS / 32];
     int ncross;
+    unsigned long long mbar;
 };
+static_assert(sizeof(McEmitShared) + 128 <= 57088, "mc_emit_kernel must fit four blocks per SM");
 
 // per cube edge: low corner (dx,dy,dz) and axis: dx | dy<<1 | dz<<2 | axis<<3   (MarchingCubeTables.cpp:15-16, low node first)
 //  e0 (0,0,0)x  e1 (1,0,0)y  e2 (0,1,0)x  e3 (0,0,0)y  e4 (0,0,1)x  e5 (1,0,1)y  e6 (0,1,1)x  e7 (0,0,1)y
 //  e8 (0,0,0)z  e9 (1,0,0)z  e10 (1,1,0)z e11 (0,1,0)z
-__device__ __forceinline__ unsigned edgeCode(int e) {
+__host__ __device__ __forceinline__ unsigned edgeCode(int e) {
     const unsigned long long codes = (0ull) | (9ull << 5) | (2ull << 10) | (8ull << 15) | (4ull << 20) | (13ull << 25) |
                                      (6ull << 30) | (12ull << 35) | (16ull << 40) | (17ull << 45) | (19ull << 50) | (18ull << 55);
     return static_cast<unsigned>(codes >> (5 * e)) & 31u;
 }
 
-__device__ __forceinline__ int edgeIndex(int axis, int ix, int iy, int iz) {
-    if (axis == 0) return (iz * ENY + iy) * EX + ix;
-    if (axis == 1) return E_YBASE + (iz * EY + iy) * ENX + ix;
-    return E_ZBASE + (iz * ENY + iy) * ENX + ix;
-}
+// flags of an edgeTab entry (bits 0..11 = edge slot of the row's cell 0)
+constexpr unsigned ET_AX0 = 1u << 12, ET_AX1 = 1u << 13, ET_AX2 = 1u << 14, ET_DX = 1u << 15, ET_DY = 1u << 16, ET_DZ = 1u << 17;
 
-__device__ __forceinline__ int ringSlot(int zNode) { // zNode >= -1
-    return (zNode + 1) & (ERING - 1);
-}
+__device__ __forceinline__ unsigned smemAddr(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
 
 __device__ __forceinline__ void cpAsync4(float* smemDst, const float* gmemSrc) {
-    const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smemDst));
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gmemSrc));
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smemAddr(smemDst)), "l"(gmemSrc));
+}
+__device__ __forceinline__ void mbarInit(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smemAddr(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbarExpectTx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbarWait(unsigned long long* bar, unsigned parity) {
+    const unsigned a = smemAddr(bar);
+    unsigned done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(a), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tmaLoadPlane(float* smemDst, const CUtensorMap* map, int x, int y, int z, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(smemAddr(smemDst)), "l"(reinterpret_cast<unsigned long long>(map)), "r"(x), "r"(y), "r"(z), "r"(smemAddr(bar)) : "memory");
 }
 
-template<bool COLOUR>
-__global__ void __launch_bounds__(MC_THREADS) mc_emit_kernel(McGeo m, const float* __restrict__ vol, const float* __restrict__ rgb,
-    const unsigned* __restrict__ segOffset, float* __restrict__ outPos, float* __restrict__ outNrm, float* __restrict__ outCol) {
-    extern __shared__ __align__(16) unsigned char smemRaw[];
-    McEmitShared& sh = *reinterpret_cast<McEmitShared*>(smemRaw);
-    float4* edgeCol = reinterpret_cast<float4*>(smemRaw + ((sizeof(McEmitShared) + 15) & ~size_t(15))); // COLOUR only
+/**
+ * TMA: the planes arrive as 40x11x1 boxes of a 3-D tensor map over the slab volume (needs sx % 4 == 0; out-of-range elements are
+ * zero-filled, which is harmless: gradients at the global border are one-sided and cells beyond the grid are masked).
+ * !TMA: the same ring filled with 4-byte cp.async copies, coordinates clamped.
+ */
+template<bool COLOUR, bool TMA>
+__global__ void __launch_bounds__(MC_THREADS) mc_emit_kernel(McGeo m, const __grid_constant__ CUtensorMap volMap, const float* __restrict__ vol,
+    const float* __restrict__ rgb, const unsigned* __restrict__ segOffset, float* __restrict__ outPos, float* __restrict__ outNrm,
+    float* __restrict__ outCol) {
+    extern __shared__ unsigned char smemRaw[];
+    unsigned char* smemAligned = smemRaw + ((128u - (smemAddr(smemRaw) & 127u)) & 127u);
+    McEmitShared& sh = *reinterpret_cast<McEmitShared*>(smemAligned);
+    float4* edgeCol = reinterpret_cast<float4*>(smemAligned + sizeof(McEmitShared)); // COLOUR only
     const int x0 = blockIdx.x * EX, y0 = blockIdx.y * EY;
     const int zcBeg = m.cz0 + blockIdx.z * (EM_STEPS * EZ);           // first global cell layer of this block
     const int zcEnd = min(zcBeg + EM_STEPS * EZ, m.cz0 + m.cnz);      // exclusive
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     // ---- which rows / steps have triangles (one global read per row of the chunk) -----------------------------------
-    if (threadIdx.x < EM_STEPS) sh.stepActive[threadIdx.x] = 0;
-    if (threadIdx.x == 0) sh.anyActive = 0;
-    __syncthreads();
-    for (int r = threadIdx.x; r < EM_STEPS * EZ * EY; r += MC_THREADS) {
-        const int ly = r % EY, lzc = r / EY;
+    {
+        const int ly = tid % EY, lzc = tid / EY; // E_ROWS == MC_THREADS
         const int cyi = y0 + ly, czi = zcBeg + lzc;
         unsigned off = 0, cnt = 0;
         if (cyi < m.cy && czi < zcEnd) {
@@ -203,129 +250,204 @@ __global__ void __launch_bounds__(MC_THREADS) mc_emit_kernel(McGeo m, const floa
             off = segOffset[seg];
             cnt = segOffset[seg + 1] - off;
         }
-        sh.segOff[r][0] = off, sh.segOff[r][1] = cnt;
-        if (cnt) sh.stepActive[lzc / EZ] = 1, sh.anyActive = 1;
+        sh.segCnt[tid] = static_cast<unsigned char>(cnt);
+        const unsigned bal = __ballot_sync(0xffffffffu, cnt != 0); // rows 16s .. 16s+15 belong to step s
+        if (lane == 0) sh.stepAct[warp] = ((bal & 0xffffu) ? 1u : 0u) | ((bal >> 16) ? 2u : 0u);
     }
+    if (tid < EZ * EY * 12) {
+        const int row = tid / 12, e = tid % 12, ly = row % EY, lz = row / EY;
+        const unsigned code = edgeCode(e);
+        const int dx = code & 1, dy = (code >> 1) & 1, dz = (code >> 2) & 1, axis = code >> 3;
+        unsigned slot;
+        if (axis == 0) slot = ((lz + dz) * ENY + ly + dy) * EX + dx;
+        else if (axis == 1) slot = E_YBASE + ((lz + dz) * EY + ly + dy) * ENX + dx;
+        else slot = E_ZBASE + ((lz + dz) * ENY + ly + dy) * ENX + dx;
+        sh.edgeTab[row][e] = slot | (ET_AX0 << axis) | (dx ? ET_DX : 0u) | (dy ? ET_DY : 0u) | (dz ? ET_DZ : 0u);
+    }
+    if (tid < ENX) sh.tab[tid] = __fadd_rn(__fmul_rn((float)(x0 + tid), m.sd[0]), m.org[0]);
+    else if (tid < ENX + ENY) sh.tab[tid] = __fadd_rn(__fmul_rn((float)(y0 + tid - ENX), m.sd[1]), m.org[1]);
+    if (TMA && tid == 0) mbarInit(&sh.mbar, 1);
     __syncthreads();
-    if (!sh.anyActive) return;
+    unsigned stepMask = 0;
+#pragma unroll
+    for (int w = 0; w < MC_THREADS / 32; ++w) stepMask |= sh.stepAct[w] << (2 * w);
+    if (!stepMask) return;
 
-    // ---- plane loader: rows of one plane, clamped to the GLOBAL grid and to the slab -------------------------------------
-    auto loadPlane = [&](int zNode) { // all threads; asynchronous
-        const int zg = min(max(zNode, 0), m.szGlobal - 1);
-        const int zl = min(max(zg - m.zPlane0, 0), m.nzPlanes - 1);
-        float* dst = &sh.ring[ringSlot(zNode)][0][0];
-        for (int i = threadIdx.x; i < EHY * EHXP; i += MC_THREADS) {
-            const int ix = i % EHXP, iy = i / EHXP;
-            if (ix >= EHX) continue;
-            const int x = min(max(x0 + ix - 1, 0), m.sx - 1), y = min(max(y0 + iy - 1, 0), m.sy - 1);
-            cpAsync4(dst + iy * EHXP + ix, vol + x + static_cast<size_t>(m.sx) * (y + static_cast<size_t>(m.sy) * zl));
+    // ---- plane loader -------------------------------------------------------------------------------------------------
+    auto slotOf = [&](int zNode) { return (zNode - zcBeg + 1) & (ERING - 1); }; // zNode >= zcBeg - 1
+    unsigned tmaParity = 0;
+    auto loadPlanes = [&](int zFirst, int zLast) { // uniform; planes zFirst..zLast (node indices), asynchronous
+        if (TMA) {
+            if (tid == 0) {
+                mbarExpectTx(&sh.mbar, static_cast<unsigned>(zLast - zFirst + 1) * E_PLANE_BYTES);
+                for (int z = zFirst; z <= zLast; ++z)
+                    tmaLoadPlane(&sh.ring[slotOf(z) * EPLANE], &volMap, x0 - EHX0, y0 - 1, z - m.zPlane0, &sh.mbar);
+            }
+        } else {
+            for (int z = zFirst; z <= zLast; ++z) {
+                const int zg = min(max(z, 0), m.szGlobal - 1);
+                const int zl = min(max(zg - m.zPlane0, 0), m.nzPlanes - 1);
+                float* dst = &sh.ring[slotOf(z) * EPLANE];
+                for (int i = tid; i < EHY * (ENX + 2); i += MC_THREADS) { // nodes -1 .. 33 of every row
+                    const int ix = i % (ENX + 2) - 1, iy = i / (ENX + 2);
+                    const int x = min(max(x0 + ix, 0), m.sx - 1), y = min(max(y0 + iy - 1, 0), m.sy - 1);
+                    cpAsync4(dst + iy * EPITCH + ix + EHX0, vol + x + static_cast<size_t>(m.sx) * (y + static_cast<size_t>(m.sy) * zl));
+                }
+            }
+            asm volatile("cp.async.commit_group;");
         }
     };
-    // first active step: its five planes; later steps add two planes each
-    int step = 0;
-    while (step < EM_STEPS && !sh.stepActive[step]) ++step;
-    int loadedUpTo = zcBeg + step * EZ - 2; // highest node plane present in the ring (none yet)
-    if (threadIdx.x < ENX) sh.tabX[threadIdx.x] = __fadd_rn(__fmul_rn((float)(x0 + threadIdx.x), m.sd[0]), m.org[0]);
-    else if (threadIdx.x < ENX + ENY) sh.tabY[threadIdx.x - ENX] = __fadd_rn(__fmul_rn((float)(y0 + threadIdx.x - ENX), m.sd[1]), m.org[1]);
+    auto waitPlanes = [&]() {
+        if (TMA) {
+            mbarWait(&sh.mbar, tmaParity);
+            tmaParity ^= 1u;
+        } else {
+            asm volatile("cp.async.wait_group 0;");
+        }
+    };
 
     const float r1x = m.rinv[0][1], r2x = m.rinv[0][2], r1y = m.rinv[1][1], r2y = m.rinv[1][2], r1z = m.rinv[2][1], r2z = m.rinv[2][2];
+    const float iso = m.iso;
+    // validity of the block's nodes (TMA zero-fills beyond the grid; clamped copies would be harmless, zeros are not)
+    const int nvx = min(ENX, m.sx - x0), nvy = min(ENY, m.sy - y0);
+    const unsigned nodeValidX = nvx >= 32 ? 0xffffffffu : (1u << nvx) - 1u;            // nodes 0..31
+    const unsigned xEdgeValid = nvx >= 33 ? 0xffffffffu : (1u << (nvx - 1)) - 1u;      // x-edge ix needs node ix+1
+    const unsigned cellValidX = m.cx - x0 >= 32 ? 0xffffffffu : (1u << (m.cx - x0)) - 1u;
     unsigned char* owner = sh.triOwner[warp];
 
-    for (; step < EM_STEPS; ++step) {
+    int loadedUpTo = -0x40000000; // highest node plane present in (or on its way into) the ring
+    bool pending = false;         // a load batch has been issued and not yet waited for
+    while (stepMask) {
+        const int step = __ffs(stepMask) - 1;
+        stepMask &= stepMask - 1;
         const int zc0 = zcBeg + step * EZ; // global cell layer = global node plane of the step's lowest cells
-        if (zc0 >= zcEnd) break;
-        if (!sh.stepActive[step]) continue;
-        // planes zc0-1 .. zc0+3 must be in the ring.  In the dense case the previous step prefetched them and nothing is issued
-        // here; otherwise the ring slots about to be overwritten may still be read by warps finishing the previous step.
+        // planes zc0-1 .. zc0+3 must be in the ring.  In the dense case the previous step prefetched the two new ones.
         if (loadedUpTo < zc0 + EZ + 1) {
-            __syncthreads();
-            for (int z = max(loadedUpTo + 1, zc0 - 1); z <= zc0 + EZ + 1; ++z) loadPlane(z);
+            if (pending) waitPlanes(), pending = false;
+            __syncthreads(); // every warp has left phase V of the previous step: no ring slot is being read any more
+            loadPlanes(max(loadedUpTo + 1, zc0 - 1), zc0 + EZ + 1);
             loadedUpTo = zc0 + EZ + 1;
-            asm volatile("cp.async.commit_group;");
+            pending = true;
         }
-        asm volatile("cp.async.wait_group 0;");
-        if (threadIdx.x == 0) sh.ncross = 0;
-        __syncthreads(); // (a) the planes have landed for everybody, (b) every warp has left the previous step: edge[], crossList and
-                         //     the ring slots the prefetch below overwrites are free
-        // prefetch the two planes the next step adds (if that step is active) while this one computes
-        const bool nextActive = step + 1 < EM_STEPS && sh.stepActive[step + 1] && zc0 + EZ < zcEnd;
-        if (nextActive) {
-            loadPlane(zc0 + EZ + 2);
-            loadPlane(zc0 + EZ + 3);
+        if (pending) waitPlanes(), pending = false;
+        __syncthreads(); // S1: the planes have landed for everybody; every warp has left phase C of the previous step
+        if (stepMask && (__ffs(stepMask) - 1) == step + 1) { // prefetch the two planes the next step adds while this one computes
+            loadPlanes(zc0 + EZ + 2, zc0 + EZ + 3);
             loadedUpTo = zc0 + EZ + 3;
-            asm volatile("cp.async.commit_group;");
+            pending = true;
         }
-        // halo coordinates (node + 1): plane iz of the step = node plane zc0 - 1 + iz = ring slot (slot0 + iz) mod ERING
-        const int slot0 = ringSlot(zc0 - 1);
-        auto H = [&](int iz, int iy, int ix) -> float {
-            return sh.ring[(slot0 + iz) & (ERING - 1)][iy][ix];
-        };
+        const int slot0 = (step * EZ) & (ERING - 1);            // slot of halo plane 0 = node plane zc0 - 1
+        auto planeOff = [&](int hz) { return ((slot0 + hz) & (ERING - 1)) * EPLANE; }; // hz = node plane + 1 (halo coordinates)
+        const int nvz = min(ENZ, zcEnd - zc0 + 1);              // valid node planes of the step (cell layers beyond zcEnd are not ours)
 
-        // ---- B1: crossed edges -> crossList (order is irrelevant) ------------------------------------------------
-        // rounds 0..26: one warp per node row, lanes = nodes 0..31; round 27: the 27 nodes of column 32, one per lane
-        for (int r = warp; r < ENZ * ENY + 1; r += MC_THREADS / 32) {
-            const bool lastCol = r == ENZ * ENY;
-            const int rr = lastCol ? lane : r;
-            const bool active = !lastCol || lane < ENZ * ENY;
-            const int iy = rr % ENY, iz = (rr / ENY) % ENZ;
-            const int ix = lastCol ? EX : lane;
-            bool cx = false, cy = false, cz = false;
-            if (active) {
-                const bool b0 = H(iz + 1, iy + 1, ix + 1) < m.iso;
-                if (ix < EX) cx = b0 != (H(iz + 1, iy + 1, ix + 2) < m.iso);
-                if (iy < EY) cy = b0 != (H(iz + 1, iy + 2, ix + 1) < m.iso);
-                if (iz < EZ) cz = b0 != (H(iz + 2, iy + 1, ix + 1) < m.iso);
+        // ---- M: bit masks ------------------------------------------------------------------------------------------------
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int q = warp + 8 * k; // node row: plane q / 9, row q % 9
+            if (q < ENZ * ENY) {
+                const int p = (q * 57) >> 9, r = q - 9 * p;
+                const unsigned b = __ballot_sync(0xffffffffu, sh.ring[planeOff(p + 1) + (r + 1) * EPITCH + lane + EHX0] < iso);
+                if (lane == 0) sh.below[q] = b;
             }
-            const unsigned bx = __ballot_sync(0xffffffffu, cx), by = __ballot_sync(0xffffffffu, cy), bz = __ballot_sync(0xffffffffu, cz);
-            const int nx = __popc(bx), ny = __popc(by), nz = __popc(bz);
-            if (nx + ny + nz == 0) continue;
-            int base = 0;
-            if (lane == 0) base = atomicAdd(&sh.ncross, nx + ny + nz);
-            base = __shfl_sync(0xffffffffu, base, 0);
-            const unsigned lt = (1u << lane) - 1u;
-            if (cx) sh.crossList[base + __popc(bx & lt)] = static_cast<unsigned short>(edgeIndex(0, ix, iy, iz));
-            if (cy) sh.crossList[base + nx + __popc(by & lt)] = static_cast<unsigned short>(edgeIndex(1, ix, iy, iz));
-            if (cz) sh.crossList[base + nx + ny + __popc(bz & lt)] = static_cast<unsigned short>(edgeIndex(2, ix, iy, iz));
         }
-        __syncthreads();
+        if (warp == 7) {
+            const int q = min(lane, ENZ * ENY - 1);
+            const int p = (q * 57) >> 9, r = q - 9 * p;
+            const unsigned b = __ballot_sync(0xffffffffu, lane < ENZ * ENY && sh.ring[planeOff(p + 1) + (r + 1) * EPITCH + EX + EHX0] < iso);
+            if (lane == 0) sh.col32 = nvx >= ENX ? b : 0u, sh.ncross = 0;
+        }
+        if (warp == 6 && lane < ENZ) sh.tab[E_TAB_Z + lane] = __fadd_rn(__fmul_rn((float)(zc0 + lane), m.sd[2]), m.org[2]);
+        __syncthreads(); // S2
 
-        // ---- B2: one vertex per crossed edge ------------------------------------------------------------------------
+        // ---- X: crossed edges -> crossList ----------------------------------------------------------------------------------
+        if (tid < 96) {
+            const int g = tid;
+            unsigned mask = 0, base = 0, stride = 1;
+            const unsigned c32 = sh.col32;
+            if (g < 27) {           // x-edges of node row g = p*9 + r
+                const int p = (g * 57) >> 9, r = g - 9 * p;
+                const unsigned b = sh.below[g];
+                if (r < nvy && p < nvz) mask = (b ^ ((b >> 1) | (((c32 >> g) & 1u) << 31))) & xEdgeValid;
+                base = g * EX;
+            } else if (g < 51) {    // y-edges between node rows r and r+1 of plane p, j = p*8 + r
+                const int j = g - 27, p = j >> 3, r = j & 7;
+                if (r + 1 < nvy && p < nvz) mask = (sh.below[p * ENY + r] ^ sh.below[p * ENY + r + 1]) & nodeValidX;
+                base = E_YBASE + j * ENX;
+            } else if (g < 69) {    // z-edges between planes p and p+1, j = p*9 + r
+                const int j = g - 51, p = j >= ENY ? 1 : 0, r = j - ENY * p;
+                if (r < nvy && p + 1 < nvz) mask = (sh.below[j] ^ sh.below[j + ENY]) & nodeValidX;
+                base = E_ZBASE + j * ENX;
+            } else if (g == 69) {   // y-edges of node column 32: bit p*8 + r
+                const unsigned rows = (1u << (nvy - 1)) - 1u; // r + 1 < nvy
+#pragma unroll
+                for (int p = 0; p < ENZ; ++p)
+                    if (p < nvz) mask |= (((c32 >> (ENY * p)) ^ (c32 >> (ENY * p + 1))) & 0xffu & rows) << (8 * p);
+                if (nvx < ENX) mask = 0;
+                base = E_YBASE + EX, stride = ENX;
+            } else if (g == 70) {   // z-edges of node column 32: bit p*9 + r
+                const unsigned rows = (1u << nvy) - 1u;
+                mask = (c32 ^ (c32 >> ENY)) & (rows | (nvz > 2 ? rows << ENY : 0u));
+                if (nvx < ENX || nvz < 2) mask = 0;
+                base = E_ZBASE + EX, stride = ENX;
+            }
+            const unsigned cnt = __popc(mask);
+            unsigned inc = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned t = __shfl_up_sync(0xffffffffu, inc, d);
+                if (lane >= d) inc += t;
+            }
+            unsigned wbase = 0;
+            if (lane == 31 && inc) wbase = atomicAdd(&sh.ncross, static_cast<int>(inc));
+            wbase = __shfl_sync(0xffffffffu, wbase, 31);
+            unsigned pos = wbase + inc - cnt;
+            while (mask) {
+                const int b = __ffs(mask) - 1;
+                mask &= mask - 1;
+                sh.crossList[pos++] = static_cast<unsigned short>(base + b * stride);
+            }
+        }
+        __syncthreads(); // S3
+
+        // ---- V: one vertex per crossed edge --------------------------------------------------------------------------------
         const int ncross = sh.ncross;
         // no node of this step touches the global border -> plain central differences
         const bool interior = x0 > 0 && x0 + EX < m.sx - 1 && y0 > 0 && y0 + EY < m.sy - 1 && zc0 > 0 && zc0 + EZ < m.szGlobal - 1;
-        for (int c = threadIdx.x; c < ncross; c += MC_THREADS) {
+        for (int c = tid; c < ncross; c += MC_THREADS) {
             const int id = sh.crossList[c];
-            int axis, ix, iy, iz;
-            if (id < E_YBASE) { axis = 0; ix = id % EX; const int t = id / EX; iy = t % ENY; iz = t / ENY; }
-            else if (id < E_ZBASE) { axis = 1; const int q = id - E_YBASE; ix = q % ENX; const int t = q / ENX; iy = t % EY; iz = t / EY; }
-            else { axis = 2; const int q = id - E_ZBASE; ix = q % ENX; const int t = q / ENX; iy = t % ENY; iz = t / ENY; }
-            const int jx = ix + (axis == 0), jy = iy + (axis == 1), jz = iz + (axis == 2);
+            int axis, ix, r, p;
+            if (id < E_YBASE) { axis = 0; ix = id & 31; const int q = id >> 5; p = (q * 57) >> 9; r = q - 9 * p; }
+            else if (id < E_ZBASE) { axis = 1; const int t = id - E_YBASE; const int q = (t * 993) >> 15; ix = t - ENX * q; p = q >> 3; r = q & 7; }
+            else { axis = 2; const int t = id - E_ZBASE; const int q = (t * 993) >> 15; ix = t - ENX * q; p = q >= ENY ? 1 : 0; r = q - ENY * p; }
+            const int offA = (r + 1) * EPITCH + ix + EHX0;
+            const int offB = offA + (axis == 0 ? 1 : (axis == 1 ? EPITCH : 0));
+            const int hzA = p + 1, hzB = hzA + (axis == 2 ? 1 : 0);
             // gradient at a node: (f(+) - f(-)) * 1/(n*sd), samples clamped at the GLOBAL grid border
-            auto grad = [&](int nx_, int ny_, int nz_, float& gx, float& gy, float& gz) {
-                const int hx = nx_ + 1, hy = ny_ + 1, hz = nz_ + 1;
+            auto grad = [&](int off, int hz, int gxi, int gyi, int gzi, float& gx, float& gy, float& gz) {
+                const float* P0 = sh.ring + planeOff(hz) + off;
+                const float* Pm = sh.ring + planeOff(hz - 1) + off;
+                const float* Pp = sh.ring + planeOff(hz + 1) + off;
                 if (interior) {
-                    gx = __fmul_rn(__fsub_rn(H(hz, hy, hx + 1), H(hz, hy, hx - 1)), r2x);
-                    gy = __fmul_rn(__fsub_rn(H(hz, hy + 1, hx), H(hz, hy - 1, hx)), r2y);
-                    gz = __fmul_rn(__fsub_rn(H(hz + 1, hy, hx), H(hz - 1, hy, hx)), r2z);
+                    gx = __fmul_rn(__fsub_rn(P0[1], P0[-1]), r2x);
+                    gy = __fmul_rn(__fsub_rn(P0[EPITCH], P0[-EPITCH]), r2y);
+                    gz = __fmul_rn(__fsub_rn(Pp[0], Pm[0]), r2z);
                 } else {
-                    const int gxi = x0 + nx_, gyi = y0 + ny_, gzi = zc0 + nz_;
-                    const int xm = gxi > 0 ? -1 : 0, xp = gxi < m.sx - 1 ? 1 : 0;
-                    const int ym = gyi > 0 ? -1 : 0, yp = gyi < m.sy - 1 ? 1 : 0;
-                    const int zm = gzi > 0 ? -1 : 0, zp = gzi < m.szGlobal - 1 ? 1 : 0;
-                    gx = xp > xm ? __fmul_rn(__fsub_rn(H(hz, hy, hx + xp), H(hz, hy, hx + xm)), xp - xm == 2 ? r2x : r1x) : 0.0f;
-                    gy = yp > ym ? __fmul_rn(__fsub_rn(H(hz, hy + yp, hx), H(hz, hy + ym, hx)), yp - ym == 2 ? r2y : r1y) : 0.0f;
-                    gz = zp > zm ? __fmul_rn(__fsub_rn(H(hz + zp, hy, hx), H(hz + zm, hy, hx)), zp - zm == 2 ? r2z : r1z) : 0.0f;
+                    const int xm = gxi > 0 ? 1 : 0, xp = gxi < m.sx - 1 ? 1 : 0;
+                    const int ym = gyi > 0 ? 1 : 0, yp = gyi < m.sy - 1 ? 1 : 0;
+                    const int zm = gzi > 0 ? 1 : 0, zp = gzi < m.szGlobal - 1 ? 1 : 0;
+                    gx = xp + xm ? __fmul_rn(__fsub_rn(P0[xp], P0[-xm]), xp + xm == 2 ? r2x : r1x) : 0.0f;
+                    gy = yp + ym ? __fmul_rn(__fsub_rn(P0[yp * EPITCH], P0[-ym * EPITCH]), yp + ym == 2 ? r2y : r1y) : 0.0f;
+                    gz = zp + zm ? __fmul_rn(__fsub_rn(zp ? Pp[0] : P0[0], zm ? Pm[0] : P0[0]), zp + zm == 2 ? r2z : r1z) : 0.0f;
                 }
             };
-            const float fa = H(iz + 1, iy + 1, ix + 1), fb = H(jz + 1, jy + 1, jx + 1);
-            const float t01 = __fdiv_rn(__fsub_rn(m.iso, fa), __fsub_rn(fb, fa));
-            const float pza = __fadd_rn(__fmul_rn((float)(zc0 + iz), m.sd[2]), m.org[2]);
-            const float pzb = __fadd_rn(__fmul_rn((float)(zc0 + jz), m.sd[2]), m.org[2]);
-            const float pa = axis == 0 ? sh.tabX[ix] : (axis == 1 ? sh.tabY[iy] : pza);
-            const float pb = axis == 0 ? sh.tabX[jx] : (axis == 1 ? sh.tabY[jy] : pzb);
+            const float fa = sh.ring[planeOff(hzA) + offA], fb = sh.ring[planeOff(hzB) + offB];
+            const float t01 = __fdiv_rn(__fsub_rn(iso, fa), __fsub_rn(fb, fa));
+            const int ti = axis == 0 ? ix : (axis == 1 ? E_TAB_Y + r : E_TAB_Z + p);
+            const float pa = sh.tab[ti], pb = sh.tab[ti + 1];
             float gax, gay, gaz, gbx, gby, gbz;
-            grad(ix, iy, iz, gax, gay, gaz);
-            grad(jx, jy, jz, gbx, gby, gbz);
+            const int gxi = x0 + ix, gyi = y0 + r, gzi = zc0 + p;
+            grad(offA, hzA, gxi, gyi, gzi, gax, gay, gaz);
+            grad(offB, hzB, gxi + (axis == 0), gyi + (axis == 1), gzi + (axis == 2), gbx, gby, gbz);
             const float gx = __fadd_rn(gax, __fmul_rn(t01, __fsub_rn(gbx, gax)));
             const float gy = __fadd_rn(gay, __fmul_rn(t01, __fsub_rn(gby, gay)));
             const float gz = __fadd_rn(gaz, __fmul_rn(t01, __fsub_rn(gbz, gaz)));
@@ -333,43 +455,40 @@ __global__ void __launch_bounds__(MC_THREADS) mc_emit_kernel(McGeo m, const floa
             const float inv = len2 > 0.0f ? -rsqrtf(len2) : 0.0f; // SFU rsqrt: 2 ulp, normals are compared at 1e-4
             sh.edge[id] = make_float4(__fadd_rn(pa, __fmul_rn(t01, __fsub_rn(pb, pa))), __fmul_rn(gx, inv), __fmul_rn(gy, inv), __fmul_rn(gz, inv));
             if (COLOUR) { // node colour = rgb / rho (0 where rho == 0), interpolated with the same t
-                auto nodeColour = [&](int nx_, int ny_, int nz_, float f, float& r, float& gg, float& b) {
+                auto nodeColour = [&](int nx_, int ny_, int nz_, float f, float& cr, float& cg, float& cb) {
                     const int x = min(x0 + nx_, m.sx - 1), y = min(y0 + ny_, m.sy - 1);
                     const int zl = min(max(zc0 + nz_ - m.zPlane0, 0), m.nzPlanes - 1);
-                    const float* c = rgb + 3 * (x + static_cast<size_t>(m.sx) * (y + static_cast<size_t>(m.sy) * zl));
-                    if (f > 0.0f) r = __fdiv_rn(c[0], f), gg = __fdiv_rn(c[1], f), b = __fdiv_rn(c[2], f);
-                    else r = gg = b = 0.0f;
+                    const float* cc = rgb + 3 * (x + static_cast<size_t>(m.sx) * (y + static_cast<size_t>(m.sy) * zl));
+                    if (f > 0.0f) cr = __fdiv_rn(cc[0], f), cg = __fdiv_rn(cc[1], f), cb = __fdiv_rn(cc[2], f);
+                    else cr = cg = cb = 0.0f;
                 };
                 float ar, ag, ab, br, bg, bb;
-                nodeColour(ix, iy, iz, fa, ar, ag, ab);
-                nodeColour(jx, jy, jz, fb, br, bg, bb);
+                nodeColour(ix, r, p, fa, ar, ag, ab);
+                nodeColour(ix + (axis == 0), r + (axis == 1), p + (axis == 2), fb, br, bg, bb);
                 edgeCol[id] = make_float4(__fadd_rn(ar, __fmul_rn(t01, __fsub_rn(br, ar))), __fadd_rn(ag, __fmul_rn(t01, __fsub_rn(bg, ag))),
                     __fadd_rn(ab, __fmul_rn(t01, __fsub_rn(bb, ab))), 0.0f);
             }
         }
-        __syncthreads();
+        __syncthreads(); // S4
 
         // ---- C: triangles, one warp per 32-cell row ---------------------------------------------------------------------
-        for (int r = warp; r < EY * EZ; r += MC_THREADS / 32) {
-            const int ly = r % EY, lz = r / EY;
-            const int cxi = x0 + lane;
+#pragma unroll 1
+        for (int rr = warp; rr < EY * EZ; rr += MC_THREADS / 32) {
+            const int ly = rr % EY, lz = rr / EY;
             const int row = (step * EZ + lz) * EY + ly;
-            const unsigned segOff = sh.segOff[row][0], segTris = sh.segOff[row][1];
+            const unsigned segTris = sh.segCnt[row];
             if (segTris == 0) continue;
+            const unsigned segOff = segOffset[blockIdx.x + static_cast<size_t>(m.nsegx) * (y0 + ly + static_cast<size_t>(m.cy) * (zc0 + lz - m.cz0))];
+            // cube index in permuted order from the (x, x+1) bit pairs of the four node rows
+            const int q = lz * ENY + ly;
+            const unsigned c32 = sh.col32;
+            const unsigned p00 = __funnelshift_r(sh.below[q], (c32 >> q) & 1u, lane) & 3u;
+            const unsigned p10 = __funnelshift_r(sh.below[q + 1], (c32 >> (q + 1)) & 1u, lane) & 3u;
+            const unsigned p01 = __funnelshift_r(sh.below[q + ENY], (c32 >> (q + ENY)) & 1u, lane) & 3u;
+            const unsigned p11 = __funnelshift_r(sh.below[q + ENY + 1], (c32 >> (q + ENY + 1)) & 1u, lane) & 3u;
             unsigned long long word = 0;
-            if (cxi < m.cx) {
-                int ci = 0;
-                ci |= (H(lz + 1, ly + 1, lane + 1) < m.iso) ? 1 : 0;
-                ci |= (H(lz + 1, ly + 1, lane + 2) < m.iso) ? 2 : 0;
-                ci |= (H(lz + 1, ly + 2, lane + 2) < m.iso) ? 4 : 0;
-                ci |= (H(lz + 1, ly + 2, lane + 1) < m.iso) ? 8 : 0;
-                ci |= (H(lz + 2, ly + 1, lane + 1) < m.iso) ? 16 : 0;
-                ci |= (H(lz + 2, ly + 1, lane + 2) < m.iso) ? 32 : 0;
-                ci |= (H(lz + 2, ly + 2, lane + 2) < m.iso) ? 64 : 0;
-                ci |= (H(lz + 2, ly + 2, lane + 1) < m.iso) ? 128 : 0;
-                word = kCaseWords[ci];
-            }
-            const unsigned n = static_cast<unsigned>(word & 15ull);
+            if ((cellValidX >> lane) & 1u) word = __ldg(&kCasePerm.w[p00 | p10 << 2 | p01 << 4 | p11 << 6]);
+            const unsigned n = static_cast<unsigned>(word) & 15u;
             unsigned inc = n;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
@@ -377,46 +496,48 @@ __global__ void __launch_bounds__(MC_THREADS) mc_emit_kernel(McGeo m, const floa
                 if (lane >= d) inc += t;
             }
             const unsigned first = inc - n; // my first triangle within the row
-            for (unsigned k = 0; k < n; ++k) owner[first + k] = static_cast<unsigned char>(lane);
+            for (unsigned k = 0; k < n; ++k) owner[first + k] = static_cast<unsigned char>(lane << 3 | k);
             __syncwarp();
             const unsigned wlo = static_cast<unsigned>(word >> 4), whi = static_cast<unsigned>(word >> 36); // 15 nibbles of edge ids
             const unsigned ncorn = segTris * 3;
             const size_t gbase = static_cast<size_t>(segOff) * 9;
-            const float tz0 = __fadd_rn(__fmul_rn((float)(zc0 + lz), m.sd[2]), m.org[2]);
-            const float tz1 = __fadd_rn(__fmul_rn((float)(zc0 + lz + 1), m.sd[2]), m.org[2]);
-            for (unsigned j0 = 0; j0 < ncorn; j0 += 32) {
-                const unsigned j = j0 + lane;
+            float* const op0 = outPos + gbase;
+            float* const on0 = outNrm + gbase;
+            const float ty0 = sh.tab[E_TAB_Y + ly], ty1 = sh.tab[E_TAB_Y + ly + 1];
+            const float tz0 = sh.tab[E_TAB_Z + lz], tz1 = sh.tab[E_TAB_Z + lz + 1];
+            const unsigned* etab = sh.edgeTab[rr];
+            for (unsigned j = lane; j < ncorn + lane; j += 32) { // trip count uniform over the warp (shuffles inside)
                 const bool act = j < ncorn;
                 const unsigned t = act ? j / 3 : 0;
-                const unsigned L = owner[t];
-                const unsigned oFirst = __shfl_sync(0xffffffffu, first, L);
+                const unsigned ok = owner[t];
+                const unsigned L = ok >> 3;
                 const unsigned oLo = __shfl_sync(0xffffffffu, wlo, L), oHi = __shfl_sync(0xffffffffu, whi, L);
                 if (!act) continue;
-                const unsigned slotc = 3 * (t - oFirst) + (j - 3 * t); // corner number inside the owner cell (0..14)
-                const int e = static_cast<int>(slotc < 8 ? (oLo >> (4 * slotc)) & 15u : (oHi >> (4 * (slotc - 8))) & 15u);
-                const unsigned code = edgeCode(e);
-                const int dz = (code >> 2) & 1;
-                const int ix = (int)L + (code & 1), iy = ly + ((code >> 1) & 1), iz = lz + dz;
-                const int axis = code >> 3;
-                const int eidx = edgeIndex(axis, ix, iy, iz);
+                const unsigned slotc = 3 * (ok & 7u) + (j - 3 * t); // corner number inside the owner cell (0..14)
+                const unsigned e = ((slotc < 8 ? oLo : oHi) >> ((4 * slotc) & 31u)) & 15u;
+                const unsigned ent = etab[e];
+                const unsigned eidx = (ent & 0xfffu) + L;
                 const float4 v = sh.edge[eidx];
-                const float px = axis == 0 ? v.x : sh.tabX[ix];
-                const float py = axis == 1 ? v.x : sh.tabY[iy];
-                const float pz = axis == 2 ? v.x : (dz ? tz1 : tz0);
-                float* op = outPos + gbase + static_cast<size_t>(j) * 3;
-                float* on = outNrm + gbase + static_cast<size_t>(j) * 3;
+                float px = sh.tab[L + ((ent & ET_DX) ? 1 : 0)];
+                float py = (ent & ET_DY) ? ty1 : ty0;
+                float pz = (ent & ET_DZ) ? tz1 : tz0;
+                if (ent & ET_AX0) px = v.x;
+                if (ent & ET_AX1) py = v.x;
+                if (ent & ET_AX2) pz = v.x;
+                float* op = op0 + j * 3;
+                float* on = on0 + j * 3;
                 op[0] = px, op[1] = py, op[2] = pz;
                 on[0] = v.y, on[1] = v.z, on[2] = v.w;
                 if (COLOUR) {
                     const float4 cc = edgeCol[eidx];
-                    float* oc = outCol + gbase + static_cast<size_t>(j) * 3;
+                    float* oc = outCol + gbase + j * 3;
                     oc[0] = cc.x, oc[1] = cc.y, oc[2] = cc.z;
                 }
             }
             __syncwarp();
         }
     }
-    asm volatile("cp.async.wait_group 0;");
+    if (pending) waitPlanes(); // never leave a bulk copy in flight into a dying block's shared memory
 }
 
 } // namespace mms

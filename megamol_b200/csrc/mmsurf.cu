@@ -294,6 +294,31 @@ __global__ void __launch_bounds__(256) normalize_state_kernel(float* __restrict_
         vol[i] = __fmul_rn(__fsub_rn(vol[i], mn), rcp);
 }
 
+
+size_t emitSmemBytes(bool colour) { return sizeof(McEmitShared) + 128 + (colour ? E_EDGES * sizeof(float4) : 0); }
+
+/** 3-D TMA descriptor over the slab volume (x fastest), box = one 40 x 11 plane tile of mc_emit_kernel.  Returns false where TMA's
+ *  rules do not hold (row pitch not a multiple of 16 bytes) or the driver entry point is missing: the kernel's cp.async variant runs. */
+bool makeVolumeTensorMap(CUtensorMap* map, const float* vol, int sx, int sy, int nz) {
+    using Encode = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+        const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static Encode encode = [] {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q{};
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            fn = nullptr;
+        }
+        return reinterpret_cast<Encode>(fn);
+    }();
+    if (!encode || sx % 4 != 0 || (reinterpret_cast<uintptr_t>(vol) & 15u) || getenv("MMS_NO_TMA")) return false;
+    const cuuint64_t dims[3] = {static_cast<cuuint64_t>(sx), static_cast<cuuint64_t>(sy), static_cast<cuuint64_t>(nz)};
+    const cuuint64_t strides[2] = {static_cast<cuuint64_t>(sx) * 4, static_cast<cuuint64_t>(sx) * sy * 4};
+    const cuuint32_t box[3] = {EPITCH, EHY, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(vol), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 } // namespace
 
 extern "C" {
@@ -344,8 +369,10 @@ int mms_create(mms_ctx** out, const mms_config* cfg) {
     c->params.gausslim = 3.0f;
     cudaFuncSetAttribute(density_splat_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SplatShared));
     cudaFuncSetAttribute(density_splat_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SplatShared));
-    cudaFuncSetAttribute(mc_emit_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(McEmitShared) + 16);
-    cudaFuncSetAttribute(mc_emit_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(McEmitShared) + 16 + E_EDGES * sizeof(float4)));
+    cudaFuncSetAttribute(mc_emit_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)emitSmemBytes(false));
+    cudaFuncSetAttribute(mc_emit_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)emitSmemBytes(false));
+    cudaFuncSetAttribute(mc_emit_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)emitSmemBytes(true));
+    cudaFuncSetAttribute(mc_emit_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)emitSmemBytes(true));
     if (!c->dstate.ensure(sizeof(DevState)) || !c->hState.ensure(sizeof(DevState))) {
         g_createError = "allocation of the state block failed";
         delete c;
@@ -800,7 +827,8 @@ int mms_count_isosurface(mms_ctx* c, float iso, uint64_t* ntris) {
         tri = c->triCount.as<unsigned char>();
     }
     cudaStream_t st = c->stream;
-    dim3 grid(m.nsegx, (m.cy + (MC_THREADS / 32) * MCC_ROWS - 1) / ((MC_THREADS / 32) * MCC_ROWS), (m.cnz + MCC_LAYERS - 1) / MCC_LAYERS);
+    if (tri) MMS_CUDA(c, cudaMemsetAsync(tri, 0, static_cast<size_t>(m.cx) * m.cy * m.cnz, st)); // the kernel writes the non-empty cells only
+    dim3 grid((m.nsegx + CN_SEGS - 1) / CN_SEGS, (m.cy + CN_ROWS - 1) / CN_ROWS, (m.cnz + CN_LAYERS - 1) / CN_LAYERS);
     mc_count_kernel<<<grid, MC_THREADS, 0, st>>>(m, c->vol.as<float>(), c->segCount.as<unsigned>(), tri);
     ++c->launches;
     DevState* ds = c->dstate.as<DevState>();
@@ -837,12 +865,17 @@ int mms_emit_isosurface(mms_ctx* c, float* pos, float* nrm, float* col, uint64_t
         }
         dim3 gridE(m.nsegx, (m.cy + EY - 1) / EY, (m.cnz + EM_STEPS * EZ - 1) / (EM_STEPS * EZ));
         c->rec(EV_EMIT0);
-        if (c->haveColour)
-            mc_emit_kernel<true><<<gridE, MC_THREADS, sizeof(McEmitShared) + 16 + E_EDGES * sizeof(float4), st>>>(m, c->vol.as<float>(),
-                c->rgb.as<float>(), c->segOffset.as<unsigned>(), P, N, C);
-        else
-            mc_emit_kernel<false><<<gridE, MC_THREADS, sizeof(McEmitShared) + 16, st>>>(m, c->vol.as<float>(), nullptr,
-                c->segOffset.as<unsigned>(), P, N, nullptr);
+        CUtensorMap map{};
+        const bool tma = makeVolumeTensorMap(&map, c->vol.as<float>(), m.sx, m.sy, m.nzPlanes);
+        const float* V = c->vol.as<float>();
+        const unsigned* S = c->segOffset.as<unsigned>();
+        if (c->haveColour) {
+            if (tma) mc_emit_kernel<true, true><<<gridE, MC_THREADS, emitSmemBytes(true), st>>>(m, map, V, c->rgb.as<float>(), S, P, N, C);
+            else mc_emit_kernel<true, false><<<gridE, MC_THREADS, emitSmemBytes(true), st>>>(m, map, V, c->rgb.as<float>(), S, P, N, C);
+        } else {
+            if (tma) mc_emit_kernel<false, true><<<gridE, MC_THREADS, emitSmemBytes(false), st>>>(m, map, V, nullptr, S, P, N, nullptr);
+            else mc_emit_kernel<false, false><<<gridE, MC_THREADS, emitSmemBytes(false), st>>>(m, map, V, nullptr, S, P, N, nullptr);
+        }
         ++c->launches;
     }
     c->rec(EV_MC1);
