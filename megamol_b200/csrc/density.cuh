@@ -242,6 +242,7 @@ __global__ void __launch_bounds__(CT_THREADS, 4) density_splat_kernel(Geo g, Dev
             {
                 const int cnt = filled;
                 int myL0x = 0, myL0y = 0, myL0z = 0; // per-voxel-wrap mode only: tile-local box origin before wrapping
+                bool myLive = false;                 // my particle reaches the tile
                 if (lane < cnt) {
                     // ---- digest my particle -------------------------------------------------------------------
                     const float4 p = recs[src];
@@ -315,14 +316,17 @@ __global__ void __launch_bounds__(CT_THREADS, 4) density_splat_kernel(Geo g, Dev
                         d.mask27 = m;
                     }
                     myDig[lane] = d;
+                    myLive = d.dims != 0u;
                 }
                 __syncwarp();
-                for (int j = 0; j < cnt; ++j) {
+                // particles of the ring cells mostly do not reach the tile: walk the non-empty digests only (ascending = canonical order)
+                const unsigned live = __ballot_sync(0xffffffffu, myLive);
+                for (unsigned rest = live; rest; rest &= rest - 1) {
+                    const int j = __ffs(rest) - 1;
                     const float4 A = reinterpret_cast<const float4*>(&myDig[j])[0];
                     const float4 B = reinterpret_cast<const float4*>(&myDig[j])[1];
                     const float4 Cc = reinterpret_cast<const float4*>(&myDig[j])[2];
                     const unsigned dims = __float_as_uint(Cc.z), mask27 = __float_as_uint(Cc.w);
-                    if (dims == 0u) continue;
                     const int sbase = __float_as_int(Cc.y);
                     if (mask27 != 0u && !anyPv) {
                         // ---- fast path: box <= 3x3x3, one pass, fixed lane pattern ------------------------------------

@@ -85,22 +85,21 @@ __global__ void __launch_bounds__(MC_THREADS) mc_count_kernel(McGeo m, const flo
     // one node plane -> mask words (nodes beyond the grid are clamped copies: they never make a valid cell look different)
     auto planeMasks = [&](int zNode, int buf) {
         const float* p = vol + plane * (zNode - m.zPlane0);
-        constexpr int ITEMS = CN_NROWS * CN_SEGS; // 272 (row, segment) words
-        constexpr int U = 8;                      // loads in flight per lane
-        for (int it0 = warp; it0 < ITEMS; it0 += U * (MC_THREADS / 32)) {
-            float v[U];
+        // warp w converts segments w and w+8 of every node row: 2 x 17 words, 6 x 6 loads in flight
+        const int xa = min((seg0 + warp) * 32 + lane, m.sx - 1), xb = min((seg0 + warp + 8) * 32 + lane, m.sx - 1);
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int it = it0 + u * (MC_THREADS / 32);
-                const int r = it / CN_SEGS, s = it % CN_SEGS;
-                const int y = min(yBeg + r, m.sy - 1), x = min((seg0 + s) * 32 + lane, m.sx - 1);
-                v[u] = it < ITEMS ? p[static_cast<size_t>(m.sx) * y + x] : 0.0f;
+        for (int r0 = 0; r0 < CN_NROWS; r0 += 3) {
+            float va[3], vb[3];
+#pragma unroll
+            for (int u = 0; u < 3; ++u) {
+                const float* row = p + static_cast<size_t>(m.sx) * min(yBeg + r0 + u, m.sy - 1);
+                va[u] = r0 + u < CN_NROWS ? row[xa] : 0.0f;
+                vb[u] = r0 + u < CN_NROWS ? row[xb] : 0.0f;
             }
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int it = it0 + u * (MC_THREADS / 32);
-                const unsigned b = __ballot_sync(0xffffffffu, v[u] < m.iso);
-                if (lane == 0 && it < ITEMS) sMask[buf][it / CN_SEGS][it % CN_SEGS] = b;
+            for (int u = 0; u < 3; ++u) {
+                const unsigned ba = __ballot_sync(0xffffffffu, va[u] < m.iso), bb = __ballot_sync(0xffffffffu, vb[u] < m.iso);
+                if (lane == 0 && r0 + u < CN_NROWS) sMask[buf][r0 + u][warp] = ba, sMask[buf][r0 + u][warp + 8] = bb;
             }
         }
         // the node column after the block's last segment (bit 0 of word CN_SEGS)
@@ -197,6 +196,11 @@ __host__ __device__ __forceinline__ unsigned edgeCode(int e) {
 // flags of an edgeTab entry (bits 0..11 = edge slot of the row's cell 0)
 constexpr unsigned ET_AX0 = 1u << 12, ET_AX1 = 1u << 13, ET_AX2 = 1u << 14, ET_DX = 1u << 15, ET_DY = 1u << 16, ET_DZ = 1u << 17;
 
+__device__ __forceinline__ float rcpApproxF(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ unsigned smemAddr(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
 
 __device__ __forceinline__ void cpAsync4(float* smemDst, const float* gmemSrc) {
@@ -441,7 +445,10 @@ __global__ void __launch_bounds__(MC_THREADS) mc_emit_kernel(McGeo m, const __gr
                 }
             };
             const float fa = sh.ring[planeOff(hzA) + offA], fb = sh.ring[planeOff(hzB) + offB];
-            const float t01 = __fdiv_rn(__fsub_rn(iso, fa), __fsub_rn(fb, fa));
+            // t = (iso - fa) / (fb - fa): SFU reciprocal (2 ulp; vertices are compared at 1e-4 of a cell); the IEEE division only
+            // where the difference is too small for rcp.approx
+            const float tnum = __fsub_rn(iso, fa), tden = __fsub_rn(fb, fa);
+            const float t01 = fabsf(tden) > 1e-30f ? __fmul_rn(tnum, rcpApproxF(tden)) : __fdiv_rn(tnum, tden);
             const int ti = axis == 0 ? ix : (axis == 1 ? E_TAB_Y + r : E_TAB_Z + p);
             const float pa = sh.tab[ti], pb = sh.tab[ti + 1];
             float gax, gay, gaz, gbx, gby, gbz;
@@ -501,12 +508,13 @@ __global__ void __launch_bounds__(MC_THREADS) mc_emit_kernel(McGeo m, const __gr
             const unsigned wlo = static_cast<unsigned>(word >> 4), whi = static_cast<unsigned>(word >> 36); // 15 nibbles of edge ids
             const unsigned ncorn = segTris * 3;
             const size_t gbase = static_cast<size_t>(segOff) * 9;
-            float* const op0 = outPos + gbase;
-            float* const on0 = outNrm + gbase;
+            float* op = outPos + gbase + lane * 3; // this lane's corner of the current round; 32 corners = 96 floats per round
+            float* on = outNrm + gbase + lane * 3;
+            float* oc = COLOUR ? outCol + gbase + lane * 3 : nullptr;
             const float ty0 = sh.tab[E_TAB_Y + ly], ty1 = sh.tab[E_TAB_Y + ly + 1];
             const float tz0 = sh.tab[E_TAB_Z + lz], tz1 = sh.tab[E_TAB_Z + lz + 1];
             const unsigned* etab = sh.edgeTab[rr];
-            for (unsigned j = lane; j < ncorn + lane; j += 32) { // trip count uniform over the warp (shuffles inside)
+            for (unsigned j = lane; j < ncorn + lane; j += 32, op += 96, on += 96) { // trip count uniform over the warp (shuffles inside)
                 const bool act = j < ncorn;
                 const unsigned t = act ? j / 3 : 0;
                 const unsigned ok = owner[t];
@@ -524,14 +532,12 @@ __global__ void __launch_bounds__(MC_THREADS) mc_emit_kernel(McGeo m, const __gr
                 if (ent & ET_AX0) px = v.x;
                 if (ent & ET_AX1) py = v.x;
                 if (ent & ET_AX2) pz = v.x;
-                float* op = op0 + j * 3;
-                float* on = on0 + j * 3;
                 op[0] = px, op[1] = py, op[2] = pz;
                 on[0] = v.y, on[1] = v.z, on[2] = v.w;
                 if (COLOUR) {
                     const float4 cc = edgeCol[eidx];
-                    float* oc = outCol + gbase + j * 3;
-                    oc[0] = cc.x, oc[1] = cc.y, oc[2] = cc.z;
+                    float* o = oc + (j - lane) * 3;
+                    o[0] = cc.x, o[1] = cc.y, o[2] = cc.z;
                 }
             }
             __syncwarp();
