@@ -21,6 +21,7 @@
 #pragma once
 #include "common.cuh"
 #include "scan.cuh"
+#include <type_traits>
 
 namespace mms {
 
@@ -43,9 +44,20 @@ struct Dig {
     unsigned mask27;            // fast path (all dims <= 3): valid lanes of the fixed 3x3x3 lane pattern
 };
 
-struct SplatShared {
+constexpr int CT_HITCAP = 768;                       // V2: (particle, voxel) pairs one warp expands at a time (32 particles x 27 worst case = 864: a second pass)
+
+struct SplatWarpV1 {
+    Dig dig[32];
+};
+struct SplatWarpV2 {
+    unsigned short hits[CT_HITCAP];                  // (lane of the particle << 5) | voxel number 0..26 inside its 3x3x3 box, in summation order
+};
+
+template<class WARPSTORE>
+struct SplatSharedT {
     float tile[CT_FLOATS];
-    Dig dig[CT_WARPS][32];
+    WARPSTORE ws[CT_WARPS];
+    float4 lut[27];                    // V2: voxel number -> (ix, iy, iz as floats, tile offset as int bits)
     unsigned cellB[CT_MAXCELLS];
     unsigned short cellN[CT_MAXCELLS]; // particles in the cell (a cell with more than 65535 particles is split by the host guard)
     int axisCells[3][CT_MAXAXIS];
@@ -59,6 +71,9 @@ struct SplatShared {
     int tl0[3], tl1[3];            // tile voxel range (inclusive), clipped to the grid / slab
     int perVoxelWrap[3];           // degenerate cyclic axis: wrap every voxel instead of choosing one image per particle
 };
+using SplatShared = SplatSharedT<SplatWarpV1>;
+using SplatShared2 = SplatSharedT<SplatWarpV2>;
+static_assert(sizeof(SplatShared) <= 57088 && sizeof(SplatShared2) <= 57088, "density_splat_kernel must fit four blocks per SM");
 
 /** Ordered, duplicate-free list of the cells along one axis whose particles can reach voxels [t0, t1]. */
 __device__ inline int buildAxisCells(int t0, int t1, int reach, int s, bool cyc, int sh, int nc, int* out, int cap) {
@@ -132,15 +147,28 @@ __device__ __forceinline__ bool kernelValue(float d2, float eps, float k0, float
     }
 }
 
-template<int MODE>
+/**
+ * V2 (host-selected: bump mode, aggregator 0, every support box <= 3x3x3 voxels, no per-voxel wrap) replaces the per-particle walk by
+ *   A  lane = particle: the 9 per-axis squared offsets once, the 27 squared distances by two additions each, a 27-bit hit mask
+ *      (inclusive pre-test d2 < eps^2 (1 + 1e-6); the exact reference test follows in B)
+ *   B  the set bits of all 32 masks are expanded into ONE list in (particle, voxel) order and the lanes walk that list: every lane
+ *      evaluates a real hit (sqrt, rcp, ex2).  Hits of one round that fall on the same voxel are applied in list order
+ *      (match.any + rank), so every voxel still receives its contributions in the canonical order: bit-identical to V1.
+ */
+template<int MODE, bool V2>
 __global__ void __launch_bounds__(CT_THREADS, 4) density_splat_kernel(Geo g, DevState* st, const float4* __restrict__ recs,
     const float* __restrict__ aux, int auxN, const unsigned* __restrict__ cellStart, float* __restrict__ vol, int reach) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
-    SplatShared& sh = *reinterpret_cast<SplatShared*>(smemRaw);
+    using Shared = SplatSharedT<typename std::conditional<V2, SplatWarpV2, SplatWarpV1>::type>;
+    Shared& sh = *reinterpret_cast<Shared*>(smemRaw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int C = 1 << g.cshift;
     for (int i = tid; i < CT_FLOATS; i += CT_THREADS) sh.tile[i] = 0.0f;
     if (tid < 64) sh.phaseCount[tid] = 0;
+    if (V2 && tid < 27) {
+        const int ix = tid % 3, iy = (tid / 3) % 3, iz = tid / 9;
+        sh.lut[tid] = make_float4((float)ix, (float)iy, (float)iz, __int_as_float(ix + iy * CT_SY + iz * CT_SZ));
+    }
     if (tid < 3) {
         const int a = tid;
         const int t0 = (a == 0 ? (int)blockIdx.x * CT_X : a == 1 ? (int)blockIdx.y * CT_Y : g.z0 + (int)blockIdx.z * CT_Z);
@@ -219,7 +247,7 @@ __global__ void __launch_bounds__(CT_THREADS, 4) density_splat_kernel(Geo g, Dev
     const bool pvx = sh.perVoxelWrap[0] != 0, pvy = sh.perVoxelWrap[1] != 0, pvz = sh.perVoxelWrap[2] != 0;
     const bool anyPv = pvx | pvy | pvz;
     const float isdx = __frcp_rn(g.sd[0]), isdy = __frcp_rn(g.sd[1]), isdz = __frcp_rn(g.sd[2]);
-    Dig* myDig = sh.dig[warp];
+    auto& myStore = sh.ws[warp];
 
     for (int phase = 0; phase < nphase; ++phase) {
         const int pBeg = sh.phaseStart[phase], pEnd = sh.phaseStart[phase + 1];
@@ -243,6 +271,7 @@ __global__ void __launch_bounds__(CT_THREADS, 4) density_splat_kernel(Geo g, Dev
                 const int cnt = filled;
                 int myL0x = 0, myL0y = 0, myL0z = 0; // per-voxel-wrap mode only: tile-local box origin before wrapping
                 bool myLive = false;                 // my particle reaches the tile
+                Dig dg{};                            // V2: my digested particle stays in registers
                 if (lane < cnt) {
                     // ---- digest my particle -------------------------------------------------------------------
                     const float4 p = recs[src];
@@ -315,17 +344,93 @@ __global__ void __launch_bounds__(CT_THREADS, 4) density_splat_kernel(Geo g, Dev
                         }
                         d.mask27 = m;
                     }
-                    myDig[lane] = d;
+                    if constexpr (!V2) myStore.dig[lane] = d;
                     myLive = d.dims != 0u;
+                    if constexpr (V2) {
+                        if (myLive && d.mask27 == 0u) st->pad[0] = 4u, myLive = false; // the host promised boxes <= 3x3x3
+                        dg = d;
+                    }
                 }
                 __syncwarp();
+                if constexpr (V2) {
+                    // ---- A: hit mask of my particle ---------------------------------------------------------------------
+                    unsigned hm = 0u;
+                    if (myLive) {
+                        const float lim = __fmul_rn(__fmul_rn(dg.eps, dg.eps), 1.000001f);
+                        float qx[3], qy[3], qz[3];
+#pragma unroll
+                        for (int i = 0; i < 3; ++i) {
+                            const float dx = __fsub_rn(__fadd_rn(__fmul_rn(dg.f0x + (float)i, g.sd[0]), g.mn[0]), dg.x);
+                            const float dy = __fsub_rn(__fadd_rn(__fmul_rn(dg.f0y + (float)i, g.sd[1]), g.mn[1]), dg.y);
+                            const float dz = __fsub_rn(__fadd_rn(__fmul_rn(dg.f0z + (float)i, g.sd[2]), g.mn[2]), dg.z);
+                            qx[i] = __fmul_rn(dx, dx), qy[i] = __fmul_rn(dy, dy), qz[i] = __fmul_rn(dz, dz);
+                        }
+#pragma unroll
+                        for (int j = 0; j < 3; ++j)
+#pragma unroll
+                            for (int i = 0; i < 3; ++i) {
+                                const float sxy = __fadd_rn(qx[i], qy[j]);
+#pragma unroll
+                                for (int k = 0; k < 3; ++k)
+                                    if (__fadd_rn(sxy, qz[k]) < lim) hm |= 1u << (i + 3 * j + 9 * k);
+                            }
+                        hm &= dg.mask27;
+                    }
+                    const unsigned hcnt = __popc(hm);
+                    const unsigned incl = warpInclusiveScan(hcnt), excl = incl - hcnt;
+                    const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+                    unsigned done = 0;
+                    int first = 0;
+                    while (done < total) {
+                        // the particles [first, last] whose hits fit the list together (a particle has <= 27 of them)
+                        const bool in = lane >= first && incl - done <= (unsigned)CT_HITCAP;
+                        const unsigned bal = __ballot_sync(0xffffffffu, in);
+                        const int last = 31 - __clz(bal);
+                        const unsigned nh = __shfl_sync(0xffffffffu, incl, last) - done;
+                        if (in) {
+                            unsigned pos = excl - done;
+                            for (unsigned mm = hm; mm; mm &= mm - 1) myStore.hits[pos++] = static_cast<unsigned short>(lane << 5 | (__ffs(mm) - 1));
+                        }
+                        __syncwarp();
+                        // ---- B: lanes = hits ------------------------------------------------------------------------------
+                        for (unsigned h0 = 0; h0 < nh; h0 += 32) {
+                            const unsigned h = h0 + lane;
+                            const bool act = h < nh;
+                            const unsigned code = act ? myStore.hits[h] : 0u;
+                            const int pl = code >> 5;
+                            const float px = __shfl_sync(0xffffffffu, dg.x, pl), py = __shfl_sync(0xffffffffu, dg.y, pl), pz = __shfl_sync(0xffffffffu, dg.z, pl);
+                            const float eps = __shfl_sync(0xffffffffu, dg.eps, pl), k0 = __shfl_sync(0xffffffffu, dg.k0, pl);
+                            const float f0x = __shfl_sync(0xffffffffu, dg.f0x, pl), f0y = __shfl_sync(0xffffffffu, dg.f0y, pl), f0z = __shfl_sync(0xffffffffu, dg.f0z, pl);
+                            const int sb = __shfl_sync(0xffffffffu, dg.base, pl);
+                            const float4 L = sh.lut[code & 31u];
+                            const float vx = __fadd_rn(__fmul_rn(f0x + L.x, g.sd[0]), g.mn[0]);
+                            const float vy = __fadd_rn(__fmul_rn(f0y + L.y, g.sd[1]), g.mn[1]);
+                            const float vz = __fadd_rn(__fmul_rn(f0z + L.z, g.sd[2]), g.mn[2]);
+                            const float dx = __fsub_rn(vx, px), dy = __fsub_rn(vy, py), dz = __fsub_rn(vz, pz);
+                            const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+                            float w = 0.0f;
+                            const bool hit = act && kernelValue<MODE>(d2, eps, k0, w);
+                            const int addr = sb + __float_as_int(L.w);
+                            // hits of this round on the same voxel: list order = canonical order
+                            const unsigned grp = __match_any_sync(0xffffffffu, hit ? addr : -1 - lane);
+                            const int rank = __popc(grp & ((1u << lane) - 1u));
+                            const int maxRank = __reduce_max_sync(0xffffffffu, hit ? rank : 0);
+                            for (int r = 0; r <= maxRank; ++r) {
+                                if (hit && rank == r) sh.tile[addr] = __fadd_rn(sh.tile[addr], w);
+                                __syncwarp();
+                            }
+                        }
+                        done += nh;
+                        first = last + 1;
+                    }
+                } else {
                 // particles of the ring cells mostly do not reach the tile: walk the non-empty digests only (ascending = canonical order)
                 const unsigned live = __ballot_sync(0xffffffffu, myLive);
                 for (unsigned rest = live; rest; rest &= rest - 1) {
                     const int j = __ffs(rest) - 1;
-                    const float4 A = reinterpret_cast<const float4*>(&myDig[j])[0];
-                    const float4 B = reinterpret_cast<const float4*>(&myDig[j])[1];
-                    const float4 Cc = reinterpret_cast<const float4*>(&myDig[j])[2];
+                    const float4 A = reinterpret_cast<const float4*>(&myStore.dig[j])[0];
+                    const float4 B = reinterpret_cast<const float4*>(&myStore.dig[j])[1];
+                    const float4 Cc = reinterpret_cast<const float4*>(&myStore.dig[j])[2];
                     const unsigned dims = __float_as_uint(Cc.z), mask27 = __float_as_uint(Cc.w);
                     const int sbase = __float_as_int(Cc.y);
                     if (mask27 != 0u && !anyPv) {
@@ -378,6 +483,7 @@ __global__ void __launch_bounds__(CT_THREADS, 4) density_splat_kernel(Geo g, Dev
                     }
                     __syncwarp(); // the next particle of this cell may touch the same voxels from other lanes
                 }
+                } // !V2
                 __syncwarp();
             }
         }

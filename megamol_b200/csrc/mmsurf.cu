@@ -147,7 +147,7 @@ struct mms_ctx {
     unsigned long long ntris = 0;
     unsigned long long launches = 0;
     int cshift = 2, reach = 2;
-    bool useGather = false, haveColour = false;
+    bool useGather = false, haveColour = false, splatV2ok = false;
     McGeo mcGeo{};
     cudaStream_t ownStream = nullptr;
     DevBuf rangeBuf; // {-min, max} as floats for device-side all-reduce + normalise
@@ -367,8 +367,9 @@ int mms_create(mms_ctx** out, const mms_config* cfg) {
     c->params.normalize = 1;
     c->params.radscale = 1.0f;
     c->params.gausslim = 3.0f;
-    cudaFuncSetAttribute(density_splat_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SplatShared));
-    cudaFuncSetAttribute(density_splat_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SplatShared));
+    cudaFuncSetAttribute(density_splat_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SplatShared));
+    cudaFuncSetAttribute(density_splat_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SplatShared));
+    cudaFuncSetAttribute(density_splat_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SplatShared2));
     cudaFuncSetAttribute(mc_emit_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)emitSmemBytes(false));
     cudaFuncSetAttribute(mc_emit_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)emitSmemBytes(false));
     cudaFuncSetAttribute(mc_emit_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)emitSmemBytes(true));
@@ -586,6 +587,10 @@ int mms_compute_density(mms_ctx* c) {
         else if (need <= 4) c->cshift = 3;
         else c->cshift = 4;
         c->reach = need;
+        // tight support box = the integers of an interval of length 2 eps / sliceDist (+ rounding slop): at most 3 per axis?
+        c->splatV2ok = true;
+        for (int a = 0; a < 3; ++a)
+            if (!(2.0f * epsMax / g0.sd[a] < 2.95f)) c->splatV2ok = false;
     }
     const Geo g = makeGeo(c);
     for (ListDev& l : c->lists) { // global-radius lists: (int)ceil(rad / sliceDist) once on the host, same fp32 operations (:573-575)
@@ -647,11 +652,19 @@ int mms_compute_density(mms_ctx* c) {
         else density_gather_kernel<1, false><<<grid, GT_THREADS, 0, st>>>(g, DS, R, A, auxN, CS, c->vol.as<float>(), nullptr, c->reach);
     } else {
         dim3 grid((g.s[0] + CT_X - 1) / CT_X, (g.s[1] + CT_Y - 1) / CT_Y, (g.nz + CT_Z - 1) / CT_Z);
-        if (g.mode == 0)
-            density_splat_kernel<0><<<grid, CT_THREADS, sizeof(SplatShared), st>>>(g, c->dstate.as<DevState>(), c->recsB.as<float4>(),
+        // V2 (lanes walk a compacted hit list) where every support box is at most 3x3x3 voxels and one periodic image per particle is enough
+        bool v2 = g.mode == 0 && auxN == 0 && c->splatV2ok && !getenv("MMS_SPLAT_V1");
+        const int tileDim[3] = {CT_X, CT_Y, CT_Z};
+        for (int a = 0; a < 3; ++a)
+            if (g.cyc[a] && g.s[a] < tileDim[a] + 2 * c->reach + 2) v2 = false;
+        if (v2)
+            density_splat_kernel<0, true><<<grid, CT_THREADS, sizeof(SplatShared2), st>>>(g, c->dstate.as<DevState>(), c->recsB.as<float4>(),
+                c->auxB.as<float>(), auxN, c->cellStart.as<unsigned>(), c->vol.as<float>(), c->reach);
+        else if (g.mode == 0)
+            density_splat_kernel<0, false><<<grid, CT_THREADS, sizeof(SplatShared), st>>>(g, c->dstate.as<DevState>(), c->recsB.as<float4>(),
                 c->auxB.as<float>(), auxN, c->cellStart.as<unsigned>(), c->vol.as<float>(), c->reach);
         else
-            density_splat_kernel<1><<<grid, CT_THREADS, sizeof(SplatShared), st>>>(g, c->dstate.as<DevState>(), c->recsB.as<float4>(),
+            density_splat_kernel<1, false><<<grid, CT_THREADS, sizeof(SplatShared), st>>>(g, c->dstate.as<DevState>(), c->recsB.as<float4>(),
                 c->auxB.as<float>(), auxN, c->cellStart.as<unsigned>(), c->vol.as<float>(), c->reach);
     }
     c->haveColour = colour;
