@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- particles -> density volume -> isosurface throughput on N B200s (one process per GPU).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c1|c4]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c1|c3|c4|c5]
 
 Workload (BASELINE.json configs[1], SURVEY.md 8d "C2"): 10 M Lennard-Jones-fluid-like particles (jittered simple
 cubic lattice, rho* = 0.795, FLOAT_XYZ + global radius 0.5) -> 512^3 ParticlesToDensity volume (bump kernel,
@@ -45,6 +45,9 @@ def workload(name: str):
     if name == "c3":
         return dict(name="C3: 1M protein-like atoms (FLOAT_XYZR + FLOAT_RGBA, stride 32) -> 512^3 QuickSurf-Gaussian density + RGB volume "
                          "+ coloured MC surface (radscale 1, quality 2, iso 0.5)", n=1_000_000, res=(512, 512, 512), kind="protein")
+    if name == "c4":
+        return dict(name="C4: 100M LJ-fluid-like particles (465^3 lattice, r=0.5, cyclic, normalize) -> 1024^3 P2D bump + MC iso 0.5",
+                    n=100_000_000, res=(1024, 1024, 1024), kind="lj", lattice=465, fixed_total=True)
     raise SystemExit(f"unknown workload {name}")
 
 
@@ -188,11 +191,14 @@ def run_ours(args, w):
     launches = (job.launches() - launches0)
     stage = job.stage_times()
     # ---- end-to-end arm --------------------------------------------------------------------------------------
-    for _ in range(min(args.warmup, 3)):
-        job.step_e2e()
-    job.barrier()
     e2e_steps = max(1, min(args.steps, 5))
-    t_e2e = job.timed(job.step_e2e, e2e_steps)
+    if args.no_e2e:
+        t_e2e = float("nan")
+    else:
+        for _ in range(min(args.warmup, 3)):
+            job.step_e2e()
+        job.barrier()
+        t_e2e = job.timed(job.step_e2e, e2e_steps)
     if rank == 0:
         sampler.stop_flag.set()
         sampler.join(timeout=3)
@@ -204,20 +210,22 @@ def run_ours(args, w):
     value = n_total / (ms * 1e-3) / 1e6
     ms_e = t_e2e / e2e_steps
     e2e_val = n_total / (ms_e * 1e-3) / 1e6
+    e2e = {"value": e2e_val, "unit": "Mparticles/s", "ms_per_step": ms_e, "steps": e2e_steps,
+           "h2d_bytes_per_step": job.h2d_bytes(), "d2h_bytes_per_step": job.d2h_bytes()}
+    if args.no_e2e:
+        e2e = {"value": None, "unit": "Mparticles/s", "skipped": "--no-e2e", "h2d_bytes_per_step": job.h2d_bytes(), "d2h_bytes_per_step": job.d2h_bytes()}
     # roofline of the dominant kernel (largest share of the device step), algorithmic bytes per DESIGN.md
     rl = job.roofline(stage, peak)
     rl["peak_source"] = peak_src
     line = {"metric": METRIC, "value": value, "unit": "Mparticles/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "gvoxels_per_s": v_total / (ms * 1e-3) / 1e9,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if w.get("fixed_total") else "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "gvoxels_per_s": v_total / (ms * 1e-3) / 1e9,
             "config": {"workload": w["name"] if world == 1 else job.describe(), "particles": n_total, "voxels": v_total, "triangles": t_total,
                        "l2": "inputs (particles + volume + mesh) are larger than the 126 MB L2; no explicit flush",
                        "parallelism": f"z-slabs x{world}"},
             "stages_ms": stage, "roofline": rl,
             "pipeline_hbm_frac": job.pipeline_bytes() / (ms * 1e-3) / 1e9 / peak,
-            "e2e": {"value": e2e_val, "unit": "Mparticles/s", "ms_per_step": ms_e, "steps": e2e_steps,
-                    "h2d_bytes_per_step": job.h2d_bytes(), "d2h_bytes_per_step": job.d2h_bytes()},
-            "gpu_launches": launches, "clocks": sampler.summary()}
+            "e2e": e2e, "gpu_launches": launches, "clocks": sampler.summary()}
     if not args.no_cpu:
         cb = cpu_reference_sample()
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
@@ -284,6 +292,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end arm (host buffers): the C4 mesh is 84 GB of pinned host memory")
     ap.add_argument("--gather", default="host", choices=["host", "fused", "nccl"],
                     help="multi-GPU: where the per-slab meshes go: host (default; stay sharded in HBM, counts all-gathered, e2e copies each slab over its "
                          "own PCIe link), fused (mc_emit stores into rank 0's mesh over NVLink), nccl (send/recv to rank 0)")

@@ -27,7 +27,7 @@
 
 namespace mms {
 
-// word = ntri | edge0<<4 | edge1<<8 | ... (generated from the compiled reference table, oracle/tools/gen_mc_tables.py)
+// word = ntri | edge0<<4 | edge1<<8 | ... (mc_case_words.inc is generated from the compiled reference table)
 struct McCaseTable {
     unsigned long long w[256];
 };

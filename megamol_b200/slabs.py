@@ -149,6 +149,13 @@ class SlabJob:
             self.origin = tuple(float(v) for v in org)
             pad_ext = ext + 1.0
             self.box = tuple(float(v) for v in pad_ext)
+        elif w["kind"] == "lj" and w.get("fixed_total"):
+            # strong-scaling configuration (BASELINE configs[3]): the frame is fixed, the ranks share it
+            Lc = int(w["lattice"])
+            self.n_total = n1
+            a = np.float32(1.0794)
+            self.lat = (Lc, Lc, -(-self.n_total // (Lc * Lc)))
+            self.box = (float(np.float32(Lc) * a),) * 3
         elif w["kind"] == "lj":
             L1 = int(np.ceil(n1 ** (1 / 3) - 1e-9))
             self.n_total = n1 * world
@@ -513,6 +520,9 @@ class SlabJob:
                "nccl": "mesh gathered to rank 0 with NCCL send/recv",
                "host": "per-slab meshes stay in their GPU's HBM (counts all-gathered -> global offsets); e2e: every rank copies its slab "
                        "over its own PCIe link"}[self.gather]
+        if self.w.get("fixed_total"):
+            return (f"{self.w['name']} on {self.world} GPUs (strong scaling): {self.n_total} particles -> "
+                    f"{self.res[0]}x{self.res[1]}x{self.res[2]}, z-slabs with halo, particles exchanged with NCCL all-to-all-v, {how}")
         return (f"{self.w['name']} weak-scaled x{self.world} along z: {self.n_total} particles -> "
                 f"{self.res[0]}x{self.res[1]}x{self.res[2]}, z-slabs with halo, particles exchanged with NCCL all-to-all-v, {how}")
 

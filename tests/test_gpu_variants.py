@@ -1,0 +1,56 @@
+"""GPU: the kernel variants the host picks between must be interchangeable bit for bit.
+
+  * density_splat_kernel V2 (compacted hit list, chosen for supports of at most 3x3x3 voxels) vs V1 (per-particle walk)
+  * mc_emit_kernel with the TMA plane loader (x resolution a multiple of 4) vs the cp.async loader
+
+The environment switches are read by libmmsurf on every call (debug knobs, not part of the C ABI)."""
+import os
+
+import numpy as np
+import pytest
+
+import megamol_b200 as mm
+from megamol_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(xyz, box, res, cyclic, radius, iso, env):
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        s = mm.Surf(0)
+        s.set_grid((0, 0, 0), box, res, cyclic)
+        s.set_params(mode=0, aggregator=0, normalize=1, sigma=1.0)
+        s.push_particles([dict(vtx=xyz, vtx_type=1, count=len(xyz), global_radius=radius)])
+        s.compute_density()
+        vol = s.get_density().copy()
+        s.extract_isosurface(iso)
+        pos, nrm = s.get_mesh()
+        pos, nrm = pos.copy(), nrm.copy()
+        s.close()
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    return vol, pos, nrm
+
+
+CASES = [(150_000, (128, 96, 72), (True, True, True), 0.5), (60_000, (72, 45, 33), (False, True, False), 0.6),
+         (200_000, (96, 64, 40), (True, False, True), 0.45)]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[f"v{i}" for i in range(len(CASES))])
+def test_variants_bit_identical(case):
+    n, res, cyclic, radius = case
+    sd = 0.4563
+    box = tuple(float(np.float32(r - 1) * np.float32(sd)) for r in res)
+    xyz = synth.uniform_box(n, 1.0) * np.asarray(box, np.float32)
+    base = _run(xyz, box, res, cyclic, radius, 0.4, {})
+    assert base[1].shape[0] > 1000
+    for env in ({"MMS_SPLAT_V1": "1"}, {"MMS_NO_TMA": "1"}):
+        other = _run(xyz, box, res, cyclic, radius, 0.4, env)
+        assert np.array_equal(base[0].view(np.uint32), other[0].view(np.uint32)), f"density differs with {env}"
+        assert base[1].shape == other[1].shape and np.array_equal(base[1], other[1]) and np.array_equal(base[2], other[2]), f"mesh differs with {env}"
