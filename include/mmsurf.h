@@ -173,6 +173,8 @@ uint64_t mms_launch_count(const mms_ctx* ctx);
  * computes density planes [plane_lo[i], plane_hi[i]] (inclusive, halo planes included); a particle is copied to every slab its
  * support box touches (the reference's home voxel +- filter size, periodic images in cyclic z).  send_buf (device) receives the
  * raw records (list stride bytes each) grouped by slab, original order inside a group; counts[i] = records for slab i (host).
+ * A slab with plane_lo > plane_hi is switched off (count 0): a rank that keeps its own chunk in place switches its own slab off and
+ * extracts only what the OTHER slabs need from it.  Particles that can never contribute (non-finite, radius <= 0) are dropped.
  * Uses the grid and parameters of the context.  Synchronises once (the counts decide the all-to-all split sizes). */
 int mms_route_particles(mms_ctx* ctx, const mms_list* list, int32_t nslabs, const int32_t* plane_lo, const int32_t* plane_hi, void* send_buf,
     uint64_t capacity_records, uint64_t* counts);

@@ -1022,7 +1022,10 @@ int mms_route_particles(mms_ctx* c, const mms_list* list, int32_t nslabs, const 
     const Geo g = makeGeo(c);
     RouteGeo r{};
     r.zmin = g.mn[2], r.sdz = g.sd[2], r.sz = g.s[2], r.cyc = g.cyc[2], r.nslabs = nslabs;
-    for (int i = 0; i < nslabs; ++i) r.lo[i] = plane_lo[i], r.hi[i] = plane_hi[i];
+    for (int i = 0; i < nslabs; ++i) {
+        r.lo[i] = plane_lo[i], r.hi[i] = plane_hi[i];
+        if (plane_lo[i] <= plane_hi[i]) r.enabled |= 1u << i; // lo > hi switches a slab off (e.g. the caller's own)
+    }
     r.sigma = g.sigma, r.radscale = g.radscale, r.gausslim = g.gausslim, r.mode = g.mode;
     for (int i = 0; i < nslabs; ++i) counts[i] = 0;
     if (d.count == 0) return MMS_OK;
@@ -1030,7 +1033,7 @@ int mms_route_particles(mms_ctx* c, const mms_list* list, int32_t nslabs, const 
     const unsigned long long chunk = ((d.count + nwarps - 1) / nwarps + 31) / 32 * 32;
     const unsigned nent = nwarps * static_cast<unsigned>(nslabs);
     const unsigned ntiles = (nent + kScanTile - 1) / kScanTile;
-    if (!c->routeCounts.ensure(nent * 4) || !c->routeOffsets.ensure((nent + 1) * 4) || !c->routeTile.ensure(std::max(ntiles, 1u) * 4) ||
+    if (!c->routeCounts.ensure(nent * 4) || !c->routeOffsets.ensure((nent + 1 + kMaxSlabs + 1) * 4) || !c->routeTile.ensure(std::max(ntiles, 1u) * 4) ||
         !c->hRoute.ensure((nslabs + 1) * 4))
         return c->fail(MMS_ERR_NOMEM, "allocation failed (routing tables)");
     cudaStream_t st = c->stream;
@@ -1040,8 +1043,10 @@ int mms_route_particles(mms_ctx* c, const mms_list* list, int32_t nslabs, const 
     exclusiveScan(c->routeCounts.as<unsigned>(), c->routeOffsets.as<unsigned>(), nullptr, c->routeTile.as<unsigned>(), nent, nullptr, st, c->launches);
     // slab d starts at offsets[d * nwarps]; the grand total sits at offsets[nent]
     unsigned* h = c->hRoute.as<unsigned>();
-    for (int i = 0; i <= nslabs; ++i)
-        MMS_CUDA(c, cudaMemcpyAsync(h + i, c->routeOffsets.as<unsigned>() + static_cast<size_t>(i) * nwarps, 4, cudaMemcpyDeviceToHost, st));
+    unsigned* heads = c->routeOffsets.as<unsigned>() + nent + 1;
+    route_heads_kernel<<<1, 32, 0, st>>>(c->routeOffsets.as<unsigned>(), nwarps, nslabs, heads);
+    ++c->launches;
+    MMS_CUDA(c, cudaMemcpyAsync(h, heads, (nslabs + 1) * 4, cudaMemcpyDeviceToHost, st));
     MMS_CUDA(c, cudaStreamSynchronize(st));
     for (int i = 0; i < nslabs; ++i) counts[i] = h[i + 1] - h[i];
     if (h[nslabs] > capacity_records)

@@ -19,7 +19,8 @@ struct RouteGeo {
     float zmin, sdz;
     int sz, cyc;
     int nslabs;
-    int lo[kMaxSlabs], hi[kMaxSlabs]; // plane range [lo, hi] each slab computes (incl. its halo planes)
+    int lo[kMaxSlabs], hi[kMaxSlabs]; // plane range [lo, hi] each slab computes (incl. its halo planes); lo > hi: slab switched off
+    unsigned enabled;                 // bit d: slab d takes part
     float sigma, radscale, gausslim;
     int mode;
 };
@@ -31,11 +32,12 @@ __device__ __forceinline__ unsigned routeMask(const RouteGeo& r, const ListDev& 
     if (r.mode == 0) f = filterSize(p.w, r.sdz);
     else f = filterSize(r.gausslim * r.radscale * p.w, r.sdz) + 1;
     unsigned m = 0;
+    if (!(p.w > 0.0f) || !isfinite(p.w) || !isfinite(p.x) || !isfinite(p.y) || !isfinite(p.z)) return 0u; // never contributes (bin.cuh)
     if (!r.cyc) {
         for (int d = 0; d < r.nslabs; ++d)
             if (Z + f >= r.lo[d] && Z - f <= r.hi[d]) m |= 1u << d;
     } else if (2 * f + 1 >= r.sz) {
-        m = (1u << r.nslabs) - 1u;
+        m = r.enabled;
     } else {
         const int zw = (static_cast<unsigned>(Z) < static_cast<unsigned>(r.sz)) ? Z : floorMod(Z, r.sz);
         const int a = zw - f, b = zw + f;
@@ -44,7 +46,13 @@ __device__ __forceinline__ unsigned routeMask(const RouteGeo& r, const ListDev& 
             if ((b >= lo && a <= hi) || (b - r.sz >= lo && a - r.sz <= hi) || (b + r.sz >= lo && a + r.sz <= hi)) m |= 1u << d;
         }
     }
-    return m;
+    return m & r.enabled;
+}
+
+/** offsets[d * nwarps] for d = 0..nslabs (slab starts + grand total) -> one compact array: a single small D2H copy */
+__global__ void route_heads_kernel(const unsigned* __restrict__ offsets, unsigned nwarps, int nslabs, unsigned* __restrict__ heads) {
+    const int d = threadIdx.x;
+    if (d <= nslabs) heads[d] = offsets[static_cast<size_t>(d) * nwarps];
 }
 
 __global__ void __launch_bounds__(256) route_count_kernel(RouteGeo r, ListDev l, unsigned long long chunk, unsigned* __restrict__ counts,

@@ -245,21 +245,28 @@ class SlabJob:
         return ms
 
     def _exchange(self, xyz_dev):
-        """all-to-all-v of the particles by destination slab; returns this rank's [n,3] tensor (source-rank order).
-        The stable partition by destination is libmmsurf's routing kernel (mms_route_particles); torch only carries the bytes."""
+        """Halo exchange.  The rank's own chunk stays where it is (the binning kernel drops what does not reach the slab); only the records
+        OTHER slabs need are extracted (libmmsurf's routing kernels with the own slab switched off: mms_route_particles) and travel in one
+        all-to-all-v.  The canonical in-cell order makes the result independent of the order in which lists are pushed, so the pieces need
+        not be re-assembled in global particle order.  Host synchronisations: the routing counts, and the count matrix.
+        Returns the received records as one [n, k] tensor."""
         torch = self.torch
         import torch.distributed as dist
         n = xyz_dev.shape[0]
-        cap = n + n // 2 + 4096
+        cap = n + 4096
         if getattr(self, "_send", None) is None or self._send.shape[0] < cap:
             self._send = torch.empty((cap, xyz_dev.shape[1]), device=self.dev, dtype=torch.float32)
-        sc = self.surf.route_particles(xyz_dev.data_ptr(), n, self.slabs, self._send.data_ptr(), cap, global_radius=self.radius)
-        self.surf.synchronize()  # the scatter kernel ran on the library's stream
-        send_counts = torch.tensor(sc, device=self.dev, dtype=torch.int64)
-        recv_counts = torch.empty_like(send_counts)
-        dist.all_to_all_single(recv_counts, send_counts)
-        rc = recv_counts.tolist()
-        recv = torch.empty((sum(rc), xyz_dev.shape[1]), device=self.dev, dtype=torch.float32)
+        others = [dict(z0=1, nz=0) if g == self.rank else s for g, s in enumerate(self.slabs)]   # plane_lo > plane_hi: switched off
+        sc = self.surf.route_particles(xyz_dev.data_ptr(), n, others, self._send.data_ptr(), cap, global_radius=self.radius)
+        mine = torch.tensor(sc, device=self.dev, dtype=torch.int64)
+        if getattr(self, "_cmat", None) is None:
+            self._cmat = torch.empty((self.world, self.world), device=self.dev, dtype=torch.int64)
+        dist.all_gather_into_tensor(self._cmat, mine)
+        rc = self._cmat[:, self.rank].tolist()         # what every source sends to me
+        nrecv = sum(rc)
+        if getattr(self, "_recv", None) is None or self._recv.shape[0] < nrecv:
+            self._recv = torch.empty((nrecv + nrecv // 4 + 4096, xyz_dev.shape[1]), device=self.dev, dtype=torch.float32)
+        recv = self._recv[:nrecv]
         dist.all_to_all_single(recv, self._send[:sum(sc)], output_split_sizes=rc, input_split_sizes=sc)
         return recv
 
@@ -278,17 +285,25 @@ class SlabJob:
         self.last["gathered_verts"] = sum(counts)
 
     def _allgather_counts(self):
-        """mesh stays sharded: all-gather of the per-slab triangle counts -> every rank knows its offset in the frame's mesh"""
+        """mesh stays sharded: all-gather of the per-slab triangle counts -> every rank knows its offset in the frame's mesh.
+        The collective is only enqueued here; the host reads the counts when somebody asks for them (tri_counts())."""
         torch = self.torch
         import torch.distributed as dist
         nverts, _, _ = self.surf.mesh_device()
         cnt = torch.tensor([nverts // 3], device=self.dev, dtype=torch.int64)
-        allc = [torch.empty_like(cnt) for _ in range(self.world)]
-        dist.all_gather(allc, cnt)
-        counts = [int(c.item()) for c in allc]
-        self.last["tri_counts"] = counts
-        self.last["tri_offset"] = sum(counts[:self.rank])
+        if getattr(self, "_tcounts", None) is None:
+            self._tcounts = torch.empty((self.world,), device=self.dev, dtype=torch.int64)
+        dist.all_gather_into_tensor(self._tcounts, cnt)
+        self.last.pop("tri_counts", None)
         self.last["gathered_verts"] = 0
+
+    def tri_counts(self):
+        """per-slab triangle counts of the last step (host list; synchronises if they are still on the device)"""
+        if "tri_counts" not in self.last:
+            counts = self._tcounts.tolist()
+            self.last["tri_counts"] = counts
+            self.last["tri_offset"] = sum(counts[:self.rank])
+        return self.last["tri_counts"]
 
     # ---- fused emit + gather -------------------------------------------------------------------------------------
     def _emit_to_root(self):
@@ -354,13 +369,14 @@ class SlabJob:
             self._gnrm = _tensor_from_ptr(torch, R["nrm"], total * 9, self.dev)
 
     # ---- steps ------------------------------------------------------------------------------------------------
-    def _compute(self, xyz_ptr, n, extract=True):
+    def _compute(self, xyz_ptr, n, extract=True, more=()):
+        """more: further (device pointer, count) pieces of the frame (the received halo)"""
         s = self.surf
         s.clear_particles()
         if self.protein:  # x y z r | R G B A interleaved, stride 32 (FLOAT_XYZR + FLOAT_RGBA)
             s.push_particles([dict(vtx=xyz_ptr, vtx_type=2, vtx_stride=32, count=n, col=xyz_ptr + 16, col_type=4, col_stride=32)])
         else:
-            s.push_particles([dict(vtx=xyz_ptr, vtx_type=1, count=n, global_radius=self.radius)])
+            s.push_particles([dict(vtx=p, vtx_type=1, count=c, global_radius=self.radius) for p, c in ((xyz_ptr, n),) + tuple(more) if c > 0])
         s.compute_density()
         if self.world > 1 and self.normalize:
             # global range with ONE max-all-reduce of {-min, max}, in place on the library's device buffer: no host round trip
@@ -379,15 +395,14 @@ class SlabJob:
             self._compute(self.d_xyz.data_ptr(), self.n_local)
             self.surf.synchronize()
         else:
+            # the library runs on torch's current stream (set_stream): everything below is stream-ordered, the host only waits where a
+            # size decides an allocation (routing counts, count matrix, triangle count)
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
             ev[0].record()
             recv = self._exchange(self.d_xyz)
             ev[1].record()
-            torch.cuda.current_stream().synchronize()
-            self._keep = [recv]
             fused = self.gather == "fused"
-            self._compute(recv.data_ptr(), recv.shape[0], extract=not fused)
-            self.surf.synchronize()
+            self._compute(self.d_xyz.data_ptr(), self.n_local, extract=not fused, more=((recv.data_ptr(), recv.shape[0]),))
             ev[2].record()
             if fused:
                 self._emit_to_root()
@@ -411,12 +426,10 @@ class SlabJob:
             self.surf.get_mesh(copy=False, colours=self.protein)
         else:
             d = self.h_xyz.to(self.dev, non_blocking=True)
-            torch.cuda.current_stream().synchronize()  # the routing kernel runs on the library's stream
             recv = self._exchange(d)
-            torch.cuda.current_stream().synchronize()
-            self._keep = [recv, d]
+            self._keep = [d]
             fused = self.gather == "fused"
-            self._compute(recv.data_ptr(), recv.shape[0], extract=not fused)
+            self._compute(d.data_ptr(), self.n_local, extract=not fused, more=((recv.data_ptr(), recv.shape[0]),))
             self.surf.get_density(copy=False)
             if fused:
                 self._emit_to_root()

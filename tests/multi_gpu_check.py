@@ -53,11 +53,12 @@ def main():
             p = gp.view(-1)[:ntri * 9].cpu().numpy().reshape(-1, 3, 3)
             q = gn.view(-1)[:ntri * 9].cpu().numpy().reshape(-1, 3, 3)
             ev, ep, en = np.array_equal(v.view(np.uint32), ref.view(np.uint32)), np.array_equal(p, rpos), np.array_equal(q, rnrm)
-            total = sum(job.last["tri_counts"])
+            counts = job.tri_counts() if gather == "host" else job.last["tri_counts"]
+            total = sum(counts)
             good = ev and ep and en and total == ntri and ntri > 10000
             if not good:
                 print(f"   volume equal {ev} (max abs diff {np.abs(v - ref).max():.3e}, differing planes {np.unique(np.argwhere(v != ref)[:, 0])[:12]}), "
-                      f"pos equal {ep}, nrm equal {en}, counts {job.last['tri_counts']} total {total} vs {ntri}", flush=True)
+                      f"pos equal {ep}, nrm equal {en}, counts {counts} total {total} vs {ntri}", flush=True)
             print(f"[multi_gpu_check] gather={gather} world={world} triangles={ntri} -> {'OK' if good else 'MISMATCH'}", flush=True)
             ok = ok and good
         job.close_keep_group() if hasattr(job, "close_keep_group") else None
