@@ -251,24 +251,26 @@ __global__ void __launch_bounds__(CT_THREADS, 4) density_splat_kernel(Geo g, Dev
 
     for (int phase = 0; phase < nphase; ++phase) {
         const int pBeg = sh.phaseStart[phase], pEnd = sh.phaseStart[phase + 1];
-        // this warp's cells of the phase: pBeg + warp, + CT_WARPS, ...  A chunk = up to 32 particles from consecutive
-        // cells of that sequence (a cell may continue in the next chunk); particles are then walked in sequence order.
-        int cur = pBeg + warp;
-        unsigned curOff = 0;
-        while (cur < pEnd) {
-            int filled = 0;
-            unsigned src = 0xffffffffu;
-            while (filled < 32 && cur < pEnd) {
-                const int ci = sh.phaseCells[cur];
-                const unsigned b = sh.cellB[ci] + curOff, e = sh.cellB[ci] + sh.cellN[ci];
-                const int take = min(32 - filled, (int)(e - b));
-                if (lane >= filled && lane < filled + take) src = b + (lane - filled);
-                filled += take;
-                if (b + take == e) { cur += CT_WARPS; curOff = 0; }
-                else curOff += take;
+        // this warp's cells of the phase: pBeg + warp, + CT_WARPS, ...  (32 of them at a time, one per lane).  The particles of that
+        // cell sequence are numbered by a warp scan of the cell sizes; a chunk = 32 consecutive particles of the sequence (a cell may
+        // continue in the next chunk), each lane finds its cell by a binary search over the lanes' running totals.
+        const int nMyCells = pBeg + warp < pEnd ? (pEnd - pBeg - warp + CT_WARPS - 1) / CT_WARPS : 0;
+        for (int k0 = 0; k0 < nMyCells; k0 += 32) {
+            unsigned cellBeg = 0, cellCnt = 0;
+            if (k0 + lane < nMyCells) {
+                const int ci = sh.phaseCells[pBeg + warp + CT_WARPS * (k0 + lane)];
+                cellBeg = sh.cellB[ci], cellCnt = sh.cellN[ci];
             }
-            {
-                const int cnt = filled;
+            const unsigned cellIncl = warpInclusiveScan(cellCnt), cellExcl = cellIncl - cellCnt;
+            const unsigned nSeq = __shfl_sync(0xffffffffu, cellIncl, 31);
+            for (unsigned t0 = 0; t0 < nSeq; t0 += 32) {
+                const unsigned t = t0 + lane;
+                unsigned owner = 0; // first lane whose running total exceeds t
+#pragma unroll
+                for (int step = 16; step >= 1; step >>= 1)
+                    if (__shfl_sync(0xffffffffu, cellIncl, owner + step - 1) <= t) owner += step;
+                const unsigned src = __shfl_sync(0xffffffffu, cellBeg, owner & 31u) + (t - __shfl_sync(0xffffffffu, cellExcl, owner & 31u));
+                const int cnt = static_cast<int>(min(32u, nSeq - t0));
                 int myL0x = 0, myL0y = 0, myL0z = 0; // per-voxel-wrap mode only: tile-local box origin before wrapping
                 bool myLive = false;                 // my particle reaches the tile
                 Dig dg{};                            // V2: my digested particle stays in registers

@@ -417,13 +417,24 @@ class SlabJob:
             self.last["n_recv"] = int(recv.shape[0])
         self.last["n_in"] = self.n_local
 
-    def step_e2e(self):
-        """the same through HOST buffers: pinned H2D of this rank's chunk, D2H of its volume slab and of the mesh"""
+    def step_e2e(self, mesh_to_host=True):
+        """the same through HOST buffers: pinned H2D of this rank's chunk, D2H of its volume slab and of the mesh.
+        mesh_to_host=False: the mesh stays in HBM (device-resident hand-off to a renderer); the particles still come from
+        host memory and the volume still goes back."""
         torch = self.torch
         if self.world == 1:
             self._compute(self.h_xyz.data_ptr(), self.n_local)
             self.surf.get_density(copy=False, with_rgb=self.protein)
-            self.surf.get_mesh(copy=False, colours=self.protein)
+            if mesh_to_host:
+                self.surf.get_mesh(copy=False, colours=self.protein)
+        elif not mesh_to_host:
+            d = self.h_xyz.to(self.dev, non_blocking=True)
+            recv = self._exchange(d)
+            self._keep = [d]
+            self._compute(d.data_ptr(), self.n_local, more=((recv.data_ptr(), recv.shape[0]),))
+            self.surf.get_density(copy=False)
+            self._allgather_counts()
+            torch.cuda.current_stream().synchronize()
         else:
             d = self.h_xyz.to(self.dev, non_blocking=True)
             recv = self._exchange(d)
