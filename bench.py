@@ -162,6 +162,31 @@ def run_reference(args, w):
     print(json.dumps(line))
 
 
+def bind_to_gpu_numa_node(local):
+    """Pin this rank's process to the CPUs NVML reports as local to its GPU, BEFORE any pinned host memory is allocated: the pinned
+    result buffers then live on the GPU's own NUMA node and N ranks do not funnel their D2H traffic into one socket's memory.
+    Best effort (no NVML / no topology information -> no-op).  Returns a short description for the JSON line."""
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        pr = torch.cuda.get_device_properties(local)
+        try:
+            h = pynvml.nvmlDeviceGetHandleByPciBusId(f"{pr.pci_domain_id:08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0")
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        ncpu = os.cpu_count() or 1
+        masks = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = [i for i in range(ncpu) if (masks[i // 64] >> (i % 64)) & 1]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if allowed and len(allowed) < len(os.sched_getaffinity(0)):
+            os.sched_setaffinity(0, allowed)
+            return f"cpus {allowed[0]}-{allowed[-1]} ({len(allowed)})"
+        return "all cpus (no narrower GPU affinity reported)"
+    except Exception as e:  # noqa: BLE001
+        return f"unbound ({type(e).__name__})"
+
+
 def run_ours(args, w):
     import torch
     import megamol_b200 as mm
@@ -173,6 +198,7 @@ def run_ours(args, w):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(local) if world > 1 else "single rank: not bound"
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -230,7 +256,7 @@ def run_ours(args, w):
             "dtype": "f32", "data": "synthetic", "gvoxels_per_s": v_total / (ms * 1e-3) / 1e9,
             "config": {"workload": w["name"] if world == 1 else job.describe(), "particles": n_total, "voxels": v_total, "triangles": t_total,
                        "l2": "inputs (particles + volume + mesh) are larger than the 126 MB L2; no explicit flush",
-                       "parallelism": f"z-slabs x{world}"},
+                       "parallelism": f"z-slabs x{world}", "host_affinity_rank0": numa},
             "stages_ms": stage, "roofline": rl,
             "pipeline_hbm_frac": job.pipeline_bytes() / (ms * 1e-3) / 1e9 / peak,
             "e2e": e2e, "e2e_mesh_on_device": e2e_dm, "gpu_launches": launches, "clocks": sampler.summary()}

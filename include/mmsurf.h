@@ -145,6 +145,16 @@ int mms_get_density_device(mms_ctx* ctx, const float** dev_volume, const float**
 int mms_set_density(mms_ctx* ctx, const float* volume);
 
 int mms_extract_isosurface(mms_ctx* ctx, float isovalue); /* = count + emit into library-owned buffers */
+
+/* Which triangulation mms_count/emit/extract_isosurface produce.
+ *   MMS_ISO_MARCHING_CUBES (default)  256-case marching cubes with the reference's table, smooth gradient normals, node-centred frame.
+ *   MMS_ISO_MARCHING_TETS             exactly what trisoup_gl::volumetrics::IsoSurface::buildMesh / makeTet / interpolate produce
+ *                                     (IsoSurface.cpp:30-31, 229-309, 430-465, 606-735): six tetrahedra per cell, regula falsi on the
+ *                                     trilinear interpolant, flat normals, the module's half-voxel shifted frame ((idx+0.5)/s*extent+min
+ *                                     with the grid's min/extent = the object-space bounding box) -- triangle for triangle and bit for
+ *                                     bit the CPU module's output.  No colour output in this mode. */
+enum { MMS_ISO_MARCHING_CUBES = 0, MMS_ISO_MARCHING_TETS = 1 };
+int mms_set_isosurface_mode(mms_ctx* ctx, int32_t mode);
 /* The two halves of extract, for callers that own the destination: count (classify + scan, one host round trip for the size),
  * then emit into caller-supplied DEVICE memory starting at triangle `first_triangle` (9 floats per triangle and array).
  * The destination may be this GPU's memory, a CUDA-IPC / peer mapping of another GPU's buffer (the z-slab driver lets every

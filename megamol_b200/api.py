@@ -13,10 +13,11 @@ VERT_NONE, VERT_FLOAT_XYZ, VERT_FLOAT_XYZR, VERT_SHORT_XYZ, VERT_DOUBLE_XYZ = ra
 (COL_NONE, COL_UINT8_RGB, COL_UINT8_RGBA, COL_FLOAT_RGB, COL_FLOAT_RGBA, COL_FLOAT_I, COL_USHORT_RGBA,
  COL_DOUBLE_I) = range(8)
 MODE_P2D_BUMP, MODE_QS_GAUSS = 0, 1
+ISO_MARCHING_CUBES, ISO_MARCHING_TETS = 0, 1
 
 EXPORTS = ["mms_create", "mms_destroy", "mms_last_error", "mms_set_grid", "mms_set_slab", "mms_set_params",
            "mms_clear_particles", "mms_push_particles", "mms_compute_density", "mms_get_density_range", "mms_normalize", "mms_density_range_device", "mms_normalize_device", "mms_set_stream",
-           "mms_get_density", "mms_get_density_device", "mms_set_density", "mms_extract_isosurface", "mms_count_isosurface", "mms_emit_isosurface", "mms_device_alloc",
+           "mms_get_density", "mms_get_density_device", "mms_set_density", "mms_extract_isosurface", "mms_set_isosurface_mode", "mms_count_isosurface", "mms_emit_isosurface", "mms_device_alloc",
            "mms_device_free", "mms_route_particles", "mms_ipc_export", "mms_ipc_open", "mms_ipc_close", "mms_get_mesh",
            "mms_get_mesh_device", "mms_get_home_voxels", "mms_get_cell_tricounts", "mms_get_timings", "mms_synchronize",
            "mms_timer_start", "mms_timer_stop", "mms_launch_count", "mms_alloc_pinned", "mms_free_pinned", "mms_version", "mms_mmpld_open", "mms_mmpld_close",
@@ -89,6 +90,7 @@ def load_library():
     L.mms_get_density.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
     L.mms_get_density_device.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
     L.mms_set_density.argtypes = [vp, vp]
+    L.mms_set_isosurface_mode.argtypes = [vp, C.c_int32]
     L.mms_extract_isosurface.argtypes = [vp, C.c_float]
     L.mms_count_isosurface.argtypes = [vp, C.c_float, C.POINTER(C.c_uint64)]
     L.mms_emit_isosurface.argtypes = [vp, vp, vp, vp, C.c_uint64]
@@ -289,6 +291,10 @@ class Surf:
         cnt = (C.c_uint64 * n)()
         self._chk(self.L.mms_route_particles(self.h, C.byref(l), n, lo, hi, int(send_ptr), int(capacity), cnt))
         return [int(c) for c in cnt]
+
+    def set_isosurface_mode(self, mode):
+        """0 = marching cubes (default), 1 = the reference IsoSurface's marching tetrahedra, bit for bit (ISO_MARCHING_TETS)"""
+        self._chk(self.L.mms_set_isosurface_mode(self.h, int(mode)))
 
     def count_isosurface(self, iso) -> int:
         n = C.c_uint64()

@@ -17,6 +17,7 @@
 #include "bin.cuh"
 #include "density.cuh"
 #include "mc.cuh"
+#include "mt.cuh"
 #include "route.cuh"
 
 using namespace mms;
@@ -152,6 +153,8 @@ struct mms_ctx {
     cudaStream_t ownStream = nullptr;
     DevBuf rangeBuf; // {-min, max} as floats for device-side all-reduce + normalise
     bool haveCount = false, meshExternal = false;
+    int isoMode = MMS_ISO_MARCHING_CUBES, countMode = MMS_ISO_MARCHING_CUBES;
+    MtGeo mtGeo{};
 
     DevBuf routeCounts, routeOffsets, routeTile;
     PinBuf hRoute;
@@ -840,9 +843,27 @@ int mms_count_isosurface(mms_ctx* c, float iso, uint64_t* ntris) {
         tri = c->triCount.as<unsigned char>();
     }
     cudaStream_t st = c->stream;
-    if (tri) MMS_CUDA(c, cudaMemsetAsync(tri, 0, static_cast<size_t>(m.cx) * m.cy * m.cnz, st)); // the kernel writes the non-empty cells only
-    dim3 grid((m.nsegx + CN_SEGS - 1) / CN_SEGS, (m.cy + CN_ROWS - 1) / CN_ROWS, (m.cnz + CN_LAYERS - 1) / CN_LAYERS);
-    mc_count_kernel<<<grid, MC_THREADS, 0, st>>>(m, c->vol.as<float>(), c->segCount.as<unsigned>(), tri);
+    c->countMode = c->isoMode;
+    if (c->isoMode == MMS_ISO_MARCHING_TETS) {
+        if (c->haveColour) return c->fail(MMS_ERR_UNSUPPORTED, "the marching-tetrahedra mode has no colour output");
+        MtGeo t{};
+        t.sx = m.sx, t.sy = m.sy, t.zPlane0 = m.zPlane0, t.szGlobal = m.szGlobal, t.cx = m.cx, t.cy = m.cy, t.cz0 = m.cz0, t.cnz = m.cnz, t.nsegx = m.nsegx;
+        for (int a = 0; a < 3; ++a) {
+            t.mn[a] = c->grid.min[a], t.ext[a] = c->grid.extent[a];
+            volatile float ext = c->grid.extent[a];
+            volatile float s = static_cast<float>(c->grid.res[a]);
+            volatile float cell = ext / s; // osbb.Width() / static_cast<float>(sx) (IsoSurface.cpp:238-240)
+            t.cell[a] = cell;
+        }
+        t.iso = iso;
+        c->mtGeo = t;
+        dim3 grid(m.nsegx, (m.cy + MT_THREADS / 32 - 1) / (MT_THREADS / 32), m.cnz);
+        mt_count_kernel<<<grid, MT_THREADS, 0, st>>>(t, c->vol.as<float>(), c->segCount.as<unsigned>(), tri);
+    } else {
+        if (tri) MMS_CUDA(c, cudaMemsetAsync(tri, 0, static_cast<size_t>(m.cx) * m.cy * m.cnz, st)); // the kernel writes the non-empty cells only
+        dim3 grid((m.nsegx + CN_SEGS - 1) / CN_SEGS, (m.cy + CN_ROWS - 1) / CN_ROWS, (m.cnz + CN_LAYERS - 1) / CN_LAYERS);
+        mc_count_kernel<<<grid, MC_THREADS, 0, st>>>(m, c->vol.as<float>(), c->segCount.as<unsigned>(), tri);
+    }
     ++c->launches;
     DevState* ds = c->dstate.as<DevState>();
     exclusiveScan(c->segCount.as<unsigned>(), c->segOffset.as<unsigned>(), nullptr, c->tileSums.as<unsigned>(), static_cast<unsigned>(nseg),
@@ -878,6 +899,16 @@ int mms_emit_isosurface(mms_ctx* c, float* pos, float* nrm, float* col, uint64_t
         }
         dim3 gridE(m.nsegx, (m.cy + EY - 1) / EY, (m.cnz + EM_STEPS * EZ - 1) / (EM_STEPS * EZ));
         c->rec(EV_EMIT0);
+        if (c->countMode == MMS_ISO_MARCHING_TETS) {
+            dim3 grid(m.nsegx, (m.cy + MT_THREADS / 32 - 1) / (MT_THREADS / 32), m.cnz);
+            mt_emit_kernel<<<grid, MT_THREADS, 0, st>>>(c->mtGeo, c->vol.as<float>(), c->segOffset.as<unsigned>(), P, N);
+            ++c->launches;
+            c->rec(EV_MC1);
+            MMS_CUDA(c, cudaGetLastError());
+            c->haveMesh = true;
+            c->meshExternal = !own;
+            return MMS_OK;
+        }
         CUtensorMap map{};
         const bool tma = makeVolumeTensorMap(&map, c->vol.as<float>(), m.sx, m.sy, m.nzPlanes);
         const float* V = c->vol.as<float>();
@@ -895,6 +926,15 @@ int mms_emit_isosurface(mms_ctx* c, float* pos, float* nrm, float* col, uint64_t
     MMS_CUDA(c, cudaGetLastError());
     c->haveMesh = true;
     c->meshExternal = !own;
+    return MMS_OK;
+}
+
+int mms_set_isosurface_mode(mms_ctx* c, int32_t mode) {
+    if (!c) return MMS_ERR_INVALID;
+    if (mode != MMS_ISO_MARCHING_CUBES && mode != MMS_ISO_MARCHING_TETS) return c->fail(MMS_ERR_INVALID, "unknown isosurface mode %d", mode);
+    c->isoMode = mode;
+    c->haveCount = false;
+    c->haveMesh = false;
     return MMS_OK;
 }
 

@@ -487,6 +487,183 @@ int64_t mmo_mc_emit(const float* vol, const float* rgb, const int32_t res[3], co
     return ntri;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Marching tetrahedra exactly as trisoup_gl::volumetrics::IsoSurface does it (IsoSurface.cpp:30-31, 229-309, 391-465,
+// 606-735): six tetrahedra per cell, vertices by regula falsi on the TRILINEAR interpolant along the tetrahedron edge,
+// one flat normal per triangle.  Every operation individually rounded (the reference's baseline x86-64 build has no FMA).
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+const unsigned kTets[6][4] = {{0, 2, 3, 7}, {0, 2, 6, 7}, {0, 4, 6, 7}, {0, 6, 1, 2}, {0, 6, 1, 4}, {5, 6, 1, 4}}; // IsoSurface.cpp:30-31
+const float kFloatEps = 1e-5f;                                                                                 // vislib FLOAT_EPSILON
+inline bool isEq(float m, float n) { return std::fabs(m - n) < kFloatEps; }                                    // mathfunctions.h:119-136
+
+struct P3 {
+    float v[3];
+};
+inline P3 lerpPoint(const P3& a, const P3& b, float t) { // AbstractPointImpl::Interpolate: a*(1-t) + b*t
+    const float at = 1.0f - t;
+    P3 r;
+    for (int d = 0; d < 3; ++d) r.v[d] = a.v[d] * at + b.v[d] * t;
+    return r;
+}
+inline float mtOffset(float v1, float v2, float want) { return (want - v1) / (v2 - v1); } // IsoSurface::getOffset
+inline float mtValue(const float* cv, unsigned i0, unsigned i1, float a) {                 // getValue (IsoSurface.cpp:405-424)
+    const float b = 1.0f - a;
+    const float x = b * static_cast<float>(kCorner[i0][0]) + a * static_cast<float>(kCorner[i1][0]);
+    const float y = b * static_cast<float>(kCorner[i0][1]) + a * static_cast<float>(kCorner[i1][1]);
+    const float z = b * static_cast<float>(kCorner[i0][2]) + a * static_cast<float>(kCorner[i1][2]);
+    float vv[4];
+    vv[0] = (1.0f - x) * cv[0] + x * cv[1];
+    vv[1] = (1.0f - x) * cv[3] + x * cv[2];
+    vv[2] = (1.0f - x) * cv[4] + x * cv[5];
+    vv[3] = (1.0f - x) * cv[7] + x * cv[6];
+    vv[0] = (1.0f - y) * vv[0] + y * vv[1];
+    vv[2] = (1.0f - y) * vv[2] + y * vv[3];
+    return (1.0f - z) * vv[0] + z * vv[2];
+}
+inline P3 mtInterpolate(const P3* pts, const float* cv, float val, unsigned i0, unsigned i1) { // IsoSurface::interpolate (:430-465)
+    float a0 = 0.0f;
+    float v0 = mtValue(cv, i0, i1, a0);
+    if (isEq(v0, val)) return pts[i0];
+    float a1 = 1.0f;
+    float v1 = mtValue(cv, i0, i1, a1);
+    if (isEq(v1, val)) return pts[i1];
+    float a = mtOffset(cv[i0], cv[i1], val);
+    float v = mtValue(cv, i0, i1, a);
+    unsigned maxStep = 100;
+    const bool flip = cv[i0] > cv[i1];
+    while (maxStep > 0 && !isEq(v, val)) {
+        if ((!flip && v > val) || (flip && v < val)) a1 = a, v1 = v;
+        else a0 = a, v0 = v;
+        a = a0 + mtOffset(v0, v1, val) * (a1 - a0);
+        v = mtValue(cv, i0, i1, a);
+        --maxStep;
+    }
+    return lerpPoint(pts[i0], pts[i1], a);
+}
+inline void cross3(const float* a, const float* b, float* r) { // AbstractVector<T,3>::Cross
+    r[0] = a[1] * b[2] - a[2] * b[1];
+    r[1] = a[2] * b[0] - a[0] * b[2];
+    r[2] = a[0] * b[1] - a[1] * b[0];
+}
+inline float normalise3(float* v) { // AbstractVectorImpl::Normalise / Length
+    float l = 0.0f;
+    for (int d = 0; d < 3; ++d) l += v[d] * v[d];
+    l = std::sqrt(l);
+    if (l != 0.0f) for (int d = 0; d < 3; ++d) v[d] /= l;
+    else v[0] = v[1] = v[2] = 0.0f;
+    return l;
+}
+/** triangles of one tetrahedron; returns their number (0..2); tri[k] = 3 points */
+inline int mtMakeTet(unsigned triIdx, unsigned tet, const P3* pts, const float* cv, float val, P3 tri[2][3]) {
+    const unsigned* T = kTets[tet];
+    const P3 &p0 = pts[T[0]], &p1 = pts[T[1]], &p2 = pts[T[2]], &p3 = pts[T[3]];
+    float e1[3], e2[3], nrm[3];
+    for (int d = 0; d < 3; ++d) e1[d] = p2.v[d] - p1.v[d], e2[d] = p3.v[d] - p1.v[d];
+    cross3(e1, e2, nrm);
+    normalise3(nrm);
+    // Plane(p1, norm): d = -1 * (a*x + b*y + c*z);  Halfspace(p0): normalised parameters, IsEqual(dist, 0) -> in plane
+    const float pd = -1.0f * (nrm[0] * p1.v[0] + nrm[1] * p1.v[1] + nrm[2] * p1.v[2]);
+    const float len = std::sqrt(nrm[0] * nrm[0] + nrm[1] * nrm[1] + nrm[2] * nrm[2]);
+    float A = 0, B = 0, C = 0, D = 0;
+    if (!isEq(len, 0.0f)) A = nrm[0] / len, B = nrm[1] / len, C = nrm[2] / len, D = pd / len;
+    const float dist = A * p0.v[0] + B * p0.v[1] + C * p0.v[2] + D;
+    bool flip = !isEq(dist, 0.0f) && dist > 0.0f;
+    auto I = [&](int a, int b) { return mtInterpolate(pts, cv, val, T[a], T[b]); };
+    int n = 0;
+    switch (triIdx) {
+    case 0x00: case 0x0F: break;
+    case 0x01: flip = !flip; // fall through
+    case 0x0E: tri[0][0] = I(0, 1); tri[0][flip ? 2 : 1] = I(0, 2); tri[0][flip ? 1 : 2] = I(0, 3); n = 1; break;
+    case 0x02: flip = !flip; // fall through
+    case 0x0D: tri[0][0] = I(1, 0); tri[0][flip ? 2 : 1] = I(1, 3); tri[0][flip ? 1 : 2] = I(1, 2); n = 1; break;
+    case 0x0C: flip = !flip; // fall through
+    case 0x03:
+        tri[0][0] = I(0, 3); tri[0][flip ? 2 : 1] = I(0, 2); tri[0][flip ? 1 : 2] = I(1, 3);
+        tri[1][0] = tri[0][flip ? 1 : 2]; tri[1][flip ? 1 : 2] = I(1, 2); tri[1][flip ? 2 : 1] = tri[0][flip ? 2 : 1];
+        n = 2; break;
+    case 0x04: flip = !flip; // fall through
+    case 0x0B: tri[0][0] = I(2, 0); tri[0][flip ? 2 : 1] = I(2, 1); tri[0][flip ? 1 : 2] = I(2, 3); n = 1; break;
+    case 0x05: flip = !flip; // fall through
+    case 0x0A:
+        tri[0][0] = I(0, 1); tri[0][flip ? 2 : 1] = I(2, 3); tri[0][flip ? 1 : 2] = I(0, 3);
+        tri[1][0] = tri[0][0]; tri[1][flip ? 2 : 1] = I(1, 2); tri[1][flip ? 1 : 2] = tri[0][flip ? 2 : 1];
+        n = 2; break;
+    case 0x06: flip = !flip; // fall through
+    case 0x09:
+        tri[0][0] = I(0, 1); tri[0][flip ? 2 : 1] = I(1, 3); tri[0][flip ? 1 : 2] = I(2, 3);
+        tri[1][0] = tri[0][0]; tri[1][flip ? 1 : 2] = I(0, 2); tri[1][flip ? 2 : 1] = tri[0][flip ? 1 : 2];
+        n = 2; break;
+    case 0x08: flip = !flip; // fall through
+    case 0x07: tri[0][0] = I(3, 0); tri[0][flip ? 2 : 1] = I(3, 2); tri[0][flip ? 1 : 2] = I(3, 1); n = 1; break;
+    }
+    return n;
+}
+} // namespace
+
+/**
+ * The reference IsoSurface's triangle soup (IsoSurface::buildMesh): cells in x-fastest order, tetrahedra 0..5, tri then tri2.
+ * bbox = {Left, Bottom, Back, Width, Height, Depth} of the object-space bounding box; cell size = extent / s and cell centres at
+ * (idx + 0.5)/s * extent + min -- the reference's own (half-voxel shifted) frame.  pos/nrm may be NULL (count only).
+ * Returns the number of triangles, or -1 if max_tris was too small.
+ */
+int64_t mmo_mt_emit(const float* vol, const int32_t res[3], const float bbox[6], float val, int64_t max_tris, float* pos, float* nrm) {
+    const unsigned sx = res[0], sy = res[1], sz = res[2];
+    if (sx < 2 || sy < 2 || sz < 2) return 0;
+    const float cellX = bbox[3] / static_cast<float>(sx), cellY = bbox[4] / static_cast<float>(sy), cellZ = bbox[5] / static_cast<float>(sz);
+    int64_t ntri = 0;
+    for (unsigned z = 0; z < sz - 1; ++z) {
+        float pz = (static_cast<float>(z) + 0.5f) / static_cast<float>(sz);
+        pz = pz * bbox[5] + bbox[2];
+        for (unsigned y = 0; y < sy - 1; ++y) {
+            float py = (static_cast<float>(y) + 0.5f) / static_cast<float>(sy);
+            py = py * bbox[4] + bbox[1];
+            for (unsigned x = 0; x < sx - 1; ++x) {
+                float px = (static_cast<float>(x) + 0.5f) / static_cast<float>(sx);
+                px = px * bbox[3] + bbox[0];
+                float cv[8];
+                bool bigger = false, smaller = false;
+                for (int j = 0; j < 8; ++j) {
+                    cv[j] = vol[(x + kCorner[j][0]) + static_cast<size_t>(sx) * ((y + kCorner[j][1]) + static_cast<size_t>(sy) * (z + kCorner[j][2]))];
+                    bigger = bigger || (cv[j] >= val);
+                    smaller = smaller || (cv[j] < val);
+                }
+                if (!bigger || !smaller) continue;
+                P3 pts[8];
+                for (int j = 0; j < 8; ++j) {
+                    pts[j].v[0] = px + static_cast<float>(kCorner[j][0]) * cellX;
+                    pts[j].v[1] = py + static_cast<float>(kCorner[j][1]) * cellY;
+                    pts[j].v[2] = pz + static_cast<float>(kCorner[j][2]) * cellZ;
+                }
+                for (unsigned tet = 0; tet < 6; ++tet) {
+                    unsigned triIdx = 0;
+                    for (int k = 0; k < 4; ++k)
+                        if (cv[kTets[tet][k]] < val) triIdx |= 1u << k;
+                    P3 tri[2][3];
+                    const int n = mtMakeTet(triIdx, tet, pts, cv, val, tri);
+                    for (int t = 0; t < n; ++t) {
+                        if (pos) {
+                            if (ntri >= max_tris) return -1;
+                            for (int i = 0; i < 3; ++i)
+                                for (int d = 0; d < 3; ++d) pos[9 * ntri + 3 * i + d] = tri[t][i].v[d];
+                            if (nrm) {
+                                float e1[3], e2[3], nn[3];
+                                for (int d = 0; d < 3; ++d) e1[d] = tri[t][1].v[d] - tri[t][0].v[d], e2[d] = tri[t][2].v[d] - tri[t][0].v[d];
+                                cross3(e1, e2, nn);
+                                normalise3(nn);
+                                for (int i = 0; i < 3; ++i)
+                                    for (int d = 0; d < 3; ++d) nrm[9 * ntri + 3 * i + d] = nn[d];
+                            }
+                        }
+                        ++ntri;
+                    }
+                }
+            }
+        }
+    }
+    return ntri;
+}
+
 /** The packed case words (for table tests). */
 void mmo_case_words(uint64_t out[256]) { std::memcpy(out, kCaseWords, sizeof(kCaseWords)); }
 

@@ -169,6 +169,24 @@ class Oracle:
         assert n == total, (n, total)
         return pos, nrm, col
 
+    def mt_emit(self, vol, bbox, iso, normals=True):
+        """The reference IsoSurface's marching-tetrahedra soup (mmo_mt_emit).  bbox = (left, bottom, back, right, top, front) of
+        the object-space bounding box.  Returns (pos [T,3,3], nrm [T,3,3] | None)."""
+        vol = np.ascontiguousarray(vol, np.float32)
+        sz, sy, sx = vol.shape
+        res = np.array([sx, sy, sz], np.int32)
+        b = np.asarray(bbox, np.float32)
+        bb = np.array([b[0], b[1], b[2], b[3] - b[0], b[4] - b[1], b[5] - b[2]], np.float32)  # Cuboid::Width() etc.: fp32 differences
+        self.lib.mmo_mt_emit.restype = C.c_int64
+        self.lib.mmo_mt_emit.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int64, C.c_void_p, C.c_void_p]
+        total = self.lib.mmo_mt_emit(vol.ctypes.data, res.ctypes.data, bb.ctypes.data, float(iso), 0, None, None)
+        pos = np.empty((total, 3, 3), np.float32)
+        nrm = np.empty((total, 3, 3), np.float32) if normals else None
+        n = self.lib.mmo_mt_emit(vol.ctypes.data, res.ctypes.data, bb.ctypes.data, float(iso), total, pos.ctypes.data,
+                                 nrm.ctypes.data if normals else None)
+        assert n == total, (n, total)
+        return pos, nrm
+
     def case_words(self):
         w = np.empty(256, np.uint64)
         self.lib.mmo_case_words(w.ctypes.data)

@@ -10,9 +10,12 @@ oracle/ref_harness.cpp) in the dev container, where /root/reference exists.  The
                      whose centre IS static_cast<int>((p - min)/sliceDist)  (ParticlesToDensity.cpp:563-579);
                      positions include exact multiples of the slice distance and their fp32 neighbours
   isosurface_ref.npz the reference IsoSurface (marching tetrahedra) vertex count / bbox of its output on one volume
-                     (informational: different algorithm)
+                     (informational for the marching-CUBES path: different algorithm)
+  isosurface_mt_*.npz the reference IsoSurface's complete output (vertices + normals) on two volumes: the golden vectors of the
+                     marching-tetrahedra compatibility mode (oracle mmo_mt_emit, libmmsurf MMS_ISO_MARCHING_TETS)
 
-Run:  python oracle/tools/gen_golden.py
+Run:  python oracle/tools/gen_golden.py            (everything)
+      python oracle/tools/gen_golden.py --only mt  (the marching-tetrahedra fixtures only)
 """
 import os
 import sys
@@ -68,7 +71,28 @@ def as_lists(c, module):
     return [dict(vtx=d, vtx_type=module.VERT_FLOAT_XYZ, count=len(d), global_radius=c["r"])]
 
 
+def gen_mt_fixtures(h):
+    """complete reference IsoSurface meshes on the volumes of two P2D cases"""
+    cases = {c["name"]: c for c in p2d_cases()}
+    for name, iso in (("sigma_clipped", 0.2), ("aniso_mixedcyc", 0.5)):
+        c = cases[name]
+        mn, ext = c["bmin"], c["bext"]
+        bbox = (mn[0], mn[1], mn[2], mn[0] + ext[0], mn[1] + ext[1], mn[2] + ext[2])
+        h.set_particles(as_lists(c, rb), bbox)
+        h.set_p2d_params(c["res"], cyclic=c["cyc"], normalize=False, sigma=c["sigma"])
+        vol, _ = h.pull_volume()
+        m = h.pull_mesh(iso)
+        np.savez_compressed(os.path.join(OUT, f"isosurface_mt_{name}.npz"), volume=vol, iso=np.float32(iso), bbox=np.array(bbox, np.float32),
+                            pos=m["pos"], nrm=m["nrm"])
+        print("IsoSurface (marching tetrahedra) golden:", name, "iso", iso, m["nverts"] // 3, "triangles")
+
+
 def main():
+    if "--only" in sys.argv and sys.argv[sys.argv.index("--only") + 1] == "mt":
+        h = rb.Harness()
+        h.set_threads(1)
+        gen_mt_fixtures(h)
+        return
     os.makedirs(OUT, exist_ok=True)
     h = rb.Harness()
     h.set_threads(1)
@@ -148,6 +172,7 @@ def main():
     np.savez_compressed(os.path.join(OUT, "isosurface_ref.npz"), volume=vol, iso=np.float32(0.5), nverts=m["nverts"], ntris=m["ntris"],
                         pos_min=m["pos"].min(0), pos_max=m["pos"].max(0), bbox=np.array(bbox, np.float32))
     print("IsoSurface reference:", m["nverts"], "vertices, GetTriCount() =", m["ntris"])
+    gen_mt_fixtures(h)
 
 
 if __name__ == "__main__":

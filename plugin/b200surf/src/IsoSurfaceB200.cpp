@@ -12,6 +12,7 @@
 #include <chrono>
 
 #include "ParticlesToDensityB200.h"
+#include "mmcore/param/EnumParam.h"
 #include "mmcore/param/FloatParam.h"
 #include "mmcore/param/IntParam.h"
 #include "mmcore/param/StringParam.h"
@@ -32,7 +33,9 @@ IsoSurfaceB200::IsoSurfaceB200()
         , outDataSlot("outData", "Gets the data")
         , attributeSlot("attr", "The attribute to show")
         , isoValueSlot("isoval", "The iso value")
-        , deviceSlot("device", "CUDA device ordinal used for volumes that are not already device resident") {
+        , deviceSlot("device", "CUDA device ordinal used for volumes that are not already device resident")
+        , algorithmSlot("algorithm", "Triangulation: marching cubes (smooth normals, node-centred frame) or the CPU module's marching "
+                                     "tetrahedra reproduced triangle for triangle") {
 
     this->inDataSlot.SetCompatibleCall<geocalls::VolumetricDataCallDescription>();
     this->MakeSlotAvailable(&this->inDataSlot);
@@ -49,6 +52,12 @@ IsoSurfaceB200::IsoSurfaceB200()
 
     this->deviceSlot << new core::param::IntParam(0, 0);
     this->MakeSlotAvailable(&this->deviceSlot);
+
+    auto* alg = new core::param::EnumParam(MMS_ISO_MARCHING_CUBES);
+    alg->SetTypePair(MMS_ISO_MARCHING_CUBES, "MarchingCubes");
+    alg->SetTypePair(MMS_ISO_MARCHING_TETS, "MarchingTetrahedra (as trisoup_gl::IsoSurface)");
+    this->algorithmSlot << alg;
+    this->MakeSlotAvailable(&this->algorithmSlot);
 }
 
 IsoSurfaceB200::~IsoSurfaceB200() {
@@ -87,6 +96,7 @@ bool IsoSurfaceB200::outExtentCallback(core::Call& caller) {
 
 bool IsoSurfaceB200::buildMesh(VolumetricDataCall* cvd, float iso) {
     const auto t0 = std::chrono::high_resolution_clock::now();
+    const int algorithm = this->algorithmSlot.Param<core::param::EnumParam>()->Value();
     mms_ctx* use = nullptr;
     // device-resident hand-off: is the callee a ParticlesToDensityB200 whose context holds exactly this volume?
     const core::CalleeSlot* callee = cvd->PeekCalleeSlot();
@@ -121,6 +131,11 @@ bool IsoSurfaceB200::buildMesh(VolumetricDataCall* cvd, float iso) {
             grid.res[a] = static_cast<int32_t>(md->Resolution[a]);
             grid.cyclic[a] = 0;
         }
+        if (algorithm == MMS_ISO_MARCHING_TETS) { // the CPU module places its cells in the object-space bounding box (IsoSurface.cpp:125, 238-252)
+            const auto& bb = cvd->AccessBoundingBoxes().ObjectSpaceBBox();
+            grid.min[0] = bb.Left(), grid.min[1] = bb.Bottom(), grid.min[2] = bb.Back();
+            grid.extent[0] = bb.Width(), grid.extent[1] = bb.Height(), grid.extent[2] = bb.Depth();
+        }
         if (mms_set_grid(this->ctx, &grid) != MMS_OK || mms_set_density(this->ctx, static_cast<const float*>(cvd->GetData())) != MMS_OK) {
             Log::DefaultLog.WriteError("IsoSurfaceB200: %s", mms_last_error(this->ctx));
             return false;
@@ -129,7 +144,8 @@ bool IsoSurfaceB200::buildMesh(VolumetricDataCall* cvd, float iso) {
     }
     uint64_t nverts = 0;
     const float *pos = nullptr, *nrm = nullptr, *col = nullptr; // col stays NULL unless the volume carries colours (QuickSurf mode)
-    if (mms_extract_isosurface(use, iso) != MMS_OK || mms_get_mesh(use, &nverts, &pos, &nrm, &col) != MMS_OK) {
+    if (mms_set_isosurface_mode(use, algorithm) != MMS_OK || mms_extract_isosurface(use, iso) != MMS_OK ||
+        mms_get_mesh(use, &nverts, &pos, &nrm, &col) != MMS_OK) {
         Log::DefaultLog.WriteError("IsoSurfaceB200: %s", mms_last_error(use));
         return false;
     }
@@ -158,6 +174,10 @@ bool IsoSurfaceB200::outDataCallback(core::Call& caller) {
         }
         if (this->attributeSlot.IsDirty()) {
             this->attributeSlot.ResetDirty();
+            recalc = true;
+        }
+        if (this->algorithmSlot.IsDirty()) {
+            this->algorithmSlot.ResetDirty();
             recalc = true;
         }
         cvd->SetFrameID(tmd->FrameID(), tmd->IsFrameForced());

@@ -43,7 +43,7 @@ private:
 
     core::CallerSlot inDataSlot;
     core::CalleeSlot outDataSlot;
-    core::param::ParamSlot attributeSlot, isoValueSlot, deviceSlot;
+    core::param::ParamSlot attributeSlot, isoValueSlot, deviceSlot, algorithmSlot;
 
     mms_ctx* ctx = nullptr; // own context, used when the volume comes from a foreign (host) source
     int ctxDevice = -1;

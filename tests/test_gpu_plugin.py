@@ -142,3 +142,30 @@ def test_quicksurf_mode_through_the_modules(plug, oracle):
     finally:
         plug.set_param(0, "mode", 0)
         plug.set_param(0, "quicksurf::colour", 0)
+
+
+def test_marching_tetrahedra_algorithm_matches_the_reference_module(ref, plug, oracle):
+    """IsoSurfaceB200 with algorithm = MarchingTetrahedra: on the volume its VolumetricDataCall delivers, the mesh equals the oracle's
+    restatement of the reference IsoSurface bit for bit (which itself equals the unmodified module bit for bit: tests/test_oracle_golden.py,
+    tests/test_oracle_vs_reference.py); next to the reference graph (whose density differs in the last bits: summation order) the two
+    soups agree triangle for triangle up to iso-value ties."""
+    n, box, res = 5000, 10.0, (24, 22, 20)
+    xyz = synth.uniform_box(n, box, seed=12)
+    lists = [dict(vtx=xyz, vtx_type=rb.VERT_FLOAT_XYZ, count=n, global_radius=1.0)]
+    bbox = (0, 0, 0, box, box, box)
+    feed(plug, lists, bbox, res, cyclic=(False,) * 3, normalize=True)
+    plug.set_param(1, "algorithm", 1)
+    try:
+        vol, _ = plug.pull_volume()
+        m = plug.pull_mesh(0.5)
+        pos, nrm = oracle.mt_emit(vol, bbox, 0.5)
+        assert m["ntris"] == 0 and m["nverts"] == 3 * pos.shape[0] and pos.shape[0] > 5000
+        assert np.array_equal(m["pos"], pos.reshape(-1, 3)) and np.array_equal(m["nrm"], nrm.reshape(-1, 3))
+        feed(ref, lists, bbox, res, cyclic=(False,) * 3, normalize=True)
+        ref.pull_volume()
+        r = ref.pull_mesh(0.5)
+        assert abs(r["nverts"] - m["nverts"]) <= 0.002 * r["nverts"]
+        if r["nverts"] == m["nverts"]:
+            assert np.abs(r["pos"] - m["pos"]).max() <= 1e-3 * box / res[0]
+    finally:
+        plug.set_param(1, "algorithm", 0)

@@ -89,3 +89,14 @@ def test_reference_isosurface_is_a_different_algorithm(oracle):
     ref_tris = int(z["nverts"]) // 3
     assert int(z["ntris"]) == 0            # the reference never fills its index buffer (IsoSurface.cpp:180)
     assert 0 < total < ref_tris < 3 * total
+
+
+@pytest.mark.parametrize("name", ["sigma_clipped", "aniso_mixedcyc"])
+def test_marching_tetrahedra_equals_the_reference_isosurface(oracle, name):
+    """Golden vectors = the complete output of the unmodified trisoup_gl IsoSurface module (vertices + normals): the oracle's
+    restatement of buildMesh / makeTet / interpolate (IsoSurface.cpp:229-309, 430-465, 606-735) reproduces them bit for bit."""
+    z = np.load(os.path.join(G.GOLDEN, f"isosurface_mt_{name}.npz"))
+    pos, nrm = oracle.mt_emit(z["volume"], z["bbox"], float(z["iso"]))
+    assert pos.shape[0] * 3 == z["pos"].shape[0] and pos.shape[0] > 1000
+    assert np.array_equal(pos.reshape(-1, 3), z["pos"])
+    assert np.array_equal(nrm.reshape(-1, 3), z["nrm"])

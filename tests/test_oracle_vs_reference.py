@@ -44,3 +44,18 @@ def test_datahash_and_dirty_protocol(harness):
     harness.set_p2d_params((8, 8, 8), sigma=0.9)
     _, m3 = harness.pull_volume()
     assert m3["datahash"] == m2["datahash"] + 1
+
+
+@pytest.mark.parametrize("iso", [0.15, 0.5, 1.1])
+def test_marching_tetrahedra_live(harness, oracle, iso):
+    """oracle mmo_mt_emit == the reference IsoSurface module, vertices and normals, bit for bit"""
+    n, box, res = 3000, 10.0, (20, 18, 16)
+    xyz = synth.uniform_box(n, box, seed=78)
+    harness.set_threads(1)
+    harness.set_particles([dict(vtx=xyz, vtx_type=1, count=n, global_radius=0.8)], (0, 0, 0, box, box, box))
+    harness.set_p2d_params(res, cyclic=(True,) * 3, normalize=False, sigma=1.0)
+    vol, _ = harness.pull_volume()
+    m = harness.pull_mesh(iso)
+    pos, nrm = oracle.mt_emit(vol, (0, 0, 0, box, box, box), iso)
+    assert pos.shape[0] * 3 == m["nverts"] and m["nverts"] > 300
+    assert np.array_equal(pos.reshape(-1, 3), m["pos"]) and np.array_equal(nrm.reshape(-1, 3), m["nrm"])
