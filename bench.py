@@ -203,6 +203,8 @@ def run_ours(args, w):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     job = slabs.SlabJob(w, rank, world, local, iso=ISO, radius=RADIUS, gather=args.gather)
+    if args.algorithm == "mt":  # the reference IsoSurface's marching tetrahedra, bit for bit (compatibility mode; flat normals, ~2.7x the triangles)
+        job.surf.set_isosurface_mode(mm.api.ISO_MARCHING_TETS)
     peak, peak_src = load_peaks()
 
     # ---- device-resident arm -------------------------------------------------------------------------------
@@ -256,7 +258,8 @@ def run_ours(args, w):
             "dtype": "f32", "data": "synthetic", "gvoxels_per_s": v_total / (ms * 1e-3) / 1e9,
             "config": {"workload": w["name"] if world == 1 else job.describe(), "particles": n_total, "voxels": v_total, "triangles": t_total,
                        "l2": "inputs (particles + volume + mesh) are larger than the 126 MB L2; no explicit flush",
-                       "parallelism": f"z-slabs x{world}", "host_affinity_rank0": numa},
+                       "parallelism": f"z-slabs x{world}", "host_affinity_rank0": numa,
+                       "isosurface": "marching cubes (default)" if args.algorithm == "mc" else "marching tetrahedra, reference-compatible mode"},
             "stages_ms": stage, "roofline": rl,
             "pipeline_hbm_frac": job.pipeline_bytes() / (ms * 1e-3) / 1e9 / peak,
             "e2e": e2e, "e2e_mesh_on_device": e2e_dm, "gpu_launches": launches, "clocks": sampler.summary()}
@@ -330,6 +333,8 @@ def main():
     ap.add_argument("--gather", default="host", choices=["host", "fused", "nccl"],
                     help="multi-GPU: where the per-slab meshes go: host (default; stay sharded in HBM, counts all-gathered, e2e copies each slab over its "
                          "own PCIe link), fused (mc_emit stores into rank 0's mesh over NVLink), nccl (send/recv to rank 0)")
+    ap.add_argument("--algorithm", default="mc", choices=["mc", "mt"],
+                    help="isosurface triangulation: mc = marching cubes (default, the north-star path), mt = the reference module's marching tetrahedra")
     ap.add_argument("--frames", type=int, default=12, help="frames of the C5 time series")
     ap.add_argument("--tmpdir", default="/tmp")
     args = ap.parse_args()

@@ -295,6 +295,7 @@ class Surf:
     def set_isosurface_mode(self, mode):
         """0 = marching cubes (default), 1 = the reference IsoSurface's marching tetrahedra, bit for bit (ISO_MARCHING_TETS)"""
         self._chk(self.L.mms_set_isosurface_mode(self.h, int(mode)))
+        self.iso_mode = int(mode)
 
     def count_isosurface(self, iso) -> int:
         n = C.c_uint64()

@@ -512,6 +512,8 @@ class SlabJob:
         # mc_emit: reads the density once more, writes the mesh; mc_count reads the density once
         emit_bytes = b["mc"]
         cand = {dens: (stage["density"], b["density"]), "mc_emit_kernel": (stage.get("mc_emit", 0.0), emit_bytes)}
+        if getattr(self.surf, "iso_mode", 0) == 1:
+            cand["mt_emit_kernel"] = cand.pop("mc_emit_kernel")
         name = max(cand, key=lambda k: cand[k][0])
         ms, by = cand[name]
         ach = by / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
