@@ -137,6 +137,9 @@ int mms_normalize_device(mms_ctx* ctx, const float* dev_negmin_max);
  * stream the caller's collectives are ordered on.  The default stream is named by cudaStreamLegacy ((cudaStream_t)0x1) or
  * cudaStreamPerThread ((cudaStream_t)0x2), never by NULL. */
 int mms_set_stream(mms_ctx* ctx, void* cuda_stream);
+/* Starts the device-to-host copy of the (final) volume on the library's copy stream and returns: a following mms_extract_isosurface
+ * overlaps with it (marching cubes only reads the volume), and mms_get_density then merely waits for the copy.  Optional. */
+int mms_prefetch_density(mms_ctx* ctx);
 /* Host copy (library-owned pinned memory) of the slab: nz*res[1]*res[0] floats, x fastest. rgb may be NULL. */
 int mms_get_density(mms_ctx* ctx, const float** host_volume, const float** host_rgb);
 int mms_get_density_device(mms_ctx* ctx, const float** dev_volume, const float** dev_rgb);

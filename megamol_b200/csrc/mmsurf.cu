@@ -142,6 +142,8 @@ struct mms_ctx {
     int arenaCur = 0;
     cudaStream_t copyStream = nullptr;
     cudaEvent_t uploadDone = nullptr;
+    cudaEvent_t volReady = nullptr, volCopied = nullptr; // mms_prefetch_density: volume final on the compute stream / host copy complete
+    bool volPrefetched = false;
     bool uploadPending = false;
     unsigned long long nparticles = 0;
     bool haveDensity = false, haveMesh = false, normalized = false;
@@ -260,6 +262,14 @@ __global__ void init_state_kernel(DevState* st) {
     st->pad[1] = 0u;
 }
 
+/** The state block goes to the host by a store into mapped pinned memory, not by a copy-engine transfer: a cudaMemcpyAsync would queue
+ *  behind a volume read-back that is in flight on the same DMA engine (mms_prefetch_density) and stall the one host round trip of the
+ *  isosurface (the triangle count) until that copy is done. */
+__global__ void publish_state_kernel(const DevState* __restrict__ st, DevState* __restrict__ hostMapped) {
+    *hostMapped = *st;
+    __threadfence_system();
+}
+
 __global__ void range_to_float_kernel(const DevState* __restrict__ st, float* __restrict__ out) {
     out[0] = -keyFloat(st->minKey);
     out[1] = keyFloat(st->maxKey);
@@ -364,6 +374,8 @@ int mms_create(mms_ctx** out, const mms_config* cfg) {
     for (auto& ev : c->ev) cudaEventCreate(&ev);
     cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking);
     cudaEventCreateWithFlags(&c->uploadDone, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->volReady, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->volCopied, cudaEventDisableTiming);
     for (auto& a : c->arena) cudaEventCreateWithFlags(&a.consumed, cudaEventDisableTiming);
     c->params.mode = MMS_MODE_P2D_BUMP;
     c->params.sigma = 1.0f;
@@ -419,6 +431,8 @@ int mms_destroy(mms_ctx* c) {
             cudaEventDestroy(a.consumed);
         }
         cudaEventDestroy(c->uploadDone);
+        cudaEventDestroy(c->volReady);
+        cudaEventDestroy(c->volCopied);
         cudaStreamDestroy(c->copyStream);
         for (auto& ev : c->ev) cudaEventDestroy(ev);
         cudaStreamDestroy(c->ownStream ? c->ownStream : c->stream);
@@ -552,6 +566,10 @@ int mms_compute_density(mms_ctx* c) {
         MMS_CUDA(c, cudaStreamWaitEvent(st, c->uploadDone, 0));
         c->uploadPending = false;
     }
+    if (c->volPrefetched) { // a prefetch copy of the previous volume may still be reading it
+        MMS_CUDA(c, cudaStreamWaitEvent(st, c->volCopied, 0));
+        c->volPrefetched = false;
+    }
     c->rec(EV_BIN0);
     init_state_kernel<<<1, 1, 0, st>>>(c->dstate.as<DevState>());
     ++c->launches;
@@ -674,6 +692,7 @@ int mms_compute_density(mms_ctx* c) {
     ++c->launches;
     c->rec(EV_DEN1);
     c->normalized = false;
+    c->volPrefetched = false;
     if (c->params.mode == MMS_MODE_P2D_BUMP && c->params.normalize && !c->params.defer_normalize) {
         c->rec(EV_NRM0);
         normalize_state_kernel<<<c->smCount * 16, 256, 0, st>>>(c->vol.as<float>(), nvox, c->dstate.as<DevState>());
@@ -724,6 +743,7 @@ int mms_normalize(mms_ctx* c, float mn, float mx) {
     c->rec(EV_NRM1);
     MMS_CUDA(c, cudaGetLastError());
     c->normalized = true;
+    c->volPrefetched = false;
     c->haveMesh = false;
     return MMS_OK;
 }
@@ -759,6 +779,7 @@ int mms_normalize_device(mms_ctx* c, const float* dev_negmin_max) {
     c->rec(EV_NRM1);
     MMS_CUDA(c, cudaGetLastError());
     c->normalized = true;
+    c->volPrefetched = false;
     c->haveMesh = false;
     return MMS_OK;
 }
@@ -771,10 +792,39 @@ int mms_get_density_device(mms_ctx* c, const float** dv, const float** drgb) {
     return MMS_OK;
 }
 
+int mms_prefetch_density(mms_ctx* c) {
+    if (!c) return MMS_ERR_INVALID;
+    if (!c->haveDensity) return c->fail(MMS_ERR_INVALID, "no density has been computed");
+    DeviceGuard guard(c->device);
+    const size_t bytes = static_cast<size_t>(c->grid.res[0]) * c->grid.res[1] * c->nz * 4;
+    if (!c->hVol.ensure(bytes)) return c->fail(MMS_ERR_NOMEM, "pinned allocation of %zu bytes failed", bytes);
+    if (c->haveColour && !c->hRgb.ensure(bytes * 3)) return c->fail(MMS_ERR_NOMEM, "pinned allocation of %zu bytes failed", bytes * 3);
+    // the volume is final once everything enqueued so far has run; the copy stream takes it from there while the compute stream
+    // goes on with the isosurface (which only reads the volume)
+    MMS_CUDA(c, cudaEventRecord(c->volReady, c->stream));
+    MMS_CUDA(c, cudaStreamWaitEvent(c->copyStream, c->volReady, 0));
+    cudaEventRecord(c->ev[EV_DV0], c->copyStream);
+    c->evSet[EV_DV0] = true;
+    MMS_CUDA(c, cudaMemcpyAsync(c->hVol.p, c->vol.p, bytes, cudaMemcpyDeviceToHost, c->copyStream));
+    if (c->haveColour) MMS_CUDA(c, cudaMemcpyAsync(c->hRgb.p, c->rgb.p, bytes * 3, cudaMemcpyDeviceToHost, c->copyStream));
+    cudaEventRecord(c->ev[EV_DV1], c->copyStream);
+    c->evSet[EV_DV1] = true;
+    MMS_CUDA(c, cudaEventRecord(c->volCopied, c->copyStream));
+    c->volPrefetched = true;
+    return MMS_OK;
+}
+
 int mms_get_density(mms_ctx* c, const float** hv, const float** hrgb) {
     if (!c || !hv) return MMS_ERR_INVALID;
     if (!c->haveDensity) return c->fail(MMS_ERR_INVALID, "no density has been computed");
     DeviceGuard guard(c->device);
+    if (c->volPrefetched) { // mms_prefetch_density already has the copy under way (or done)
+        MMS_CUDA(c, cudaEventSynchronize(c->volCopied));
+        if (int rc = checkDeviceError(c)) return rc;
+        *hv = c->hVol.as<float>();
+        if (hrgb) *hrgb = c->haveColour ? c->hRgb.as<float>() : nullptr;
+        return MMS_OK;
+    }
     const size_t bytes = static_cast<size_t>(c->grid.res[0]) * c->grid.res[1] * c->nz * 4;
     if (!c->hVol.ensure(bytes)) return c->fail(MMS_ERR_NOMEM, "pinned allocation of %zu bytes failed", bytes);
     const bool wantRgb = hrgb && c->haveColour;
@@ -801,6 +851,7 @@ int mms_set_density(mms_ctx* c, const float* volume) {
     c->haveDensity = true;
     c->haveColour = false;
     c->haveMesh = false;
+    c->volPrefetched = false;
     return MMS_OK;
 }
 
@@ -868,7 +919,8 @@ int mms_count_isosurface(mms_ctx* c, float iso, uint64_t* ntris) {
     DevState* ds = c->dstate.as<DevState>();
     exclusiveScan(c->segCount.as<unsigned>(), c->segOffset.as<unsigned>(), nullptr, c->tileSums.as<unsigned>(), static_cast<unsigned>(nseg),
         &ds->totalTris, st, c->launches);
-    MMS_CUDA(c, cudaMemcpyAsync(c->hState.p, c->dstate.p, sizeof(DevState), cudaMemcpyDeviceToHost, st));
+    publish_state_kernel<<<1, 1, 0, st>>>(c->dstate.as<DevState>(), c->hState.as<DevState>());
+    ++c->launches;
     MMS_CUDA(c, cudaStreamSynchronize(st)); // the one host round trip: the mesh size decides the allocation
     c->ntris = c->hState.as<DevState>()->totalTris;
     if (ntris) *ntris = c->ntris;

@@ -369,8 +369,9 @@ class SlabJob:
             self._gnrm = _tensor_from_ptr(torch, R["nrm"], total * 9, self.dev)
 
     # ---- steps ------------------------------------------------------------------------------------------------
-    def _compute(self, xyz_ptr, n, extract=True, more=()):
-        """more: further (device pointer, count) pieces of the frame (the received halo)"""
+    def _compute(self, xyz_ptr, n, extract=True, more=(), prefetch=False):
+        """more: further (device pointer, count) pieces of the frame (the received halo); prefetch: start the volume's D2H copy before
+        the isosurface kernels (end-to-end arm: the copy overlaps marching cubes)"""
         s = self.surf
         s.clear_particles()
         if self.protein:  # x y z r | R G B A interleaved, stride 32 (FLOAT_XYZR + FLOAT_RGBA)
@@ -385,6 +386,8 @@ class SlabJob:
             t = _tensor_from_ptr(self.torch, ptr, 2, self.dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             s.normalize_device(ptr)
+        if prefetch:
+            s.prefetch_density()
         if extract:
             s.extract_isosurface(self.iso)
 
@@ -423,7 +426,7 @@ class SlabJob:
         host memory and the volume still goes back."""
         torch = self.torch
         if self.world == 1:
-            self._compute(self.h_xyz.data_ptr(), self.n_local)
+            self._compute(self.h_xyz.data_ptr(), self.n_local, prefetch=True)
             self.surf.get_density(copy=False, with_rgb=self.protein)
             if mesh_to_host:
                 self.surf.get_mesh(copy=False, colours=self.protein)
@@ -431,7 +434,7 @@ class SlabJob:
             d = self.h_xyz.to(self.dev, non_blocking=True)
             recv = self._exchange(d)
             self._keep = [d]
-            self._compute(d.data_ptr(), self.n_local, more=((recv.data_ptr(), recv.shape[0]),))
+            self._compute(d.data_ptr(), self.n_local, more=((recv.data_ptr(), recv.shape[0]),), prefetch=True)
             self.surf.get_density(copy=False)
             self._allgather_counts()
             torch.cuda.current_stream().synchronize()
@@ -440,7 +443,7 @@ class SlabJob:
             recv = self._exchange(d)
             self._keep = [d]
             fused = self.gather == "fused"
-            self._compute(d.data_ptr(), self.n_local, extract=not fused, more=((recv.data_ptr(), recv.shape[0]),))
+            self._compute(d.data_ptr(), self.n_local, extract=not fused, more=((recv.data_ptr(), recv.shape[0]),), prefetch=True)
             self.surf.get_density(copy=False)
             if fused:
                 self._emit_to_root()

@@ -54,3 +54,28 @@ def test_variants_bit_identical(case):
         other = _run(xyz, box, res, cyclic, radius, 0.4, env)
         assert np.array_equal(base[0].view(np.uint32), other[0].view(np.uint32)), f"density differs with {env}"
         assert base[1].shape == other[1].shape and np.array_equal(base[1], other[1]) and np.array_equal(base[2], other[2]), f"mesh differs with {env}"
+
+
+def test_prefetched_volume_copy_equals_plain_copy():
+    """mms_prefetch_density: the D2H copy that overlaps the isosurface kernels delivers the same volume as the plain copy"""
+    n, res = 120_000, (96, 80, 64)
+    box = tuple(float(np.float32(r - 1) * np.float32(0.4563)) for r in res)
+    xyz = synth.uniform_box(n, 1.0) * np.asarray(box, np.float32)
+    out = []
+    for prefetch in (False, True):
+        s = mm.Surf(0)
+        s.set_grid((0, 0, 0), box, res, (True, True, True))
+        s.set_params(mode=0, aggregator=0, normalize=1, sigma=1.0)
+        for _ in range(2):  # second frame: the prefetch of frame 1 must not disturb frame 2
+            s.clear_particles()
+            s.push_particles([dict(vtx=xyz, vtx_type=1, count=n, global_radius=0.5)])
+            s.compute_density()
+            if prefetch:
+                s.prefetch_density()
+            s.extract_isosurface(0.4)
+            vol = s.get_density()
+            pos, _ = s.get_mesh()
+        out.append((vol.copy(), pos.copy()))
+        s.close()
+    assert np.array_equal(out[0][0].view(np.uint32), out[1][0].view(np.uint32)) and np.array_equal(out[0][1], out[1][1])
+    assert out[0][0].max() == 1.0 and out[0][1].shape[0] > 1000
