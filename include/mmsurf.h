@@ -12,7 +12,9 @@
  *                                   (ParticlesToDensity.cpp:458-486; SimpleSphericalParticles.h:27-50 enums,
  *                                   :86-178 type -> float conversion)
  *   mms_compute_density             createVolumeCPU's binning + scatter + reduction + range + normalise
- *                                   (ParticlesToDensity.cpp:561-626, :669-682)
+ *                                   (ParticlesToDensity.cpp:561-626, :669-682); aggregator 2 also :629-667
+ *   mms_push_particles_dir, mms_get_vector_field   the direction accessors and the vector-field outputs of aggregator 2
+ *                                   (ParticlesToDensity.cpp:484-508, 629-667)
  *   mms_get_density / _range        what getDataCallback hands to VolumetricDataCall::SetData / metadata
  *                                   Min/MaxValues (ParticlesToDensity.cpp:249-295)
  *   mms_extract_isosurface          trisoup_gl::volumetrics::IsoSurface::buildMesh
@@ -89,7 +91,8 @@ typedef struct mms_grid {
 
 typedef struct mms_params {
     int32_t mode;            /* mms_mode */
-    int32_t aggregator;      /* ParticlesToDensity "aggregator": 0 position, 1 intensity-weighted; 2 -> MMS_ERR_UNSUPPORTED */
+    int32_t aggregator;      /* ParticlesToDensity "aggregator": 0 position, 1 intensity-weighted, 2 direction-weighted vector field
+                                (P2D mode, sigma <= 1; directions come in through mms_push_particles_dir, results through mms_get_vector_field) */
     int32_t normalize;       /* ParticlesToDensity "normalize" */
     int32_t defer_normalize; /* 1: compute_density leaves the raw sums; caller normalises with mms_normalize (slabs) */
     float sigma;             /* ParticlesToDensity "sigma" */
@@ -124,6 +127,11 @@ int mms_clear_particles(mms_ctx* ctx);
  * is still being read back (streaming). */
 int mms_push_particles(mms_ctx* ctx, int32_t nlists, const mms_list* lists);
 
+/* The same with per-list direction data (SimpleSphericalParticles::DIRDATA_FLOAT_XYZ: 3 floats, SimpleSphericalParticles.h:58,179-193,504-510)
+ * for aggregator 2: dirs[i] = direction pointer of lists[i] or NULL (DIRDATA_NONE: the reference's accessors then deliver 0),
+ * dir_strides[i] = its stride in bytes (0 = 12).  dirs == NULL is mms_push_particles. */
+int mms_push_particles_dir(mms_ctx* ctx, int32_t nlists, const mms_list* lists, const void* const* dirs, const uint32_t* dir_strides);
+
 int mms_compute_density(mms_ctx* ctx);
 /* Range of the (un-normalised) sums of the last compute_density: the reference's minDens/maxDens. */
 int mms_get_density_range(mms_ctx* ctx, float minmax[2]);
@@ -143,6 +151,13 @@ int mms_prefetch_density(mms_ctx* ctx);
 /* Host copy (library-owned pinned memory) of the slab: nz*res[1]*res[0] floats, x fastest. rgb may be NULL. */
 int mms_get_density(mms_ctx* ctx, const float** host_volume, const float** host_rgb);
 int mms_get_density_device(mms_ctx* ctx, const float** dev_volume, const float** dev_rgb);
+/* Aggregator 2 (IVecToSingleCell_Volume, ParticlesToDensity.cpp:493-508,629-667): what createVolumeCPU leaves behind per voxel,
+ * x fastest, slab-shaped.  vec = the 3-component volume handed to VolumetricDataCall (sum(w d)/sum(w), after "normalize" each
+ * component (c - minDens)/(maxDens - minDens)); magnitude = the un-normalised |v| ("densities"; mms_get_density_range is its
+ * range = minDens/maxDens, mms_get_density / the isosurface see this scalar volume); direction = v/|v| (0 where |v| == 0).
+ * Any of the three pointers may be NULL.  Host pointers are library-owned pinned memory. */
+int mms_get_vector_field(mms_ctx* ctx, const float** host_vec, const float** host_magnitude, const float** host_direction);
+int mms_get_vector_field_device(mms_ctx* ctx, const float** dev_vec, const float** dev_magnitude, const float** dev_direction);
 /* Use a caller-supplied volume instead of computing one (IsoSurface fed by another VolumetricDataCall source).
  * `volume` may be host or device memory, res-shaped for the current slab. */
 int mms_set_density(mms_ctx* ctx, const float* volume);

@@ -16,7 +16,7 @@ MODE_P2D_BUMP, MODE_QS_GAUSS = 0, 1
 ISO_MARCHING_CUBES, ISO_MARCHING_TETS = 0, 1
 
 EXPORTS = ["mms_create", "mms_destroy", "mms_last_error", "mms_set_grid", "mms_set_slab", "mms_set_params",
-           "mms_clear_particles", "mms_push_particles", "mms_compute_density", "mms_get_density_range", "mms_normalize", "mms_density_range_device", "mms_normalize_device", "mms_set_stream",
+           "mms_clear_particles", "mms_push_particles", "mms_push_particles_dir", "mms_get_vector_field", "mms_get_vector_field_device", "mms_compute_density", "mms_get_density_range", "mms_normalize", "mms_density_range_device", "mms_normalize_device", "mms_set_stream",
            "mms_get_density", "mms_prefetch_density", "mms_get_density_device", "mms_set_density", "mms_extract_isosurface", "mms_set_isosurface_mode", "mms_count_isosurface", "mms_emit_isosurface", "mms_device_alloc",
            "mms_device_free", "mms_route_particles", "mms_ipc_export", "mms_ipc_open", "mms_ipc_close", "mms_get_mesh",
            "mms_get_mesh_device", "mms_get_home_voxels", "mms_get_cell_tricounts", "mms_get_timings", "mms_synchronize",
@@ -81,6 +81,9 @@ def load_library():
     L.mms_set_params.argtypes = [vp, C.POINTER(MmsParams)]
     L.mms_clear_particles.argtypes = [vp]
     L.mms_push_particles.argtypes = [vp, C.c_int32, C.POINTER(MmsList)]
+    L.mms_push_particles_dir.argtypes = [vp, C.c_int32, C.POINTER(MmsList), C.POINTER(vp), C.POINTER(C.c_uint32)]
+    L.mms_get_vector_field.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    L.mms_get_vector_field_device.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     L.mms_compute_density.argtypes = [vp]
     L.mms_get_density_range.argtypes = [vp, C.POINTER(C.c_float)]
     L.mms_normalize.argtypes = [vp, C.c_float, C.c_float]
@@ -200,8 +203,11 @@ class Surf:
 
     def push_particles(self, lists):
         """lists: dicts {vtx: ndarray | int address (host or device), vtx_type, count, [vtx_stride], [col], [col_type],
-        [col_stride], [global_radius], [global_rgba], [irange]}"""
+        [col_stride], [global_radius], [global_rgba], [irange], [dir: ndarray | address of DIRDATA_FLOAT_XYZ], [dir_stride]}"""
         arr = (MmsList * len(lists))()
+        dirs = (C.c_void_p * max(len(lists), 1))()
+        dstrides = (C.c_uint32 * max(len(lists), 1))()
+        have_dirs = False
         for i, l in enumerate(lists):
             for key, fld in (("vtx", "vtx"), ("col", "col")):
                 v = l.get(key)
@@ -224,7 +230,19 @@ class Surf:
                 arr[i].global_rgba[k] = rgba[k]
             ir = l.get("irange", (0.0, 1.0))
             arr[i].irange[0], arr[i].irange[1] = ir
-        self._chk(self.L.mms_push_particles(self.h, len(lists), arr))
+            d = l.get("dir")
+            if d is not None:
+                if isinstance(d, np.ndarray):
+                    d = np.ascontiguousarray(d)
+                    self._keep.append(d)
+                    d = d.ctypes.data
+                dirs[i] = int(d)
+                dstrides[i] = int(l.get("dir_stride", 0))
+                have_dirs = True
+        if have_dirs:
+            self._chk(self.L.mms_push_particles_dir(self.h, len(lists), arr, dirs, dstrides))
+        else:
+            self._chk(self.L.mms_push_particles(self.h, len(lists), arr))
 
     def compute_density(self):
         self._chk(self.L.mms_compute_density(self.h))
@@ -267,6 +285,14 @@ class Surf:
             return v
         c = _np_view(q.value, (self.nz, self.res[1], self.res[0], 3), np.float32) if q.value else None
         return v, (c.copy() if (copy and c is not None) else c)
+
+    def get_vector_field(self):
+        """Aggregator 2: (vec [nz,sy,sx,3] as handed to VolumetricDataCall, magnitude [nz,sy,sx] un-normalised, direction [nz,sy,sx,3])."""
+        p, q, r = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self._chk(self.L.mms_get_vector_field(self.h, C.byref(p), C.byref(q), C.byref(r)))
+        shape = (self.nz, self.res[1], self.res[0])
+        return (_np_view(p.value, shape + (3,), np.float32).copy(), _np_view(q.value, shape, np.float32).copy(),
+                _np_view(r.value, shape + (3,), np.float32).copy())
 
     def density_device_ptr(self):
         p = C.c_void_p()

@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(256) bin_count_kernel(Geo g, ListDev l, unsign
     }
 }
 
-/** aux: 0 floats (plain), 1 float (aggregator 1: intensity) or 4 floats (QuickSurf colour) per record. */
+/** aux: 0 floats (plain), 1 float (aggregator 1: intensity) or 4 floats (QuickSurf colour; aggregator 2: direction) per record. */
 __global__ void __launch_bounds__(256) bin_scatter_kernel(Geo g, ListDev l, unsigned* __restrict__ cursor,
     float4* __restrict__ recs, float* __restrict__ aux, int auxN) {
     const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(256) bin_scatter_kernel(Geo g, ListDev l, unsi
         if (auxN == 1) {
             aux[slot] = fetchColourRaw(l, j).x; // iAcc->Get_f (ParticlesToDensity.cpp:483,515)
         } else if (auxN == 4) {
-            reinterpret_cast<float4*>(aux)[slot] = quicksurfColour(l, fetchColourRaw(l, j));
+            reinterpret_cast<float4*>(aux)[slot] = g.mode == 0 ? fetchDirection(l, j) : quicksurfColour(l, fetchColourRaw(l, j));
         }
     }
 }

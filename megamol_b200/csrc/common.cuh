@@ -17,7 +17,7 @@ struct Geo {
     int cshift;   // log2(cell edge in voxels)
     int nc[3];    // cell grid = ceil(s / cell)
     float sigma;
-    int agg;      // 0 position, 1 intensity-weighted
+    int agg;      // 0 position, 1 intensity-weighted, 2 direction-weighted (vector field)
     int mode;     // 0 P2D bump, 1 QuickSurf Gaussian
     float radscale, gausslim;
     int colour;
@@ -39,6 +39,9 @@ struct ListDev {
     int valign; // 16: float4 loads ok, 4: scalar float loads ok, 1: bytewise
     int calign;
     int gf[3];  // lists with a global radius: support half-width per axis (filter size / Gaussian cut-off), set per compute
+    const char* dir; // DIRDATA_FLOAT_XYZ (aggregator 2) or nullptr = DIRDATA_NONE: the accessors deliver 0 (SimpleSphericalParticles.h:179-193)
+    unsigned dstride;
+    int dalign;
 };
 
 /** Values produced on the device and consumed by later kernels without a host round trip. */
@@ -132,6 +135,13 @@ __device__ __forceinline__ float4 fetchColourRaw(const ListDev& l, unsigned long
     default: c = make_float4(l.gcol[0], l.gcol[1], l.gcol[2], l.gcol[3]);
     }
     return c;
+}
+
+/** Direction accessors dx/dy/dz as floats (ParticlesToDensity.cpp:484-486,497-499). */
+__device__ __forceinline__ float4 fetchDirection(const ListDev& l, unsigned long long j) {
+    if (!l.dir) return make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    const char* p = l.dir + j * l.dstride;
+    return make_float4(loadF32(p, l.dalign), loadF32(p + 4, l.dalign), loadF32(p + 8, l.dalign), 0.0f);
 }
 
 /** QuickSurf's colour conversion (QuickSurf.cpp:511-577): everything to [0,1] RGB. */

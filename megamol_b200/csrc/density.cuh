@@ -131,14 +131,17 @@ __device__ __forceinline__ float rcpApprox(float x) {
 }
 
 /** Contribution of one voxel; returns false if the voxel is outside the kernel support. */
-template<int MODE>
+template<int MODE, bool PRECISE = false>
 __device__ __forceinline__ bool kernelValue(float d2, float eps, float k0, float& w, float lim2 = -1.0f) {
     if (MODE == 0) {
         const float dis = __fsqrt_rn(d2);
         if (dis >= eps) return false;
         const float q = __fmul_rn(k0, dis);
         const float den = __fsub_rn(1.0f, __fmul_rn(q, q));
-        w = ex2Approx(-1.4426950408889634f * rcpApprox(den));
+        // PRECISE (aggregator 2): the vector field is a QUOTIENT of weighted sums, so a voxel whose only contributors sit in the far
+        // tail of the bump still gets v = d -- as long as the weight does not flush to zero and keeps its relative accuracy there:
+        // IEEE division and expf (2 ulp, subnormal results kept) instead of the SFU pair (rcp.approx in the exponent, ftz)
+        w = PRECISE ? expf(__fdiv_rn(-1.0f, den)) : ex2Approx(-1.4426950408889634f * rcpApprox(den));
         return true;
     } else {
         if (!(d2 < (lim2 >= 0.0f ? lim2 : __fmul_rn(eps, eps)))) return false;
@@ -626,6 +629,10 @@ __global__ void __launch_bounds__(GT_THREADS, 2) density_gather_kernel(Geo g, De
                     c.k0 = __fdiv_rn(1.0f, eps);
                     c.lim = eps;
                     if (auxN == 1) c.cr = aux[idx];
+                    if (COLOUR && auxN == 4) { // aggregator 2: the particle's direction (dxAcc/dyAcc/dzAcc, ParticlesToDensity.cpp:497-499)
+                        const float4 d = reinterpret_cast<const float4*>(aux)[idx];
+                        c.cr = d.x, c.cg = d.y, c.cb = d.z;
+                    }
                 } else {
                     const float sr = __fmul_rn(p.w, g.radscale);
                     eps = __fmul_rn(g.gausslim, sr);
@@ -705,8 +712,13 @@ __global__ void __launch_bounds__(GT_THREADS, 2) density_gather_kernel(Geo g, De
                             accG[k] = __fadd_rn(accG[k], __fmul_rn(w, B.z));
                             accB[k] = __fadd_rn(accB[k], __fmul_rn(w, B.w));
                         }
-                    } else if (kernelValue<MODE>(d2, MODE == 0 ? B.x : 0.0f, A.w, w, B.x)) {
-                        if (MODE == 0) {
+                    } else if (kernelValue<MODE, (MODE == 0 && COLOUR)>(d2, MODE == 0 ? B.x : 0.0f, A.w, w, B.x)) {
+                        if (MODE == 0 && COLOUR) { // aggregator 2: weights += w, vol += w * dir (:501-505), product and sum rounded separately
+                            acc[k] = __fadd_rn(acc[k], w);
+                            accR[k] = __fadd_rn(accR[k], __fmul_rn(w, B.y));
+                            accG[k] = __fadd_rn(accG[k], __fmul_rn(w, B.z));
+                            accB[k] = __fadd_rn(accB[k], __fmul_rn(w, B.w));
+                        } else if (MODE == 0) {
                             acc[k] = __fadd_rn(acc[k], g.agg == 1 ? __fmul_rn(w, B.y) : w);
                         } else {
                             acc[k] = __fadd_rn(acc[k], w);
@@ -734,7 +746,37 @@ __global__ void __launch_bounds__(GT_THREADS, 2) density_gather_kernel(Geo g, De
         }
     }
     const unsigned kmin = __reduce_min_sync(0xffffffffu, floatKey(vmin)), kmax = __reduce_max_sync(0xffffffffu, floatKey(vmax));
-    if (lane == 0 && kmin <= kmax) {
+    if (lane == 0 && kmin <= kmax && !(MODE == 0 && COLOUR)) { // aggregator 2: the range is that of |v|, taken by vector_finalize_kernel
+        atomicMin(&st->minKey, kmin);
+        atomicMax(&st->maxKey, kmax);
+    }
+}
+
+/**
+ * Aggregator 2 (IVecToSingleCell_Volume), the per-voxel pass after the accumulation (ParticlesToDensity.cpp:634-657):
+ *   v = sum(w d) / (sum(w) == 0 ? 1 : sum(w));  density = sqrt(vx vx + vy vy + vz vz);  direction = density == 0 ? 0 : v / density
+ * and the range of the densities (minDens starts at FLT_MAX, maxDens at 0).  In: weights = sum(w), vec = sum(w d).
+ * Out: vec = v, weights -> density, dir = direction.  Individually rounded operations, the reference's evaluation order.
+ */
+__global__ void __launch_bounds__(256) vector_finalize_kernel(float* __restrict__ weights, float* __restrict__ vec, float* __restrict__ dir,
+    size_t nvox, DevState* __restrict__ st) {
+    const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+    float vmin = INFINITY, vmax = 0.0f;
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvox; i += stride) {
+        const float w = weights[i];
+        const float div = w == 0.0f ? 1.0f : w;
+        const float x = __fdiv_rn(vec[3 * i + 0], div), y = __fdiv_rn(vec[3 * i + 1], div), z = __fdiv_rn(vec[3 * i + 2], div);
+        const float den = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z)));
+        vec[3 * i + 0] = x, vec[3 * i + 1] = y, vec[3 * i + 2] = z;
+        weights[i] = den;
+        const bool zero = den == 0.0f;
+        dir[3 * i + 0] = zero ? 0.0f : __fdiv_rn(x, den);
+        dir[3 * i + 1] = zero ? 0.0f : __fdiv_rn(y, den);
+        dir[3 * i + 2] = zero ? 0.0f : __fdiv_rn(z, den);
+        vmin = fminf(vmin, den), vmax = fmaxf(vmax, den); // std::max / std::min drop a NaN density the same way
+    }
+    const unsigned kmin = __reduce_min_sync(0xffffffffu, floatKey(vmin)), kmax = __reduce_max_sync(0xffffffffu, floatKey(vmax));
+    if ((threadIdx.x & 31) == 0) {
         atomicMin(&st->minKey, kmin);
         atomicMax(&st->maxKey, kmax);
     }

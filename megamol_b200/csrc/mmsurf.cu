@@ -151,6 +151,7 @@ struct mms_ctx {
     unsigned long long launches = 0;
     int cshift = 2, reach = 2;
     bool useGather = false, haveColour = false, splatV2ok = false;
+    bool haveVector = false; // aggregator 2: rgb = vector volume, vol = |v|, dirVol = unit directions
     McGeo mcGeo{};
     cudaStream_t ownStream = nullptr;
     DevBuf rangeBuf; // {-min, max} as floats for device-side all-reduce + normalise
@@ -161,8 +162,8 @@ struct mms_ctx {
     DevBuf routeCounts, routeOffsets, routeTile;
     PinBuf hRoute;
     DevBuf cellCount, cellStart, cursor, tileSums, recsA, recsB, auxA, auxB, vol, rgb, segCount, segOffset, meshPos, meshNrm,
-        meshCol, triCount, home, dstate;
-    PinBuf hState, hVol, hRgb, hPos, hNrm, hCol, hHome, hTri;
+        meshCol, triCount, home, dstate, dirVol;
+    PinBuf hState, hVol, hRgb, hPos, hNrm, hCol, hHome, hTri, hDir;
     cudaEvent_t ev[EV_COUNT]{};
     bool evSet[EV_COUNT]{};
     int smCount = 148;
@@ -421,9 +422,9 @@ int mms_destroy(mms_ctx* c) {
         DeviceGuard guard(c->device);
         mms_clear_particles(c);
         for (DevBuf* b : {&c->cellCount, &c->cellStart, &c->cursor, &c->tileSums, &c->recsA, &c->recsB, &c->auxA, &c->auxB, &c->vol,
-                 &c->rgb, &c->segCount, &c->segOffset, &c->meshPos, &c->meshNrm, &c->meshCol, &c->triCount, &c->home, &c->dstate, &c->routeCounts, &c->routeOffsets, &c->routeTile, &c->rangeBuf})
+                 &c->rgb, &c->segCount, &c->segOffset, &c->meshPos, &c->meshNrm, &c->meshCol, &c->triCount, &c->home, &c->dstate, &c->routeCounts, &c->routeOffsets, &c->routeTile, &c->rangeBuf, &c->dirVol})
             b->release();
-        for (PinBuf* b : {&c->hState, &c->hVol, &c->hRgb, &c->hPos, &c->hNrm, &c->hCol, &c->hHome, &c->hTri, &c->hRoute}) b->release();
+        for (PinBuf* b : {&c->hState, &c->hVol, &c->hRgb, &c->hPos, &c->hNrm, &c->hCol, &c->hHome, &c->hTri, &c->hRoute, &c->hDir}) b->release();
         cudaStreamSynchronize(c->stream);
         cudaStreamSynchronize(c->copyStream);
         for (auto& a : c->arena) {
@@ -472,9 +473,9 @@ int mms_set_params(mms_ctx* c, const mms_params* p) {
     if (!c || !p) return MMS_ERR_INVALID;
     if (p->mode != MMS_MODE_P2D_BUMP && p->mode != MMS_MODE_QS_GAUSS) return c->fail(MMS_ERR_INVALID, "unknown mode %d", p->mode);
     if (p->mode == MMS_MODE_P2D_BUMP) {
-        if (p->aggregator == 2)
-            return c->fail(MMS_ERR_UNSUPPORTED, "aggregator 2 (IVecToSingleCell_Volume, vector field) is not implemented on this path");
-        if (p->aggregator != 0 && p->aggregator != 1) return c->fail(MMS_ERR_INVALID, "unknown aggregator %d", p->aggregator);
+        if (p->aggregator < 0 || p->aggregator > 2) return c->fail(MMS_ERR_INVALID, "unknown aggregator %d", p->aggregator);
+        if (p->aggregator == 2 && p->sigma > 1.0f)
+            return c->fail(MMS_ERR_UNSUPPORTED, "aggregator 2 (vector field) with sigma > 1 is not implemented");
         if (!(p->sigma > 0.0f)) return c->fail(MMS_ERR_INVALID, "sigma must be > 0");
     } else {
         if (!(p->radscale > 0.0f) || !(p->gausslim > 0.0f)) return c->fail(MMS_ERR_INVALID, "radscale and gausslim must be > 0");
@@ -483,7 +484,7 @@ int mms_set_params(mms_ctx* c, const mms_params* p) {
     return MMS_OK;
 }
 
-int mms_push_particles(mms_ctx* c, int32_t nlists, const mms_list* lists) {
+static int pushLists(mms_ctx* c, int32_t nlists, const mms_list* lists, const void* const* dirs, const uint32_t* dirStrides) {
     if (!c || nlists < 0 || (nlists > 0 && !lists)) return MMS_ERR_INVALID;
     DeviceGuard guard(c->device);
     if (c->lists.size() + nlists > static_cast<size_t>(kMaxLists)) return c->fail(MMS_ERR_UNSUPPORTED, "more than %d particle lists", kMaxLists);
@@ -541,6 +542,25 @@ int mms_push_particles(mms_ctx* c, int32_t nlists, const mms_list* lists) {
             }
             c->uploadPending = true;
         }
+        if (dirs && dirs[i]) { // DIRDATA_FLOAT_XYZ; stride 0 = tightly packed (SimpleSphericalParticles.h:504-510)
+            d.dstride = dirStrides && dirStrides[i] ? dirStrides[i] : 12u;
+            const size_t dbytes = (l.count - 1) * static_cast<size_t>(d.dstride) + 12;
+            const char* hd = static_cast<const char*>(dirs[i]);
+            if (isDevicePointer(hd)) {
+                d.dir = hd;
+            } else {
+                if (!arena.waited) {
+                    if (arena.consumedSet) MMS_CUDA(c, cudaStreamWaitEvent(c->copyStream, arena.consumed, 0));
+                    arena.waited = true;
+                }
+                char* dd = arena.alloc(dbytes, reinterpret_cast<uintptr_t>(hd) & 15u);
+                if (!dd) return c->fail(MMS_ERR_NOMEM, "device allocation of %zu bytes for directions of list %d failed", dbytes, i);
+                MMS_CUDA(c, cudaMemcpyAsync(dd, hd, dbytes, cudaMemcpyHostToDevice, c->copyStream));
+                d.dir = dd;
+                c->uploadPending = true;
+            }
+            d.dalign = alignOf(d.dir, d.dstride, 4) >= 4 ? 4 : 1;
+        }
         d.valign = alignOf(d.vtx, d.vstride, l.vtx_type == MMS_VERT_DOUBLE_XYZ ? 8 : (l.vtx_type == MMS_VERT_FLOAT_XYZR ? 16 : 4));
         if (l.vtx_type == MMS_VERT_DOUBLE_XYZ && d.valign < 8) d.valign = 1;
         if ((l.vtx_type == MMS_VERT_FLOAT_XYZ || l.vtx_type == MMS_VERT_FLOAT_XYZR) && d.valign < 4) d.valign = 1;
@@ -555,6 +575,12 @@ int mms_push_particles(mms_ctx* c, int32_t nlists, const mms_list* lists) {
     if (c->uploadPending) MMS_CUDA(c, cudaEventRecord(c->uploadDone, c->copyStream));
     // results of the previous compute stay readable: pushing frame k+1 while frame k is being read back is the streaming pattern
     return MMS_OK;
+}
+
+int mms_push_particles(mms_ctx* c, int32_t nlists, const mms_list* lists) { return pushLists(c, nlists, lists, nullptr, nullptr); }
+
+int mms_push_particles_dir(mms_ctx* c, int32_t nlists, const mms_list* lists, const void* const* dirs, const uint32_t* dir_strides) {
+    return pushLists(c, nlists, lists, dirs, dir_strides);
 }
 
 int mms_compute_density(mms_ctx* c) {
@@ -598,7 +624,8 @@ int mms_compute_density(mms_ctx* c) {
         const float epsMax = (c->params.mode == MMS_MODE_P2D_BUMP) ? c->params.sigma * rmax : c->params.gausslim * c->params.radscale * rmax;
         int need = 1;
         for (int a = 0; a < 3; ++a) need = std::max(need, static_cast<int>(std::ceil(epsMax / g0.sd[a] + 0.02f)));
-        c->useGather = c->params.mode == MMS_MODE_QS_GAUSS || need > 8;
+        // aggregator 2 keeps four sums per voxel: the register-accumulating gather kernel has them (as the QuickSurf colour sums)
+        c->useGather = c->params.mode == MMS_MODE_QS_GAUSS || need > 8 || (c->params.mode == MMS_MODE_P2D_BUMP && c->params.aggregator == 2);
         if (c->useGather) {
             if (need > 96) return c->fail(MMS_ERR_UNSUPPORTED, "kernel support of %d voxels per side is not supported", need);
             if (c->params.mode == MMS_MODE_P2D_BUMP && c->params.sigma > 1.0f)
@@ -624,8 +651,10 @@ int mms_compute_density(mms_ctx* c) {
     const size_t ncells = static_cast<size_t>(g.nc[0]) * g.nc[1] * g.nc[2];
     const size_t nvox = static_cast<size_t>(g.s[0]) * g.s[1] * g.nz;
     const bool colour = g.mode == 1 && c->params.colour != 0;
-    const int auxN = (g.mode == 0 && g.agg == 1) ? 1 : (colour ? 4 : 0);
-    if (colour && !c->rgb.ensure(nvox * 12)) return c->fail(MMS_ERR_NOMEM, "device allocation failed (colour volume)");
+    const bool vector = g.mode == 0 && g.agg == 2;
+    const int auxN = (g.mode == 0 && g.agg == 1) ? 1 : ((colour || vector) ? 4 : 0);
+    if ((colour || vector) && !c->rgb.ensure(nvox * 12)) return c->fail(MMS_ERR_NOMEM, "device allocation failed (colour / vector volume)");
+    if (vector && !c->dirVol.ensure(nvox * 12)) return c->fail(MMS_ERR_NOMEM, "device allocation failed (direction volume)");
     const size_t n = static_cast<size_t>(c->nparticles);
     const unsigned ntiles = static_cast<unsigned>((ncells + kScanTile - 1) / kScanTile);
     if (!c->cellCount.ensure(ncells * 4) || !c->cellStart.ensure((ncells + 1) * 4) || !c->cursor.ensure(ncells * 4) ||
@@ -668,7 +697,8 @@ int mms_compute_density(mms_ctx* c) {
         const float* A = c->auxB.as<float>();
         const unsigned* CS = c->cellStart.as<unsigned>();
         DevState* DS = c->dstate.as<DevState>();
-        if (g.mode == 0) density_gather_kernel<0, false><<<grid, GT_THREADS, 0, st>>>(g, DS, R, A, auxN, CS, c->vol.as<float>(), nullptr, c->reach);
+        if (vector) density_gather_kernel<0, true><<<grid, GT_THREADS, 0, st>>>(g, DS, R, A, auxN, CS, c->vol.as<float>(), c->rgb.as<float>(), c->reach);
+        else if (g.mode == 0) density_gather_kernel<0, false><<<grid, GT_THREADS, 0, st>>>(g, DS, R, A, auxN, CS, c->vol.as<float>(), nullptr, c->reach);
         else if (colour) density_gather_kernel<1, true><<<grid, GT_THREADS, 0, st>>>(g, DS, R, A, auxN, CS, c->vol.as<float>(), c->rgb.as<float>(), c->reach);
         else density_gather_kernel<1, false><<<grid, GT_THREADS, 0, st>>>(g, DS, R, A, auxN, CS, c->vol.as<float>(), nullptr, c->reach);
     } else {
@@ -689,13 +719,21 @@ int mms_compute_density(mms_ctx* c) {
                 c->auxB.as<float>(), auxN, c->cellStart.as<unsigned>(), c->vol.as<float>(), c->reach);
     }
     c->haveColour = colour;
+    c->haveVector = vector;
     ++c->launches;
+    if (vector) {
+        vector_finalize_kernel<<<gridFor(nvox, 256, c->smCount * 16), 256, 0, st>>>(c->vol.as<float>(), c->rgb.as<float>(), c->dirVol.as<float>(), nvox,
+            c->dstate.as<DevState>());
+        ++c->launches;
+    }
     c->rec(EV_DEN1);
     c->normalized = false;
     c->volPrefetched = false;
     if (c->params.mode == MMS_MODE_P2D_BUMP && c->params.normalize && !c->params.defer_normalize) {
         c->rec(EV_NRM0);
-        normalize_state_kernel<<<c->smCount * 16, 256, 0, st>>>(c->vol.as<float>(), nvox, c->dstate.as<DevState>());
+        // aggregator 2: the reference normalises the three COMPONENTS with the range of the magnitudes (:669-682); |v| itself stays as it is
+        normalize_state_kernel<<<c->smCount * 16, 256, 0, st>>>(vector ? c->rgb.as<float>() : c->vol.as<float>(), vector ? nvox * 3 : nvox,
+            c->dstate.as<DevState>());
         ++c->launches;
         c->rec(EV_NRM1);
         c->normalized = true;
@@ -738,7 +776,7 @@ int mms_normalize(mms_ctx* c, float mn, float mx) {
     volatile float range = mx - mn;
     volatile float rcp = 1.0f / range;
     c->rec(EV_NRM0);
-    normalize_kernel<<<c->smCount * 8, 256, 0, c->stream>>>(c->vol.as<float>(), nvox, mn, rcp);
+    normalize_kernel<<<c->smCount * 8, 256, 0, c->stream>>>(c->haveVector ? c->rgb.as<float>() : c->vol.as<float>(), c->haveVector ? nvox * 3 : nvox, mn, rcp);
     ++c->launches;
     c->rec(EV_NRM1);
     MMS_CUDA(c, cudaGetLastError());
@@ -774,7 +812,8 @@ int mms_normalize_device(mms_ctx* c, const float* dev_negmin_max) {
     DeviceGuard guard(c->device);
     const size_t nvox = static_cast<size_t>(c->grid.res[0]) * c->grid.res[1] * c->nz;
     c->rec(EV_NRM0);
-    normalize_ptr_kernel<<<c->smCount * 16, 256, 0, c->stream>>>(c->vol.as<float>(), nvox, dev_negmin_max);
+    normalize_ptr_kernel<<<c->smCount * 16, 256, 0, c->stream>>>(c->haveVector ? c->rgb.as<float>() : c->vol.as<float>(), c->haveVector ? nvox * 3 : nvox,
+        dev_negmin_max);
     ++c->launches;
     c->rec(EV_NRM1);
     MMS_CUDA(c, cudaGetLastError());
@@ -850,8 +889,41 @@ int mms_set_density(mms_ctx* c, const float* volume) {
     MMS_CUDA(c, cudaMemcpyAsync(c->hState.p, c->dstate.p, sizeof(DevState), cudaMemcpyDeviceToHost, c->stream));
     c->haveDensity = true;
     c->haveColour = false;
+    c->haveVector = false;
     c->haveMesh = false;
     c->volPrefetched = false;
+    return MMS_OK;
+}
+
+int mms_get_vector_field(mms_ctx* c, const float** hvec, const float** hmag, const float** hdir) {
+    if (!c) return MMS_ERR_INVALID;
+    if (!c->haveDensity || !c->haveVector) return c->fail(MMS_ERR_INVALID, "no vector field has been computed (aggregator 2)");
+    DeviceGuard guard(c->device);
+    const size_t bytes = static_cast<size_t>(c->grid.res[0]) * c->grid.res[1] * c->nz * 4;
+    if ((hvec && !c->hRgb.ensure(bytes * 3)) || (hmag && !c->hVol.ensure(bytes)) || (hdir && !c->hDir.ensure(bytes * 3)))
+        return c->fail(MMS_ERR_NOMEM, "pinned allocation of %zu bytes failed", bytes * 3);
+    if (c->volPrefetched) { // never two copies into hVol at once
+        MMS_CUDA(c, cudaEventSynchronize(c->volCopied));
+        c->volPrefetched = false;
+    }
+    c->rec(EV_DV0);
+    if (hvec) MMS_CUDA(c, cudaMemcpyAsync(c->hRgb.p, c->rgb.p, bytes * 3, cudaMemcpyDeviceToHost, c->stream));
+    if (hmag) MMS_CUDA(c, cudaMemcpyAsync(c->hVol.p, c->vol.p, bytes, cudaMemcpyDeviceToHost, c->stream));
+    if (hdir) MMS_CUDA(c, cudaMemcpyAsync(c->hDir.p, c->dirVol.p, bytes * 3, cudaMemcpyDeviceToHost, c->stream));
+    c->rec(EV_DV1);
+    if (int rc = checkDeviceError(c)) return rc;
+    if (hvec) *hvec = c->hRgb.as<float>();
+    if (hmag) *hmag = c->hVol.as<float>();
+    if (hdir) *hdir = c->hDir.as<float>();
+    return MMS_OK;
+}
+
+int mms_get_vector_field_device(mms_ctx* c, const float** dvec, const float** dmag, const float** ddir) {
+    if (!c) return MMS_ERR_INVALID;
+    if (!c->haveDensity || !c->haveVector) return c->fail(MMS_ERR_INVALID, "no vector field has been computed (aggregator 2)");
+    if (dvec) *dvec = c->rgb.as<float>();
+    if (dmag) *dmag = c->vol.as<float>();
+    if (ddir) *ddir = c->dirVol.as<float>();
     return MMS_OK;
 }
 

@@ -7,7 +7,8 @@
 // What each function follows (paths relative to the reference checkout):
 //   home voxel / support box / bump kernel / aggregators 0,1 / reduction order / normalise
 //        plugins/datatools/src/ParticlesToDensity.cpp:416-434 (geometry), :458-476 (radius, kernel),
-//        :490-529 (aggregators), :561-620 (binning + scatter loop), :669-682 (range, normalise)
+//        :490-529 (aggregators), :561-620 (binning + scatter loop), :669-682 (range, normalise);
+//        aggregator 2 (vector field): :493-508, :629-667
 //   particle accessors (type -> float conversion, global radius, colour-R as intensity)
 //        plugins/geometry_calls/include/geometry_calls/SimpleSphericalParticles.h:86-178,
 //        plugins/geometry_calls/include/geometry_calls/Accessor.h:54-146
@@ -283,6 +284,94 @@ int mmo_density_p2d(int nlists, const mmo_list* lists, const mmo_grid* grid, flo
         const float rcp = 1.0f / (mx - mn);
 #pragma omp parallel for
         for (int64_t i = 0; i < static_cast<int64_t>(nvox); ++i) vol[i] = (vol[i] - mn) * rcp;
+    }
+    return 0;
+}
+
+/**
+ * ParticlesToDensity aggregator 2 (IVecToSingleCell_Volume): :493-508 (volOp), :629-667 (per-voxel pass), :669-682 (normalise).
+ * dirs[li] = DIRDATA_FLOAT_XYZ pointer of list li or NULL (DIRDATA_NONE: the accessors deliver 0), dir_strides[li] bytes (0 = 12).
+ * Out: vec = the 3-component volume the module hands to VolumetricDataCall (normalised component-wise with the range of the
+ * magnitudes if `normalize`), mag = |v| before normalisation ("densities"), dir = v/|v| ("directions"), minmax = minDens/maxDens
+ * (minDens starts at FLT_MAX, maxDens at 0).  Accumulation order = particle order = the reference at ONE OpenMP thread.
+ */
+int mmo_density_p2d_vector(int nlists, const mmo_list* lists, const void* const* dirs, const uint32_t* dir_strides, const mmo_grid* grid,
+    float sigma, int normalize, float* vec, float* mag, float* dir, float minmax[2]) {
+    const Geometry g = geometry(*grid);
+    const int sx = g.s[0], sy = g.s[1], sz = g.s[2];
+    const size_t nvox = static_cast<size_t>(sx) * sy * sz;
+    std::vector<float> weights(nvox, 0.0f);
+    std::fill(vec, vec + 3 * nvox, 0.0f);
+    for (int li = 0; li < nlists; ++li) {
+        const mmo_list& l = lists[li];
+        if (l.vtx_type == VERT_NONE) continue;
+        const char* dptr = dirs ? static_cast<const char*>(dirs[li]) : nullptr;
+        const unsigned dstride = (dir_strides && dir_strides[li]) ? dir_strides[li] : 12u;
+#pragma omp parallel
+        {
+            const int nt = omp_get_num_threads(), tid = omp_get_thread_num();
+            const int zlo = static_cast<int>(static_cast<long>(sz) * tid / nt);
+            const int zhi = static_cast<int>(static_cast<long>(sz) * (tid + 1) / nt); // exclusive
+            for (uint64_t j = 0; j < l.count && zlo < zhi; ++j) {
+                const Particle p = fetch(l, j);
+                const float rad = p.r;
+                if (rad == 0.0f) continue;
+                float d[3] = {0.0f, 0.0f, 0.0f};
+                if (dptr) std::memcpy(d, dptr + j * dstride, 12);
+                const int x = homeVoxel(p.x, g.min[0], g.sd[0]);
+                const int y = homeVoxel(p.y, g.min[1], g.sd[1]);
+                const int z = homeVoxel(p.z, g.min[2], g.sd[2]);
+                const int fx = static_cast<int>(std::ceil(rad / g.sd[0]));
+                const int fy = static_cast<int>(std::ceil(rad / g.sd[1]));
+                const int fz = static_cast<int>(std::ceil(rad / g.sd[2]));
+                const float eps = sigma * rad;
+                for (int hz = z - fz; hz <= z + fz; ++hz) {
+                    long tz = hz;
+                    if (g.cyc[2]) tz = floorMod(hz, sz);
+                    else if (hz < 0 || hz > sz - 1) continue;
+                    if (tz < zlo || tz >= zhi) continue;
+                    float zd = static_cast<float>(hz) * g.sd[2] + g.min[2];
+                    zd = std::fabs(zd - p.z);
+                    for (int hy = y - fy; hy <= y + fy; ++hy) {
+                        long ty = hy;
+                        if (g.cyc[1]) ty = floorMod(hy, sy);
+                        else if (hy < 0 || hy > sy - 1) continue;
+                        float yd = static_cast<float>(hy) * g.sd[1] + g.min[1];
+                        yd = std::fabs(yd - p.y);
+                        for (int hx = x - fx; hx <= x + fx; ++hx) {
+                            long tx = hx;
+                            if (g.cyc[0]) tx = floorMod(hx, sx);
+                            else if (hx < 0 || hx > sx - 1) continue;
+                            float xd = static_cast<float>(hx) * g.sd[0] + g.min[0];
+                            xd = std::fabs(xd - p.x);
+                            const float dis = std::sqrt(xd * xd + yd * yd + zd * zd);
+                            const float w = bump(dis, eps);
+                            const size_t o = tx + (ty + tz * sy) * static_cast<size_t>(sx);
+                            vec[3 * o + 0] += w * d[0];
+                            vec[3 * o + 1] += w * d[1];
+                            vec[3 * o + 2] += w * d[2];
+                            weights[o] += w;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    float mx = 0.0f, mn = std::numeric_limits<float>::max();
+    for (size_t i = 0; i < nvox; ++i) {
+        const float div = weights[i] == 0.0f ? 1.0f : weights[i];
+        vec[3 * i + 0] /= div, vec[3 * i + 1] /= div, vec[3 * i + 2] /= div;
+        const float den = std::sqrt(vec[3 * i + 0] * vec[3 * i + 0] + vec[3 * i + 1] * vec[3 * i + 1] + vec[3 * i + 2] * vec[3 * i + 2]);
+        if (mag) mag[i] = den;
+        if (dir)
+            for (int k = 0; k < 3; ++k) dir[3 * i + k] = den == 0.0f ? 0.0f : vec[3 * i + k] / den;
+        mx = std::max(mx, den);
+        mn = std::min(mn, den);
+    }
+    if (minmax) minmax[0] = mn, minmax[1] = mx;
+    if (normalize) {
+        const float rcp = 1.0f / (mx - mn);
+        for (size_t i = 0; i < 3 * nvox; ++i) vec[i] = (vec[i] - mn) * rcp;
     }
     return 0;
 }

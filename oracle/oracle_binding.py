@@ -71,6 +71,26 @@ def pack_lists(lists, struct=MmoList):
     return arr, keep
 
 
+def pack_dirs(lists):
+    """Per-list direction data (DIRDATA_FLOAT_XYZ): optional keys `dir` (ndarray or address) and `dir_stride` of the list dicts
+    -> (void* array, uint32 array, keep-alive list)."""
+    ptrs = (C.c_void_p * max(len(lists), 1))()
+    strides = (C.c_uint32 * max(len(lists), 1))()
+    keep = []
+    for i, l in enumerate(lists):
+        d = l.get("dir")
+        if d is None:
+            continue
+        if isinstance(d, np.ndarray):
+            d = np.ascontiguousarray(d)
+            keep.append(d)
+            ptrs[i] = d.ctypes.data
+        else:
+            ptrs[i] = int(d)
+        strides[i] = l.get("dir_stride", 0)
+    return ptrs, strides, keep
+
+
 def make_grid(bbox_min, bbox_extent, res, cyclic, struct=MmoGrid):
     g = struct()
     for a in range(3):
@@ -119,6 +139,24 @@ class Oracle:
         if rc:
             raise RuntimeError(f"mmo_density_p2d rc={rc}")
         return vol, (float(mm[0]), float(mm[1]))
+
+    def density_p2d_vector(self, lists, bbox_min, bbox_extent, res, cyclic, sigma=1.0, normalize=False):
+        """Aggregator 2.  Returns (vec [sz,sy,sx,3], magnitude [sz,sy,sx], direction [sz,sy,sx,3], (minDens, maxDens))."""
+        arr, keep = pack_lists(lists)
+        ptrs, strides, keep2 = pack_dirs(lists)
+        g = make_grid(bbox_min, bbox_extent, res, cyclic)
+        shape = (res[2], res[1], res[0])
+        vec = np.empty(shape + (3,), np.float32)
+        mag = np.empty(shape, np.float32)
+        dirs = np.empty(shape + (3,), np.float32)
+        mm = np.zeros(2, np.float32)
+        self.lib.mmo_density_p2d_vector.argtypes = [C.c_int, C.POINTER(MmoList), C.c_void_p, C.c_void_p, C.POINTER(MmoGrid), C.c_float,
+                                                    C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        rc = self.lib.mmo_density_p2d_vector(len(lists), arr, ptrs, strides, C.byref(g), float(sigma), int(normalize),
+                                             vec.ctypes.data, mag.ctypes.data, dirs.ctypes.data, mm.ctypes.data)
+        if rc:
+            raise RuntimeError(f"mmo_density_p2d_vector rc={rc}")
+        return vec, mag, dirs, (float(mm[0]), float(mm[1]))
 
     def normalize(self, vol, mn, mx):
         self.lib.mmo_normalize(vol.ctypes.data, vol.size, float(mn), float(mx))

@@ -50,6 +50,10 @@ class Harness:
                                     C.POINTER(C.c_double)]
         L.mmh_copy_mesh.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.mmh_mc_tables.argtypes = [C.c_void_p] * 5
+        L.mmh_set_directions.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint]
+        L.mmh_pull_grid_particles.argtypes = [C.c_void_p, C.c_uint, C.POINTER(C.c_uint64), C.POINTER(C.c_float), C.c_void_p, C.c_void_p,
+                                              C.c_void_p]
+        L.mmh_pull_info.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p, C.c_void_p, C.c_void_p]
         self.h = L.mmh_create()
         if not self.h:
             raise RuntimeError("mmh_create failed")
@@ -77,7 +81,8 @@ class Harness:
 
     def set_particles(self, lists, bbox, frame_id: int = 0):
         """lists: iterable of dicts with keys vtx (np array, raw bytes), vtx_type, vtx_stride, optional col/col_type/
-        col_stride, global_radius, global_rgba, irange. bbox = (minx,miny,minz,maxx,maxy,maxz)."""
+        col_stride, global_radius, global_rgba, irange, dir (np array of DIRDATA_FLOAT_XYZ) / dir_stride.
+        bbox = (minx,miny,minz,maxx,maxy,maxz)."""
         arr = (MmhList * len(lists))()
         self._keep = []
         for i, l in enumerate(lists):
@@ -108,6 +113,16 @@ class Harness:
         rc = self.lib.mmh_set_particles(self.h, len(lists), arr, bb, frame_id)
         if rc:
             raise RuntimeError(f"mmh_set_particles rc={rc}")
+        for i, l in enumerate(lists):
+            d = l.get("dir")
+            if d is None:
+                continue
+            if isinstance(d, np.ndarray):
+                d = np.ascontiguousarray(d)
+                self._keep.append(d)
+                d = d.ctypes.data
+            if self.lib.mmh_set_directions(self.h, i, int(d), int(l.get("dir_stride", 0))):
+                raise RuntimeError("mmh_set_directions failed")
 
     def set_p2d_params(self, res, cyclic=(True, True, True), normalize=True, sigma=1.0, aggregator=0,
                        for_surface=False):
@@ -125,21 +140,61 @@ class Harness:
         if rc:
             raise RuntimeError(f"no parameter {name!r} on module {module}")
 
-    def pull_volume(self, copy: bool = True):
+    def pull_volume(self, copy: bool = True, components: int = 1):
+        """components = 3 for aggregator 2 (the buffer must be sized before the call; the metadata confirms it)."""
         sx, sy, sz = self.res
         info = (C.c_uint64 * 5)()
         mm = (C.c_double * 2)()
         org = (C.c_float * 3)()
         sd = (C.c_float * 3)()
         ms = C.c_double()
-        out = np.empty((sz, sy, sx), dtype=np.float32) if copy else None
+        shape = (sz, sy, sx) if components == 1 else (sz, sy, sx, components)
+        out = np.empty(shape, dtype=np.float32) if copy else None
         rc = self.lib.mmh_pull_volume(self.h, self.frame, out.ctypes.data if copy else None, info, mm, org, sd,
                                       C.byref(ms))
         if rc:
             raise RuntimeError(f"mmh_pull_volume rc={rc}")
         meta = {"resolution": tuple(info[:3]), "components": info[3], "datahash": info[4], "min": mm[0], "max": mm[1],
                 "origin": tuple(org), "slicedist": tuple(sd), "ms": ms.value}
+        if copy and info[3] != components:
+            raise RuntimeError(f"volume has {info[3]} components, buffer was sized for {components}")
         return out, meta
+
+    def pull_grid_particles(self):
+        """'outParticles' of ParticlesToDensity (aggregator 2): dict(lists, count, vtx_type, col_type, dir_type, datahash,
+        global_radius, pos [n,3], dir [n,3], col [n])."""
+        info = (C.c_uint64 * 6)()
+        rad = C.c_float()
+        rc = self.lib.mmh_pull_grid_particles(self.h, self.frame, info, C.byref(rad), None, None, None)
+        if rc:
+            raise RuntimeError(f"mmh_pull_grid_particles rc={rc}")
+        n = int(info[1])
+        pos = np.zeros((n, 3), np.float32)
+        dirs = np.zeros((n, 3), np.float32)
+        col = np.zeros(n, np.float32)
+        if n:
+            rc = self.lib.mmh_pull_grid_particles(self.h, self.frame, info, C.byref(rad), pos.ctypes.data, dirs.ctypes.data,
+                                                  col.ctypes.data)
+            if rc:
+                raise RuntimeError(f"mmh_pull_grid_particles rc={rc}")
+        return {"lists": int(info[0]), "count": n, "vtx_type": int(info[2]), "col_type": int(info[3]), "dir_type": int(info[4]),
+                "datahash": int(info[5]), "global_radius": rad.value, "pos": pos, "dir": dirs, "col": col}
+
+    def pull_info(self):
+        """'outInfo' of ParticlesToDensity (aggregator 2): dict(columns, rows, datahash, names, ranges [c,2], data [rows,c])."""
+        dims = (C.c_uint64 * 3)()
+        rc = self.lib.mmh_pull_info(self.h, dims, None, None, None)
+        if rc:
+            raise RuntimeError(f"mmh_pull_info rc={rc}")
+        cols, rows = int(dims[0]), int(dims[1])
+        data = np.zeros((rows, cols), np.float32)
+        names = C.create_string_buffer(32 * max(cols, 1))
+        ranges = np.zeros((cols, 2), np.float32)
+        rc = self.lib.mmh_pull_info(self.h, dims, data.ctypes.data if rows * cols else None, names, ranges.ctypes.data if cols else None)
+        if rc:
+            raise RuntimeError(f"mmh_pull_info rc={rc}")
+        nm = [names.raw[32 * c:32 * c + 32].split(b"\0")[0].decode() for c in range(cols)]
+        return {"columns": cols, "rows": rows, "datahash": int(dims[2]), "names": nm, "ranges": ranges, "data": data}
 
     def pull_mesh(self, isoval: float, copy: bool = True, colours: bool = False):
         nv = C.c_uint64()

@@ -13,6 +13,7 @@
 // The file includes reference headers but copies no reference code.
 #include <chrono>
 #include <cstdint>
+#include <cstdio>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -20,6 +21,7 @@
 
 #include <omp.h>
 
+#include "datatools/table/TableDataCall.h"
 #include "geometry_calls/MultiParticleDataCall.h"
 #include "geometry_calls/VolumetricDataCall.h"
 #include "geometry_calls_gl/CallTriMeshDataGL.h"
@@ -80,6 +82,8 @@ public:
     }
     ~ParticleSource() override { Release(); }
     std::vector<mmh_list> lists;
+    std::vector<const void*> dirs;      // per list: DIRDATA_FLOAT_XYZ pointer or nullptr (DIRDATA_NONE)
+    std::vector<unsigned> dirStrides;
     float bbox[6] = {0, 0, 0, 1, 1, 1};
     unsigned frameCount = 1;
     unsigned frameID = 0;
@@ -119,6 +123,8 @@ private:
                 l.vtx_stride);
             p.SetColourData(static_cast<geocalls::SimpleSphericalParticles::ColourDataType>(l.col_type), l.col,
                 l.col_stride);
+            if (i < dirs.size() && dirs[i] != nullptr)
+                p.SetDirData(geocalls::SimpleSphericalParticles::DIRDATA_FLOAT_XYZ, dirs[i], dirStrides[i]);
         }
         m->SetUnlocker(nullptr);
         return true;
@@ -129,14 +135,18 @@ private:
 /** The consumer end: what a renderer would be. */
 class Sink : public core::Module {
 public:
-    Sink() : volSlot("inVolume", "volume"), meshSlot("inMesh", "mesh") {
+    Sink() : volSlot("inVolume", "volume"), meshSlot("inMesh", "mesh"), gridSlot("inGrid", "grid particles"), infoSlot("inInfo", "table") {
+        gridSlot.SetCompatibleCall<geocalls::MultiParticleDataCallDescription>();
+        MakeSlotAvailable(&gridSlot);
+        infoSlot.SetCompatibleCall<datatools::table::TableDataCallDescription>();
+        MakeSlotAvailable(&infoSlot);
         volSlot.SetCompatibleCall<geocalls::VolumetricDataCallDescription>();
         MakeSlotAvailable(&volSlot);
         meshSlot.SetCompatibleCall<geocalls_gl::CallTriMeshDataGLDescription>();
         MakeSlotAvailable(&meshSlot);
     }
     ~Sink() override { Release(); }
-    core::CallerSlot volSlot, meshSlot;
+    core::CallerSlot volSlot, meshSlot, gridSlot, infoSlot;
 
 protected:
     bool create() override { return true; }
@@ -182,11 +192,15 @@ struct Harness {
         ok = ok && connect<geocalls::VolumetricDataCallDescription>(*iso, "inData", *p2d, "outData", calls);
         ok = ok && connect<geocalls::VolumetricDataCallDescription>(*sink, "inVolume", *p2d, "outData", calls);
         ok = ok && connect<geocalls_gl::CallTriMeshDataGLDescription>(*sink, "inMesh", *iso, "outData", calls);
+        ok = ok && connect<geocalls::MultiParticleDataCallDescription>(*sink, "inGrid", *p2d, "outParticles", calls);
+        ok = ok && connect<datatools::table::TableDataCallDescription>(*sink, "inInfo", *p2d, "outInfo", calls);
     }
     ~Harness() {
         // callers first, so that no slot is left pointing at a destroyed call
         sink->volSlot.ConnectCall(nullptr);
         sink->meshSlot.ConnectCall(nullptr);
+        sink->gridSlot.ConnectCall(nullptr);
+        sink->infoSlot.ConnectCall(nullptr);
     }
 };
 
@@ -235,9 +249,21 @@ void mmh_destroy(void* hv) { delete static_cast<Harness*>(hv); }
 int mmh_set_particles(void* hv, int nlists, const mmh_list* lists, const float bbox[6], unsigned frame_id) {
     auto* h = static_cast<Harness*>(hv);
     h->src->lists.assign(lists, lists + nlists);
+    h->src->dirs.assign(nlists, nullptr);
+    h->src->dirStrides.assign(nlists, 0u);
     std::memcpy(h->src->bbox, bbox, sizeof(float) * 6);
     h->src->frameID = frame_id;
     h->src->frameCount = frame_id + 1;
+    ++h->src->hash;
+    return 0;
+}
+
+/** Direction data (DIRDATA_FLOAT_XYZ) of list `list` of the last mmh_set_particles; consumed by aggregator 2. */
+int mmh_set_directions(void* hv, int list, const void* dir, unsigned stride) {
+    auto* h = static_cast<Harness*>(hv);
+    if (list < 0 || static_cast<size_t>(list) >= h->src->dirs.size()) return -1;
+    h->src->dirs[list] = dir;
+    h->src->dirStrides[list] = stride;
     ++h->src->hash;
     return 0;
 }
@@ -303,6 +329,62 @@ int mmh_pull_volume(void* hv, unsigned frame_id, float* out_vol, uint64_t info[5
     if (out_vol) {
         if (!data) return -6;
         std::memcpy(out_vol, data, sizeof(float) * md->Resolution[0] * md->Resolution[1] * md->Resolution[2] * md->Components);
+    }
+    return 0;
+}
+
+/**
+ * Pulls "outParticles" like a sphere/arrow renderer would: MultiParticleDataCall GetExtent(1) then GetData(0).
+ * info = {list count, particle count of list 0, vertex type, colour type, direction type, data hash}; NULL outputs are skipped,
+ * pos/dir receive 3 floats per particle, col one float (COLDATA_FLOAT_I).
+ */
+int mmh_pull_grid_particles(void* hv, unsigned frame_id, uint64_t info[6], float* global_radius, float* pos, float* dir, float* col) {
+    auto* h = static_cast<Harness*>(hv);
+    auto* g = h->sink->gridSlot.CallAs<geocalls::MultiParticleDataCall>();
+    if (!g) return -1;
+    g->SetFrameID(frame_id, true);
+    if (!(*g)(1)) return -2;
+    if (!(*g)(0)) return -3;
+    for (int i = 0; i < 6; ++i) info[i] = 0;
+    info[0] = g->GetParticleListCount();
+    info[5] = g->DataHash();
+    if (info[0] == 0) return 0;
+    const auto& p = g->AccessParticles(0);
+    info[1] = p.GetCount();
+    info[2] = p.GetVertexDataType();
+    info[3] = p.GetColourDataType();
+    info[4] = p.GetDirDataType();
+    if (global_radius) *global_radius = p.GetGlobalRadius();
+    const size_t n = p.GetCount();
+    auto gather = [n](float* dst, const void* src, unsigned stride, int comps) {
+        for (size_t i = 0; i < n; ++i) std::memcpy(dst + i * comps, static_cast<const char*>(src) + i * stride, sizeof(float) * comps);
+    };
+    if (n > 0) {
+        if (pos && p.GetVertexData()) gather(pos, p.GetVertexData(), p.GetVertexDataStride() ? p.GetVertexDataStride() : 12, 3);
+        if (dir && p.GetDirData()) gather(dir, p.GetDirData(), p.GetDirDataStride() ? p.GetDirDataStride() : 12, 3);
+        if (col && p.GetColourData()) gather(col, p.GetColourData(), p.GetColourDataStride() ? p.GetColourDataStride() : 4, 1);
+    }
+    return 0;
+}
+
+/**
+ * Pulls "outInfo": TableDataCall GetHash(1) then GetData(0).  dims = {columns, rows, data hash}; data (rows x columns floats, row
+ * major), names (columns x 32 chars) and ranges (columns x {min, max}) may be NULL.
+ */
+int mmh_pull_info(void* hv, uint64_t dims[3], float* data, char* names, float* ranges) {
+    auto* h = static_cast<Harness*>(hv);
+    auto* t = h->sink->infoSlot.CallAs<datatools::table::TableDataCall>();
+    if (!t) return -1;
+    if (!(*t)(1)) return -2;
+    if (!(*t)(0)) return -3;
+    dims[0] = t->GetColumnsCount();
+    dims[1] = t->GetRowsCount();
+    dims[2] = t->DataHash();
+    if (data && t->GetData() && dims[0] * dims[1] > 0) std::memcpy(data, t->GetData(), sizeof(float) * dims[0] * dims[1]);
+    for (size_t c = 0; c < dims[0]; ++c) {
+        const auto& ci = t->GetColumnsInfos()[c];
+        if (names) std::snprintf(names + 32 * c, 32, "%s", ci.Name().c_str());
+        if (ranges) ranges[2 * c] = ci.MinimumValue(), ranges[2 * c + 1] = ci.MaximumValue();
     }
     return 0;
 }

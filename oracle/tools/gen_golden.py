@@ -14,8 +14,13 @@ oracle/ref_harness.cpp) in the dev container, where /root/reference exists.  The
   isosurface_mt_*.npz the reference IsoSurface's complete output (vertices + normals) on two volumes: the golden vectors of the
                      marching-tetrahedra compatibility mode (oracle mmo_mt_emit, libmmsurf MMS_ISO_MARCHING_TETS)
 
+  p2d_vec_*.npz      aggregator 2 (IVecToSingleCell_Volume) at ONE OpenMP thread: inputs incl. DIRDATA_FLOAT_XYZ, the 3-component volume,
+                     Min/MaxValues, and what the module serves on "outParticles" (grid positions, directions, colours, global radius)
+                     and "outInfo" (7-column table, names, ranges)
+
 Run:  python oracle/tools/gen_golden.py            (everything)
       python oracle/tools/gen_golden.py --only mt  (the marching-tetrahedra fixtures only)
+      python oracle/tools/gen_golden.py --only vec (the aggregator-2 fixtures only)
 """
 import os
 import sys
@@ -87,11 +92,55 @@ def gen_mt_fixtures(h):
         print("IsoSurface (marching tetrahedra) golden:", name, "iso", iso, m["nverts"] // 3, "triangles")
 
 
+def vec_cases():
+    """aggregator 2: (name, lists, keep-alive data, bbox min, extent, res, cyclic, normalize, sigma)"""
+    n = 700
+    xyz = (synth.uniform_box(n, 10.0, seed=4101)).astype(np.float32)
+    d = (np.stack([synth.uniform(4102, 0, n, k) for k in range(3)], 1) * 2 - 1).astype(np.float32)
+    yield dict(name="cyclic_tight", data=xyz, dirs=d, layout="xyz+dir", radius=0.6, bmin=(0, 0, 0), bext=(10, 10, 10), res=(40, 18, 16),
+               cyc=(1, 1, 1), norm=1, sigma=1.0)
+    n = 900
+    buf = np.zeros((n, 7), np.float32)  # x y z r dx dy dz, stride 28
+    u = np.stack([synth.uniform(4201, 0, n, k) for k in range(3)], 1)
+    buf[:, :3] = np.array([1, 2, 3], np.float32) + (u * 1.1 - 0.05) * np.array([12, 9, 7], np.float32)  # some particles outside the box
+    buf[:, 3] = 0.25 + 0.5 * synth.uniform(4202, 0, n, 0)
+    buf[::29, 3] = 0.0
+    buf[:, 4:7] = np.stack([synth.uniform(4203, 0, n, k) for k in range(3)], 1) * 3 - 1.5
+    buf[::17, 4:7] = 0.0
+    yield dict(name="noncyc_interleaved", data=buf, dirs=None, layout="xyzr|dir", radius=-1.0, bmin=(1, 2, 3), bext=(12, 9, 7), res=(40, 20, 18),
+               cyc=(0, 0, 0), norm=0, sigma=0.9)
+
+
+def vec_lists(c, module):
+    d = c["data"]
+    if c["layout"] == "xyz+dir":
+        return [dict(vtx=d, vtx_type=module.VERT_FLOAT_XYZ, count=len(d), global_radius=c["radius"], dir=c["dirs"])]
+    return [dict(vtx=d, vtx_type=module.VERT_FLOAT_XYZR, vtx_stride=28, count=len(d), dir=d.ctypes.data + 16, dir_stride=28)]
+
+
+def gen_vec_fixtures(h):
+    for c in vec_cases():
+        mn, ext = c["bmin"], c["bext"]
+        bbox = (mn[0], mn[1], mn[2], mn[0] + ext[0], mn[1] + ext[1], mn[2] + ext[2])
+        h.set_particles(vec_lists(c, rb), bbox)
+        h.set_p2d_params(c["res"], cyclic=c["cyc"], normalize=bool(c["norm"]), sigma=c["sigma"], aggregator=2)
+        vol, meta = h.pull_volume(components=3)
+        g = h.pull_grid_particles()
+        t = h.pull_info()
+        assert g["lists"] == 1 and g["vtx_type"] == 1 and g["col_type"] == 5 and g["dir_type"] == 1 and t["columns"] == 7
+        np.savez_compressed(os.path.join(OUT, f"p2d_vec_{c['name']}.npz"), data=c["data"], dirs=c["dirs"] if c["dirs"] is not None else np.zeros(0, np.float32),
+                            layout=c["layout"], radius=np.float32(c["radius"]), res=np.array(c["res"]), bmin=np.array(mn, np.float32),
+                            bext=np.array(ext, np.float32), sigma=np.float32(c["sigma"]), cyclic=np.array(c["cyc"]), normalize=c["norm"],
+                            volume=vol, minmax=np.array([meta["min"], meta["max"]]), grid_pos=g["pos"], grid_dir=g["dir"], grid_col=g["col"],
+                            grid_radius=np.float32(g["global_radius"]), info=t["data"], info_names=np.array(t["names"]), info_ranges=t["ranges"])
+        print("aggregator 2 golden:", c["name"], vol.shape, "min/max", meta["min"], meta["max"], g["count"], "grid particles")
+
+
 def main():
-    if "--only" in sys.argv and sys.argv[sys.argv.index("--only") + 1] == "mt":
+    if "--only" in sys.argv:
         h = rb.Harness()
         h.set_threads(1)
-        gen_mt_fixtures(h)
+        {"mt": gen_mt_fixtures, "vec": gen_vec_fixtures}[sys.argv[sys.argv.index("--only") + 1]](h)
         return
     os.makedirs(OUT, exist_ok=True)
     h = rb.Harness()
@@ -173,6 +222,7 @@ def main():
                         pos_min=m["pos"].min(0), pos_max=m["pos"].max(0), bbox=np.array(bbox, np.float32))
     print("IsoSurface reference:", m["nverts"], "vertices, GetTriCount() =", m["ntris"])
     gen_mt_fixtures(h)
+    gen_vec_fixtures(h)
 
 
 if __name__ == "__main__":

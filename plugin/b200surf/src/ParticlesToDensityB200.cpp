@@ -7,8 +7,10 @@
  */
 #include "ParticlesToDensityB200.h"
 
+#include <algorithm>
 #include <cfloat>
 #include <chrono>
+#include <numeric>
 #include <vector>
 
 #include "datatools/table/TableDataCall.h"
@@ -201,17 +203,19 @@ bool ParticlesToDensityB200::getMetadataCallback(core::Call& c) {
 
 void ParticlesToDensityB200::fillMetadata(MultiParticleDataCall* in) {
     auto& md = this->metadata;
-    md.Components = 1;
+    md.Components = this->isVector ? 3 : 1;
     md.GridType = geocalls::GridType_t::CARTESIAN;
     md.Resolution[0] = static_cast<size_t>(this->xResSlot.Param<core::param::IntParam>()->Value());
     md.Resolution[1] = static_cast<size_t>(this->yResSlot.Param<core::param::IntParam>()->Value());
     md.Resolution[2] = static_cast<size_t>(this->zResSlot.Param<core::param::IntParam>()->Value());
     md.ScalarType = geocalls::ScalarType_t::FLOATING_POINT;
     md.ScalarLength = sizeof(float);
-    this->minValue = this->minDens;
-    this->maxValue = this->maxDens;
-    md.MinValues = &this->minValue; // owned by the module, allocated once (the reference leaks a new[] per call)
-    md.MaxValues = &this->maxValue;
+    for (int k = 0; k < 3; ++k) { // the vector volume reports the range of the magnitudes for all three components (:262-272)
+        this->minValue[k] = this->minDens;
+        this->maxValue[k] = this->maxDens;
+    }
+    md.MinValues = this->minValue; // owned by the module, allocated once (the reference leaks a new[] per call)
+    md.MaxValues = this->maxValue;
     const auto bbox = in->AccessBoundingBoxes().ObjectSpaceBBox();
     md.Extents[0] = bbox.Width();
     md.Extents[1] = bbox.Height();
@@ -292,6 +296,8 @@ bool ParticlesToDensityB200::computeVolume(MultiParticleDataCall* in) {
         grid.cyclic[0] = grid.cyclic[1] = grid.cyclic[2] = 0; // QuickSurf has no periodic images
 
     std::vector<mms_list> lists;
+    std::vector<const void*> dirs;
+    std::vector<uint32_t> dirStrides;
     size_t total = 0;
     for (unsigned int i = 0; i < in->GetParticleListCount(); ++i) {
         const auto& parts = in->AccessParticles(i);
@@ -312,6 +318,9 @@ bool ParticlesToDensityB200::computeVolume(MultiParticleDataCall* in) {
         l.irange[1] = parts.GetMaxColourIndexValue();
         total += l.count;
         lists.push_back(l);
+        const bool hasDir = parts.GetDirDataType() == geocalls::SimpleSphericalParticles::DIRDATA_FLOAT_XYZ;
+        dirs.push_back(hasDir ? parts.GetDirData() : nullptr);
+        dirStrides.push_back(hasDir ? parts.GetDirDataStride() : 0u);
     }
     auto fail = [&](const char* what) {
         Log::DefaultLog.WriteError("ParticlesToDensityB200: %s: %s", what, mms_last_error(this->ctx));
@@ -323,16 +332,20 @@ bool ParticlesToDensityB200::computeVolume(MultiParticleDataCall* in) {
         return fail("set_params");
     if (mms_clear_particles(this->ctx) != MMS_OK)
         return fail("clear_particles");
-    if (mms_push_particles(this->ctx, static_cast<int32_t>(lists.size()), lists.data()) != MMS_OK)
+    if (mms_push_particles_dir(this->ctx, static_cast<int32_t>(lists.size()), lists.data(), dirs.data(), dirStrides.data()) != MMS_OK)
         return fail("push_particles");
     if (mms_compute_density(this->ctx) != MMS_OK)
         return fail("compute_density");
     float mm[2] = {0, 0};
     if (mms_get_density_range(this->ctx, mm) != MMS_OK)
         return fail("get_density_range");
-    if (mms_get_density(this->ctx, &this->hostVolume, nullptr) != MMS_OK) // RAM contract of VolumetricDataCall::GetData()
-        return fail("get_density");
     this->minDens = mm[0], this->maxDens = mm[1];
+    this->isVector = p.mode == MMS_MODE_P2D_BUMP && p.aggregator == 2;
+    if (this->isVector) {
+        if (!this->buildVectorOutputs(grid, p.normalize != 0))
+            return fail("get_vector_field");
+    } else if (mms_get_density(this->ctx, &this->hostVolume, nullptr) != MMS_OK) // RAM contract of VolumetricDataCall::GetData()
+        return fail("get_density");
     this->hasColour = p.colour != 0;
     Log::DefaultLog.WriteInfo("ParticlesToDensityB200: Captured density %f -> %f", this->minDens, this->maxDens);
     if (p.normalize) {
@@ -342,6 +355,50 @@ bool ParticlesToDensityB200::computeVolume(MultiParticleDataCall* in) {
     const std::chrono::duration<float, std::milli> ms = std::chrono::high_resolution_clock::now() - t0;
     Log::DefaultLog.WriteInfo("ParticlesToDensityB200: creation of %u x %u x %u volume from %llu particles took %f ms.", grid.res[0],
         grid.res[1], grid.res[2], static_cast<unsigned long long>(total), ms.count());
+    return true;
+}
+
+/**
+ * Aggregator 2: the host-side tail of createVolumeCPU (ParticlesToDensity.cpp:634-667 bookkeeping, :684-727 compaction).  The
+ * per-voxel arithmetic (v = sum(w d)/sum(w), |v|, v/|v|, range, normalisation) already happened on the device; what is left is
+ * the table / grid-particle bookkeeping: colours (|v| - min)/(max - min), the seven table columns, and the removal of the
+ * zero-length vectors by a sort on |v|, descending.  The reference sorts with simultaneous_sort (order of equal magnitudes
+ * unspecified); this module keeps equal magnitudes in voxel order.
+ */
+bool ParticlesToDensityB200::buildVectorOutputs(const mms_grid& grid, bool normalize) {
+    const float *vec = nullptr, *mag = nullptr, *dir = nullptr;
+    if (mms_get_vector_field(this->ctx, &vec, &mag, &dir) != MMS_OK)
+        return false;
+    this->hostVolume = vec;
+    const size_t sx = grid.res[0], sy = grid.res[1], sz = grid.res[2], n = sx * sy * sz;
+    const float mn = this->minDens, mx = this->maxDens;
+    float sd[3];
+    for (int a = 0; a < 3; ++a)
+        sd[a] = grid.extent[a] / static_cast<float>(grid.res[a] - 1);
+    std::vector<size_t> order(n);
+    std::iota(order.begin(), order.end(), size_t(0));
+    std::stable_sort(order.begin(), order.end(), [mag](size_t a, size_t b) { return mag[a] > mag[b]; });
+    size_t kept = 0;
+    while (kept < n && mag[order[kept]] != 0.0f) // std::find(densities, 0.0f) on the sorted magnitudes (:696-697)
+        ++kept;
+    this->gridPos.resize(3 * kept);
+    this->directions.resize(3 * kept);
+    this->colors.resize(kept);
+    this->infoData.resize(7 * kept);
+    for (size_t r = 0; r < kept; ++r) {
+        const size_t i = order[r];
+        const size_t x = i % sx, y = (i / sx) % sy, z = i / (sx * sy);
+        const float pos[3] = {grid.min[0] + sd[0] * x, grid.min[1] + sd[1] * y, grid.min[2] + sd[2] * z}; // :440-442
+        const float colour = (mag[i] - mn) / (mx - mn);
+        for (int k = 0; k < 3; ++k) {
+            this->gridPos[3 * r + k] = pos[k];
+            this->directions[3 * r + k] = dir[3 * i + k];
+            this->infoData[7 * r + k] = pos[k];
+            this->infoData[7 * r + 3 + k] = dir[3 * i + k];
+        }
+        this->colors[r] = colour;
+        this->infoData[7 * r + 6] = normalize ? colour : mag[i];
+    }
     return true;
 }
 
@@ -384,14 +441,50 @@ bool ParticlesToDensityB200::getDataCallback(core::Call& c) {
         outVol->SetMetadata(&this->metadata);
         outVol->SetDataHash(this->datahash);
     }
+    const bool vectorParam = this->aggregatorSlot.Param<core::param::EnumParam>()->Value() == 2;
     if (auto* outInfo = dynamic_cast<datatools::table::TableDataCall*>(&c)) { // table rows exist only for the vector aggregator
-        outInfo->SetDataHash(this->datahash);
-        outInfo->Set(0, 0, nullptr, nullptr);
+        if (vectorParam) { // :325-377
+            using CT = datatools::table::TableDataCall::ColumnType;
+            static const char* const kNames[7] = {"PositionX", "PositionY", "PositionZ", "VelocityX", "VelocityY", "VelocityZ", "VelocityMag"};
+            for (int k = 0; k < 7; ++k)
+                this->info[k].SetName(kNames[k]).SetType(CT::QUANTITATIVE);
+            const bool have = this->has_data && this->isVector;
+            if (!have) {
+                this->infoData.clear();
+                outInfo->SetDataHash(0);
+            } else {
+                const auto bb = in->AccessBoundingBoxes().ObjectSpaceBBox();
+                this->info[0].SetMinimumValue(bb.Left()).SetMaximumValue(bb.Right());
+                this->info[1].SetMinimumValue(bb.Bottom()).SetMaximumValue(bb.Top());
+                this->info[2].SetMinimumValue(bb.Back()).SetMaximumValue(bb.Front());
+                for (int k = 3; k < 6; ++k)
+                    this->info[k].SetMinimumValue(-1.0f).SetMaximumValue(1.0f);
+                this->info[6].SetMinimumValue(this->minDens).SetMaximumValue(this->maxDens);
+                outInfo->SetDataHash(this->datahash);
+            }
+            outInfo->Set(this->info.size(), this->infoData.size() / this->info.size(), this->info.data(), this->infoData.data());
+        } else {
+            outInfo->SetDataHash(this->datahash);
+            outInfo->Set(0, 0, nullptr, nullptr);
+        }
     }
-    if (outGrid != nullptr) { // grid particles exist only for the vector aggregator, which this path does not implement
+    if (outGrid != nullptr) { // grid particles exist only for the vector aggregator (:297-315)
         outGrid->SetFrameID(this->time);
         outGrid->SetDataHash(this->datahash);
-        outGrid->SetParticleListCount(0);
+        if (vectorParam && this->isVector) {
+            outGrid->SetParticleListCount(1);
+            auto& gp = outGrid->AccessParticles(0);
+            gp.SetCount(this->colors.size());
+            if (gp.GetCount() > 0) {
+                gp.SetVertexData(MultiParticleDataCall::Particles::VERTDATA_FLOAT_XYZ, this->gridPos.data());
+                gp.SetDirData(geocalls::SimpleSphericalParticles::DIRDATA_FLOAT_XYZ, this->directions.data());
+                gp.SetColourData(geocalls::SimpleSphericalParticles::COLDATA_FLOAT_I, this->colors.data());
+                gp.SetGlobalRadius(in->AccessBoundingBoxes().ObjectSpaceBBox().Width() /
+                                   static_cast<float>(this->xResSlot.Param<core::param::IntParam>()->Value()) / 5.0f);
+            }
+        } else {
+            outGrid->SetParticleListCount(0);
+        }
     }
     in->Unlock();
     return true;

@@ -5,8 +5,12 @@
  */
 #pragma once
 
+#include <array>
 #include <cstddef>
 #include <limits>
+#include <vector>
+
+#include "datatools/table/TableDataCall.h"
 
 #include "geometry_calls/MultiParticleDataCall.h"
 #include "geometry_calls/VolumetricDataCall.h"
@@ -60,6 +64,7 @@ private:
     bool computeVolume(geocalls::MultiParticleDataCall* in);
     void fillMetadata(geocalls::MultiParticleDataCall* in);
     void surfaceBBox(geocalls::MultiParticleDataCall* in);
+    bool buildVectorOutputs(const mms_grid& grid, bool normalize);
 
     core::param::ParamSlot aggregatorSlot, xResSlot, yResSlot, zResSlot, cyclXSlot, cyclYSlot, cyclZSlot, normalizeSlot,
         sigmaSlot, surfaceSlot;
@@ -79,7 +84,11 @@ private:
     bool has_data = false;
     bool hasColour = false;
     geocalls::VolumetricDataCall::Metadata metadata;
-    double minValue = 0.0, maxValue = 0.0;
+    double minValue[3] = {0.0, 0.0, 0.0}, maxValue[3] = {0.0, 0.0, 0.0};
+    // aggregator 2 (IVecToSingleCell_Volume): what "outParticles" and "outInfo" hand out (ParticlesToDensity.h:117-125)
+    bool isVector = false;
+    std::vector<float> gridPos, directions, colors, infoData;
+    std::array<datatools::table::TableDataCall::ColumnInfo, 7> info;
     float sliceDists[3] = {0, 0, 0};
 };
 

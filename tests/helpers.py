@@ -46,3 +46,19 @@ def tie_mask_cells(vol, iso, tol_rel=DENSITY_RTOL):
             for dx in (0, 1):
                 m |= near[dz:dz + m.shape[0], dy:dy + m.shape[1], dx:dx + m.shape[2]]
     return m
+
+
+def voxel_index_of(pos, bmin, bext, res):
+    """Grid-particle positions (ParticlesToDensity "outParticles", aggregator 2) -> linear voxel indices (x fastest)."""
+    sd = np.asarray(bext, np.float64) / (np.asarray(res, np.float64) - 1.0)
+    ijk = np.rint((np.asarray(pos, np.float64) - np.asarray(bmin, np.float64)) / sd).astype(np.int64)
+    return ijk[:, 0] + res[0] * (ijk[:, 1] + res[1] * ijk[:, 2])
+
+
+def vector_tail_mask(oracle, c):
+    """Aggregator 2 divides sum(w d) by sum(w).  Where sum(w) is a handful of subnormal units, ONE unit of difference in a weight
+    (expf implementations differ by an ulp) moves the quotient by percents: those voxels (sz,sy,sx) are only checked for being
+    non-zero, not for their value."""
+    lists = [{k: v for k, v in l.items() if k not in ("dir", "dir_stride")} for l in c["lists"]]
+    w, _ = oracle.density_p2d(lists, c["bmin"], c["bext"], c["res"], c["cyclic"], sigma=c["sigma"], aggregator=0, normalize=False)
+    return (w > 0) & (w < 1e-30)

@@ -169,3 +169,51 @@ def test_marching_tetrahedra_algorithm_matches_the_reference_module(ref, plug, o
             assert np.abs(r["pos"] - m["pos"]).max() <= 1e-3 * box / res[0]
     finally:
         plug.set_param(1, "algorithm", 0)
+
+
+@pytest.mark.parametrize("cyc,norm", [(True, True), (False, False)])
+def test_vector_aggregator_matches_the_reference_module(ref, plug, oracle, cyc, norm):
+    """aggregator = IVecToSingleCell_Volume: the 3-component VolumetricDataCall, the grid particles on "outParticles" and the table on
+    "outInfo" of ParticlesToDensityB200 next to the unmodified ParticlesToDensity (ParticlesToDensity.cpp:249-378, 629-727)."""
+    n, box, res = 1500, 10.0, (40, 20, 18)
+    xyz = synth.uniform_box(n, box, seed=4301)
+    d = (np.stack([synth.uniform(4302, 0, n, k) for k in range(3)], 1) * 2 - 1).astype(np.float32)
+    lists = [dict(vtx=xyz, vtx_type=rb.VERT_FLOAT_XYZ, count=n, global_radius=0.6, dir=d)]
+    bbox = (0, 0, 0, box, box, box)
+    out = []
+    for h in (ref, plug):
+        feed(h, lists, bbox, res, cyclic=(cyc,) * 3, normalize=norm, sigma=1.0, aggregator=2)
+        vol, meta = h.pull_volume(components=3)
+        out.append((vol, meta, h.pull_grid_particles(), h.pull_info()))
+    (rv, rm, rg, rt), (pv, pm, pg, pt) = out
+    for k in ("resolution", "components", "origin", "slicedist"):
+        assert rm[k] == pm[k], k
+    assert pm["components"] == 3
+    assert abs(pm["min"] - rm["min"]) <= 1e-5 and abs(pm["max"] - rm["max"]) <= 1e-5 * max(1.0, abs(rm["max"]))
+    _, omag, _, (omn, omx) = oracle.density_p2d_vector(lists, bbox[:3], (box,) * 3, res, (cyc,) * 3, sigma=1.0, normalize=False)
+    c = dict(lists=lists, bmin=bbox[:3], bext=(box,) * 3, res=res, cyclic=(cyc,) * 3, sigma=1.0)
+    tail = H.vector_tail_mask(oracle, c)
+    scale = 1.0 / ((omx - omn) if norm else 1.0)
+    assert (np.abs(pv.astype(np.float64) - rv) / np.maximum(np.abs(rv), scale))[~tail].max() < 1e-5
+    # grid particles: same voxels, sorted by magnitude, same payload per voxel
+    for k in ("lists", "count", "vtx_type", "col_type", "dir_type"):
+        assert rg[k] == pg[k], k
+    assert abs(rg["global_radius"] - pg["global_radius"]) < 1e-7
+    ri, pi = H.voxel_index_of(rg["pos"], bbox[:3], (box,) * 3, res), H.voxel_index_of(pg["pos"], bbox[:3], (box,) * 3, res)
+    assert np.array_equal(np.sort(ri), np.sort(pi))
+    assert np.all(np.diff(pg["col"]) <= 0)
+    ro, po = np.argsort(ri), np.argsort(pi)
+    assert np.array_equal(rg["pos"][ro], pg["pos"][po])
+    keep = ~tail.ravel()[ri[ro]]
+    assert np.abs(rg["col"][ro] - pg["col"][po])[keep].max() < 1e-5
+    solid = keep & (omag.ravel()[ri[ro]] > 1e-3)
+    assert np.abs(rg["dir"][ro] - pg["dir"][po])[solid].max() < 1e-4
+    # table
+    assert rt["names"] == pt["names"] and rt["columns"] == pt["columns"] == 7 and rt["rows"] == pt["rows"] == pg["count"]
+    assert np.allclose(rt["ranges"], pt["ranges"], rtol=1e-5, atol=1e-6)
+    assert np.array_equal(pt["data"][:, :3], pg["pos"]) and np.array_equal(pt["data"][:, 3:6], pg["dir"])
+    assert np.abs(rt["data"][ro][:, 6] - pt["data"][po][:, 6])[keep].max() < 1e-5 * max(1.0, omx)
+    # back to a scalar aggregator: no grid particles, empty table
+    feed(plug, lists, bbox, res, cyclic=(cyc,) * 3, normalize=norm, aggregator=0)
+    plug.pull_volume()
+    assert plug.pull_grid_particles()["lists"] == 0 and plug.pull_info()["rows"] == 0

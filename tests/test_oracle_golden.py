@@ -23,6 +23,35 @@ def test_density_bit_identical_to_reference(oracle, path):
     assert np.array_equal(sd, c["slicedist"])
 
 
+@pytest.mark.parametrize("path", G.vec_cases(), ids=lambda p: os.path.basename(p)[8:-4])
+def test_vector_field_bit_identical_to_reference(oracle, path):
+    """Aggregator 2 (IVecToSingleCell_Volume): the 3-component volume bit for bit, and the module's "outParticles" / "outInfo" payloads
+    rebuilt from the oracle's magnitude / direction volumes (the order of equal magnitudes is the sort's business: compared per voxel)."""
+    from tests import helpers as H
+    c = G.load_vec(path)
+    vec, mag, dirs, (mn, mx) = oracle.density_p2d_vector(c["lists"], c["bmin"], c["bext"], c["res"], c["cyclic"], sigma=c["sigma"],
+                                                         normalize=c["normalize"])
+    assert np.array_equal(vec.view(np.uint32), c["volume"].view(np.uint32))
+    assert c["minmax"] == ((0.0, 1.0) if c["normalize"] else (mn, mx))
+    # grid particles: exactly the voxels with a non-zero magnitude, sorted by magnitude (descending)
+    idx = H.voxel_index_of(c["grid_pos"], c["bmin"], c["bext"], c["res"])
+    assert len(np.unique(idx)) == len(idx) == int(np.count_nonzero(mag))
+    assert np.array_equal(np.sort(idx), np.flatnonzero(mag.ravel()))
+    m = mag.ravel()[idx]
+    assert np.all(np.diff(m) <= 0)
+    assert np.array_equal(c["grid_dir"], dirs.reshape(-1, 3)[idx])
+    col = ((m - np.float32(mn)) / (np.float32(mx) - np.float32(mn))).astype(np.float32)
+    assert np.array_equal(c["grid_col"], col)
+    sd = np.array(c["bext"], np.float32) / (np.array(c["res"], np.float32) - np.float32(1))
+    ijk = np.stack([idx % c["res"][0], (idx // c["res"][0]) % c["res"][1], idx // (c["res"][0] * c["res"][1])], 1).astype(np.float32)
+    assert np.array_equal(c["grid_pos"], (np.array(c["bmin"], np.float32) + sd * ijk).astype(np.float32))
+    assert abs(c["grid_radius"] - c["bext"][0] / c["res"][0] / 5.0) < 1e-7
+    # table: position, direction, magnitude (normalised like the colours if "normalize")
+    assert c["info_names"] == ["PositionX", "PositionY", "PositionZ", "VelocityX", "VelocityY", "VelocityZ", "VelocityMag"]
+    assert np.array_equal(c["info"][:, :3], c["grid_pos"]) and np.array_equal(c["info"][:, 3:6], c["grid_dir"])
+    assert np.array_equal(c["info"][:, 6], col if c["normalize"] else m)
+
+
 def test_home_voxels_match_reference_kat(oracle):
     z = np.load(os.path.join(G.GOLDEN, "home_voxel_kat.npz"))
     pts = np.ascontiguousarray(z["points"])
