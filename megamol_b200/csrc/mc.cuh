@@ -503,7 +503,9 @@ __global__ void __launch_bounds__(MC_THREADS) mc_emit_kernel(McGeo m, const __gr
                 if (lane >= d) inc += t;
             }
             const unsigned first = inc - n; // my first triangle within the row
-            for (unsigned k = 0; k < n; ++k) owner[first + k] = static_cast<unsigned char>(lane << 3 | k);
+#pragma unroll
+            for (unsigned k = 0; k < 5; ++k) // a cell has at most five triangles: five predicated stores instead of a counted loop
+                if (k < n) owner[first + k] = static_cast<unsigned char>(lane << 3 | k);
             __syncwarp();
             const unsigned wlo = static_cast<unsigned>(word >> 4), whi = static_cast<unsigned>(word >> 36); // 15 nibbles of edge ids
             const unsigned ncorn = segTris * 3;

@@ -33,12 +33,15 @@ def available(path: str = REF_LIB) -> bool:
 class Harness:
     """source -> ParticlesToDensity -> IsoSurface -> sink, driven through the reference's Call/Slot API."""
 
-    def __init__(self, lib_path: str = REF_LIB, preload: str | None = None):
+    def __init__(self, lib_path: str = REF_LIB, preload: str | None = None, molecule: bool = False):
+        """molecule=True: the density module is fed by a MolecularDataCall source (set_molecule) instead of particle lists."""
         if preload:
             C.CDLL(preload, mode=C.RTLD_GLOBAL)
         self.lib = C.CDLL(lib_path)
         L = self.lib
         L.mmh_create.restype = C.c_void_p
+        L.mmh_create_molecule.restype = C.c_void_p
+        L.mmh_set_molecule.argtypes = [C.c_void_p, C.c_uint, C.c_void_p, C.c_void_p, C.c_uint, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
         L.mmh_destroy.argtypes = [C.c_void_p]
         L.mmh_set_particles.argtypes = [C.c_void_p, C.c_int, C.POINTER(MmhList), C.POINTER(C.c_float), C.c_uint]
         L.mmh_set_p2d_params.argtypes = [C.c_void_p] + [C.c_int] * 8 + [C.c_float, C.c_int]
@@ -54,9 +57,9 @@ class Harness:
         L.mmh_pull_grid_particles.argtypes = [C.c_void_p, C.c_uint, C.POINTER(C.c_uint64), C.POINTER(C.c_float), C.c_void_p, C.c_void_p,
                                               C.c_void_p]
         L.mmh_pull_info.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p, C.c_void_p, C.c_void_p]
-        self.h = L.mmh_create()
+        self.h = L.mmh_create_molecule() if molecule else L.mmh_create()
         if not self.h:
-            raise RuntimeError("mmh_create failed")
+            raise RuntimeError("mmh_create failed" + (": the density module does not accept a MolecularDataCall" if molecule else ""))
         self._keep = []
         self.res = (16, 16, 16)
         self.frame = 0
@@ -123,6 +126,17 @@ class Harness:
                 d = d.ctypes.data
             if self.lib.mmh_set_directions(self.h, i, int(d), int(l.get("dir_stride", 0))):
                 raise RuntimeError("mmh_set_directions failed")
+
+    def set_molecule(self, pos, type_idx, radii, rgb, bbox):
+        """pos [n,3] float32, type_idx [n] uint32, radii [t] float32, rgb [t,3] uint8; bbox = (minx,miny,minz,maxx,maxy,maxz)."""
+        pos = np.ascontiguousarray(pos, np.float32)
+        type_idx = np.ascontiguousarray(type_idx, np.uint32)
+        radii = np.ascontiguousarray(radii, np.float32)
+        rgb = np.ascontiguousarray(rgb, np.uint8)
+        bb = (C.c_float * 6)(*[float(b) for b in bbox])
+        rc = self.lib.mmh_set_molecule(self.h, len(pos), pos.ctypes.data, type_idx.ctypes.data, len(radii), radii.ctypes.data, rgb.ctypes.data, bb)
+        if rc:
+            raise RuntimeError(f"mmh_set_molecule rc={rc}")
 
     def set_p2d_params(self, res, cyclic=(True, True, True), normalize=True, sigma=1.0, aggregator=0,
                        for_surface=False):

@@ -37,6 +37,7 @@
 #include "mmcore/param/IntParam.h"
 #include "mmcore/param/ParamSlot.h"
 #include "mmcore/utility/log/Log.h"
+#include "protein_calls/MolecularDataCall.h"
 #include "trisoup/volumetrics/MarchingCubeTables.h"
 
 #ifdef MMH_B200
@@ -132,6 +133,50 @@ private:
     core::CalleeSlot outSlot;
 };
 
+/** Answers MolecularDataCall GetData/GetExtent (stands in for PDBLoader): atoms with per-type radius and colour. */
+class MoleculeSource : public core::Module {
+public:
+    MoleculeSource() : outSlot("outData", "molecule") {
+        using MDC = protein_calls::MolecularDataCall;
+        outSlot.SetCallback(MDC::ClassName(), MDC::FunctionName(MDC::CallForGetData), &MoleculeSource::getData);
+        outSlot.SetCallback(MDC::ClassName(), MDC::FunctionName(MDC::CallForGetExtent), &MoleculeSource::getExtent);
+        MakeSlotAvailable(&outSlot);
+    }
+    ~MoleculeSource() override { Release(); }
+    std::vector<float> pos;
+    std::vector<unsigned> typeIdx;
+    std::vector<protein_calls::MolecularDataCall::AtomType> types;
+    float bbox[6] = {0, 0, 0, 1, 1, 1};
+    size_t hash = 1;
+
+protected:
+    bool create() override { return true; }
+    void release() override {}
+
+private:
+    bool getExtent(core::Call& c) {
+        auto* m = dynamic_cast<protein_calls::MolecularDataCall*>(&c);
+        if (!m) return false;
+        m->SetFrameCount(1);
+        m->AccessBoundingBoxes().Clear();
+        m->AccessBoundingBoxes().SetObjectSpaceBBox(bbox[0], bbox[1], bbox[2], bbox[3], bbox[4], bbox[5]);
+        m->AccessBoundingBoxes().SetObjectSpaceClipBox(bbox[0], bbox[1], bbox[2], bbox[3], bbox[4], bbox[5]);
+        m->SetDataHash(hash);
+        m->SetUnlocker(nullptr);
+        return true;
+    }
+    bool getData(core::Call& c) {
+        auto* m = dynamic_cast<protein_calls::MolecularDataCall*>(&c);
+        if (!m) return false;
+        m->SetDataHash(hash);
+        m->SetAtoms(static_cast<unsigned>(typeIdx.size()), static_cast<unsigned>(types.size()), typeIdx.data(), pos.data(), types.data(),
+            nullptr, nullptr, nullptr, nullptr);
+        m->SetUnlocker(nullptr);
+        return true;
+    }
+    core::CalleeSlot outSlot;
+};
+
 /** The consumer end: what a renderer would be. */
 class Sink : public core::Module {
 public:
@@ -169,6 +214,7 @@ bool connect(core::Module& from, const char* fromSlot, core::Module& to, const c
 struct Harness {
     std::shared_ptr<core::RootModuleNamespace> root = std::make_shared<core::RootModuleNamespace>();
     std::shared_ptr<ParticleSource> src = std::make_shared<ParticleSource>();
+    std::shared_ptr<MoleculeSource> mol = std::make_shared<MoleculeSource>();
     std::shared_ptr<P2DModule> p2d = std::make_shared<P2DModule>();
     std::shared_ptr<IsoModule> iso = std::make_shared<IsoModule>();
     std::shared_ptr<Sink> sink = std::make_shared<Sink>();
@@ -176,19 +222,23 @@ struct Harness {
     const geocalls_gl::CallTriMeshDataGL::Mesh* mesh = nullptr;
     bool ok = false;
 
-    Harness() {
+    /** molecule: feed the density module from the MolecularDataCall source instead of the particle source. */
+    explicit Harness(bool molecule = false) {
         core::utility::log::Log::DefaultLog.SetLevel(core::utility::log::Log::log_level::error);
         core::utility::log::Log::DefaultLog.SetEchoLevel(core::utility::log::Log::log_level::error);
         src->setName("src");
         p2d->setName("p2d");
         iso->setName("iso");
         sink->setName("sink");
+        mol->setName("mol");
+        root->AddChild(mol);
         root->AddChild(src);
         root->AddChild(p2d);
         root->AddChild(iso);
         root->AddChild(sink);
-        ok = src->Create() && p2d->Create() && iso->Create() && sink->Create();
-        ok = ok && connect<geocalls::MultiParticleDataCallDescription>(*p2d, "inData", *src, "outData", calls);
+        ok = src->Create() && mol->Create() && p2d->Create() && iso->Create() && sink->Create();
+        if (molecule) ok = ok && connect<protein_calls::MolecularDataCallDescription>(*p2d, "inData", *mol, "outData", calls);
+        else ok = ok && connect<geocalls::MultiParticleDataCallDescription>(*p2d, "inData", *src, "outData", calls);
         ok = ok && connect<geocalls::VolumetricDataCallDescription>(*iso, "inData", *p2d, "outData", calls);
         ok = ok && connect<geocalls::VolumetricDataCallDescription>(*sink, "inVolume", *p2d, "outData", calls);
         ok = ok && connect<geocalls_gl::CallTriMeshDataGLDescription>(*sink, "inMesh", *iso, "outData", calls);
@@ -243,7 +293,33 @@ void* mmh_create() {
     return h;
 }
 
+/** The same graph fed by a MolecularDataCall source.  NULL where the density module's inData does not accept that call
+ *  (the reference ParticlesToDensity: MultiParticleDataCall only, ParticlesToDensity.cpp:149-150). */
+void* mmh_create_molecule() {
+    auto* h = new Harness(true);
+    if (!h->ok) {
+        delete h;
+        return nullptr;
+    }
+    return h;
+}
+
 void mmh_destroy(void* hv) { delete static_cast<Harness*>(hv); }
+
+/** Atoms of the molecule source: positions (3 floats per atom), type index per atom, per type a radius and an RGB byte triple. */
+int mmh_set_molecule(void* hv, unsigned natoms, const float* pos, const unsigned* type_idx, unsigned ntypes, const float* radii,
+    const uint8_t* rgb, const float bbox[6]) {
+    auto* h = static_cast<Harness*>(hv);
+    auto& m = *h->mol;
+    m.pos.assign(pos, pos + 3 * static_cast<size_t>(natoms));
+    m.typeIdx.assign(type_idx, type_idx + natoms);
+    m.types.clear();
+    for (unsigned t = 0; t < ntypes; ++t)
+        m.types.emplace_back(vislib::StringA("X"), radii[t], rgb[3 * t], rgb[3 * t + 1], rgb[3 * t + 2]);
+    std::memcpy(m.bbox, bbox, sizeof(float) * 6);
+    ++m.hash;
+    return 0;
+}
 
 /** Replaces the source's particle lists; bumps the data hash so that consumers recompute. */
 int mmh_set_particles(void* hv, int nlists, const mmh_list* lists, const float bbox[6], unsigned frame_id) {

@@ -120,6 +120,7 @@ ParticlesToDensityB200::ParticlesToDensityB200()
     this->MakeSlotAvailable(&this->qsColourSlot);
 
     this->inDataSlot.SetCompatibleCall<geocalls::MultiParticleDataCallDescription>();
+    this->inDataSlot.SetCompatibleCall<protein_calls::MolecularDataCallDescription>();
     this->MakeSlotAvailable(&this->inDataSlot);
 }
 
@@ -163,7 +164,7 @@ bool ParticlesToDensityB200::getExtentCallback(core::Call& c) {
     auto* out = dynamic_cast<VolumetricDataCall*>(&c);
     auto* outGrid = dynamic_cast<MultiParticleDataCall*>(&c);
     auto* outInfo = dynamic_cast<datatools::table::TableDataCall*>(&c);
-    auto* in = this->inDataSlot.CallAs<MultiParticleDataCall>();
+    auto* in = this->inDataSlot.CallAs<core::AbstractGetData3DCall>(); // MultiParticleDataCall or MolecularDataCall: 0 = data, 1 = extent
     if (in == nullptr)
         return false;
     const unsigned int frameID = out != nullptr ? out->FrameID() : (outGrid != nullptr ? outGrid->FrameID() : 0);
@@ -193,7 +194,7 @@ bool ParticlesToDensityB200::getMetadataCallback(core::Call& c) {
     if (!this->getExtentCallback(c))
         return false;
     auto* out = dynamic_cast<VolumetricDataCall*>(&c);
-    auto* in = this->inDataSlot.CallAs<MultiParticleDataCall>();
+    auto* in = this->inDataSlot.CallAs<core::AbstractGetData3DCall>();
     if (out != nullptr && in != nullptr) {
         this->fillMetadata(in);
         out->SetMetadata(&this->metadata);
@@ -201,7 +202,7 @@ bool ParticlesToDensityB200::getMetadataCallback(core::Call& c) {
     return true;
 }
 
-void ParticlesToDensityB200::fillMetadata(MultiParticleDataCall* in) {
+void ParticlesToDensityB200::fillMetadata(core::AbstractGetData3DCall* in) {
     auto& md = this->metadata;
     md.Components = this->isVector ? 3 : 1;
     md.GridType = geocalls::GridType_t::CARTESIAN;
@@ -232,7 +233,7 @@ void ParticlesToDensityB200::fillMetadata(MultiParticleDataCall* in) {
     md.MemLoc = geocalls::MemoryLocation::RAM;
 }
 
-void ParticlesToDensityB200::surfaceBBox(MultiParticleDataCall* in) {
+void ParticlesToDensityB200::surfaceBBox(core::AbstractGetData3DCall* in) {
     // "forSurfaceReconstruction" (ParticlesToDensity.cpp:749-799): grow the box by 10 % plus a two-voxel margin and make
     // the voxels cubic by CHANGING sizex / sizey; the modified box only lives in the incoming call for this request.
     const int sz = this->zResSlot.Param<core::param::IntParam>()->Value();
@@ -259,7 +260,7 @@ void ParticlesToDensityB200::surfaceBBox(MultiParticleDataCall* in) {
     in->AccessBoundingBoxes().SetObjectSpaceClipBox(l, b, k, r, t, f);
 }
 
-bool ParticlesToDensityB200::computeVolume(MultiParticleDataCall* in) {
+bool ParticlesToDensityB200::computeVolume(core::AbstractGetData3DCall* in) {
     const auto t0 = std::chrono::high_resolution_clock::now();
     const int device = this->deviceSlot.Param<core::param::IntParam>()->Value();
     if (this->ctx == nullptr || this->ctxDevice != device) {
@@ -299,8 +300,41 @@ bool ParticlesToDensityB200::computeVolume(MultiParticleDataCall* in) {
     std::vector<const void*> dirs;
     std::vector<uint32_t> dirStrides;
     size_t total = 0;
-    for (unsigned int i = 0; i < in->GetParticleListCount(); ++i) {
-        const auto& parts = in->AccessParticles(i);
+    auto* mpdc = dynamic_cast<MultiParticleDataCall*>(in);
+    if (auto* mol = dynamic_cast<protein_calls::MolecularDataCall*>(in)) {
+        // one FLOAT_XYZR list with interleaved FLOAT_RGBA colours, what QuickSurf::calculateSurface(MolecularDataCall&) assembles
+        // (QuickSurf.cpp:369-386); colour = the atom type's colour (MolecularDataCall.h:958), bytes / 255
+        const size_t n = mol->AtomCount();
+        if (n > 0 && (mol->AtomTypeCount() == 0 || mol->AtomPositions() == nullptr || mol->AtomTypeIndices() == nullptr)) {
+            Log::DefaultLog.WriteError("ParticlesToDensityB200: MolecularDataCall without atom types or positions");
+            return false;
+        }
+        this->atoms.resize(8 * n);
+        for (size_t i = 0; i < n; ++i) {
+            const auto& type = mol->AtomTypes()[mol->AtomTypeIndices()[i]];
+            float* a = &this->atoms[8 * i];
+            a[0] = mol->AtomPositions()[3 * i + 0], a[1] = mol->AtomPositions()[3 * i + 1], a[2] = mol->AtomPositions()[3 * i + 2];
+            a[3] = type.Radius();
+            a[4] = type.Colour()[0] / 255.0f, a[5] = type.Colour()[1] / 255.0f, a[6] = type.Colour()[2] / 255.0f, a[7] = 1.0f;
+        }
+        if (n > 0) {
+            mms_list l{};
+            l.vtx = this->atoms.data();
+            l.vtx_type = MMS_VERT_FLOAT_XYZR;
+            l.vtx_stride = 32;
+            l.col = this->atoms.data() + 4;
+            l.col_type = MMS_COL_FLOAT_RGBA;
+            l.col_stride = 32;
+            l.count = n;
+            l.irange[1] = 1.0f;
+            total = n;
+            lists.push_back(l);
+            dirs.push_back(nullptr);
+            dirStrides.push_back(0u);
+        }
+    }
+    for (unsigned int i = 0; mpdc != nullptr && i < mpdc->GetParticleListCount(); ++i) {
+        const auto& parts = mpdc->AccessParticles(i);
         if (parts.GetVertexDataType() == MultiParticleDataCall::Particles::VERTDATA_NONE)
             continue;
         mms_list l{};
@@ -403,7 +437,7 @@ bool ParticlesToDensityB200::buildVectorOutputs(const mms_grid& grid, bool norma
 }
 
 bool ParticlesToDensityB200::getDataCallback(core::Call& c) {
-    auto* in = this->inDataSlot.CallAs<MultiParticleDataCall>();
+    auto* in = this->inDataSlot.CallAs<core::AbstractGetData3DCall>();
     if (in == nullptr)
         return false;
     auto* outVol = dynamic_cast<VolumetricDataCall*>(&c);

@@ -2,6 +2,9 @@
  * ParticlesToDensityB200.h -- drop-in for datatools::ParticlesToDensity (plugins/datatools/src/ParticlesToDensity.h):
  * same slots (inData / outData / outParticles / outInfo), same parameters with the same defaults, same call protocol;
  * the volume is computed by libmmsurf on a B200 instead of createVolumeCPU.
+ * "inData" additionally accepts a protein_calls::MolecularDataCall, the other input of the reference's QuickSurf module
+ * (QuickSurf::calculateSurface(MolecularDataCall&), plugins/protein_cuda/src/QuickSurf.cpp:326-404): one sphere per atom with
+ * the radius of its atom type, coloured with the atom type's colour.
  */
 #pragma once
 
@@ -18,6 +21,8 @@
 #include "mmcore/CallerSlot.h"
 #include "mmcore/Module.h"
 #include "mmcore/param/ParamSlot.h"
+#include "mmstd/data/AbstractGetData3DCall.h"
+#include "protein_calls/MolecularDataCall.h"
 
 #include "mmsurf.h"
 
@@ -61,9 +66,9 @@ private:
 
     bool anythingDirty() const;
     void resetDirty();
-    bool computeVolume(geocalls::MultiParticleDataCall* in);
-    void fillMetadata(geocalls::MultiParticleDataCall* in);
-    void surfaceBBox(geocalls::MultiParticleDataCall* in);
+    bool computeVolume(core::AbstractGetData3DCall* in);
+    void fillMetadata(core::AbstractGetData3DCall* in);
+    void surfaceBBox(core::AbstractGetData3DCall* in);
     bool buildVectorOutputs(const mms_grid& grid, bool normalize);
 
     core::param::ParamSlot aggregatorSlot, xResSlot, yResSlot, zResSlot, cyclXSlot, cyclYSlot, cyclZSlot, normalizeSlot,
@@ -88,6 +93,7 @@ private:
     // aggregator 2 (IVecToSingleCell_Volume): what "outParticles" and "outInfo" hand out (ParticlesToDensity.h:117-125)
     bool isVector = false;
     std::vector<float> gridPos, directions, colors, infoData;
+    std::vector<float> atoms; // MolecularDataCall input: x y z r R G B A per atom, rebuilt per frame
     std::array<datatools::table::TableDataCall::ColumnInfo, 7> info;
     float sliceDists[3] = {0, 0, 0};
 };

@@ -172,6 +172,25 @@ def test_external_volume_isosurface(surf, oracle):
     assert cosang.min() > 0.97
 
 
+def test_noise_volume_isosurface_emits_in_windows(surf, oracle):
+    """White noise crosses about half of all grid edges: far more than the emit kernel's compact vertex store holds per step (E_CAP),
+    so the step is emitted in several windows of its crossing list.  Same mesh as the oracle, triangle for triangle."""
+    res = (70, 41, 37)
+    vol = synth.uniform(991, 0, res[0] * res[1] * res[2], 0).reshape(res[2], res[1], res[0]).astype(np.float32)
+    surf.clear_particles()
+    surf.set_grid((0, 0, 0), tuple(float(r - 1) for r in res), res, (False,) * 3)
+    surf.set_params(want_cell_tricounts=1)
+    surf.set_density(vol)
+    surf.extract_isosurface(0.5)
+    counts = surf.cell_tricounts()
+    pos, nrm = surf.get_mesh()
+    total, ref_counts, _ = oracle.mc_count(vol, 0.5)
+    assert np.array_equal(counts, ref_counts) and pos.shape[0] == total and total > 2 * vol.size
+    rpos, rnrm, _ = oracle.mc_emit(vol, (0, 0, 0), (1, 1, 1), 0.5)
+    assert np.abs(pos - rpos).max() <= H.VERTEX_TOL_CELLS
+    assert np.abs(nrm - rnrm).max() < 1e-4
+
+
 def test_emit_into_caller_buffers(surf, oracle):
     """mms_count_isosurface + mms_emit_isosurface: the mesh lands at an offset of caller-owned device memory (the hook the
     z-slab driver uses to let every rank write into rank 0's mesh, and the hook for GL-interop vertex buffers)."""

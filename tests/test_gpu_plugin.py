@@ -217,3 +217,56 @@ def test_vector_aggregator_matches_the_reference_module(ref, plug, oracle, cyc, 
     feed(plug, lists, bbox, res, cyclic=(cyc,) * 3, normalize=norm, aggregator=0)
     plug.pull_volume()
     assert plug.pull_grid_particles()["lists"] == 0 and plug.pull_info()["rows"] == 0
+
+
+def test_molecular_data_call_input(plug, oracle):
+    """ParticlesToDensityB200.inData connected to a protein_calls::MolecularDataCall (the second input of the reference's QuickSurf
+    module, QuickSurf.cpp:326-404): one sphere per atom, radius and colour of its atom type -> same volume, same coloured mesh as
+    the equivalent FLOAT_XYZR + FLOAT_RGBA particle list through the MultiParticleDataCall path, bit for bit."""
+    n = 2500
+    data, _, _ = synth.protein_like(n, seed=5, nballs=5, extent=36.0)
+    radii = np.array([1.2, 1.52, 1.55, 1.7, 1.8], np.float32)
+    rgb = np.array([[255, 255, 255], [255, 13, 13], [48, 80, 248], [144, 144, 144], [255, 255, 48]], np.uint8)
+    tidx = (np.arange(n) * 7 % 5).astype(np.uint32)
+    pos = np.ascontiguousarray(data[:, :3])
+    buf = np.zeros((n, 8), np.float32)
+    buf[:, :3] = pos
+    buf[:, 3] = radii[tidx]
+    buf[:, 4:7] = rgb[tidx].astype(np.float32) / np.float32(255.0)
+    buf[:, 7] = 1.0
+    lists = [dict(vtx=buf, vtx_type=rb.VERT_FLOAT_XYZR, vtx_stride=32, count=n, col=buf.ctypes.data + 16, col_type=rb.COL_FLOAT_RGBA, col_stride=32)]
+    bbox, res = (0, 0, 0, 36, 36, 36), (46, 44, 42)
+
+    def pull(h):
+        h.set_p2d_params(res, cyclic=(False,) * 3, normalize=False)
+        h.set_param(0, "mode", 1)
+        h.set_param(0, "quicksurf::quality", 1)
+        h.set_param(0, "quicksurf::colour", 1)
+        vol, meta = h.pull_volume()
+        return vol, meta, h.pull_mesh(0.5, colours=True)
+
+    mol = rb.Harness(rb.PLUG_LIB, molecule=True)
+    mol.set_molecule(pos, tidx, radii, rgb, bbox)
+    mvol, mmeta, mmesh = pull(mol)
+    plug.set_particles(lists, bbox)
+    try:
+        pvol, pmeta, pmesh = pull(plug)
+    finally:
+        plug.set_param(0, "mode", 0)
+        plug.set_param(0, "quicksurf::colour", 0)
+    assert mmeta["resolution"] == pmeta["resolution"] and mmeta["origin"] == pmeta["origin"]
+    assert np.array_equal(mvol, pvol) and mvol.max() > 0.5
+    assert mmesh["nverts"] == pmesh["nverts"] > 1000
+    for k in ("pos", "nrm", "col"):
+        assert np.array_equal(mmesh[k], pmesh[k]), k
+    # and it is the right volume: the oracle's Gaussian density of those spheres
+    sd = np.array(mmeta["slicedist"], np.float32)
+    rvol, _ = oracle.density_gauss(lists, mmeta["origin"], sd, res, radscale=1.0, gausslim=2.5, colour=False)
+    assert (np.abs(mvol - rvol) / np.maximum(rvol, 1e-5 * rvol.max())).max() < 2e-5
+    # bump mode through the same input
+    mol.set_param(0, "mode", 0)
+    mol.set_p2d_params(res, cyclic=(False,) * 3, normalize=False, sigma=1.0)
+    bvol, _ = mol.pull_volume()
+    rb_vol, _ = oracle.density_p2d(lists, bbox[:3], (36.0,) * 3, res, (0, 0, 0), sigma=1.0)
+    assert H.density_close(bvol, rb_vol) < H.DENSITY_RTOL
+    mol.close()
