@@ -1,3 +1,5 @@
+#!/bin/bash
+# On an N-GPU box (gpurun --gpus N -- 'bash scripts/gpu_scale.sh N'): the 2-rank NCCL tests, then the C2 (weak) and C4 (strong) lines.
 N=$1
 timeout 600 python -m pytest tests/test_gpu_multi.py tests/test_gpu_variants.py -m gpu -x -q 2>&1 | tail -4
 for WL in c2 c4; do
