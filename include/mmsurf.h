@@ -132,6 +132,11 @@ int mms_push_particles(mms_ctx* ctx, int32_t nlists, const mms_list* lists);
  * dir_strides[i] = its stride in bytes (0 = 12).  dirs == NULL is mms_push_particles. */
 int mms_push_particles_dir(mms_ctx* ctx, int32_t nlists, const mms_list* lists, const void* const* dirs, const uint32_t* dir_strides);
 
+/* Largest radius over the lists pushed so far (global radii and per-particle radii; finite, > 0), found on the device: QuickSurf sizes
+ * its grid padding from it before any density is computed (QuickSurf::calculateSurface, plugins/protein_cuda/src/QuickSurf.cpp:419-470).
+ * Synchronises. */
+int mms_get_max_radius(mms_ctx* ctx, float* rmax);
+
 int mms_compute_density(mms_ctx* ctx);
 /* Range of the (un-normalised) sums of the last compute_density: the reference's minDens/maxDens. */
 int mms_get_density_range(mms_ctx* ctx, float minmax[2]);

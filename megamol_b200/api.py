@@ -16,7 +16,7 @@ MODE_P2D_BUMP, MODE_QS_GAUSS = 0, 1
 ISO_MARCHING_CUBES, ISO_MARCHING_TETS = 0, 1
 
 EXPORTS = ["mms_create", "mms_destroy", "mms_last_error", "mms_set_grid", "mms_set_slab", "mms_set_params",
-           "mms_clear_particles", "mms_push_particles", "mms_push_particles_dir", "mms_get_vector_field", "mms_get_vector_field_device", "mms_compute_density", "mms_get_density_range", "mms_normalize", "mms_density_range_device", "mms_normalize_device", "mms_set_stream",
+           "mms_clear_particles", "mms_push_particles", "mms_push_particles_dir", "mms_get_vector_field", "mms_get_vector_field_device", "mms_get_max_radius", "mms_compute_density", "mms_get_density_range", "mms_normalize", "mms_density_range_device", "mms_normalize_device", "mms_set_stream",
            "mms_get_density", "mms_prefetch_density", "mms_get_density_device", "mms_set_density", "mms_extract_isosurface", "mms_set_isosurface_mode", "mms_count_isosurface", "mms_emit_isosurface", "mms_device_alloc",
            "mms_device_free", "mms_route_particles", "mms_ipc_export", "mms_ipc_open", "mms_ipc_close", "mms_get_mesh",
            "mms_get_mesh_device", "mms_get_home_voxels", "mms_get_cell_tricounts", "mms_get_timings", "mms_synchronize",
@@ -84,6 +84,7 @@ def load_library():
     L.mms_push_particles_dir.argtypes = [vp, C.c_int32, C.POINTER(MmsList), C.POINTER(vp), C.POINTER(C.c_uint32)]
     L.mms_get_vector_field.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     L.mms_get_vector_field_device.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    L.mms_get_max_radius.argtypes = [vp, C.POINTER(C.c_float)]
     L.mms_compute_density.argtypes = [vp]
     L.mms_get_density_range.argtypes = [vp, C.POINTER(C.c_float)]
     L.mms_normalize.argtypes = [vp, C.c_float, C.c_float]
@@ -243,6 +244,11 @@ class Surf:
             self._chk(self.L.mms_push_particles_dir(self.h, len(lists), arr, dirs, dstrides))
         else:
             self._chk(self.L.mms_push_particles(self.h, len(lists), arr))
+
+    def max_radius(self) -> float:
+        r = C.c_float()
+        self._chk(self.L.mms_get_max_radius(self.h, C.byref(r)))
+        return float(r.value)
 
     def compute_density(self):
         self._chk(self.L.mms_compute_density(self.h))

@@ -789,7 +789,7 @@ __global__ void __launch_bounds__(256) normalize_kernel(float* __restrict__ vol,
 }
 
 /** Largest radius over a list with per-particle radii (decides the cell size on the host). */
-__global__ void __launch_bounds__(256) radius_max_kernel(ListDev l, DevState* st) {
+__global__ void __launch_bounds__(256) radius_max_kernel(ListDev l, unsigned* rmaxBits) {
     const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
     float rmax = 0.0f;
     for (unsigned long long j = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; j < l.count; j += stride) {
@@ -797,7 +797,7 @@ __global__ void __launch_bounds__(256) radius_max_kernel(ListDev l, DevState* st
         if (r > 0.0f && isfinite(r)) rmax = fmaxf(rmax, r);
     }
     rmax = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(rmax)));
-    if ((threadIdx.x & 31) == 0 && rmax > 0.0f) atomicMax(&st->rmaxBits, __float_as_uint(rmax));
+    if ((threadIdx.x & 31) == 0 && rmax > 0.0f) atomicMax(rmaxBits, __float_as_uint(rmax));
 }
 
 } // namespace mms

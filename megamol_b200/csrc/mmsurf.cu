@@ -162,7 +162,7 @@ struct mms_ctx {
     DevBuf routeCounts, routeOffsets, routeTile;
     PinBuf hRoute;
     DevBuf cellCount, cellStart, cursor, tileSums, recsA, recsB, auxA, auxB, vol, rgb, segCount, segOffset, meshPos, meshNrm,
-        meshCol, triCount, home, dstate, dirVol;
+        meshCol, triCount, home, dstate, dirVol, rmaxBuf;
     PinBuf hState, hVol, hRgb, hPos, hNrm, hCol, hHome, hTri, hDir;
     cudaEvent_t ev[EV_COUNT]{};
     bool evSet[EV_COUNT]{};
@@ -422,7 +422,7 @@ int mms_destroy(mms_ctx* c) {
         DeviceGuard guard(c->device);
         mms_clear_particles(c);
         for (DevBuf* b : {&c->cellCount, &c->cellStart, &c->cursor, &c->tileSums, &c->recsA, &c->recsB, &c->auxA, &c->auxB, &c->vol,
-                 &c->rgb, &c->segCount, &c->segOffset, &c->meshPos, &c->meshNrm, &c->meshCol, &c->triCount, &c->home, &c->dstate, &c->routeCounts, &c->routeOffsets, &c->routeTile, &c->rangeBuf, &c->dirVol})
+                 &c->rgb, &c->segCount, &c->segOffset, &c->meshPos, &c->meshNrm, &c->meshCol, &c->triCount, &c->home, &c->dstate, &c->routeCounts, &c->routeOffsets, &c->routeTile, &c->rangeBuf, &c->dirVol, &c->rmaxBuf})
             b->release();
         for (PinBuf* b : {&c->hState, &c->hVol, &c->hRgb, &c->hPos, &c->hNrm, &c->hCol, &c->hHome, &c->hTri, &c->hRoute, &c->hDir}) b->release();
         cudaStreamSynchronize(c->stream);
@@ -583,6 +583,36 @@ int mms_push_particles_dir(mms_ctx* c, int32_t nlists, const mms_list* lists, co
     return pushLists(c, nlists, lists, dirs, dir_strides);
 }
 
+int mms_get_max_radius(mms_ctx* c, float* rmaxOut) {
+    if (!c || !rmaxOut) return MMS_ERR_INVALID;
+    DeviceGuard guard(c->device);
+    float rmax = 0.0f;
+    bool perParticle = false;
+    for (const ListDev& l : c->lists) {
+        if (l.vtype == MMS_VERT_FLOAT_XYZR) perParticle = true;
+        else if (l.grad > rmax && std::isfinite(l.grad)) rmax = l.grad;
+    }
+    if (perParticle) {
+        cudaStream_t st = c->stream;
+        if (c->uploadPending) MMS_CUDA(c, cudaStreamWaitEvent(st, c->uploadDone, 0)); // compute_density waits again; harmless
+        if (!c->rmaxBuf.ensure(16)) return c->fail(MMS_ERR_NOMEM, "device allocation failed");
+        MMS_CUDA(c, cudaMemsetAsync(c->rmaxBuf.p, 0, 4, st));
+        for (const ListDev& l : c->lists)
+            if (l.vtype == MMS_VERT_FLOAT_XYZR) {
+                radius_max_kernel<<<gridFor(l.count, 256, c->smCount * 16), 256, 0, st>>>(l, c->rmaxBuf.as<unsigned>());
+                ++c->launches;
+            }
+        unsigned bits = 0;
+        MMS_CUDA(c, cudaMemcpyAsync(&bits, c->rmaxBuf.p, 4, cudaMemcpyDeviceToHost, st));
+        MMS_CUDA(c, cudaStreamSynchronize(st));
+        float r = 0.0f;
+        std::memcpy(&r, &bits, 4);
+        rmax = std::max(rmax, r);
+    }
+    *rmaxOut = rmax;
+    return MMS_OK;
+}
+
 int mms_compute_density(mms_ctx* c) {
     if (!c || !c->haveGrid) return c ? c->fail(MMS_ERR_INVALID, "mms_set_grid has not been called") : MMS_ERR_INVALID;
     if (c->nparticles >= (1ull << 32) - 1) return c->fail(MMS_ERR_UNSUPPORTED, "2^32 or more particles per context");
@@ -610,7 +640,7 @@ int mms_compute_density(mms_ctx* c) {
         if (perParticle) {
             for (const ListDev& l : c->lists)
                 if (l.vtype == MMS_VERT_FLOAT_XYZR) {
-                    radius_max_kernel<<<gridFor(l.count, 256, c->smCount * 16), 256, 0, st>>>(l, c->dstate.as<DevState>());
+                    radius_max_kernel<<<gridFor(l.count, 256, c->smCount * 16), 256, 0, st>>>(l, &c->dstate.as<DevState>()->rmaxBits);
                     ++c->launches;
                 }
             MMS_CUDA(c, cudaMemcpyAsync(c->hState.p, c->dstate.p, sizeof(DevState), cudaMemcpyDeviceToHost, st));

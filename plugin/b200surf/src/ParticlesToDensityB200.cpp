@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <cfloat>
+#include <cmath>
 #include <chrono>
 #include <numeric>
 #include <vector>
@@ -51,6 +52,7 @@ ParticlesToDensityB200::ParticlesToDensityB200()
         , qsQualitySlot("quicksurf::quality", "Quality: 0 low .. 3 ultra (Gaussian cut-off 2.0/2.5/3.0/4.0 sigma)")
         , qsRadScaleSlot("quicksurf::radiusScale", "Radius scale")
         , qsColourSlot("quicksurf::colour", "Also build the density-weighted colour volume (coloured isosurface)")
+        , qsGridSpacingSlot("quicksurf::gridSpacing", "Grid spacing of QuickSurf's own grid set-up (0 = use sizex/sizey/sizez on the bounding box)")
         , outDataSlot("outData", "Provides a density volume for the particles")
         , outParticlesSlot("outParticles", "Provides the particles in grid form (vector aggregator only)")
         , outInfoSlot("outInfo", "Provides information about the grid (vector aggregator only)")
@@ -118,6 +120,8 @@ ParticlesToDensityB200::ParticlesToDensityB200()
     this->MakeSlotAvailable(&this->qsRadScaleSlot);
     this->qsColourSlot << new core::param::BoolParam(false);
     this->MakeSlotAvailable(&this->qsColourSlot);
+    this->qsGridSpacingSlot << new core::param::FloatParam(0.0f, 0.0f);
+    this->MakeSlotAvailable(&this->qsGridSpacingSlot);
 
     this->inDataSlot.SetCompatibleCall<geocalls::MultiParticleDataCallDescription>();
     this->inDataSlot.SetCompatibleCall<protein_calls::MolecularDataCallDescription>();
@@ -151,12 +155,12 @@ bool ParticlesToDensityB200::anythingDirty() const {
     return this->aggregatorSlot.IsDirty() || this->xResSlot.IsDirty() || this->yResSlot.IsDirty() || this->zResSlot.IsDirty() ||
            this->cyclXSlot.IsDirty() || this->cyclYSlot.IsDirty() || this->cyclZSlot.IsDirty() || this->normalizeSlot.IsDirty() ||
            this->sigmaSlot.IsDirty() || this->deviceSlot.IsDirty() || this->modeSlot.IsDirty() || this->qsQualitySlot.IsDirty() ||
-           this->qsRadScaleSlot.IsDirty() || this->qsColourSlot.IsDirty();
+           this->qsRadScaleSlot.IsDirty() || this->qsColourSlot.IsDirty() || this->qsGridSpacingSlot.IsDirty();
 }
 
 void ParticlesToDensityB200::resetDirty() {
     for (auto* s : {&aggregatorSlot, &xResSlot, &yResSlot, &zResSlot, &cyclXSlot, &cyclYSlot, &cyclZSlot, &normalizeSlot, &sigmaSlot, &deviceSlot, &modeSlot,
-             &qsQualitySlot, &qsRadScaleSlot, &qsColourSlot})
+             &qsQualitySlot, &qsRadScaleSlot, &qsColourSlot, &qsGridSpacingSlot})
         s->ResetDirty();
 }
 
@@ -209,6 +213,9 @@ void ParticlesToDensityB200::fillMetadata(core::AbstractGetData3DCall* in) {
     md.Resolution[0] = static_cast<size_t>(this->xResSlot.Param<core::param::IntParam>()->Value());
     md.Resolution[1] = static_cast<size_t>(this->yResSlot.Param<core::param::IntParam>()->Value());
     md.Resolution[2] = static_cast<size_t>(this->zResSlot.Param<core::param::IntParam>()->Value());
+    if (this->ownGrid && this->has_data)
+        for (int a = 0; a < 3; ++a)
+            md.Resolution[a] = static_cast<size_t>(this->gridUsed.res[a]);
     md.ScalarType = geocalls::ScalarType_t::FLOATING_POINT;
     md.ScalarLength = sizeof(float);
     for (int k = 0; k < 3; ++k) { // the vector volume reports the range of the magnitudes for all three components (:262-272)
@@ -230,6 +237,13 @@ void ParticlesToDensityB200::fillMetadata(core::AbstractGetData3DCall* in) {
     md.Origin[0] = bbox.Left();
     md.Origin[1] = bbox.Bottom();
     md.Origin[2] = bbox.Back();
+    if (this->ownGrid && this->has_data) { // QuickSurf's own grid: padded origin, spacing = quicksurf::gridSpacing
+        for (int a = 0; a < 3; ++a) {
+            md.Extents[a] = this->gridUsed.extent[a];
+            md.Origin[a] = this->gridUsed.min[a];
+            this->sliceDists[a] = md.Extents[a] / static_cast<float>(md.Resolution[a] - 1);
+        }
+    }
     md.MemLoc = geocalls::MemoryLocation::RAM;
 }
 
@@ -360,14 +374,39 @@ bool ParticlesToDensityB200::computeVolume(core::AbstractGetData3DCall* in) {
         Log::DefaultLog.WriteError("ParticlesToDensityB200: %s: %s", what, mms_last_error(this->ctx));
         return false;
     };
-    if (mms_set_grid(this->ctx, &grid) != MMS_OK)
-        return fail("set_grid");
-    if (mms_set_params(this->ctx, &p) != MMS_OK)
-        return fail("set_params");
     if (mms_clear_particles(this->ctx) != MMS_OK)
         return fail("clear_particles");
     if (mms_push_particles_dir(this->ctx, static_cast<int32_t>(lists.size()), lists.data(), dirs.data(), dirStrides.data()) != MMS_OK)
         return fail("push_particles");
+    const float gridSpacing = this->qsGridSpacingSlot.Param<core::param::FloatParam>()->Value();
+    this->ownGrid = p.mode == MMS_MODE_QS_GAUSS && gridSpacing > 0.0f;
+    if (this->ownGrid) {
+        // QuickSurf's grid set-up (QuickSurf.cpp:456-480): the bounding box grown by a padding derived from the largest radius, then
+        // ceil(extent / gridspacing) voxels of exactly that spacing, origin = the padded minimum.  The molecule path skips the
+        // padding ("we ignore the padding and the radscale", :345-360).
+        float pad = 0.0f;
+        if (mpdc != nullptr) {
+            float rmax = 0.0f;
+            if (mms_get_max_radius(this->ctx, &rmax) != MMS_OK)
+                return fail("get_max_radius");
+            float gridpadding = p.radscale * rmax * 1.5f;
+            const float pi = std::acos(-1.0f);
+            const float padrad = static_cast<float>(0.4 * std::sqrt(4.0 / 3.0 * pi * gridpadding * gridpadding * gridpadding));
+            pad = std::max(gridpadding, padrad);
+        }
+        const float lo[3] = {bbox.Left() - pad, bbox.Bottom() - pad, bbox.Back() - pad};
+        const float hi[3] = {bbox.Right() + pad, bbox.Top() + pad, bbox.Front() + pad};
+        for (int a = 0; a < 3; ++a) {
+            grid.min[a] = lo[a];
+            grid.res[a] = std::max(2, static_cast<int>(std::ceil((hi[a] - lo[a]) / gridSpacing)));
+            grid.extent[a] = static_cast<float>(grid.res[a] - 1) * gridSpacing; // node i sits at origin + i * gridspacing
+        }
+    }
+    this->gridUsed = grid;
+    if (mms_set_grid(this->ctx, &grid) != MMS_OK)
+        return fail("set_grid");
+    if (mms_set_params(this->ctx, &p) != MMS_OK)
+        return fail("set_params");
     if (mms_compute_density(this->ctx) != MMS_OK)
         return fail("compute_density");
     float mm[2] = {0, 0};

@@ -75,7 +75,7 @@ private:
         sigmaSlot, surfaceSlot;
     core::param::ParamSlot deviceSlot; // extra: CUDA device ordinal
     // extra: QuickSurf semantics as a kernel mode (names and defaults of protein_cuda::QuickSurf, QuickSurf.cpp:18-31,62-72)
-    core::param::ParamSlot modeSlot, qsQualitySlot, qsRadScaleSlot, qsColourSlot;
+    core::param::ParamSlot modeSlot, qsQualitySlot, qsRadScaleSlot, qsColourSlot, qsGridSpacingSlot;
     core::CalleeSlot outDataSlot, outParticlesSlot, outInfoSlot;
     core::CallerSlot inDataSlot;
 
@@ -96,6 +96,8 @@ private:
     std::vector<float> atoms; // MolecularDataCall input: x y z r R G B A per atom, rebuilt per frame
     std::array<datatools::table::TableDataCall::ColumnInfo, 7> info;
     float sliceDists[3] = {0, 0, 0};
+    mms_grid gridUsed{}; // the grid of the last compute (differs from bbox + sizex/y/z when QuickSurf's own grid set-up is on)
+    bool ownGrid = false;
 };
 
 } // namespace megamol::b200surf

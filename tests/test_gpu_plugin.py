@@ -270,3 +270,43 @@ def test_molecular_data_call_input(plug, oracle):
     rb_vol, _ = oracle.density_p2d(lists, bbox[:3], (36.0,) * 3, res, (0, 0, 0), sigma=1.0)
     assert H.density_close(bvol, rb_vol) < H.DENSITY_RTOL
     mol.close()
+
+
+def test_quicksurf_own_grid_setup(plug, oracle):
+    """quicksurf::gridSpacing > 0: the module sets the grid up like QuickSurf::calculateSurface (QuickSurf.cpp:456-480): bounding box
+    padded by max(1.5 radscale r_max, 0.4 sqrt(4/3 pi pad^3)), ceil(extent / spacing) voxels of exactly that spacing."""
+    n = 2000
+    data, _, _ = synth.protein_like(n, seed=9, nballs=4, extent=30.0)
+    data = np.ascontiguousarray(data)
+    lists = [dict(vtx=data, vtx_type=rb.VERT_FLOAT_XYZR, vtx_stride=32, count=n, col=data.ctypes.data + 16, col_type=rb.COL_FLOAT_RGBA,
+                  col_stride=32)]
+    bbox = (1.0, 2.0, 3.0, 31.0, 30.0, 29.0)
+    spacing, radscale = np.float32(0.8), np.float32(1.25)
+    feed(plug, lists, bbox, (16, 16, 16), cyclic=(False,) * 3, normalize=False)
+    plug.set_param(0, "mode", 1)
+    plug.set_param(0, "quicksurf::quality", 0)
+    plug.set_param(0, "quicksurf::radiusScale", float(radscale))
+    plug.set_param(0, "quicksurf::gridSpacing", float(spacing))
+    try:
+        rmax = np.float32(data[:, 3].max())
+        pad = np.float32(radscale * rmax * np.float32(1.5))
+        padrad = np.float32(0.4 * np.sqrt(4.0 / 3.0 * float(np.float32(np.pi)) * float(pad) ** 3))
+        pad = max(pad, padrad)
+        lo = np.array(bbox[:3], np.float32) - pad
+        hi = np.array(bbox[3:], np.float32) + pad
+        res = tuple(int(np.ceil(np.float32(hi[a] - lo[a]) / spacing)) for a in range(3))
+        plug.res = res  # the harness sizes its copy buffer from this
+        vol, meta = plug.pull_volume()
+        assert meta["resolution"] == res
+        assert np.allclose(meta["origin"], lo, rtol=0, atol=1e-5)
+        assert np.allclose(meta["slicedist"], [spacing] * 3, rtol=1e-6)
+        rvol, _ = oracle.density_gauss(lists, meta["origin"], np.array(meta["slicedist"], np.float32), res, radscale=float(radscale), gausslim=2.0)
+        assert (np.abs(vol - rvol) / np.maximum(rvol, 1e-5 * rvol.max())).max() < 2e-5
+        m = plug.pull_mesh(0.5)
+        assert m["nverts"] > 1000
+        assert m["pos"].min(0).min() >= lo.min() - 1e-3 and (m["pos"].max(0) <= hi + spacing).all()
+    finally:
+        plug.set_param(0, "mode", 0)
+        plug.set_param(0, "quicksurf::gridSpacing", 0.0)
+        plug.set_param(0, "quicksurf::radiusScale", 1.0)
+        plug.set_param(0, "quicksurf::quality", 2)
