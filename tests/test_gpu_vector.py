@@ -103,3 +103,33 @@ def test_vector_aggregator_rejects_what_it_does_not_implement(surf):
     surf.compute_density()
     with pytest.raises(mm.MmsError):
         surf.get_vector_field()  # the last compute was a scalar aggregator: there is no vector field
+
+
+def test_mixed_lists_with_and_without_directions(surf, oracle):
+    """Two lists in one call: FLOAT_XYZR with a strided direction array and a FLOAT_XYZ list with DIRDATA_NONE (its particles only add
+    to the weights, pulling the average towards 0), the direction data handed over as a device pointer."""
+    import torch
+    n1, n2, box, res = 900, 600, 9.0, (40, 18, 20)
+    a = np.zeros((n1, 4), np.float32)
+    a[:, :3] = synth.uniform_box(n1, box, seed=501)
+    a[:, 3] = 0.3 + 0.4 * synth.uniform(502, 0, n1, 0)
+    d = np.zeros((n1, 5), np.float32)  # dx dy dz + two floats of padding: stride 20
+    d[:, :3] = np.stack([synth.uniform(503, 0, n1, k) for k in range(3)], 1) * 2 - 1
+    b = synth.uniform_box(n2, box, seed=504)
+    lists = [dict(vtx=a, vtx_type=2, count=n1, dir=d, dir_stride=20), dict(vtx=b, vtx_type=1, count=n2, global_radius=0.5)]
+    c = dict(lists=lists, bmin=(0, 0, 0), bext=(box,) * 3, res=res, cyclic=(1, 0, 1), sigma=0.9, normalize=0)
+    ovec, omag, _, (omn, omx) = oracle.density_p2d_vector(lists, c["bmin"], c["bext"], res, c["cyclic"], sigma=0.9, normalize=False)
+    dd = torch.from_numpy(d).cuda()
+    gl = [dict(lists[0], dir=dd.data_ptr()), lists[1]]
+    surf.clear_particles()
+    surf.set_grid(c["bmin"], c["bext"], res, c["cyclic"])
+    surf.set_params(mode=0, aggregator=2, normalize=0, defer_normalize=0, sigma=0.9)
+    surf.push_particles(gl)
+    surf.compute_density()
+    vec, mag, _ = surf.get_vector_field()
+    tail = H.vector_tail_mask(oracle, c)
+    assert (np.abs(vec.astype(np.float64) - ovec) / np.maximum(np.abs(ovec), 1.0))[~tail].max() < VEC_RTOL
+    assert np.array_equal(mag != 0, omag != 0)
+    mn, mx = surf.density_range()
+    assert abs(mx - omx) <= VEC_RTOL * omx and mn == omn == 0.0
+    surf.set_params(aggregator=0, sigma=1.0)
