@@ -1,0 +1,3 @@
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -6
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+python bench.py --steps 10 --warmup 3 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; tail -c 900 gpurun_out/bench_n1.json; tail -3 gpurun_out/bench_n1.err
