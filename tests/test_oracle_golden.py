@@ -52,6 +52,22 @@ def test_vector_field_bit_identical_to_reference(oracle, path):
     assert np.array_equal(c["info"][:, 6], col if c["normalize"] else m)
 
 
+def test_vector_field_of_a_uniform_direction_is_that_direction(oracle):
+    """Property of aggregator 2: sum(w d0)/sum(w) = d0 wherever any particle reaches, whatever the weights; 0 elsewhere."""
+    from megamol_b200 import synth
+    n, box, res = 800, 8.0, (20, 18, 16)
+    xyz = synth.uniform_box(n, box, seed=61)
+    d0 = np.array([0.3, -1.2, 0.7], np.float32)
+    lists = [dict(vtx=xyz, vtx_type=1, count=n, global_radius=0.45, dir=np.tile(d0, (n, 1)))]
+    vec, mag, dirs, (mn, mx) = oracle.density_p2d_vector(lists, (0, 0, 0), (box,) * 3, res, (1, 0, 1), sigma=1.0, normalize=False)
+    w, _ = oracle.density_p2d([dict(vtx=xyz, vtx_type=1, count=n, global_radius=0.45)], (0, 0, 0), (box,) * 3, res, (1, 0, 1))
+    hit = w > 1e-30
+    assert hit.any() and (~hit).any()
+    assert np.abs(vec[hit] - d0).max() < 1e-5 and not vec[w == 0].any()
+    assert abs(mx - float(np.linalg.norm(d0))) < 1e-5 and mn == 0.0
+    assert np.abs(dirs[hit] - d0 / np.linalg.norm(d0)).max() < 1e-5
+
+
 def test_home_voxels_match_reference_kat(oracle):
     z = np.load(os.path.join(G.GOLDEN, "home_voxel_kat.npz"))
     pts = np.ascontiguousarray(z["points"])
