@@ -516,6 +516,7 @@ __global__ void __launch_bounds__(MC_THREADS) mc_emit_kernel(McGeo m, const __gr
             const float ty0 = sh.tab[E_TAB_Y + ly], ty1 = sh.tab[E_TAB_Y + ly + 1];
             const float tz0 = sh.tab[E_TAB_Z + lz], tz1 = sh.tab[E_TAB_Z + lz + 1];
             const unsigned* etab = sh.edgeTab[rr];
+#pragma unroll 2 // two independent gather chains in flight: 3.08 -> 3.04 ms (unroll 4 spills: 3.16 ms)
             for (unsigned j = lane; j < ncorn + lane; j += 32, op += 96, on += 96) { // trip count uniform over the warp (shuffles inside)
                 const bool act = j < ncorn;
                 const unsigned t = act ? j / 3 : 0;
