@@ -6,18 +6,20 @@
 //                     cells look up their triangle count (case table of trisoup::volumetrics::MarchingCubeTables,
 //                     MarchingCubeTables.cpp:11-16,58,278; cube index bit i <=> corner i < iso).
 //   (exclusive scan of the segment counts: scan.cuh -> triangle offsets in CELL-LINEAR order)
-//   mc_emit_kernel    a block owns a 32x8-cell column and marches in z, two cell layers per step; the density planes live in
-//                     a ring in shared memory that TMA (cp.async.bulk.tensor, one 40x11 box per plane, mbarrier completion)
-//                     fills one step ahead.  Per step:
-//                       M  bit masks of the step's 27 node rows (ballot)
-//                       X  crossed grid edges = XOR of neighbouring masks; one thread per (row, axis) group, warp scan of the
-//                          pop-counts, the set bits are expanded into a compact list
-//                       V  one vertex per crossed edge, full lanes: interpolation parameter, coordinate, gradient normal
-//                          -> one float4 record per edge in shared memory
-//                       C  per 32-cell row: cube indices from the masks, warp prefix scan of the per-cell triangle counts,
-//                          then the row's triangle corners are FLATTENED over the lanes (corner j -> lane j mod 32): a lane
-//                          looks up its edge record through a 12-entry table and writes 3+3 floats; consecutive lanes write
-//                          consecutive 12-byte pieces, so every warp store covers one contiguous span of the output.
+//   mc_emit_kernel    a block owns a 32x8-cell column and marches in z, ONE cell layer per iteration; the density planes live
+//                     in a ring in shared memory that TMA (cp.async.bulk.tensor, one 40x11 box per plane, mbarrier completion)
+//                     fills one iteration ahead.  The vertex records (one float4 per crossed grid edge) are kept per NODE PLANE
+//                     (x- and y-edges) and per CELL LAYER (z-edges) in small rings, so every edge vertex of the column is computed
+//                     exactly once while the march passes it.  Iteration j runs three independent pieces of work between two
+//                     block barriers -- they touch different buffers, so no barrier separates them:
+//                       MX(j+1) a warp per node row of plane j+1: "below iso" masks by ballot, crossed edges = XOR with the
+//                               neighbouring masks (x: shifted, y: next row, z: plane j), ballot-compacted into a crossing list
+//                       V(j)    one vertex per crossed edge of plane j / layer j-1, full lanes: interpolation parameter, coordinate,
+//                               gradient normal -> one float4 record
+//                       C(j-2)  a warp per 32-cell row of layer j-2: cube indices from the masks, warp prefix scan of the per-cell
+//                               triangle counts, then the row's triangle corners are FLATTENED over the lanes (corner j -> lane
+//                               j mod 32): a lane looks up its edge record through a 12-entry table and writes 3+3 floats;
+//                               consecutive lanes write consecutive 12-byte pieces, every warp store covers one contiguous span.
 // Output order = cell-linear (x fastest, then y, then z), inside a cell the table's order: independent of the
 // tile shape and of the z-slab decomposition.
 #pragma once
@@ -146,43 +148,48 @@ __global__ void __launch_bounds__(MC_THREADS) mc_count_kernel(McGeo m, const flo
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// emit: z-marching, software-pipelined
+// emit: z-marching column blocks, one cell layer per iteration, vertex records kept per node plane / cell layer
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int EX = 32, EY = 8, EZ = 2;                      // cells per step
-constexpr int ENX = EX + 1, ENY = EY + 1, ENZ = EZ + 1;     // nodes per step
+constexpr int EX = 32, EY = 8;                              // cells per layer of a block column
+constexpr int ENX = EX + 1, ENY = EY + 1;                   // nodes per plane of a block column
 constexpr int EHY = EY + 3;                                 // node rows + gradient halo (y0-1 .. y0+9)
 constexpr int EPITCH = 40;                                  // x0-4 .. x0+35 (x0-1 .. x0+33 are needed): TMA wants the box start and width in
                                                             // multiples of 16 bytes (an unaligned start coordinate is an illegal instruction)
 constexpr int EHX0 = 4;                                     // ring column of node 0
 constexpr int EPLANE = 448;                                 // floats per ring slot: 11*40 = 440, padded to 14*128 bytes
-constexpr int ERING = 8;                                    // plane slots (5 of the current step + 2 prefetched; power of two)
-constexpr int EM_STEPS = 16;                                // steps per block (32 cell layers)
-constexpr int E_XEDGES = ENZ * ENY * EX;                    // 864  x-edges: (plane*9 + row)*32 + ix,      ix < 32
-constexpr int E_YEDGES = ENZ * EY * ENX;                    // 792  y-edges: (plane*8 + row)*33 + ix,      row < 8
-constexpr int E_ZEDGES = EZ * ENY * ENX;                    // 594  z-edges: (plane*9 + row)*33 + ix,      plane < 2
-constexpr int E_YBASE = E_XEDGES, E_ZBASE = E_XEDGES + E_YEDGES, E_EDGES = E_XEDGES + E_YEDGES + E_ZEDGES;
+constexpr int ERING = 6;                                    // plane slots: V(j) reads planes j-2 .. j+1 while plane j+2 is in flight
+constexpr int EM_LAYERS = 32;                               // cell layers per block
+// a crossed grid edge is named (axis, node row r, node ix): list entry = axis << 10 | r << 6 | ix; its record sits at r*33 + ix of
+//   x-edges  node-plane buffer            (r < 9, ix < 32)
+//   y-edges  node-plane buffer + E_YOFF   (r < 8, ix < 33)
+//   z-edges  cell-layer buffer            (r < 9, ix < 33)
+constexpr int E_YOFF = ENY * ENX;                           // 297
+constexpr int E_PLREC = E_YOFF + EY * ENX;                  // 561 records per node plane
+constexpr int E_ZEDGES = ENY * ENX;                         // 297 records per cell layer
+constexpr int E_ZREC0 = 3 * E_PLREC;                        // records: three node-plane buffers, then two cell-layer buffers
+constexpr int E_RECS = 3 * E_PLREC + 2 * E_ZEDGES;          // 2277
+constexpr int E_LIST = 864;                                 // >= 9*32 + 8*33 + 9*33 = 849 crossings per iteration
 constexpr int E_MAXROWTRIS = 160;
-constexpr int E_ROWS = EM_STEPS * EZ * EY;                  // 256 cell rows per block chunk
-constexpr int E_TAB_Y = ENX, E_TAB_Z = ENX + ENY;           // node position table: 33 x, 9 y, 3 z (z per step)
-constexpr unsigned E_PLANE_BYTES = EHY * EPITCH * 4;        // 1584
+constexpr int E_ROWS = EM_LAYERS * EY;                      // 256 cell rows per block
+constexpr int E_TAB_Y = ENX;                                // node position table: 33 x, 9 y
+constexpr unsigned E_PLANE_BYTES = EHY * EPITCH * 4;
 
 struct __align__(128) McEmitShared {
-    float ring[ERING * EPLANE];                 // plane with node index z sits in slot (z - zcBeg + 1) mod ERING      14336 B
-    float4 edge[E_EDGES];                       // {interpolated coordinate along the edge's axis, nx, ny, nz}          36000 B
-    union {
-        unsigned short crossList[E_EDGES];      // phases X, V
-        unsigned char triOwner[MC_THREADS / 32][E_MAXROWTRIS]; // phase C: (owner lane << 3) | triangle number inside the owner cell
-    };
+    float ring[ERING * EPLANE];                 // node plane p (relative to the block's first cell layer) sits in slot (p + 1) mod ERING
+    float4 rec[E_RECS];                         // {interpolated coordinate along the edge's axis, nx, ny, nz}
+    unsigned short list[2][E_LIST];             // crossing list of plane j in list[j & 1]
+    unsigned char triOwner[MC_THREADS / 32][E_MAXROWTRIS]; // (owner lane << 3) | triangle number inside the owner cell
+    unsigned segOff[E_ROWS];                    // first triangle of every cell row of the block
     unsigned char segCnt[E_ROWS];               // its triangle count (<= 160)
-    unsigned edgeTab[EZ * EY][12];              // per (layer, row) of a step and cube edge: edge slot of cell 0 | flags
-    float tab[E_TAB_Z + ENZ + 3];               // node positions float(idx)*sd + origin (ParticlesToDensity.cpp:605)
-    unsigned below[ENZ * ENY];                  // "below iso" bits of the step's node rows, nodes 0..31
-    unsigned col32;                             // ... of node 32 of every row (bit plane*9 + row)
-    unsigned stepAct[MC_THREADS / 32];
-    int ncross;
-    unsigned long long mbar;
+    unsigned etab[MC_THREADS / 32][12];         // per warp (= cell row) and cube edge: record slot of cell 0 | flags
+    uint2 below[4][ENY];                        // "below iso" bits of node plane j in below[j & 3]: .x nodes 0..31, .y node 32
+    float tab[ENX + ENY + 2];                   // node positions float(idx)*sd + origin (ParticlesToDensity.cpp:605)
+    unsigned actWarp[MC_THREADS / 32];
+    int ncross[4];                              // length of the crossing list of plane j in ncross[j mod 3]
+    unsigned long long mbar[2];                 // plane loads alternate between two mbarriers (see the loop)
 };
 static_assert(sizeof(McEmitShared) + 128 <= 57088, "mc_emit_kernel must fit four blocks per SM");
+static_assert(E_RECS < 4096, "record slots are 12-bit fields of the edge table");
 
 // per cube edge: low corner (dx,dy,dz) and axis: dx | dy<<1 | dz<<2 | axis<<3   (MarchingCubeTables.cpp:15-16, low node first)
 //  e0 (0,0,0)x  e1 (1,0,0)y  e2 (0,1,0)x  e3 (0,0,0)y  e4 (0,0,1)x  e5 (1,0,1)y  e6 (0,1,1)x  e7 (0,0,1)y
@@ -193,7 +200,7 @@ __host__ __device__ __forceinline__ unsigned edgeCode(int e) {
     return static_cast<unsigned>(codes >> (5 * e)) & 31u;
 }
 
-// flags of an edgeTab entry (bits 0..11 = edge slot of the row's cell 0)
+// flags of an etab entry (bits 0..11 = record slot of the row's cell 0)
 constexpr unsigned ET_AX0 = 1u << 12, ET_AX1 = 1u << 13, ET_AX2 = 1u << 14, ET_DX = 1u << 15, ET_DY = 1u << 16, ET_DZ = 1u << 17;
 
 __device__ __forceinline__ float rcpApproxF(float x) {
@@ -230,68 +237,75 @@ __device__ __forceinline__ void tmaLoadPlane(float* smemDst, const CUtensorMap* 
  * TMA: the planes arrive as 40x11x1 boxes of a 3-D tensor map over the slab volume (needs sx % 4 == 0; out-of-range elements are
  * zero-filled, which is harmless: gradients at the global border are one-sided and cells beyond the grid are masked).
  * !TMA: the same ring filled with 4-byte cp.async copies, coordinates clamped.
+ *
+ * Iteration j (j = first active layer - 1 .. last active layer + 2) runs MX(j+1), V(j) and C(j-2); what they share:
+ *   ring      MX(j+1) reads plane j+1, V(j) planes j-2 .. j+1; the load of plane j+2 is in flight into the slot of plane j-4
+ *   below     MX(j+1) writes [(j+1)&3] and reads [j&3]; C(j-2) reads [(j-2)&3], [(j-1)&3]
+ *   list      MX(j+1) writes [(j+1)&1], V(j) reads [j&1]
+ *   rec       V(j) writes plane buffer j mod 3 and layer buffer (j-1)&1; C(j-2) reads planes (j-2) mod 3, (j-1) mod 3, layer (j-2)&1
+ * so ONE block barrier per iteration orders everything.  Inside an iteration the warps split the work by role = (warp - j) mod 8
+ * (rotating, so that nobody is the slow one every time): roles 0..2 run MX (three node rows each), roles 3..7 walk the crossing
+ * list of V; then every warp emits the triangles of cell row `warp` of layer j-2.
  */
 template<bool COLOUR, bool TMA>
-__global__ void __launch_bounds__(MC_THREADS) mc_emit_kernel(McGeo m, const __grid_constant__ CUtensorMap volMap, const float* __restrict__ vol,
-    const float* __restrict__ rgb, const unsigned* __restrict__ segOffset, float* __restrict__ outPos, float* __restrict__ outNrm,
-    float* __restrict__ outCol) {
+__global__ void __launch_bounds__(MC_THREADS, COLOUR ? 2 : 4) mc_emit_kernel(McGeo m, const __grid_constant__ CUtensorMap volMap,
+    const float* __restrict__ vol, const float* __restrict__ rgb, const unsigned* __restrict__ segOffset, float* __restrict__ outPos,
+    float* __restrict__ outNrm, float* __restrict__ outCol) {
     extern __shared__ unsigned char smemRaw[];
     unsigned char* smemAligned = smemRaw + ((128u - (smemAddr(smemRaw) & 127u)) & 127u);
     McEmitShared& sh = *reinterpret_cast<McEmitShared*>(smemAligned);
-    float4* edgeCol = reinterpret_cast<float4*>(smemAligned + sizeof(McEmitShared)); // COLOUR only
+    float4* recCol = reinterpret_cast<float4*>(smemAligned + sizeof(McEmitShared)); // COLOUR only
     const int x0 = blockIdx.x * EX, y0 = blockIdx.y * EY;
-    const int zcBeg = m.cz0 + blockIdx.z * (EM_STEPS * EZ);           // first global cell layer of this block
-    const int zcEnd = min(zcBeg + EM_STEPS * EZ, m.cz0 + m.cnz);      // exclusive
+    const int zcBeg = m.cz0 + blockIdx.z * EM_LAYERS;                      // first global cell layer (= node plane) of this block
+    const int nLayers = min(EM_LAYERS, m.cz0 + m.cnz - zcBeg);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-    // ---- which rows / steps have triangles (one global read per row of the chunk) -----------------------------------
+    // ---- the block's cell rows: first triangle, triangle count, which layers have any (one global read per row) ---------
     {
-        const int ly = tid % EY, lzc = tid / EY; // E_ROWS == MC_THREADS
-        const int cyi = y0 + ly, czi = zcBeg + lzc;
+        const int ly = tid % EY, k = tid / EY; // E_ROWS == MC_THREADS
+        const int cyi = y0 + ly;
         unsigned off = 0, cnt = 0;
-        if (cyi < m.cy && czi < zcEnd) {
-            const size_t seg = blockIdx.x + static_cast<size_t>(m.nsegx) * (cyi + static_cast<size_t>(m.cy) * (czi - m.cz0));
+        if (cyi < m.cy && k < nLayers) {
+            const size_t seg = blockIdx.x + static_cast<size_t>(m.nsegx) * (cyi + static_cast<size_t>(m.cy) * (zcBeg + k - m.cz0));
             off = segOffset[seg];
             cnt = segOffset[seg + 1] - off;
         }
+        sh.segOff[tid] = off;
         sh.segCnt[tid] = static_cast<unsigned char>(cnt);
-        const unsigned bal = __ballot_sync(0xffffffffu, cnt != 0); // rows 16s .. 16s+15 belong to step s
-        if (lane == 0) sh.stepAct[warp] = ((bal & 0xffffu) ? 1u : 0u) | ((bal >> 16) ? 2u : 0u);
-    }
-    if (tid < EZ * EY * 12) {
-        const int row = tid / 12, e = tid % 12, ly = row % EY, lz = row / EY;
-        const unsigned code = edgeCode(e);
-        const int dx = code & 1, dy = (code >> 1) & 1, dz = (code >> 2) & 1, axis = code >> 3;
-        unsigned slot;
-        if (axis == 0) slot = ((lz + dz) * ENY + ly + dy) * EX + dx;
-        else if (axis == 1) slot = E_YBASE + ((lz + dz) * EY + ly + dy) * ENX + dx;
-        else slot = E_ZBASE + ((lz + dz) * ENY + ly + dy) * ENX + dx;
-        sh.edgeTab[row][e] = slot | (ET_AX0 << axis) | (dx ? ET_DX : 0u) | (dy ? ET_DY : 0u) | (dz ? ET_DZ : 0u);
+        const unsigned bal = __ballot_sync(0xffffffffu, cnt != 0); // rows 8i .. 8i+7 of this warp belong to layer 4*warp + i
+        if (lane == 0)
+            sh.actWarp[warp] = ((bal & 0xffu) ? 1u : 0u) | ((bal & 0xff00u) ? 2u : 0u) | ((bal & 0xff0000u) ? 4u : 0u) | ((bal >> 24) ? 8u : 0u);
     }
     if (tid < ENX) sh.tab[tid] = __fadd_rn(__fmul_rn((float)(x0 + tid), m.sd[0]), m.org[0]);
     else if (tid < ENX + ENY) sh.tab[tid] = __fadd_rn(__fmul_rn((float)(y0 + tid - ENX), m.sd[1]), m.org[1]);
-    if (TMA && tid == 0) mbarInit(&sh.mbar, 1);
+    if (tid < 4) sh.ncross[tid] = 0;
+    if (TMA && tid == 0) mbarInit(&sh.mbar[0], 1), mbarInit(&sh.mbar[1], 1);
     __syncthreads();
-    unsigned stepMask = 0;
+    unsigned act = 0;
 #pragma unroll
-    for (int w = 0; w < MC_THREADS / 32; ++w) stepMask |= sh.stepAct[w] << (2 * w);
-    if (!stepMask) return;
+    for (int w = 0; w < MC_THREADS / 32; ++w) act |= sh.actWarp[w] << (4 * w);
+    if (!act) return;
+    const int kFirst = __ffs(act) - 1, kLast = 31 - __clz(act);
 
     // ---- plane loader -------------------------------------------------------------------------------------------------
-    auto slotOf = [&](int zNode) { return (zNode - zcBeg + 1) & (ERING - 1); }; // zNode >= zcBeg - 1
-    unsigned tmaParity = 0;
-    auto loadPlanes = [&](int zFirst, int zLast) { // uniform; planes zFirst..zLast (node indices), asynchronous
+    // Load batch q signals mbar[q & 1] (phase parity (q >> 1) & 1).  Two barriers, because thread 0 arms the next batch right after its
+    // own wait: with a single barrier a fast load could complete the NEXT phase before a slower warp has polled this one, and that
+    // warp would then wait for a phase nobody arms.  Batch q+2 re-uses batch q's barrier one block barrier later: everybody is past it.
+    unsigned qIssue = 0, qWait = 0;
+    auto issuePlanes = [&](int pFirst, int pLast, int slotOff) { // uniform; asynchronous; plane pFirst goes to ring offset slotOff (floats)
         if (TMA) {
             if (tid == 0) {
-                mbarExpectTx(&sh.mbar, static_cast<unsigned>(zLast - zFirst + 1) * E_PLANE_BYTES);
-                for (int z = zFirst; z <= zLast; ++z)
-                    tmaLoadPlane(&sh.ring[slotOf(z) * EPLANE], &volMap, x0 - EHX0, y0 - 1, z - m.zPlane0, &sh.mbar);
+                unsigned long long* bar = &sh.mbar[qIssue & 1u];
+                mbarExpectTx(bar, static_cast<unsigned>(pLast - pFirst + 1) * E_PLANE_BYTES);
+                for (int p = pFirst; p <= pLast; ++p, slotOff = slotOff == (ERING - 1) * EPLANE ? 0 : slotOff + EPLANE)
+                    tmaLoadPlane(&sh.ring[slotOff], &volMap, x0 - EHX0, y0 - 1, zcBeg + p - m.zPlane0, bar);
             }
+            ++qIssue;
         } else {
-            for (int z = zFirst; z <= zLast; ++z) {
-                const int zg = min(max(z, 0), m.szGlobal - 1);
+            for (int p = pFirst; p <= pLast; ++p, slotOff = slotOff == (ERING - 1) * EPLANE ? 0 : slotOff + EPLANE) {
+                const int zg = min(max(zcBeg + p, 0), m.szGlobal - 1);
                 const int zl = min(max(zg - m.zPlane0, 0), m.nzPlanes - 1);
-                float* dst = &sh.ring[slotOf(z) * EPLANE];
+                float* dst = &sh.ring[slotOff];
                 for (int i = tid; i < EHY * (ENX + 2); i += MC_THREADS) { // nodes -1 .. 33 of every row
                     const int ix = i % (ENX + 2) - 1, iy = i / (ENX + 2);
                     const int x = min(max(x0 + ix, 0), m.sx - 1), y = min(max(y0 + iy - 1, 0), m.sy - 1);
@@ -299,14 +313,6 @@ __global__ void __launch_bounds__(MC_THREADS) mc_emit_kernel(McGeo m, const __gr
                 }
             }
             asm volatile("cp.async.commit_group;");
-        }
-    };
-    auto waitPlanes = [&]() {
-        if (TMA) {
-            mbarWait(&sh.mbar, tmaParity);
-            tmaParity ^= 1u;
-        } else {
-            asm volatile("cp.async.wait_group 0;");
         }
     };
 
@@ -317,236 +323,255 @@ __global__ void __launch_bounds__(MC_THREADS) mc_emit_kernel(McGeo m, const __gr
     const unsigned nodeValidX = nvx >= 32 ? 0xffffffffu : (1u << nvx) - 1u;            // nodes 0..31
     const unsigned xEdgeValid = nvx >= 33 ? 0xffffffffu : (1u << (nvx - 1)) - 1u;      // x-edge ix needs node ix+1
     const unsigned cellValidX = m.cx - x0 >= 32 ? 0xffffffffu : (1u << (m.cx - x0)) - 1u;
+    const unsigned ltMask = (1u << lane) - 1u;
+    const bool xyInterior = x0 > 0 && x0 + EX < m.sx - 1 && y0 > 0 && y0 + EY < m.sy - 1; // no node of the column touches the x/y border
     unsigned char* owner = sh.triOwner[warp];
-
-    int loadedUpTo = -0x40000000; // highest node plane present in (or on its way into) the ring
-    bool pending = false;         // a load batch has been issued and not yet waited for
-    while (stepMask) {
-        const int step = __ffs(stepMask) - 1;
-        stepMask &= stepMask - 1;
-        const int zc0 = zcBeg + step * EZ; // global cell layer = global node plane of the step's lowest cells
-        // planes zc0-1 .. zc0+3 must be in the ring.  In the dense case the previous step prefetched the two new ones.
-        if (loadedUpTo < zc0 + EZ + 1) {
-            if (pending) waitPlanes(), pending = false;
-            __syncthreads(); // every warp has left phase V of the previous step: no ring slot is being read any more
-            loadPlanes(max(loadedUpTo + 1, zc0 - 1), zc0 + EZ + 1);
-            loadedUpTo = zc0 + EZ + 1;
-            pending = true;
-        }
-        if (pending) waitPlanes(), pending = false;
-        __syncthreads(); // S1: the planes have landed for everybody; every warp has left phase C of the previous step
-        if (stepMask && (__ffs(stepMask) - 1) == step + 1) { // prefetch the two planes the next step adds while this one computes
-            loadPlanes(zc0 + EZ + 2, zc0 + EZ + 3);
-            loadedUpTo = zc0 + EZ + 3;
-            pending = true;
-        }
-        const int slot0 = (step * EZ) & (ERING - 1);            // slot of halo plane 0 = node plane zc0 - 1
-        auto planeOff = [&](int hz) { return ((slot0 + hz) & (ERING - 1)) * EPLANE; }; // hz = node plane + 1 (halo coordinates)
-        const int nvz = min(ENZ, zcEnd - zc0 + 1);              // valid node planes of the step (cell layers beyond zcEnd are not ours)
-
-        // ---- M: bit masks ------------------------------------------------------------------------------------------------
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int q = warp + 8 * k; // node row: plane q / 9, row q % 9
-            if (q < ENZ * ENY) {
-                const int p = (q * 57) >> 9, r = q - 9 * p;
-                const unsigned b = __ballot_sync(0xffffffffu, sh.ring[planeOff(p + 1) + (r + 1) * EPITCH + lane + EHX0] < iso);
-                if (lane == 0) sh.below[q] = b;
-            }
-        }
-        if (warp == 7) {
-            const int q = min(lane, ENZ * ENY - 1);
-            const int p = (q * 57) >> 9, r = q - 9 * p;
-            const unsigned b = __ballot_sync(0xffffffffu, lane < ENZ * ENY && sh.ring[planeOff(p + 1) + (r + 1) * EPITCH + EX + EHX0] < iso);
-            if (lane == 0) sh.col32 = nvx >= ENX ? b : 0u, sh.ncross = 0;
-        }
-        if (warp == 6 && lane < ENZ) sh.tab[E_TAB_Z + lane] = __fadd_rn(__fmul_rn((float)(zc0 + lane), m.sd[2]), m.org[2]);
-        __syncthreads(); // S2
-
-        // ---- X: crossed edges -> crossList ----------------------------------------------------------------------------------
-        if (tid < 96) {
-            const int g = tid;
-            unsigned mask = 0, base = 0, stride = 1;
-            const unsigned c32 = sh.col32;
-            if (g < 27) {           // x-edges of node row g = p*9 + r
-                const int p = (g * 57) >> 9, r = g - 9 * p;
-                const unsigned b = sh.below[g];
-                if (r < nvy && p < nvz) mask = (b ^ ((b >> 1) | (((c32 >> g) & 1u) << 31))) & xEdgeValid;
-                base = g * EX;
-            } else if (g < 51) {    // y-edges between node rows r and r+1 of plane p, j = p*8 + r
-                const int j = g - 27, p = j >> 3, r = j & 7;
-                if (r + 1 < nvy && p < nvz) mask = (sh.below[p * ENY + r] ^ sh.below[p * ENY + r + 1]) & nodeValidX;
-                base = E_YBASE + j * ENX;
-            } else if (g < 69) {    // z-edges between planes p and p+1, j = p*9 + r
-                const int j = g - 51, p = j >= ENY ? 1 : 0, r = j - ENY * p;
-                if (r < nvy && p + 1 < nvz) mask = (sh.below[j] ^ sh.below[j + ENY]) & nodeValidX;
-                base = E_ZBASE + j * ENX;
-            } else if (g == 69) {   // y-edges of node column 32: bit p*8 + r
-                const unsigned rows = (1u << (nvy - 1)) - 1u; // r + 1 < nvy
-#pragma unroll
-                for (int p = 0; p < ENZ; ++p)
-                    if (p < nvz) mask |= (((c32 >> (ENY * p)) ^ (c32 >> (ENY * p + 1))) & 0xffu & rows) << (8 * p);
-                if (nvx < ENX) mask = 0;
-                base = E_YBASE + EX, stride = ENX;
-            } else if (g == 70) {   // z-edges of node column 32: bit p*9 + r
-                const unsigned rows = (1u << nvy) - 1u;
-                mask = (c32 ^ (c32 >> ENY)) & (rows | (nvz > 2 ? rows << ENY : 0u));
-                if (nvx < ENX || nvz < 2) mask = 0;
-                base = E_ZBASE + EX, stride = ENX;
-            }
-            const unsigned cnt = __popc(mask);
-            unsigned inc = cnt;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const unsigned t = __shfl_up_sync(0xffffffffu, inc, d);
-                if (lane >= d) inc += t;
-            }
-            unsigned wbase = 0;
-            if (lane == 31 && inc) wbase = atomicAdd(&sh.ncross, static_cast<int>(inc));
-            wbase = __shfl_sync(0xffffffffu, wbase, 31);
-            unsigned pos = wbase + inc - cnt;
-            while (mask) {
-                const int b = __ffs(mask) - 1;
-                mask &= mask - 1;
-                sh.crossList[pos++] = static_cast<unsigned short>(base + b * stride);
-            }
-        }
-        __syncthreads(); // S3
-
-        // ---- V: one vertex per crossed edge --------------------------------------------------------------------------------
-        const int ncross = sh.ncross;
-        // no node of this step touches the global border -> plain central differences
-        const bool interior = x0 > 0 && x0 + EX < m.sx - 1 && y0 > 0 && y0 + EY < m.sy - 1 && zc0 > 0 && zc0 + EZ < m.szGlobal - 1;
-        for (int c = tid; c < ncross; c += MC_THREADS) {
-            const int id = sh.crossList[c];
-            int axis, ix, r, p;
-            if (id < E_YBASE) { axis = 0; ix = id & 31; const int q = id >> 5; p = (q * 57) >> 9; r = q - 9 * p; }
-            else if (id < E_ZBASE) { axis = 1; const int t = id - E_YBASE; const int q = (t * 993) >> 15; ix = t - ENX * q; p = q >> 3; r = q & 7; }
-            else { axis = 2; const int t = id - E_ZBASE; const int q = (t * 993) >> 15; ix = t - ENX * q; p = q >= ENY ? 1 : 0; r = q - ENY * p; }
-            const int offA = (r + 1) * EPITCH + ix + EHX0;
-            const int offB = offA + (axis == 0 ? 1 : (axis == 1 ? EPITCH : 0));
-            const int hzA = p + 1, hzB = hzA + (axis == 2 ? 1 : 0);
-            // gradient at a node: (f(+) - f(-)) * 1/(n*sd), samples clamped at the GLOBAL grid border
-            auto grad = [&](int off, int hz, int gxi, int gyi, int gzi, float& gx, float& gy, float& gz) {
-                const float* P0 = sh.ring + planeOff(hz) + off;
-                const float* Pm = sh.ring + planeOff(hz - 1) + off;
-                const float* Pp = sh.ring + planeOff(hz + 1) + off;
-                if (interior) {
-                    gx = __fmul_rn(__fsub_rn(P0[1], P0[-1]), r2x);
-                    gy = __fmul_rn(__fsub_rn(P0[EPITCH], P0[-EPITCH]), r2y);
-                    gz = __fmul_rn(__fsub_rn(Pp[0], Pm[0]), r2z);
-                } else {
-                    const int xm = gxi > 0 ? 1 : 0, xp = gxi < m.sx - 1 ? 1 : 0;
-                    const int ym = gyi > 0 ? 1 : 0, yp = gyi < m.sy - 1 ? 1 : 0;
-                    const int zm = gzi > 0 ? 1 : 0, zp = gzi < m.szGlobal - 1 ? 1 : 0;
-                    gx = xp + xm ? __fmul_rn(__fsub_rn(P0[xp], P0[-xm]), xp + xm == 2 ? r2x : r1x) : 0.0f;
-                    gy = yp + ym ? __fmul_rn(__fsub_rn(P0[yp * EPITCH], P0[-ym * EPITCH]), yp + ym == 2 ? r2y : r1y) : 0.0f;
-                    gz = zp + zm ? __fmul_rn(__fsub_rn(zp ? Pp[0] : P0[0], zm ? Pm[0] : P0[0]), zp + zm == 2 ? r2z : r1z) : 0.0f;
-                }
-            };
-            const float fa = sh.ring[planeOff(hzA) + offA], fb = sh.ring[planeOff(hzB) + offB];
-            // t = (iso - fa) / (fb - fa): SFU reciprocal (2 ulp; vertices are compared at 1e-4 of a cell); the IEEE division only
-            // where the difference is too small for rcp.approx
-            const float tnum = __fsub_rn(iso, fa), tden = __fsub_rn(fb, fa);
-            const float t01 = fabsf(tden) > 1e-30f ? __fmul_rn(tnum, rcpApproxF(tden)) : __fdiv_rn(tnum, tden);
-            const int ti = axis == 0 ? ix : (axis == 1 ? E_TAB_Y + r : E_TAB_Z + p);
-            const float pa = sh.tab[ti], pb = sh.tab[ti + 1];
-            float gax, gay, gaz, gbx, gby, gbz;
-            const int gxi = x0 + ix, gyi = y0 + r, gzi = zc0 + p;
-            grad(offA, hzA, gxi, gyi, gzi, gax, gay, gaz);
-            grad(offB, hzB, gxi + (axis == 0), gyi + (axis == 1), gzi + (axis == 2), gbx, gby, gbz);
-            const float gx = __fadd_rn(gax, __fmul_rn(t01, __fsub_rn(gbx, gax)));
-            const float gy = __fadd_rn(gay, __fmul_rn(t01, __fsub_rn(gby, gay)));
-            const float gz = __fadd_rn(gaz, __fmul_rn(t01, __fsub_rn(gbz, gaz)));
-            const float len2 = __fadd_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)), __fmul_rn(gz, gz));
-            const float inv = len2 > 0.0f ? -rsqrtf(len2) : 0.0f; // SFU rsqrt: 2 ulp, normals are compared at 1e-4
-            sh.edge[id] = make_float4(__fadd_rn(pa, __fmul_rn(t01, __fsub_rn(pb, pa))), __fmul_rn(gx, inv), __fmul_rn(gy, inv), __fmul_rn(gz, inv));
-            if (COLOUR) { // node colour = rgb / rho (0 where rho == 0), interpolated with the same t
-                auto nodeColour = [&](int nx_, int ny_, int nz_, float f, float& cr, float& cg, float& cb) {
-                    const int x = min(x0 + nx_, m.sx - 1), y = min(y0 + ny_, m.sy - 1);
-                    const int zl = min(max(zc0 + nz_ - m.zPlane0, 0), m.nzPlanes - 1);
-                    const float* cc = rgb + 3 * (x + static_cast<size_t>(m.sx) * (y + static_cast<size_t>(m.sy) * zl));
-                    if (f > 0.0f) cr = __fdiv_rn(cc[0], f), cg = __fdiv_rn(cc[1], f), cb = __fdiv_rn(cc[2], f);
-                    else cr = cg = cb = 0.0f;
-                };
-                float ar, ag, ab, br, bg, bb;
-                nodeColour(ix, r, p, fa, ar, ag, ab);
-                nodeColour(ix + (axis == 0), r + (axis == 1), p + (axis == 2), fb, br, bg, bb);
-                edgeCol[id] = make_float4(__fadd_rn(ar, __fmul_rn(t01, __fsub_rn(br, ar))), __fadd_rn(ag, __fmul_rn(t01, __fsub_rn(bg, ag))),
-                    __fadd_rn(ab, __fmul_rn(t01, __fsub_rn(bb, ab))), 0.0f);
-            }
-        }
-        __syncthreads(); // S4
-
-        // ---- C: triangles, one warp per 32-cell row ---------------------------------------------------------------------
-#pragma unroll 1
-        for (int rr = warp; rr < EY * EZ; rr += MC_THREADS / 32) {
-            const int ly = rr % EY, lz = rr / EY;
-            const int row = (step * EZ + lz) * EY + ly;
-            const unsigned segTris = sh.segCnt[row];
-            if (segTris == 0) continue;
-            const unsigned segOff = segOffset[blockIdx.x + static_cast<size_t>(m.nsegx) * (y0 + ly + static_cast<size_t>(m.cy) * (zc0 + lz - m.cz0))];
-            // cube index in permuted order from the (x, x+1) bit pairs of the four node rows
-            const int q = lz * ENY + ly;
-            const unsigned c32 = sh.col32;
-            const unsigned p00 = __funnelshift_r(sh.below[q], (c32 >> q) & 1u, lane) & 3u;
-            const unsigned p10 = __funnelshift_r(sh.below[q + 1], (c32 >> (q + 1)) & 1u, lane) & 3u;
-            const unsigned p01 = __funnelshift_r(sh.below[q + ENY], (c32 >> (q + ENY)) & 1u, lane) & 3u;
-            const unsigned p11 = __funnelshift_r(sh.below[q + ENY + 1], (c32 >> (q + ENY + 1)) & 1u, lane) & 3u;
-            unsigned long long word = 0;
-            if ((cellValidX >> lane) & 1u) word = __ldg(&kCasePerm.w[p00 | p10 << 2 | p01 << 4 | p11 << 6]);
-            const unsigned n = static_cast<unsigned>(word) & 15u;
-            unsigned inc = n;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const unsigned t = __shfl_up_sync(0xffffffffu, inc, d);
-                if (lane >= d) inc += t;
-            }
-            const unsigned first = inc - n; // my first triangle within the row
-#pragma unroll
-            for (unsigned k = 0; k < 5; ++k) // a cell has at most five triangles: five predicated stores instead of a counted loop
-                if (k < n) owner[first + k] = static_cast<unsigned char>(lane << 3 | k);
-            __syncwarp();
-            const unsigned wlo = static_cast<unsigned>(word >> 4), whi = static_cast<unsigned>(word >> 36); // 15 nibbles of edge ids
-            const unsigned ncorn = segTris * 3;
-            const size_t gbase = static_cast<size_t>(segOff) * 9;
-            float* op = outPos + gbase + lane * 3; // this lane's corner of the current round; 32 corners = 96 floats per round
-            float* on = outNrm + gbase + lane * 3;
-            float* oc = COLOUR ? outCol + gbase + lane * 3 : nullptr;
-            const float ty0 = sh.tab[E_TAB_Y + ly], ty1 = sh.tab[E_TAB_Y + ly + 1];
-            const float tz0 = sh.tab[E_TAB_Z + lz], tz1 = sh.tab[E_TAB_Z + lz + 1];
-            const unsigned* etab = sh.edgeTab[rr];
-#pragma unroll 2 // two independent gather chains in flight: 3.08 -> 3.04 ms (unroll 4 spills: 3.16 ms)
-            for (unsigned j = lane; j < ncorn + lane; j += 32, op += 96, on += 96) { // trip count uniform over the warp (shuffles inside)
-                const bool act = j < ncorn;
-                const unsigned t = act ? j / 3 : 0;
-                const unsigned ok = owner[t];
-                const unsigned L = ok >> 3;
-                const unsigned oLo = __shfl_sync(0xffffffffu, wlo, L), oHi = __shfl_sync(0xffffffffu, whi, L);
-                if (!act) continue;
-                const unsigned slotc = 3 * (ok & 7u) + (j - 3 * t); // corner number inside the owner cell (0..14)
-                const unsigned e = ((slotc < 8 ? oLo : oHi) >> ((4 * slotc) & 31u)) & 15u;
-                const unsigned ent = etab[e];
-                const unsigned eidx = (ent & 0xfffu) + L;
-                const float4 v = sh.edge[eidx];
-                float px = sh.tab[L + ((ent & ET_DX) ? 1 : 0)];
-                float py = (ent & ET_DY) ? ty1 : ty0;
-                float pz = (ent & ET_DZ) ? tz1 : tz0;
-                if (ent & ET_AX0) px = v.x;
-                if (ent & ET_AX1) py = v.x;
-                if (ent & ET_AX2) pz = v.x;
-                op[0] = px, op[1] = py, op[2] = pz;
-                on[0] = v.y, on[1] = v.z, on[2] = v.w;
-                if (COLOUR) {
-                    const float4 cc = edgeCol[eidx];
-                    float* o = oc + (j - lane) * 3;
-                    o[0] = cc.x, o[1] = cc.y, o[2] = cc.z;
-                }
-            }
-            __syncwarp();
-        }
+    // this warp's cell row is always row `warp` of the layer: static part of its edge table (lanes 0..11)
+    unsigned etStatic = 0;
+    bool etZ = false, etUp = false;
+    if (lane < 12) {
+        const unsigned code = edgeCode(lane);
+        const int dx = code & 1, dy = (code >> 1) & 1, dz = (code >> 2) & 1, axis = code >> 3;
+        const unsigned slot = (warp + dy) * ENX + dx + (axis == 1 ? E_YOFF : 0);
+        etStatic = slot | (ET_AX0 << axis) | (dx ? ET_DX : 0u) | (dy ? ET_DY : 0u) | (dz ? ET_DZ : 0u);
+        etZ = axis == 2, etUp = dz != 0;
     }
-    if (pending) waitPlanes(); // never leave a bulk copy in flight into a dying block's shared memory
+    const float ty0 = sh.tab[E_TAB_Y + warp], ty1 = sh.tab[E_TAB_Y + warp + 1];
+
+    // per-iteration state, rotated at the end of every iteration (no divisions in the loop)
+    int oM2 = ((kFirst + 4) % ERING) * EPLANE, oM1 = ((kFirst + 5) % ERING) * EPLANE, o0 = (kFirst % ERING) * EPLANE; // ring offsets of planes
+    int oP1 = ((kFirst + 1) % ERING) * EPLANE, oP2 = ((kFirst + 2) % ERING) * EPLANE;                                  // j-2 .. j+2, j = kFirst-1
+    int n3M = (kFirst + 1) % 3, n3J = (kFirst + 2) % 3, n3P = kFirst % 3;                       // (j-1) mod 3, j mod 3, (j+1) mod 3
+    int role = (warp - kFirst + 1) & 7;                                                           // (warp - j) mod 8
+    unsigned long long actWin = (static_cast<unsigned long long>(act) << 3) >> kFirst;            // bit i <=> layer j - 2 + i is active
+    issuePlanes(kFirst - 1, kFirst, o0); // planes j, j+1
+    bool pending = TMA; // a bulk load has been issued and not yet waited for
+    if (!TMA) {
+        asm volatile("cp.async.wait_group 0;");
+        __syncthreads();
+    }
+    for (int j = kFirst - 1; j <= kLast + 2; ++j) {
+        if (TMA && pending) {
+            mbarWait(&sh.mbar[qWait & 1u], (qWait >> 1) & 1u); // planes .. j+1 have landed (every thread waits itself: visibility)
+            ++qWait;
+            pending = false;
+        }
+        if (j <= kLast) { // plane j+2 for the next iteration; its slot held plane j-4, last read two barriers ago
+            issuePlanes(j + 2, j + 2, oP2);
+            pending = TMA;
+        }
+        const unsigned aw = static_cast<unsigned>(actWin);
+        const bool actC = aw & 1u, actJ = (aw >> 2) & 1u, actJ1 = (aw >> 3) & 1u; // layers j-2, j, j+1
+
+        if (role < 3) {
+            // ---- MX(j+1): masks of node plane j+1, crossed edges -> crossing list; three warps, three node rows each -------------
+            if (role == 0 && lane == 0) sh.ncross[n3M] = 0; // counter of plane j+2: last read by V(j-1), next used by MX(j+2)
+            if (actJ | actJ1) {
+                const int jj = j + 1, r0 = role * 3;
+                const float* P = sh.ring + oP1 + (r0 + 1) * EPITCH + EHX0; // node (row r0, x 0) of plane j+1
+                uint2* belowJ = sh.below[jj & 3] + r0;
+                const uint2* belowP = sh.below[j & 3] + r0;
+                unsigned short* list = sh.list[jj & 1];
+                // node 32 of rows r0 .. r0+3: bit i of cw; nodes 0..31: b[i]
+                const unsigned cw = __ballot_sync(0xffffffffu, lane < 4 && r0 + lane < ENY && nvx >= ENX && P[lane * EPITCH + EX] < iso);
+                unsigned b[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) b[i] = (i < 3 || role < 2) ? __ballot_sync(0xffffffffu, P[i * EPITCH + lane] < iso) : 0u;
+                unsigned mx[3], my[3], mz[3], y32 = 0, z32 = 0, tot = 0;
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    const int r = r0 + i;
+                    const unsigned c = (cw >> i) & 1u;
+                    mx[i] = my[i] = mz[i] = 0;
+                    if (r < nvy) {
+                        mx[i] = (b[i] ^ ((b[i] >> 1) | (c << 31))) & xEdgeValid;
+                        if (r < EY && r + 1 < nvy) my[i] = (b[i] ^ b[i + 1]) & nodeValidX, y32 |= (c ^ ((cw >> (i + 1)) & 1u)) << i;
+                        if (actJ) { // z-edges of layer j: plane j below
+                            const uint2 bp = belowP[i];
+                            mz[i] = (b[i] ^ bp.x) & nodeValidX, z32 |= (c ^ bp.y) << i;
+                        }
+                    }
+                    if (lane == 0) belowJ[i] = make_uint2(b[i], c);
+                    tot += __popc(mx[i]) + __popc(my[i]) + __popc(mz[i]);
+                }
+                tot += __popc(y32) + __popc(z32);
+                if (tot) {
+                    unsigned pos = 0;
+                    if (lane == 0) pos = static_cast<unsigned>(atomicAdd(&sh.ncross[n3P], static_cast<int>(tot)));
+                    pos = __shfl_sync(0xffffffffu, pos, 0);
+                    const unsigned me = (r0 << 6) | lane;
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) {
+                        if ((mx[i] >> lane) & 1u) list[pos + __popc(mx[i] & ltMask)] = static_cast<unsigned short>(me + (i << 6));
+                        pos += __popc(mx[i]);
+                        if ((my[i] >> lane) & 1u) list[pos + __popc(my[i] & ltMask)] = static_cast<unsigned short>(me + ((i << 6) | (1 << 10)));
+                        pos += __popc(my[i]);
+                        if ((mz[i] >> lane) & 1u) list[pos + __popc(mz[i] & ltMask)] = static_cast<unsigned short>(me + ((i << 6) | (2 << 10)));
+                        pos += __popc(mz[i]);
+                    }
+                    // node column 32: lane i < 3 takes the y-edge, lane 4+i the z-edge of row r0+i
+                    const unsigned m32 = y32 | (z32 << 4);
+                    if ((m32 >> lane) & 1u)
+                        list[pos + __popc(m32 & ltMask)] = static_cast<unsigned short>(((r0 + (lane & 3)) << 6) | EX | (lane < 4 ? 1 << 10 : 2 << 10));
+                }
+            }
+        } else {
+            // ---- V(j): one vertex per crossed edge of node plane j (x, y) and of cell layer j-1 (z); five warps, 160 entries a round ---
+            const int ncross = sh.ncross[n3J];
+            const int cBeg = ((role - 3) << 5) + lane;
+            if (cBeg - lane < ncross) {
+                const unsigned short* list = sh.list[j & 1];
+                const int zg = zcBeg + j; // global index of node plane j
+                // no node of this iteration touches the global border -> plain central differences, no per-round check
+                const bool allInterior = xyInterior && zg - 1 > 0 && zg < m.szGlobal - 1;
+                const int recPlane = n3J * E_PLREC, recLayer = E_ZREC0 + ((j + 1) & 1) * E_ZEDGES;
+                const float pzA = __fadd_rn(__fmul_rn((float)(zg - 1), m.sd[2]), m.org[2]), pzB = __fadd_rn(__fmul_rn((float)zg, m.sd[2]), m.org[2]);
+#pragma unroll 1
+                for (int c = cBeg; c < ncross; c += 5 * 32) {
+                    const unsigned ent = list[c];
+                    const int axis = ent >> 10, r = (ent >> 6) & 15, ix = ent & 63;
+                    const int offA = r * EPITCH + ix + (EPITCH + EHX0);
+                    const int offB = offA + (axis == 0 ? 1 : (axis == 1 ? EPITCH : 0));
+                    // node A is the edge's low node: in plane j-1 for a z-edge, else in plane j; node B is always in plane j
+                    const float* A0 = sh.ring + (axis == 2 ? oM1 : o0) + offA;
+                    const float* AM = sh.ring + (axis == 2 ? oM2 : oM1) + offA;
+                    const float* AP = sh.ring + (axis == 2 ? o0 : oP1) + offA;
+                    const float* B0 = sh.ring + o0 + offB;
+                    const float* BM = sh.ring + oM1 + offB;
+                    const float* BP = sh.ring + oP1 + offB;
+                    const int gxi = x0 + ix, gyi = y0 + r, gzi = zg - (axis == 2); // node A; node B = A + unit vector of the axis
+                    bool slow = false;
+                    if (!allInterior) {
+                        const bool border = min(min(gxi, gyi), gzi) <= 0 || gxi + (axis == 0) >= m.sx - 1 || gyi + (axis == 1) >= m.sy - 1 || zg >= m.szGlobal - 1;
+                        slow = __any_sync(__activemask(), border);
+                    }
+                    float gax, gay, gaz, gbx, gby, gbz;
+                    if (!slow) { // gradient at a node: (f(+) - f(-)) * 1/(2 sd)
+                        gax = __fmul_rn(__fsub_rn(A0[1], A0[-1]), r2x), gay = __fmul_rn(__fsub_rn(A0[EPITCH], A0[-EPITCH]), r2y);
+                        gaz = __fmul_rn(__fsub_rn(AP[0], AM[0]), r2z);
+                        gbx = __fmul_rn(__fsub_rn(B0[1], B0[-1]), r2x), gby = __fmul_rn(__fsub_rn(B0[EPITCH], B0[-EPITCH]), r2y);
+                        gbz = __fmul_rn(__fsub_rn(BP[0], BM[0]), r2z);
+                    } else { // samples clamped at the GLOBAL grid border: one-sided differences there
+                        auto grad = [&](const float* P0, const float* Pm, const float* Pp, int gx_, int gy_, int gz_, float& gx, float& gy, float& gz) {
+                            const int xm = gx_ > 0 ? 1 : 0, xp = gx_ < m.sx - 1 ? 1 : 0;
+                            const int ym = gy_ > 0 ? 1 : 0, yp = gy_ < m.sy - 1 ? 1 : 0;
+                            const int zm = gz_ > 0 ? 1 : 0, zp = gz_ < m.szGlobal - 1 ? 1 : 0;
+                            gx = xp + xm ? __fmul_rn(__fsub_rn(P0[xp], P0[-xm]), xp + xm == 2 ? r2x : r1x) : 0.0f;
+                            gy = yp + ym ? __fmul_rn(__fsub_rn(P0[yp * EPITCH], P0[-ym * EPITCH]), yp + ym == 2 ? r2y : r1y) : 0.0f;
+                            gz = zp + zm ? __fmul_rn(__fsub_rn(zp ? Pp[0] : P0[0], zm ? Pm[0] : P0[0]), zp + zm == 2 ? r2z : r1z) : 0.0f;
+                        };
+                        grad(A0, AM, AP, gxi, gyi, gzi, gax, gay, gaz);
+                        grad(B0, BM, BP, gxi + (axis == 0), gyi + (axis == 1), zg, gbx, gby, gbz);
+                    }
+                    const float fa = A0[0], fb = B0[0];
+                    // t = (iso - fa) / (fb - fa): SFU reciprocal (2 ulp; vertices are compared at 1e-4 of a cell); the IEEE division only
+                    // where the difference is too small for rcp.approx
+                    const float tnum = __fsub_rn(iso, fa), tden = __fsub_rn(fb, fa);
+                    const float t01 = fabsf(tden) > 1e-30f ? __fmul_rn(tnum, rcpApproxF(tden)) : __fdiv_rn(tnum, tden);
+                    const int ti = axis == 0 ? ix : E_TAB_Y + r;
+                    float pa = sh.tab[ti], pb = sh.tab[ti + 1];
+                    if (axis == 2) pa = pzA, pb = pzB;
+                    const float gx = __fadd_rn(gax, __fmul_rn(t01, __fsub_rn(gbx, gax)));
+                    const float gy = __fadd_rn(gay, __fmul_rn(t01, __fsub_rn(gby, gay)));
+                    const float gz = __fadd_rn(gaz, __fmul_rn(t01, __fsub_rn(gbz, gaz)));
+                    const float len2 = __fadd_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)), __fmul_rn(gz, gz));
+                    const float inv = len2 > 0.0f ? -rsqrtf(len2) : 0.0f; // SFU rsqrt: 2 ulp, normals are compared at 1e-4
+                    const int slot = r * ENX + ix + (axis == 0 ? recPlane : (axis == 1 ? recPlane + E_YOFF : recLayer));
+                    sh.rec[slot] = make_float4(__fadd_rn(pa, __fmul_rn(t01, __fsub_rn(pb, pa))), __fmul_rn(gx, inv), __fmul_rn(gy, inv), __fmul_rn(gz, inv));
+                    if (COLOUR) { // node colour = rgb / rho (0 where rho == 0), interpolated with the same t
+                        auto nodeColour = [&](int nx_, int ny_, int gz_, float f, float& cr, float& cg, float& cb) {
+                            const int x = min(nx_, m.sx - 1), y = min(ny_, m.sy - 1);
+                            const int zl = min(max(gz_ - m.zPlane0, 0), m.nzPlanes - 1);
+                            const float* cc = rgb + 3 * (x + static_cast<size_t>(m.sx) * (y + static_cast<size_t>(m.sy) * zl));
+                            if (f > 0.0f) cr = __fdiv_rn(cc[0], f), cg = __fdiv_rn(cc[1], f), cb = __fdiv_rn(cc[2], f);
+                            else cr = cg = cb = 0.0f;
+                        };
+                        float ar, ag, ab, br, bg, bb;
+                        nodeColour(gxi, gyi, gzi, fa, ar, ag, ab);
+                        nodeColour(gxi + (axis == 0), gyi + (axis == 1), zg, fb, br, bg, bb);
+                        recCol[slot] = make_float4(__fadd_rn(ar, __fmul_rn(t01, __fsub_rn(br, ar))), __fadd_rn(ag, __fmul_rn(t01, __fsub_rn(bg, ag))),
+                            __fadd_rn(ab, __fmul_rn(t01, __fsub_rn(bb, ab))), 0.0f);
+                    }
+                }
+            }
+        }
+
+        // ---- C(j-2): triangles of cell layer k = j-2, one warp per 32-cell row --------------------------------------------------------
+        if (actC) {
+            const int k = j - 2;
+            const int row = k * EY + warp;
+            const unsigned segTris = sh.segCnt[row];
+            if (segTris != 0) {
+                const unsigned segOff = sh.segOff[row];
+                // cube index in permuted order from the (x, x+1) bit pairs of the four node rows
+                const uint2 m00 = sh.below[k & 3][warp], m10 = sh.below[k & 3][warp + 1];
+                const uint2 m01 = sh.below[(k + 1) & 3][warp], m11 = sh.below[(k + 1) & 3][warp + 1];
+                const unsigned p00 = __funnelshift_r(m00.x, m00.y, lane) & 3u, p10 = __funnelshift_r(m10.x, m10.y, lane) & 3u;
+                const unsigned p01 = __funnelshift_r(m01.x, m01.y, lane) & 3u, p11 = __funnelshift_r(m11.x, m11.y, lane) & 3u;
+                unsigned long long word = 0;
+                if ((cellValidX >> lane) & 1u) word = __ldg(&kCasePerm.w[p00 | p10 << 2 | p01 << 4 | p11 << 6]);
+                const unsigned n = static_cast<unsigned>(word) & 15u;
+                unsigned inc = n;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const unsigned t = __shfl_up_sync(0xffffffffu, inc, d);
+                    if (lane >= d) inc += t;
+                }
+                const unsigned first = inc - n; // my first triangle within the row
+#pragma unroll
+                for (unsigned q = 0; q < 5; ++q) // a cell has at most five triangles: five predicated stores instead of a counted loop
+                    if (q < n) owner[first + q] = static_cast<unsigned char>(lane << 3 | q);
+                // this layer's edge table: records of node planes k = j-2 (buffer (j+1) mod 3), k+1 (buffer (j-1) mod 3) and of cell layer k
+                if (lane < 12) sh.etab[warp][lane] = etStatic + (etZ ? E_ZREC0 + (j & 1) * E_ZEDGES : (etUp ? n3M : n3P) * E_PLREC);
+                __syncwarp();
+                const unsigned wlo = static_cast<unsigned>(word >> 4), whi = static_cast<unsigned>(word >> 36); // 15 nibbles of edge ids
+                const unsigned ncorn = segTris * 3;
+                const size_t gbase = static_cast<size_t>(segOff) * 9;
+                float* op = outPos + gbase + lane * 3; // this lane's corner of the current round; 32 corners = 96 floats per round
+                float* on = outNrm + gbase + lane * 3;
+                float* oc = COLOUR ? outCol + gbase + lane * 3 : nullptr;
+                const float tz0 = __fadd_rn(__fmul_rn((float)(zcBeg + k), m.sd[2]), m.org[2]);
+                const float tz1 = __fadd_rn(__fmul_rn((float)(zcBeg + k + 1), m.sd[2]), m.org[2]);
+                const unsigned* etab = sh.etab[warp];
+#pragma unroll 2 // two independent gather chains in flight
+                for (unsigned jc = lane; jc < ncorn + lane; jc += 32, op += 96, on += 96) { // trip count uniform over the warp (shuffles inside)
+                    const bool actc = jc < ncorn;
+                    const unsigned t = actc ? jc / 3 : 0;
+                    const unsigned ok = owner[t];
+                    const unsigned L = ok >> 3;
+                    const unsigned oLo = __shfl_sync(0xffffffffu, wlo, L), oHi = __shfl_sync(0xffffffffu, whi, L);
+                    if (!actc) continue;
+                    const unsigned slotc = 3 * (ok & 7u) + (jc - 3 * t); // corner number inside the owner cell (0..14)
+                    const unsigned e = ((slotc < 8 ? oLo : oHi) >> ((4 * slotc) & 31u)) & 15u;
+                    const unsigned ent = etab[e];
+                    const unsigned eidx = (ent & 0xfffu) + L;
+                    const float4 v = sh.rec[eidx];
+                    float px = sh.tab[L + ((ent >> 15) & 1u)]; // ET_DX
+                    float py = (ent & ET_DY) ? ty1 : ty0;
+                    float pz = (ent & ET_DZ) ? tz1 : tz0;
+                    if (ent & ET_AX0) px = v.x;
+                    if (ent & ET_AX1) py = v.x;
+                    if (ent & ET_AX2) pz = v.x;
+                    op[0] = px, op[1] = py, op[2] = pz;
+                    on[0] = v.y, on[1] = v.z, on[2] = v.w;
+                    if (COLOUR) {
+                        const float4 cc = recCol[eidx];
+                        float* o = oc + (jc - lane) * 3;
+                        o[0] = cc.x, o[1] = cc.y, o[2] = cc.z;
+                    }
+                }
+            }
+        }
+        if (!TMA) asm volatile("cp.async.wait_group 0;");
+        __syncthreads();
+        // rotate: j -> j+1
+        oM2 = oM1, oM1 = o0, o0 = oP1, oP1 = oP2, oP2 = oP2 == (ERING - 1) * EPLANE ? 0 : oP2 + EPLANE;
+        const int t3 = n3M;
+        n3M = n3J, n3J = n3P, n3P = t3;
+        role = (role + 7) & 7;
+        actWin >>= 1;
+    }
+    if (TMA && pending) mbarWait(&sh.mbar[qWait & 1u], (qWait >> 1) & 1u); // never leave a bulk copy in flight into a dying block's shared memory
 }
 
 } // namespace mms

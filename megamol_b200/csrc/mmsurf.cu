@@ -17,6 +17,7 @@
 #include "bin.cuh"
 #include "density.cuh"
 #include "mc.cuh"
+#include "mc_emit_v4.cuh" // TEMPORARY: A/B check of the new emit kernel (MMS_EMIT_V4=1)
 #include "mt.cuh"
 #include "route.cuh"
 
@@ -309,7 +310,8 @@ __global__ void __launch_bounds__(256) normalize_state_kernel(float* __restrict_
 }
 
 
-size_t emitSmemBytes(bool colour) { return sizeof(McEmitShared) + 128 + (colour ? E_EDGES * sizeof(float4) : 0); }
+size_t emitSmemBytes(bool colour) { return sizeof(McEmitShared) + 128 + (colour ? E_RECS * sizeof(float4) : 0); }
+size_t emitV4SmemBytes(bool colour) { return sizeof(v4::McEmitV4Shared) + 128 + (colour ? v4::E_EDGES * sizeof(float4) : 0); }
 
 /** 3-D TMA descriptor over the slab volume (x fastest), box = one 40 x 11 plane tile of mc_emit_kernel.  Returns false where TMA's
  *  rules do not hold (row pitch not a multiple of 16 bytes) or the driver entry point is missing: the kernel's cp.async variant runs. */
@@ -390,6 +392,10 @@ int mms_create(mms_ctx** out, const mms_config* cfg) {
     cudaFuncSetAttribute(mc_emit_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)emitSmemBytes(false));
     cudaFuncSetAttribute(mc_emit_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)emitSmemBytes(true));
     cudaFuncSetAttribute(mc_emit_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)emitSmemBytes(true));
+    cudaFuncSetAttribute(v4::mc_emit_v4_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)emitV4SmemBytes(false));
+    cudaFuncSetAttribute(v4::mc_emit_v4_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)emitV4SmemBytes(false));
+    cudaFuncSetAttribute(v4::mc_emit_v4_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)emitV4SmemBytes(true));
+    cudaFuncSetAttribute(v4::mc_emit_v4_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)emitV4SmemBytes(true));
     if (!c->dstate.ensure(sizeof(DevState)) || !c->hState.ensure(sizeof(DevState))) {
         g_createError = "allocation of the state block failed";
         delete c;
@@ -1051,7 +1057,7 @@ int mms_emit_isosurface(mms_ctx* c, float* pos, float* nrm, float* col, uint64_t
             P += first_triangle * 9, N += first_triangle * 9;
             if (C) C += first_triangle * 9;
         }
-        dim3 gridE(m.nsegx, (m.cy + EY - 1) / EY, (m.cnz + EM_STEPS * EZ - 1) / (EM_STEPS * EZ));
+        dim3 gridE(m.nsegx, (m.cy + EY - 1) / EY, (m.cnz + EM_LAYERS - 1) / EM_LAYERS);
         c->rec(EV_EMIT0);
         if (c->countMode == MMS_ISO_MARCHING_TETS) {
             dim3 grid(m.nsegx, (m.cy + MT_THREADS / 32 - 1) / (MT_THREADS / 32), m.cnz);
@@ -1067,7 +1073,16 @@ int mms_emit_isosurface(mms_ctx* c, float* pos, float* nrm, float* col, uint64_t
         const bool tma = makeVolumeTensorMap(&map, c->vol.as<float>(), m.sx, m.sy, m.nzPlanes);
         const float* V = c->vol.as<float>();
         const unsigned* S = c->segOffset.as<unsigned>();
-        if (c->haveColour) {
+        if (getenv("MMS_EMIT_V4")) {
+            dim3 g4(m.nsegx, (m.cy + v4::EY - 1) / v4::EY, (m.cnz + v4::EM_STEPS * v4::EZ - 1) / (v4::EM_STEPS * v4::EZ));
+            if (c->haveColour) {
+                if (tma) v4::mc_emit_v4_kernel<true, true><<<g4, MC_THREADS, emitV4SmemBytes(true), st>>>(m, map, V, c->rgb.as<float>(), S, P, N, C);
+                else v4::mc_emit_v4_kernel<true, false><<<g4, MC_THREADS, emitV4SmemBytes(true), st>>>(m, map, V, c->rgb.as<float>(), S, P, N, C);
+            } else {
+                if (tma) v4::mc_emit_v4_kernel<false, true><<<g4, MC_THREADS, emitV4SmemBytes(false), st>>>(m, map, V, nullptr, S, P, N, nullptr);
+                else v4::mc_emit_v4_kernel<false, false><<<g4, MC_THREADS, emitV4SmemBytes(false), st>>>(m, map, V, nullptr, S, P, N, nullptr);
+            }
+        } else if (c->haveColour) {
             if (tma) mc_emit_kernel<true, true><<<gridE, MC_THREADS, emitSmemBytes(true), st>>>(m, map, V, c->rgb.as<float>(), S, P, N, C);
             else mc_emit_kernel<true, false><<<gridE, MC_THREADS, emitSmemBytes(true), st>>>(m, map, V, c->rgb.as<float>(), S, P, N, C);
         } else {

@@ -50,7 +50,7 @@ def test_variants_bit_identical(case):
     xyz = synth.uniform_box(n, 1.0) * np.asarray(box, np.float32)
     base = _run(xyz, box, res, cyclic, radius, 0.4, {})
     assert base[1].shape[0] > 1000
-    for env in ({"MMS_SPLAT_V1": "1"}, {"MMS_NO_TMA": "1"}):
+    for env in ({"MMS_SPLAT_V1": "1"}, {"MMS_NO_TMA": "1"}, {"MMS_EMIT_V4": "1"}):
         other = _run(xyz, box, res, cyclic, radius, 0.4, env)
         assert np.array_equal(base[0].view(np.uint32), other[0].view(np.uint32)), f"density differs with {env}"
         assert base[1].shape == other[1].shape and np.array_equal(base[1], other[1]) and np.array_equal(base[2], other[2]), f"mesh differs with {env}"
