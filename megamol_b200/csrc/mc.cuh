@@ -178,7 +178,7 @@ struct __align__(128) McEmitShared {
     float ring[ERING * EPLANE];                 // node plane p (relative to the block's first cell layer) sits in slot (p + 1) mod ERING
     float4 rec[E_RECS];                         // {interpolated coordinate along the edge's axis, nx, ny, nz}
     unsigned short list[2][E_LIST];             // crossing list of plane j in list[j & 1]
-    unsigned char triOwner[MC_THREADS / 32][E_MAXROWTRIS]; // (owner lane << 3) | triangle number inside the owner cell
+    unsigned short triOwner[MC_THREADS / 32][E_MAXROWTRIS]; // per triangle of a row: (owner lane & 15) << 12 | its three cube edges (nibbles)
     unsigned segOff[E_ROWS];                    // first triangle of every cell row of the block
     unsigned char segCnt[E_ROWS];               // its triangle count (<= 160)
     unsigned etab[MC_THREADS / 32][12];         // per warp (= cell row) and cube edge: record slot of cell 0 | flags
@@ -206,6 +206,11 @@ constexpr unsigned ET_AX0 = 1u << 12, ET_AX1 = 1u << 13, ET_AX2 = 1u << 14, ET_D
 __device__ __forceinline__ float rcpApproxF(float x) {
     float y;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rsqrtApproxF(float x) { // = rsqrtf(x) for normal x (gradients below 1e-19 do not occur), without its denormal branch
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
 __device__ __forceinline__ unsigned smemAddr(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
@@ -325,7 +330,7 @@ __global__ void __launch_bounds__(MC_THREADS, COLOUR ? 2 : 4) mc_emit_kernel(McG
     const unsigned cellValidX = m.cx - x0 >= 32 ? 0xffffffffu : (1u << (m.cx - x0)) - 1u;
     const unsigned ltMask = (1u << lane) - 1u;
     const bool xyInterior = x0 > 0 && x0 + EX < m.sx - 1 && y0 > 0 && y0 + EY < m.sy - 1; // no node of the column touches the x/y border
-    unsigned char* owner = sh.triOwner[warp];
+    unsigned short* owner = sh.triOwner[warp];
     // this warp's cell row is always row `warp` of the layer: static part of its edge table (lanes 0..11)
     unsigned etStatic = 0;
     bool etZ = false, etUp = false;
@@ -344,6 +349,8 @@ __global__ void __launch_bounds__(MC_THREADS, COLOUR ? 2 : 4) mc_emit_kernel(McG
     int n3M = (kFirst + 1) % 3, n3J = (kFirst + 2) % 3, n3P = kFirst % 3;                       // (j-1) mod 3, j mod 3, (j+1) mod 3
     int role = (warp - kFirst + 1) & 7;                                                           // (warp - j) mod 8
     unsigned long long actWin = (static_cast<unsigned long long>(act) << 3) >> kFirst;            // bit i <=> layer j - 2 + i is active
+    auto planeZ = [&](int p) { return __fadd_rn(__fmul_rn((float)(zcBeg + p), m.sd[2]), m.org[2]); }; // node position (ParticlesToDensity.cpp:605)
+    float pzM2 = planeZ(kFirst - 3), pzM1 = planeZ(kFirst - 2), pz0 = planeZ(kFirst - 1);      // z of node planes j-2, j-1, j
     issuePlanes(kFirst - 1, kFirst, o0); // planes j, j+1
     bool pending = TMA; // a bulk load has been issued and not yet waited for
     if (!TMA) {
@@ -425,7 +432,6 @@ __global__ void __launch_bounds__(MC_THREADS, COLOUR ? 2 : 4) mc_emit_kernel(McG
                 // no node of this iteration touches the global border -> plain central differences, no per-round check
                 const bool allInterior = xyInterior && zg - 1 > 0 && zg < m.szGlobal - 1;
                 const int recPlane = n3J * E_PLREC, recLayer = E_ZREC0 + ((j + 1) & 1) * E_ZEDGES;
-                const float pzA = __fadd_rn(__fmul_rn((float)(zg - 1), m.sd[2]), m.org[2]), pzB = __fadd_rn(__fmul_rn((float)zg, m.sd[2]), m.org[2]);
 #pragma unroll 1
                 for (int c = cBeg; c < ncross; c += 5 * 32) {
                     const unsigned ent = list[c];
@@ -433,12 +439,13 @@ __global__ void __launch_bounds__(MC_THREADS, COLOUR ? 2 : 4) mc_emit_kernel(McG
                     const int offA = r * EPITCH + ix + (EPITCH + EHX0);
                     const int offB = offA + (axis == 0 ? 1 : (axis == 1 ? EPITCH : 0));
                     // node A is the edge's low node: in plane j-1 for a z-edge, else in plane j; node B is always in plane j
-                    const float* A0 = sh.ring + (axis == 2 ? oM1 : o0) + offA;
-                    const float* AM = sh.ring + (axis == 2 ? oM2 : oM1) + offA;
-                    const float* AP = sh.ring + (axis == 2 ? o0 : oP1) + offA;
-                    const float* B0 = sh.ring + o0 + offB;
-                    const float* BM = sh.ring + oM1 + offB;
-                    const float* BP = sh.ring + oP1 + offB;
+                    const float* ring = sh.ring;
+                    const float* A0 = ring + ((axis == 2 ? oM1 : o0) + offA);
+                    const float* AM = ring + ((axis == 2 ? oM2 : oM1) + offA);
+                    const float* AP = ring + ((axis == 2 ? o0 : oP1) + offA);
+                    const float* B0 = ring + (o0 + offB);
+                    const float* BM = ring + (oM1 + offB);
+                    const float* BP = ring + (oP1 + offB);
                     const int gxi = x0 + ix, gyi = y0 + r, gzi = zg - (axis == 2); // node A; node B = A + unit vector of the axis
                     bool slow = false;
                     if (!allInterior) {
@@ -470,12 +477,12 @@ __global__ void __launch_bounds__(MC_THREADS, COLOUR ? 2 : 4) mc_emit_kernel(McG
                     const float t01 = fabsf(tden) > 1e-30f ? __fmul_rn(tnum, rcpApproxF(tden)) : __fdiv_rn(tnum, tden);
                     const int ti = axis == 0 ? ix : E_TAB_Y + r;
                     float pa = sh.tab[ti], pb = sh.tab[ti + 1];
-                    if (axis == 2) pa = pzA, pb = pzB;
+                    if (axis == 2) pa = pzM1, pb = pz0;
                     const float gx = __fadd_rn(gax, __fmul_rn(t01, __fsub_rn(gbx, gax)));
                     const float gy = __fadd_rn(gay, __fmul_rn(t01, __fsub_rn(gby, gay)));
                     const float gz = __fadd_rn(gaz, __fmul_rn(t01, __fsub_rn(gbz, gaz)));
                     const float len2 = __fadd_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)), __fmul_rn(gz, gz));
-                    const float inv = len2 > 0.0f ? -rsqrtf(len2) : 0.0f; // SFU rsqrt: 2 ulp, normals are compared at 1e-4
+                    const float inv = len2 > 0.0f ? -rsqrtApproxF(len2) : 0.0f; // SFU rsqrt: 2 ulp, normals are compared at 1e-4
                     const int slot = r * ENX + ix + (axis == 0 ? recPlane : (axis == 1 ? recPlane + E_YOFF : recLayer));
                     sh.rec[slot] = make_float4(__fadd_rn(pa, __fmul_rn(t01, __fsub_rn(pb, pa))), __fmul_rn(gx, inv), __fmul_rn(gy, inv), __fmul_rn(gz, inv));
                     if (COLOUR) { // node colour = rgb / rho (0 where rho == 0), interpolated with the same t
@@ -520,29 +527,24 @@ __global__ void __launch_bounds__(MC_THREADS, COLOUR ? 2 : 4) mc_emit_kernel(McG
                 const unsigned first = inc - n; // my first triangle within the row
 #pragma unroll
                 for (unsigned q = 0; q < 5; ++q) // a cell has at most five triangles: five predicated stores instead of a counted loop
-                    if (q < n) owner[first + q] = static_cast<unsigned char>(lane << 3 | q);
+                    if (q < n) owner[first + q] = static_cast<unsigned short>(lane << 12 | (static_cast<unsigned>(word >> (4 + 12 * q)) & 0xfffu));
+                const unsigned tHalf = __shfl_sync(0xffffffffu, first, 16); // triangles from here on belong to lanes 16..31 (the table keeps 4 lane bits)
                 // this layer's edge table: records of node planes k = j-2 (buffer (j+1) mod 3), k+1 (buffer (j-1) mod 3) and of cell layer k
                 if (lane < 12) sh.etab[warp][lane] = etStatic + (etZ ? E_ZREC0 + (j & 1) * E_ZEDGES : (etUp ? n3M : n3P) * E_PLREC);
                 __syncwarp();
-                const unsigned wlo = static_cast<unsigned>(word >> 4), whi = static_cast<unsigned>(word >> 36); // 15 nibbles of edge ids
                 const unsigned ncorn = segTris * 3;
                 const size_t gbase = static_cast<size_t>(segOff) * 9;
                 float* op = outPos + gbase + lane * 3; // this lane's corner of the current round; 32 corners = 96 floats per round
                 float* on = outNrm + gbase + lane * 3;
                 float* oc = COLOUR ? outCol + gbase + lane * 3 : nullptr;
-                const float tz0 = __fadd_rn(__fmul_rn((float)(zcBeg + k), m.sd[2]), m.org[2]);
-                const float tz1 = __fadd_rn(__fmul_rn((float)(zcBeg + k + 1), m.sd[2]), m.org[2]);
+                const float tz0 = pzM2, tz1 = pzM1;
                 const unsigned* etab = sh.etab[warp];
 #pragma unroll 2 // two independent gather chains in flight
-                for (unsigned jc = lane; jc < ncorn + lane; jc += 32, op += 96, on += 96) { // trip count uniform over the warp (shuffles inside)
-                    const bool actc = jc < ncorn;
-                    const unsigned t = actc ? jc / 3 : 0;
+                for (unsigned jc = lane; jc < ncorn; jc += 32, op += 96, on += 96) {
+                    const unsigned t = jc / 3;
                     const unsigned ok = owner[t];
-                    const unsigned L = ok >> 3;
-                    const unsigned oLo = __shfl_sync(0xffffffffu, wlo, L), oHi = __shfl_sync(0xffffffffu, whi, L);
-                    if (!actc) continue;
-                    const unsigned slotc = 3 * (ok & 7u) + (jc - 3 * t); // corner number inside the owner cell (0..14)
-                    const unsigned e = ((slotc < 8 ? oLo : oHi) >> ((4 * slotc) & 31u)) & 15u;
+                    const unsigned L = (ok >> 12) + (t >= tHalf ? 16u : 0u);
+                    const unsigned e = (ok >> (4 * (jc - 3 * t))) & 15u; // this corner's cube edge
                     const unsigned ent = etab[e];
                     const unsigned eidx = (ent & 0xfffu) + L;
                     const float4 v = sh.rec[eidx];
@@ -570,6 +572,7 @@ __global__ void __launch_bounds__(MC_THREADS, COLOUR ? 2 : 4) mc_emit_kernel(McG
         n3M = n3J, n3J = n3P, n3P = t3;
         role = (role + 7) & 7;
         actWin >>= 1;
+        pzM2 = pzM1, pzM1 = pz0, pz0 = planeZ(j + 1);
     }
     if (TMA && pending) mbarWait(&sh.mbar[qWait & 1u], (qWait >> 1) & 1u); // never leave a bulk copy in flight into a dying block's shared memory
 }

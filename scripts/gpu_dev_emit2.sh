@@ -2,7 +2,7 @@
 # dev: parity tests of the MC path, device-resident bench line, one ncu capture of the emit kernel
 TAG=${1:-r2x}
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_variants.py tests/test_gpu_parity.py tests/test_gpu_golden.py tests/test_gpu_slabs.py tests/test_gpu_quicksurf.py -m gpu -x -q 2>&1 | tail -5
+timeout 600 python -m pytest tests/test_gpu_variants.py tests/test_gpu_parity.py tests/test_gpu_golden.py tests/test_gpu_slabs.py tests/test_gpu_quicksurf.py -m gpu -x -q 2>&1 | tail -25
 timeout 120 python bench.py --steps 10 --warmup 3 --no-cpu --no-e2e > gpurun_out/bench_dev_$TAG.log 2>&1
 tail -1 gpurun_out/bench_dev_$TAG.log | python -c "
 import sys, json
