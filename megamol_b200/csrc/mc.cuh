@@ -158,7 +158,7 @@ constexpr int EPITCH = 40;                                  // x0-4 .. x0+35 (x0
 constexpr int EHX0 = 4;                                     // ring column of node 0
 constexpr int EPLANE = 448;                                 // floats per ring slot: 11*40 = 440, padded to 14*128 bytes
 constexpr int ERING = 6;                                    // plane slots: V(j) reads planes j-2 .. j+1 while plane j+2 is in flight
-constexpr int EM_LAYERS = 32;                               // cell layers per block
+constexpr int EM_LAYERS = 64;                               // cell layers per block
 // a crossed grid edge is named (axis, node row r, node ix): list entry = axis << 10 | r << 6 | ix; its record sits at r*33 + ix of
 //   x-edges  node-plane buffer            (r < 9, ix < 32)
 //   y-edges  node-plane buffer + E_YOFF   (r < 8, ix < 33)
@@ -170,7 +170,7 @@ constexpr int E_ZREC0 = 3 * E_PLREC;                        // records: three no
 constexpr int E_RECS = 3 * E_PLREC + 2 * E_ZEDGES;          // 2277
 constexpr int E_LIST = 864;                                 // >= 9*32 + 8*33 + 9*33 = 849 crossings per iteration
 constexpr int E_MAXROWTRIS = 160;
-constexpr int E_ROWS = EM_LAYERS * EY;                      // 256 cell rows per block
+constexpr int E_ROWS = EM_LAYERS * EY;                      // 512 cell rows per block
 constexpr int E_TAB_Y = ENX;                                // node position table: 33 x, 9 y
 constexpr unsigned E_PLANE_BYTES = EHY * EPITCH * 4;
 
@@ -184,7 +184,7 @@ struct __align__(128) McEmitShared {
     unsigned etab[MC_THREADS / 32][12];         // per warp (= cell row) and cube edge: record slot of cell 0 | flags
     uint2 below[4][ENY];                        // "below iso" bits of node plane j in below[j & 3]: .x nodes 0..31, .y node 32
     float tab[ENX + ENY + 2];                   // node positions float(idx)*sd + origin (ParticlesToDensity.cpp:605)
-    unsigned actWarp[MC_THREADS / 32];
+    unsigned actWarp[2][MC_THREADS / 32];
     int ncross[4];                              // length of the crossing list of plane j in ncross[j mod 3]
     unsigned long long mbar[2];                 // plane loads alternate between two mbarriers (see the loop)
 };
@@ -266,8 +266,10 @@ __global__ void __launch_bounds__(MC_THREADS, COLOUR ? 2 : 4) mc_emit_kernel(McG
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     // ---- the block's cell rows: first triangle, triangle count, which layers have any (one global read per row) ---------
-    {
-        const int ly = tid % EY, k = tid / EY; // E_ROWS == MC_THREADS
+    static_assert(E_ROWS == 2 * MC_THREADS, "two cell rows per thread");
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int ly = tid % EY, k = tid / EY + h * (EM_LAYERS / 2);
         const int cyi = y0 + ly;
         unsigned off = 0, cnt = 0;
         if (cyi < m.cy && k < nLayers) {
@@ -275,22 +277,23 @@ __global__ void __launch_bounds__(MC_THREADS, COLOUR ? 2 : 4) mc_emit_kernel(McG
             off = segOffset[seg];
             cnt = segOffset[seg + 1] - off;
         }
-        sh.segOff[tid] = off;
-        sh.segCnt[tid] = static_cast<unsigned char>(cnt);
-        const unsigned bal = __ballot_sync(0xffffffffu, cnt != 0); // rows 8i .. 8i+7 of this warp belong to layer 4*warp + i
+        sh.segOff[tid + h * MC_THREADS] = off;
+        sh.segCnt[tid + h * MC_THREADS] = static_cast<unsigned char>(cnt);
+        const unsigned bal = __ballot_sync(0xffffffffu, cnt != 0); // rows 8i .. 8i+7 of this warp belong to layer 32*h + 4*warp + i
         if (lane == 0)
-            sh.actWarp[warp] = ((bal & 0xffu) ? 1u : 0u) | ((bal & 0xff00u) ? 2u : 0u) | ((bal & 0xff0000u) ? 4u : 0u) | ((bal >> 24) ? 8u : 0u);
+            sh.actWarp[h][warp] = ((bal & 0xffu) ? 1u : 0u) | ((bal & 0xff00u) ? 2u : 0u) | ((bal & 0xff0000u) ? 4u : 0u) | ((bal >> 24) ? 8u : 0u);
     }
     if (tid < ENX) sh.tab[tid] = __fadd_rn(__fmul_rn((float)(x0 + tid), m.sd[0]), m.org[0]);
     else if (tid < ENX + ENY) sh.tab[tid] = __fadd_rn(__fmul_rn((float)(y0 + tid - ENX), m.sd[1]), m.org[1]);
     if (tid < 4) sh.ncross[tid] = 0;
     if (TMA && tid == 0) mbarInit(&sh.mbar[0], 1), mbarInit(&sh.mbar[1], 1);
     __syncthreads();
-    unsigned act = 0;
+    unsigned actLo = 0, actHi = 0;
 #pragma unroll
-    for (int w = 0; w < MC_THREADS / 32; ++w) act |= sh.actWarp[w] << (4 * w);
+    for (int w = 0; w < MC_THREADS / 32; ++w) actLo |= sh.actWarp[0][w] << (4 * w), actHi |= sh.actWarp[1][w] << (4 * w);
+    const unsigned long long act = static_cast<unsigned long long>(actHi) << 32 | actLo; // bit k <=> cell layer k of the block has triangles
     if (!act) return;
-    const int kFirst = __ffs(act) - 1, kLast = 31 - __clz(act);
+    const int kFirst = __ffsll(static_cast<long long>(act)) - 1, kLast = 63 - __clzll(static_cast<long long>(act));
 
     // ---- plane loader -------------------------------------------------------------------------------------------------
     // Load batch q signals mbar[q & 1] (phase parity (q >> 1) & 1).  Two barriers, because thread 0 arms the next batch right after its
@@ -348,7 +351,8 @@ __global__ void __launch_bounds__(MC_THREADS, COLOUR ? 2 : 4) mc_emit_kernel(McG
     int oP1 = ((kFirst + 1) % ERING) * EPLANE, oP2 = ((kFirst + 2) % ERING) * EPLANE;                                  // j-2 .. j+2, j = kFirst-1
     int n3M = (kFirst + 1) % 3, n3J = (kFirst + 2) % 3, n3P = kFirst % 3;                       // (j-1) mod 3, j mod 3, (j+1) mod 3
     int role = (warp - kFirst + 1) & 7;                                                           // (warp - j) mod 8
-    unsigned long long actWin = (static_cast<unsigned long long>(act) << 3) >> kFirst;            // bit i <=> layer j - 2 + i is active
+    unsigned long long actRem = act >> kFirst;                                                    // bit 0 <=> layer j+1 is active
+    unsigned actHist = 1u;                                                                        // bits 0..3 <=> layers j+1, j, j-1, j-2 are active
     auto planeZ = [&](int p) { return __fadd_rn(__fmul_rn((float)(zcBeg + p), m.sd[2]), m.org[2]); }; // node position (ParticlesToDensity.cpp:605)
     float pzM2 = planeZ(kFirst - 3), pzM1 = planeZ(kFirst - 2), pz0 = planeZ(kFirst - 1);      // z of node planes j-2, j-1, j
     issuePlanes(kFirst - 1, kFirst, o0); // planes j, j+1
@@ -367,8 +371,7 @@ __global__ void __launch_bounds__(MC_THREADS, COLOUR ? 2 : 4) mc_emit_kernel(McG
             issuePlanes(j + 2, j + 2, oP2);
             pending = TMA;
         }
-        const unsigned aw = static_cast<unsigned>(actWin);
-        const bool actC = aw & 1u, actJ = (aw >> 2) & 1u, actJ1 = (aw >> 3) & 1u; // layers j-2, j, j+1
+        const bool actC = (actHist >> 3) & 1u, actJ = (actHist >> 1) & 1u, actJ1 = actHist & 1u; // layers j-2, j, j+1
 
         if (role < 3) {
             // ---- MX(j+1): masks of node plane j+1, crossed edges -> crossing list; three warps, three node rows each -------------
@@ -571,7 +574,8 @@ __global__ void __launch_bounds__(MC_THREADS, COLOUR ? 2 : 4) mc_emit_kernel(McG
         const int t3 = n3M;
         n3M = n3J, n3J = n3P, n3P = t3;
         role = (role + 7) & 7;
-        actWin >>= 1;
+        actRem >>= 1;
+        actHist = ((actHist << 1) | (static_cast<unsigned>(actRem) & 1u)) & 15u;
         pzM2 = pzM1, pzM1 = pz0, pz0 = planeZ(j + 1);
     }
     if (TMA && pending) mbarWait(&sh.mbar[qWait & 1u], (qWait >> 1) & 1u); // never leave a bulk copy in flight into a dying block's shared memory
