@@ -514,6 +514,337 @@ __global__ void __launch_bounds__(CT_THREADS, 4) density_splat_kernel(Geo g, Dev
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// density_splat3_kernel: warp-owned sub-tiles (supports of at most 3x3x3 voxels: C1, C2, C4) -- no colour phases, no block barriers
+// ---------------------------------------------------------------------------------------------------------------
+// A warp OWNS a 32x8x4-voxel sub-tile (eight of them make the 32x16x16 block tile): nobody else ever touches its voxels, so there is
+// nothing to colour and nothing to wait for.  The warp streams, in ascending GLOBAL cell order (z, y, x) and canonical in-cell order,
+// the particles of every cell row that can reach the sub-tile -- the cells of a row are contiguous in the sorted record array, so a
+// row is one or two coalesced ranges --, rejects those whose support box misses the sub-tile with a few float compares (most of the
+// ring), and queues the survivors.  Every 32 queued particles are digested with full lanes: tight support box, 27-bit hit mask, the
+// hits of all 32 expanded into one (particle, voxel) list that the lanes walk (real hits only: sqrt, rcp, ex2).  Hits of one round
+// on the same voxel are applied in list order (match.any + rank).  Every voxel therefore receives its contributions in the order
+//        (cell z, cell y, cell x, canonical in-cell order)
+// which depends on nothing but the data: bit-identical run to run and for every tile / z-slab decomposition.
+constexpr int S3_X = 32, S3_Y = 8, S3_Z = 4;         // voxels owned by one warp
+constexpr int S3_SY = 35, S3_SZ = 297;               // padded strides (= 3 and 9 mod 32): a 3x3x3 pattern hits 27 different banks
+constexpr int S3_FLOATS = S3_SZ * S3_Z;              // 1188
+constexpr int S3_QCAP = 64;                          // survivor queue (ring)
+constexpr int S3_HITCAP = 512;                       // (particle, voxel) pairs expanded at a time (32 x 27 worst case: further passes)
+constexpr int S3_MAXCELLS = 12;                      // cells along one axis that can reach a sub-tile (32/4 + 2 ring cells + wrap slack)
+
+struct Splat3Warp {
+    float tile[S3_FLOATS];
+    float4 queue[S3_QCAP];
+    unsigned short hits[S3_HITCAP];                  // (lane of the particle << 5) | voxel number 0..26 inside its 3x3x3 box, in summation order
+};
+/** Cells along one axis whose particles can reach a voxel range, ascending global id; shift = what to add to the voxel coordinate
+ *  of a particle of that cell (the image next to the cell's own voxels) to get the periodic image that lies next to the range
+ *  (0, -s or +s); mid = centre of the cell's voxels. */
+struct Splat3Axis {
+    int n;
+    int cell[S3_MAXCELLS];
+    float shift[S3_MAXCELLS];
+    float mid[S3_MAXCELLS];
+};
+struct Splat3Shared {
+    Splat3Warp w[CT_WARPS];
+    float4 lut[27];                                  // voxel number -> (ix, iy, iz as floats, sub-tile offset as int bits)
+    Splat3Axis axis[7];                              // x of the block tile | y of the two sub-tile rows | z of the four sub-tile layers
+    int nruns;                                       // x cells in runs of consecutive ids with one shift: contiguous record ranges
+    int runA[4], runB[4];
+    float runShift[4], runMid[4];
+};
+static_assert(sizeof(Splat3Shared) <= 57088, "density_splat3_kernel must fit four blocks per SM");
+
+__global__ void __launch_bounds__(CT_THREADS, 4) density_splat3_kernel(Geo g, DevState* st, const float4* __restrict__ recs,
+    const unsigned* __restrict__ cellStart, float* __restrict__ vol, int reach) {
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    Splat3Shared& sh = *reinterpret_cast<Splat3Shared*>(smemRaw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < 27) {
+        const int ix = tid % 3, iy = (tid / 3) % 3, iz = tid / 9;
+        sh.lut[tid] = make_float4((float)ix, (float)iy, (float)iz, __int_as_float(ix + iy * S3_SY + iz * S3_SZ));
+    }
+    if (lane == 0 && warp < 7) { // one thread of seven warps each: the cell lists of the block's x range, its two y ranges and its four z ranges
+        const int q = warp;
+        const int a = q == 0 ? 0 : (q < 3 ? 1 : 2);
+        const int sub = q == 0 ? 0 : (q < 3 ? q - 1 : q - 3);
+        const int t0 = a == 0 ? (int)blockIdx.x * CT_X : (a == 1 ? (int)blockIdx.y * CT_Y + sub * S3_Y : g.z0 + (int)blockIdx.z * CT_Z + sub * S3_Z);
+        const int lim = a == 2 ? g.z0 + g.nz : g.s[a];
+        const int t1 = min(t0 + (a == 0 ? S3_X : (a == 1 ? S3_Y : S3_Z)), lim) - 1;
+        Splat3Axis& A = sh.axis[q];
+        int tmp[CT_MAXAXIS];
+        int n = t1 >= t0 ? buildAxisCells(t0, t1, reach, g.s[a], g.cyc[a] != 0, g.cshift, g.nc[a], tmp, S3_MAXCELLS) : 0;
+        for (int i = 1; i < n; ++i) { // ascending global cell id: the summation order must not depend on where the tile sits
+            const int c = tmp[i];
+            int k = i - 1;
+            for (; k >= 0 && tmp[k] > c; --k) tmp[k + 1] = tmp[k];
+            tmp[k + 1] = c;
+        }
+        A.n = n;
+        const int C = 1 << g.cshift, lo = t0 - reach, hi = t1 + reach;
+        for (int i = 0; i < n; ++i) {
+            const int v0 = tmp[i] * C, v1 = min(v0 + C, g.s[a]) - 1; // the cell's voxels
+            float shift = 0.0f;
+            if (g.cyc[a] && !(v1 >= lo && v0 <= hi)) shift = (v1 + g.s[a] >= lo && v0 + g.s[a] <= hi) ? (float)g.s[a] : -(float)g.s[a];
+            A.cell[i] = tmp[i], A.shift[i] = shift, A.mid[i] = 0.5f * (float)(v0 + v1);
+        }
+        if (q == 0) {
+            int nr = 0;
+            for (int i = 0; i < n;) {
+                const int ca = A.cell[i];
+                int cb = ca;
+                for (++i; i < n && A.cell[i] == cb + 1 && A.shift[i] == A.shift[i - 1]; ++i) ++cb;
+                if (nr < 4) sh.runA[nr] = ca, sh.runB[nr] = cb, sh.runShift[nr] = A.shift[i - 1], sh.runMid[nr] = 0.5f * (float)(ca * C + min((cb + 1) * C, g.s[0]) - 1);
+                ++nr;
+            }
+            sh.nruns = n < 0 ? -1 : (nr <= 4 ? nr : -1);
+        }
+    }
+    __syncthreads(); // the only block barrier: from here on the warps are independent
+    Splat3Warp& W = sh.w[warp];
+    const int t0x = (int)blockIdx.x * CT_X, t0y = (int)blockIdx.y * CT_Y + (warp & 1) * S3_Y, t0z = g.z0 + (int)blockIdx.z * CT_Z + (warp >> 1) * S3_Z;
+    const int t1x = min(t0x + S3_X, g.s[0]) - 1, t1y = min(t0y + S3_Y, g.s[1]) - 1, t1z = min(t0z + S3_Z, g.z0 + g.nz) - 1;
+    if (t1y < t0y || t1z < t0z) return;
+    const Splat3Axis& AY = sh.axis[1 + (warp & 1)];
+    const Splat3Axis& AZ = sh.axis[3 + (warp >> 1)];
+    const int nruns = sh.nruns;
+    if (nruns < 0 || AY.n < 0 || AZ.n < 0) {
+        if (lane == 0) st->pad[0] = 1u; // cannot happen when the host picked the cell size from the reach
+        return;
+    }
+    for (int i = lane; i < S3_FLOATS / 4; i += 32) reinterpret_cast<float4*>(W.tile)[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    __syncwarp();
+    const float isdx = __frcp_rn(g.sd[0]), isdy = __frcp_rn(g.sd[1]), isdz = __frcp_rn(g.sd[2]);
+    const unsigned ltMask = (1u << lane) - 1u;
+    unsigned qHead = 0, qTail = 0; // ring positions (uniform)
+
+    // tight support box of a particle along one axis, clipped to the sub-tile: first voxel (tile-local), extent, true (un-wrapped) index
+    auto axisBox = [&](float pos, float rad, float eps, float mn, float sd, float isd, int s, bool cyc, int tl0, int tl1, int& l0, int& bd, int& tru) {
+        // The slop only has to beat fp32 rounding of the bound itself: contributions within 0.48% of the support radius are exactly 0
+        // (exp(-x), x > 104).
+        const float aa = pos - mn;
+        const float vlo = (aa - eps) * isd, vhi = (aa + eps) * isd;
+        const float slop = fmaxf(fmaxf(fabsf(vlo), fabsf(vhi)), 1.0f) * 4e-6f;
+        int lo = __float2int_ru(vlo - slop), hi = __float2int_rd(vhi + slop);
+        if (g.sigma > 1.0f) { // the reference's box around the home voxel clips the kernel (:573-579)
+            const int H = homeVoxel(pos, mn, sd);
+            const int f = filterSize(rad, sd);
+            lo = max(lo, H - f), hi = min(hi, H + f);
+        }
+        hi = min(hi, lo + 2 * reach); // footprint bound the cell ring relies on (never binds for sane input)
+        int kk = 0, off = 0;          // true index = normalised index + off; kk: the image one period below
+        if (cyc) {
+            if (lo < 0 || lo >= s) {
+                const int mm = floorMod(lo, s);
+                off = lo - mm, hi -= off, lo = mm;
+            }
+            if (!(hi >= tl0 && lo <= tl1)) kk = -s;
+        }
+        const int l = max(lo + kk, tl0), h = min(hi + kk, tl1);
+        l0 = l - tl0, bd = h - l + 1, tru = l - kk + off;
+    };
+
+    // ---- a batch of queued particles: digest, hit masks, hit list, evaluation ----------------------------------------------------
+    auto processBatch = [&](int cnt) {
+        Dig dg{};
+        bool myLive = false;
+        if (lane < cnt) {
+            const float4 p = W.queue[(qHead + lane) & (S3_QCAP - 1)];
+            dg.x = p.x, dg.y = p.y, dg.z = p.z;
+            const float eps = __fmul_rn(g.sigma, p.w); // sigma * rad (:526)
+            dg.k0 = __fdiv_rn(1.0f, eps);               // (1.0f / epsilon) (:475)
+            dg.eps = eps;
+            int lx, ly, lz, bx, by, bz, tx, ty, tz;
+            axisBox(p.x, p.w, eps, g.mn[0], g.sd[0], isdx, g.s[0], g.cyc[0] != 0, t0x, t1x, lx, bx, tx);
+            axisBox(p.y, p.w, eps, g.mn[1], g.sd[1], isdy, g.s[1], g.cyc[1] != 0, t0y, t1y, ly, by, ty);
+            axisBox(p.z, p.w, eps, g.mn[2], g.sd[2], isdz, g.s[2], g.cyc[2] != 0, t0z, t1z, lz, bz, tz);
+            dg.f0x = (float)tx, dg.f0y = (float)ty, dg.f0z = (float)tz;
+            dg.base = lx + ly * S3_SY + lz * S3_SZ;
+            unsigned mk = 0u;
+            if (bx > 0 && by > 0 && bz > 0) {
+                if (bx <= 3 && by <= 3 && bz <= 3) {
+                    const unsigned mx = bx == 1 ? 0x1249249u : (bx == 2 ? 0x36DB6DBu : 0x7FFFFFFu);
+                    const unsigned my = by == 1 ? 0x01C0E07u : (by == 2 ? 0x0FC7E3Fu : 0x7FFFFFFu);
+                    const unsigned mz = bz == 1 ? 0x00001FFu : (bz == 2 ? 0x003FFFFu : 0x7FFFFFFu);
+                    mk = mx & my & mz;
+                } else {
+                    st->pad[0] = 4u; // the host promised boxes <= 3x3x3
+                }
+            }
+            dg.mask27 = mk;
+            myLive = mk != 0u;
+        }
+        // ---- A: hit mask of my particle ---------------------------------------------------------------------
+        unsigned hm = 0u;
+        if (myLive) {
+            const float lim = __fmul_rn(__fmul_rn(dg.eps, dg.eps), 1.000001f);
+            float qx[3], qy[3], qz[3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const float dx = __fsub_rn(__fadd_rn(__fmul_rn(dg.f0x + (float)i, g.sd[0]), g.mn[0]), dg.x);
+                const float dy = __fsub_rn(__fadd_rn(__fmul_rn(dg.f0y + (float)i, g.sd[1]), g.mn[1]), dg.y);
+                const float dz = __fsub_rn(__fadd_rn(__fmul_rn(dg.f0z + (float)i, g.sd[2]), g.mn[2]), dg.z);
+                qx[i] = __fmul_rn(dx, dx), qy[i] = __fmul_rn(dy, dy), qz[i] = __fmul_rn(dz, dz);
+            }
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    const float sxy = __fadd_rn(qx[i], qy[j]);
+#pragma unroll
+                    for (int k = 0; k < 3; ++k)
+                        if (__fadd_rn(sxy, qz[k]) < lim) hm |= 1u << (i + 3 * j + 9 * k);
+                }
+            hm &= dg.mask27;
+        }
+        const unsigned hcnt = __popc(hm);
+        const unsigned incl = warpInclusiveScan(hcnt), excl = incl - hcnt;
+        const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+        unsigned done = 0;
+        int first = 0;
+        while (done < total) {
+            // the particles [first, last] whose hits fit the list together (a particle has <= 27 of them)
+            const bool in = lane >= first && incl - done <= (unsigned)S3_HITCAP;
+            const unsigned bal = __ballot_sync(0xffffffffu, in);
+            const int last = 31 - __clz(bal);
+            const unsigned nh = __shfl_sync(0xffffffffu, incl, last) - done;
+            if (in) {
+                unsigned pos = excl - done;
+                for (unsigned mm = hm; mm; mm &= mm - 1) W.hits[pos++] = static_cast<unsigned short>(lane << 5 | (__ffs(mm) - 1));
+            }
+            __syncwarp();
+            // ---- B: lanes = hits ------------------------------------------------------------------------------
+            for (unsigned h0 = 0; h0 < nh; h0 += 32) {
+                const unsigned h = h0 + lane;
+                const bool act = h < nh;
+                const unsigned code = act ? W.hits[h] : 0u;
+                const int pl = code >> 5;
+                const float px = __shfl_sync(0xffffffffu, dg.x, pl), py = __shfl_sync(0xffffffffu, dg.y, pl), pz = __shfl_sync(0xffffffffu, dg.z, pl);
+                const float eps = __shfl_sync(0xffffffffu, dg.eps, pl), k0 = __shfl_sync(0xffffffffu, dg.k0, pl);
+                const float f0x = __shfl_sync(0xffffffffu, dg.f0x, pl), f0y = __shfl_sync(0xffffffffu, dg.f0y, pl), f0z = __shfl_sync(0xffffffffu, dg.f0z, pl);
+                const int sb = __shfl_sync(0xffffffffu, dg.base, pl);
+                const float4 L = sh.lut[code & 31u];
+                const float vx = __fadd_rn(__fmul_rn(f0x + L.x, g.sd[0]), g.mn[0]);
+                const float vy = __fadd_rn(__fmul_rn(f0y + L.y, g.sd[1]), g.mn[1]);
+                const float vz = __fadd_rn(__fmul_rn(f0z + L.z, g.sd[2]), g.mn[2]);
+                const float dx = __fsub_rn(vx, px), dy = __fsub_rn(vy, py), dz = __fsub_rn(vz, pz);
+                const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+                float w = 0.0f;
+                const bool hit = act && kernelValue<0>(d2, eps, k0, w);
+                const int addr = sb + __float_as_int(L.w);
+                // hits of this round on the same voxel: list order = canonical order
+                const unsigned grp = __match_any_sync(0xffffffffu, hit ? addr : -1 - lane);
+                const int rank = __popc(grp & ltMask);
+                const int maxRank = __reduce_max_sync(0xffffffffu, hit ? rank : 0);
+                for (int r = 0; r <= maxRank; ++r) {
+                    if (hit && rank == r) W.tile[addr] = __fadd_rn(W.tile[addr], w);
+                    __syncwarp();
+                }
+            }
+            done += nh;
+            first = last + 1;
+        }
+    };
+
+    // ---- stream the cell rows ----------------------------------------------------------------------------------------------------
+    // Conservative pre-test in voxel coordinates: the support box of a particle lies inside [u - e, u + e], u = (p - min)/sd; on a periodic
+    // axis u is first brought next to the voxels of the particle's own cell (row / run centre +- half a period: robust against a home
+    // voxel that the binning's exact division puts one cell further) and then moved to the image next to the sub-tile (the cell's
+    // shift); e = eps/sd + slack for the rounding of this test and the slop of the exact integer box (which follows in the digest).
+    const float ax = isdx, bx_ = -g.mn[0] * isdx, ay = isdy, by_ = -g.mn[1] * isdy, az = isdz, bz_ = -g.mn[2] * isdz;
+    const float fsx = (float)g.s[0], fsy = (float)g.s[1], fsz = (float)g.s[2];
+    const float rsx = __frcp_rn(fsx), rsy = __frcp_rn(fsy), rsz = __frcp_rn(fsz);
+    const float dlx = 0.05f + 1e-5f * fsx, dly = 0.05f + 1e-5f * fsy, dlz = 0.05f + 1e-5f * fsz;
+    const bool cycx = g.cyc[0] != 0, cycy = g.cyc[1] != 0, cycz = g.cyc[2] != 0;
+    const float sig = g.sigma;
+    const float lox = (float)t0x, hix = (float)t1x, loy = (float)t0y, hiy = (float)t1y, loz = (float)t0z, hiz = (float)t1z;
+    // Row descriptors: lane i owns (cell z, cell y, x run) number i of the sub-tile's neighbourhood, in summation order, and loads its
+    // record range -- one round of table reads for all rows instead of one dependent read per row.
+    const int nay = AY.n, naz = AZ.n;
+    const int nrows = naz * nay * nruns; // <= 4 * 4 * 4; in practice 12 .. 24
+    for (int row0 = 0; row0 < nrows; row0 += 32) {
+        unsigned myB = 0, myE = 0;
+        int myCode = 0; // kz | ky << 4 | kr << 8
+        if (row0 + lane < nrows) {
+            const int i = row0 + lane;
+            const int kr = i % nruns, t = i / nruns, ky = t % nay, kz = t / nay;
+            const size_t rowBase = (static_cast<size_t>(AZ.cell[kz]) * g.nc[1] + AY.cell[ky]) * g.nc[0];
+            myB = cellStart[rowBase + sh.runA[kr]], myE = cellStart[rowBase + sh.runB[kr] + 1];
+            myCode = kz | ky << 4 | kr << 8;
+        }
+        const unsigned nonEmpty = __ballot_sync(0xffffffffu, myE > myB);
+        // flattened walk over the chunks (32 records) of the non-empty rows; the records of the NEXT chunk are requested before the
+        // current one is tested, so that the load latency overlaps the work
+        unsigned rest = nonEmpty;
+        unsigned base = 0, end = 0;
+        int code = 0;
+        auto nextChunk = [&]() { // -> false when the rows are exhausted
+            base += 32;
+            if (base >= end) {
+                if (!rest) return false;
+                const int r = __ffs(rest) - 1;
+                rest &= rest - 1;
+                base = __shfl_sync(0xffffffffu, myB, r), end = __shfl_sync(0xffffffffu, myE, r), code = __shfl_sync(0xffffffffu, myCode, r);
+            }
+            return true;
+        };
+        bool more = nextChunk();
+        float4 pNext = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (more && base + lane < end) pNext = recs[base + lane];
+        while (more) {
+            const float4 p = pNext;
+            bool keep = base + lane < end;
+            const int kz = code & 15, ky = (code >> 4) & 15, kr = code >> 8;
+            more = nextChunk();
+            if (more && base + lane < end) pNext = recs[base + lane];
+            if (keep) {
+                const float eps = sig * p.w;
+                float ux = fmaf(p.x, ax, bx_), uy = fmaf(p.y, ay, by_), uz = fmaf(p.z, az, bz_);
+                if (cycx) ux = fmaf(-rintf((ux - sh.runMid[kr]) * rsx), fsx, ux) + sh.runShift[kr];
+                if (cycy) uy = fmaf(-rintf((uy - AY.mid[ky]) * rsy), fsy, uy) + AY.shift[ky];
+                if (cycz) uz = fmaf(-rintf((uz - AZ.mid[kz]) * rsz), fsz, uz) + AZ.shift[kz];
+                const float ex = fmaf(eps, ax, dlx), ey = fmaf(eps, ay, dly), ez = fmaf(eps, az, dlz);
+                keep = ux + ex >= lox && ux - ex <= hix && uy + ey >= loy && uy - ey <= hiy && uz + ez >= loz && uz - ez <= hiz;
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, keep);
+            if (keep) W.queue[(qTail + __popc(bal & ltMask)) & (S3_QCAP - 1)] = p;
+            qTail += __popc(bal);
+            __syncwarp();
+            if (qTail - qHead >= 32u) {
+                processBatch(32);
+                qHead += 32;
+            }
+        }
+    }
+    if (qTail != qHead) processBatch(static_cast<int>(qTail - qHead));
+    __syncwarp();
+
+    // write-out: 32 rows of 32 consecutive voxels (128 B), plus the sub-tile's min/max
+    float vmin = INFINITY, vmax = -INFINITY;
+    if (t0x + lane <= t1x) {
+        float* out = vol + (t0x + lane) + static_cast<size_t>(g.s[0]) * (t0y + static_cast<size_t>(g.s[1]) * (t0z - g.z0));
+        const size_t planeStride = static_cast<size_t>(g.s[0]) * g.s[1];
+        const int ny = t1y - t0y + 1, nz = t1z - t0z + 1;
+        for (int lz = 0; lz < nz; ++lz, out += planeStride) {
+            const float* src = W.tile + lane + lz * S3_SZ;
+            float* o = out;
+#pragma unroll 4
+            for (int ly = 0; ly < ny; ++ly, o += g.s[0], src += S3_SY) {
+                const float v = *src;
+                *o = v;
+                vmin = fminf(vmin, v), vmax = fmaxf(vmax, v);
+            }
+        }
+    }
+    const unsigned kmin = __reduce_min_sync(0xffffffffu, floatKey(vmin)), kmax = __reduce_max_sync(0xffffffffu, floatKey(vmax));
+    if (lane == 0 && kmin <= kmax) {
+        atomicMin(&st->minKey, kmin);
+        atomicMax(&st->maxKey, kmax);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Wide supports: voxel gather
 // ---------------------------------------------------------------------------------------------------------------
 // density_gather_kernel: QuickSurf-Gaussian mode (supports of ~10 voxels, optional density-weighted RGB volume) and

@@ -388,6 +388,7 @@ int mms_create(mms_ctx** out, const mms_config* cfg) {
     cudaFuncSetAttribute(density_splat_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SplatShared));
     cudaFuncSetAttribute(density_splat_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SplatShared));
     cudaFuncSetAttribute(density_splat_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SplatShared2));
+    cudaFuncSetAttribute(density_splat3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Splat3Shared));
     cudaFuncSetAttribute(mc_emit_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)emitSmemBytes(false));
     cudaFuncSetAttribute(mc_emit_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)emitSmemBytes(false));
     cudaFuncSetAttribute(mc_emit_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)emitSmemBytes(true));
@@ -742,9 +743,12 @@ int mms_compute_density(mms_ctx* c) {
         // V2 (lanes walk a compacted hit list) where every support box is at most 3x3x3 voxels and one periodic image per particle is enough
         bool v2 = g.mode == 0 && auxN == 0 && c->splatV2ok && !getenv("MMS_SPLAT_V1");
         const int tileDim[3] = {CT_X, CT_Y, CT_Z};
-        for (int a = 0; a < 3; ++a)
-            if (g.cyc[a] && g.s[a] < tileDim[a] + 2 * c->reach + 2) v2 = false;
-        if (v2)
+        for (int a = 0; a < 3; ++a) // a periodic axis so short that one cell holds particles of two images of the tile: the general kernel
+            if (g.cyc[a] && g.s[a] < tileDim[a] + 2 * c->reach + 2 + (1 << g.cshift)) v2 = false;
+        if (v2 && !getenv("MMS_SPLAT_V2"))
+            density_splat3_kernel<<<grid, CT_THREADS, sizeof(Splat3Shared), st>>>(g, c->dstate.as<DevState>(), c->recsB.as<float4>(),
+                c->cellStart.as<unsigned>(), c->vol.as<float>(), c->reach);
+        else if (v2)
             density_splat_kernel<0, true><<<grid, CT_THREADS, sizeof(SplatShared2), st>>>(g, c->dstate.as<DevState>(), c->recsB.as<float4>(),
                 c->auxB.as<float>(), auxN, c->cellStart.as<unsigned>(), c->vol.as<float>(), c->reach);
         else if (g.mode == 0)

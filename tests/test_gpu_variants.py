@@ -50,10 +50,16 @@ def test_variants_bit_identical(case):
     xyz = synth.uniform_box(n, 1.0) * np.asarray(box, np.float32)
     base = _run(xyz, box, res, cyclic, radius, 0.4, {})
     assert base[1].shape[0] > 1000
-    for env in ({"MMS_SPLAT_V1": "1"}, {"MMS_NO_TMA": "1"}, {"MMS_EMIT_V4": "1"}):
+    for env in ({"MMS_NO_TMA": "1"}, {"MMS_EMIT_V4": "1"}):  # the isosurface variants: same bits
         other = _run(xyz, box, res, cyclic, radius, 0.4, env)
         assert np.array_equal(base[0].view(np.uint32), other[0].view(np.uint32)), f"density differs with {env}"
         assert base[1].shape == other[1].shape and np.array_equal(base[1], other[1]) and np.array_equal(base[2], other[2]), f"mesh differs with {env}"
+    # the density kernels sum a voxel's contributions in different (each one fixed) orders: equal up to fp32 re-association
+    for env in ({"MMS_SPLAT_V1": "1"}, {"MMS_SPLAT_V2": "1"}):
+        other = _run(xyz, box, res, cyclic, radius, 0.4, env)
+        a, b = base[0].astype(np.float64), other[0].astype(np.float64)
+        assert np.array_equal(a == 0, b == 0), f"support differs with {env}"
+        assert (np.abs(a - b) <= 4e-7 * np.maximum(np.abs(b), 1e-3)).all(), f"density differs with {env}"
 
 
 def test_prefetched_volume_copy_equals_plain_copy():
