@@ -537,9 +537,9 @@ struct Splat3Warp {
     float4 queue[S3_QCAP];
     unsigned short hits[S3_HITCAP];                  // (lane of the particle << 5) | voxel number 0..26 inside its 3x3x3 box, in summation order
 };
-/** Cells along one axis whose particles can reach a voxel range, ascending global id; shift = what to add to the voxel coordinate
+/** Cells along one axis whose particles can reach a voxel range, ascending global id; shift = what to add to the coordinate
  *  of a particle of that cell (the image next to the cell's own voxels) to get the periodic image that lies next to the range
- *  (0, -s or +s); mid = centre of the cell's voxels. */
+ *  (0, -period or +period); mid = centre of the cell's voxels.  Both in OBJECT-space units. */
 struct Splat3Axis {
     int n;
     int cell[S3_MAXCELLS];
@@ -555,8 +555,16 @@ struct Splat3Shared {
     float runShift[4], runMid[4];
 };
 static_assert(sizeof(Splat3Shared) <= 57088, "density_splat3_kernel must fit four blocks per SM");
+/** Derived grid constants, computed once on the host: as kernel parameters they are constant-bank operands (no registers, nothing to
+ *  re-derive inside the loops). */
+struct Splat3Consts {
+    float isd[3];    // 1 / sliceDist
+    float per[3];    // period = s * sliceDist
+    float rper[3];   // 1 / period
+    float slack[3];  // slack of the pre-test, object units
+};
 
-__global__ void __launch_bounds__(CT_THREADS, 4) density_splat3_kernel(Geo g, DevState* st, const float4* __restrict__ recs,
+__global__ void __launch_bounds__(CT_THREADS, 4) density_splat3_kernel(Geo g, Splat3Consts kc, DevState* st, const float4* __restrict__ recs,
     const unsigned* __restrict__ cellStart, float* __restrict__ vol, int reach) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     Splat3Shared& sh = *reinterpret_cast<Splat3Shared*>(smemRaw);
@@ -587,7 +595,7 @@ __global__ void __launch_bounds__(CT_THREADS, 4) density_splat3_kernel(Geo g, De
             const int v0 = tmp[i] * C, v1 = min(v0 + C, g.s[a]) - 1; // the cell's voxels
             float shift = 0.0f;
             if (g.cyc[a] && !(v1 >= lo && v0 <= hi)) shift = (v1 + g.s[a] >= lo && v0 + g.s[a] <= hi) ? (float)g.s[a] : -(float)g.s[a];
-            A.cell[i] = tmp[i], A.shift[i] = shift, A.mid[i] = 0.5f * (float)(v0 + v1);
+            A.cell[i] = tmp[i], A.shift[i] = shift * g.sd[a], A.mid[i] = 0.5f * (float)(v0 + v1) * g.sd[a] + g.mn[a];
         }
         if (q == 0) {
             int nr = 0;
@@ -595,7 +603,9 @@ __global__ void __launch_bounds__(CT_THREADS, 4) density_splat3_kernel(Geo g, De
                 const int ca = A.cell[i];
                 int cb = ca;
                 for (++i; i < n && A.cell[i] == cb + 1 && A.shift[i] == A.shift[i - 1]; ++i) ++cb;
-                if (nr < 4) sh.runA[nr] = ca, sh.runB[nr] = cb, sh.runShift[nr] = A.shift[i - 1], sh.runMid[nr] = 0.5f * (float)(ca * C + min((cb + 1) * C, g.s[0]) - 1);
+                if (nr < 4)
+                    sh.runA[nr] = ca, sh.runB[nr] = cb, sh.runShift[nr] = A.shift[i - 1],
+                    sh.runMid[nr] = 0.5f * (float)(ca * C + min((cb + 1) * C, g.s[0]) - 1) * g.sd[0] + g.mn[0];
                 ++nr;
             }
             sh.nruns = n < 0 ? -1 : (nr <= 4 ? nr : -1);
@@ -615,7 +625,6 @@ __global__ void __launch_bounds__(CT_THREADS, 4) density_splat3_kernel(Geo g, De
     }
     for (int i = lane; i < S3_FLOATS / 4; i += 32) reinterpret_cast<float4*>(W.tile)[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     __syncwarp();
-    const float isdx = __frcp_rn(g.sd[0]), isdy = __frcp_rn(g.sd[1]), isdz = __frcp_rn(g.sd[2]);
     const unsigned ltMask = (1u << lane) - 1u;
     unsigned qHead = 0, qTail = 0; // ring positions (uniform)
 
@@ -656,9 +665,9 @@ __global__ void __launch_bounds__(CT_THREADS, 4) density_splat3_kernel(Geo g, De
             dg.k0 = __fdiv_rn(1.0f, eps);               // (1.0f / epsilon) (:475)
             dg.eps = eps;
             int lx, ly, lz, bx, by, bz, tx, ty, tz;
-            axisBox(p.x, p.w, eps, g.mn[0], g.sd[0], isdx, g.s[0], g.cyc[0] != 0, t0x, t1x, lx, bx, tx);
-            axisBox(p.y, p.w, eps, g.mn[1], g.sd[1], isdy, g.s[1], g.cyc[1] != 0, t0y, t1y, ly, by, ty);
-            axisBox(p.z, p.w, eps, g.mn[2], g.sd[2], isdz, g.s[2], g.cyc[2] != 0, t0z, t1z, lz, bz, tz);
+            axisBox(p.x, p.w, eps, g.mn[0], g.sd[0], kc.isd[0], g.s[0], g.cyc[0] != 0, t0x, t1x, lx, bx, tx);
+            axisBox(p.y, p.w, eps, g.mn[1], g.sd[1], kc.isd[1], g.s[1], g.cyc[1] != 0, t0y, t1y, ly, by, ty);
+            axisBox(p.z, p.w, eps, g.mn[2], g.sd[2], kc.isd[2], g.s[2], g.cyc[2] != 0, t0z, t1z, lz, bz, tz);
             dg.f0x = (float)tx, dg.f0y = (float)ty, dg.f0z = (float)tz;
             dg.base = lx + ly * S3_SY + lz * S3_SZ;
             unsigned mk = 0u;
@@ -748,17 +757,13 @@ __global__ void __launch_bounds__(CT_THREADS, 4) density_splat3_kernel(Geo g, De
     };
 
     // ---- stream the cell rows ----------------------------------------------------------------------------------------------------
-    // Conservative pre-test in voxel coordinates: the support box of a particle lies inside [u - e, u + e], u = (p - min)/sd; on a periodic
-    // axis u is first brought next to the voxels of the particle's own cell (row / run centre +- half a period: robust against a home
-    // voxel that the binning's exact division puts one cell further) and then moved to the image next to the sub-tile (the cell's
-    // shift); e = eps/sd + slack for the rounding of this test and the slop of the exact integer box (which follows in the digest).
-    const float ax = isdx, bx_ = -g.mn[0] * isdx, ay = isdy, by_ = -g.mn[1] * isdy, az = isdz, bz_ = -g.mn[2] * isdz;
-    const float fsx = (float)g.s[0], fsy = (float)g.s[1], fsz = (float)g.s[2];
-    const float rsx = __frcp_rn(fsx), rsy = __frcp_rn(fsy), rsz = __frcp_rn(fsz);
-    const float dlx = 0.05f + 1e-5f * fsx, dly = 0.05f + 1e-5f * fsy, dlz = 0.05f + 1e-5f * fsz;
-    const bool cycx = g.cyc[0] != 0, cycy = g.cyc[1] != 0, cycz = g.cyc[2] != 0;
-    const float sig = g.sigma;
-    const float lox = (float)t0x, hix = (float)t1x, loy = (float)t0y, hiy = (float)t1y, loz = (float)t0z, hiz = (float)t1z;
+    // Conservative pre-test in object space: the support of a particle is [p - eps, p + eps]; the sub-tile's voxels span [lo, hi] (plus
+    // a slack for the rounding of this test and the slop of the exact integer box, which follows in the digest).  On a periodic axis
+    // the particle is first brought next to the voxels of its own cell (row / run centre +- half a period: robust against a home voxel
+    // that the binning's exact division puts one cell further) and then moved to the image next to the sub-tile (the cell's shift).
+    const float lox = fmaf((float)t0x, g.sd[0], g.mn[0]) - kc.slack[0], hix = fmaf((float)t1x, g.sd[0], g.mn[0]) + kc.slack[0];
+    const float loy = fmaf((float)t0y, g.sd[1], g.mn[1]) - kc.slack[1], hiy = fmaf((float)t1y, g.sd[1], g.mn[1]) + kc.slack[1];
+    const float loz = fmaf((float)t0z, g.sd[2], g.mn[2]) - kc.slack[2], hiz = fmaf((float)t1z, g.sd[2], g.mn[2]) + kc.slack[2];
     // Row descriptors: lane i owns (cell z, cell y, x run) number i of the sub-tile's neighbourhood, in summation order, and loads its
     // record range -- one round of table reads for all rows instead of one dependent read per row.
     const int nay = AY.n, naz = AZ.n;
@@ -799,13 +804,12 @@ __global__ void __launch_bounds__(CT_THREADS, 4) density_splat3_kernel(Geo g, De
             more = nextChunk();
             if (more && base + lane < end) pNext = recs[base + lane];
             if (keep) {
-                const float eps = sig * p.w;
-                float ux = fmaf(p.x, ax, bx_), uy = fmaf(p.y, ay, by_), uz = fmaf(p.z, az, bz_);
-                if (cycx) ux = fmaf(-rintf((ux - sh.runMid[kr]) * rsx), fsx, ux) + sh.runShift[kr];
-                if (cycy) uy = fmaf(-rintf((uy - AY.mid[ky]) * rsy), fsy, uy) + AY.shift[ky];
-                if (cycz) uz = fmaf(-rintf((uz - AZ.mid[kz]) * rsz), fsz, uz) + AZ.shift[kz];
-                const float ex = fmaf(eps, ax, dlx), ey = fmaf(eps, ay, dly), ez = fmaf(eps, az, dlz);
-                keep = ux + ex >= lox && ux - ex <= hix && uy + ey >= loy && uy - ey <= hiy && uz + ez >= loz && uz - ez <= hiz;
+                const float eps = g.sigma * p.w;
+                float ux = p.x, uy = p.y, uz = p.z;
+                if (g.cyc[0]) ux = fmaf(-rintf((ux - sh.runMid[kr]) * kc.rper[0]), kc.per[0], ux) + sh.runShift[kr];
+                if (g.cyc[1]) uy = fmaf(-rintf((uy - AY.mid[ky]) * kc.rper[1]), kc.per[1], uy) + AY.shift[ky];
+                if (g.cyc[2]) uz = fmaf(-rintf((uz - AZ.mid[kz]) * kc.rper[2]), kc.per[2], uz) + AZ.shift[kz];
+                keep = ux + eps >= lox && ux - eps <= hix && uy + eps >= loy && uy - eps <= hiy && uz + eps >= loz && uz - eps <= hiz;
             }
             const unsigned bal = __ballot_sync(0xffffffffu, keep);
             if (keep) W.queue[(qTail + __popc(bal & ltMask)) & (S3_QCAP - 1)] = p;

@@ -745,9 +745,17 @@ int mms_compute_density(mms_ctx* c) {
         const int tileDim[3] = {CT_X, CT_Y, CT_Z};
         for (int a = 0; a < 3; ++a) // a periodic axis so short that one cell holds particles of two images of the tile: the general kernel
             if (g.cyc[a] && g.s[a] < tileDim[a] + 2 * c->reach + 2 + (1 << g.cshift)) v2 = false;
-        if (v2 && !getenv("MMS_SPLAT_V2"))
-            density_splat3_kernel<<<grid, CT_THREADS, sizeof(Splat3Shared), st>>>(g, c->dstate.as<DevState>(), c->recsB.as<float4>(),
+        if (v2 && !getenv("MMS_SPLAT_V2")) {
+            Splat3Consts kc{};
+            for (int a = 0; a < 3; ++a) {
+                kc.isd[a] = 1.0f / g.sd[a];
+                kc.per[a] = static_cast<float>(g.s[a]) * g.sd[a];
+                kc.rper[a] = 1.0f / kc.per[a];
+                kc.slack[a] = (0.05f + 1e-5f * static_cast<float>(g.s[a])) * g.sd[a];
+            }
+            density_splat3_kernel<<<grid, CT_THREADS, sizeof(Splat3Shared), st>>>(g, kc, c->dstate.as<DevState>(), c->recsB.as<float4>(),
                 c->cellStart.as<unsigned>(), c->vol.as<float>(), c->reach);
+        }
         else if (v2)
             density_splat_kernel<0, true><<<grid, CT_THREADS, sizeof(SplatShared2), st>>>(g, c->dstate.as<DevState>(), c->recsB.as<float4>(),
                 c->auxB.as<float>(), auxN, c->cellStart.as<unsigned>(), c->vol.as<float>(), c->reach);
