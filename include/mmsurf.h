@@ -166,6 +166,13 @@ int mms_get_vector_field_device(mms_ctx* ctx, const float** dev_vec, const float
 /* Use a caller-supplied volume instead of computing one (IsoSurface fed by another VolumetricDataCall source).
  * `volume` may be host or device memory, res-shaped for the current slab. */
 int mms_set_density(mms_ctx* ctx, const float* volume);
+/* Device-resident hand-off between two contexts on the same device (IsoSurfaceB200 behind a ParticlesToDensityB200, replacing the
+ * host array of VolumetricDataCall::GetData, VolumetricDataCall.h:136-144): `ctx` takes over the producer's grid, slab and (colour)
+ * volume BY REFERENCE -- nothing is copied -- and can then count / emit / read back isosurfaces with its OWN buffers, so that
+ * several consumers of one producer do not overwrite each other's meshes.  The reference lasts until either context computes, sets
+ * or adopts another density; the producer's volume must not be recomputed while `ctx` is using it (module callbacks run one at a
+ * time).  Stream-ordered after everything the producer has enqueued so far. */
+int mms_adopt_density(mms_ctx* ctx, mms_ctx* producer);
 
 int mms_extract_isosurface(mms_ctx* ctx, float isovalue); /* = count + emit into library-owned buffers */
 

@@ -17,7 +17,7 @@ ISO_MARCHING_CUBES, ISO_MARCHING_TETS = 0, 1
 
 EXPORTS = ["mms_create", "mms_destroy", "mms_last_error", "mms_set_grid", "mms_set_slab", "mms_set_params",
            "mms_clear_particles", "mms_push_particles", "mms_push_particles_dir", "mms_get_vector_field", "mms_get_vector_field_device", "mms_get_max_radius", "mms_compute_density", "mms_get_density_range", "mms_normalize", "mms_density_range_device", "mms_normalize_device", "mms_set_stream",
-           "mms_get_density", "mms_prefetch_density", "mms_get_density_device", "mms_set_density", "mms_extract_isosurface", "mms_set_isosurface_mode", "mms_count_isosurface", "mms_emit_isosurface", "mms_device_alloc",
+           "mms_get_density", "mms_prefetch_density", "mms_get_density_device", "mms_set_density", "mms_adopt_density", "mms_extract_isosurface", "mms_set_isosurface_mode", "mms_count_isosurface", "mms_emit_isosurface", "mms_device_alloc",
            "mms_device_free", "mms_route_particles", "mms_ipc_export", "mms_ipc_open", "mms_ipc_close", "mms_get_mesh",
            "mms_get_mesh_device", "mms_get_home_voxels", "mms_get_cell_tricounts", "mms_get_timings", "mms_synchronize",
            "mms_timer_start", "mms_timer_stop", "mms_launch_count", "mms_alloc_pinned", "mms_free_pinned", "mms_version", "mms_mmpld_open", "mms_mmpld_close",
@@ -95,6 +95,7 @@ def load_library():
     L.mms_prefetch_density.argtypes = [vp]
     L.mms_get_density_device.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
     L.mms_set_density.argtypes = [vp, vp]
+    L.mms_adopt_density.argtypes = [vp, vp]
     L.mms_set_isosurface_mode.argtypes = [vp, C.c_int32]
     L.mms_extract_isosurface.argtypes = [vp, C.c_float]
     L.mms_count_isosurface.argtypes = [vp, C.c_float, C.POINTER(C.c_uint64)]
@@ -314,6 +315,11 @@ class Surf:
             self._chk(self.L.mms_synchronize(self.h))
         else:
             self._chk(self.L.mms_set_density(self.h, int(vol)))
+
+    def adopt_density(self, producer: "Surf"):
+        """device-resident hand-off: use the producer context's (colour) volume by reference, with this context's own mesh buffers"""
+        self._chk(self.L.mms_adopt_density(self.h, producer.h))
+        self.res, self.nz = producer.res, producer.nz
 
     def extract_isosurface(self, iso):
         self._chk(self.L.mms_extract_isosurface(self.h, float(iso)))

@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmmsurf.so")
 SOURCES = ["mmsurf.cu", "mmpld.cpp"]
-HEADERS = ["common.cuh", "scan.cuh", "bin.cuh", "density.cuh", "mc.cuh", "mc_case_words.inc", "../../include/mmsurf.h"]
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cuh", ".inc", ".h"))) + ["../../include/mmsurf.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
               "-Xptxas", "-v", "--fmad=true", "-shared", "-cudart", "shared", "-Xcompiler", "-pthread"]
 

@@ -32,6 +32,18 @@ __device__ __forceinline__ bool axisReaches(int X, int f, int lo, int hi, int s,
     return (b >= lo && a <= hi) || (b - s >= lo && a - s <= hi) || (b + s >= lo && a + s <= hi);
 }
 
+/** Bump mode: does the interval [p - eps, p + eps], eps = sigma * rad, contain a grid node of this axis?  If it contains none, every
+ *  voxel the reference visits for this particle has dis >= eps and receives nothing (ParticlesToDensity.cpp:472-476): the particle is
+ *  dropped before the sort.  With voxels much larger than the kernel (the modules' default 16^3 grid) that is almost every particle.
+ *  Same bounds and slop as the density kernels' tight support box, so nothing that contributes is ever dropped. */
+__device__ __forceinline__ bool supportHasNode(float p, float rad, const Geo& g, int a) {
+    const float eps = g.sigma * rad, isd = __frcp_rn(g.sd[a]);
+    const float aa = p - g.mn[a];
+    const float vlo = (aa - eps) * isd, vhi = (aa + eps) * isd;
+    const float slop = fmaxf(fmaxf(fabsf(vlo), fabsf(vhi)), 1.0f) * 4e-6f;
+    return __float2int_ru(vlo - slop) <= __float2int_rd(vhi + slop);
+}
+
 __device__ __forceinline__ Binned binParticle(const Geo& g, const ListDev& l, unsigned long long j) {
     Binned q;
     q.p = fetchParticle(l, j);
@@ -51,6 +63,7 @@ __device__ __forceinline__ Binned binParticle(const Geo& g, const ListDev& l, un
         const float cut = g.gausslim * g.radscale * r;
         fx = filterSize(cut, g.sd[0]) + 1, fy = filterSize(cut, g.sd[1]) + 1, fz = filterSize(cut, g.sd[2]) + 1;
     }
+    if (g.mode == 0 && !(supportHasNode(q.p.x, q.p.w, g, 0) && supportHasNode(q.p.y, q.p.w, g, 1) && supportHasNode(q.p.z, q.p.w, g, 2))) return q;
     if (!axisReaches(q.X, fx, 0, g.s[0] - 1, g.s[0], g.cyc[0])) return q;
     if (!axisReaches(q.Y, fy, 0, g.s[1] - 1, g.s[1], g.cyc[1])) return q;
     if (!axisReaches(q.Z, fz, g.z0, g.z0 + g.nz - 1, g.s[2], g.cyc[2])) return q;
@@ -116,13 +129,16 @@ __device__ __forceinline__ bool recLess(const float4& a, const float* aa, const 
     return false;
 }
 
+constexpr unsigned kBigCell = 1024;  // cells with more records than this are sorted by cell_sort_big_kernel
+constexpr int kBigThreads = 512;
+
 /**
  * One thread per sorted slot: rank of my record among the records of my cell (ties: slot order, the tied
  * records are bit-identical so their order cannot change any sum), written to the second buffer.
  */
 __global__ void __launch_bounds__(256) cell_order_kernel(Geo g, const unsigned* __restrict__ cellStart,
     const float4* __restrict__ in, const float* __restrict__ auxIn, float4* __restrict__ out, float* __restrict__ auxOut,
-    int auxN, const DevState* __restrict__ st) {
+    int auxN, const DevState* __restrict__ st, unsigned* __restrict__ bigCells, unsigned* __restrict__ nBig) {
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= st->kept) return;
     const float4 me = in[i];
@@ -133,6 +149,10 @@ __global__ void __launch_bounds__(256) cell_order_kernel(Geo g, const unsigned* 
     const int zw = g.cyc[2] ? floorMod(Z, g.s[2]) : min(max(Z, 0), g.s[2] - 1);
     const int cell = (xw >> g.cshift) + g.nc[0] * ((yw >> g.cshift) + g.nc[1] * (zw >> g.cshift));
     const unsigned b = cellStart[cell], e = cellStart[cell + 1];
+    if (e - b > kBigCell) { // crowded cell: ranking by all pairs would be quadratic; cell_sort_big_kernel sorts it
+        if (i == b) bigCells[atomicAdd(nBig, 1u)] = static_cast<unsigned>(cell);
+        return;
+    }
     float myAux[4] = {0, 0, 0, 0};
     for (int k = 0; k < auxN; ++k) myAux[k] = auxIn[static_cast<size_t>(i) * auxN + k];
     unsigned rank = 0;
@@ -145,6 +165,92 @@ __global__ void __launch_bounds__(256) cell_order_kernel(Geo g, const unsigned* 
     }
     out[b + rank] = me;
     for (int k = 0; k < auxN; ++k) auxOut[static_cast<size_t>(b + rank) * auxN + k] = myAux[k];
+}
+
+/**
+ * Canonical order inside CROWDED cells (coarse grids with wide kernels, clustered data): a block takes a cell from the list
+ * cell_order_kernel left behind, sorts chunks of kBigThreads records by all-pairs ranking in shared memory and merges them bottom-up,
+ * ping-ponging between the two record buffers; every element finds its place in the merged run by a binary search in the other run
+ * (ties: the left run first; tied records are bit-identical).  O(k log^2 k) per cell instead of O(k^2).  The launch is unconditional and
+ * tiny; with no crowded cell every block leaves at once.
+ */
+__global__ void __launch_bounds__(kBigThreads) cell_sort_big_kernel(const unsigned* __restrict__ cellStart, float4* recA, float* auxA,
+    float4* recB, float* auxB, int auxN, const unsigned* __restrict__ bigCells, const unsigned* __restrict__ nBig, unsigned* __restrict__ next) {
+    __shared__ float4 sRec[kBigThreads];
+    __shared__ float sAux[kBigThreads][4];
+    __shared__ unsigned sCell;
+    const int tid = threadIdx.x;
+    const unsigned n = *nBig;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) sCell = atomicAdd(next, 1u);
+        __syncthreads();
+        if (sCell >= n) return;
+        const unsigned cell = bigCells[sCell];
+        const unsigned b = cellStart[cell], k = cellStart[cell + 1] - b;
+        // ---- sorted chunks: A -> B ----------------------------------------------------------------------------------
+        for (unsigned c0 = 0; c0 < k; c0 += kBigThreads) {
+            const unsigned m = min(static_cast<unsigned>(kBigThreads), k - c0);
+            __syncthreads();
+            if (static_cast<unsigned>(tid) < m) {
+                sRec[tid] = recA[b + c0 + tid];
+                for (int q = 0; q < auxN; ++q) sAux[tid][q] = auxA[static_cast<size_t>(b + c0 + tid) * auxN + q];
+            }
+            __syncthreads();
+            if (static_cast<unsigned>(tid) < m) {
+                const float4 me = sRec[tid];
+                float ma[4] = {0, 0, 0, 0};
+                for (int q = 0; q < auxN; ++q) ma[q] = sAux[tid][q];
+                unsigned rank = 0;
+                for (unsigned o = 0; o < m; ++o) {
+                    if (o == static_cast<unsigned>(tid)) continue;
+                    const float4 ot = sRec[o];
+                    if (recLess(ot, sAux[o], me, ma, auxN) || (!recLess(me, ma, ot, sAux[o], auxN) && o < static_cast<unsigned>(tid))) ++rank;
+                }
+                recB[b + c0 + rank] = me;
+                for (int q = 0; q < auxN; ++q) auxB[static_cast<size_t>(b + c0 + rank) * auxN + q] = ma[q];
+            }
+        }
+        // ---- bottom-up merge, B -> A -> B ... ----------------------------------------------------------------------------
+        float4* src = recB;
+        float* srcAux = auxB;
+        float4* dst = recA;
+        float* dstAux = auxA;
+        for (unsigned L = kBigThreads; L < k; L <<= 1) {
+            __syncthreads(); // the previous pass (global writes of this block) is complete and visible
+            for (unsigned i = tid; i < k; i += kBigThreads) {
+                const unsigned run = i / L, pairBase = (run >> 1) * 2 * L;
+                const bool left = (run & 1u) == 0;
+                // the other run of my pair
+                const unsigned oBeg = left ? min(pairBase + L, k) : pairBase, oEnd = left ? min(pairBase + 2 * L, k) : pairBase + L;
+                const float4 me = src[b + i];
+                float ma[4] = {0, 0, 0, 0};
+                for (int q = 0; q < auxN; ++q) ma[q] = srcAux[static_cast<size_t>(b + i) * auxN + q];
+                // left element: number of right elements strictly less than me; right element: number of left elements <= me
+                unsigned lo = oBeg, hi = oEnd;
+                while (lo < hi) {
+                    const unsigned mid = (lo + hi) >> 1;
+                    const float4 ot = src[b + mid];
+                    float oa[4] = {0, 0, 0, 0};
+                    for (int q = 0; q < auxN; ++q) oa[q] = srcAux[static_cast<size_t>(b + mid) * auxN + q];
+                    const bool before = left ? recLess(ot, oa, me, ma, auxN) : !recLess(me, ma, ot, oa, auxN);
+                    if (before) lo = mid + 1; else hi = mid;
+                }
+                const unsigned pos = pairBase + (i - (left ? pairBase : pairBase + L)) + (lo - oBeg);
+                dst[b + pos] = me;
+                for (int q = 0; q < auxN; ++q) dstAux[static_cast<size_t>(b + pos) * auxN + q] = ma[q];
+            }
+            float4* t = src; src = dst; dst = t;
+            float* ta = srcAux; srcAux = dstAux; dstAux = ta;
+        }
+        __syncthreads();
+        if (src != recB) { // an odd number of merge passes left the result in A
+            for (unsigned i = tid; i < k; i += kBigThreads) {
+                recB[b + i] = recA[b + i];
+                for (int q = 0; q < auxN; ++q) auxB[static_cast<size_t>(b + i) * auxN + q] = auxA[static_cast<size_t>(b + i) * auxN + q];
+            }
+        }
+    }
 }
 
 } // namespace mms

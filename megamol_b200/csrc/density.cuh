@@ -31,7 +31,7 @@ constexpr int CT_FLOATS = CT_SZ * CT_Z;
 constexpr int CT_WARPS = 8;
 constexpr int CT_THREADS = CT_WARPS * 32;
 constexpr int CT_MAXAXIS = 16;                       // cells per axis in a tile's neighbourhood (<= 32/4 + 3)
-constexpr int CT_MAXCELLS = 640;                     // neighbourhood cells (C = 4: at most 11 x 7 x 7 = 539)
+constexpr int CT_MAXCELLS = 576;                     // neighbourhood cells (C = 4: at most 11 x 7 x 7 = 539)
 
 /** A digested particle (per-warp staging, read back with broadcast LDS.128). 12 words; the shared-memory budget
  *  (tile 36.6 KB + 12 KB of these + tables) is trimmed to 56 KB so that FOUR blocks fit one SM. */
@@ -44,22 +44,11 @@ struct Dig {
     unsigned mask27;            // fast path (all dims <= 3): valid lanes of the fixed 3x3x3 lane pattern
 };
 
-constexpr int CT_HITCAP = 768;                       // V2: (particle, voxel) pairs one warp expands at a time (32 particles x 27 worst case = 864: a second pass)
-
-struct SplatWarpV1 {
-    Dig dig[32];
-};
-struct SplatWarpV2 {
-    unsigned short hits[CT_HITCAP];                  // (lane of the particle << 5) | voxel number 0..26 inside its 3x3x3 box, in summation order
-};
-
-template<class WARPSTORE>
-struct SplatSharedT {
+struct SplatShared {
     float tile[CT_FLOATS];
-    WARPSTORE ws[CT_WARPS];
-    float4 lut[27];                    // V2: voxel number -> (ix, iy, iz as floats, tile offset as int bits)
+    Dig dig[CT_WARPS][32];
     unsigned cellB[CT_MAXCELLS];
-    unsigned short cellN[CT_MAXCELLS]; // particles in the cell (a cell with more than 65535 particles is split by the host guard)
+    unsigned cellN[CT_MAXCELLS];       // particles in the cell
     int axisCells[3][CT_MAXAXIS];
     int axisCount[3];
     int colList[3][4][CT_MAXAXIS]; // per axis, per colour: positions in axisCells
@@ -71,9 +60,7 @@ struct SplatSharedT {
     int tl0[3], tl1[3];            // tile voxel range (inclusive), clipped to the grid / slab
     int perVoxelWrap[3];           // degenerate cyclic axis: wrap every voxel instead of choosing one image per particle
 };
-using SplatShared = SplatSharedT<SplatWarpV1>;
-using SplatShared2 = SplatSharedT<SplatWarpV2>;
-static_assert(sizeof(SplatShared) <= 57088 && sizeof(SplatShared2) <= 57088, "density_splat_kernel must fit four blocks per SM");
+static_assert(sizeof(SplatShared) <= 57088, "density_splat_kernel must fit four blocks per SM");
 
 /** Ordered, duplicate-free list of the cells along one axis whose particles can reach voxels [t0, t1]. */
 __device__ inline int buildAxisCells(int t0, int t1, int reach, int s, bool cyc, int sh, int nc, int* out, int cap) {
@@ -150,28 +137,17 @@ __device__ __forceinline__ bool kernelValue(float d2, float eps, float k0, float
     }
 }
 
-/**
- * V2 (host-selected: bump mode, aggregator 0, every support box <= 3x3x3 voxels, no per-voxel wrap) replaces the per-particle walk by
- *   A  lane = particle: the 9 per-axis squared offsets once, the 27 squared distances by two additions each, a 27-bit hit mask
- *      (inclusive pre-test d2 < eps^2 (1 + 1e-6); the exact reference test follows in B)
- *   B  the set bits of all 32 masks are expanded into ONE list in (particle, voxel) order and the lanes walk that list: every lane
- *      evaluates a real hit (sqrt, rcp, ex2).  Hits of one round that fall on the same voxel are applied in list order
- *      (match.any + rank), so every voxel still receives its contributions in the canonical order: bit-identical to V1.
- */
-template<int MODE, bool V2>
+/** The general splat kernel: any support box the cell size allows, aggregators 0 and 1, periodic axes of any length (per-voxel wrap).
+ *  Supports of at most 3x3x3 voxels with aggregator 0 (C1, C2, C4) take density_splat3_kernel instead. */
+template<int MODE>
 __global__ void __launch_bounds__(CT_THREADS, 4) density_splat_kernel(Geo g, DevState* st, const float4* __restrict__ recs,
     const float* __restrict__ aux, int auxN, const unsigned* __restrict__ cellStart, float* __restrict__ vol, int reach) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
-    using Shared = SplatSharedT<typename std::conditional<V2, SplatWarpV2, SplatWarpV1>::type>;
-    Shared& sh = *reinterpret_cast<Shared*>(smemRaw);
+    SplatShared& sh = *reinterpret_cast<SplatShared*>(smemRaw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int C = 1 << g.cshift;
     for (int i = tid; i < CT_FLOATS; i += CT_THREADS) sh.tile[i] = 0.0f;
     if (tid < 64) sh.phaseCount[tid] = 0;
-    if (V2 && tid < 27) {
-        const int ix = tid % 3, iy = (tid / 3) % 3, iz = tid / 9;
-        sh.lut[tid] = make_float4((float)ix, (float)iy, (float)iz, __int_as_float(ix + iy * CT_SY + iz * CT_SZ));
-    }
     if (tid < 3) {
         const int a = tid;
         const int t0 = (a == 0 ? (int)blockIdx.x * CT_X : a == 1 ? (int)blockIdx.y * CT_Y : g.z0 + (int)blockIdx.z * CT_Z);
@@ -208,8 +184,7 @@ __global__ void __launch_bounds__(CT_THREADS, 4) density_splat_kernel(Geo g, Dev
         const size_t cell = cxg + static_cast<size_t>(g.nc[0]) * (cyg + static_cast<size_t>(g.nc[1]) * czg);
         const unsigned b = cellStart[cell], e = cellStart[cell + 1];
         sh.cellB[i] = b;
-        sh.cellN[i] = static_cast<unsigned short>(min(e - b, 65535u));
-        if (e - b > 65535u) st->pad[0] = 3u; // a cell this crowded needs the (not yet written) split path
+        sh.cellN[i] = e - b;
         if (e > b) {
             const bool irx = g.cyc[0] && ((g.nc[0] & 1) || (g.s[0] & (C - 1))), iry = g.cyc[1] && ((g.nc[1] & 1) || (g.s[1] & (C - 1))),
                        irz = g.cyc[2] && ((g.nc[2] & 1) || (g.s[2] & (C - 1)));
@@ -250,7 +225,7 @@ __global__ void __launch_bounds__(CT_THREADS, 4) density_splat_kernel(Geo g, Dev
     const bool pvx = sh.perVoxelWrap[0] != 0, pvy = sh.perVoxelWrap[1] != 0, pvz = sh.perVoxelWrap[2] != 0;
     const bool anyPv = pvx | pvy | pvz;
     const float isdx = __frcp_rn(g.sd[0]), isdy = __frcp_rn(g.sd[1]), isdz = __frcp_rn(g.sd[2]);
-    auto& myStore = sh.ws[warp];
+    Dig* myDig = sh.dig[warp];
 
     for (int phase = 0; phase < nphase; ++phase) {
         const int pBeg = sh.phaseStart[phase], pEnd = sh.phaseStart[phase + 1];
@@ -276,7 +251,6 @@ __global__ void __launch_bounds__(CT_THREADS, 4) density_splat_kernel(Geo g, Dev
                 const int cnt = static_cast<int>(min(32u, nSeq - t0));
                 int myL0x = 0, myL0y = 0, myL0z = 0; // per-voxel-wrap mode only: tile-local box origin before wrapping
                 bool myLive = false;                 // my particle reaches the tile
-                Dig dg{};                            // V2: my digested particle stays in registers
                 if (lane < cnt) {
                     // ---- digest my particle -------------------------------------------------------------------
                     const float4 p = recs[src];
@@ -349,93 +323,17 @@ __global__ void __launch_bounds__(CT_THREADS, 4) density_splat_kernel(Geo g, Dev
                         }
                         d.mask27 = m;
                     }
-                    if constexpr (!V2) myStore.dig[lane] = d;
+                    myDig[lane] = d;
                     myLive = d.dims != 0u;
-                    if constexpr (V2) {
-                        if (myLive && d.mask27 == 0u) st->pad[0] = 4u, myLive = false; // the host promised boxes <= 3x3x3
-                        dg = d;
-                    }
                 }
                 __syncwarp();
-                if constexpr (V2) {
-                    // ---- A: hit mask of my particle ---------------------------------------------------------------------
-                    unsigned hm = 0u;
-                    if (myLive) {
-                        const float lim = __fmul_rn(__fmul_rn(dg.eps, dg.eps), 1.000001f);
-                        float qx[3], qy[3], qz[3];
-#pragma unroll
-                        for (int i = 0; i < 3; ++i) {
-                            const float dx = __fsub_rn(__fadd_rn(__fmul_rn(dg.f0x + (float)i, g.sd[0]), g.mn[0]), dg.x);
-                            const float dy = __fsub_rn(__fadd_rn(__fmul_rn(dg.f0y + (float)i, g.sd[1]), g.mn[1]), dg.y);
-                            const float dz = __fsub_rn(__fadd_rn(__fmul_rn(dg.f0z + (float)i, g.sd[2]), g.mn[2]), dg.z);
-                            qx[i] = __fmul_rn(dx, dx), qy[i] = __fmul_rn(dy, dy), qz[i] = __fmul_rn(dz, dz);
-                        }
-#pragma unroll
-                        for (int j = 0; j < 3; ++j)
-#pragma unroll
-                            for (int i = 0; i < 3; ++i) {
-                                const float sxy = __fadd_rn(qx[i], qy[j]);
-#pragma unroll
-                                for (int k = 0; k < 3; ++k)
-                                    if (__fadd_rn(sxy, qz[k]) < lim) hm |= 1u << (i + 3 * j + 9 * k);
-                            }
-                        hm &= dg.mask27;
-                    }
-                    const unsigned hcnt = __popc(hm);
-                    const unsigned incl = warpInclusiveScan(hcnt), excl = incl - hcnt;
-                    const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
-                    unsigned done = 0;
-                    int first = 0;
-                    while (done < total) {
-                        // the particles [first, last] whose hits fit the list together (a particle has <= 27 of them)
-                        const bool in = lane >= first && incl - done <= (unsigned)CT_HITCAP;
-                        const unsigned bal = __ballot_sync(0xffffffffu, in);
-                        const int last = 31 - __clz(bal);
-                        const unsigned nh = __shfl_sync(0xffffffffu, incl, last) - done;
-                        if (in) {
-                            unsigned pos = excl - done;
-                            for (unsigned mm = hm; mm; mm &= mm - 1) myStore.hits[pos++] = static_cast<unsigned short>(lane << 5 | (__ffs(mm) - 1));
-                        }
-                        __syncwarp();
-                        // ---- B: lanes = hits ------------------------------------------------------------------------------
-                        for (unsigned h0 = 0; h0 < nh; h0 += 32) {
-                            const unsigned h = h0 + lane;
-                            const bool act = h < nh;
-                            const unsigned code = act ? myStore.hits[h] : 0u;
-                            const int pl = code >> 5;
-                            const float px = __shfl_sync(0xffffffffu, dg.x, pl), py = __shfl_sync(0xffffffffu, dg.y, pl), pz = __shfl_sync(0xffffffffu, dg.z, pl);
-                            const float eps = __shfl_sync(0xffffffffu, dg.eps, pl), k0 = __shfl_sync(0xffffffffu, dg.k0, pl);
-                            const float f0x = __shfl_sync(0xffffffffu, dg.f0x, pl), f0y = __shfl_sync(0xffffffffu, dg.f0y, pl), f0z = __shfl_sync(0xffffffffu, dg.f0z, pl);
-                            const int sb = __shfl_sync(0xffffffffu, dg.base, pl);
-                            const float4 L = sh.lut[code & 31u];
-                            const float vx = __fadd_rn(__fmul_rn(f0x + L.x, g.sd[0]), g.mn[0]);
-                            const float vy = __fadd_rn(__fmul_rn(f0y + L.y, g.sd[1]), g.mn[1]);
-                            const float vz = __fadd_rn(__fmul_rn(f0z + L.z, g.sd[2]), g.mn[2]);
-                            const float dx = __fsub_rn(vx, px), dy = __fsub_rn(vy, py), dz = __fsub_rn(vz, pz);
-                            const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-                            float w = 0.0f;
-                            const bool hit = act && kernelValue<MODE>(d2, eps, k0, w);
-                            const int addr = sb + __float_as_int(L.w);
-                            // hits of this round on the same voxel: list order = canonical order
-                            const unsigned grp = __match_any_sync(0xffffffffu, hit ? addr : -1 - lane);
-                            const int rank = __popc(grp & ((1u << lane) - 1u));
-                            const int maxRank = __reduce_max_sync(0xffffffffu, hit ? rank : 0);
-                            for (int r = 0; r <= maxRank; ++r) {
-                                if (hit && rank == r) sh.tile[addr] = __fadd_rn(sh.tile[addr], w);
-                                __syncwarp();
-                            }
-                        }
-                        done += nh;
-                        first = last + 1;
-                    }
-                } else {
                 // particles of the ring cells mostly do not reach the tile: walk the non-empty digests only (ascending = canonical order)
                 const unsigned live = __ballot_sync(0xffffffffu, myLive);
                 for (unsigned rest = live; rest; rest &= rest - 1) {
                     const int j = __ffs(rest) - 1;
-                    const float4 A = reinterpret_cast<const float4*>(&myStore.dig[j])[0];
-                    const float4 B = reinterpret_cast<const float4*>(&myStore.dig[j])[1];
-                    const float4 Cc = reinterpret_cast<const float4*>(&myStore.dig[j])[2];
+                    const float4 A = reinterpret_cast<const float4*>(&myDig[j])[0];
+                    const float4 B = reinterpret_cast<const float4*>(&myDig[j])[1];
+                    const float4 Cc = reinterpret_cast<const float4*>(&myDig[j])[2];
                     const unsigned dims = __float_as_uint(Cc.z), mask27 = __float_as_uint(Cc.w);
                     const int sbase = __float_as_int(Cc.y);
                     if (mask27 != 0u && !anyPv) {
@@ -488,7 +386,6 @@ __global__ void __launch_bounds__(CT_THREADS, 4) density_splat_kernel(Geo g, Dev
                     }
                     __syncwarp(); // the next particle of this cell may touch the same voxels from other lanes
                 }
-                } // !V2
                 __syncwarp();
             }
         }
@@ -876,7 +773,12 @@ struct GatherShared {
     unsigned scanTmp[33];
 };
 
-template<int MODE, bool COLOUR>
+/** GENERAL (host-selected): periodic axes so short that SEVERAL images of a particle reach one tile -- down to supports wider than
+ *  the axis, where a voxel receives the same particle more than once, exactly as the reference's loop over the un-wrapped box does
+ *  (ParticlesToDensity.cpp:577-613) -- and, in bump mode, the reference's integer support box home +- ceil(rad/sliceDist), which
+ *  clips the kernel when sigma > 1 (:573-579).  Every (particle, image) pair is a candidate of its own, in (particle, image z, y, x)
+ *  order.  !GENERAL: at most one image per particle and tile, no box test (sigma <= 1: the box never clips). */
+template<int MODE, bool COLOUR, bool GENERAL>
 __global__ void __launch_bounds__(GT_THREADS, 2) density_gather_kernel(Geo g, DevState* st, const float4* __restrict__ recs,
     const float* __restrict__ aux, int auxN, const unsigned* __restrict__ cellStart, float* __restrict__ vol, float* __restrict__ rgb,
     int reach) {
@@ -888,8 +790,8 @@ __global__ void __launch_bounds__(GT_THREADS, 2) density_gather_kernel(Geo g, De
         const int a = tid;
         const int t0 = a == 0 ? t0x : (a == 1 ? t0y : t0z), t1 = a == 0 ? t1x : (a == 1 ? t1y : t1z);
         sh.axisCount[a] = buildAxisCells(t0, t1, reach, g.s[a], g.cyc[a] != 0, g.cshift, g.nc[a], sh.axisCells[a], CT_MAXAXIS);
-        // two periodic images of one particle reaching the same tile is not handled by this kernel
-        if (g.cyc[a] && g.s[a] < (t1 - t0 + 1) + 2 * reach + 2) st->pad[0] = 2u;
+        // two periodic images of one particle reaching the same tile: the GENERAL variant's business (the host selects it)
+        if (!GENERAL && g.cyc[a] && g.s[a] < (t1 - t0 + 1) + 2 * reach + 2) st->pad[0] = 2u;
     }
     __syncthreads();
     const int ncx = sh.axisCount[0], ncy = sh.axisCount[1], ncz = sh.axisCount[2];
@@ -946,7 +848,9 @@ __global__ void __launch_bounds__(GT_THREADS, 2) density_gather_kernel(Geo g, De
             const unsigned nin = min((unsigned)GT_CHUNK, ncand - chunk);
             __syncthreads();
             GCand c;
-            bool keep = false;
+            bool valid = false;
+            int qmin[3] = {0, 0, 0}, nq[3] = {1, 1, 1}, boxLo[3] = {0, 0, 0}, boxHi[3] = {0, 0, 0};
+            float px3[3] = {0.0f, 0.0f, 0.0f}, eps2 = 0.0f;
             if ((unsigned)tid < nin) {
                 const unsigned pos = chunk + tid;
                 int lo = 0, hi = nseg;
@@ -978,43 +882,92 @@ __global__ void __launch_bounds__(GT_THREADS, 2) density_gather_kernel(Geo g, De
                         c.cr = col.x, c.cg = col.y, c.cb = col.z;
                     }
                 }
-                // periodic image that can reach this tile (at most one: checked above)
+                // periodic images that can reach this tile: voxel index seen by the particle = t + q*s must meet [H - R, H + R]
                 const float pp[3] = {p.x, p.y, p.z};
                 const int tl0[3] = {t0x, t0y, t0z}, tl1[3] = {t1x, t1y, t1z};
-                int kk[3] = {0, 0, 0};
-                float gap2 = 0.0f; // squared distance from the particle to the tile's box (in the particle's image frame)
 #pragma unroll
                 for (int a = 0; a < 3; ++a) {
-                    int k = 0;
+                    qmin[a] = 0, nq[a] = 1, boxLo[a] = -(1 << 20), boxHi[a] = 1 << 20;
+                    if (GENERAL && MODE == 0) { // the reference's integer support box, in un-wrapped voxel indices
+                        const int H = homeVoxel(pp[a], g.mn[a], g.sd[a]), f = filterSize(p.w, g.sd[a]);
+                        boxLo[a] = H - f, boxHi[a] = H + f;
+                    }
                     if (g.cyc[a]) {
                         const int H = homeVoxel(pp[a], g.mn[a], g.sd[a]);
-                        // voxel index seen by the particle = t + k, k a multiple of s, must meet [H - R, H + R], R = reach + 1:
-                        // the smallest such k is ceil((H - R - t1) / s) * s (at most one k works: checked per block above)
-                        const int R = reach + 1;
-                        const int a0 = H - R - tl1[a];
-                        const int q = -((-a0 - floorMod(-a0, g.s[a])) / g.s[a]); // ceil(a0 / s)
-                        k = q * g.s[a];
-                        if (tl0[a] + k > H + R) k = 0; // no image reaches this tile
+                        const int R = (GENERAL && MODE == 0) ? filterSize(p.w, g.sd[a]) : reach + 1;
+                        const int a0 = H - R - tl1[a], a1 = H + R - tl0[a];
+                        const int qlo = -((-a0 - floorMod(-a0, g.s[a])) / g.s[a]); // ceil(a0 / s)
+                        const int qhi = (a1 - floorMod(a1, g.s[a])) / g.s[a];      // floor(a1 / s)
+                        qmin[a] = qlo;
+                        nq[a] = GENERAL ? max(qhi - qlo + 1, 0) : 1; // !GENERAL: at most one image works (checked per block above)
+                        if (!GENERAL && tl0[a] + qlo * g.s[a] > H + R) qmin[a] = 0; // no image reaches this tile: gap2 rejects it
                     }
-                    kk[a] = k;
+                }
+                eps2 = eps * eps * 1.01f; // sphere / tile-box rejection (1 % slack for the rounding of this test; the exact test is per voxel)
+                px3[0] = p.x, px3[1] = p.y, px3[2] = p.z;
+                valid = true;
+            }
+            // squared distance from the particle to the tile's box in the frame of image (qx, qy, qz)
+            auto imageKeep = [&](int qx, int qy, int qz) {
+                const int q[3] = {qx, qy, qz};
+                const int tl0[3] = {t0x, t0y, t0z}, tl1[3] = {t1x, t1y, t1z};
+                float gap2 = 0.0f;
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    const int k = q[a] * g.s[a];
                     const float lo_ = (float)(tl0[a] + k) * g.sd[a] + g.mn[a], hi_ = (float)(tl1[a] + k) * g.sd[a] + g.mn[a];
-                    const float d = fmaxf(fmaxf(lo_ - pp[a], pp[a] - hi_), 0.0f);
+                    const float d = fmaxf(fmaxf(lo_ - px3[a], px3[a] - hi_), 0.0f);
                     gap2 += d * d;
                 }
-                c.kx = kk[0], c.ky = kk[1], c.kz = kk[2], c.pad = 0;
-                // sphere / tile-box rejection (1 % slack for the rounding of this test; the exact test is per voxel)
-                keep = gap2 <= eps * eps * 1.01f;
+                return gap2 <= eps2;
+            };
+            // allowed tile-local voxel ranges of the integer box for image (qx, qy, qz), packed: x 2 x 6 bits, y and z 2 x 4 bits
+            auto packBox = [&](int qx, int qy, int qz) {
+                const int lx = min(max(boxLo[0] - qx * g.s[0] - t0x, 0), GT_X + 1), ux = min(max(boxHi[0] - qx * g.s[0] - t0x + 1, 0), GT_X + 1);
+                const int ly = min(max(boxLo[1] - qy * g.s[1] - t0y, 0), GT_Y + 1), uy = min(max(boxHi[1] - qy * g.s[1] - t0y + 1, 0), GT_Y + 1);
+                const int lz = min(max(boxLo[2] - qz * g.s[2] - t0z, 0), GT_Z + 1), uz = min(max(boxHi[2] - qz * g.s[2] - t0z + 1, 0), GT_Z + 1);
+                return lx | ux << 6 | ly << 12 | uy << 16 | lz << 20 | uz << 24;
+            };
+            unsigned mine = 0; // my particle's images that pass the rejection test
+            if (valid) {
+                if (!GENERAL) mine = imageKeep(qmin[0], qmin[1], qmin[2]) ? 1u : 0u;
+                else
+                    for (int iz = 0; iz < nq[2]; ++iz)
+                        for (int iy = 0; iy < nq[1]; ++iy)
+                            for (int ix = 0; ix < nq[0]; ++ix) mine += imageKeep(qmin[0] + ix, qmin[1] + iy, qmin[2] + iz) ? 1u : 0u;
             }
-            // order-preserving compaction of the survivors
-            unsigned nkeep;
-            const unsigned slot = blockExclusiveScan(keep ? 1u : 0u, &nkeep, sh.scanTmp);
-            if (keep) sh.cand[slot] = c;
-            __syncthreads();
-            const unsigned nstaged = nkeep;
+            // order-preserving expansion of the surviving (particle, image) pairs, GT_CHUNK of them at a time
+            unsigned ntotal;
+            const unsigned slot0 = blockExclusiveScan(mine, &ntotal, sh.scanTmp);
+            for (unsigned w0 = 0; w0 < ntotal; w0 += GT_CHUNK) {
+                if (w0) __syncthreads(); // the previous window has been consumed
+                if (mine && slot0 + mine > w0 && slot0 < w0 + GT_CHUNK) {
+                    unsigned sl = slot0;
+                    for (int iz = 0; iz < nq[2]; ++iz)
+                        for (int iy = 0; iy < nq[1]; ++iy)
+                            for (int ix = 0; ix < nq[0]; ++ix) {
+                                const int qx = qmin[0] + ix, qy = qmin[1] + iy, qz = qmin[2] + iz;
+                                if (GENERAL && !imageKeep(qx, qy, qz)) continue;
+                                if (sl >= w0 && sl < w0 + GT_CHUNK) {
+                                    c.kx = qx * g.s[0], c.ky = qy * g.s[1], c.kz = qz * g.s[2];
+                                    c.pad = (GENERAL && MODE == 0) ? packBox(qx, qy, qz) : 0;
+                                    sh.cand[sl - w0] = c;
+                                }
+                                ++sl;
+                            }
+                }
+                __syncthreads();
+                const unsigned nstaged = min((unsigned)GT_CHUNK, ntotal - w0);
             for (unsigned j = 0; j < nstaged; ++j) {
                 const float4 A = reinterpret_cast<const float4*>(&sh.cand[j])[0];
                 const float4 B = reinterpret_cast<const float4*>(&sh.cand[j])[1];
                 const int4 K = reinterpret_cast<const int4*>(&sh.cand[j])[2];
+                int zLo = 0, zHi = GT_Z;
+                if (GENERAL && MODE == 0) { // the reference's integer support box (clips the kernel when sigma > 1)
+                    const int bx = K.w;
+                    if (lane < (bx & 63) || lane >= ((bx >> 6) & 63) || ty < ((bx >> 12) & 15) || ty >= ((bx >> 16) & 15)) continue;
+                    zLo = (bx >> 20) & 15, zHi = (bx >> 24) & 15;
+                }
                 float px = vx, py = vy;
                 if (K.x | K.y | K.z) { // periodic image: the reference's un-wrapped voxel index (ParticlesToDensity.cpp:605-613)
                     px = __fadd_rn(__fmul_rn((float)(vxI + K.x), g.sd[0]), g.mn[0]);
@@ -1047,7 +1000,7 @@ __global__ void __launch_bounds__(GT_THREADS, 2) density_gather_kernel(Geo g, De
                             accG[k] = __fadd_rn(accG[k], __fmul_rn(w, B.z));
                             accB[k] = __fadd_rn(accB[k], __fmul_rn(w, B.w));
                         }
-                    } else if (kernelValue<MODE, (MODE == 0 && COLOUR)>(d2, MODE == 0 ? B.x : 0.0f, A.w, w, B.x)) {
+                    } else if ((!GENERAL || (k >= zLo && k < zHi)) && kernelValue<MODE, (MODE == 0 && COLOUR)>(d2, MODE == 0 ? B.x : 0.0f, A.w, w, B.x)) {
                         if (MODE == 0 && COLOUR) { // aggregator 2: weights += w, vol += w * dir (:501-505), product and sum rounded separately
                             acc[k] = __fadd_rn(acc[k], w);
                             accR[k] = __fadd_rn(accR[k], __fmul_rn(w, B.y));
@@ -1066,6 +1019,7 @@ __global__ void __launch_bounds__(GT_THREADS, 2) density_gather_kernel(Geo g, De
                     }
                 }
             }
+            } // window
         }
     }
     float vmin = INFINITY, vmax = -INFINITY;

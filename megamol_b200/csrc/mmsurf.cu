@@ -157,13 +157,18 @@ struct mms_ctx {
     cudaStream_t ownStream = nullptr;
     DevBuf rangeBuf; // {-min, max} as floats for device-side all-reduce + normalise
     bool haveCount = false, meshExternal = false;
+    const float* adoptedVol = nullptr; // mms_adopt_density: another context's volume (and colour volume), by reference
+    const float* adoptedRgb = nullptr;
+    cudaEvent_t adoptReady = nullptr;
+    const float* isoVol() { return adoptedVol ? adoptedVol : vol.as<float>(); }
+    const float* isoRgb() { return adoptedVol ? adoptedRgb : rgb.as<float>(); }
     int isoMode = MMS_ISO_MARCHING_CUBES, countMode = MMS_ISO_MARCHING_CUBES;
     MtGeo mtGeo{};
 
     DevBuf routeCounts, routeOffsets, routeTile;
     PinBuf hRoute;
     DevBuf cellCount, cellStart, cursor, tileSums, recsA, recsB, auxA, auxB, vol, rgb, segCount, segOffset, meshPos, meshNrm,
-        meshCol, triCount, home, dstate, dirVol, rmaxBuf;
+        meshCol, triCount, home, dstate, dirVol, rmaxBuf, bigCells;
     PinBuf hState, hVol, hRgb, hPos, hNrm, hCol, hHome, hTri, hDir;
     cudaEvent_t ev[EV_COUNT]{};
     bool evSet[EV_COUNT]{};
@@ -262,6 +267,8 @@ __global__ void init_state_kernel(DevState* st) {
     st->totalTris = 0ull;
     st->pad[0] = 0u; // error flag
     st->pad[1] = 0u;
+    st->nBig = 0u;
+    st->bigNext = 0u;
 }
 
 /** The state block goes to the host by a store into mapped pinned memory, not by a copy-engine transfer: a cudaMemcpyAsync would queue
@@ -379,15 +386,15 @@ int mms_create(mms_ctx** out, const mms_config* cfg) {
     cudaEventCreateWithFlags(&c->uploadDone, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&c->volReady, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&c->volCopied, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->adoptReady, cudaEventDisableTiming);
     for (auto& a : c->arena) cudaEventCreateWithFlags(&a.consumed, cudaEventDisableTiming);
     c->params.mode = MMS_MODE_P2D_BUMP;
     c->params.sigma = 1.0f;
     c->params.normalize = 1;
     c->params.radscale = 1.0f;
     c->params.gausslim = 3.0f;
-    cudaFuncSetAttribute(density_splat_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SplatShared));
-    cudaFuncSetAttribute(density_splat_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SplatShared));
-    cudaFuncSetAttribute(density_splat_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SplatShared2));
+    cudaFuncSetAttribute(density_splat_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SplatShared));
+    cudaFuncSetAttribute(density_splat_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SplatShared));
     cudaFuncSetAttribute(density_splat3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Splat3Shared));
     cudaFuncSetAttribute(mc_emit_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)emitSmemBytes(false));
     cudaFuncSetAttribute(mc_emit_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)emitSmemBytes(false));
@@ -429,7 +436,7 @@ int mms_destroy(mms_ctx* c) {
         DeviceGuard guard(c->device);
         mms_clear_particles(c);
         for (DevBuf* b : {&c->cellCount, &c->cellStart, &c->cursor, &c->tileSums, &c->recsA, &c->recsB, &c->auxA, &c->auxB, &c->vol,
-                 &c->rgb, &c->segCount, &c->segOffset, &c->meshPos, &c->meshNrm, &c->meshCol, &c->triCount, &c->home, &c->dstate, &c->routeCounts, &c->routeOffsets, &c->routeTile, &c->rangeBuf, &c->dirVol, &c->rmaxBuf})
+                 &c->rgb, &c->segCount, &c->segOffset, &c->meshPos, &c->meshNrm, &c->meshCol, &c->triCount, &c->home, &c->dstate, &c->routeCounts, &c->routeOffsets, &c->routeTile, &c->rangeBuf, &c->dirVol, &c->rmaxBuf, &c->bigCells})
             b->release();
         for (PinBuf* b : {&c->hState, &c->hVol, &c->hRgb, &c->hPos, &c->hNrm, &c->hCol, &c->hHome, &c->hTri, &c->hRoute, &c->hDir}) b->release();
         cudaStreamSynchronize(c->stream);
@@ -441,6 +448,7 @@ int mms_destroy(mms_ctx* c) {
         cudaEventDestroy(c->uploadDone);
         cudaEventDestroy(c->volReady);
         cudaEventDestroy(c->volCopied);
+        cudaEventDestroy(c->adoptReady);
         cudaStreamDestroy(c->copyStream);
         for (auto& ev : c->ev) cudaEventDestroy(ev);
         cudaStreamDestroy(c->ownStream ? c->ownStream : c->stream);
@@ -459,10 +467,11 @@ int mms_set_grid(mms_ctx* c, const mms_grid* g) {
     if (static_cast<unsigned long long>(g->res[0]) * g->res[1] * g->res[2] >= (1ull << 32))
         return c->fail(MMS_ERR_UNSUPPORTED, "volumes of 2^32 voxels or more are not supported");
     c->grid = *g;
+    c->adoptedVol = c->adoptedRgb = nullptr;
     c->haveGrid = true;
     c->z0 = 0, c->nz = g->res[2];
     c->cellZ0 = 0, c->cellNz = g->res[2] - 1;
-    c->haveDensity = c->haveMesh = false;
+    c->haveDensity = c->haveMesh = c->haveCount = false;
     return MMS_OK;
 }
 
@@ -472,7 +481,7 @@ int mms_set_slab(mms_ctx* c, int32_t z0, int32_t nz, int32_t cell_z0, int32_t ce
     if (cell_nz < 0 || cell_z0 < z0 || (cell_nz > 0 && cell_z0 + cell_nz + 1 > z0 + nz))
         return c->fail(MMS_ERR_INVALID, "cell layers must lie inside the slab's planes");
     c->z0 = z0, c->nz = nz, c->cellZ0 = cell_z0, c->cellNz = cell_nz;
-    c->haveDensity = c->haveMesh = false;
+    c->haveDensity = c->haveMesh = c->haveCount = false;
     return MMS_OK;
 }
 
@@ -481,8 +490,6 @@ int mms_set_params(mms_ctx* c, const mms_params* p) {
     if (p->mode != MMS_MODE_P2D_BUMP && p->mode != MMS_MODE_QS_GAUSS) return c->fail(MMS_ERR_INVALID, "unknown mode %d", p->mode);
     if (p->mode == MMS_MODE_P2D_BUMP) {
         if (p->aggregator < 0 || p->aggregator > 2) return c->fail(MMS_ERR_INVALID, "unknown aggregator %d", p->aggregator);
-        if (p->aggregator == 2 && p->sigma > 1.0f)
-            return c->fail(MMS_ERR_UNSUPPORTED, "aggregator 2 (vector field) with sigma > 1 is not implemented");
         if (!(p->sigma > 0.0f)) return c->fail(MMS_ERR_INVALID, "sigma must be > 0");
     } else {
         if (!(p->radscale > 0.0f) || !(p->gausslim > 0.0f)) return c->fail(MMS_ERR_INVALID, "radscale and gausslim must be > 0");
@@ -625,6 +632,7 @@ int mms_compute_density(mms_ctx* c) {
     if (c->nparticles >= (1ull << 32) - 1) return c->fail(MMS_ERR_UNSUPPORTED, "2^32 or more particles per context");
     DeviceGuard guard(c->device);
     cudaStream_t st = c->stream;
+    c->adoptedVol = c->adoptedRgb = nullptr;
     if (c->uploadPending) {
         MMS_CUDA(c, cudaStreamWaitEvent(st, c->uploadDone, 0));
         c->uploadPending = false;
@@ -663,10 +671,12 @@ int mms_compute_density(mms_ctx* c) {
         for (int a = 0; a < 3; ++a) need = std::max(need, static_cast<int>(std::ceil(epsMax / g0.sd[a] + 0.02f)));
         // aggregator 2 keeps four sums per voxel: the register-accumulating gather kernel has them (as the QuickSurf colour sums)
         c->useGather = c->params.mode == MMS_MODE_QS_GAUSS || need > 8 || (c->params.mode == MMS_MODE_P2D_BUMP && c->params.aggregator == 2);
+        // a support box wider than a periodic axis: a voxel receives the same particle through several images (the reference's loop over the
+        // un-wrapped box, ParticlesToDensity.cpp:583-603) -- the gather kernel enumerates them, the splat kernels keep one image per voxel
+        for (int a = 0; a < 3; ++a)
+            if (c->grid.cyclic[a] && 2 * need + 1 > c->grid.res[a]) c->useGather = true;
         if (c->useGather) {
             if (need > 96) return c->fail(MMS_ERR_UNSUPPORTED, "kernel support of %d voxels per side is not supported", need);
-            if (c->params.mode == MMS_MODE_P2D_BUMP && c->params.sigma > 1.0f)
-                return c->fail(MMS_ERR_UNSUPPORTED, "sigma > 1 with supports wider than 8 voxels is not implemented");
             c->cshift = need <= 16 ? 3 : 4; // gather: cells only organise the candidate stream
         } else if (need <= 2) c->cshift = 2;
         else if (need <= 4) c->cshift = 3;
@@ -696,7 +706,7 @@ int mms_compute_density(mms_ctx* c) {
     const unsigned ntiles = static_cast<unsigned>((ncells + kScanTile - 1) / kScanTile);
     if (!c->cellCount.ensure(ncells * 4) || !c->cellStart.ensure((ncells + 1) * 4) || !c->cursor.ensure(ncells * 4) ||
         !c->tileSums.ensure(std::max<size_t>(ntiles, 1) * 4) || !c->recsA.ensure(std::max<size_t>(n, 1) * 16) ||
-        !c->recsB.ensure(std::max<size_t>(n, 1) * 16) || !c->vol.ensure(nvox * 4))
+        !c->recsB.ensure(std::max<size_t>(n, 1) * 16) || !c->vol.ensure(nvox * 4) || !c->bigCells.ensure((n / kBigCell + 2) * 4))
         return c->fail(MMS_ERR_NOMEM, "device allocation failed (cells %zu, particles %zu, voxels %zu)", ncells, n, nvox);
     if (auxN && (!c->auxA.ensure(std::max<size_t>(n, 1) * 4 * auxN) || !c->auxB.ensure(std::max<size_t>(n, 1) * 4 * auxN)))
         return c->fail(MMS_ERR_NOMEM, "device allocation failed (aux)");
@@ -723,9 +733,13 @@ int mms_compute_density(mms_ctx* c) {
     c->arena[c->arenaCur].consumedSet = true;
     if (n > 0) {
         // upper bound n threads; slots >= kept are never claimed, the kernel reads the segment table only
+        DevState* ds = c->dstate.as<DevState>();
         cell_order_kernel<<<gridFor(n, 256, 1 << 30), 256, 0, st>>>(g, c->cellStart.as<unsigned>(), c->recsA.as<float4>(), c->auxA.as<float>(),
-            c->recsB.as<float4>(), c->auxB.as<float>(), auxN, c->dstate.as<DevState>());
-        ++c->launches;
+            c->recsB.as<float4>(), c->auxB.as<float>(), auxN, ds, c->bigCells.as<unsigned>(), &ds->nBig);
+        // crowded cells (rare: coarse grids with wide kernels, clustered data) get a merge sort; no crowded cell -> the blocks leave at once
+        cell_sort_big_kernel<<<c->smCount, kBigThreads, 0, st>>>(c->cellStart.as<unsigned>(), c->recsA.as<float4>(), c->auxA.as<float>(),
+            c->recsB.as<float4>(), c->auxB.as<float>(), auxN, c->bigCells.as<unsigned>(), &ds->nBig, &ds->bigNext);
+        c->launches += 2;
     }
     c->rec(EV_BIN1);
     if (c->useGather) {
@@ -734,10 +748,21 @@ int mms_compute_density(mms_ctx* c) {
         const float* A = c->auxB.as<float>();
         const unsigned* CS = c->cellStart.as<unsigned>();
         DevState* DS = c->dstate.as<DevState>();
-        if (vector) density_gather_kernel<0, true><<<grid, GT_THREADS, 0, st>>>(g, DS, R, A, auxN, CS, c->vol.as<float>(), c->rgb.as<float>(), c->reach);
-        else if (g.mode == 0) density_gather_kernel<0, false><<<grid, GT_THREADS, 0, st>>>(g, DS, R, A, auxN, CS, c->vol.as<float>(), nullptr, c->reach);
-        else if (colour) density_gather_kernel<1, true><<<grid, GT_THREADS, 0, st>>>(g, DS, R, A, auxN, CS, c->vol.as<float>(), c->rgb.as<float>(), c->reach);
-        else density_gather_kernel<1, false><<<grid, GT_THREADS, 0, st>>>(g, DS, R, A, auxN, CS, c->vol.as<float>(), nullptr, c->reach);
+        // GENERAL: several periodic images of a particle can reach one tile, or the reference's integer support box clips the kernel (sigma > 1)
+        bool general = g.mode == 0 && g.sigma > 1.0f;
+        const int gtile[3] = {GT_X, GT_Y, GT_Z};
+        for (int a = 0; a < 3; ++a)
+            if (g.cyc[a] && g.s[a] < gtile[a] + 2 * c->reach + 2) general = true;
+        float* V = c->vol.as<float>();
+        float* C3 = c->rgb.as<float>();
+#define MMS_GATHER(M, COL, out) \
+        (general ? density_gather_kernel<M, COL, true><<<grid, GT_THREADS, 0, st>>>(g, DS, R, A, auxN, CS, V, out, c->reach) \
+                 : density_gather_kernel<M, COL, false><<<grid, GT_THREADS, 0, st>>>(g, DS, R, A, auxN, CS, V, out, c->reach))
+        if (vector) MMS_GATHER(0, true, C3);
+        else if (g.mode == 0) MMS_GATHER(0, false, nullptr);
+        else if (colour) MMS_GATHER(1, true, C3);
+        else MMS_GATHER(1, false, nullptr);
+#undef MMS_GATHER
     } else {
         dim3 grid((g.s[0] + CT_X - 1) / CT_X, (g.s[1] + CT_Y - 1) / CT_Y, (g.nz + CT_Z - 1) / CT_Z);
         // V2 (lanes walk a compacted hit list) where every support box is at most 3x3x3 voxels and one periodic image per particle is enough
@@ -745,7 +770,7 @@ int mms_compute_density(mms_ctx* c) {
         const int tileDim[3] = {CT_X, CT_Y, CT_Z};
         for (int a = 0; a < 3; ++a) // a periodic axis so short that one cell holds particles of two images of the tile: the general kernel
             if (g.cyc[a] && g.s[a] < tileDim[a] + 2 * c->reach + 2 + (1 << g.cshift)) v2 = false;
-        if (v2 && !getenv("MMS_SPLAT_V2")) {
+        if (v2) {
             Splat3Consts kc{};
             for (int a = 0; a < 3; ++a) {
                 kc.isd[a] = 1.0f / g.sd[a];
@@ -756,14 +781,11 @@ int mms_compute_density(mms_ctx* c) {
             density_splat3_kernel<<<grid, CT_THREADS, sizeof(Splat3Shared), st>>>(g, kc, c->dstate.as<DevState>(), c->recsB.as<float4>(),
                 c->cellStart.as<unsigned>(), c->vol.as<float>(), c->reach);
         }
-        else if (v2)
-            density_splat_kernel<0, true><<<grid, CT_THREADS, sizeof(SplatShared2), st>>>(g, c->dstate.as<DevState>(), c->recsB.as<float4>(),
-                c->auxB.as<float>(), auxN, c->cellStart.as<unsigned>(), c->vol.as<float>(), c->reach);
         else if (g.mode == 0)
-            density_splat_kernel<0, false><<<grid, CT_THREADS, sizeof(SplatShared), st>>>(g, c->dstate.as<DevState>(), c->recsB.as<float4>(),
+            density_splat_kernel<0><<<grid, CT_THREADS, sizeof(SplatShared), st>>>(g, c->dstate.as<DevState>(), c->recsB.as<float4>(),
                 c->auxB.as<float>(), auxN, c->cellStart.as<unsigned>(), c->vol.as<float>(), c->reach);
         else
-            density_splat_kernel<1, false><<<grid, CT_THREADS, sizeof(SplatShared), st>>>(g, c->dstate.as<DevState>(), c->recsB.as<float4>(),
+            density_splat_kernel<1><<<grid, CT_THREADS, sizeof(SplatShared), st>>>(g, c->dstate.as<DevState>(), c->recsB.as<float4>(),
                 c->auxB.as<float>(), auxN, c->cellStart.as<unsigned>(), c->vol.as<float>(), c->reach);
     }
     c->haveColour = colour;
@@ -789,20 +811,23 @@ int mms_compute_density(mms_ctx* c) {
     MMS_CUDA(c, cudaMemcpyAsync(c->hState.p, c->dstate.p, sizeof(DevState), cudaMemcpyDeviceToHost, st));
     MMS_CUDA(c, cudaGetLastError());
     c->haveDensity = true;
-    c->haveMesh = false;
+    c->haveMesh = c->haveCount = false; // a count (segment offsets, cached geometry) of the old volume must not be emitted
     return MMS_OK;
 }
 
-static int checkDeviceError(mms_ctx* c) {
-    MMS_CUDA(c, cudaStreamSynchronize(c->stream));
+/** Device-side failures are flagged in DevState::pad[0]; the host sees them wherever it synchronises anyway (volume / range / vector
+ *  field read-back, the triangle count).  Purely device-resident sequences (mms_*_device) end in mms_count_isosurface, which checks. */
+static int deviceErrorFromState(mms_ctx* c) {
     const DevState* hs = c->hState.as<DevState>();
-    if (hs->pad[0] == 3)
-        return c->fail(MMS_ERR_UNSUPPORTED, "more than 65535 particles in one cell of the sort grid (extremely clustered input)");
     if (hs->pad[0] == 2)
-        return c->fail(MMS_ERR_UNSUPPORTED, "wide kernel support on a periodic axis shorter than tile + 2*support is not implemented");
+        return c->fail(MMS_ERR_UNSUPPORTED, "internal error: the single-image gather kernel ran on a short periodic axis");
     if (hs->pad[0] != 0)
         return c->fail(MMS_ERR_UNSUPPORTED, "internal error: the splat kernel's neighbourhood list overflowed (%d cells per axis)", CT_MAXAXIS);
     return MMS_OK;
+}
+static int checkDeviceError(mms_ctx* c) {
+    MMS_CUDA(c, cudaStreamSynchronize(c->stream));
+    return deviceErrorFromState(c);
 }
 
 int mms_get_density_range(mms_ctx* c, float minmax[2]) {
@@ -819,6 +844,7 @@ int mms_get_density_range(mms_ctx* c, float minmax[2]) {
 int mms_normalize(mms_ctx* c, float mn, float mx) {
     if (!c) return MMS_ERR_INVALID;
     if (!c->haveDensity) return c->fail(MMS_ERR_INVALID, "no density has been computed");
+    if (c->adoptedVol) return c->fail(MMS_ERR_INVALID, "an adopted volume belongs to its producer: normalise there");
     DeviceGuard guard(c->device);
     const size_t nvox = static_cast<size_t>(c->grid.res[0]) * c->grid.res[1] * c->nz;
     volatile float range = mx - mn;
@@ -830,7 +856,7 @@ int mms_normalize(mms_ctx* c, float mn, float mx) {
     MMS_CUDA(c, cudaGetLastError());
     c->normalized = true;
     c->volPrefetched = false;
-    c->haveMesh = false;
+    c->haveMesh = c->haveCount = false; // a count (segment offsets, cached geometry) of the old volume must not be emitted
     return MMS_OK;
 }
 
@@ -857,6 +883,7 @@ int mms_density_range_device(mms_ctx* c, float** dev_negmin_max) {
 int mms_normalize_device(mms_ctx* c, const float* dev_negmin_max) {
     if (!c || !dev_negmin_max) return MMS_ERR_INVALID;
     if (!c->haveDensity) return c->fail(MMS_ERR_INVALID, "no density has been computed");
+    if (c->adoptedVol) return c->fail(MMS_ERR_INVALID, "an adopted volume belongs to its producer: normalise there");
     DeviceGuard guard(c->device);
     const size_t nvox = static_cast<size_t>(c->grid.res[0]) * c->grid.res[1] * c->nz;
     c->rec(EV_NRM0);
@@ -867,15 +894,15 @@ int mms_normalize_device(mms_ctx* c, const float* dev_negmin_max) {
     MMS_CUDA(c, cudaGetLastError());
     c->normalized = true;
     c->volPrefetched = false;
-    c->haveMesh = false;
+    c->haveMesh = c->haveCount = false; // a count (segment offsets, cached geometry) of the old volume must not be emitted
     return MMS_OK;
 }
 
 int mms_get_density_device(mms_ctx* c, const float** dv, const float** drgb) {
     if (!c || !dv) return MMS_ERR_INVALID;
     if (!c->haveDensity) return c->fail(MMS_ERR_INVALID, "no density has been computed");
-    *dv = c->vol.as<float>();
-    if (drgb) *drgb = c->haveColour ? c->rgb.as<float>() : nullptr;
+    *dv = c->isoVol();
+    if (drgb) *drgb = c->haveColour ? c->isoRgb() : nullptr;
     return MMS_OK;
 }
 
@@ -892,8 +919,8 @@ int mms_prefetch_density(mms_ctx* c) {
     MMS_CUDA(c, cudaStreamWaitEvent(c->copyStream, c->volReady, 0));
     cudaEventRecord(c->ev[EV_DV0], c->copyStream);
     c->evSet[EV_DV0] = true;
-    MMS_CUDA(c, cudaMemcpyAsync(c->hVol.p, c->vol.p, bytes, cudaMemcpyDeviceToHost, c->copyStream));
-    if (c->haveColour) MMS_CUDA(c, cudaMemcpyAsync(c->hRgb.p, c->rgb.p, bytes * 3, cudaMemcpyDeviceToHost, c->copyStream));
+    MMS_CUDA(c, cudaMemcpyAsync(c->hVol.p, c->isoVol(), bytes, cudaMemcpyDeviceToHost, c->copyStream));
+    if (c->haveColour) MMS_CUDA(c, cudaMemcpyAsync(c->hRgb.p, c->isoRgb(), bytes * 3, cudaMemcpyDeviceToHost, c->copyStream));
     cudaEventRecord(c->ev[EV_DV1], c->copyStream);
     c->evSet[EV_DV1] = true;
     MMS_CUDA(c, cudaEventRecord(c->volCopied, c->copyStream));
@@ -917,8 +944,8 @@ int mms_get_density(mms_ctx* c, const float** hv, const float** hrgb) {
     const bool wantRgb = hrgb && c->haveColour;
     if (wantRgb && !c->hRgb.ensure(bytes * 3)) return c->fail(MMS_ERR_NOMEM, "pinned allocation of %zu bytes failed", bytes * 3);
     c->rec(EV_DV0);
-    MMS_CUDA(c, cudaMemcpyAsync(c->hVol.p, c->vol.p, bytes, cudaMemcpyDeviceToHost, c->stream));
-    if (wantRgb) MMS_CUDA(c, cudaMemcpyAsync(c->hRgb.p, c->rgb.p, bytes * 3, cudaMemcpyDeviceToHost, c->stream));
+    MMS_CUDA(c, cudaMemcpyAsync(c->hVol.p, c->isoVol(), bytes, cudaMemcpyDeviceToHost, c->stream));
+    if (wantRgb) MMS_CUDA(c, cudaMemcpyAsync(c->hRgb.p, c->isoRgb(), bytes * 3, cudaMemcpyDeviceToHost, c->stream));
     c->rec(EV_DV1);
     if (int rc = checkDeviceError(c)) return rc;
     *hv = c->hVol.as<float>();
@@ -931,6 +958,7 @@ int mms_set_density(mms_ctx* c, const float* volume) {
     DeviceGuard guard(c->device);
     const size_t bytes = static_cast<size_t>(c->grid.res[0]) * c->grid.res[1] * c->nz * 4;
     if (!c->vol.ensure(bytes)) return c->fail(MMS_ERR_NOMEM, "device allocation of %zu bytes failed", bytes);
+    c->adoptedVol = c->adoptedRgb = nullptr;
     MMS_CUDA(c, cudaMemcpyAsync(c->vol.p, volume, bytes, cudaMemcpyDefault, c->stream));
     init_state_kernel<<<1, 1, 0, c->stream>>>(c->dstate.as<DevState>());
     ++c->launches;
@@ -938,7 +966,31 @@ int mms_set_density(mms_ctx* c, const float* volume) {
     c->haveDensity = true;
     c->haveColour = false;
     c->haveVector = false;
-    c->haveMesh = false;
+    c->haveMesh = c->haveCount = false; // a count (segment offsets, cached geometry) of the old volume must not be emitted
+    c->volPrefetched = false;
+    return MMS_OK;
+}
+
+int mms_adopt_density(mms_ctx* c, mms_ctx* p) {
+    if (!c || !p || c == p) return MMS_ERR_INVALID;
+    if (!p->haveDensity) return c->fail(MMS_ERR_INVALID, "the producer context has no density");
+    if (p->device != c->device) return c->fail(MMS_ERR_INVALID, "mms_adopt_density: the two contexts live on different devices (%d, %d)", c->device, p->device);
+    DeviceGuard guard(c->device);
+    c->grid = p->grid;
+    c->haveGrid = true;
+    c->z0 = p->z0, c->nz = p->nz, c->cellZ0 = p->cellZ0, c->cellNz = p->cellNz;
+    c->adoptedVol = p->adoptedVol ? p->adoptedVol : p->vol.as<float>();
+    c->haveColour = p->haveColour;
+    c->adoptedRgb = p->haveColour ? (p->adoptedVol ? p->adoptedRgb : p->rgb.as<float>()) : nullptr;
+    c->haveVector = false;
+    // everything the producer has enqueued so far (its density kernels, normalisation) comes first
+    MMS_CUDA(c, cudaEventRecord(c->adoptReady, p->stream));
+    MMS_CUDA(c, cudaStreamWaitEvent(c->stream, c->adoptReady, 0));
+    init_state_kernel<<<1, 1, 0, c->stream>>>(c->dstate.as<DevState>());
+    ++c->launches;
+    MMS_CUDA(c, cudaMemcpyAsync(c->hState.p, c->dstate.p, sizeof(DevState), cudaMemcpyDeviceToHost, c->stream));
+    c->haveDensity = true;
+    c->haveMesh = c->haveCount = false;
     c->volPrefetched = false;
     return MMS_OK;
 }
@@ -997,11 +1049,14 @@ int mms_count_isosurface(mms_ctx* c, float iso, uint64_t* ntris) {
     m.iso = iso;
     c->mcGeo = m;
     c->ntris = 0;
-    c->haveCount = true;
+    c->haveCount = false; // set once the count has run and the device reported no error
     c->haveMesh = false;
     if (ntris) *ntris = 0;
     c->rec(EV_MC0);
-    if (m.cnz <= 0) return MMS_OK;
+    if (m.cnz <= 0) {
+        c->haveCount = true; // an empty slab: nothing to count, nothing to emit
+        return MMS_OK;
+    }
     const size_t nseg = static_cast<size_t>(m.nsegx) * m.cy * m.cnz;
     if (nseg >= (1ull << 32) - 1) return c->fail(MMS_ERR_UNSUPPORTED, "too many cell segments");
     const unsigned ntiles = static_cast<unsigned>((nseg + kScanTile - 1) / kScanTile);
@@ -1029,11 +1084,11 @@ int mms_count_isosurface(mms_ctx* c, float iso, uint64_t* ntris) {
         t.iso = iso;
         c->mtGeo = t;
         dim3 grid(m.nsegx, (m.cy + MT_THREADS / 32 - 1) / (MT_THREADS / 32), m.cnz);
-        mt_count_kernel<<<grid, MT_THREADS, 0, st>>>(t, c->vol.as<float>(), c->segCount.as<unsigned>(), tri);
+        mt_count_kernel<<<grid, MT_THREADS, 0, st>>>(t, c->isoVol(), c->segCount.as<unsigned>(), tri);
     } else {
         if (tri) MMS_CUDA(c, cudaMemsetAsync(tri, 0, static_cast<size_t>(m.cx) * m.cy * m.cnz, st)); // the kernel writes the non-empty cells only
         dim3 grid((m.nsegx + CN_SEGS - 1) / CN_SEGS, (m.cy + CN_ROWS - 1) / CN_ROWS, (m.cnz + CN_LAYERS - 1) / CN_LAYERS);
-        mc_count_kernel<<<grid, MC_THREADS, 0, st>>>(m, c->vol.as<float>(), c->segCount.as<unsigned>(), tri);
+        mc_count_kernel<<<grid, MC_THREADS, 0, st>>>(m, c->isoVol(), c->segCount.as<unsigned>(), tri);
     }
     ++c->launches;
     DevState* ds = c->dstate.as<DevState>();
@@ -1042,7 +1097,10 @@ int mms_count_isosurface(mms_ctx* c, float iso, uint64_t* ntris) {
     publish_state_kernel<<<1, 1, 0, st>>>(c->dstate.as<DevState>(), c->hState.as<DevState>());
     ++c->launches;
     MMS_CUDA(c, cudaStreamSynchronize(st)); // the one host round trip: the mesh size decides the allocation
+    // the state block also carries the density kernels' error flag: a truncated volume must not become a mesh
+    if (int rc = deviceErrorFromState(c)) return rc;
     c->ntris = c->hState.as<DevState>()->totalTris;
+    c->haveCount = true;
     if (ntris) *ntris = c->ntris;
     return MMS_OK;
 }
@@ -1073,7 +1131,7 @@ int mms_emit_isosurface(mms_ctx* c, float* pos, float* nrm, float* col, uint64_t
         c->rec(EV_EMIT0);
         if (c->countMode == MMS_ISO_MARCHING_TETS) {
             dim3 grid(m.nsegx, (m.cy + MT_THREADS / 32 - 1) / (MT_THREADS / 32), m.cnz);
-            mt_emit_kernel<<<grid, MT_THREADS, 0, st>>>(c->mtGeo, c->vol.as<float>(), c->segOffset.as<unsigned>(), P, N);
+            mt_emit_kernel<<<grid, MT_THREADS, 0, st>>>(c->mtGeo, c->isoVol(), c->segOffset.as<unsigned>(), P, N);
             ++c->launches;
             c->rec(EV_MC1);
             MMS_CUDA(c, cudaGetLastError());
@@ -1082,21 +1140,22 @@ int mms_emit_isosurface(mms_ctx* c, float* pos, float* nrm, float* col, uint64_t
             return MMS_OK;
         }
         CUtensorMap map{};
-        const bool tma = makeVolumeTensorMap(&map, c->vol.as<float>(), m.sx, m.sy, m.nzPlanes);
-        const float* V = c->vol.as<float>();
+        const bool tma = makeVolumeTensorMap(&map, c->isoVol(), m.sx, m.sy, m.nzPlanes);
+        const float* V = c->isoVol();
+        const float* RGB = c->isoRgb();
         const unsigned* S = c->segOffset.as<unsigned>();
         if (getenv("MMS_EMIT_V4")) {
             dim3 g4(m.nsegx, (m.cy + v4::EY - 1) / v4::EY, (m.cnz + v4::EM_STEPS * v4::EZ - 1) / (v4::EM_STEPS * v4::EZ));
             if (c->haveColour) {
-                if (tma) v4::mc_emit_v4_kernel<true, true><<<g4, MC_THREADS, emitV4SmemBytes(true), st>>>(m, map, V, c->rgb.as<float>(), S, P, N, C);
-                else v4::mc_emit_v4_kernel<true, false><<<g4, MC_THREADS, emitV4SmemBytes(true), st>>>(m, map, V, c->rgb.as<float>(), S, P, N, C);
+                if (tma) v4::mc_emit_v4_kernel<true, true><<<g4, MC_THREADS, emitV4SmemBytes(true), st>>>(m, map, V, RGB, S, P, N, C);
+                else v4::mc_emit_v4_kernel<true, false><<<g4, MC_THREADS, emitV4SmemBytes(true), st>>>(m, map, V, RGB, S, P, N, C);
             } else {
                 if (tma) v4::mc_emit_v4_kernel<false, true><<<g4, MC_THREADS, emitV4SmemBytes(false), st>>>(m, map, V, nullptr, S, P, N, nullptr);
                 else v4::mc_emit_v4_kernel<false, false><<<g4, MC_THREADS, emitV4SmemBytes(false), st>>>(m, map, V, nullptr, S, P, N, nullptr);
             }
         } else if (c->haveColour) {
-            if (tma) mc_emit_kernel<true, true><<<gridE, MC_THREADS, emitSmemBytes(true), st>>>(m, map, V, c->rgb.as<float>(), S, P, N, C);
-            else mc_emit_kernel<true, false><<<gridE, MC_THREADS, emitSmemBytes(true), st>>>(m, map, V, c->rgb.as<float>(), S, P, N, C);
+            if (tma) mc_emit_kernel<true, true><<<gridE, MC_THREADS, emitSmemBytes(true), st>>>(m, map, V, RGB, S, P, N, C);
+            else mc_emit_kernel<true, false><<<gridE, MC_THREADS, emitSmemBytes(true), st>>>(m, map, V, RGB, S, P, N, C);
         } else {
             if (tma) mc_emit_kernel<false, true><<<gridE, MC_THREADS, emitSmemBytes(false), st>>>(m, map, V, nullptr, S, P, N, nullptr);
             else mc_emit_kernel<false, false><<<gridE, MC_THREADS, emitSmemBytes(false), st>>>(m, map, V, nullptr, S, P, N, nullptr);
@@ -1115,7 +1174,7 @@ int mms_set_isosurface_mode(mms_ctx* c, int32_t mode) {
     if (mode != MMS_ISO_MARCHING_CUBES && mode != MMS_ISO_MARCHING_TETS) return c->fail(MMS_ERR_INVALID, "unknown isosurface mode %d", mode);
     c->isoMode = mode;
     c->haveCount = false;
-    c->haveMesh = false;
+    c->haveMesh = c->haveCount = false; // a count (segment offsets, cached geometry) of the old volume must not be emitted
     return MMS_OK;
 }
 

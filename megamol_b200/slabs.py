@@ -325,9 +325,12 @@ class SlabJob:
         if self.rank == 0:
             need = total * 36
             if R["cap"] < need:
-                for k in ("pos", "nrm"):
-                    if R[k]:
-                        L.mms_device_free(self.local, R[k])
+                # the other ranks still map the current buffers (cudaIpcOpenMemHandle) and close those mappings only when they see
+                # the new generation below: freeing an exported allocation before its importers have closed it is undefined
+                # behaviour, so the buffers retire for one generation and are freed at the NEXT regrow (or at close, after a barrier)
+                for ptr in R.get("retired", []):
+                    L.mms_device_free(self.local, ptr)
+                R["retired"] = [R[k] for k in ("pos", "nrm") if R[k]]
                 cap = need + need // 8 + 256
                 hb = bytearray(144)
                 for i, k in enumerate(("pos", "nrm")):
@@ -561,10 +564,17 @@ class SlabJob:
             self.torch.cuda.synchronize()
             import torch.distributed as dist
             dist.barrier()
-            for k in ("pos", "nrm"):
-                if R[k]:
-                    (self.surf.L.mms_device_free if self.rank == 0 else self.surf.L.mms_ipc_close)(self.local, R[k])
-                    R[k] = None
+            if self.rank != 0:  # importers close their mappings first ...
+                for k in ("pos", "nrm"):
+                    if R[k]:
+                        self.surf.L.mms_ipc_close(self.local, R[k])
+                        R[k] = None
+            dist.barrier()
+            if self.rank == 0:  # ... then the exporter frees (current and retired buffers)
+                for ptr in [R[k] for k in ("pos", "nrm") if R[k]] + R.get("retired", []):
+                    self.surf.L.mms_device_free(self.local, ptr)
+                R["pos"] = R["nrm"] = None
+                R["retired"] = []
         self.surf.close()
         if self.world > 1 and destroy_group:
             import torch.distributed as dist

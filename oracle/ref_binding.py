@@ -52,6 +52,8 @@ class Harness:
         L.mmh_pull_mesh.argtypes = [C.c_void_p, C.c_uint, C.c_float, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
                                     C.POINTER(C.c_double)]
         L.mmh_copy_mesh.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.mmh_pull_mesh2.argtypes = L.mmh_pull_mesh.argtypes
+        L.mmh_select_mesh.argtypes = [C.c_void_p, C.c_int]
         L.mmh_mc_tables.argtypes = [C.c_void_p] * 5
         L.mmh_set_directions.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint]
         L.mmh_pull_grid_particles.argtypes = [C.c_void_p, C.c_uint, C.POINTER(C.c_uint64), C.POINTER(C.c_float), C.c_void_p, C.c_void_p,
@@ -210,11 +212,22 @@ class Harness:
         nm = [names.raw[32 * c:32 * c + 32].split(b"\0")[0].decode() for c in range(cols)]
         return {"columns": cols, "rows": rows, "datahash": int(dims[2]), "names": nm, "ranges": ranges, "data": data}
 
-    def pull_mesh(self, isoval: float, copy: bool = True, colours: bool = False):
+    def reread_mesh(self, which: int, nverts: int):
+        """the mesh isosurface module `which` handed out last, read AGAIN through the pointers it left in its CallTriMeshData"""
+        if self.lib.mmh_select_mesh(self.h, int(which)):
+            raise RuntimeError("no mesh has been pulled from that module")
+        pos = np.empty((nverts, 3), np.float32)
+        nrm = np.empty((nverts, 3), np.float32)
+        if self.lib.mmh_copy_mesh(self.h, pos.ctypes.data, nrm.ctypes.data, None):
+            raise RuntimeError("mmh_copy_mesh failed")
+        return pos, nrm
+
+    def pull_mesh(self, isoval: float, copy: bool = True, colours: bool = False, which: int = 0):
         nv = C.c_uint64()
         nt = C.c_uint64()
         ms = C.c_double()
-        rc = self.lib.mmh_pull_mesh(self.h, self.frame, float(isoval), C.byref(nv), C.byref(nt), C.byref(ms))
+        fn = self.lib.mmh_pull_mesh2 if which else self.lib.mmh_pull_mesh
+        rc = fn(self.h, self.frame, float(isoval), C.byref(nv), C.byref(nt), C.byref(ms))
         if rc:
             raise RuntimeError(f"mmh_pull_mesh rc={rc}")
         res = {"nverts": nv.value, "ntris": nt.value, "ms": ms.value}

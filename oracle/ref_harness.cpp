@@ -180,7 +180,8 @@ private:
 /** The consumer end: what a renderer would be. */
 class Sink : public core::Module {
 public:
-    Sink() : volSlot("inVolume", "volume"), meshSlot("inMesh", "mesh"), gridSlot("inGrid", "grid particles"), infoSlot("inInfo", "table") {
+    Sink() : volSlot("inVolume", "volume"), meshSlot("inMesh", "mesh"), mesh2Slot("inMesh2", "mesh of a second isosurface module"),
+             gridSlot("inGrid", "grid particles"), infoSlot("inInfo", "table") {
         gridSlot.SetCompatibleCall<geocalls::MultiParticleDataCallDescription>();
         MakeSlotAvailable(&gridSlot);
         infoSlot.SetCompatibleCall<datatools::table::TableDataCallDescription>();
@@ -189,9 +190,11 @@ public:
         MakeSlotAvailable(&volSlot);
         meshSlot.SetCompatibleCall<geocalls_gl::CallTriMeshDataGLDescription>();
         MakeSlotAvailable(&meshSlot);
+        mesh2Slot.SetCompatibleCall<geocalls_gl::CallTriMeshDataGLDescription>();
+        MakeSlotAvailable(&mesh2Slot);
     }
     ~Sink() override { Release(); }
-    core::CallerSlot volSlot, meshSlot, gridSlot, infoSlot;
+    core::CallerSlot volSlot, meshSlot, mesh2Slot, gridSlot, infoSlot;
 
 protected:
     bool create() override { return true; }
@@ -217,9 +220,11 @@ struct Harness {
     std::shared_ptr<MoleculeSource> mol = std::make_shared<MoleculeSource>();
     std::shared_ptr<P2DModule> p2d = std::make_shared<P2DModule>();
     std::shared_ptr<IsoModule> iso = std::make_shared<IsoModule>();
+    std::shared_ptr<IsoModule> iso2 = std::make_shared<IsoModule>(); // a second consumer of the same density module
     std::shared_ptr<Sink> sink = std::make_shared<Sink>();
     std::vector<std::unique_ptr<core::Call>> calls;
     const geocalls_gl::CallTriMeshDataGL::Mesh* mesh = nullptr;
+    const geocalls_gl::CallTriMeshDataGL::Mesh* meshOf[2] = {nullptr, nullptr};
     bool ok = false;
 
     /** molecule: feed the density module from the MolecularDataCall source instead of the particle source. */
@@ -229,19 +234,23 @@ struct Harness {
         src->setName("src");
         p2d->setName("p2d");
         iso->setName("iso");
+        iso2->setName("iso2");
         sink->setName("sink");
         mol->setName("mol");
         root->AddChild(mol);
         root->AddChild(src);
         root->AddChild(p2d);
         root->AddChild(iso);
+        root->AddChild(iso2);
         root->AddChild(sink);
-        ok = src->Create() && mol->Create() && p2d->Create() && iso->Create() && sink->Create();
+        ok = src->Create() && mol->Create() && p2d->Create() && iso->Create() && iso2->Create() && sink->Create();
         if (molecule) ok = ok && connect<protein_calls::MolecularDataCallDescription>(*p2d, "inData", *mol, "outData", calls);
         else ok = ok && connect<geocalls::MultiParticleDataCallDescription>(*p2d, "inData", *src, "outData", calls);
         ok = ok && connect<geocalls::VolumetricDataCallDescription>(*iso, "inData", *p2d, "outData", calls);
         ok = ok && connect<geocalls::VolumetricDataCallDescription>(*sink, "inVolume", *p2d, "outData", calls);
         ok = ok && connect<geocalls_gl::CallTriMeshDataGLDescription>(*sink, "inMesh", *iso, "outData", calls);
+        ok = ok && connect<geocalls::VolumetricDataCallDescription>(*iso2, "inData", *p2d, "outData", calls);
+        ok = ok && connect<geocalls_gl::CallTriMeshDataGLDescription>(*sink, "inMesh2", *iso2, "outData", calls);
         ok = ok && connect<geocalls::MultiParticleDataCallDescription>(*sink, "inGrid", *p2d, "outParticles", calls);
         ok = ok && connect<datatools::table::TableDataCallDescription>(*sink, "inInfo", *p2d, "outInfo", calls);
     }
@@ -249,6 +258,7 @@ struct Harness {
         // callers first, so that no slot is left pointing at a destroyed call
         sink->volSlot.ConnectCall(nullptr);
         sink->meshSlot.ConnectCall(nullptr);
+        sink->mesh2Slot.ConnectCall(nullptr);
         sink->gridSlot.ConnectCall(nullptr);
         sink->infoSlot.ConnectCall(nullptr);
     }
@@ -466,24 +476,40 @@ int mmh_pull_info(void* hv, uint64_t dims[3], float* data, char* names, float* r
 }
 
 /** Pulls the mesh like TriSoupRenderer would: CallTriMeshData GetExtent(1) then GetData(0). */
-int mmh_pull_mesh(void* hv, unsigned frame_id, float isoval, uint64_t* nverts, uint64_t* ntris, double* ms) {
-    auto* h = static_cast<Harness*>(hv);
-    if (!setParam<core::param::FloatParam>(*h->iso, "isoval", isoval)) return -1;
-    auto* t = h->sink->meshSlot.CallAs<geocalls_gl::CallTriMeshDataGL>();
+static int pullMeshOf(Harness* h, int which, unsigned frame_id, float isoval, uint64_t* nverts, uint64_t* ntris, double* ms) {
+    auto& module = which == 0 ? h->iso : h->iso2;
+    if (!setParam<core::param::FloatParam>(*module, "isoval", isoval)) return -1;
+    auto* t = (which == 0 ? h->sink->meshSlot : h->sink->mesh2Slot).CallAs<geocalls_gl::CallTriMeshDataGL>();
     if (!t) return -2;
     t->SetFrameID(frame_id, true);
     const double t0 = nowMs();
     if (!(*t)(1)) return -3;
     if (!(*t)(0)) return -4;
     if (ms) *ms = nowMs() - t0;
-    h->mesh = nullptr;
+    h->meshOf[which] = nullptr;
     *nverts = 0;
     *ntris = 0;
     if (t->Count() >= 1 && t->Objects()) {
-        h->mesh = &t->Objects()[0];
-        *nverts = h->mesh->GetVertexCount();
-        *ntris = h->mesh->GetTriCount();
+        h->meshOf[which] = &t->Objects()[0];
+        *nverts = h->meshOf[which]->GetVertexCount();
+        *ntris = h->meshOf[which]->GetTriCount();
     }
+    h->mesh = h->meshOf[which];
+    return 0;
+}
+
+int mmh_pull_mesh(void* hv, unsigned frame_id, float isoval, uint64_t* nverts, uint64_t* ntris, double* ms) {
+    return pullMeshOf(static_cast<Harness*>(hv), 0, frame_id, isoval, nverts, ntris, ms);
+}
+/** The same through the SECOND isosurface module connected to the same density module (its own isoval). */
+int mmh_pull_mesh2(void* hv, unsigned frame_id, float isoval, uint64_t* nverts, uint64_t* ntris, double* ms) {
+    return pullMeshOf(static_cast<Harness*>(hv), 1, frame_id, isoval, nverts, ntris, ms);
+}
+/** Which mesh mmh_copy_mesh reads: the one last handed out by isosurface module 0 or 1 (pointers as the module left them). */
+int mmh_select_mesh(void* hv, int which) {
+    auto* h = static_cast<Harness*>(hv);
+    if (which < 0 || which > 1 || !h->meshOf[which]) return -1;
+    h->mesh = h->meshOf[which];
     return 0;
 }
 

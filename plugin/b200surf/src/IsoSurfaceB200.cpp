@@ -97,32 +97,42 @@ bool IsoSurfaceB200::outExtentCallback(core::Call& caller) {
 bool IsoSurfaceB200::buildMesh(VolumetricDataCall* cvd, float iso) {
     const auto t0 = std::chrono::high_resolution_clock::now();
     const int algorithm = this->algorithmSlot.Param<core::param::EnumParam>()->Value();
-    mms_ctx* use = nullptr;
-    // device-resident hand-off: is the callee a ParticlesToDensityB200 whose context holds exactly this volume?
+    // device-resident hand-off: is the callee a ParticlesToDensityB200 whose context holds exactly this volume?  Then this module's OWN
+    // context adopts that volume by reference (mms_adopt_density): no host round trip, and the mesh lives in this module's buffers --
+    // several IsoSurfaceB200 behind one producer, or a producer that recomputes, cannot touch a mesh this module has handed out.
+    mms_ctx* producer = nullptr;
+    int device = this->deviceSlot.Param<core::param::IntParam>()->Value();
     const core::CalleeSlot* callee = cvd->PeekCalleeSlot();
     if (callee != nullptr) {
         auto parent = callee->Parent();
         auto* p2d = dynamic_cast<const ParticlesToDensityB200*>(parent.get());
-        if (p2d != nullptr && p2d->Context() != nullptr && p2d->VolumeHash() == cvd->DataHash())
-            use = p2d->Context();
+        if (p2d != nullptr && p2d->Context() != nullptr && p2d->VolumeHash() == cvd->DataHash()) {
+            producer = p2d->Context();
+            device = p2d->Device();
+        }
     }
-    if (use == nullptr) {
+    if (this->ctx == nullptr || this->ctxDevice != device) {
+        if (this->ctx != nullptr)
+            mms_destroy(this->ctx);
+        this->ctx = nullptr;
+        mms_config cfg{device, 0};
+        if (mms_create(&this->ctx, &cfg) != MMS_OK) {
+            Log::DefaultLog.WriteError("IsoSurfaceB200: %s", mms_last_error(nullptr));
+            return false;
+        }
+        this->ctxDevice = device;
+    }
+    mms_ctx* use = this->ctx;
+    if (producer != nullptr) {
+        if (mms_adopt_density(this->ctx, producer) != MMS_OK) {
+            Log::DefaultLog.WriteError("IsoSurfaceB200: %s", mms_last_error(this->ctx));
+            return false;
+        }
+    } else {
         const auto* md = cvd->GetMetadata();
         if (md == nullptr || cvd->GetData() == nullptr || md->Components != 1 || md->GridType != geocalls::GridType_t::CARTESIAN) {
             Log::DefaultLog.WriteError("IsoSurfaceB200: need a host-resident single-component cartesian float volume");
             return false;
-        }
-        const int device = this->deviceSlot.Param<core::param::IntParam>()->Value();
-        if (this->ctx == nullptr || this->ctxDevice != device) {
-            if (this->ctx != nullptr)
-                mms_destroy(this->ctx);
-            this->ctx = nullptr;
-            mms_config cfg{device, 0};
-            if (mms_create(&this->ctx, &cfg) != MMS_OK) {
-                Log::DefaultLog.WriteError("IsoSurfaceB200: %s", mms_last_error(nullptr));
-                return false;
-            }
-            this->ctxDevice = device;
         }
         mms_grid grid{};
         for (int a = 0; a < 3; ++a) {
@@ -140,7 +150,6 @@ bool IsoSurfaceB200::buildMesh(VolumetricDataCall* cvd, float iso) {
             Log::DefaultLog.WriteError("IsoSurfaceB200: %s", mms_last_error(this->ctx));
             return false;
         }
-        use = this->ctx;
     }
     uint64_t nverts = 0;
     const float *pos = nullptr, *nrm = nullptr, *col = nullptr; // col stays NULL unless the volume carries colours (QuickSurf mode)
@@ -157,7 +166,7 @@ bool IsoSurfaceB200::buildMesh(VolumetricDataCall* cvd, float iso) {
     this->mesh.SetTriangleData(0, static_cast<unsigned int*>(nullptr), false);
     const std::chrono::duration<float, std::milli> ms = std::chrono::high_resolution_clock::now() - t0;
     Log::DefaultLog.WriteInfo("IsoSurfaceB200: %llu triangles at iso %f took %f ms (%s volume).", static_cast<unsigned long long>(nverts / 3), iso,
-        ms.count(), use == this->ctx ? "uploaded" : "device-resident");
+        ms.count(), producer == nullptr ? "uploaded" : "device-resident");
     return true;
 }
 

@@ -49,6 +49,10 @@ public:
     std::size_t VolumeHash() const {
         return this->datahash;
     }
+    /** CUDA device ordinal of Context(). */
+    int Device() const {
+        return this->ctxDevice;
+    }
     /** true if the context also holds a density-weighted RGB volume (QuickSurf mode with colour). */
     bool HasColour() const {
         return this->hasColour;

@@ -105,6 +105,30 @@ def test_mesh_call_contract(ref, plug, oracle):
     assert m3["nverts"] != m["nverts"]
 
 
+def test_two_isosurface_modules_share_one_density_module(plug):
+    """Two IsoSurfaceB200 behind one ParticlesToDensityB200 (different iso values): each keeps its mesh in its own context
+    (mms_adopt_density takes only the device volume from the producer).  The mesh module 0 handed out stays intact -- its pointers are
+    read again -- after module 1 has extracted another surface from the same producer, and after the producer has recomputed."""
+    n, box, res = 6000, 10.0, (32, 28, 24)
+    xyz = synth.uniform_box(n, box, seed=23)
+    lists = [dict(vtx=xyz, vtx_type=rb.VERT_FLOAT_XYZ, count=n, global_radius=1.0)]
+    feed(plug, lists, (0, 0, 0, box, box, box), res, cyclic=(True,) * 3, normalize=True)
+    plug.pull_volume(copy=False)
+    a = plug.pull_mesh(0.3, which=0)
+    b = plug.pull_mesh(0.6, which=1)
+    assert a["nverts"] > 0 and b["nverts"] > 0 and a["nverts"] != b["nverts"]
+    pos, nrm = plug.reread_mesh(0, a["nverts"])
+    assert np.array_equal(pos, a["pos"]) and np.array_equal(nrm, a["nrm"]), "module 1 overwrote the mesh module 0 had handed out"
+    # the producer recomputes (new particles) and only module 1 pulls again: module 0's pointers still hold its old mesh
+    xyz2 = synth.uniform_box(n, box, seed=24)
+    plug.set_particles([dict(vtx=xyz2, vtx_type=rb.VERT_FLOAT_XYZ, count=n, global_radius=1.0)], (0, 0, 0, box, box, box))
+    plug.pull_volume(copy=False)
+    b2 = plug.pull_mesh(0.6, which=1)
+    assert b2["nverts"] != b["nverts"] or not np.array_equal(b2["pos"], b["pos"])
+    pos, nrm = plug.reread_mesh(0, a["nverts"])
+    assert np.array_equal(pos, a["pos"]) and np.array_equal(nrm, a["nrm"])
+
+
 def test_for_surface_reconstruction_bbox(ref, plug):
     xyz = synth.uniform_box(2000, 6.0, seed=17)
     lists = [dict(vtx=xyz, vtx_type=rb.VERT_FLOAT_XYZ, count=2000, global_radius=0.7)]
