@@ -56,7 +56,12 @@ enum mms_colour_type {
 /* Density semantics. */
 enum mms_mode {
     MMS_MODE_P2D_BUMP = 0, /* datatools::ParticlesToDensity: compact bump RBF, support box from the home voxel */
-    MMS_MODE_QS_GAUSS = 1  /* QuickSurf: Gaussian exp2(d^2 w), radial cut-off gausslim*radscale*r, optional colour */
+    MMS_MODE_QS_GAUSS = 1, /* QuickSurf: Gaussian exp2(d^2 w), radial cut-off gausslim*radscale*r, optional colour */
+    MMS_MODE_QS_GAUSS_REFCELLS = 2 /* the same Gaussian with the candidate set of protein_cuda's CUDAQuickSurf (CUDAQuickSurf.cu:232-253):
+                                      NO radial cut-off, every atom of the acceleration cells (size max(gausslim*radscale*rmax,
+                                      spacing)) around the voxel's 8x8x8 block contributes.  Reproduces the reference's density up to
+                                      the fp32 summation order -- including its dependence on the block tiling -- at ~15x the pair
+                                      evaluations of mode 1; needs a uniform grid spacing and particles inside the grid. */
 };
 
 typedef struct mms_ctx mms_ctx;

@@ -60,7 +60,7 @@ __device__ __forceinline__ Binned binParticle(const Geo& g, const ListDev& l, un
     } else if (g.mode == 0) {
         fx = filterSize(r, g.sd[0]), fy = filterSize(r, g.sd[1]), fz = filterSize(r, g.sd[2]);
     } else {
-        const float cut = g.gausslim * g.radscale * r;
+        const float cut = g.qsAc > 0.0f ? 2.0f * g.qsAc : g.gausslim * g.radscale * r; // reference cells: an atom two cell sizes from a tile can be its candidate
         fx = filterSize(cut, g.sd[0]) + 1, fy = filterSize(cut, g.sd[1]) + 1, fz = filterSize(cut, g.sd[2]) + 1;
     }
     if (g.mode == 0 && !(supportHasNode(q.p.x, q.p.w, g, 0) && supportHasNode(q.p.y, q.p.w, g, 1) && supportHasNode(q.p.z, q.p.w, g, 2))) return q;

@@ -21,6 +21,9 @@ struct Geo {
     int mode;     // 0 P2D bump, 1 QuickSurf Gaussian
     float radscale, gausslim;
     int colour;
+    // MMS_MODE_QS_GAUSS_REFCELLS: the reference's acceleration grid (CUDAQuickSurf.cu:1259-1282); qsAc == 0: radial cut-off
+    float qsAc, qsInvAc;
+    int qsCells[3];
 };
 
 /** One particle list on the device (mirror of mms_list with device pointers). */

@@ -777,12 +777,16 @@ struct GatherShared {
  *  the axis, where a voxel receives the same particle more than once, exactly as the reference's loop over the un-wrapped box does
  *  (ParticlesToDensity.cpp:577-613) -- and, in bump mode, the reference's integer support box home +- ceil(rad/sliceDist), which
  *  clips the kernel when sigma > 1 (:573-579).  Every (particle, image) pair is a candidate of its own, in (particle, image z, y, x)
- *  order.  !GENERAL: at most one image per particle and tile, no box test (sigma <= 1: the box never clips). */
+ *  order.  !GENERAL: at most one image per particle and tile, no box test (sigma <= 1: the box never clips).
+ *  MODE 1 (Gaussian, non-periodic) && GENERAL = MMS_MODE_QS_GAUSS_REFCELLS: the candidate set of the reference's CUDAQuickSurf instead
+ *  of the radial cut-off -- every atom whose acceleration cell lies in the cell range of the voxel's 8x8x8 block
+ *  (CUDAQuickSurf.cu:232-253), coordinates relative to the grid origin like the reference's (QuickSurf.cpp:553-556). */
 template<int MODE, bool COLOUR, bool GENERAL>
 __global__ void __launch_bounds__(GT_THREADS, 2) density_gather_kernel(Geo g, DevState* st, const float4* __restrict__ recs,
     const float* __restrict__ aux, int auxN, const unsigned* __restrict__ cellStart, float* __restrict__ vol, float* __restrict__ rgb,
     int reach) {
     __shared__ GatherShared sh;
+    constexpr bool QSREF = MODE == 1 && GENERAL;
     const int tid = threadIdx.x, lane = tid & 31, ty = tid >> 5;
     const int t0x = (int)blockIdx.x * GT_X, t0y = (int)blockIdx.y * GT_Y, t0z = g.z0 + (int)blockIdx.z * GT_Z;
     const int t1x = min(t0x + GT_X, g.s[0]) - 1, t1y = min(t0y + GT_Y, g.s[1]) - 1, t1z = min(t0z + GT_Z, g.z0 + g.nz) - 1;
@@ -811,12 +815,23 @@ __global__ void __launch_bounds__(GT_THREADS, 2) density_gather_kernel(Geo g, De
     // warp = one row of the tile (an 8 x 4 patch per warp has better lane efficiency -- 63 % instead of 45 % -- but unbalances the warps
     // between the per-chunk barriers: 26.2 ms instead of 23.2 ms on C3)
     const int vxI = t0x + lane, vyI = t0y + ty;
-    const float vx = __fadd_rn(__fmul_rn((float)vxI, g.sd[0]), g.mn[0]);
-    const float vy = __fadd_rn(__fmul_rn((float)vyI, g.sd[1]), g.mn[1]);
+    // QSREF: coorx = gridspacing * xindex, relative to the grid origin (CUDAQuickSurf.cu:255-257)
+    const float vx = QSREF ? __fmul_rn(g.sd[0], (float)vxI) : __fadd_rn(__fmul_rn((float)vxI, g.sd[0]), g.mn[0]);
+    const float vy = QSREF ? __fmul_rn(g.sd[1], (float)vyI) : __fadd_rn(__fmul_rn((float)vyI, g.sd[1]), g.mn[1]);
+    // QSREF: acceleration-cell ranges of the reference's 8x8x8 thread blocks this tile covers (its own expressions, :232-253)
+    auto abMin = [&](int b, int) { const int v = __float2int_rz(__fmul_rn(__fmaf_rn((float)(b * 8), g.sd[0], -g.qsAc), g.qsInvAc)); return v < 0 ? 0 : v; };
+    auto abMax = [&](int b, int nc) { const int v = __float2int_rz(__fmul_rn(__fmaf_rn((float)((b + 1) * 8), g.sd[0], g.qsAc), g.qsInvAc)); return v >= nc - 1 ? nc - 1 : v; };
+    int refLo[3] = {0, 0, 0}, refHi[3] = {0, 0, 0}, myXlo = 0, myXhi = 0;
+    if (QSREF) {
+        refLo[0] = abMin(t0x / 8, 0), refHi[0] = abMax(t1x / 8, g.qsCells[0]);
+        refLo[1] = abMin(t0y / 8, 0), refHi[1] = abMax(t0y / 8, g.qsCells[1]);
+        refLo[2] = abMin(t0z / 8, 0), refHi[2] = abMax(t0z / 8, g.qsCells[2]);
+        myXlo = abMin(vxI / 8, 0), myXhi = abMax(vxI / 8, g.qsCells[0]);
+    }
     float vz[GT_Z], acc[GT_Z], accR[GT_Z], accG[GT_Z], accB[GT_Z];
 #pragma unroll
     for (int k = 0; k < GT_Z; ++k) {
-        vz[k] = __fadd_rn(__fmul_rn((float)(t0z + k), g.sd[2]), g.mn[2]);
+        vz[k] = QSREF ? __fmul_rn(g.sd[2], (float)(t0z + k)) : __fadd_rn(__fmul_rn((float)(t0z + k), g.sd[2]), g.mn[2]);
         acc[k] = 0.0f, accR[k] = 0.0f, accG[k] = 0.0f, accB[k] = 0.0f;
     }
 
@@ -877,6 +892,10 @@ __global__ void __launch_bounds__(GT_THREADS, 2) density_gather_kernel(Geo g, De
                     eps = __fmul_rn(g.gausslim, sr);
                     c.k0 = __fdiv_rn(-1.4426950408889634f, __fmul_rn(__fmul_rn(2.0f, sr), sr));
                     c.lim = __fmul_rn(eps, eps);
+                    if (QSREF) { // no cut-off; positions relative to the grid origin
+                        c.lim = INFINITY;
+                        c.x = __fsub_rn(p.x, g.mn[0]), c.y = __fsub_rn(p.y, g.mn[1]), c.z = __fsub_rn(p.z, g.mn[2]);
+                    }
                     if (auxN == 4) {
                         const float4 col = reinterpret_cast<const float4*>(aux)[idx];
                         c.cr = col.x, c.cg = col.y, c.cb = col.z;
@@ -888,6 +907,11 @@ __global__ void __launch_bounds__(GT_THREADS, 2) density_gather_kernel(Geo g, De
 #pragma unroll
                 for (int a = 0; a < 3; ++a) {
                     qmin[a] = 0, nq[a] = 1, boxLo[a] = -(1 << 20), boxHi[a] = 1 << 20;
+                    if (QSREF) { // the atom's acceleration cell: min(int(p * invcellsize), ncells - 1) (CUDASpatialSearch.cu:92-94)
+                        const float rel = a == 0 ? c.x : (a == 1 ? c.y : c.z);
+                        qmin[a] = min(__float2int_rz(__fmul_rn(rel, g.qsInvAc)), g.qsCells[a] - 1);
+                        continue;
+                    }
                     if (GENERAL && MODE == 0) { // the reference's integer support box, in un-wrapped voxel indices
                         const int H = homeVoxel(pp[a], g.mn[a], g.sd[a]), f = filterSize(p.w, g.sd[a]);
                         boxLo[a] = H - f, boxHi[a] = H + f;
@@ -909,6 +933,8 @@ __global__ void __launch_bounds__(GT_THREADS, 2) density_gather_kernel(Geo g, De
             }
             // squared distance from the particle to the tile's box in the frame of image (qx, qy, qz)
             auto imageKeep = [&](int qx, int qy, int qz) {
+                if (QSREF) // qx, qy, qz = the atom's acceleration cell: inside the cell range of the tile's thread blocks?
+                    return qx >= refLo[0] && qx <= refHi[0] && qy >= refLo[1] && qy <= refHi[1] && qz >= refLo[2] && qz <= refHi[2];
                 const int q[3] = {qx, qy, qz};
                 const int tl0[3] = {t0x, t0y, t0z}, tl1[3] = {t1x, t1y, t1z};
                 float gap2 = 0.0f;
@@ -949,7 +975,7 @@ __global__ void __launch_bounds__(GT_THREADS, 2) density_gather_kernel(Geo g, De
                                 const int qx = qmin[0] + ix, qy = qmin[1] + iy, qz = qmin[2] + iz;
                                 if (GENERAL && !imageKeep(qx, qy, qz)) continue;
                                 if (sl >= w0 && sl < w0 + GT_CHUNK) {
-                                    c.kx = qx * g.s[0], c.ky = qy * g.s[1], c.kz = qz * g.s[2];
+                                    c.kx = QSREF ? qx : qx * g.s[0], c.ky = QSREF ? qy : qy * g.s[1], c.kz = QSREF ? qz : qz * g.s[2];
                                     c.pad = (GENERAL && MODE == 0) ? packBox(qx, qy, qz) : 0;
                                     sh.cand[sl - w0] = c;
                                 }
@@ -968,15 +994,16 @@ __global__ void __launch_bounds__(GT_THREADS, 2) density_gather_kernel(Geo g, De
                     if (lane < (bx & 63) || lane >= ((bx >> 6) & 63) || ty < ((bx >> 12) & 15) || ty >= ((bx >> 16) & 15)) continue;
                     zLo = (bx >> 20) & 15, zHi = (bx >> 24) & 15;
                 }
+                if (QSREF && (K.x < myXlo || K.x > myXhi)) continue; // not in the cell range of MY 8-voxel block along x
                 float px = vx, py = vy;
-                if (K.x | K.y | K.z) { // periodic image: the reference's un-wrapped voxel index (ParticlesToDensity.cpp:605-613)
+                if (!QSREF && (K.x | K.y | K.z)) { // periodic image: the reference's un-wrapped voxel index (ParticlesToDensity.cpp:605-613)
                     px = __fadd_rn(__fmul_rn((float)(vxI + K.x), g.sd[0]), g.mn[0]);
                     py = __fadd_rn(__fmul_rn((float)(vyI + K.y), g.sd[1]), g.mn[1]);
                 }
                 const float dx = __fsub_rn(px, A.x), dy = __fsub_rn(py, A.y);
                 const float dxy2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
                 float lim2 = MODE == 0 ? B.x * B.x * 1.0001f : B.x;
-                if (K.z == 0) { // the tile's planes are at least gz away from the particle: a column further out than sqrt(lim2 - gz^2) has no hit
+                if (!QSREF && K.z == 0) { // the tile's planes are at least gz away from the particle: a column further out than sqrt(lim2 - gz^2) has no hit
                     const float gz = fmaxf(fmaxf(vz[0] - A.z, A.z - vz[GT_Z - 1]), 0.0f);
                     lim2 -= gz * gz * 0.999f;
                 }
@@ -984,7 +1011,7 @@ __global__ void __launch_bounds__(GT_THREADS, 2) density_gather_kernel(Geo g, De
 #pragma unroll
                 for (int k = 0; k < GT_Z; ++k) {
                     float pz = vz[k];
-                    if (K.z) pz = __fadd_rn(__fmul_rn((float)(t0z + k + K.z), g.sd[2]), g.mn[2]);
+                    if (!QSREF && K.z) pz = __fadd_rn(__fmul_rn((float)(t0z + k + K.z), g.sd[2]), g.mn[2]);
                     const float dz = __fsub_rn(pz, A.z);
                     const float d2 = __fadd_rn(dxy2, __fmul_rn(dz, dz)); // (no per-plane skip: branches here cost the eight independent
                                                                          //  ex2 chains their overlap -- measured 28.5 vs 23.2 ms)

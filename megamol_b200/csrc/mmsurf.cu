@@ -157,6 +157,8 @@ struct mms_ctx {
     cudaStream_t ownStream = nullptr;
     DevBuf rangeBuf; // {-min, max} as floats for device-side all-reduce + normalise
     bool haveCount = false, meshExternal = false;
+    float qsAc = 0.0f;    // MMS_MODE_QS_GAUSS_REFCELLS: the reference's acceleration grid of this frame
+    int qsCells[3] = {1, 1, 1};
     const float* adoptedVol = nullptr; // mms_adopt_density: another context's volume (and colour volume), by reference
     const float* adoptedRgb = nullptr;
     cudaEvent_t adoptReady = nullptr;
@@ -246,7 +248,9 @@ Geo makeGeo(const mms_ctx* c) {
     for (int a = 0; a < 3; ++a) g.nc[a] = (g.s[a] + (1 << g.cshift) - 1) >> g.cshift;
     g.sigma = c->params.sigma;
     g.agg = c->params.aggregator;
-    g.mode = c->params.mode;
+    g.mode = c->params.mode == MMS_MODE_P2D_BUMP ? 0 : 1; // both Gaussian modes are mode 1 on the device; qsAc > 0 selects the reference cells
+    g.qsAc = c->qsAc, g.qsInvAc = c->qsAc > 0.0f ? 1.0f / c->qsAc : 0.0f;
+    for (int a = 0; a < 3; ++a) g.qsCells[a] = c->qsCells[a];
     g.radscale = c->params.radscale;
     g.gausslim = c->params.gausslim;
     g.colour = c->params.colour;
@@ -487,7 +491,8 @@ int mms_set_slab(mms_ctx* c, int32_t z0, int32_t nz, int32_t cell_z0, int32_t ce
 
 int mms_set_params(mms_ctx* c, const mms_params* p) {
     if (!c || !p) return MMS_ERR_INVALID;
-    if (p->mode != MMS_MODE_P2D_BUMP && p->mode != MMS_MODE_QS_GAUSS) return c->fail(MMS_ERR_INVALID, "unknown mode %d", p->mode);
+    if (p->mode != MMS_MODE_P2D_BUMP && p->mode != MMS_MODE_QS_GAUSS && p->mode != MMS_MODE_QS_GAUSS_REFCELLS)
+        return c->fail(MMS_ERR_INVALID, "unknown mode %d", p->mode);
     if (p->mode == MMS_MODE_P2D_BUMP) {
         if (p->aggregator < 0 || p->aggregator > 2) return c->fail(MMS_ERR_INVALID, "unknown aggregator %d", p->aggregator);
         if (!(p->sigma > 0.0f)) return c->fail(MMS_ERR_INVALID, "sigma must be > 0");
@@ -666,11 +671,25 @@ int mms_compute_density(mms_ctx* c) {
             rmax = std::max(rmax, r);
         }
         const Geo g0 = makeGeo(c);
-        const float epsMax = (c->params.mode == MMS_MODE_P2D_BUMP) ? c->params.sigma * rmax : c->params.gausslim * c->params.radscale * rmax;
+        float epsMax = (c->params.mode == MMS_MODE_P2D_BUMP) ? c->params.sigma * rmax : c->params.gausslim * c->params.radscale * rmax;
+        c->qsAc = 0.0f;
+        if (c->params.mode == MMS_MODE_QS_GAUSS_REFCELLS) {
+            // the reference's acceleration grid, its own fp32 expressions (CUDAQuickSurf.cu:1259-1264, 1279-1282)
+            const float gridspacing = g0.sd[0];
+            for (int a = 1; a < 3; ++a)
+                if (std::fabs(g0.sd[a] - gridspacing) > 1e-5f * gridspacing)
+                    return c->fail(MMS_ERR_UNSUPPORTED, "the reference candidate set needs one grid spacing for all axes (QuickSurf's gridspacing)");
+            if (c->z0 != 0 || c->nz != c->grid.res[2]) return c->fail(MMS_ERR_UNSUPPORTED, "the reference candidate set is not available on z-slabs");
+            float ac = c->params.gausslim * c->params.radscale * rmax;
+            if (ac < gridspacing) ac = gridspacing;
+            c->qsAc = ac;
+            for (int a = 0; a < 3; ++a) c->qsCells[a] = std::max(static_cast<int>((c->grid.res[a] * gridspacing) / ac), 1);
+            epsMax = 2.0f * ac + gridspacing; // an atom up to two cell sizes (+ a voxel) away from a tile can sit in one of its candidate cells
+        }
         int need = 1;
         for (int a = 0; a < 3; ++a) need = std::max(need, static_cast<int>(std::ceil(epsMax / g0.sd[a] + 0.02f)));
         // aggregator 2 keeps four sums per voxel: the register-accumulating gather kernel has them (as the QuickSurf colour sums)
-        c->useGather = c->params.mode == MMS_MODE_QS_GAUSS || need > 8 || (c->params.mode == MMS_MODE_P2D_BUMP && c->params.aggregator == 2);
+        c->useGather = c->params.mode != MMS_MODE_P2D_BUMP || need > 8 || (c->params.mode == MMS_MODE_P2D_BUMP && c->params.aggregator == 2);
         // a support box wider than a periodic axis: a voxel receives the same particle through several images (the reference's loop over the
         // un-wrapped box, ParticlesToDensity.cpp:583-603) -- the gather kernel enumerates them, the splat kernels keep one image per voxel
         for (int a = 0; a < 3; ++a)
@@ -698,6 +717,9 @@ int mms_compute_density(mms_ctx* c) {
     const size_t ncells = static_cast<size_t>(g.nc[0]) * g.nc[1] * g.nc[2];
     const size_t nvox = static_cast<size_t>(g.s[0]) * g.s[1] * g.nz;
     const bool colour = g.mode == 1 && c->params.colour != 0;
+    if (g.qsAc > 0.0f)
+        for (ListDev& l : c->lists)
+            for (int a = 0; a < 3; ++a) l.gf[a] = static_cast<int>(std::ceil(2.0f * g.qsAc / g.sd[a])) + 1;
     const bool vector = g.mode == 0 && g.agg == 2;
     const int auxN = (g.mode == 0 && g.agg == 1) ? 1 : ((colour || vector) ? 4 : 0);
     if ((colour || vector) && !c->rgb.ensure(nvox * 12)) return c->fail(MMS_ERR_NOMEM, "device allocation failed (colour / vector volume)");
@@ -749,7 +771,7 @@ int mms_compute_density(mms_ctx* c) {
         const unsigned* CS = c->cellStart.as<unsigned>();
         DevState* DS = c->dstate.as<DevState>();
         // GENERAL: several periodic images of a particle can reach one tile, or the reference's integer support box clips the kernel (sigma > 1)
-        bool general = g.mode == 0 && g.sigma > 1.0f;
+        bool general = (g.mode == 0 && g.sigma > 1.0f) || g.qsAc > 0.0f; // (Gaussian mode is non-periodic: GENERAL there = the reference cells)
         const int gtile[3] = {GT_X, GT_Y, GT_Z};
         for (int a = 0; a < 3; ++a)
             if (g.cyc[a] && g.s[a] < gtile[a] + 2 * c->reach + 2) general = true;

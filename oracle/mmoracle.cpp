@@ -455,6 +455,70 @@ int mmo_density_gauss(int nlists, const mmo_list* lists, const float origin[3], 
     return 0;
 }
 
+/**
+ * The REFERENCE's candidate set for the same Gaussian density (protein_cuda QuickSurf): no radial cut-off at all -- a voxel sums
+ * exp2f(d^2 w_p) over EVERY atom of the acceleration-grid cells that overlap its 8x8x8 thread-block tile grown by one cell size
+ * (CUDAQuickSurf.cu:232-253,293-315; cell size max(gausslim*radscale*rmax, gridspacing), :1259-1264,1279-1282; atoms hashed with
+ * min(int(p / cellsize), ncells-1), CUDASpatialSearch.cu:92-94; cells visited z, y, x, atoms of a cell in input order -- the radix
+ * sort by cell is stable).  xyzr positions are relative to the grid origin (QuickSurf.cpp:553-556); rgb, if given, becomes the
+ * RGB3F volume texture sum(w rgb) * 1/isovalue (:510-513).  Used to pin the restatement above to the compiled reference kernels
+ * (tests/test_gpu_quicksurf_ref.py) and to measure what the clean cut-off leaves out.
+ */
+int mmo_density_gauss_refset(uint64_t natoms, const float* xyzr, const float* rgba, const int32_t res[3], float maxrad, float radscale,
+    float gridspacing, float isovalue, float gausslim, float* vol, float* rgb) {
+    float acgridspacing = gausslim * radscale * maxrad;
+    if (acgridspacing < gridspacing) acgridspacing = gridspacing;
+    const int ncx = std::max(int((res[0] * gridspacing) / acgridspacing), 1), ncy = std::max(int((res[1] * gridspacing) / acgridspacing), 1),
+              ncz = std::max(int((res[2] * gridspacing) / acgridspacing), 1);
+    const float invac = 1.0f / acgridspacing, invisovalue = 1.0f / isovalue;
+    const float log2e = std::log2(2.718281828);
+    std::vector<std::vector<uint32_t>> cells(static_cast<size_t>(ncx) * ncy * ncz);
+    std::vector<float> w(natoms);
+    for (uint64_t i = 0; i < natoms; ++i) {
+        const int cx = std::min(int(xyzr[4 * i] * invac), ncx - 1), cy = std::min(int(xyzr[4 * i + 1] * invac), ncy - 1),
+                  cz = std::min(int(xyzr[4 * i + 2] * invac), ncz - 1);
+        if (cx < 0 || cy < 0 || cz < 0) return -1; // the reference would index out of bounds: QuickSurf pads its grid so this cannot happen
+        cells[(static_cast<size_t>(cz) * ncy + cy) * ncx + cx].push_back(static_cast<uint32_t>(i));
+        const float scaledrad = xyzr[4 * i + 3] * radscale;
+        w[i] = -1.0f * log2e / (2.0f * scaledrad * scaledrad);
+    }
+    const int B = 8; // GBLOCKSZX x GBLOCKSZY x (GBLOCKSZZ * GUNROLL)
+    const int nbx = (res[0] + B - 1) / B, nby = (res[1] + B - 1) / B, nbz = (res[2] + B - 1) / B;
+#pragma omp parallel for collapse(2) schedule(dynamic)
+    for (int bz = 0; bz < nbz; ++bz)
+        for (int by = 0; by < nby; ++by)
+            for (int bx = 0; bx < nbx; ++bx) {
+                auto range = [&](int b, int nc, int& lo, int& hi) {
+                    lo = int(((b * B) * gridspacing - acgridspacing) * invac);
+                    hi = int((((b + 1) * B) * gridspacing + acgridspacing) * invac);
+                    lo = lo < 0 ? 0 : lo;
+                    hi = hi >= nc - 1 ? nc - 1 : hi;
+                };
+                int x0, x1, y0, y1, z0, z1;
+                range(bx, ncx, x0, x1), range(by, ncy, y0, y1), range(bz, ncz, z0, z1);
+                for (int k = bz * B; k < std::min((bz + 1) * B, res[2]); ++k)
+                    for (int j = by * B; j < std::min((by + 1) * B, res[1]); ++j)
+                        for (int i = bx * B; i < std::min((bx + 1) * B, res[0]); ++i) {
+                            const float coorx = gridspacing * i, coory = gridspacing * j, coorz = gridspacing * k;
+                            float d = 0.0f, cr = 0.0f, cg = 0.0f, cb = 0.0f;
+                            for (int zc = z0; zc <= z1; ++zc)
+                                for (int yc = y0; yc <= y1; ++yc)
+                                    for (int xc = x0; xc <= x1; ++xc)
+                                        for (uint32_t a : cells[(static_cast<size_t>(zc) * ncy + yc) * ncx + xc]) {
+                                            const float dx = coorx - xyzr[4 * a], dy = coory - xyzr[4 * a + 1], dz = coorz - xyzr[4 * a + 2];
+                                            const float dxy2 = dx * dx + dy * dy;
+                                            const float t = std::exp2((dxy2 + dz * dz) * w[a]);
+                                            d += t;
+                                            if (rgb) cr += t * rgba[4 * a], cg += t * rgba[4 * a + 1], cb += t * rgba[4 * a + 2];
+                                        }
+                            const size_t o = i + (j + static_cast<size_t>(k) * res[1]) * res[0];
+                            vol[o] = d;
+                            if (rgb) rgb[3 * o] = cr * invisovalue, rgb[3 * o + 1] = cg * invisovalue, rgb[3 * o + 2] = cb * invisovalue;
+                        }
+            }
+    return 0;
+}
+
 /** Cube index of cell (x,y,z): bit i set iff corner i < iso. */
 static inline int cubeIndex(const float* vol, int sx, int sy, int x, int y, int z, float iso) {
     int ci = 0;

@@ -177,6 +177,23 @@ class Oracle:
             raise RuntimeError(f"mmo_density_gauss rc={rc}")
         return vol, rgb
 
+    def density_gauss_refset(self, xyzr, rgba, res, maxrad, radscale, gridspacing, isovalue, gausslim):
+        """The reference QuickSurf's candidate set (no radial cut-off; mmo_density_gauss_refset).  xyzr relative to the grid origin."""
+        xyzr = np.ascontiguousarray(xyzr, np.float32)
+        r = np.asarray(res, np.int32)
+        vol = np.empty((res[2], res[1], res[0]), np.float32)
+        rgb = np.empty((res[2], res[1], res[0], 3), np.float32) if rgba is not None else None
+        if rgba is not None:
+            rgba = np.ascontiguousarray(rgba, np.float32)
+        self.lib.mmo_density_gauss_refset.argtypes = [C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float,
+                                                      C.c_float, C.c_float, C.c_void_p, C.c_void_p]
+        rc = self.lib.mmo_density_gauss_refset(len(xyzr), xyzr.ctypes.data, rgba.ctypes.data if rgba is not None else None, r.ctypes.data,
+                                               float(maxrad), float(radscale), float(gridspacing), float(isovalue), float(gausslim),
+                                               vol.ctypes.data, rgb.ctypes.data if rgb is not None else None)
+        if rc:
+            raise RuntimeError(f"mmo_density_gauss_refset rc={rc}")
+        return vol, rgb
+
     def mc_count(self, vol, iso, want_cubeidx=False):
         vol = np.ascontiguousarray(vol, np.float32)
         sz, sy, sx = vol.shape

@@ -52,6 +52,9 @@ ParticlesToDensityB200::ParticlesToDensityB200()
         , qsQualitySlot("quicksurf::quality", "Quality: 0 low .. 3 ultra (Gaussian cut-off 2.0/2.5/3.0/4.0 sigma)")
         , qsRadScaleSlot("quicksurf::radiusScale", "Radius scale")
         , qsColourSlot("quicksurf::colour", "Also build the density-weighted colour volume (coloured isosurface)")
+        , qsRefCellsSlot("quicksurf::referenceCandidates",
+              "Sum over the candidate set of protein_cuda's QuickSurf (all atoms of the acceleration cells around a voxel's 8^3 block, no radial "
+              "cut-off): the reference's density up to fp32 summation order, at ~15x the cost of the radial cut-off")
         , qsGridSpacingSlot("quicksurf::gridSpacing", "Grid spacing of QuickSurf's own grid set-up (0 = use sizex/sizey/sizez on the bounding box)")
         , outDataSlot("outData", "Provides a density volume for the particles")
         , outParticlesSlot("outParticles", "Provides the particles in grid form (vector aggregator only)")
@@ -120,6 +123,8 @@ ParticlesToDensityB200::ParticlesToDensityB200()
     this->MakeSlotAvailable(&this->qsRadScaleSlot);
     this->qsColourSlot << new core::param::BoolParam(false);
     this->MakeSlotAvailable(&this->qsColourSlot);
+    this->qsRefCellsSlot << new core::param::BoolParam(false);
+    this->MakeSlotAvailable(&this->qsRefCellsSlot);
     this->qsGridSpacingSlot << new core::param::FloatParam(0.0f, 0.0f);
     this->MakeSlotAvailable(&this->qsGridSpacingSlot);
 
@@ -155,12 +160,13 @@ bool ParticlesToDensityB200::anythingDirty() const {
     return this->aggregatorSlot.IsDirty() || this->xResSlot.IsDirty() || this->yResSlot.IsDirty() || this->zResSlot.IsDirty() ||
            this->cyclXSlot.IsDirty() || this->cyclYSlot.IsDirty() || this->cyclZSlot.IsDirty() || this->normalizeSlot.IsDirty() ||
            this->sigmaSlot.IsDirty() || this->deviceSlot.IsDirty() || this->modeSlot.IsDirty() || this->qsQualitySlot.IsDirty() ||
-           this->qsRadScaleSlot.IsDirty() || this->qsColourSlot.IsDirty() || this->qsGridSpacingSlot.IsDirty();
+           this->qsRadScaleSlot.IsDirty() || this->qsColourSlot.IsDirty() || this->qsGridSpacingSlot.IsDirty() ||
+           this->qsRefCellsSlot.IsDirty();
 }
 
 void ParticlesToDensityB200::resetDirty() {
     for (auto* s : {&aggregatorSlot, &xResSlot, &yResSlot, &zResSlot, &cyclXSlot, &cyclYSlot, &cyclZSlot, &normalizeSlot, &sigmaSlot, &deviceSlot, &modeSlot,
-             &qsQualitySlot, &qsRadScaleSlot, &qsColourSlot, &qsGridSpacingSlot})
+             &qsQualitySlot, &qsRadScaleSlot, &qsColourSlot, &qsGridSpacingSlot, &qsRefCellsSlot})
         s->ResetDirty();
 }
 
@@ -307,7 +313,10 @@ bool ParticlesToDensityB200::computeVolume(core::AbstractGetData3DCall* in) {
     p.radscale = this->qsRadScaleSlot.Param<core::param::FloatParam>()->Value();
     p.gausslim = kGaussLim[this->qsQualitySlot.Param<core::param::IntParam>()->Value() & 3];
     p.colour = p.mode == MMS_MODE_QS_GAUSS && this->qsColourSlot.Param<core::param::BoolParam>()->Value();
-    if (p.mode == MMS_MODE_QS_GAUSS)
+    const bool gaussian = p.mode == MMS_MODE_QS_GAUSS;
+    if (gaussian && this->qsRefCellsSlot.Param<core::param::BoolParam>()->Value())
+        p.mode = MMS_MODE_QS_GAUSS_REFCELLS;
+    if (gaussian)
         grid.cyclic[0] = grid.cyclic[1] = grid.cyclic[2] = 0; // QuickSurf has no periodic images
 
     std::vector<mms_list> lists;
@@ -379,7 +388,7 @@ bool ParticlesToDensityB200::computeVolume(core::AbstractGetData3DCall* in) {
     if (mms_push_particles_dir(this->ctx, static_cast<int32_t>(lists.size()), lists.data(), dirs.data(), dirStrides.data()) != MMS_OK)
         return fail("push_particles");
     const float gridSpacing = this->qsGridSpacingSlot.Param<core::param::FloatParam>()->Value();
-    this->ownGrid = p.mode == MMS_MODE_QS_GAUSS && gridSpacing > 0.0f;
+    this->ownGrid = gaussian && gridSpacing > 0.0f;
     if (this->ownGrid) {
         // QuickSurf's grid set-up (QuickSurf.cpp:456-480): the bounding box grown by a padding derived from the largest radius, then
         // ceil(extent / gridspacing) voxels of exactly that spacing, origin = the padded minimum.  The molecule path skips the

@@ -79,7 +79,7 @@ private:
         sigmaSlot, surfaceSlot;
     core::param::ParamSlot deviceSlot; // extra: CUDA device ordinal
     // extra: QuickSurf semantics as a kernel mode (names and defaults of protein_cuda::QuickSurf, QuickSurf.cpp:18-31,62-72)
-    core::param::ParamSlot modeSlot, qsQualitySlot, qsRadScaleSlot, qsColourSlot, qsGridSpacingSlot;
+    core::param::ParamSlot modeSlot, qsQualitySlot, qsRadScaleSlot, qsColourSlot, qsGridSpacingSlot, qsRefCellsSlot;
     core::CalleeSlot outDataSlot, outParticlesSlot, outInfoSlot;
     core::CallerSlot inDataSlot;
 
