@@ -109,8 +109,8 @@ def cpu_reference_sample(threads=None, reps=1):
     # same voxel size as C2: box = 127 * (L_c2 / 511)
     if rb.available():
         h = rb.Harness()
-        if threads:
-            h.set_threads(threads)
+        # torchrun exports OMP_NUM_THREADS=1 to its ranks: the reference arm always gets every host core it may use
+        h.set_threads(threads or len(os.sched_getaffinity(0)) or os.cpu_count() or 1)
         cores = h.threads
         kind = "reference"
         best = None
@@ -181,6 +181,55 @@ def run_reference(args, w):
     print(json.dumps(line))
 
 
+def pcie_probe(job, nbytes=1 << 30, reps=3):
+    """Pinned-memory copy bandwidth of THIS box, all ranks at the same time (the e2e arm's roof): host -> device and device -> host,
+    best of `reps`, one 1 GiB buffer per rank.  Returns GB/s per direction (this rank) -- the caller aggregates."""
+    import torch
+    n = nbytes // 4
+    h = torch.empty(n, dtype=torch.float32, pin_memory=True)
+    d = torch.empty(n, dtype=torch.float32, device=job.dev)
+    out = {}
+    for name, dst, src in (("h2d", d, h), ("d2h", h, d)):
+        best = 0.0
+        for _ in range(reps):
+            job.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            dst.copy_(src, non_blocking=True)
+            e1.record()
+            torch.cuda.synchronize()
+            best = max(best, nbytes / (e0.elapsed_time(e1) * 1e-3) / 1e9)
+        out[name] = best
+    del h, d
+    return out
+
+
+def modules_e2e(w, steps=3):
+    """The same end-to-end step through the DROP-IN MODULES (plugin/b200surf compiled against the reference's module/call runtime,
+    oracle/_ref/libmmplug.so): a MultiParticleDataCall source -> ParticlesToDensityB200 -> IsoSurfaceB200 -> VolumetricDataCall +
+    CallTriMeshData pulled like a renderer would (host pointers).  Adds the call walk, metadata and list handling of the modules to
+    what `e2e` measures through the bare C ABI.  None where the harness library was not built."""
+    from oracle import ref_binding as rb
+    if not rb.available(rb.PLUG_LIB):
+        return None
+    xyz, L = synth.lj_fluid(w["n"])
+    h = rb.Harness(rb.PLUG_LIB)
+    lists = [dict(vtx=xyz, vtx_type=1, count=len(xyz), global_radius=RADIUS)]
+    times = []
+    for it in range(steps + 2):
+        h.set_particles(lists, (0, 0, 0, L, L, L))   # new data hash: both modules recompute
+        h.set_p2d_params(w["res"], cyclic=(True, True, True), normalize=True, sigma=1.0)
+        t0 = time.perf_counter()
+        h.pull_volume(copy=False)
+        m = h.pull_mesh(ISO, copy=False)
+        times.append(time.perf_counter() - t0)
+    dt = float(np.median(times[2:]))
+    h.close()
+    return {"value": w["n"] / dt / 1e6, "unit": "Mparticles/s", "ms_per_step": dt * 1e3, "steps": steps, "triangles": m["nverts"] // 3,
+            "note": "ParticlesToDensityB200 + IsoSurfaceB200 driven through the reference's Call/Slot runtime (libmmplug.so): host particle "
+                    "array in, host volume + host mesh pointers out"}
+
+
 def bind_to_gpu_numa_node(local):
     """Pin this rank's process to the CPUs NVML reports as local to its GPU, BEFORE any pinned host memory is allocated: the pinned
     result buffers then live on the GPU's own NUMA node and N ranks do not funnel their D2H traffic into one socket's memory.
@@ -221,7 +270,7 @@ def run_ours(args, w):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    job = slabs.SlabJob(w, rank, world, local, iso=ISO, radius=RADIUS, gather=args.gather)
+    job = slabs.SlabJob(w, rank, world, local, iso=ISO, radius=RADIUS, gather=args.gather, exchange=args.exchange)
     if args.algorithm == "mt":  # the reference IsoSurface's marching tetrahedra, bit for bit (compatibility mode; flat normals, ~2.7x the triangles)
         job.surf.set_isosurface_mode(mm.api.ISO_MARCHING_TETS)
     peak, peak_src = load_peaks()
@@ -252,35 +301,61 @@ def run_ours(args, w):
         sampler.stop_flag.set()
         sampler.join(timeout=3)
     n_total, v_total, t_total = job.totals()
+    # everything the record needs from the job (it may be replaced by the C4 job below)
+    info = dict(h2d=job.h2d_bytes(), d2h=job.d2h_bytes(), roofline=job.roofline(stage, peak), describe=job.describe(), protein=job.protein,
+                pipeline_bytes=job.pipeline_bytes())
+    # the e2e arm's own roof: pinned copies over PCIe, all ranks at once
+    pc = pcie_probe(job) if not args.no_e2e else None
+    if pc is not None and world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([pc["h2d"], pc["d2h"]], device=job.dev, dtype=torch.float64)
+        dist.all_reduce(t)
+        pc = {"h2d": float(t[0].item()), "d2h": float(t[1].item())}
+    # N > 1: the configuration the north-star target is quoted on (C4, strong scaling) inside the same record
+    c4 = None
+    if world > 1 and args.workload == "c2" and not args.no_c4:
+        job.close_keep_group()
+        job = None
+        c4 = run_c4(args, rank, world, local)
     if rank != 0:
-        job.close()
+        if job is not None:
+            job.close()
+        else:
+            import torch.distributed as dist
+            dist.barrier()
+            dist.destroy_process_group()
         return
     ms = t_dev / args.steps
     value = n_total / (ms * 1e-3) / 1e6
     ms_e = t_e2e / e2e_steps
     e2e_val = n_total / (ms_e * 1e-3) / 1e6
     e2e = {"value": e2e_val, "unit": "Mparticles/s", "ms_per_step": ms_e, "steps": e2e_steps,
-           "h2d_bytes_per_step": job.h2d_bytes(), "d2h_bytes_per_step": job.d2h_bytes()}
+           "h2d_bytes_per_step": info["h2d"], "d2h_bytes_per_step": info["d2h"]}
     if t_e2e_dm == t_e2e_dm:
         e2e_dm = {"value": n_total / (t_e2e_dm / e2e_steps * 1e-3) / 1e6, "unit": "Mparticles/s", "ms_per_step": t_e2e_dm / e2e_steps,
                   "note": "host particles in (pinned H2D), volume back to the host (D2H), mesh stays in HBM for a device-resident consumer",
-                  "h2d_bytes_per_step": job.h2d_bytes(), "d2h_bytes_per_step": v_total * (16 if job.protein else 4)}
+                  "h2d_bytes_per_step": info["h2d"], "d2h_bytes_per_step": v_total * (16 if info["protein"] else 4)}
     else:
         e2e_dm = None
+    if pc is not None and not args.no_e2e:
+        # lower bound of the e2e step if it were nothing but its PCIe transfers at the measured copy bandwidth
+        floor_ms = (info["h2d"] / (pc["h2d"] * 1e9) + info["d2h"] / (pc["d2h"] * 1e9)) * 1e3
+        e2e["pcie"] = {"h2d_gbs": pc["h2d"], "d2h_gbs": pc["d2h"], "transfer_floor_ms": floor_ms, "frac": floor_ms / ms_e,
+                       "how": "1 GiB pinned copies, all ranks at the same time, best of 3 (aggregate GB/s); frac = transfer floor / e2e step"}
     if args.no_e2e:
-        e2e = {"value": None, "unit": "Mparticles/s", "skipped": "--no-e2e", "h2d_bytes_per_step": job.h2d_bytes(), "d2h_bytes_per_step": job.d2h_bytes()}
+        e2e = {"value": None, "unit": "Mparticles/s", "skipped": "--no-e2e", "h2d_bytes_per_step": info["h2d"], "d2h_bytes_per_step": info["d2h"]}
     # roofline of the dominant kernel (largest share of the device step), algorithmic bytes per DESIGN.md
-    rl = job.roofline(stage, peak)
+    rl = info["roofline"]
     rl["peak_source"] = peak_src
     line = {"metric": METRIC, "value": value, "unit": "Mparticles/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if w.get("fixed_total") else "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "gvoxels_per_s": v_total / (ms * 1e-3) / 1e9,
-            "config": {"workload": w["name"] if world == 1 else job.describe(), "particles": n_total, "voxels": v_total, "triangles": t_total,
+            "config": {"workload": w["name"] if world == 1 else info["describe"], "particles": n_total, "voxels": v_total, "triangles": t_total,
                        "l2": "inputs (particles + volume + mesh) are larger than the 126 MB L2; no explicit flush",
                        "parallelism": f"z-slabs x{world}", "host_affinity_rank0": numa,
                        "isosurface": "marching cubes (default)" if args.algorithm == "mc" else "marching tetrahedra, reference-compatible mode"},
             "stages_ms": stage, "roofline": rl,
-            "pipeline_hbm_frac": job.pipeline_bytes() / (ms * 1e-3) / 1e9 / peak,
+            "pipeline_hbm_frac": info["pipeline_bytes"] / (ms * 1e-3) / 1e9 / peak,
             "e2e": e2e, "e2e_mesh_on_device": e2e_dm, "gpu_launches": launches, "clocks": sampler.summary()}
     if not args.no_cpu:
         cb = cpu_reference_sample()
@@ -288,8 +363,49 @@ def run_ours(args, w):
         line["cpu_baseline"]["gvoxels_per_s"] = cb["gvoxels_per_s"]
         if world == 1 and args.workload == "c2":
             line["cpu_port"] = cpu_port_full()
+    if c4 is not None:
+        line["c4"] = c4
+    if world == 1 and args.workload == "c2" and not args.no_e2e:
+        job.close()
+        job = None
+        me = modules_e2e(w)
+        if me is not None:
+            line["e2e_modules"] = me
     print(json.dumps(line))
-    job.close()
+    if job is not None:
+        job.close()
+    elif world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_c4(args, rank, world, local):
+    """BASELINE configs[3] / the north-star target: 100 M particles -> 1024^3, z-slabs over the ranks of this run (strong scaling)."""
+    from megamol_b200 import slabs
+    w = workload("c4")
+    job = slabs.SlabJob(w, rank, world, local, iso=ISO, radius=RADIUS, gather=args.gather, exchange=args.exchange)
+    for _ in range(2):
+        job.step_device()
+    t_dev = job.timed(job.step_device, 3) / 3
+    stage = job.stage_times()
+    job.step_e2e(mesh_to_host=False)
+    t_dm = job.timed(lambda: job.step_e2e(mesh_to_host=False), 2) / 2
+    t_full = None
+    # the C4 mesh is 68 GB of host arrays: with the mesh on the host only where every rank's share (8.5 GB pinned) is moderate
+    if not args.no_e2e and world >= 8 and os.environ.get("MMS_BENCH_C4_FULL_E2E", "1") != "0":
+        job.step_e2e()
+        t_full = job.timed(job.step_e2e, 2) / 2
+    n_total, v_total, t_total = job.totals()
+    out = {"workload": job.describe(), "particles": n_total, "voxels": v_total, "triangles": t_total, "ms_per_step": t_dev,
+           "value": n_total / (t_dev * 1e-3) / 1e6, "unit": "Mparticles/s", "gvoxels_per_s": v_total / (t_dev * 1e-3) / 1e9, "stages_ms": stage,
+           "e2e_mesh_on_device": {"ms_per_step": t_dm, "value": n_total / (t_dm * 1e-3) / 1e6,
+                                  "note": "host particles in, 4.3 GB volume back to the host, mesh stays sharded in HBM"},
+           "e2e": None if t_full is None else {"ms_per_step": t_full, "value": n_total / (t_full * 1e-3) / 1e6,
+                                               "h2d_bytes_per_step": job.h2d_bytes(), "d2h_bytes_per_step": job.d2h_bytes()},
+           "target": "north star: under 100 ms end to end on 8 GPUs"}
+    job.close_keep_group()
+    return out
 
 
 def run_c5(args):
@@ -357,6 +473,10 @@ def main():
     ap.add_argument("--algorithm", default="mc", choices=["mc", "mt"],
                     help="isosurface triangulation: mc = marching cubes (default, the north-star path), mt = the reference module's marching tetrahedra")
     ap.add_argument("--frames", type=int, default=12, help="frames of the C5 time series")
+    ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
+                    help="multi-GPU halo exchange: fused (default; one push kernel writes into the neighbours' receive buffers over NVLink/CUDA IPC, "
+                         "no host synchronisation) or nccl (round-1 baseline: routing kernels + count matrix + all-to-all-v)")
+    ap.add_argument("--no-c4", action="store_true", help="N > 1: skip the C4 (100 M particles -> 1024^3, strong scaling) figures in the record")
     ap.add_argument("--tmpdir", default="/tmp")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -224,6 +224,28 @@ uint64_t mms_launch_count(const mms_ctx* ctx);
 int mms_route_particles(mms_ctx* ctx, const mms_list* list, int32_t nslabs, const int32_t* plane_lo, const int32_t* plane_hi, void* send_buf,
     uint64_t capacity_records, uint64_t* counts);
 
+/* ---- halo exchange without host round trips (replaces mms_route_particles + an all-to-all-v; and, as a whole, the volume-sized
+ * MPI_Allreduce of plugins/datatools/src/MPIVolumeAggregator.cpp:94-152) --------------------------------------------------------------
+ * Every slab owns a receive buffer (x y z r records) and a record counter in device memory; the other slabs map them (CUDA IPC between
+ * processes: mms_ipc_export / mms_ipc_open; peer access inside one process) and APPEND what that slab needs from their share of the
+ * frame with one kernel (halo_push_kernel: ballot-aggregated system-scope atomics over NVLink).  Per frame and slab:
+ *     mms_clear_particles, mms_push_particles(own share)           (as always)
+ *     mms_halo_push(...)                                           one kernel per pushed list; nothing to wait for on the host
+ *     <every slab's push is complete: a stream-ordered collective (any tiny all-reduce) between processes, events inside one>
+ *     mms_halo_receive(ctx, radius_bound)                          the received records become one more list; its LENGTH stays on the device
+ *     mms_compute_density ...
+ * The counters alternate between two words per frame; a slab clears the word of the NEXT frame while it consumes this one's. */
+/* This context's receive buffer (capacity_records x 16 bytes, grow-only; growing invalidates earlier mappings) and its counter block
+ * (4 x uint32: counter of even frames, counter of odd frames, 2 spare). */
+int mms_halo_buffers(mms_ctx* ctx, uint64_t capacity_records, void** recv_buf, void** counters);
+/* Routes the lists pushed so far: slab i computes planes [plane_lo[i], plane_hi[i]]; peer_bufs[i] / peer_counters[i] are slab i's receive
+ * buffer / counter block as mapped into THIS process (ignored for i == my_slab); capacity_records as given to the peers' mms_halo_buffers. */
+int mms_halo_push(mms_ctx* ctx, int32_t nslabs, int32_t my_slab, const int32_t* plane_lo, const int32_t* plane_hi, void* const* peer_bufs,
+    void* const* peer_counters, uint64_t capacity_records);
+/* Adds what the peers have pushed into this context's buffer as a FLOAT_XYZR list (radii <= radius_bound: the largest radius any slab
+ * may send -- it sizes the sort cells without a device scan).  Call once every peer's mms_halo_push of this frame has completed. */
+int mms_halo_receive(mms_ctx* ctx, float radius_bound);
+
 /* Device buffers that can be shared between the per-GPU processes of one node (CUDA IPC over NVLink / PCIe P2P). */
 int mms_device_alloc(int32_t device, size_t bytes, void** ptr);
 int mms_device_free(int32_t device, void* ptr);

@@ -18,7 +18,7 @@ ISO_MARCHING_CUBES, ISO_MARCHING_TETS = 0, 1
 EXPORTS = ["mms_create", "mms_destroy", "mms_last_error", "mms_set_grid", "mms_set_slab", "mms_set_params",
            "mms_clear_particles", "mms_push_particles", "mms_push_particles_dir", "mms_get_vector_field", "mms_get_vector_field_device", "mms_get_max_radius", "mms_compute_density", "mms_get_density_range", "mms_normalize", "mms_density_range_device", "mms_normalize_device", "mms_set_stream",
            "mms_get_density", "mms_prefetch_density", "mms_get_density_device", "mms_set_density", "mms_adopt_density", "mms_extract_isosurface", "mms_set_isosurface_mode", "mms_count_isosurface", "mms_emit_isosurface", "mms_device_alloc",
-           "mms_device_free", "mms_route_particles", "mms_ipc_export", "mms_ipc_open", "mms_ipc_close", "mms_get_mesh",
+           "mms_device_free", "mms_route_particles", "mms_halo_buffers", "mms_halo_push", "mms_halo_receive", "mms_ipc_export", "mms_ipc_open", "mms_ipc_close", "mms_get_mesh",
            "mms_get_mesh_device", "mms_get_home_voxels", "mms_get_cell_tricounts", "mms_get_timings", "mms_synchronize",
            "mms_timer_start", "mms_timer_stop", "mms_launch_count", "mms_alloc_pinned", "mms_free_pinned", "mms_version", "mms_mmpld_open", "mms_mmpld_close",
            "mms_mmpld_last_error", "mms_mmpld_info", "mms_mmpld_prefetch", "mms_mmpld_read_frame"]
@@ -104,6 +104,9 @@ def load_library():
                                       C.POINTER(C.c_uint64)]
     L.mms_device_alloc.argtypes = [C.c_int32, C.c_size_t, C.POINTER(vp)]
     L.mms_device_free.argtypes = [C.c_int32, vp]
+    L.mms_halo_buffers.argtypes = [vp, C.c_uint64, C.POINTER(vp), C.POINTER(vp)]
+    L.mms_halo_push.argtypes = [vp, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(vp), C.POINTER(vp), C.c_uint64]
+    L.mms_halo_receive.argtypes = [vp, C.c_float]
     L.mms_ipc_export.argtypes = [C.c_int32, vp, C.POINTER(C.c_ubyte)]
     L.mms_ipc_open.argtypes = [C.c_int32, C.POINTER(C.c_ubyte), C.POINTER(vp)]
     L.mms_ipc_close.argtypes = [C.c_int32, vp]
@@ -334,6 +337,24 @@ class Surf:
         cnt = (C.c_uint64 * n)()
         self._chk(self.L.mms_route_particles(self.h, C.byref(l), n, lo, hi, int(send_ptr), int(capacity), cnt))
         return [int(c) for c in cnt]
+
+    def halo_buffers(self, capacity):
+        """this context's halo receive buffer and counter block (device addresses), see include/mmsurf.h"""
+        b, c = C.c_void_p(), C.c_void_p()
+        self._chk(self.L.mms_halo_buffers(self.h, int(capacity), C.byref(b), C.byref(c)))
+        return b.value, c.value
+
+    def halo_push(self, slabs, mine, peer_bufs, peer_counters, capacity):
+        """append what the other slabs need from the pushed lists to THEIR receive buffers (one kernel per list, no synchronisation)"""
+        n = len(slabs)
+        lo = (C.c_int32 * n)(*[s["z0"] for s in slabs])
+        hi = (C.c_int32 * n)(*[s["z0"] + s["nz"] - 1 for s in slabs])
+        pb = (C.c_void_p * n)(*[C.c_void_p(p) for p in peer_bufs])
+        pc = (C.c_void_p * n)(*[C.c_void_p(p) for p in peer_counters])
+        self._chk(self.L.mms_halo_push(self.h, n, int(mine), lo, hi, pb, pc, int(capacity)))
+
+    def halo_receive(self, radius_bound):
+        self._chk(self.L.mms_halo_receive(self.h, float(radius_bound)))
 
     def set_isosurface_mode(self, mode):
         """0 = marching cubes (default), 1 = the reference IsoSurface's marching tetrahedra, bit for bit (ISO_MARCHING_TETS)"""

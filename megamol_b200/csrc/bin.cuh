@@ -79,7 +79,9 @@ __global__ void __launch_bounds__(256) bin_count_kernel(Geo g, ListDev l, unsign
     const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
     float rmax = 0.0f;
     unsigned kept = 0;
-    for (unsigned long long j = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; j < l.count; j += stride) {
+    const unsigned long long count = listCount(l);
+    if (l.countPtr && threadIdx.x == 0 && blockIdx.x == 0 && *l.countPtr > l.count) st->pad[0] = 5u; // halo receive buffer overflowed
+    for (unsigned long long j = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; j < count; j += stride) {
         const Binned q = binParticle(g, l, j);
         if (homeOut) {
             int* h = homeOut + 3 * (l.base + j);
@@ -103,7 +105,8 @@ __global__ void __launch_bounds__(256) bin_count_kernel(Geo g, ListDev l, unsign
 __global__ void __launch_bounds__(256) bin_scatter_kernel(Geo g, ListDev l, unsigned* __restrict__ cursor,
     float4* __restrict__ recs, float* __restrict__ aux, int auxN) {
     const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
-    for (unsigned long long j = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; j < l.count; j += stride) {
+    const unsigned long long count = listCount(l);
+    for (unsigned long long j = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; j < count; j += stride) {
         const Binned q = binParticle(g, l, j);
         if (q.cell < 0) continue;
         const unsigned slot = atomicAdd(&cursor[q.cell], 1u);

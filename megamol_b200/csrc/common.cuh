@@ -45,7 +45,17 @@ struct ListDev {
     const char* dir; // DIRDATA_FLOAT_XYZ (aggregator 2) or nullptr = DIRDATA_NONE: the accessors deliver 0 (SimpleSphericalParticles.h:179-193)
     unsigned dstride;
     int dalign;
+    // halo receive list (mms_halo_receive): the length lives on the device (written by the peers' halo_push_kernel), `count` is its bound
+    const unsigned* countPtr;
+    int radiusBound; // 1: `grad` bounds the per-particle radii (no device scan for the largest radius)
 };
+
+/** Number of particles of a list: host-known, or (halo receive list) read from device memory and clamped to the buffer's capacity. */
+__device__ __forceinline__ unsigned long long listCount(const ListDev& l) {
+    if (!l.countPtr) return l.count;
+    const unsigned long long n = *l.countPtr;
+    return n < l.count ? n : l.count;
+}
 
 /** Values produced on the device and consumed by later kernels without a host round trip. */
 struct DevState {

@@ -1108,7 +1108,8 @@ __global__ void __launch_bounds__(256) normalize_kernel(float* __restrict__ vol,
 __global__ void __launch_bounds__(256) radius_max_kernel(ListDev l, unsigned* rmaxBits) {
     const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
     float rmax = 0.0f;
-    for (unsigned long long j = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; j < l.count; j += stride) {
+    const unsigned long long count = listCount(l);
+    for (unsigned long long j = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; j < count; j += stride) {
         const float r = fetchParticle(l, j).w;
         if (r > 0.0f && isfinite(r)) rmax = fmaxf(rmax, r);
     }

@@ -168,6 +168,9 @@ struct mms_ctx {
     MtGeo mtGeo{};
 
     DevBuf routeCounts, routeOffsets, routeTile;
+    DevBuf haloBuf, haloCounters; // mms_halo_*: receive buffer (float4 records) and counter block of this slab
+    uint64_t haloCap = 0;
+    unsigned haloFrame = 0;       // parity selects the counter word of the current frame
     PinBuf hRoute;
     DevBuf cellCount, cellStart, cursor, tileSums, recsA, recsB, auxA, auxB, vol, rgb, segCount, segOffset, meshPos, meshNrm,
         meshCol, triCount, home, dstate, dirVol, rmaxBuf, bigCells;
@@ -440,7 +443,7 @@ int mms_destroy(mms_ctx* c) {
         DeviceGuard guard(c->device);
         mms_clear_particles(c);
         for (DevBuf* b : {&c->cellCount, &c->cellStart, &c->cursor, &c->tileSums, &c->recsA, &c->recsB, &c->auxA, &c->auxB, &c->vol,
-                 &c->rgb, &c->segCount, &c->segOffset, &c->meshPos, &c->meshNrm, &c->meshCol, &c->triCount, &c->home, &c->dstate, &c->routeCounts, &c->routeOffsets, &c->routeTile, &c->rangeBuf, &c->dirVol, &c->rmaxBuf, &c->bigCells})
+                 &c->rgb, &c->segCount, &c->segOffset, &c->meshPos, &c->meshNrm, &c->meshCol, &c->triCount, &c->home, &c->dstate, &c->routeCounts, &c->routeOffsets, &c->routeTile, &c->rangeBuf, &c->dirVol, &c->rmaxBuf, &c->bigCells, &c->haloBuf, &c->haloCounters})
             b->release();
         for (PinBuf* b : {&c->hState, &c->hVol, &c->hRgb, &c->hPos, &c->hNrm, &c->hCol, &c->hHome, &c->hTri, &c->hRoute, &c->hDir}) b->release();
         cudaStreamSynchronize(c->stream);
@@ -608,7 +611,7 @@ int mms_get_max_radius(mms_ctx* c, float* rmaxOut) {
     float rmax = 0.0f;
     bool perParticle = false;
     for (const ListDev& l : c->lists) {
-        if (l.vtype == MMS_VERT_FLOAT_XYZR) perParticle = true;
+        if (l.vtype == MMS_VERT_FLOAT_XYZR && !l.radiusBound) perParticle = true;
         else if (l.grad > rmax && std::isfinite(l.grad)) rmax = l.grad;
     }
     if (perParticle) {
@@ -617,7 +620,7 @@ int mms_get_max_radius(mms_ctx* c, float* rmaxOut) {
         if (!c->rmaxBuf.ensure(16)) return c->fail(MMS_ERR_NOMEM, "device allocation failed");
         MMS_CUDA(c, cudaMemsetAsync(c->rmaxBuf.p, 0, 4, st));
         for (const ListDev& l : c->lists)
-            if (l.vtype == MMS_VERT_FLOAT_XYZR) {
+            if (l.vtype == MMS_VERT_FLOAT_XYZR && !l.radiusBound) {
                 radius_max_kernel<<<gridFor(l.count, 256, c->smCount * 16), 256, 0, st>>>(l, c->rmaxBuf.as<unsigned>());
                 ++c->launches;
             }
@@ -654,12 +657,12 @@ int mms_compute_density(mms_ctx* c) {
         float rmax = 0.0f;
         bool perParticle = false;
         for (const ListDev& l : c->lists) {
-            if (l.vtype == MMS_VERT_FLOAT_XYZR) perParticle = true;
+            if (l.vtype == MMS_VERT_FLOAT_XYZR && !l.radiusBound) perParticle = true;
             else if (l.grad > rmax && std::isfinite(l.grad)) rmax = l.grad;
         }
         if (perParticle) {
             for (const ListDev& l : c->lists)
-                if (l.vtype == MMS_VERT_FLOAT_XYZR) {
+                if (l.vtype == MMS_VERT_FLOAT_XYZR && !l.radiusBound) {
                     radius_max_kernel<<<gridFor(l.count, 256, c->smCount * 16), 256, 0, st>>>(l, &c->dstate.as<DevState>()->rmaxBits);
                     ++c->launches;
                 }
@@ -1356,6 +1359,76 @@ int mms_route_particles(mms_ctx* c, const mms_list* list, int32_t nslabs, const 
     route_scatter_kernel<<<blocks, 256, 0, st>>>(r, d, chunk, c->routeOffsets.as<unsigned>(), nwarps, static_cast<unsigned*>(send_buf), static_cast<int>(d.vstride / 4));
     ++c->launches;
     MMS_CUDA(c, cudaGetLastError());
+    return MMS_OK;
+}
+
+int mms_halo_buffers(mms_ctx* c, uint64_t cap, void** buf, void** counters) {
+    if (!c || !buf || !counters || cap == 0) return MMS_ERR_INVALID;
+    DeviceGuard guard(c->device);
+    const bool fresh = c->haloCounters.p == nullptr;
+    if (!c->haloBuf.ensure(cap * 16) || !c->haloCounters.ensure(16)) return c->fail(MMS_ERR_NOMEM, "allocation of the halo receive buffer (%llu records) failed",
+        static_cast<unsigned long long>(cap));
+    if (fresh) MMS_CUDA(c, cudaMemset(c->haloCounters.p, 0, 16));
+    c->haloCap = cap;
+    *buf = c->haloBuf.p;
+    *counters = c->haloCounters.p;
+    return MMS_OK;
+}
+
+int mms_halo_push(mms_ctx* c, int32_t nslabs, int32_t mine, const int32_t* plane_lo, const int32_t* plane_hi, void* const* peer_bufs,
+    void* const* peer_counters, uint64_t cap) {
+    if (!c || !plane_lo || !plane_hi || !peer_bufs || !peer_counters || nslabs < 1 || mine < 0 || mine >= nslabs) return MMS_ERR_INVALID;
+    if (!c->haveGrid) return c->fail(MMS_ERR_INVALID, "mms_set_grid has not been called");
+    if (nslabs > kMaxSlabs) return c->fail(MMS_ERR_UNSUPPORTED, "more than %d slabs", kMaxSlabs);
+    if (!c->haloCounters.p) return c->fail(MMS_ERR_INVALID, "mms_halo_buffers has not been called");
+    DeviceGuard guard(c->device);
+    cudaStream_t st = c->stream;
+    if (c->uploadPending) MMS_CUDA(c, cudaStreamWaitEvent(st, c->uploadDone, 0)); // (compute_density waits again; harmless)
+    const Geo g = makeGeo(c);
+    RouteGeo r{};
+    r.zmin = g.mn[2], r.sdz = g.sd[2], r.sz = g.s[2], r.cyc = g.cyc[2], r.nslabs = nslabs;
+    HaloPeers hp{};
+    ++c->haloFrame;
+    const unsigned word = c->haloFrame & 1u;
+    for (int i = 0; i < nslabs; ++i) {
+        r.lo[i] = plane_lo[i], r.hi[i] = plane_hi[i];
+        if (i != mine && plane_lo[i] <= plane_hi[i] && peer_bufs[i] && peer_counters[i]) {
+            r.enabled |= 1u << i;
+            hp.buf[i] = static_cast<float4*>(peer_bufs[i]);
+            hp.counter[i] = static_cast<unsigned*>(peer_counters[i]) + word;
+        }
+    }
+    hp.cap = static_cast<unsigned>(std::min<uint64_t>(cap, 0xffffffffull));
+    r.sigma = g.sigma, r.radscale = g.radscale, r.gausslim = g.gausslim, r.mode = g.mode;
+    // my own counter of the NEXT frame: nobody pushes into it before this frame's "all pushes complete" point
+    MMS_CUDA(c, cudaMemsetAsync(c->haloCounters.as<unsigned>() + (word ^ 1u), 0, 4, st));
+    if (r.enabled)
+        for (const ListDev& l : c->lists) {
+            if (l.countPtr) continue; // a received list is never forwarded
+            halo_push_kernel<<<gridFor(l.count, 256, c->smCount * 16), 256, 0, st>>>(r, l, hp);
+            ++c->launches;
+        }
+    MMS_CUDA(c, cudaGetLastError());
+    return MMS_OK;
+}
+
+int mms_halo_receive(mms_ctx* c, float radius_bound) {
+    if (!c) return MMS_ERR_INVALID;
+    if (!c->haloCounters.p || !c->haloCap) return c->fail(MMS_ERR_INVALID, "mms_halo_buffers has not been called");
+    if (c->lists.size() + 1 > static_cast<size_t>(kMaxLists)) return c->fail(MMS_ERR_UNSUPPORTED, "more than %d particle lists", kMaxLists);
+    ListDev d{};
+    d.vtx = static_cast<const char*>(c->haloBuf.p);
+    d.count = c->haloCap; // the bound; the length is read on the device
+    d.countPtr = c->haloCounters.as<unsigned>() + (c->haloFrame & 1u);
+    d.base = c->nparticles;
+    d.vtype = MMS_VERT_FLOAT_XYZR;
+    d.vstride = 16;
+    d.valign = 16;
+    d.calign = 4;
+    d.grad = radius_bound;
+    d.radiusBound = 1;
+    c->lists.push_back(d);
+    c->nparticles += c->haloCap;
     return MMS_OK;
 }
 

@@ -101,4 +101,40 @@ __global__ void __launch_bounds__(256) route_scatter_kernel(RouteGeo r, ListDev 
     }
 }
 
+/** Receive buffers of the other slabs (peer memory: CUDA IPC mappings or peer access) and their record counters. */
+struct HaloPeers {
+    float4* buf[kMaxSlabs];
+    unsigned* counter[kMaxSlabs];
+    unsigned cap;
+};
+
+/**
+ * Halo exchange in ONE kernel, no host round trip, no collective: every record of the list that another slab needs (routeMask; the
+ * caller switches its own slab off) is appended, as an x y z r record, straight to that slab's receive buffer in peer memory.  A warp
+ * claims its slots with one system-scope atomicAdd per destination (ballot-aggregated), so the NVLink atomics stay few.  The order of
+ * arrival is arbitrary -- the canonical in-cell order of the binning makes the density independent of it.
+ */
+__global__ void __launch_bounds__(256) halo_push_kernel(RouteGeo r, ListDev l, HaloPeers hp) {
+    const unsigned lane = threadIdx.x & 31, lt = (1u << lane) - 1u;
+    const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
+    const unsigned long long count = listCount(l), rounded = (count + 31) & ~31ull;
+    for (unsigned long long j = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; j < rounded; j += stride) {
+        const unsigned m = j < count ? routeMask(r, l, j) : 0u;
+        unsigned all = __reduce_or_sync(0xffffffffu, m);
+        if (!all) continue;
+        const float4 p = m ? fetchParticle(l, j) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        for (; all; all &= all - 1) {
+            const int d = __ffs(all) - 1;
+            const unsigned b = __ballot_sync(0xffffffffu, (m >> d) & 1u);
+            unsigned base = 0;
+            if (lane == static_cast<unsigned>(__ffs(b) - 1)) base = atomicAdd_system(hp.counter[d], static_cast<unsigned>(__popc(b)));
+            base = __shfl_sync(0xffffffffu, base, __ffs(b) - 1);
+            if ((m >> d) & 1u) {
+                const unsigned slot = base + __popc(b & lt);
+                if (slot < hp.cap) hp.buf[d][slot] = p; // (an overflow shows in the counter: the receiver reports it)
+            }
+        }
+    }
+}
+
 } // namespace mms

@@ -116,7 +116,8 @@ def gather_rows_to_root(local, rank, world, out=None):
 class SlabJob:
     """The bench/test driver: generates this rank's chunk of the synthetic frame and runs full steps."""
 
-    def __init__(self, w, rank, world, local, iso, radius, sigma=1.0, cyclic=(True, True, True), normalize=True, gather="host"):
+    def __init__(self, w, rank, world, local, iso, radius, sigma=1.0, cyclic=(True, True, True), normalize=True, gather="host",
+                 exchange="fused"):
         import torch
         import megamol_b200 as mm
         from megamol_b200 import synth
@@ -130,6 +131,13 @@ class SlabJob:
         #   "fused" every rank's mc_emit_kernel stores straight into rank 0's buffers over NVLink (CUDA IPC): emit + gather in one kernel
         #   "nccl"  emit locally, then NCCL send/recv to rank 0 (the baseline the fused kernel is compared with)
         self.gather = gather
+        # how the halo particles travel:
+        #   "fused" (default) every rank's halo_push_kernel appends what the other slabs need straight to THEIR receive buffers (CUDA IPC
+        #           mappings, stores and counter atomics over NVLink); the only collective is a one-word all-reduce that orders "all pushes
+        #           done" on the stream.  No host synchronisation, no count matrix, no all-to-all.
+        #   "nccl"  the round-1 path, kept as the baseline: routing kernels -> host sync for the counts -> count matrix all-gather ->
+        #           all-to-all-v
+        self.exchange = exchange
         self._root = dict(gen=0, cap=0, pos=None, nrm=None)   # rank 0: owned buffers; others: IPC mappings
         self.dev = torch.device("cuda", local)
         self.normalize = normalize
@@ -197,6 +205,8 @@ class SlabJob:
                 self.surf.set_slab(self.me["z0"], self.me["nz"], self.me["cell_z0"], self.me["cell_nz"])
             self.surf.set_params(mode=0, aggregator=0, normalize=int(normalize), defer_normalize=int(world > 1), sigma=sigma)
         self.sdz = float(np.float32(self.box[2]) / np.float32(self.res[2] - 1))
+        if world > 1 and self.exchange == "fused":
+            self._halo_setup()
         self._keep = []
         self.last = {}
         self.gather_ms = 0.0
@@ -244,6 +254,52 @@ class SlabJob:
         self.barrier()
         return ms
 
+    def _halo_setup(self):
+        """Once: every rank's receive buffer and counter block, exported over CUDA IPC and mapped by all the others."""
+        import ctypes as C
+        import torch.distributed as dist
+        L = self.surf.L
+        # a slab receives at most what its neighbours' halos hold; the frames here are z-ordered, so a rank's own share bounds it amply.
+        # (An overflow is detected on the device and reported by the next host-synchronising call.)
+        self._halo_cap = self.n_local + (1 << 20)
+        buf, ctr = self.surf.halo_buffers(self._halo_cap)
+        mine = []
+        for ptr in (buf, ctr):
+            h = (C.c_ubyte * 64)()
+            if L.mms_ipc_export(self.local, C.c_void_p(ptr), h):
+                raise RuntimeError("cudaIpcGetMemHandle failed")
+            mine.append(bytes(h))
+        allh = [None] * self.world
+        dist.all_gather_object(allh, (mine[0], mine[1], self._halo_cap))
+        self._peer_bufs, self._peer_ctrs, self._peer_open = [], [], []
+        caps = []
+        for g, (hb, hc, cap) in enumerate(allh):
+            caps.append(cap)
+            if g == self.rank:
+                self._peer_bufs.append(buf)
+                self._peer_ctrs.append(ctr)
+                continue
+            ptrs = []
+            for raw in (hb, hc):
+                hh = (C.c_ubyte * 64).from_buffer_copy(raw)
+                p = C.c_void_p()
+                if L.mms_ipc_open(self.local, hh, C.byref(p)):
+                    raise RuntimeError("cudaIpcOpenMemHandle failed (is peer access available between the GPUs?)")
+                ptrs.append(p.value)
+                self._peer_open.append(p.value)
+            self._peer_bufs.append(ptrs[0])
+            self._peer_ctrs.append(ptrs[1])
+        self._peer_cap = min(caps)
+        self._tick = self.torch.zeros(1, device=self.dev, dtype=self.torch.float32)
+
+    def _halo(self):
+        """Fused halo exchange of the lists pushed so far: one push kernel, a one-word all-reduce as the stream-ordered "all pushes are
+        complete" point, then the received records join the frame as one more list (its length stays on the device)."""
+        import torch.distributed as dist
+        self.surf.halo_push(self.slabs, self.rank, self._peer_bufs, self._peer_ctrs, self._peer_cap)
+        dist.all_reduce(self._tick)
+        self.surf.halo_receive(self.radius)
+
     def _exchange(self, xyz_dev):
         """Halo exchange.  The rank's own chunk stays where it is (the binning kernel drops what does not reach the slab); only the records
         OTHER slabs need are extracted (libmmsurf's routing kernels with the own slab switched off: mms_route_particles) and travel in one
@@ -269,6 +325,13 @@ class SlabJob:
         recv = self._recv[:nrecv]
         dist.all_to_all_single(recv, self._send[:sum(sc)], output_split_sizes=rc, input_split_sizes=sc)
         return recv
+
+    def _more(self, xyz_dev):
+        """-> (extra (pointer, count) pieces for _compute, number of received records or -1 where only the device knows it)"""
+        if self.exchange == "fused":
+            return (), -1
+        recv = self._exchange(xyz_dev)
+        return ((recv.data_ptr(), recv.shape[0]),), int(recv.shape[0])
 
     def _gather_mesh(self):
         """all-gather of triangle counts, then the per-slab vertex/normal arrays travel to rank 0 over NCCL."""
@@ -381,6 +444,12 @@ class SlabJob:
             s.push_particles([dict(vtx=xyz_ptr, vtx_type=2, vtx_stride=32, count=n, col=xyz_ptr + 16, col_type=4, col_stride=32)])
         else:
             s.push_particles([dict(vtx=p, vtx_type=1, count=c, global_radius=self.radius) for p, c in ((xyz_ptr, n),) + tuple(more) if c > 0])
+        if self.world > 1 and self.exchange == "fused":
+            ev0, ev1 = self.torch.cuda.Event(enable_timing=True), self.torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            self._halo()
+            ev1.record()
+            self._halo_events = (ev0, ev1)
         s.compute_density()
         if self.world > 1 and self.normalize:
             # global range with ONE max-all-reduce of {-min, max}, in place on the library's device buffer: no host round trip
@@ -405,10 +474,10 @@ class SlabJob:
             # size decides an allocation (routing counts, count matrix, triangle count)
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
             ev[0].record()
-            recv = self._exchange(self.d_xyz)
+            more, nrecv = self._more(self.d_xyz)
             ev[1].record()
             fused = self.gather == "fused"
-            self._compute(self.d_xyz.data_ptr(), self.n_local, extract=not fused, more=((recv.data_ptr(), recv.shape[0]),))
+            self._compute(self.d_xyz.data_ptr(), self.n_local, extract=not fused, more=more)
             ev[2].record()
             if fused:
                 self._emit_to_root()
@@ -418,9 +487,9 @@ class SlabJob:
                 self._allgather_counts()
             ev[3].record()
             torch.cuda.current_stream().synchronize()
-            self.last["exchange_ms"] = ev[0].elapsed_time(ev[1])
+            self.last["exchange_ms"] = ev[0].elapsed_time(ev[1]) if self.exchange != "fused" else self._halo_events[0].elapsed_time(self._halo_events[1])
             self.last["gather_ms"] = ev[2].elapsed_time(ev[3])
-            self.last["n_recv"] = int(recv.shape[0])
+            self.last["n_recv"] = nrecv
         self.last["n_in"] = self.n_local
 
     def step_e2e(self, mesh_to_host=True):
@@ -435,18 +504,18 @@ class SlabJob:
                 self.surf.get_mesh(copy=False, colours=self.protein)
         elif not mesh_to_host:
             d = self.h_xyz.to(self.dev, non_blocking=True)
-            recv = self._exchange(d)
+            more, _ = self._more(d)
             self._keep = [d]
-            self._compute(d.data_ptr(), self.n_local, more=((recv.data_ptr(), recv.shape[0]),), prefetch=True)
+            self._compute(d.data_ptr(), self.n_local, more=more, prefetch=True)
             self.surf.get_density(copy=False)
             self._allgather_counts()
             torch.cuda.current_stream().synchronize()
         else:
             d = self.h_xyz.to(self.dev, non_blocking=True)
-            recv = self._exchange(d)
+            more, _ = self._more(d)
             self._keep = [d]
             fused = self.gather == "fused"
-            self._compute(d.data_ptr(), self.n_local, extract=not fused, more=((recv.data_ptr(), recv.shape[0]),), prefetch=True)
+            self._compute(d.data_ptr(), self.n_local, extract=not fused, more=more, prefetch=True)
             self.surf.get_density(copy=False)
             if fused:
                 self._emit_to_root()
@@ -554,9 +623,13 @@ class SlabJob:
                        "over its own PCIe link"}[self.gather]
         if self.w.get("fixed_total"):
             return (f"{self.w['name']} on {self.world} GPUs (strong scaling): {self.n_total} particles -> "
-                    f"{self.res[0]}x{self.res[1]}x{self.res[2]}, z-slabs with halo, particles exchanged with NCCL all-to-all-v, {how}")
+                    f"{self.res[0]}x{self.res[1]}x{self.res[2]}, z-slabs with halo, {self._exchange_how()}, {how}")
         return (f"{self.w['name']} weak-scaled x{self.world} along z: {self.n_total} particles -> "
-                f"{self.res[0]}x{self.res[1]}x{self.res[2]}, z-slabs with halo, particles exchanged with NCCL all-to-all-v, {how}")
+                f"{self.res[0]}x{self.res[1]}x{self.res[2]}, z-slabs with halo, {self._exchange_how()}, {how}")
+
+    def _exchange_how(self):
+        return ("halo particles pushed straight into the neighbours' receive buffers over NVLink (fused kernel, CUDA IPC)" if self.exchange == "fused"
+                else "particles exchanged with NCCL all-to-all-v")
 
     def close(self, destroy_group=True):
         R = self._root
@@ -564,6 +637,9 @@ class SlabJob:
             self.torch.cuda.synchronize()
             import torch.distributed as dist
             dist.barrier()
+            for p in getattr(self, "_peer_open", []):  # halo receive buffers / counters of the other ranks
+                self.surf.L.mms_ipc_close(self.local, p)
+            self._peer_open = []
             if self.rank != 0:  # importers close their mappings first ...
                 for k in ("pos", "nrm"):
                     if R[k]:

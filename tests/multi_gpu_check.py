@@ -1,5 +1,6 @@
 """Run under torchrun on >= 2 GPUs (tests/test_gpu_multi.py spawns it): the z-slab pipeline with real NCCL exchange, device-side range
-all-reduce and every mesh-gather mode must reproduce the single-GPU result bit for bit."""
+all-reduce, both halo-exchange paths (fused push over CUDA IPC / NCCL all-to-all-v) and every mesh-gather mode must reproduce the
+single-GPU result bit for bit."""
 import os
 import sys
 
@@ -20,8 +21,8 @@ def main():
     w = dict(name="check", n=150_000, res=(64, 48, 40), kind="uniform", box=32.0)
     iso, radius = 0.35, 0.7
     ok = True
-    for gather in ("nccl", "fused", "host"):
-        job = slabs.SlabJob(w, rank, world, local, iso=iso, radius=radius, gather=gather)
+    for gather, exchange in (("host", "fused"), ("nccl", "fused"), ("fused", "fused"), ("host", "nccl")):
+        job = slabs.SlabJob(w, rank, world, local, iso=iso, radius=radius, gather=gather, exchange=exchange)
         for _ in range(2):
             job.step_device()
         # volume: every rank's own cell planes (+ the last plane on the last rank)
@@ -59,7 +60,8 @@ def main():
             if not good:
                 print(f"   volume equal {ev} (max abs diff {np.abs(v - ref).max():.3e}, differing planes {np.unique(np.argwhere(v != ref)[:, 0])[:12]}), "
                       f"pos equal {ep}, nrm equal {en}, counts {counts} total {total} vs {ntri}", flush=True)
-            print(f"[multi_gpu_check] gather={gather} world={world} triangles={ntri} -> {'OK' if good else 'MISMATCH'}", flush=True)
+            print(f"[multi_gpu_check] exchange={exchange} gather={gather} world={world} triangles={ntri} exchange_ms={job.last.get('exchange_ms', 0):.3f} "
+                  f"-> {'OK' if good else 'MISMATCH'}", flush=True)
             ok = ok and good
         job.close_keep_group() if hasattr(job, "close_keep_group") else None
         dist.barrier()
