@@ -246,6 +246,30 @@ int mms_halo_push(mms_ctx* ctx, int32_t nslabs, int32_t my_slab, const int32_t* 
  * may send -- it sizes the sort cells without a device scan).  Call once every peer's mms_halo_push of this frame has completed. */
 int mms_halo_receive(mms_ctx* ctx, float radius_bound);
 
+/* ---- several GPUs behind ONE handle, inside one process (the drop-in modules' `devices` parameter) ---------------------------------
+ * The z-slab decomposition of SURVEY 8e driven from C: one context per device, slab g owns cell layers [g(sz-1)/G, (g+1)(sz-1)/G) and
+ * computes one extra density plane on each interior side, every list is split into G contiguous shares that travel over each GPU's own
+ * PCIe link, the halo particles go through mms_halo_push / mms_halo_receive with peer access (ordered by CUDA events, no host
+ * synchronisation), the global density range is combined by a kernel reading the peers' ranges (instead of the reference's
+ * volume-sized MPI_Allreduce, plugins/datatools/src/MPIVolumeAggregator.cpp:94-152).  Results are bit-identical to one GPU.
+ * Scalar ParticlesToDensity modes (aggregators 0 / 1 need no per-particle extras beyond x y z r: aggregator 0 only for G > 1). */
+typedef struct mms_slabs mms_slabs;
+int mms_slabs_create(mms_slabs** out, const int32_t* devices, int32_t ndevices);
+int mms_slabs_destroy(mms_slabs* s);
+const char* mms_slabs_last_error(const mms_slabs* s); /* s may be NULL: error of the last failed mms_slabs_create */
+int32_t mms_slabs_count(const mms_slabs* s);
+mms_ctx* mms_slabs_context(mms_slabs* s, int32_t i); /* the i-th device's context (timings, device pointers, mms_adopt_density) */
+int mms_slabs_set_grid(mms_slabs* s, const mms_grid* grid);
+int mms_slabs_set_params(mms_slabs* s, const mms_params* params);
+int mms_slabs_clear_particles(mms_slabs* s);
+int mms_slabs_push_particles(mms_slabs* s, int32_t nlists, const mms_list* lists); /* host lists; split into contiguous shares */
+int mms_slabs_compute_density(mms_slabs* s);
+int mms_slabs_get_density_range(mms_slabs* s, float minmax[2]);
+int mms_slabs_get_density(mms_slabs* s, const float** host_volume); /* the WHOLE volume, library-owned pinned memory */
+int mms_slabs_extract_isosurface(mms_slabs* s, float isovalue);
+/* The whole mesh in cell-linear order (= the single-GPU order), library-owned pinned memory; every slab is copied over its own link. */
+int mms_slabs_get_mesh(mms_slabs* s, uint64_t* nverts, const float** positions, const float** normals);
+
 /* Device buffers that can be shared between the per-GPU processes of one node (CUDA IPC over NVLink / PCIe P2P). */
 int mms_device_alloc(int32_t device, size_t bytes, void** ptr);
 int mms_device_free(int32_t device, void* ptr);

@@ -4,4 +4,4 @@ The product is libmmsurf.so (CUDA kernels for sm_100a behind the C ABI of includ
 modules in plugin/b200surf.  This package is the thin Python host layer used by the tests and by bench.py:
 ctypes binding (api.py), synthetic workloads (synth.py) and the multi-GPU z-slab driver (slabs.py).
 """
-from .api import Surf, MmsError, lib_path, load_library  # noqa: F401
+from .api import Surf, SurfGroup, MmsError, lib_path, load_library  # noqa: F401

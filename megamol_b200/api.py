@@ -18,7 +18,7 @@ ISO_MARCHING_CUBES, ISO_MARCHING_TETS = 0, 1
 EXPORTS = ["mms_create", "mms_destroy", "mms_last_error", "mms_set_grid", "mms_set_slab", "mms_set_params",
            "mms_clear_particles", "mms_push_particles", "mms_push_particles_dir", "mms_get_vector_field", "mms_get_vector_field_device", "mms_get_max_radius", "mms_compute_density", "mms_get_density_range", "mms_normalize", "mms_density_range_device", "mms_normalize_device", "mms_set_stream",
            "mms_get_density", "mms_prefetch_density", "mms_get_density_device", "mms_set_density", "mms_adopt_density", "mms_extract_isosurface", "mms_set_isosurface_mode", "mms_count_isosurface", "mms_emit_isosurface", "mms_device_alloc",
-           "mms_device_free", "mms_route_particles", "mms_halo_buffers", "mms_halo_push", "mms_halo_receive", "mms_ipc_export", "mms_ipc_open", "mms_ipc_close", "mms_get_mesh",
+           "mms_device_free", "mms_route_particles", "mms_halo_buffers", "mms_halo_push", "mms_halo_receive", "mms_slabs_create", "mms_slabs_destroy", "mms_slabs_last_error", "mms_slabs_count", "mms_slabs_context", "mms_slabs_set_grid", "mms_slabs_set_params", "mms_slabs_clear_particles", "mms_slabs_push_particles", "mms_slabs_compute_density", "mms_slabs_get_density_range", "mms_slabs_get_density", "mms_slabs_extract_isosurface", "mms_slabs_get_mesh", "mms_ipc_export", "mms_ipc_open", "mms_ipc_close", "mms_get_mesh",
            "mms_get_mesh_device", "mms_get_home_voxels", "mms_get_cell_tricounts", "mms_get_timings", "mms_synchronize",
            "mms_timer_start", "mms_timer_stop", "mms_launch_count", "mms_alloc_pinned", "mms_free_pinned", "mms_version", "mms_mmpld_open", "mms_mmpld_close",
            "mms_mmpld_last_error", "mms_mmpld_info", "mms_mmpld_prefetch", "mms_mmpld_read_frame"]
@@ -107,6 +107,22 @@ def load_library():
     L.mms_halo_buffers.argtypes = [vp, C.c_uint64, C.POINTER(vp), C.POINTER(vp)]
     L.mms_halo_push.argtypes = [vp, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(vp), C.POINTER(vp), C.c_uint64]
     L.mms_halo_receive.argtypes = [vp, C.c_float]
+    L.mms_slabs_create.argtypes = [C.POINTER(vp), C.POINTER(C.c_int32), C.c_int32]
+    L.mms_slabs_destroy.argtypes = [vp]
+    L.mms_slabs_last_error.argtypes = [vp]
+    L.mms_slabs_last_error.restype = C.c_char_p
+    L.mms_slabs_count.argtypes = [vp]
+    L.mms_slabs_context.argtypes = [vp, C.c_int32]
+    L.mms_slabs_context.restype = vp
+    L.mms_slabs_set_grid.argtypes = [vp, C.POINTER(MmsGrid)]
+    L.mms_slabs_set_params.argtypes = [vp, C.POINTER(MmsParams)]
+    L.mms_slabs_clear_particles.argtypes = [vp]
+    L.mms_slabs_push_particles.argtypes = [vp, C.c_int32, C.POINTER(MmsList)]
+    L.mms_slabs_compute_density.argtypes = [vp]
+    L.mms_slabs_get_density_range.argtypes = [vp, C.POINTER(C.c_float)]
+    L.mms_slabs_get_density.argtypes = [vp, C.POINTER(vp)]
+    L.mms_slabs_extract_isosurface.argtypes = [vp, C.c_float]
+    L.mms_slabs_get_mesh.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(vp), C.POINTER(vp)]
     L.mms_ipc_export.argtypes = [C.c_int32, vp, C.POINTER(C.c_ubyte)]
     L.mms_ipc_open.argtypes = [C.c_int32, C.POINTER(C.c_ubyte), C.POINTER(vp)]
     L.mms_ipc_close.argtypes = [C.c_int32, vp]
@@ -420,3 +436,77 @@ class Surf:
 
     def launch_count(self):
         return int(self.L.mms_launch_count(self.h))
+
+
+class SurfGroup:
+    """Several GPUs behind one handle inside one process (mms_slabs_*, include/mmsurf.h): z-slabs with halo, fused halo push over peer
+    memory, global range by peer reads.  Host lists in, whole host volume / whole host mesh out; bit-identical to one GPU."""
+
+    def __init__(self, devices):
+        self.L = load_library()
+        self.h = C.c_void_p()
+        devs = (C.c_int32 * len(devices))(*[int(d) for d in devices])
+        rc = self.L.mms_slabs_create(C.byref(self.h), devs, len(devices))
+        if rc:
+            raise MmsError(rc, self.L.mms_slabs_last_error(None).decode())
+        self.params = MmsParams(mode=0, aggregator=0, normalize=1, defer_normalize=0, sigma=1.0, radscale=1.0, gausslim=3.0)
+        self.res = None
+        self._keep = []
+
+    def _chk(self, rc):
+        if rc:
+            raise MmsError(rc, self.L.mms_slabs_last_error(self.h).decode())
+
+    def close(self):
+        if self.h:
+            self.L.mms_slabs_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def set_grid(self, bbox_min, bbox_extent, res, cyclic=(True, True, True)):
+        g = MmsGrid()
+        for a in range(3):
+            g.min[a], g.extent[a], g.res[a], g.cyclic[a] = float(bbox_min[a]), float(bbox_extent[a]), int(res[a]), int(bool(cyclic[a]))
+        self._chk(self.L.mms_slabs_set_grid(self.h, C.byref(g)))
+        self.res = tuple(int(r) for r in res)
+
+    def set_params(self, **kw):
+        for k, v in kw.items():
+            setattr(self.params, k, v)
+        self._chk(self.L.mms_slabs_set_params(self.h, C.byref(self.params)))
+
+    def clear_particles(self):
+        self._chk(self.L.mms_slabs_clear_particles(self.h))
+        self._keep = []
+
+    def push_particles(self, lists):
+        arr = (MmsList * len(lists))()
+        for i, l in enumerate(lists):
+            v = np.ascontiguousarray(l["vtx"])
+            self._keep.append(v)
+            arr[i].vtx, arr[i].vtx_type, arr[i].vtx_stride, arr[i].count = v.ctypes.data, l["vtx_type"], l.get("vtx_stride", 0), l["count"]
+            arr[i].global_radius = l.get("global_radius", 0.5)
+        self._chk(self.L.mms_slabs_push_particles(self.h, len(lists), arr))
+
+    def compute_density(self):
+        self._chk(self.L.mms_slabs_compute_density(self.h))
+
+    def density_range(self):
+        mm = (C.c_float * 2)()
+        self._chk(self.L.mms_slabs_get_density_range(self.h, mm))
+        return float(mm[0]), float(mm[1])
+
+    def get_density(self):
+        p = C.c_void_p()
+        self._chk(self.L.mms_slabs_get_density(self.h, C.byref(p)))
+        return _np_view(p.value, (self.res[2], self.res[1], self.res[0]), np.float32).copy()
+
+    def extract_isosurface(self, iso):
+        self._chk(self.L.mms_slabs_extract_isosurface(self.h, float(iso)))
+
+    def get_mesh(self):
+        n, p, q = C.c_uint64(), C.c_void_p(), C.c_void_p()
+        self._chk(self.L.mms_slabs_get_mesh(self.h, C.byref(n), C.byref(p), C.byref(q)))
+        nt = n.value // 3
+        if nt == 0:
+            return np.zeros((0, 3, 3), np.float32), np.zeros((0, 3, 3), np.float32)
+        return _np_view(p.value, (nt, 3, 3), np.float32).copy(), _np_view(q.value, (nt, 3, 3), np.float32).copy()

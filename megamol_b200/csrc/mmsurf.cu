@@ -156,7 +156,7 @@ struct mms_ctx {
     McGeo mcGeo{};
     cudaStream_t ownStream = nullptr;
     DevBuf rangeBuf; // {-min, max} as floats for device-side all-reduce + normalise
-    bool haveCount = false, meshExternal = false;
+    bool haveCount = false, meshExternal = false, countPending = false;
     float qsAc = 0.0f;    // MMS_MODE_QS_GAUSS_REFCELLS: the reference's acceleration grid of this frame
     int qsCells[3] = {1, 1, 1};
     const float* adoptedVol = nullptr; // mms_adopt_density: another context's volume (and colour volume), by reference
@@ -323,6 +323,17 @@ __global__ void __launch_bounds__(256) normalize_state_kernel(float* __restrict_
         vol[i] = __fmul_rn(__fsub_rn(vol[i], mn), rcp);
 }
 
+
+/** Global density range of a slab group: every device reads all the slabs' {-min, max} (peer memory) and keeps the maximum of each. */
+struct RangePeers {
+    const float* r[16];
+    int n;
+};
+__global__ void range_combine_kernel(RangePeers p, float* __restrict__ out) {
+    float a = -INFINITY, b = -INFINITY;
+    for (int i = 0; i < p.n; ++i) a = fmaxf(a, p.r[i][0]), b = fmaxf(b, p.r[i][1]);
+    out[0] = a, out[1] = b;
+}
 
 size_t emitSmemBytes(bool colour) { return sizeof(McEmitShared) + 128 + (colour ? E_RECS * sizeof(float4) : 0); }
 size_t emitV4SmemBytes(bool colour) { return sizeof(v4::McEmitV4Shared) + 128 + (colour ? v4::E_EDGES * sizeof(float4) : 0); }
@@ -1052,10 +1063,12 @@ int mms_get_vector_field_device(mms_ctx* c, const float** dvec, const float** dm
     return MMS_OK;
 }
 
-int mms_count_isosurface(mms_ctx* c, float iso, uint64_t* ntris) {
+/** Count, first half: everything up to (not including) the host round trip.  countPending tells countFinish whether kernels are in flight. */
+static int countLaunch(mms_ctx* c, float iso) {
     if (!c) return MMS_ERR_INVALID;
     if (!c->haveDensity) return c->fail(MMS_ERR_INVALID, "no density has been computed");
     DeviceGuard guard(c->device);
+    c->countPending = false;
     McGeo m{};
     m.sx = c->grid.res[0], m.sy = c->grid.res[1];
     m.nzPlanes = c->nz, m.zPlane0 = c->z0, m.szGlobal = c->grid.res[2];
@@ -1076,7 +1089,6 @@ int mms_count_isosurface(mms_ctx* c, float iso, uint64_t* ntris) {
     c->ntris = 0;
     c->haveCount = false; // set once the count has run and the device reported no error
     c->haveMesh = false;
-    if (ntris) *ntris = 0;
     c->rec(EV_MC0);
     if (m.cnz <= 0) {
         c->haveCount = true; // an empty slab: nothing to count, nothing to emit
@@ -1121,13 +1133,30 @@ int mms_count_isosurface(mms_ctx* c, float iso, uint64_t* ntris) {
         &ds->totalTris, st, c->launches);
     publish_state_kernel<<<1, 1, 0, st>>>(c->dstate.as<DevState>(), c->hState.as<DevState>());
     ++c->launches;
-    MMS_CUDA(c, cudaStreamSynchronize(st)); // the one host round trip: the mesh size decides the allocation
+    MMS_CUDA(c, cudaGetLastError());
+    c->countPending = true;
+    return MMS_OK;
+}
+
+/** Count, second half: the one host round trip (the mesh size decides the allocation). */
+static int countFinish(mms_ctx* c, uint64_t* ntris) {
+    if (ntris) *ntris = 0;
+    if (!c->countPending) return MMS_OK; // empty slab
+    DeviceGuard guard(c->device);
+    c->countPending = false;
+    MMS_CUDA(c, cudaStreamSynchronize(c->stream));
     // the state block also carries the density kernels' error flag: a truncated volume must not become a mesh
     if (int rc = deviceErrorFromState(c)) return rc;
     c->ntris = c->hState.as<DevState>()->totalTris;
     c->haveCount = true;
     if (ntris) *ntris = c->ntris;
     return MMS_OK;
+}
+
+int mms_count_isosurface(mms_ctx* c, float iso, uint64_t* ntris) {
+    if (ntris) *ntris = 0;
+    if (int rc = countLaunch(c, iso)) return rc;
+    return countFinish(c, ntris);
 }
 
 int mms_emit_isosurface(mms_ctx* c, float* pos, float* nrm, float* col, uint64_t first_triangle) {
@@ -1509,4 +1538,340 @@ void mms_free_pinned(void* p) {
     if (p) cudaFreeHost(p);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------------
+// several GPUs behind one handle (single process)
+// ---------------------------------------------------------------------------------------------------------------------------------
 } // extern "C"
+
+struct mms_slabs {
+    std::vector<mms_ctx*> ctx;
+    std::vector<int> dev;
+    std::string err;
+    mms_grid grid{};
+    bool haveGrid = false, haveDensity = false, haveMesh = false;
+    mms_params params{};
+    struct Plan {
+        int cellZ0, cellNz, z0, nz;
+    };
+    std::vector<Plan> plan;
+    std::vector<cudaEvent_t> evPushed, evRange;
+    std::vector<void*> haloBuf, haloCtr;
+    std::vector<DevBuf> combined; // per device: the combined {-min, max}
+    uint64_t haloCap = 0, nparticles = 0;
+    float radiusBound = 0.0f;
+    bool perParticleRadii = false;
+    PinBuf hVol, hPos, hNrm;
+    uint64_t ntris = 0;
+    int fail(int code, const char* fmt, ...) {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof(buf), fmt, ap);
+        va_end(ap);
+        err = buf;
+        return code;
+    }
+    int failFrom(int code, mms_ctx* c) {
+        err = c->err;
+        return code;
+    }
+};
+
+extern "C" {
+
+const char* mms_slabs_last_error(const mms_slabs* s) { return s ? s->err.c_str() : g_createError.c_str(); }
+int32_t mms_slabs_count(const mms_slabs* s) { return s ? static_cast<int32_t>(s->ctx.size()) : 0; }
+mms_ctx* mms_slabs_context(mms_slabs* s, int32_t i) { return (s && i >= 0 && i < static_cast<int32_t>(s->ctx.size())) ? s->ctx[i] : nullptr; }
+
+int mms_slabs_destroy(mms_slabs* s) {
+    if (!s) return MMS_ERR_INVALID;
+    for (size_t g = 0; g < s->ctx.size(); ++g) {
+        DeviceGuard guard(s->dev[g]);
+        cudaStreamSynchronize(s->ctx[g]->stream);
+        if (g < s->evPushed.size()) cudaEventDestroy(s->evPushed[g]), cudaEventDestroy(s->evRange[g]);
+        if (g < s->combined.size()) s->combined[g].release();
+    }
+    for (mms_ctx* c : s->ctx) mms_destroy(c);
+    s->hVol.release(), s->hPos.release(), s->hNrm.release();
+    delete s;
+    return MMS_OK;
+}
+
+int mms_slabs_create(mms_slabs** out, const int32_t* devices, int32_t n) {
+    if (!out || !devices || n < 1) return MMS_ERR_INVALID;
+    *out = nullptr;
+    if (n > kMaxSlabs) {
+        g_createError = "too many devices for one slab group";
+        return MMS_ERR_UNSUPPORTED;
+    }
+    auto* s = new mms_slabs();
+    for (int g = 0; g < n; ++g) {
+        mms_config cfg{devices[g], 0};
+        mms_ctx* c = nullptr;
+        if (int rc = mms_create(&c, &cfg)) {
+            mms_slabs_destroy(s);
+            return rc;
+        }
+        s->ctx.push_back(c);
+        s->dev.push_back(devices[g]);
+    }
+    s->combined.resize(n);
+    for (int g = 0; g < n; ++g) {
+        DeviceGuard guard(devices[g]);
+        for (int h = 0; h < n; ++h) {
+            if (h == g || devices[h] == devices[g]) continue;
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, devices[g], devices[h]);
+            if (!can) {
+                g_createError = "the devices of a slab group need peer access to each other (NVLink / PCIe P2P)";
+                mms_slabs_destroy(s);
+                return MMS_ERR_UNSUPPORTED;
+            }
+            const cudaError_t e = cudaDeviceEnablePeerAccess(devices[h], 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+                g_createError = std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e);
+                cudaGetLastError();
+                mms_slabs_destroy(s);
+                return MMS_ERR_CUDA;
+            }
+            cudaGetLastError();
+        }
+        cudaEvent_t a = nullptr, b = nullptr;
+        cudaEventCreateWithFlags(&a, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&b, cudaEventDisableTiming);
+        s->evPushed.push_back(a), s->evRange.push_back(b);
+        if (!s->combined[g].ensure(16)) {
+            g_createError = "allocation failed";
+            mms_slabs_destroy(s);
+            return MMS_ERR_NOMEM;
+        }
+    }
+    s->params = s->ctx[0]->params;
+    *out = s;
+    return MMS_OK;
+}
+
+int mms_slabs_set_grid(mms_slabs* s, const mms_grid* grid) {
+    if (!s || !grid) return MMS_ERR_INVALID;
+    const int G = static_cast<int>(s->ctx.size()), sz = grid->res[2], ncell = sz - 1;
+    s->plan.clear();
+    for (int g = 0; g < G; ++g) { // megamol_b200/slabs.py plan_slabs
+        const int c0 = static_cast<int>(static_cast<long long>(g) * ncell / G), c1 = static_cast<int>(static_cast<long long>(g + 1) * ncell / G);
+        int p0 = std::max(c0 - 1, 0), p1 = std::min(c1 + 1, sz - 1);
+        if (c1 <= c0) p0 = p1 = std::min(c0, sz - 1); // more devices than cell layers: this one idles on a one-plane slab
+        s->plan.push_back({c0, c1 - c0, p0, p1 - p0 + 1});
+    }
+    for (int g = 0; g < G; ++g) {
+        if (int rc = mms_set_grid(s->ctx[g], grid)) return s->failFrom(rc, s->ctx[g]);
+        if (G > 1)
+            if (int rc = mms_set_slab(s->ctx[g], s->plan[g].z0, s->plan[g].nz, s->plan[g].cellZ0, s->plan[g].cellNz)) return s->failFrom(rc, s->ctx[g]);
+    }
+    s->grid = *grid;
+    s->haveGrid = true;
+    s->haveDensity = s->haveMesh = false;
+    return MMS_OK;
+}
+
+int mms_slabs_set_params(mms_slabs* s, const mms_params* p) {
+    if (!s || !p) return MMS_ERR_INVALID;
+    const int G = static_cast<int>(s->ctx.size());
+    if (G > 1 && (p->mode != MMS_MODE_P2D_BUMP || p->aggregator != 0))
+        return s->fail(MMS_ERR_UNSUPPORTED, "a slab group of several devices computes the scalar ParticlesToDensity volume (aggregator 0)");
+    mms_params q = *p;
+    if (G > 1) q.defer_normalize = 1; // the range is global: normalised after the slabs' ranges have been combined
+    for (mms_ctx* c : s->ctx)
+        if (int rc = mms_set_params(c, &q)) return s->failFrom(rc, c);
+    s->params = *p;
+    return MMS_OK;
+}
+
+int mms_slabs_clear_particles(mms_slabs* s) {
+    if (!s) return MMS_ERR_INVALID;
+    for (mms_ctx* c : s->ctx) mms_clear_particles(c);
+    s->nparticles = 0;
+    s->radiusBound = 0.0f;
+    s->perParticleRadii = false;
+    return MMS_OK;
+}
+
+int mms_slabs_push_particles(mms_slabs* s, int32_t nlists, const mms_list* lists) {
+    if (!s || nlists < 0 || (nlists > 0 && !lists)) return MMS_ERR_INVALID;
+    const int G = static_cast<int>(s->ctx.size());
+    for (int i = 0; i < nlists; ++i) {
+        const mms_list& l = lists[i];
+        if (l.vtx_type == MMS_VERT_NONE || l.count == 0) continue;
+        if (l.vtx_type < 0 || l.vtx_type > 4 || l.col_type < 0 || l.col_type > 7 || !l.vtx) return s->fail(MMS_ERR_INVALID, "bad list %d", i);
+        if (G > 1 && isDevicePointer(l.vtx)) return s->fail(MMS_ERR_UNSUPPORTED, "a slab group takes host lists (they are split over the devices' PCIe links)");
+        const unsigned vstride = l.vtx_stride ? l.vtx_stride : kVertSize[l.vtx_type];
+        const int ctype = l.col ? l.col_type : MMS_COL_NONE;
+        const unsigned cstride = l.col_stride ? l.col_stride : kColSize[ctype];
+        if (l.vtx_type == MMS_VERT_FLOAT_XYZR) s->perParticleRadii = true;
+        else if (std::isfinite(l.global_radius)) s->radiusBound = std::max(s->radiusBound, l.global_radius);
+        for (int g = 0; g < G; ++g) {
+            const uint64_t i0 = l.count * static_cast<uint64_t>(g) / G, i1 = l.count * static_cast<uint64_t>(g + 1) / G;
+            if (i1 <= i0) continue;
+            mms_list sub = l;
+            sub.vtx = static_cast<const char*>(l.vtx) + i0 * vstride;
+            sub.vtx_stride = vstride;
+            if (ctype) sub.col = static_cast<const char*>(l.col) + i0 * cstride, sub.col_stride = cstride;
+            sub.count = i1 - i0;
+            if (int rc = mms_push_particles(s->ctx[g], 1, &sub)) return s->failFrom(rc, s->ctx[g]);
+        }
+        s->nparticles += l.count;
+    }
+    return MMS_OK;
+}
+
+int mms_slabs_compute_density(mms_slabs* s) {
+    if (!s || !s->haveGrid) return s ? s->fail(MMS_ERR_INVALID, "mms_slabs_set_grid has not been called") : MMS_ERR_INVALID;
+    const int G = static_cast<int>(s->ctx.size());
+    s->haveDensity = s->haveMesh = false;
+    if (G == 1) {
+        if (int rc = mms_compute_density(s->ctx[0])) return s->failFrom(rc, s->ctx[0]);
+        s->haveDensity = true;
+        return MMS_OK;
+    }
+    // per-particle radii: the largest one sizes everybody's sort cells (one device scan per share; the only host wait of this call)
+    float bound = s->radiusBound;
+    if (s->perParticleRadii)
+        for (mms_ctx* c : s->ctx) {
+            float r = 0.0f;
+            if (int rc = mms_get_max_radius(c, &r)) return s->failFrom(rc, c);
+            bound = std::max(bound, r);
+        }
+    // ---- halo exchange: push into the peers' buffers, ordered by events --------------------------------------------------------------
+    const uint64_t cap = std::max<uint64_t>(s->nparticles, 1);
+    s->haloBuf.assign(G, nullptr), s->haloCtr.assign(G, nullptr);
+    for (int g = 0; g < G; ++g)
+        if (int rc = mms_halo_buffers(s->ctx[g], cap, &s->haloBuf[g], &s->haloCtr[g])) return s->failFrom(rc, s->ctx[g]);
+    std::vector<int32_t> lo(G), hi(G);
+    for (int g = 0; g < G; ++g) lo[g] = s->plan[g].z0, hi[g] = s->plan[g].z0 + s->plan[g].nz - 1;
+    for (int g = 0; g < G; ++g) {
+        mms_ctx* c = s->ctx[g];
+        if (int rc = mms_halo_push(c, G, g, lo.data(), hi.data(), s->haloBuf.data(), s->haloCtr.data(), cap)) return s->failFrom(rc, c);
+        DeviceGuard guard(s->dev[g]);
+        MMS_CUDA(c, cudaEventRecord(s->evPushed[g], c->stream));
+    }
+    for (int g = 0; g < G; ++g) {
+        mms_ctx* c = s->ctx[g];
+        {
+            DeviceGuard guard(s->dev[g]);
+            for (int h = 0; h < G; ++h)
+                if (h != g) MMS_CUDA(c, cudaStreamWaitEvent(c->stream, s->evPushed[h], 0)); // every peer's push into MY buffer is complete
+        }
+        if (int rc = mms_halo_receive(c, bound)) return s->failFrom(rc, c);
+        if (int rc = mms_compute_density(c)) return s->failFrom(rc, c);
+    }
+    // ---- global range -> normalise (ParticlesToDensity.cpp:669-682) -----------------------------------------------------------------
+    if (s->params.mode == MMS_MODE_P2D_BUMP && s->params.normalize && !s->params.defer_normalize) {
+        RangePeers rp{};
+        rp.n = G;
+        for (int g = 0; g < G; ++g) {
+            mms_ctx* c = s->ctx[g];
+            float* r = nullptr;
+            if (int rc = mms_density_range_device(c, &r)) return s->failFrom(rc, c);
+            rp.r[g] = r;
+            DeviceGuard guard(s->dev[g]);
+            MMS_CUDA(c, cudaEventRecord(s->evRange[g], c->stream));
+        }
+        for (int g = 0; g < G; ++g) {
+            mms_ctx* c = s->ctx[g];
+            {
+                DeviceGuard guard(s->dev[g]);
+                for (int h = 0; h < G; ++h)
+                    if (h != g) MMS_CUDA(c, cudaStreamWaitEvent(c->stream, s->evRange[h], 0));
+                range_combine_kernel<<<1, 1, 0, c->stream>>>(rp, s->combined[g].as<float>());
+                ++c->launches;
+            }
+            if (int rc = mms_normalize_device(c, s->combined[g].as<float>())) return s->failFrom(rc, c);
+        }
+    }
+    s->haveDensity = true;
+    return MMS_OK;
+}
+
+int mms_slabs_get_density_range(mms_slabs* s, float minmax[2]) {
+    if (!s || !minmax) return MMS_ERR_INVALID;
+    if (!s->haveDensity) return s->fail(MMS_ERR_INVALID, "no density has been computed");
+    float mn = INFINITY, mx = -INFINITY;
+    for (mms_ctx* c : s->ctx) {
+        float r[2];
+        if (int rc = mms_get_density_range(c, r)) return s->failFrom(rc, c);
+        mn = std::min(mn, r[0]), mx = std::max(mx, r[1]);
+    }
+    minmax[0] = mn, minmax[1] = mx;
+    return MMS_OK;
+}
+
+int mms_slabs_get_density(mms_slabs* s, const float** hv) {
+    if (!s || !hv) return MMS_ERR_INVALID;
+    if (!s->haveDensity) return s->fail(MMS_ERR_INVALID, "no density has been computed");
+    const int G = static_cast<int>(s->ctx.size());
+    if (G == 1) {
+        if (int rc = mms_get_density(s->ctx[0], hv, nullptr)) return s->failFrom(rc, s->ctx[0]);
+        return MMS_OK;
+    }
+    const size_t plane = static_cast<size_t>(s->grid.res[0]) * s->grid.res[1];
+    if (!s->hVol.ensure(plane * s->grid.res[2] * 4)) return s->fail(MMS_ERR_NOMEM, "pinned allocation of the volume failed");
+    for (int g = 0; g < G; ++g) { // every slab sends the planes of its own cell layers (the last one also the final plane)
+        mms_ctx* c = s->ctx[g];
+        const int p0 = s->plan[g].cellZ0, p1 = g == G - 1 ? s->grid.res[2] : s->plan[g].cellZ0 + s->plan[g].cellNz;
+        if (p1 <= p0) continue;
+        DeviceGuard guard(s->dev[g]);
+        MMS_CUDA(c, cudaMemcpyAsync(s->hVol.as<float>() + plane * p0, c->vol.as<float>() + plane * (p0 - s->plan[g].z0), plane * (p1 - p0) * 4,
+            cudaMemcpyDeviceToHost, c->stream));
+    }
+    for (mms_ctx* c : s->ctx)
+        if (int rc = checkDeviceError(c)) return s->failFrom(rc, c);
+    *hv = s->hVol.as<float>();
+    return MMS_OK;
+}
+
+int mms_slabs_extract_isosurface(mms_slabs* s, float iso) {
+    if (!s) return MMS_ERR_INVALID;
+    if (!s->haveDensity) return s->fail(MMS_ERR_INVALID, "no density has been computed");
+    for (mms_ctx* c : s->ctx) // all counts in flight before the first host wait
+        if (int rc = countLaunch(c, iso)) return s->failFrom(rc, c);
+    s->ntris = 0;
+    for (mms_ctx* c : s->ctx) {
+        uint64_t n = 0;
+        if (int rc = countFinish(c, &n)) return s->failFrom(rc, c);
+        s->ntris += n;
+    }
+    for (mms_ctx* c : s->ctx)
+        if (int rc = mms_emit_isosurface(c, nullptr, nullptr, nullptr, 0)) return s->failFrom(rc, c);
+    s->haveMesh = true;
+    return MMS_OK;
+}
+
+int mms_slabs_get_mesh(mms_slabs* s, uint64_t* nverts, const float** pos, const float** nrm) {
+    if (!s || !nverts) return MMS_ERR_INVALID;
+    if (!s->haveMesh) return s->fail(MMS_ERR_INVALID, "no isosurface has been extracted");
+    *nverts = s->ntris * 3;
+    if (pos) *pos = nullptr;
+    if (nrm) *nrm = nullptr;
+    const size_t bytes = static_cast<size_t>(s->ntris) * 36;
+    if (!bytes) return MMS_OK;
+    if ((pos && !s->hPos.ensure(bytes)) || (nrm && !s->hNrm.ensure(bytes))) return s->fail(MMS_ERR_NOMEM, "pinned allocation of the mesh (%zu bytes) failed", bytes);
+    size_t off = 0;
+    for (size_t g = 0; g < s->ctx.size(); ++g) { // slab order = cell-linear order; every slab over its own link
+        mms_ctx* c = s->ctx[g];
+        const size_t b = static_cast<size_t>(c->ntris) * 36;
+        if (b) {
+            DeviceGuard guard(s->dev[g]);
+            if (pos) MMS_CUDA(c, cudaMemcpyAsync(s->hPos.as<char>() + off, c->meshPos.p, b, cudaMemcpyDeviceToHost, c->stream));
+            if (nrm) MMS_CUDA(c, cudaMemcpyAsync(s->hNrm.as<char>() + off, c->meshNrm.p, b, cudaMemcpyDeviceToHost, c->stream));
+        }
+        off += b;
+    }
+    for (size_t g = 0; g < s->ctx.size(); ++g) {
+        DeviceGuard guard(s->dev[g]);
+        MMS_CUDA(s->ctx[g], cudaStreamSynchronize(s->ctx[g]->stream));
+    }
+    if (pos) *pos = s->hPos.as<float>();
+    if (nrm) *nrm = s->hNrm.as<float>();
+    return MMS_OK;
+}
+
+} // extern "C"
+
