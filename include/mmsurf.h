@@ -266,6 +266,8 @@ int mms_slabs_push_particles(mms_slabs* s, int32_t nlists, const mms_list* lists
 int mms_slabs_compute_density(mms_slabs* s);
 int mms_slabs_get_density_range(mms_slabs* s, float minmax[2]);
 int mms_slabs_get_density(mms_slabs* s, const float** host_volume); /* the WHOLE volume, library-owned pinned memory */
+/* mms_adopt_density for groups on the same devices: device-resident hand-off of every slab (IsoSurfaceB200 behind a multi-GPU producer) */
+int mms_slabs_adopt_density(mms_slabs* s, mms_slabs* producer);
 int mms_slabs_extract_isosurface(mms_slabs* s, float isovalue);
 /* The whole mesh in cell-linear order (= the single-GPU order), library-owned pinned memory; every slab is copied over its own link. */
 int mms_slabs_get_mesh(mms_slabs* s, uint64_t* nverts, const float** positions, const float** normals);

@@ -1827,6 +1827,18 @@ int mms_slabs_get_density(mms_slabs* s, const float** hv) {
     return MMS_OK;
 }
 
+int mms_slabs_adopt_density(mms_slabs* s, mms_slabs* p) {
+    if (!s || !p || s == p) return MMS_ERR_INVALID;
+    if (!p->haveDensity) return s->fail(MMS_ERR_INVALID, "the producer group has no density");
+    if (s->dev != p->dev) return s->fail(MMS_ERR_INVALID, "mms_slabs_adopt_density: the two groups must use the same devices in the same order");
+    for (size_t g = 0; g < s->ctx.size(); ++g)
+        if (int rc = mms_adopt_density(s->ctx[g], p->ctx[g])) return s->failFrom(rc, s->ctx[g]);
+    s->grid = p->grid, s->plan = p->plan, s->params = p->params;
+    s->haveGrid = s->haveDensity = true;
+    s->haveMesh = false;
+    return MMS_OK;
+}
+
 int mms_slabs_extract_isosurface(mms_slabs* s, float iso) {
     if (!s) return MMS_ERR_INVALID;
     if (!s->haveDensity) return s->fail(MMS_ERR_INVALID, "no density has been computed");

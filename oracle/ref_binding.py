@@ -47,6 +47,7 @@ class Harness:
         L.mmh_set_p2d_params.argtypes = [C.c_void_p] + [C.c_int] * 8 + [C.c_float, C.c_int]
         L.mmh_set_param_int.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int]
         L.mmh_set_param_float.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_float]
+        L.mmh_set_param_string.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_char_p]
         L.mmh_pull_volume.argtypes = [C.c_void_p, C.c_uint, C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_double),
                                       C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_double)]
         L.mmh_pull_mesh.argtypes = [C.c_void_p, C.c_uint, C.c_float, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
@@ -149,6 +150,10 @@ class Harness:
             raise RuntimeError(f"mmh_set_p2d_params rc={rc}")
 
     def set_param(self, module: int, name: str, value):
+        if isinstance(value, str):
+            if self.lib.mmh_set_param_string(self.h, module, name.encode(), value.encode()):
+                raise KeyError(name)
+            return
         if isinstance(value, float):
             rc = self.lib.mmh_set_param_float(self.h, module, name.encode(), value)
         else:

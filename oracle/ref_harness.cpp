@@ -35,6 +35,7 @@
 #include "mmcore/param/EnumParam.h"
 #include "mmcore/param/FloatParam.h"
 #include "mmcore/param/IntParam.h"
+#include "mmcore/param/StringParam.h"
 #include "mmcore/param/ParamSlot.h"
 #include "mmcore/utility/log/Log.h"
 #include "protein_calls/MolecularDataCall.h"
@@ -377,6 +378,16 @@ int mmh_set_param_int(void* hv, int module, const char* name, int v) {
     if (setParam<core::param::EnumParam>(m, name, v)) return 0;
     if (setParam<core::param::BoolParam>(m, name, v != 0)) return 0;
     return -1;
+}
+int mmh_set_param_string(void* hv, int module, const char* name, const char* v) {
+    auto* h = static_cast<Harness*>(hv);
+    core::Module& m = module == 0 ? static_cast<core::Module&>(*h->p2d) : static_cast<core::Module&>(*h->iso);
+    auto* s = dynamic_cast<core::param::ParamSlot*>(m.FindSlot(name));
+    if (!s) return -1;
+    auto* p = s->Param<core::param::StringParam>();
+    if (!p) return -1;
+    p->SetValue(v);
+    return 0;
 }
 int mmh_set_param_float(void* hv, int module, const char* name, float v) {
     auto* h = static_cast<Harness*>(hv);

@@ -73,6 +73,10 @@ void IsoSurfaceB200::release() {
         mms_destroy(this->ctx);
         this->ctx = nullptr;
     }
+    if (this->group != nullptr) {
+        mms_slabs_destroy(this->group);
+        this->group = nullptr;
+    }
 }
 
 bool IsoSurfaceB200::outExtentCallback(core::Call& caller) {
@@ -106,7 +110,35 @@ bool IsoSurfaceB200::buildMesh(VolumetricDataCall* cvd, float iso) {
     if (callee != nullptr) {
         auto parent = callee->Parent();
         auto* p2d = dynamic_cast<const ParticlesToDensityB200*>(parent.get());
-        if (p2d != nullptr && p2d->Context() != nullptr && p2d->VolumeHash() == cvd->DataHash()) {
+        if (p2d != nullptr && p2d->Group() != nullptr && p2d->VolumeHash() == cvd->DataHash() && algorithm == MMS_ISO_MARCHING_CUBES) {
+            // a multi-device producer: this module's own slab group on the same devices adopts every slab's volume, the slabs' meshes are
+            // concatenated (= the single-GPU order) into this module's pinned arrays
+            if (this->group == nullptr || this->groupDevices != p2d->GroupDevices()) {
+                if (this->group != nullptr) mms_slabs_destroy(this->group);
+                this->group = nullptr;
+                this->groupDevices = p2d->GroupDevices();
+                if (mms_slabs_create(&this->group, this->groupDevices.data(), static_cast<int32_t>(this->groupDevices.size())) != MMS_OK) {
+                    Log::DefaultLog.WriteError("IsoSurfaceB200: %s", mms_slabs_last_error(nullptr));
+                    return false;
+                }
+            }
+            uint64_t nv = 0;
+            const float *gp = nullptr, *gn = nullptr;
+            if (mms_slabs_adopt_density(this->group, p2d->Group()) != MMS_OK || mms_slabs_extract_isosurface(this->group, iso) != MMS_OK ||
+                mms_slabs_get_mesh(this->group, &nv, &gp, &gn) != MMS_OK) {
+                Log::DefaultLog.WriteError("IsoSurfaceB200: %s", mms_slabs_last_error(this->group));
+                return false;
+            }
+            this->mesh.SetMaterial(nullptr);
+            this->mesh.SetVertexData(static_cast<unsigned int>(nv), const_cast<float*>(gp), const_cast<float*>(gn), static_cast<float*>(nullptr),
+                static_cast<float*>(nullptr), false);
+            this->mesh.SetTriangleData(0, static_cast<unsigned int*>(nullptr), false);
+            const std::chrono::duration<float, std::milli> msg = std::chrono::high_resolution_clock::now() - t0;
+            Log::DefaultLog.WriteInfo("IsoSurfaceB200: %llu triangles at iso %f took %f ms (device-resident volume on %zu devices).",
+                static_cast<unsigned long long>(nv / 3), iso, msg.count(), this->groupDevices.size());
+            return true;
+        }
+        if (p2d != nullptr && p2d->Context() != nullptr && p2d->Group() == nullptr && p2d->VolumeHash() == cvd->DataHash()) {
             producer = p2d->Context();
             device = p2d->Device();
         }

@@ -5,6 +5,7 @@
  * reference's: one Mesh, unindexed triangle soup, float positions + float normals.
  */
 #pragma once
+#include <vector>
 
 #include <cstddef>
 
@@ -47,6 +48,8 @@ private:
 
     mms_ctx* ctx = nullptr; // own context, used when the volume comes from a foreign (host) source
     int ctxDevice = -1;
+    mms_slabs* group = nullptr; // own slab group, used behind a multi-device ParticlesToDensityB200
+    std::vector<int32_t> groupDevices;
     std::size_t dataHash = 0;
     unsigned int frameIdx = 0;
     bool has_mesh = false;

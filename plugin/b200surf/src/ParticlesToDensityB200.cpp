@@ -19,6 +19,7 @@
 #include "mmcore/param/EnumParam.h"
 #include "mmcore/param/FloatParam.h"
 #include "mmcore/param/IntParam.h"
+#include "mmcore/param/StringParam.h"
 #include "mmcore/utility/log/Log.h"
 
 using namespace megamol;
@@ -48,6 +49,8 @@ ParticlesToDensityB200::ParticlesToDensityB200()
         , sigmaSlot("sigma", "Sigma for Gauss in multiple of rad")
         , surfaceSlot("forSurfaceReconstruction", "Set true if this volume is used for surface reconstruction")
         , deviceSlot("device", "CUDA device ordinal the volume is computed on")
+        , devicesSlot("devices", "Several CUDA devices, comma separated (e.g. 0,1,2,3): the volume is computed in z-slabs with halo, one per "
+                                 "device (position aggregator of the bump mode); empty = the single device of 'device'")
         , modeSlot("mode", "Density semantics: ParticlesToDensity bump kernel or QuickSurf Gaussian")
         , qsQualitySlot("quicksurf::quality", "Quality: 0 low .. 3 ultra (Gaussian cut-off 2.0/2.5/3.0/4.0 sigma)")
         , qsRadScaleSlot("quicksurf::radiusScale", "Radius scale")
@@ -111,6 +114,8 @@ ParticlesToDensityB200::ParticlesToDensityB200()
 
     this->deviceSlot << new core::param::IntParam(0, 0);
     this->MakeSlotAvailable(&this->deviceSlot);
+    this->devicesSlot << new core::param::StringParam("");
+    this->MakeSlotAvailable(&this->devicesSlot);
 
     auto* mp = new core::param::EnumParam(0);
     mp->SetTypePair(0, "ParticlesToDensity_Bump");
@@ -146,6 +151,11 @@ void ParticlesToDensityB200::release() {
         mms_destroy(this->ctx);
         this->ctx = nullptr;
     }
+    if (this->group != nullptr) {
+        mms_slabs_destroy(this->group);
+        this->group = nullptr;
+        this->groupActive = false;
+    }
     this->metadata.MinValues = nullptr;
     this->metadata.MaxValues = nullptr;
     for (auto& s : this->metadata.SliceDists)
@@ -159,13 +169,13 @@ bool ParticlesToDensityB200::dummyCallback(core::Call&) {
 bool ParticlesToDensityB200::anythingDirty() const {
     return this->aggregatorSlot.IsDirty() || this->xResSlot.IsDirty() || this->yResSlot.IsDirty() || this->zResSlot.IsDirty() ||
            this->cyclXSlot.IsDirty() || this->cyclYSlot.IsDirty() || this->cyclZSlot.IsDirty() || this->normalizeSlot.IsDirty() ||
-           this->sigmaSlot.IsDirty() || this->deviceSlot.IsDirty() || this->modeSlot.IsDirty() || this->qsQualitySlot.IsDirty() ||
+           this->sigmaSlot.IsDirty() || this->deviceSlot.IsDirty() || this->devicesSlot.IsDirty() || this->modeSlot.IsDirty() || this->qsQualitySlot.IsDirty() ||
            this->qsRadScaleSlot.IsDirty() || this->qsColourSlot.IsDirty() || this->qsGridSpacingSlot.IsDirty() ||
            this->qsRefCellsSlot.IsDirty();
 }
 
 void ParticlesToDensityB200::resetDirty() {
-    for (auto* s : {&aggregatorSlot, &xResSlot, &yResSlot, &zResSlot, &cyclXSlot, &cyclYSlot, &cyclZSlot, &normalizeSlot, &sigmaSlot, &deviceSlot, &modeSlot,
+    for (auto* s : {&aggregatorSlot, &xResSlot, &yResSlot, &zResSlot, &cyclXSlot, &cyclYSlot, &cyclZSlot, &normalizeSlot, &sigmaSlot, &deviceSlot, &devicesSlot, &modeSlot,
              &qsQualitySlot, &qsRadScaleSlot, &qsColourSlot, &qsGridSpacingSlot, &qsRefCellsSlot})
         s->ResetDirty();
 }
@@ -383,6 +393,61 @@ bool ParticlesToDensityB200::computeVolume(core::AbstractGetData3DCall* in) {
         Log::DefaultLog.WriteError("ParticlesToDensityB200: %s: %s", what, mms_last_error(this->ctx));
         return false;
     };
+    // ---- several devices: z-slabs behind one handle (mms_slabs_*), same host contract ---------------------------------------------------
+    std::vector<int32_t> devs;
+    {
+        const std::string text = this->devicesSlot.Param<core::param::StringParam>()->Value();
+        size_t pos = 0;
+        while (pos < text.size()) {
+            size_t end = text.find(',', pos);
+            if (end == std::string::npos) end = text.size();
+            const std::string tok = text.substr(pos, end - pos);
+            if (tok.find_first_of("0123456789") != std::string::npos) devs.push_back(std::atoi(tok.c_str()));
+            pos = end + 1;
+        }
+    }
+    this->groupActive = false;
+    if (devs.size() > 1) {
+        if (p.mode != MMS_MODE_P2D_BUMP || p.aggregator != 0) {
+            Log::DefaultLog.WriteError("ParticlesToDensityB200: 'devices' computes the position aggregator of the bump mode; use 'device' for the other modes");
+            return false;
+        }
+        if (this->group == nullptr || devs != this->groupDevices) {
+            if (this->group != nullptr) mms_slabs_destroy(this->group);
+            this->group = nullptr;
+            if (mms_slabs_create(&this->group, devs.data(), static_cast<int32_t>(devs.size())) != MMS_OK) {
+                Log::DefaultLog.WriteError("ParticlesToDensityB200: %s", mms_slabs_last_error(nullptr));
+                return false;
+            }
+            this->groupDevices = devs;
+        }
+        auto gfail = [&](const char* what) {
+            Log::DefaultLog.WriteError("ParticlesToDensityB200: %s: %s", what, mms_slabs_last_error(this->group));
+            return false;
+        };
+        this->gridUsed = grid;
+        this->ownGrid = false;
+        float mm2[2] = {0, 0};
+        if (mms_slabs_clear_particles(this->group) != MMS_OK || mms_slabs_set_grid(this->group, &grid) != MMS_OK ||
+            mms_slabs_set_params(this->group, &p) != MMS_OK ||
+            mms_slabs_push_particles(this->group, static_cast<int32_t>(lists.size()), lists.data()) != MMS_OK ||
+            mms_slabs_compute_density(this->group) != MMS_OK || mms_slabs_get_density_range(this->group, mm2) != MMS_OK ||
+            mms_slabs_get_density(this->group, &this->hostVolume) != MMS_OK)
+            return gfail("slab group");
+        this->minDens = mm2[0], this->maxDens = mm2[1];
+        this->isVector = false;
+        this->hasColour = false;
+        this->groupActive = true;
+        Log::DefaultLog.WriteInfo("ParticlesToDensityB200: Captured density %f -> %f", this->minDens, this->maxDens);
+        if (p.normalize) {
+            this->minDens = 0.0f;
+            this->maxDens = 1.0f;
+        }
+        const std::chrono::duration<float, std::milli> msg = std::chrono::high_resolution_clock::now() - t0;
+        Log::DefaultLog.WriteInfo("ParticlesToDensityB200: creation of %u x %u x %u volume from %llu particles on %zu devices took %f ms.", grid.res[0],
+            grid.res[1], grid.res[2], static_cast<unsigned long long>(total), devs.size(), msg.count());
+        return true;
+    }
     if (mms_clear_particles(this->ctx) != MMS_OK)
         return fail("clear_particles");
     if (mms_push_particles_dir(this->ctx, static_cast<int32_t>(lists.size()), lists.data(), dirs.data(), dirStrides.data()) != MMS_OK)

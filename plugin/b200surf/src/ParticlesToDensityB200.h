@@ -53,6 +53,13 @@ public:
     int Device() const {
         return this->ctxDevice;
     }
+    /** Several devices ("devices" parameter): the slab group holding the volume of the last GetData, else NULL. */
+    mms_slabs* Group() const {
+        return this->groupActive ? this->group : nullptr;
+    }
+    const std::vector<int32_t>& GroupDevices() const {
+        return this->groupDevices;
+    }
     /** true if the context also holds a density-weighted RGB volume (QuickSurf mode with colour). */
     bool HasColour() const {
         return this->hasColour;
@@ -85,6 +92,10 @@ private:
 
     mms_ctx* ctx = nullptr;
     int ctxDevice = -1;
+    core::param::ParamSlot devicesSlot; // extra: several CUDA devices, e.g. "0,1,2,3": the volume is computed in z-slabs (scalar bump mode)
+    mms_slabs* group = nullptr;
+    std::vector<int32_t> groupDevices;
+    bool groupActive = false;
     const float* hostVolume = nullptr;
     std::size_t in_datahash = std::numeric_limits<std::size_t>::max();
     std::size_t datahash = 0;

@@ -3,7 +3,7 @@
 # then the default bench line at N (weak C2 + the C4 figures inside), fused and nccl exchange.
 N=$1
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_multi.py tests/test_gpu_slab_group.py -m gpu -q 2>&1 | tail -30
+timeout 900 python -m pytest tests/test_gpu_multi.py tests/test_gpu_slab_group.py tests/test_gpu_plugin.py -m gpu -q 2>&1 | tail -30
 cat gpurun_out/multi_gpu_check.log
 for EX in fused nccl; do
   EXTRA=""; if [ $EX = nccl ]; then EXTRA="--no-c4 --no-e2e"; fi

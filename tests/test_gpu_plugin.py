@@ -129,6 +129,29 @@ def test_two_isosurface_modules_share_one_density_module(plug):
     assert np.array_equal(pos, a["pos"]) and np.array_equal(nrm, a["nrm"])
 
 
+def test_modules_on_two_devices(plug):
+    """The modules' `devices` parameter: ParticlesToDensityB200 computes the volume in z-slabs on two GPUs behind one handle (mms_slabs_*),
+    IsoSurfaceB200 adopts the slabs' device volumes into its own group; volume and mesh equal the single-device modules' bit for bit."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    n, box, res = 200_000, 20.0, (64, 56, 48)
+    xyz = synth.uniform_box(n, box, seed=29)
+    lists = [dict(vtx=xyz, vtx_type=rb.VERT_FLOAT_XYZ, count=n, global_radius=0.6)]
+    outs = []
+    for devices in ("", "0,1"):
+        plug.set_param(0, "devices", devices)
+        feed(plug, lists, (0, 0, 0, box, box, box), res, cyclic=(True,) * 3, normalize=True)
+        vol, meta = plug.pull_volume()
+        m = plug.pull_mesh(0.4)
+        outs.append((vol.copy(), meta, m))
+    plug.set_param(0, "devices", "")
+    (v1, m1, s1), (v2, m2, s2) = outs
+    assert np.array_equal(v1.view(np.uint32), v2.view(np.uint32))
+    assert m1["minmax"] == m2["minmax"] and m1["res"] == m2["res"]
+    assert s1["nverts"] == s2["nverts"] > 1000 and np.array_equal(s1["pos"], s2["pos"]) and np.array_equal(s1["nrm"], s2["nrm"])
+
+
 def test_for_surface_reconstruction_bbox(ref, plug):
     xyz = synth.uniform_box(2000, 6.0, seed=17)
     lists = [dict(vtx=xyz, vtx_type=rb.VERT_FLOAT_XYZ, count=2000, global_radius=0.7)]
