@@ -148,7 +148,7 @@ def test_modules_on_two_devices(plug):
     plug.set_param(0, "devices", "")
     (v1, m1, s1), (v2, m2, s2) = outs
     assert np.array_equal(v1.view(np.uint32), v2.view(np.uint32))
-    assert m1["minmax"] == m2["minmax"] and m1["res"] == m2["res"]
+    assert (m1["min"], m1["max"]) == (m2["min"], m2["max"]) and m1["resolution"] == m2["resolution"] and m1["slicedist"] == m2["slicedist"]
     assert s1["nverts"] == s2["nverts"] > 1000 and np.array_equal(s1["pos"], s2["pos"]) and np.array_equal(s1["nrm"], s2["nrm"])
 
 
