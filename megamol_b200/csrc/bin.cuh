@@ -37,7 +37,7 @@ __device__ __forceinline__ bool axisReaches(int X, int f, int lo, int hi, int s,
  *  dropped before the sort.  With voxels much larger than the kernel (the modules' default 16^3 grid) that is almost every particle.
  *  Same bounds and slop as the density kernels' tight support box, so nothing that contributes is ever dropped. */
 __device__ __forceinline__ bool supportHasNode(float p, float rad, const Geo& g, int a) {
-    const float eps = g.sigma * rad, isd = __frcp_rn(g.sd[a]);
+    const float eps = g.sigma * rad, isd = g.isd[a];
     const float aa = p - g.mn[a];
     const float vlo = (aa - eps) * isd, vhi = (aa + eps) * isd;
     const float slop = fmaxf(fmaxf(fabsf(vlo), fabsf(vhi)), 1.0f) * 4e-6f;

@@ -11,6 +11,7 @@ constexpr int kMaxLists = 64;
 struct Geo {
     float mn[3];  // bbox Left/Bottom/Back
     float sd[3];  // sliceDist = range / float(res-1), computed on the HOST in fp32 exactly like the reference
+    float isd[3]; // 1 / sliceDist (only for the slop-protected support bounds, never for the binning itself)
     int s[3];     // resolution
     int cyc[3];   // cyclX/Y/Z
     int z0, nz;   // slab: voxel planes [z0, z0+nz)

@@ -244,6 +244,7 @@ Geo makeGeo(const mms_ctx* c) {
         volatile float denom = static_cast<float>(c->grid.res[a] - 1);
         volatile float sd = range / denom;
         g.sd[a] = sd;
+        g.isd[a] = 1.0f / sd;
         g.cyc[a] = c->grid.cyclic[a] != 0;
     }
     g.z0 = c->z0, g.nz = c->nz;

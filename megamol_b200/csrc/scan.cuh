@@ -7,7 +7,7 @@
 namespace mms {
 
 constexpr int kScanThreads = 256;
-constexpr int kScanItems = 16; // per thread
+constexpr int kScanItems = 4;  // per thread: one 16-byte vector, so that a warp reads and writes 512 contiguous bytes
 constexpr int kScanTile = kScanThreads * kScanItems;
 
 __device__ __forceinline__ unsigned warpInclusiveScan(unsigned v) {
@@ -39,17 +39,22 @@ __device__ __forceinline__ unsigned blockExclusiveScan(unsigned v, unsigned* tot
     return res;
 }
 
+/** Four consecutive counters of a thread: one aligned 16-byte load where the tile is complete (cudaMalloc'ed arrays), else scalar. */
+__device__ __forceinline__ uint4 scanLoad4(const unsigned* __restrict__ in, size_t i, unsigned n) {
+    if (i + 3 < n) return *reinterpret_cast<const uint4*>(in + i);
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (i < n) v.x = in[i];
+    if (i + 1 < n) v.y = in[i + 1];
+    if (i + 2 < n) v.z = in[i + 2];
+    return v;
+}
+
 __global__ void __launch_bounds__(kScanThreads) scan_reduce_kernel(const unsigned* __restrict__ in, unsigned* __restrict__ tileSums, unsigned n) {
     __shared__ unsigned ws[33];
-    const size_t base = static_cast<size_t>(blockIdx.x) * kScanTile;
-    unsigned s = 0;
-#pragma unroll
-    for (int k = 0; k < kScanItems; ++k) {
-        const size_t i = base + static_cast<size_t>(k) * kScanThreads + threadIdx.x;
-        if (i < n) s += in[i];
-    }
+    const size_t i = (static_cast<size_t>(blockIdx.x) * kScanThreads + threadIdx.x) * kScanItems;
+    const uint4 v = scanLoad4(in, i, n);
     unsigned total;
-    blockExclusiveScan(s, &total, ws);
+    blockExclusiveScan(v.x + v.y + v.z + v.w, &total, ws);
     if (threadIdx.x == 0) tileSums[blockIdx.x] = total;
 }
 
@@ -74,26 +79,21 @@ __global__ void __launch_bounds__(1024) scan_tilesums_kernel(unsigned* __restric
 __global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const unsigned* __restrict__ in, const unsigned* __restrict__ tileSums,
     unsigned* __restrict__ out, unsigned* __restrict__ copy, unsigned n) {
     __shared__ unsigned ws[33];
-    // thread t owns kScanItems CONSECUTIVE items so that its local scan is a plain loop
-    const size_t base = static_cast<size_t>(blockIdx.x) * kScanTile + static_cast<size_t>(threadIdx.x) * kScanItems;
-    unsigned v[kScanItems];
-    unsigned s = 0;
-#pragma unroll
-    for (int k = 0; k < kScanItems; ++k) {
-        const size_t i = base + k;
-        v[k] = i < n ? in[i] : 0u;
-        s += v[k];
-    }
+    const size_t i = (static_cast<size_t>(blockIdx.x) * kScanThreads + threadIdx.x) * kScanItems;
+    const uint4 v = scanLoad4(in, i, n);
     unsigned total;
-    unsigned ex = blockExclusiveScan(s, &total, ws) + tileSums[blockIdx.x];
-#pragma unroll
-    for (int k = 0; k < kScanItems; ++k) {
-        const size_t i = base + k;
-        if (i < n) {
-            out[i] = ex;
-            if (copy) copy[i] = ex;
-        }
-        ex += v[k];
+    const unsigned ex = blockExclusiveScan(v.x + v.y + v.z + v.w, &total, ws) + tileSums[blockIdx.x];
+    const uint4 o = make_uint4(ex, ex + v.x, ex + v.x + v.y, ex + v.x + v.y + v.z);
+    if (i + 3 < n) { // (out[n], the grand total, belongs to the tile-sums kernel: a full vector never reaches it)
+        *reinterpret_cast<uint4*>(out + i) = o;
+        if (copy) *reinterpret_cast<uint4*>(copy + i) = o;
+    } else {
+        const unsigned e[3] = {o.x, o.y, o.z};
+        for (int k = 0; k < 3; ++k)
+            if (i + k < n) {
+                out[i + k] = e[k];
+                if (copy) copy[i + k] = e[k];
+            }
     }
 }
 

@@ -71,17 +71,24 @@ int mmq_density(long natoms, const float* xyzr_f, const float* rgba, const int n
     uint2* cellStartEnd_d = nullptr;
     float* devdensity = nullptr;
     float3* devvoltexmap = nullptr;
-    MMQ_CUDA(cudaMalloc((void**)&devdensity, ncells * sizeof(float)));
+    // The density kernels test only the FIRST of their GUNROLL / GTEXUNROLL unrolled planes against volsz.z and store the others
+    // unconditionally (CUDAQuickSurf.cu:645-657): a z extent that is no multiple of 8 is written up to 7 planes past its end.  In the
+    // reference those stores land in the rest of the caller's allocation; here the buffers carry the slack so that they land in ours.
+    const long padcells = (long)volsz.x * volsz.y * (((long)volsz.z + 7) / 8 * 8);
+    MMQ_CUDA(cudaMalloc((void**)&devdensity, padcells * sizeof(float)));
     MMQ_CUDA(cudaMalloc((void**)&xyzr_d, natoms * sizeof(float4)));
     MMQ_CUDA(cudaMalloc((void**)&sorted_xyzr_d, natoms * sizeof(float4)));
     MMQ_CUDA(cudaMalloc((void**)&atomIndex_d, natoms * sizeof(unsigned int)));
     MMQ_CUDA(cudaMalloc((void**)&sorted_atomIndex_d, natoms * sizeof(unsigned int)));
     MMQ_CUDA(cudaMalloc((void**)&atomHash_d, natoms * sizeof(unsigned int)));
     MMQ_CUDA(cudaMalloc((void**)&cellStartEnd_d, acncells * sizeof(uint2)));
+    // vmd_cuda_build_density_atom_grid sorts the colour array unconditionally (sortAtomsColorsGenCellLists, CUDASpatialSearch.cu:237-239):
+    // the buffers exist with or without colours (MegaMol's QuickSurf module always passes colours, QuickSurf.cpp:511-577)
+    MMQ_CUDA(cudaMalloc((void**)&color_d, natoms * sizeof(float4)));
+    MMQ_CUDA(cudaMalloc((void**)&sorted_color_d, natoms * sizeof(float4)));
+    MMQ_CUDA(cudaMemset(color_d, 0, natoms * sizeof(float4)));
     if (colorperatom) {
-        MMQ_CUDA(cudaMalloc((void**)&devvoltexmap, ncells * sizeof(float3)));
-        MMQ_CUDA(cudaMalloc((void**)&color_d, natoms * sizeof(float4)));
-        MMQ_CUDA(cudaMalloc((void**)&sorted_color_d, natoms * sizeof(float4)));
+        MMQ_CUDA(cudaMalloc((void**)&devvoltexmap, padcells * sizeof(float3)));
         MMQ_CUDA(cudaMemcpy(color_d, rgba, natoms * sizeof(float4), cudaMemcpyHostToDevice));
     }
     MMQ_CUDA(cudaMemcpy(xyzr_d, xyzr, natoms * sizeof(float4), cudaMemcpyHostToDevice));
