@@ -279,6 +279,32 @@ int mms_ipc_export(int32_t device, const void* devptr, unsigned char handle[64])
 int mms_ipc_open(int32_t device, const unsigned char handle[64], void** ptr);
 int mms_ipc_close(int32_t device, void* ptr);
 
+/* ---- Device-resident hand-off to consumers ---------------------------------------------------------------------
+ * The reference hands results over in host memory; its one VRAM variant is VolumetricDataCall::SetData(uint32_t texture) with
+ * MemLoc = VRAM (geometry_calls/VolumetricDataCall.h:290-292, VolumetricDataCallTypes.h:22,133), and the tri-soup renderers re-buffer
+ * the host arrays into GL buffers every frame (trisoup_gl/src/ModernTrisoupRenderer.cpp:308-440).  With mms_share_enable the volume and
+ * the mesh live in exportable device memory (CUDA virtual-memory allocations with a POSIX file-descriptor handle): a renderer imports
+ * the descriptor once per (re)allocation -- glImportMemoryFdEXT + glNamedBufferStorageMemEXT, VkImportMemoryFdInfoKHR, or
+ * cuMemImportFromShareableHandle / mms_share_open for a CUDA consumer -- and draws from it; nothing crosses PCIe.
+ * Each mms_share_* call returns NEW descriptors (the caller closes them, close(2); an import consumes nothing of the library's).
+ * The calls synchronise the context's stream: the contents are final on return.  A buffer keeps its allocation (and the importer's
+ * mapping stays valid) until a later frame outgrows it: alloc_bytes changes then, which is the importer's cue to re-import. */
+typedef struct mms_share {
+    int32_t fd;           /* POSIX file descriptor of the allocation, -1 = nothing to share (empty mesh, no colours) */
+    uint32_t reserved;
+    uint64_t alloc_bytes; /* size of the whole allocation = the size to import / map */
+    uint64_t offset;      /* first payload byte inside the allocation */
+    uint64_t bytes;       /* payload bytes */
+} mms_share;
+int mms_share_enable(mms_ctx* ctx, int32_t on);
+/* Volume (res.x * res.y * slab planes floats) and, in colour / vector mode, the 3-float-per-voxel volume. */
+int mms_share_density(mms_ctx* ctx, mms_share* volume, mms_share* rgb);
+/* Triangle soup of the last mms_extract_isosurface: 3 floats per vertex each, same layout as mms_get_mesh. */
+int mms_share_mesh(mms_ctx* ctx, uint64_t* nverts, mms_share* positions, mms_share* normals, mms_share* colours);
+/* The CUDA consumer's side: maps a shared allocation on `device` (may be another process, another device with peer access). */
+int mms_share_open(int32_t device, const mms_share* share, void** devptr);
+int mms_share_close(int32_t device, void* devptr, const mms_share* share);
+
 /* Pinned host memory for callers that want zero-staging H2D (e.g. an MMPLD reader). */
 void* mms_alloc_pinned(size_t bytes);
 void mms_free_pinned(void* p);

@@ -18,7 +18,7 @@ ISO_MARCHING_CUBES, ISO_MARCHING_TETS = 0, 1
 EXPORTS = ["mms_create", "mms_destroy", "mms_last_error", "mms_set_grid", "mms_set_slab", "mms_set_params",
            "mms_clear_particles", "mms_push_particles", "mms_push_particles_dir", "mms_get_vector_field", "mms_get_vector_field_device", "mms_get_max_radius", "mms_compute_density", "mms_get_density_range", "mms_normalize", "mms_density_range_device", "mms_normalize_device", "mms_set_stream",
            "mms_get_density", "mms_prefetch_density", "mms_get_density_device", "mms_set_density", "mms_adopt_density", "mms_extract_isosurface", "mms_set_isosurface_mode", "mms_count_isosurface", "mms_emit_isosurface", "mms_device_alloc",
-           "mms_device_free", "mms_route_particles", "mms_halo_buffers", "mms_halo_push", "mms_halo_receive", "mms_slabs_create", "mms_slabs_destroy", "mms_slabs_last_error", "mms_slabs_count", "mms_slabs_context", "mms_slabs_set_grid", "mms_slabs_set_params", "mms_slabs_clear_particles", "mms_slabs_push_particles", "mms_slabs_compute_density", "mms_slabs_get_density_range", "mms_slabs_get_density", "mms_slabs_adopt_density", "mms_slabs_extract_isosurface", "mms_slabs_get_mesh", "mms_ipc_export", "mms_ipc_open", "mms_ipc_close", "mms_get_mesh",
+           "mms_device_free", "mms_route_particles", "mms_halo_buffers", "mms_halo_push", "mms_halo_receive", "mms_slabs_create", "mms_slabs_destroy", "mms_slabs_last_error", "mms_slabs_count", "mms_slabs_context", "mms_slabs_set_grid", "mms_slabs_set_params", "mms_slabs_clear_particles", "mms_slabs_push_particles", "mms_slabs_compute_density", "mms_slabs_get_density_range", "mms_slabs_get_density", "mms_slabs_adopt_density", "mms_slabs_extract_isosurface", "mms_slabs_get_mesh", "mms_ipc_export", "mms_ipc_open", "mms_ipc_close", "mms_share_enable", "mms_share_density", "mms_share_mesh", "mms_share_open", "mms_share_close", "mms_get_mesh",
            "mms_get_mesh_device", "mms_get_home_voxels", "mms_get_cell_tricounts", "mms_get_timings", "mms_synchronize",
            "mms_timer_start", "mms_timer_stop", "mms_launch_count", "mms_alloc_pinned", "mms_free_pinned", "mms_version", "mms_mmpld_open", "mms_mmpld_close",
            "mms_mmpld_last_error", "mms_mmpld_info", "mms_mmpld_prefetch", "mms_mmpld_read_frame"]
@@ -48,6 +48,10 @@ class MmsParams(C.Structure):
     _fields_ = [("mode", C.c_int32), ("aggregator", C.c_int32), ("normalize", C.c_int32), ("defer_normalize", C.c_int32),
                 ("sigma", C.c_float), ("radscale", C.c_float), ("gausslim", C.c_float), ("colour", C.c_int32),
                 ("want_home_voxels", C.c_int32), ("want_cell_tricounts", C.c_int32)]
+
+
+class MmsShare(C.Structure):
+    _fields_ = [("fd", C.c_int32), ("reserved", C.c_uint32), ("alloc_bytes", C.c_uint64), ("offset", C.c_uint64), ("bytes", C.c_uint64)]
 
 
 class MmsTimings(C.Structure):
@@ -127,6 +131,12 @@ def load_library():
     L.mms_ipc_export.argtypes = [C.c_int32, vp, C.POINTER(C.c_ubyte)]
     L.mms_ipc_open.argtypes = [C.c_int32, C.POINTER(C.c_ubyte), C.POINTER(vp)]
     L.mms_ipc_close.argtypes = [C.c_int32, vp]
+    sp = C.POINTER(MmsShare)
+    L.mms_share_enable.argtypes = [vp, C.c_int32]
+    L.mms_share_density.argtypes = [vp, sp, sp]
+    L.mms_share_mesh.argtypes = [vp, C.POINTER(C.c_uint64), sp, sp, sp]
+    L.mms_share_open.argtypes = [C.c_int32, sp, C.POINTER(vp)]
+    L.mms_share_close.argtypes = [C.c_int32, vp, sp]
     L.mms_get_mesh.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     L.mms_get_mesh_device.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     L.mms_get_home_voxels.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_uint64)]
@@ -343,6 +353,23 @@ class Surf:
 
     def extract_isosurface(self, iso):
         self._chk(self.L.mms_extract_isosurface(self.h, float(iso)))
+
+    # ---- device-resident hand-off (mms_share_*): exportable volume / mesh buffers, file-descriptor handles ----
+    def share_enable(self, on=True):
+        self._chk(self.L.mms_share_enable(self.h, 1 if on else 0))
+
+    def share_density(self):
+        """-> (volume share, colour/vector share); the caller owns (closes) the descriptors"""
+        v, r = MmsShare(), MmsShare()
+        self._chk(self.L.mms_share_density(self.h, C.byref(v), C.byref(r)))
+        return v, r
+
+    def share_mesh(self):
+        """-> (vertex count, positions share, normals share, colours share)"""
+        n = C.c_uint64()
+        p, q, c = MmsShare(), MmsShare(), MmsShare()
+        self._chk(self.L.mms_share_mesh(self.h, C.byref(n), C.byref(p), C.byref(q), C.byref(c)))
+        return n.value, p, q, c
 
     def route_particles(self, ptr, count, slabs, send_ptr, capacity, vtx_type=VERT_FLOAT_XYZ, stride=0, global_radius=0.5):
         """Stable partition of a device-resident list by destination slab (mms_route_particles) -> per-slab record counts."""

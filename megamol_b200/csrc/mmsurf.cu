@@ -7,8 +7,10 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <type_traits>
 #include <vector>
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include "../../include/mmsurf.h"
@@ -30,14 +32,111 @@ namespace {
 
 std::string g_createError;
 
+/** Driver entry points of the virtual-memory API (exportable allocations), looked up through the runtime: the library links cudart only. */
+struct Vmm {
+    CUresult (*create)(CUmemGenericAllocationHandle*, size_t, const CUmemAllocationProp*, unsigned long long) = nullptr;
+    CUresult (*release)(CUmemGenericAllocationHandle) = nullptr;
+    CUresult (*reserve)(CUdeviceptr*, size_t, size_t, CUdeviceptr, unsigned long long) = nullptr;
+    CUresult (*addrFree)(CUdeviceptr, size_t) = nullptr;
+    CUresult (*map)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long) = nullptr;
+    CUresult (*unmap)(CUdeviceptr, size_t) = nullptr;
+    CUresult (*setAccess)(CUdeviceptr, size_t, const CUmemAccessDesc*, size_t) = nullptr;
+    CUresult (*granularity)(size_t*, const CUmemAllocationProp*, CUmemAllocationGranularity_flags) = nullptr;
+    CUresult (*exportHandle)(void*, CUmemGenericAllocationHandle, CUmemAllocationHandleType, unsigned long long) = nullptr;
+    CUresult (*importHandle)(CUmemGenericAllocationHandle*, void*, CUmemAllocationHandleType) = nullptr;
+    bool ok = false;
+    static const Vmm& get() {
+        static const Vmm v = [] {
+            Vmm t;
+            auto load = [](const char* name, auto& fn) {
+                void* p = nullptr;
+                cudaDriverEntryPointQueryResult q{};
+                if (cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+                    cudaGetLastError();
+                    p = nullptr;
+                }
+                fn = reinterpret_cast<std::remove_reference_t<decltype(fn)>>(p);
+                return p != nullptr;
+            };
+            bool all = load("cuMemCreate", t.create);
+            all &= load("cuMemRelease", t.release);
+            all &= load("cuMemAddressReserve", t.reserve);
+            all &= load("cuMemAddressFree", t.addrFree);
+            all &= load("cuMemMap", t.map);
+            all &= load("cuMemUnmap", t.unmap);
+            all &= load("cuMemSetAccess", t.setAccess);
+            all &= load("cuMemGetAllocationGranularity", t.granularity);
+            all &= load("cuMemExportToShareableHandle", t.exportHandle);
+            all &= load("cuMemImportFromShareableHandle", t.importHandle);
+            t.ok = all;
+            return t;
+        }();
+        return v;
+    }
+    static CUmemAllocationProp prop(int device) {
+        CUmemAllocationProp pr{};
+        pr.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+        pr.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+        pr.location.id = device;
+        pr.requestedHandleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+        return pr;
+    }
+    /** Maps an allocation handle read-write for `device`; returns nullptr on failure. */
+    static void* mapHandle(CUmemGenericAllocationHandle h, size_t bytes, int device) {
+        const Vmm& v = get();
+        CUdeviceptr va = 0;
+        if (v.reserve(&va, bytes, 0, 0, 0) != CUDA_SUCCESS) return nullptr;
+        if (v.map(va, bytes, 0, h, 0) != CUDA_SUCCESS) {
+            v.addrFree(va, bytes);
+            return nullptr;
+        }
+        CUmemAccessDesc acc{};
+        acc.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+        acc.location.id = device;
+        acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+        if (v.setAccess(va, bytes, &acc, 1) != CUDA_SUCCESS) {
+            v.unmap(va, bytes);
+            v.addrFree(va, bytes);
+            return nullptr;
+        }
+        return reinterpret_cast<void*>(va);
+    }
+};
+
+/** Grow-only device buffer.  `shareable` buffers (mms_share_enable) come from the virtual-memory API with a POSIX file-descriptor handle,
+ *  so that a renderer can import them (GL_EXT_memory_object_fd / VkImportMemoryFdInfoKHR / cuMemImportFromShareableHandle). */
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
+    bool shareable = false;
+    int device = 0;
+    CUmemGenericAllocationHandle handle = 0;
+    bool allocShared(size_t bytes) {
+        const Vmm& v = Vmm::get();
+        if (!v.ok) return false;
+        const CUmemAllocationProp pr = Vmm::prop(device);
+        size_t gran = 0;
+        if (v.granularity(&gran, &pr, CU_MEM_ALLOC_GRANULARITY_MINIMUM) != CUDA_SUCCESS || gran == 0) return false;
+        const size_t want = (bytes + gran - 1) / gran * gran;
+        if (v.create(&handle, want, &pr, 0) != CUDA_SUCCESS) return false;
+        p = Vmm::mapHandle(handle, want, device);
+        if (!p) {
+            v.release(handle);
+            handle = 0;
+            return false;
+        }
+        cap = want;
+        return true;
+    }
     bool ensure(size_t bytes) {
         if (bytes <= cap) return true;
-        if (p) cudaFree(p);
-        p = nullptr;
         size_t want = std::max(bytes, cap + cap / 2);
+        release();
+        if (shareable) {
+            if (allocShared(want) || allocShared(bytes)) return true;
+            cap = 0, p = nullptr;
+            return false;
+        }
         if (cudaMalloc(&p, want) != cudaSuccess) {
             cudaGetLastError();
             want = bytes;
@@ -52,8 +151,15 @@ struct DevBuf {
         return true;
     }
     void release() {
-        if (p) cudaFree(p);
+        if (p && handle) {
+            const Vmm& v = Vmm::get();
+            v.unmap(reinterpret_cast<CUdeviceptr>(p), cap);
+            v.addrFree(reinterpret_cast<CUdeviceptr>(p), cap);
+            v.release(handle);
+        } else if (p)
+            cudaFree(p);
         p = nullptr;
+        handle = 0;
         cap = 0;
     }
     template<class T> T* as() { return static_cast<T*>(p); }
@@ -1525,6 +1631,81 @@ int mms_ipc_open(int32_t device, const unsigned char handle[64], void** ptr) {
 int mms_ipc_close(int32_t device, void* ptr) {
     DeviceGuard guard(device);
     return cudaIpcCloseMemHandle(ptr) == cudaSuccess ? MMS_OK : MMS_ERR_CUDA;
+}
+
+// ---- device-resident hand-off ------------------------------------------------------------------------------------
+int mms_share_enable(mms_ctx* c, int32_t on) {
+    if (!c) return MMS_ERR_INVALID;
+    if (on && !Vmm::get().ok) return c->fail(MMS_ERR_UNSUPPORTED, "the driver has no virtual-memory API (cuMemCreate ...)");
+    DeviceGuard guard(c->device);
+    MMS_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (DevBuf* b : {&c->vol, &c->rgb, &c->meshPos, &c->meshNrm, &c->meshCol}) {
+        if (b->shareable != (on != 0)) b->release(); // re-allocated from the other kind of memory on the next frame
+        b->shareable = on != 0;
+        b->device = c->device;
+    }
+    c->haveDensity = c->haveMesh = c->haveCount = false;
+    return MMS_OK;
+}
+
+static int shareOf(mms_ctx* c, DevBuf& b, uint64_t bytes, mms_share* out) {
+    if (!out) return MMS_OK;
+    *out = mms_share{-1, 0, 0, 0, 0};
+    if (!bytes) return MMS_OK;
+    if (!b.shareable || !b.handle) return c->fail(MMS_ERR_INVALID, "mms_share_enable was not in force when this buffer was produced");
+    int fd = -1;
+    if (Vmm::get().exportHandle(&fd, b.handle, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0) != CUDA_SUCCESS || fd < 0)
+        return c->fail(MMS_ERR_CUDA, "cuMemExportToShareableHandle failed");
+    out->fd = fd;
+    out->alloc_bytes = b.cap;
+    out->offset = 0;
+    out->bytes = bytes;
+    return MMS_OK;
+}
+
+int mms_share_density(mms_ctx* c, mms_share* vol, mms_share* rgb) {
+    if (!c) return MMS_ERR_INVALID;
+    if (!c->haveDensity || c->adoptedVol) return c->fail(MMS_ERR_INVALID, "no density of this context's own has been computed");
+    DeviceGuard guard(c->device);
+    if (int rc = checkDeviceError(c)) return rc; // (synchronises: the importer has no stream of ours to wait on)
+    const uint64_t nvox = static_cast<uint64_t>(c->grid.res[0]) * c->grid.res[1] * c->nz;
+    if (int rc = shareOf(c, c->vol, nvox * 4, vol)) return rc;
+    return shareOf(c, c->rgb, (c->haveColour || c->haveVector) ? nvox * 12 : 0, rgb);
+}
+
+int mms_share_mesh(mms_ctx* c, uint64_t* nverts, mms_share* pos, mms_share* nrm, mms_share* col) {
+    if (!c || !nverts) return MMS_ERR_INVALID;
+    if (!c->haveMesh || c->meshExternal) return c->fail(MMS_ERR_INVALID, "no isosurface has been extracted into library memory");
+    DeviceGuard guard(c->device);
+    MMS_CUDA(c, cudaStreamSynchronize(c->stream));
+    *nverts = c->ntris * 3;
+    const uint64_t bytes = c->ntris * 36;
+    if (int rc = shareOf(c, c->meshPos, bytes, pos)) return rc;
+    if (int rc = shareOf(c, c->meshNrm, bytes, nrm)) return rc;
+    return shareOf(c, c->meshCol, c->haveColour ? bytes : 0, col);
+}
+
+int mms_share_open(int32_t device, const mms_share* s, void** devptr) {
+    if (!s || !devptr || s->fd < 0 || !s->alloc_bytes || !Vmm::get().ok) return MMS_ERR_INVALID;
+    DeviceGuard guard(device);
+    cudaFree(nullptr); // a context on this device, should the importer be a fresh process
+    CUmemGenericAllocationHandle h = 0;
+    if (Vmm::get().importHandle(&h, reinterpret_cast<void*>(static_cast<intptr_t>(s->fd)), CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR) != CUDA_SUCCESS)
+        return MMS_ERR_CUDA;
+    void* p = Vmm::mapHandle(h, s->alloc_bytes, device);
+    Vmm::get().release(h); // the mapping keeps the memory alive
+    if (!p) return MMS_ERR_CUDA;
+    *devptr = static_cast<char*>(p) + s->offset;
+    return MMS_OK;
+}
+
+int mms_share_close(int32_t device, void* devptr, const mms_share* s) {
+    if (!devptr || !s || !Vmm::get().ok) return MMS_ERR_INVALID;
+    DeviceGuard guard(device);
+    const CUdeviceptr va = reinterpret_cast<CUdeviceptr>(static_cast<char*>(devptr) - s->offset);
+    if (Vmm::get().unmap(va, s->alloc_bytes) != CUDA_SUCCESS) return MMS_ERR_CUDA;
+    Vmm::get().addrFree(va, s->alloc_bytes);
+    return MMS_OK;
 }
 
 void* mms_alloc_pinned(size_t bytes) {

@@ -246,6 +246,23 @@ class Harness:
             res.update(pos=pos, nrm=nrm, col=col)
         return res
 
+    def share_density(self):
+        """B200 modules, 'memoryLocation' = VRAM: dict(fd, alloc_bytes, offset, bytes, memloc) of the volume's device allocation"""
+        out = (C.c_int64 * 5)()
+        self.lib.mmh_share_density.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
+        if self.lib.mmh_share_density(self.h, out):
+            raise RuntimeError("the density module has no device-resident volume to share")
+        return dict(fd=out[0], alloc_bytes=out[1], offset=out[2], bytes=out[3], memloc=out[4])
+
+    def share_mesh(self, which: int = 0):
+        """B200 modules, 'deviceMesh' on: (nverts, positions share, normals share) as dicts(fd, alloc_bytes, offset, bytes)"""
+        out = (C.c_int64 * 9)()
+        self.lib.mmh_share_mesh.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int64)]
+        if self.lib.mmh_share_mesh(self.h, int(which), out):
+            raise RuntimeError("the isosurface module has no device-resident mesh to share")
+        mk = lambda o: dict(fd=out[o], alloc_bytes=out[o + 1], offset=out[o + 2], bytes=out[o + 3])
+        return out[0], mk(1), mk(5)
+
     def mc_tables(self):
         tri = np.empty((256, 16), np.int32)
         cnt = np.empty(256, np.uint8)

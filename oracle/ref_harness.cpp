@@ -20,6 +20,7 @@
 #include <vector>
 
 #include <omp.h>
+#include <unistd.h>
 
 #include "datatools/table/TableDataCall.h"
 #include "geometry_calls/MultiParticleDataCall.h"
@@ -544,6 +545,32 @@ int mmh_copy_mesh(void* hv, float* pos, float* nrm, float* col) {
     }
     return 0;
 }
+
+#ifdef MMH_B200
+/** Device-resident hand-off of the B200 modules: out[0..4] = volume share {fd, alloc_bytes, offset, bytes, MemLoc of the metadata}. */
+int mmh_share_density(void* hv, int64_t out[5]) {
+    auto* h = static_cast<Harness*>(hv);
+    mms_share v{}, rgb{};
+    if (!h->p2d->ShareDensity(&v, &rgb)) return -1;
+    if (rgb.fd >= 0) close(rgb.fd);
+    auto* call = h->sink->volSlot.CallAs<geocalls::VolumetricDataCall>();
+    out[0] = v.fd, out[1] = static_cast<int64_t>(v.alloc_bytes), out[2] = static_cast<int64_t>(v.offset), out[3] = static_cast<int64_t>(v.bytes);
+    out[4] = (call && call->GetMetadata()) ? static_cast<int64_t>(call->GetMetadata()->MemLoc) : -1;
+    return 0;
+}
+/** out = {nverts, then for positions and normals: fd, alloc_bytes, offset, bytes}. */
+int mmh_share_mesh(void* hv, int which, int64_t out[9]) {
+    auto* h = static_cast<Harness*>(hv);
+    mms_share p{}, n{}, c{};
+    uint64_t nv = 0;
+    if (!(which ? h->iso2 : h->iso)->ShareMesh(&nv, &p, &n, &c)) return -1;
+    if (c.fd >= 0) close(c.fd);
+    out[0] = static_cast<int64_t>(nv);
+    out[1] = p.fd, out[2] = static_cast<int64_t>(p.alloc_bytes), out[3] = static_cast<int64_t>(p.offset), out[4] = static_cast<int64_t>(p.bytes);
+    out[5] = n.fd, out[6] = static_cast<int64_t>(n.alloc_bytes), out[7] = static_cast<int64_t>(n.offset), out[8] = static_cast<int64_t>(n.bytes);
+    return 0;
+}
+#endif
 
 /** The reference's marching-cubes tables (plugins/trisoup/src/volumetrics/MarchingCubeTables.cpp:11-285). */
 void mmh_mc_tables(int32_t tri[256 * 16], uint8_t count[256], uint32_t edgeflags[256], uint32_t vertoff[8 * 3],

@@ -12,6 +12,7 @@
 #include <chrono>
 
 #include "ParticlesToDensityB200.h"
+#include "mmcore/param/BoolParam.h"
 #include "mmcore/param/EnumParam.h"
 #include "mmcore/param/FloatParam.h"
 #include "mmcore/param/IntParam.h"
@@ -35,7 +36,8 @@ IsoSurfaceB200::IsoSurfaceB200()
         , isoValueSlot("isoval", "The iso value")
         , deviceSlot("device", "CUDA device ordinal used for volumes that are not already device resident")
         , algorithmSlot("algorithm", "Triangulation: marching cubes (smooth normals, node-centred frame) or the CPU module's marching "
-                                     "tetrahedra reproduced triangle for triangle") {
+                                     "tetrahedra reproduced triangle for triangle")
+        , deviceMeshSlot("deviceMesh", "Leave the mesh in importable device memory (ShareMesh()); CallTriMeshData then carries no object") {
 
     this->inDataSlot.SetCompatibleCall<geocalls::VolumetricDataCallDescription>();
     this->MakeSlotAvailable(&this->inDataSlot);
@@ -58,6 +60,9 @@ IsoSurfaceB200::IsoSurfaceB200()
     alg->SetTypePair(MMS_ISO_MARCHING_TETS, "MarchingTetrahedra (as trisoup_gl::IsoSurface)");
     this->algorithmSlot << alg;
     this->MakeSlotAvailable(&this->algorithmSlot);
+
+    this->deviceMeshSlot << new core::param::BoolParam(false);
+    this->MakeSlotAvailable(&this->deviceMeshSlot);
 }
 
 IsoSurfaceB200::~IsoSurfaceB200() {
@@ -110,6 +115,10 @@ bool IsoSurfaceB200::buildMesh(VolumetricDataCall* cvd, float iso) {
     if (callee != nullptr) {
         auto parent = callee->Parent();
         auto* p2d = dynamic_cast<const ParticlesToDensityB200*>(parent.get());
+        if (p2d != nullptr && p2d->Group() != nullptr && this->deviceMeshSlot.Param<core::param::BoolParam>()->Value()) {
+            Log::DefaultLog.WriteError("IsoSurfaceB200: 'deviceMesh' hands out ONE device allocation; it cannot follow a multi-device producer");
+            return false;
+        }
         if (p2d != nullptr && p2d->Group() != nullptr && p2d->VolumeHash() == cvd->DataHash() && algorithm == MMS_ISO_MARCHING_CUBES) {
             // a multi-device producer: this module's own slab group on the same devices adopts every slab's volume, the slabs' meshes are
             // concatenated (= the single-GPU order) into this module's pinned arrays
@@ -153,6 +162,15 @@ bool IsoSurfaceB200::buildMesh(VolumetricDataCall* cvd, float iso) {
             return false;
         }
         this->ctxDevice = device;
+        this->meshOnDevice = false;
+    }
+    const bool wantDevice = this->deviceMeshSlot.Param<core::param::BoolParam>()->Value();
+    if (wantDevice != this->meshOnDevice) {
+        if (mms_share_enable(this->ctx, wantDevice ? 1 : 0) != MMS_OK) {
+            Log::DefaultLog.WriteError("IsoSurfaceB200: %s", mms_last_error(this->ctx));
+            return false;
+        }
+        this->meshOnDevice = wantDevice;
     }
     mms_ctx* use = this->ctx;
     if (producer != nullptr) {
@@ -186,7 +204,7 @@ bool IsoSurfaceB200::buildMesh(VolumetricDataCall* cvd, float iso) {
     uint64_t nverts = 0;
     const float *pos = nullptr, *nrm = nullptr, *col = nullptr; // col stays NULL unless the volume carries colours (QuickSurf mode)
     if (mms_set_isosurface_mode(use, algorithm) != MMS_OK || mms_extract_isosurface(use, iso) != MMS_OK ||
-        mms_get_mesh(use, &nverts, &pos, &nrm, &col) != MMS_OK) {
+        (!this->meshOnDevice && mms_get_mesh(use, &nverts, &pos, &nrm, &col) != MMS_OK)) {
         Log::DefaultLog.WriteError("IsoSurfaceB200: %s", mms_last_error(use));
         return false;
     }
@@ -199,6 +217,16 @@ bool IsoSurfaceB200::buildMesh(VolumetricDataCall* cvd, float iso) {
     const std::chrono::duration<float, std::milli> ms = std::chrono::high_resolution_clock::now() - t0;
     Log::DefaultLog.WriteInfo("IsoSurfaceB200: %llu triangles at iso %f took %f ms (%s volume).", static_cast<unsigned long long>(nverts / 3), iso,
         ms.count(), producer == nullptr ? "uploaded" : "device-resident");
+    return true;
+}
+
+bool IsoSurfaceB200::ShareMesh(uint64_t* nverts, mms_share* positions, mms_share* normals, mms_share* colours) {
+    if (!this->has_mesh || !this->meshOnDevice || this->ctx == nullptr)
+        return false;
+    if (mms_share_mesh(this->ctx, nverts, positions, normals, colours) != MMS_OK) {
+        Log::DefaultLog.WriteError("IsoSurfaceB200: %s", mms_last_error(this->ctx));
+        return false;
+    }
     return true;
 }
 
@@ -219,6 +247,10 @@ bool IsoSurfaceB200::outDataCallback(core::Call& caller) {
         }
         if (this->algorithmSlot.IsDirty()) {
             this->algorithmSlot.ResetDirty();
+            recalc = true;
+        }
+        if (this->deviceMeshSlot.IsDirty()) {
+            this->deviceMeshSlot.ResetDirty();
             recalc = true;
         }
         cvd->SetFrameID(tmd->FrameID(), tmd->IsFrameForced());
@@ -242,7 +274,7 @@ bool IsoSurfaceB200::outDataCallback(core::Call& caller) {
     }
     tmd->SetDataHash(this->dataHash);
     tmd->SetFrameID(this->frameIdx);
-    tmd->SetObjects(1, &this->mesh);
+    tmd->SetObjects(this->meshOnDevice ? 0 : 1, &this->mesh); // device mesh: nothing for a host-side consumer, see ShareMesh()
     tmd->SetUnlocker(nullptr);
     return true;
 }

@@ -33,6 +33,14 @@ public:
     IsoSurfaceB200();
     ~IsoSurfaceB200() override;
 
+    /**
+     * Device-resident hand-off ('deviceMesh' on): the triangle soup of the last GetData as importable device memory -- positions,
+     * normals (and colours) with 3 floats per vertex, the layout CallTriMeshData hands out on the host.  A renderer imports the
+     * descriptors (GL_EXT_memory_object_fd / Vulkan / CUDA) instead of re-buffering host arrays every frame
+     * (trisoup_gl/src/ModernTrisoupRenderer.cpp:308-440).  The caller closes the descriptors.
+     */
+    bool ShareMesh(uint64_t* nverts, mms_share* positions, mms_share* normals, mms_share* colours);
+
 protected:
     bool create() override;
     void release() override;
@@ -44,7 +52,8 @@ private:
 
     core::CallerSlot inDataSlot;
     core::CalleeSlot outDataSlot;
-    core::param::ParamSlot attributeSlot, isoValueSlot, deviceSlot, algorithmSlot;
+    core::param::ParamSlot attributeSlot, isoValueSlot, deviceSlot, algorithmSlot, deviceMeshSlot;
+    bool meshOnDevice = false;
 
     mms_ctx* ctx = nullptr; // own context, used when the volume comes from a foreign (host) source
     int ctxDevice = -1;

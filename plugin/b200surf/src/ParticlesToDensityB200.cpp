@@ -51,6 +51,8 @@ ParticlesToDensityB200::ParticlesToDensityB200()
         , deviceSlot("device", "CUDA device ordinal the volume is computed on")
         , devicesSlot("devices", "Several CUDA devices, comma separated (e.g. 0,1,2,3): the volume is computed in z-slabs with halo, one per "
                                  "device (position aggregator of the bump mode); empty = the single device of 'device'")
+        , memLocSlot("memoryLocation", "RAM: the volume is copied to host memory (the contract of VolumetricDataCall::GetData()); VRAM: it "
+                                       "stays in importable device memory (MemLoc = VRAM, GetData() = nullptr, see ShareDensity())")
         , modeSlot("mode", "Density semantics: ParticlesToDensity bump kernel or QuickSurf Gaussian")
         , qsQualitySlot("quicksurf::quality", "Quality: 0 low .. 3 ultra (Gaussian cut-off 2.0/2.5/3.0/4.0 sigma)")
         , qsRadScaleSlot("quicksurf::radiusScale", "Radius scale")
@@ -116,6 +118,11 @@ ParticlesToDensityB200::ParticlesToDensityB200()
     this->MakeSlotAvailable(&this->deviceSlot);
     this->devicesSlot << new core::param::StringParam("");
     this->MakeSlotAvailable(&this->devicesSlot);
+    auto* ml = new core::param::EnumParam(static_cast<int>(geocalls::MemoryLocation::RAM));
+    ml->SetTypePair(static_cast<int>(geocalls::MemoryLocation::RAM), "RAM");
+    ml->SetTypePair(static_cast<int>(geocalls::MemoryLocation::VRAM), "VRAM");
+    this->memLocSlot << ml;
+    this->MakeSlotAvailable(&this->memLocSlot);
 
     auto* mp = new core::param::EnumParam(0);
     mp->SetTypePair(0, "ParticlesToDensity_Bump");
@@ -169,13 +176,13 @@ bool ParticlesToDensityB200::dummyCallback(core::Call&) {
 bool ParticlesToDensityB200::anythingDirty() const {
     return this->aggregatorSlot.IsDirty() || this->xResSlot.IsDirty() || this->yResSlot.IsDirty() || this->zResSlot.IsDirty() ||
            this->cyclXSlot.IsDirty() || this->cyclYSlot.IsDirty() || this->cyclZSlot.IsDirty() || this->normalizeSlot.IsDirty() ||
-           this->sigmaSlot.IsDirty() || this->deviceSlot.IsDirty() || this->devicesSlot.IsDirty() || this->modeSlot.IsDirty() || this->qsQualitySlot.IsDirty() ||
+           this->sigmaSlot.IsDirty() || this->deviceSlot.IsDirty() || this->devicesSlot.IsDirty() || this->memLocSlot.IsDirty() || this->modeSlot.IsDirty() || this->qsQualitySlot.IsDirty() ||
            this->qsRadScaleSlot.IsDirty() || this->qsColourSlot.IsDirty() || this->qsGridSpacingSlot.IsDirty() ||
            this->qsRefCellsSlot.IsDirty();
 }
 
 void ParticlesToDensityB200::resetDirty() {
-    for (auto* s : {&aggregatorSlot, &xResSlot, &yResSlot, &zResSlot, &cyclXSlot, &cyclYSlot, &cyclZSlot, &normalizeSlot, &sigmaSlot, &deviceSlot, &devicesSlot, &modeSlot,
+    for (auto* s : {&aggregatorSlot, &xResSlot, &yResSlot, &zResSlot, &cyclXSlot, &cyclYSlot, &cyclZSlot, &normalizeSlot, &sigmaSlot, &deviceSlot, &devicesSlot, &memLocSlot, &modeSlot,
              &qsQualitySlot, &qsRadScaleSlot, &qsColourSlot, &qsGridSpacingSlot, &qsRefCellsSlot})
         s->ResetDirty();
 }
@@ -260,7 +267,17 @@ void ParticlesToDensityB200::fillMetadata(core::AbstractGetData3DCall* in) {
             this->sliceDists[a] = md.Extents[a] / static_cast<float>(md.Resolution[a] - 1);
         }
     }
-    md.MemLoc = geocalls::MemoryLocation::RAM;
+    md.MemLoc = this->volumeOnDevice ? geocalls::MemoryLocation::VRAM : geocalls::MemoryLocation::RAM;
+}
+
+bool ParticlesToDensityB200::ShareDensity(mms_share* volume, mms_share* rgb) {
+    if (!this->has_data || !this->volumeOnDevice || this->ctx == nullptr || this->groupActive)
+        return false;
+    if (mms_share_density(this->ctx, volume, rgb) != MMS_OK) {
+        Log::DefaultLog.WriteError("ParticlesToDensityB200: %s", mms_last_error(this->ctx));
+        return false;
+    }
+    return true;
 }
 
 void ParticlesToDensityB200::surfaceBBox(core::AbstractGetData3DCall* in) {
@@ -303,6 +320,16 @@ bool ParticlesToDensityB200::computeVolume(core::AbstractGetData3DCall* in) {
             return false;
         }
         this->ctxDevice = device;
+        this->volumeOnDevice = false;
+    }
+    const bool wantDevice =
+        this->memLocSlot.Param<core::param::EnumParam>()->Value() == static_cast<int>(geocalls::MemoryLocation::VRAM);
+    if (wantDevice != this->volumeOnDevice) {
+        if (mms_share_enable(this->ctx, wantDevice ? 1 : 0) != MMS_OK) {
+            Log::DefaultLog.WriteError("ParticlesToDensityB200: %s", mms_last_error(this->ctx));
+            return false;
+        }
+        this->volumeOnDevice = wantDevice;
     }
     const auto bbox = in->AccessBoundingBoxes().ObjectSpaceBBox();
     mms_grid grid{};
@@ -408,6 +435,10 @@ bool ParticlesToDensityB200::computeVolume(core::AbstractGetData3DCall* in) {
     }
     this->groupActive = false;
     if (devs.size() > 1) {
+        if (this->volumeOnDevice) {
+            Log::DefaultLog.WriteError("ParticlesToDensityB200: 'memoryLocation' = VRAM hands out ONE device allocation; it cannot be combined with 'devices'");
+            return false;
+        }
         if (p.mode != MMS_MODE_P2D_BUMP || p.aggregator != 0) {
             Log::DefaultLog.WriteError("ParticlesToDensityB200: 'devices' computes the position aggregator of the bump mode; use 'device' for the other modes");
             return false;
@@ -491,6 +522,8 @@ bool ParticlesToDensityB200::computeVolume(core::AbstractGetData3DCall* in) {
     if (this->isVector) {
         if (!this->buildVectorOutputs(grid, p.normalize != 0))
             return fail("get_vector_field");
+    } else if (this->volumeOnDevice) {
+        this->hostVolume = nullptr; // VRAM: consumers import the device memory (ShareDensity) or adopt it (IsoSurfaceB200)
     } else if (mms_get_density(this->ctx, &this->hostVolume, nullptr) != MMS_OK) // RAM contract of VolumetricDataCall::GetData()
         return fail("get_density");
     this->hasColour = p.colour != 0;

@@ -60,6 +60,12 @@ public:
     const std::vector<int32_t>& GroupDevices() const {
         return this->groupDevices;
     }
+    /**
+     * Device-resident hand-off ('memoryLocation' = VRAM): the volume (and, with colours, the RGB volume) as importable device memory --
+     * what VolumetricDataCall::SetData(uint32_t texture) + MemLoc VRAM (VolumetricDataCall.h:290-292) is for GL.  The caller closes the
+     * descriptors.  false when the parameter is off or nothing has been computed.
+     */
+    bool ShareDensity(mms_share* volume, mms_share* rgb);
     /** true if the context also holds a density-weighted RGB volume (QuickSurf mode with colour). */
     bool HasColour() const {
         return this->hasColour;
@@ -92,6 +98,8 @@ private:
 
     mms_ctx* ctx = nullptr;
     int ctxDevice = -1;
+    core::param::ParamSlot memLocSlot; // extra: RAM (the reference's contract) or VRAM (no host copy; consumers import the device memory)
+    bool volumeOnDevice = false;
     core::param::ParamSlot devicesSlot; // extra: several CUDA devices, e.g. "0,1,2,3": the volume is computed in z-slabs (scalar bump mode)
     mms_slabs* group = nullptr;
     std::vector<int32_t> groupDevices;

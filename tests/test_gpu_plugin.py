@@ -129,6 +129,62 @@ def test_two_isosurface_modules_share_one_density_module(plug):
     assert np.array_equal(pos, a["pos"]) and np.array_equal(nrm, a["nrm"])
 
 
+def _read_share(sh):
+    """a CUDA consumer: import the descriptor, map, copy out, unmap"""
+    import ctypes as C
+    import os
+    from megamol_b200 import api
+    L = api.load_library()
+    share = api.MmsShare(int(sh["fd"]), 0, int(sh["alloc_bytes"]), int(sh["offset"]), int(sh["bytes"]))
+    p = C.c_void_p()
+    assert L.mms_share_open(0, C.byref(share), C.byref(p)) == 0
+    out = np.empty(share.bytes // 4, np.float32)
+    rt = C.CDLL("libcudart.so.12")
+    rt.cudaMemcpy.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+    assert rt.cudaMemcpy(out.ctypes.data, p, share.bytes, 2) == 0
+    assert L.mms_share_close(0, p, C.byref(share)) == 0
+    os.close(share.fd)
+    return out
+
+
+def test_device_resident_hand_off_through_the_modules():
+    """'memoryLocation' = VRAM on the density module (MemLoc VRAM, GetData() = nullptr, no host copy) and 'deviceMesh'
+    on the isosurface module (CallTriMeshData without objects): a consumer that imports the modules' device memory sees exactly the
+    volume and the soup the host contract delivers."""
+    n, box, res = 8000, 10.0, (40, 36, 32)
+    xyz = synth.uniform_box(n, box, seed=29)
+    lists = [dict(vtx=xyz, vtx_type=rb.VERT_FLOAT_XYZ, count=n, global_radius=1.0)]
+    host = rb.Harness(rb.PLUG_LIB)
+    feed(host, lists, (0, 0, 0, box, box, box), res, cyclic=(True,) * 3, normalize=True)
+    vol, _ = host.pull_volume()
+    mesh = host.pull_mesh(0.4)
+    dev = rb.Harness(rb.PLUG_LIB)
+    feed(dev, lists, (0, 0, 0, box, box, box), res, cyclic=(True,) * 3, normalize=True)
+    dev.set_param(0, "memoryLocation", 0)  # geocalls::MemoryLocation::VRAM
+    dev.set_param(1, "deviceMesh", 1)
+    _, meta = dev.pull_volume(copy=False)
+    assert meta["resolution"] == res
+    with pytest.raises(RuntimeError):  # GetData() is nullptr for a VRAM volume (VolumetricDataCall.h:136-144)
+        dev.pull_volume(copy=True)
+    sv = dev.share_density()
+    assert sv["memloc"] == 0
+    assert np.array_equal(_read_share(sv), vol.ravel())
+    m = dev.pull_mesh(0.4, copy=False)
+    assert m["nverts"] == 0  # no host object
+    nverts, sp, sn = dev.share_mesh()
+    assert nverts == mesh["nverts"]
+    assert np.array_equal(_read_share(sp), mesh["pos"].ravel())
+    assert np.array_equal(_read_share(sn), mesh["nrm"].ravel())
+    # back to the host contract on the same modules
+    dev.set_param(0, "memoryLocation", 1)
+    dev.set_param(1, "deviceMesh", 0)
+    vol2, _ = dev.pull_volume()
+    assert np.array_equal(vol2, vol)
+    m2 = dev.pull_mesh(0.4)
+    assert np.array_equal(m2["pos"], mesh["pos"])
+    host.close(), dev.close()
+
+
 def test_modules_on_two_devices(plug):
     """The modules' `devices` parameter: ParticlesToDensityB200 computes the volume in z-slabs on two GPUs behind one handle (mms_slabs_*),
     IsoSurfaceB200 adopts the slabs' device volumes into its own group; volume and mesh equal the single-device modules' bit for bit."""
