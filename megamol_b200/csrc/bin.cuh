@@ -79,6 +79,7 @@ __global__ void __launch_bounds__(256) bin_count_kernel(Geo g, ListDev l, unsign
     const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
     float rmax = 0.0f;
     unsigned kept = 0;
+    bool outside = false; // a kept particle whose home voxel lies outside the grid on a periodic axis (binned through the wrap)
     const unsigned long long count = listCount(l);
     if (l.countPtr && threadIdx.x == 0 && blockIdx.x == 0 && *l.countPtr > l.count) st->pad[0] = 5u; // halo receive buffer overflowed
     for (unsigned long long j = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; j < count; j += stride) {
@@ -91,8 +92,12 @@ __global__ void __launch_bounds__(256) bin_count_kernel(Geo g, ListDev l, unsign
             atomicAdd(&cellCount[q.cell], 1u);
             rmax = fmaxf(rmax, q.p.w);
             ++kept;
+            outside |= (g.cyc[0] && static_cast<unsigned>(q.X) >= static_cast<unsigned>(g.s[0])) ||
+                       (g.cyc[1] && static_cast<unsigned>(q.Y) >= static_cast<unsigned>(g.s[1])) ||
+                       (g.cyc[2] && static_cast<unsigned>(q.Z) >= static_cast<unsigned>(g.s[2]));
         }
     }
+    if (outside) st->pad[1] = 1u; // density_splat3_kernel: its pre-test has to normalise the coordinates first
     rmax = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(rmax))); // positive floats order like uints
     kept = __reduce_add_sync(0xffffffffu, kept);
     if ((threadIdx.x & 31) == 0 && kept) {

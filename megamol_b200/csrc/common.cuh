@@ -65,7 +65,7 @@ struct DevState {
     unsigned minKey;     // density range, order-preserving uint keys (atomicMin/Max)
     unsigned maxKey;
     unsigned long long totalTris;
-    unsigned pad[2];     // [0] error flag of the density kernels
+    unsigned pad[2];     // [0] error flag of the density kernels, [1] some kept particle lies outside the grid on a periodic axis
     unsigned nBig;       // crowded cells (more than kBigCell records) found by cell_order_kernel ...
     unsigned bigNext;    // ... and the work counter of cell_sort_big_kernel
 };

@@ -63,7 +63,7 @@ struct SplatShared {
 static_assert(sizeof(SplatShared) <= 57088, "density_splat_kernel must fit four blocks per SM");
 
 /** Ordered, duplicate-free list of the cells along one axis whose particles can reach voxels [t0, t1]. */
-__device__ inline int buildAxisCells(int t0, int t1, int reach, int s, bool cyc, int sh, int nc, int* out, int cap) {
+__host__ __device__ inline int buildAxisCells(int t0, int t1, int reach, int s, bool cyc, int sh, int nc, int* out, int cap) {
     int a = t0 - reach, b = t1 + reach;
     int n = 0;
     if (!cyc) {
@@ -427,12 +427,14 @@ constexpr int S3_SY = 35, S3_SZ = 297;               // padded strides (= 3 and 
 constexpr int S3_FLOATS = S3_SZ * S3_Z;              // 1188
 constexpr int S3_QCAP = 64;                          // survivor queue (ring)
 constexpr int S3_HITCAP = 512;                       // (particle, voxel) pairs expanded at a time (32 x 27 worst case: further passes)
+constexpr int S3_PRECELLS = 6;                       // y / z cells that can reach a sub-tile (8 + 2*2 voxels: at most 4 cells of 4 voxels)
 constexpr int S3_MAXCELLS = 12;                      // cells along one axis that can reach a sub-tile (32/4 + 2 ring cells + wrap slack)
 
 struct Splat3Warp {
     float tile[S3_FLOATS];
     float4 queue[S3_QCAP];
     unsigned short hits[S3_HITCAP];                  // (lane of the particle << 5) | voxel number 0..26 inside its 3x3x3 box, in summation order
+    float2 bx[4], by[S3_PRECELLS], bz[S3_PRECELLS];  // pre-test bounds of the sub-tile per x run / y cell / z cell, the cell's periodic shift folded in
 };
 /** Cells along one axis whose particles can reach a voxel range, ascending global id; shift = what to add to the coordinate
  *  of a particle of that cell (the image next to the cell's own voxels) to get the periodic image that lies next to the range
@@ -443,13 +445,17 @@ struct Splat3Axis {
     float shift[S3_MAXCELLS];
     float mid[S3_MAXCELLS];
 };
+/** The x cells of a block tile in runs of consecutive ids with one shift: contiguous record ranges. */
+struct Splat3Runs {
+    int nruns;                                       // -1: more than four runs (cannot happen when the host picked the cell size from the reach)
+    int runA[4], runB[4];
+    float runShift[4], runMid[4];
+};
 struct Splat3Shared {
     Splat3Warp w[CT_WARPS];
     float4 lut[27];                                  // voxel number -> (ix, iy, iz as floats, sub-tile offset as int bits)
-    Splat3Axis axis[7];                              // x of the block tile | y of the two sub-tile rows | z of the four sub-tile layers
-    int nruns;                                       // x cells in runs of consecutive ids with one shift: contiguous record ranges
-    int runA[4], runB[4];
-    float runShift[4], runMid[4];
+    Splat3Axis axis[6];                              // y of the two sub-tile rows | z of the four sub-tile layers
+    Splat3Runs runs;                                 // x of the block tile
 };
 static_assert(sizeof(Splat3Shared) <= 57088, "density_splat3_kernel must fit four blocks per SM");
 /** Derived grid constants, computed once on the host: as kernel parameters they are constant-bank operands (no registers, nothing to
@@ -461,8 +467,63 @@ struct Splat3Consts {
     float slack[3];  // slack of the pre-test, object units
 };
 
+/** Cell list of one axis range [t0, t1] of a sub-tile (a = axis, lim = end of the grid / slab along it): ascending global cell id -- the
+ *  summation order must not depend on where the tile sits.  Depends on the grid geometry only, so the host builds the tables of all
+ *  block coordinates once per geometry (splat3BuildTables) and the kernel just loads its seven. */
+__host__ __device__ inline void splat3AxisTable(const Geo& g, int reach, int a, int t0, int lim, int extent, Splat3Axis& A) {
+    const int t1 = (t0 + extent < lim ? t0 + extent : lim) - 1;
+    int tmp[CT_MAXAXIS];
+    const int n = t1 >= t0 ? buildAxisCells(t0, t1, reach, g.s[a], g.cyc[a] != 0, g.cshift, g.nc[a], tmp, S3_MAXCELLS) : 0;
+    for (int i = 1; i < n; ++i) {
+        const int c = tmp[i];
+        int k = i - 1;
+        for (; k >= 0 && tmp[k] > c; --k) tmp[k + 1] = tmp[k];
+        tmp[k + 1] = c;
+    }
+    A.n = n;
+    const int C = 1 << g.cshift, lo = t0 - reach, hi = t1 + reach;
+    for (int i = 0; i < S3_MAXCELLS; ++i) A.cell[i] = 0, A.shift[i] = 0.0f, A.mid[i] = 0.0f;
+    for (int i = 0; i < n; ++i) {
+        const int v0 = tmp[i] * C, v1 = (v0 + C < g.s[a] ? v0 + C : g.s[a]) - 1; // the cell's voxels
+        float shift = 0.0f;
+        if (g.cyc[a] && !(v1 >= lo && v0 <= hi)) shift = (v1 + g.s[a] >= lo && v0 + g.s[a] <= hi) ? (float)g.s[a] : -(float)g.s[a];
+        A.cell[i] = tmp[i], A.shift[i] = shift * g.sd[a], A.mid[i] = 0.5f * (float)(v0 + v1) * g.sd[a] + g.mn[a];
+    }
+}
+__host__ __device__ inline void splat3RunTable(const Geo& g, const Splat3Axis& A, Splat3Runs& R) {
+    const int C = 1 << g.cshift, n = A.n;
+    int nr = 0;
+    for (int k = 0; k < 4; ++k) R.runA[k] = R.runB[k] = 0, R.runShift[k] = R.runMid[k] = 0.0f;
+    for (int i = 0; i < n;) {
+        const int ca = A.cell[i];
+        int cb = ca;
+        for (++i; i < n && A.cell[i] == cb + 1 && A.shift[i] == A.shift[i - 1]; ++i) ++cb;
+        if (nr < 4) {
+            const int vEnd = (cb + 1) * C < g.s[0] ? (cb + 1) * C : g.s[0];
+            R.runA[nr] = ca, R.runB[nr] = cb, R.runShift[nr] = A.shift[i - 1];
+            R.runMid[nr] = 0.5f * (float)(ca * C + vEnd - 1) * g.sd[0] + g.mn[0];
+        }
+        ++nr;
+    }
+    R.nruns = n < 0 ? -1 : (nr <= 4 ? nr : -1);
+}
+/** Table layout in device memory: runs[gx] | axisY[2 * gy] | axisZ[4 * gz] (gx, gy, gz = grid of block tiles). */
+inline size_t splat3TableBytes(int gx, int gy, int gz) { return sizeof(Splat3Runs) * gx + sizeof(Splat3Axis) * (2 * gy + 4 * gz); }
+inline void splat3BuildTables(const Geo& g, int reach, int gx, int gy, int gz, unsigned char* out) {
+    Splat3Runs* runs = reinterpret_cast<Splat3Runs*>(out);
+    Splat3Axis* ay = reinterpret_cast<Splat3Axis*>(out + sizeof(Splat3Runs) * gx);
+    Splat3Axis* az = ay + 2 * gy;
+    for (int b = 0; b < gx; ++b) {
+        Splat3Axis A;
+        splat3AxisTable(g, reach, 0, b * CT_X, g.s[0], S3_X, A);
+        splat3RunTable(g, A, runs[b]);
+    }
+    for (int b = 0; b < 2 * gy; ++b) splat3AxisTable(g, reach, 1, (b >> 1) * CT_Y + (b & 1) * S3_Y, g.s[1], S3_Y, ay[b]);
+    for (int b = 0; b < 4 * gz; ++b) splat3AxisTable(g, reach, 2, g.z0 + (b >> 2) * CT_Z + (b & 3) * S3_Z, g.z0 + g.nz, S3_Z, az[b]);
+}
+
 __global__ void __launch_bounds__(CT_THREADS, 4) density_splat3_kernel(Geo g, Splat3Consts kc, DevState* st, const float4* __restrict__ recs,
-    const unsigned* __restrict__ cellStart, float* __restrict__ vol, int reach) {
+    const unsigned* __restrict__ cellStart, float* __restrict__ vol, int reach, const unsigned char* __restrict__ tables) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     Splat3Shared& sh = *reinterpret_cast<Splat3Shared*>(smemRaw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -470,52 +531,25 @@ __global__ void __launch_bounds__(CT_THREADS, 4) density_splat3_kernel(Geo g, Sp
         const int ix = tid % 3, iy = (tid / 3) % 3, iz = tid / 9;
         sh.lut[tid] = make_float4((float)ix, (float)iy, (float)iz, __int_as_float(ix + iy * S3_SY + iz * S3_SZ));
     }
-    if (lane == 0 && warp < 7) { // one thread of seven warps each: the cell lists of the block's x range, its two y ranges and its four z ranges
-        const int q = warp;
-        const int a = q == 0 ? 0 : (q < 3 ? 1 : 2);
-        const int sub = q == 0 ? 0 : (q < 3 ? q - 1 : q - 3);
-        const int t0 = a == 0 ? (int)blockIdx.x * CT_X : (a == 1 ? (int)blockIdx.y * CT_Y + sub * S3_Y : g.z0 + (int)blockIdx.z * CT_Z + sub * S3_Z);
-        const int lim = a == 2 ? g.z0 + g.nz : g.s[a];
-        const int t1 = min(t0 + (a == 0 ? S3_X : (a == 1 ? S3_Y : S3_Z)), lim) - 1;
-        Splat3Axis& A = sh.axis[q];
-        int tmp[CT_MAXAXIS];
-        int n = t1 >= t0 ? buildAxisCells(t0, t1, reach, g.s[a], g.cyc[a] != 0, g.cshift, g.nc[a], tmp, S3_MAXCELLS) : 0;
-        for (int i = 1; i < n; ++i) { // ascending global cell id: the summation order must not depend on where the tile sits
-            const int c = tmp[i];
-            int k = i - 1;
-            for (; k >= 0 && tmp[k] > c; --k) tmp[k + 1] = tmp[k];
-            tmp[k + 1] = c;
-        }
-        A.n = n;
-        const int C = 1 << g.cshift, lo = t0 - reach, hi = t1 + reach;
-        for (int i = 0; i < n; ++i) {
-            const int v0 = tmp[i] * C, v1 = min(v0 + C, g.s[a]) - 1; // the cell's voxels
-            float shift = 0.0f;
-            if (g.cyc[a] && !(v1 >= lo && v0 <= hi)) shift = (v1 + g.s[a] >= lo && v0 + g.s[a] <= hi) ? (float)g.s[a] : -(float)g.s[a];
-            A.cell[i] = tmp[i], A.shift[i] = shift * g.sd[a], A.mid[i] = 0.5f * (float)(v0 + v1) * g.sd[a] + g.mn[a];
-        }
-        if (q == 0) {
-            int nr = 0;
-            for (int i = 0; i < n;) {
-                const int ca = A.cell[i];
-                int cb = ca;
-                for (++i; i < n && A.cell[i] == cb + 1 && A.shift[i] == A.shift[i - 1]; ++i) ++cb;
-                if (nr < 4)
-                    sh.runA[nr] = ca, sh.runB[nr] = cb, sh.runShift[nr] = A.shift[i - 1],
-                    sh.runMid[nr] = 0.5f * (float)(ca * C + min((cb + 1) * C, g.s[0]) - 1) * g.sd[0] + g.mn[0];
-                ++nr;
-            }
-            sh.nruns = n < 0 ? -1 : (nr <= 4 ? nr : -1);
-        }
+    {   // the cell lists of the block's x range, its two y ranges and its four z ranges: warps 0..5 copy one axis table each, warp 6 the runs
+        const unsigned char* ty = tables + sizeof(Splat3Runs) * gridDim.x;
+        const int* src = nullptr;
+        int* dst = nullptr;
+        int nw = 0;
+        if (warp < 2) src = reinterpret_cast<const int*>(ty + sizeof(Splat3Axis) * (2 * blockIdx.y + warp)), dst = reinterpret_cast<int*>(&sh.axis[warp]), nw = sizeof(Splat3Axis) / 4;
+        else if (warp < 6) src = reinterpret_cast<const int*>(ty + sizeof(Splat3Axis) * (2 * gridDim.y + 4 * blockIdx.z + warp - 2)), dst = reinterpret_cast<int*>(&sh.axis[warp]), nw = sizeof(Splat3Axis) / 4;
+        else if (warp == 6) src = reinterpret_cast<const int*>(tables + sizeof(Splat3Runs) * blockIdx.x), dst = reinterpret_cast<int*>(&sh.runs), nw = sizeof(Splat3Runs) / 4;
+        for (int i = lane; i < nw; i += 32) dst[i] = __ldg(src + i);
     }
     __syncthreads(); // the only block barrier: from here on the warps are independent
     Splat3Warp& W = sh.w[warp];
     const int t0x = (int)blockIdx.x * CT_X, t0y = (int)blockIdx.y * CT_Y + (warp & 1) * S3_Y, t0z = g.z0 + (int)blockIdx.z * CT_Z + (warp >> 1) * S3_Z;
     const int t1x = min(t0x + S3_X, g.s[0]) - 1, t1y = min(t0y + S3_Y, g.s[1]) - 1, t1z = min(t0z + S3_Z, g.z0 + g.nz) - 1;
     if (t1y < t0y || t1z < t0z) return;
-    const Splat3Axis& AY = sh.axis[1 + (warp & 1)];
-    const Splat3Axis& AZ = sh.axis[3 + (warp >> 1)];
-    const int nruns = sh.nruns;
+    const Splat3Axis& AY = sh.axis[warp & 1];
+    const Splat3Axis& AZ = sh.axis[2 + (warp >> 1)];
+    const int nruns = sh.runs.nruns;
+    const bool anyWrapped = st->pad[1] != 0u; // set by bin_count_kernel
     if (nruns < 0 || AY.n < 0 || AZ.n < 0) {
         if (lane == 0) st->pad[0] = 1u; // cannot happen when the host picked the cell size from the reach
         return;
@@ -658,12 +692,22 @@ __global__ void __launch_bounds__(CT_THREADS, 4) density_splat3_kernel(Geo g, Sp
     // a slack for the rounding of this test and the slop of the exact integer box, which follows in the digest).  On a periodic axis
     // the particle is first brought next to the voxels of its own cell (row / run centre +- half a period: robust against a home voxel
     // that the binning's exact division puts one cell further) and then moved to the image next to the sub-tile (the cell's shift).
-    const float lox = fmaf((float)t0x, g.sd[0], g.mn[0]) - kc.slack[0], hix = fmaf((float)t1x, g.sd[0], g.mn[0]) + kc.slack[0];
-    const float loy = fmaf((float)t0y, g.sd[1], g.mn[1]) - kc.slack[1], hiy = fmaf((float)t1y, g.sd[1], g.mn[1]) + kc.slack[1];
-    const float loz = fmaf((float)t0z, g.sd[2], g.mn[2]) - kc.slack[2], hiz = fmaf((float)t1z, g.sd[2], g.mn[2]) + kc.slack[2];
+    // With the cell's shift folded into the bounds the test of an in-box particle is p + eps >= lo - shift && p - eps <= hi - shift.
+    const int nay = AY.n, naz = AZ.n;
+    if (nay > S3_PRECELLS || naz > S3_PRECELLS) {
+        if (lane == 0) st->pad[0] = 1u; // cannot happen: 8 + 2*2 voxels touch at most four 4-voxel cells
+        return;
+    }
+    if (lane < 4 + 2 * S3_PRECELLS) {
+        const int a = lane < 4 ? 0 : (lane < 4 + S3_PRECELLS ? 1 : 2), i = lane < 4 ? lane : (lane < 4 + S3_PRECELLS ? lane - 4 : lane - 4 - S3_PRECELLS);
+        const int t0 = a == 0 ? t0x : (a == 1 ? t0y : t0z), t1 = a == 0 ? t1x : (a == 1 ? t1y : t1z);
+        const float shift = a == 0 ? sh.runs.runShift[i] : (a == 1 ? AY.shift[i] : AZ.shift[i]);
+        const float2 b = make_float2(fmaf((float)t0, g.sd[a], g.mn[a]) - kc.slack[a] - shift, fmaf((float)t1, g.sd[a], g.mn[a]) + kc.slack[a] - shift);
+        (a == 0 ? W.bx : (a == 1 ? W.by : W.bz))[i] = b;
+    }
+    __syncwarp();
     // Row descriptors: lane i owns (cell z, cell y, x run) number i of the sub-tile's neighbourhood, in summation order, and loads its
     // record range -- one round of table reads for all rows instead of one dependent read per row.
-    const int nay = AY.n, naz = AZ.n;
     const int nrows = naz * nay * nruns; // <= 4 * 4 * 4; in practice 12 .. 24
     for (int row0 = 0; row0 < nrows; row0 += 32) {
         unsigned myB = 0, myE = 0;
@@ -672,7 +716,7 @@ __global__ void __launch_bounds__(CT_THREADS, 4) density_splat3_kernel(Geo g, Sp
             const int i = row0 + lane;
             const int kr = i % nruns, t = i / nruns, ky = t % nay, kz = t / nay;
             const size_t rowBase = (static_cast<size_t>(AZ.cell[kz]) * g.nc[1] + AY.cell[ky]) * g.nc[0];
-            myB = cellStart[rowBase + sh.runA[kr]], myE = cellStart[rowBase + sh.runB[kr] + 1];
+            myB = cellStart[rowBase + sh.runs.runA[kr]], myE = cellStart[rowBase + sh.runs.runB[kr] + 1];
             myCode = kz | ky << 4 | kr << 8;
         }
         const unsigned nonEmpty = __ballot_sync(0xffffffffu, myE > myB);
@@ -703,10 +747,13 @@ __global__ void __launch_bounds__(CT_THREADS, 4) density_splat3_kernel(Geo g, Sp
             if (keep) {
                 const float eps = g.sigma * p.w;
                 float ux = p.x, uy = p.y, uz = p.z;
-                if (g.cyc[0]) ux = fmaf(-rintf((ux - sh.runMid[kr]) * kc.rper[0]), kc.per[0], ux) + sh.runShift[kr];
-                if (g.cyc[1]) uy = fmaf(-rintf((uy - AY.mid[ky]) * kc.rper[1]), kc.per[1], uy) + AY.shift[ky];
-                if (g.cyc[2]) uz = fmaf(-rintf((uz - AZ.mid[kz]) * kc.rper[2]), kc.per[2], uz) + AZ.shift[kz];
-                keep = ux + eps >= lox && ux - eps <= hix && uy + eps >= loy && uy - eps <= hiy && uz + eps >= loz && uz - eps <= hiz;
+                if (anyWrapped) { // some particle lies outside the box (binned through the periodic wrap): bring it next to its cell first
+                    if (g.cyc[0]) ux = fmaf(-rintf((ux - sh.runs.runMid[kr]) * kc.rper[0]), kc.per[0], ux);
+                    if (g.cyc[1]) uy = fmaf(-rintf((uy - AY.mid[ky]) * kc.rper[1]), kc.per[1], uy);
+                    if (g.cyc[2]) uz = fmaf(-rintf((uz - AZ.mid[kz]) * kc.rper[2]), kc.per[2], uz);
+                }
+                const float2 bx = W.bx[kr], by = W.by[ky], bz = W.bz[kz];
+                keep = ux + eps >= bx.x && ux - eps <= bx.y && uy + eps >= by.x && uy - eps <= by.y && uz + eps >= bz.x && uz - eps <= bz.y;
             }
             const unsigned bal = __ballot_sync(0xffffffffu, keep);
             if (keep) W.queue[(qTail + __popc(bal & ltMask)) & (S3_QCAP - 1)] = p;

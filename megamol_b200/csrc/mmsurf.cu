@@ -279,7 +279,10 @@ struct mms_ctx {
     unsigned haloFrame = 0;       // parity selects the counter word of the current frame
     PinBuf hRoute;
     DevBuf cellCount, cellStart, cursor, tileSums, recsA, recsB, auxA, auxB, vol, rgb, segCount, segOffset, meshPos, meshNrm,
-        meshCol, triCount, home, dstate, dirVol, rmaxBuf, bigCells;
+        meshCol, triCount, home, dstate, dirVol, rmaxBuf, bigCells, s3Tables;
+    Geo s3Geo{};          // density_splat3_kernel: the geometry its cell tables (s3Tables) were built for
+    int s3Reach = -1;
+    std::vector<unsigned char> s3Host;
     PinBuf hState, hVol, hRgb, hPos, hNrm, hCol, hHome, hTri, hDir;
     cudaEvent_t ev[EV_COUNT]{};
     bool evSet[EV_COUNT]{};
@@ -561,7 +564,7 @@ int mms_destroy(mms_ctx* c) {
         DeviceGuard guard(c->device);
         mms_clear_particles(c);
         for (DevBuf* b : {&c->cellCount, &c->cellStart, &c->cursor, &c->tileSums, &c->recsA, &c->recsB, &c->auxA, &c->auxB, &c->vol,
-                 &c->rgb, &c->segCount, &c->segOffset, &c->meshPos, &c->meshNrm, &c->meshCol, &c->triCount, &c->home, &c->dstate, &c->routeCounts, &c->routeOffsets, &c->routeTile, &c->rangeBuf, &c->dirVol, &c->rmaxBuf, &c->bigCells, &c->haloBuf, &c->haloCounters})
+                 &c->rgb, &c->segCount, &c->segOffset, &c->meshPos, &c->meshNrm, &c->meshCol, &c->triCount, &c->home, &c->dstate, &c->routeCounts, &c->routeOffsets, &c->routeTile, &c->rangeBuf, &c->dirVol, &c->rmaxBuf, &c->bigCells, &c->haloBuf, &c->haloCounters, &c->s3Tables})
             b->release();
         for (PinBuf* b : {&c->hState, &c->hVol, &c->hRgb, &c->hPos, &c->hNrm, &c->hCol, &c->hHome, &c->hTri, &c->hRoute, &c->hDir}) b->release();
         cudaStreamSynchronize(c->stream);
@@ -921,8 +924,17 @@ int mms_compute_density(mms_ctx* c) {
                 kc.rper[a] = 1.0f / kc.per[a];
                 kc.slack[a] = (0.05f + 1e-5f * static_cast<float>(g.s[a])) * g.sd[a];
             }
+            // per-block-coordinate cell lists: a function of the geometry alone -> built on the host, uploaded when the geometry changes
+            if (c->s3Reach != c->reach || std::memcmp(&c->s3Geo, &g, sizeof(Geo)) != 0 || !c->s3Tables.p) {
+                const size_t bytes = splat3TableBytes(grid.x, grid.y, grid.z);
+                if (!c->s3Tables.ensure(bytes)) return c->fail(MMS_ERR_NOMEM, "device allocation failed (splat tables)");
+                c->s3Host.assign(bytes, 0);
+                splat3BuildTables(g, c->reach, grid.x, grid.y, grid.z, c->s3Host.data());
+                MMS_CUDA(c, cudaMemcpyAsync(c->s3Tables.p, c->s3Host.data(), bytes, cudaMemcpyHostToDevice, st)); // pageable: staged before it returns
+                c->s3Geo = g, c->s3Reach = c->reach;
+            }
             density_splat3_kernel<<<grid, CT_THREADS, sizeof(Splat3Shared), st>>>(g, kc, c->dstate.as<DevState>(), c->recsB.as<float4>(),
-                c->cellStart.as<unsigned>(), c->vol.as<float>(), c->reach);
+                c->cellStart.as<unsigned>(), c->vol.as<float>(), c->reach, c->s3Tables.as<unsigned char>());
         }
         else if (g.mode == 0)
             density_splat_kernel<0><<<grid, CT_THREADS, sizeof(SplatShared), st>>>(g, c->dstate.as<DevState>(), c->recsB.as<float4>(),

@@ -28,6 +28,9 @@ CASES = [
     (20000, (40, 37, 33), 20.0, 0.6, 1.0, (True, True, True), 0.0),
     (20000, (64, 48, 50), 20.0, 1.3, 1.0, (False, True, False), 0.02),
     (50000, (96, 96, 96), 48.0, 0.5, 1.0, (True, True, True), 0.0),
+    # periodic, a quarter of the particles outside the box (binned through the wrap), on the warp-tile splat kernel (supports <= 3^3 voxels)
+    (30000, (64, 48, 40), 24.0, 0.45, 1.0, (True, True, True), 0.15),
+    (30000, (64, 48, 40), 24.0, 0.45, 1.0, (True, False, True), 0.15),
 ]
 
 
