@@ -1115,6 +1115,157 @@ __global__ void __launch_bounds__(GT_THREADS, 2) density_gather_kernel(Geo g, De
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// density_gauss_kernel: QuickSurf-Gaussian mode with the radial cut-off on a non-periodic grid (C3)
+// ---------------------------------------------------------------------------------------------------------------
+// A WARP owns an 8x4x8-voxel patch (a thread: a column of eight voxels in registers; eight patches make the 32x8x8 tile of a block, but
+// the warps never talk to each other: no block barrier, no shared candidate stage).  The warp streams, in ascending (cell z, cell y,
+// cell x) and canonical in-cell order, the records of every cell row its patch's neighbourhood touches -- the x cells of a row are one
+// contiguous record range --, 32 records per round: each lane turns its record into a candidate (cut-off^2, exponent scale, colour),
+// tests its sphere against the patch's box, and the warp then walks the surviving candidates of the round in record order (ballot
+// mask; candidate fields broadcast from a 1 KB per-warp stage).  With a cut-off of ~10 voxels nearly every lane of the warp lies inside
+// the circle of a candidate that reaches the patch at all.  A candidate that is skipped would have added an exact 0 to every voxel of
+// the patch, so every voxel receives its non-zero terms in the order (cell z, cell y, cell x, canonical in-cell order): the same
+// bits as density_gather_kernel's, for every tile and z-slab decomposition.  Distances and weights are rounded operation by operation
+// (the cut-off test d2 < lim decides whether a term exists: it must not depend on contraction); the colour sums use fused multiply-adds.
+struct GaussCand {          // 64 bytes
+    float x, y, z, k0;      // k0 = -log2e / (2 (r radscale)^2)
+    float lim, cr, cg, cb;  // lim = cut-off^2
+    float dz2[GT_Z];        // (z_k - z)^2 of the patch's eight planes: the same for every lane, computed once by the lane that stages the atom
+};
+constexpr int GP_X = 8, GP_Y = 4; // voxel columns of a warp's patch
+struct GaussShared {
+    GaussCand cand[GT_THREADS / 32][32];
+};
+
+template<bool COLOUR>
+__global__ void __launch_bounds__(GT_THREADS, 2) density_gauss_kernel(Geo g, DevState* st, const float4* __restrict__ recs,
+    const float* __restrict__ aux, int auxN, const unsigned* __restrict__ cellStart, float* __restrict__ vol, float* __restrict__ rgb,
+    int reach) {
+    __shared__ GaussShared sh;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int t0x = (int)blockIdx.x * GT_X, t0y = (int)blockIdx.y * GT_Y, t0z = g.z0 + (int)blockIdx.z * GT_Z;
+    const int t1x = min(t0x + GT_X, g.s[0]) - 1, t1y = min(t0y + GT_Y, g.s[1]) - 1, t1z = min(t0z + GT_Z, g.z0 + g.nz) - 1;
+    const int p0x = t0x + (warp & 3) * GP_X, p0y = t0y + (warp >> 2) * GP_Y;
+    const int p1x = min(p0x + GP_X - 1, t1x), p1y = min(p0y + GP_Y - 1, t1y);
+    if (p0x > t1x || p0y > t1y) return; // patch beyond the grid
+    GaussCand* stage = sh.cand[warp];
+
+    const int vxI = p0x + (lane & 7), vyI = p0y + (lane >> 3);
+    const float vx = __fadd_rn(__fmul_rn((float)vxI, g.sd[0]), g.mn[0]), vy = __fadd_rn(__fmul_rn((float)vyI, g.sd[1]), g.mn[1]);
+    float vz[GT_Z], acc[GT_Z], accR[GT_Z], accG[GT_Z], accB[GT_Z];
+#pragma unroll
+    for (int k = 0; k < GT_Z; ++k) {
+        vz[k] = __fadd_rn(__fmul_rn((float)(t0z + k), g.sd[2]), g.mn[2]);
+        acc[k] = 0.0f, accR[k] = 0.0f, accG[k] = 0.0f, accB[k] = 0.0f;
+    }
+    // the patch's box (node positions) for the sphere / box rejection
+    const float bx0 = __fadd_rn(__fmul_rn((float)p0x, g.sd[0]), g.mn[0]), bx1 = __fadd_rn(__fmul_rn((float)p1x, g.sd[0]), g.mn[0]);
+    const float by0 = __fadd_rn(__fmul_rn((float)p0y, g.sd[1]), g.mn[1]), by1 = __fadd_rn(__fmul_rn((float)p1y, g.sd[1]), g.mn[1]);
+    const float bz0 = vz[0], bz1 = __fadd_rn(__fmul_rn((float)t1z, g.sd[2]), g.mn[2]);
+
+    // cells whose particles can reach the patch (non-periodic: one contiguous range per axis)
+    const int cx0 = max(p0x - reach, 0) >> g.cshift, cx1 = min(p1x + reach, g.s[0] - 1) >> g.cshift;
+    const int cy0 = max(p0y - reach, 0) >> g.cshift, cy1 = min(p1y + reach, g.s[1] - 1) >> g.cshift;
+    const int cz0 = max(t0z - reach, 0) >> g.cshift, cz1 = min(t1z + reach, g.s[2] - 1) >> g.cshift;
+    const int nyc = cy1 - cy0 + 1, nrows = nyc * (cz1 - cz0 + 1);
+
+    for (int row0 = 0; row0 < nrows; row0 += 32) {
+        // lane i owns cell row number row0 + i (ascending cell z, then cell y) and loads its record range
+        unsigned myB = 0, myE = 0;
+        if (row0 + lane < nrows) {
+            const int i = row0 + lane, cz = cz0 + i / nyc, cy = cy0 + i % nyc;
+            const size_t rowBase = (static_cast<size_t>(cz) * g.nc[1] + cy) * g.nc[0];
+            myB = cellStart[rowBase + cx0], myE = cellStart[rowBase + cx1 + 1];
+        }
+        unsigned rest = __ballot_sync(0xffffffffu, myE > myB);
+        unsigned base = 0, end = 0;
+        auto nextChunk = [&]() { // -> false when the rows are exhausted
+            base += 32;
+            if (base >= end) {
+                if (!rest) return false;
+                const int r = __ffs(rest) - 1;
+                rest &= rest - 1;
+                base = __shfl_sync(0xffffffffu, myB, r), end = __shfl_sync(0xffffffffu, myE, r);
+            }
+            return true;
+        };
+        bool more = nextChunk();
+        float4 pNext = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (more && base + lane < end) pNext = recs[base + lane];
+        while (more) {
+            const float4 p = pNext;
+            const unsigned idx = base + lane;
+            const bool have = idx < end;
+            more = nextChunk(); // the records of the next round are requested before this one is worked on
+            if (more && base + lane < end) pNext = recs[base + lane];
+            bool rel = false;
+            if (have) {
+                const float sr = __fmul_rn(p.w, g.radscale);
+                const float eps = __fmul_rn(g.gausslim, sr);
+                const float lim = __fmul_rn(eps, eps);
+                // squared distance from the atom to the patch's box, 0.1 % slack for the rounding of this test (the exact test is per voxel)
+                const float gx = fmaxf(fmaxf(bx0 - p.x, p.x - bx1), 0.0f), gy = fmaxf(fmaxf(by0 - p.y, p.y - by1), 0.0f);
+                const float gz = fmaxf(fmaxf(bz0 - p.z, p.z - bz1), 0.0f);
+                rel = (gx * gx + gy * gy + gz * gz) * 0.999f < lim;
+                if (rel) { // a few per cent of the stream: only these pay for the division, the colour fetch and the stage
+                    float4 col = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
+                    if (COLOUR && auxN == 4) col = reinterpret_cast<const float4*>(aux)[idx];
+                    float4* sg = reinterpret_cast<float4*>(&stage[lane]);
+                    sg[0] = make_float4(p.x, p.y, p.z, __fdiv_rn(-1.4426950408889634f, __fmul_rn(__fmul_rn(2.0f, sr), sr)));
+                    sg[1] = make_float4(lim, col.x, col.y, col.z);
+                    float q[GT_Z];
+#pragma unroll
+                    for (int k = 0; k < GT_Z; ++k) {
+                        const float dz = __fsub_rn(vz[k], p.z);
+                        q[k] = __fmul_rn(dz, dz);
+                    }
+                    sg[2] = make_float4(q[0], q[1], q[2], q[3]);
+                    sg[3] = make_float4(q[4], q[5], q[6], q[7]);
+                }
+            }
+            unsigned bits = __ballot_sync(0xffffffffu, rel);
+            __syncwarp();
+            while (bits) {
+                const int j = __ffs(bits) - 1;
+                bits &= bits - 1;
+                const float4* sg = reinterpret_cast<const float4*>(&stage[j]);
+                const float4 A = sg[0], B = sg[1], Q0 = sg[2], Q1 = sg[3];
+                const float dz2[GT_Z] = {Q0.x, Q0.y, Q0.z, Q0.w, Q1.x, Q1.y, Q1.z, Q1.w};
+                const float dx = __fsub_rn(vx, A.x), dy = __fsub_rn(vy, A.y);
+                const float dxy2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+#pragma unroll
+                for (int k = 0; k < GT_Z; ++k) {
+                    const float d2 = __fadd_rn(dxy2, dz2[k]);
+                    // branch-free: outside the cut-off the weight is an exact 0, and x + 0 == x -- the same bits as skipping
+                    const float e = ex2Approx(__fmul_rn(d2, A.w));
+                    const float w = d2 < B.x ? e : 0.0f;
+                    acc[k] = __fadd_rn(acc[k], w);
+                    if (COLOUR) accR[k] = fmaf(w, B.y, accR[k]), accG[k] = fmaf(w, B.z, accG[k]), accB[k] = fmaf(w, B.w, accB[k]);
+                }
+            }
+            __syncwarp(); // the stage is rewritten in the next round
+        }
+    }
+    float vmin = INFINITY, vmax = -INFINITY;
+    if (vxI <= t1x && vyI <= t1y) {
+#pragma unroll
+        for (int k = 0; k < GT_Z; ++k) {
+            const int z = t0z + k;
+            if (z > t1z) break;
+            const size_t o = vxI + static_cast<size_t>(g.s[0]) * (vyI + static_cast<size_t>(g.s[1]) * (z - g.z0));
+            vol[o] = acc[k];
+            if (COLOUR) rgb[3 * o + 0] = accR[k], rgb[3 * o + 1] = accG[k], rgb[3 * o + 2] = accB[k];
+            vmin = fminf(vmin, acc[k]), vmax = fmaxf(vmax, acc[k]);
+        }
+    }
+    const unsigned kmin = __reduce_min_sync(0xffffffffu, floatKey(vmin)), kmax = __reduce_max_sync(0xffffffffu, floatKey(vmax));
+    if (lane == 0 && kmin <= kmax) {
+        atomicMin(&st->minKey, kmin);
+        atomicMax(&st->maxKey, kmax);
+    }
+}
+
 /**
  * Aggregator 2 (IVecToSingleCell_Volume), the per-voxel pass after the accumulation (ParticlesToDensity.cpp:634-657):
  *   v = sum(w d) / (sum(w) == 0 ? 1 : sum(w));  density = sqrt(vx vx + vy vy + vz vz);  direction = density == 0 ? 0 : v / density

@@ -904,7 +904,11 @@ int mms_compute_density(mms_ctx* c) {
 #define MMS_GATHER(M, COL, out) \
         (general ? density_gather_kernel<M, COL, true><<<grid, GT_THREADS, 0, st>>>(g, DS, R, A, auxN, CS, V, out, c->reach) \
                  : density_gather_kernel<M, COL, false><<<grid, GT_THREADS, 0, st>>>(g, DS, R, A, auxN, CS, V, out, c->reach))
-        if (vector) MMS_GATHER(0, true, C3);
+        // Gaussian mode, radial cut-off, no periodic axis (QuickSurf's own case): the warp-patch kernel
+        const bool gauss = g.mode == 1 && !general && !g.cyc[0] && !g.cyc[1] && !g.cyc[2] && !getenv("MMS_GATHER_GENERIC");
+        if (gauss && colour) density_gauss_kernel<true><<<grid, GT_THREADS, 0, st>>>(g, DS, R, A, auxN, CS, V, C3, c->reach);
+        else if (gauss) density_gauss_kernel<false><<<grid, GT_THREADS, 0, st>>>(g, DS, R, A, auxN, CS, V, nullptr, c->reach);
+        else if (vector) MMS_GATHER(0, true, C3);
         else if (g.mode == 0) MMS_GATHER(0, false, nullptr);
         else if (colour) MMS_GATHER(1, true, C3);
         else MMS_GATHER(1, false, nullptr);
