@@ -200,6 +200,15 @@ int mms_emit_isosurface(mms_ctx* ctx, float* pos, float* nrm, float* col, uint64
 /* Triangle soup: nverts = 3 * triangles; pos/nrm/col = 3 floats per vertex (col NULL unless colour mode). */
 int mms_get_mesh(mms_ctx* ctx, uint64_t* nverts, const float** pos, const float** nrm, const float** col);
 int mms_get_mesh_device(mms_ctx* ctx, uint64_t* nverts, const float** pos, const float** nrm, const float** col);
+/* Opt-in INDEXED mesh (the default stays the reference's unindexed soup): one vertex per crossed grid edge + three 32-bit indices
+ * per triangle, what CallTriMeshData::Mesh::SetVertexData + SetTriangleData(cnt, unsigned int*) carry
+ * (plugins/geometry_calls/include/geometry_calls/CallTriMeshData.h, plugins/mesh_gl/.../CallTriMeshDataGL.h:922-1000) -- about 28 bytes
+ * per triangle instead of 72.  Same triangles in the same order as the soup, and pos[idx[k]] / nrm[idx[k]] are bit for bit the soup's
+ * k-th vertex.  Marching cubes without colours on a whole-volume context (no z-slabs); mms_set_mesh_indexed invalidates a count.
+ * pos, nrm: 3 floats per vertex; idx: 3 indices per triangle.  The soup getters (mms_get_mesh*, mms_share_mesh) refuse an indexed mesh. */
+int mms_set_mesh_indexed(mms_ctx* ctx, int32_t on);
+int mms_get_mesh_indexed(mms_ctx* ctx, uint64_t* nverts, uint64_t* ntris, const float** pos, const float** nrm, const uint32_t** idx);
+int mms_get_mesh_indexed_device(mms_ctx* ctx, uint64_t* nverts, uint64_t* ntris, const float** pos, const float** nrm, const uint32_t** idx);
 
 /* Test hooks (host pointers). home: 3 int32 per particle, list-major input order. tricounts: one byte per
  * cell, x fastest, (res0-1)*(res1-1)*cell_nz entries. */

@@ -19,7 +19,7 @@ EXPORTS = ["mms_create", "mms_destroy", "mms_last_error", "mms_set_grid", "mms_s
            "mms_clear_particles", "mms_push_particles", "mms_push_particles_dir", "mms_get_vector_field", "mms_get_vector_field_device", "mms_get_max_radius", "mms_compute_density", "mms_get_density_range", "mms_normalize", "mms_density_range_device", "mms_normalize_device", "mms_set_stream",
            "mms_get_density", "mms_prefetch_density", "mms_get_density_device", "mms_set_density", "mms_adopt_density", "mms_extract_isosurface", "mms_set_isosurface_mode", "mms_count_isosurface", "mms_emit_isosurface", "mms_device_alloc",
            "mms_device_free", "mms_route_particles", "mms_halo_buffers", "mms_halo_push", "mms_halo_receive", "mms_slabs_create", "mms_slabs_destroy", "mms_slabs_last_error", "mms_slabs_count", "mms_slabs_context", "mms_slabs_set_grid", "mms_slabs_set_params", "mms_slabs_clear_particles", "mms_slabs_push_particles", "mms_slabs_compute_density", "mms_slabs_get_density_range", "mms_slabs_get_density", "mms_slabs_adopt_density", "mms_slabs_extract_isosurface", "mms_slabs_get_mesh", "mms_ipc_export", "mms_ipc_open", "mms_ipc_close", "mms_share_enable", "mms_share_density", "mms_share_mesh", "mms_share_open", "mms_share_close", "mms_get_mesh",
-           "mms_get_mesh_device", "mms_get_home_voxels", "mms_get_cell_tricounts", "mms_get_timings", "mms_synchronize",
+           "mms_get_mesh_device", "mms_set_mesh_indexed", "mms_get_mesh_indexed", "mms_get_mesh_indexed_device", "mms_get_home_voxels", "mms_get_cell_tricounts", "mms_get_timings", "mms_synchronize",
            "mms_timer_start", "mms_timer_stop", "mms_launch_count", "mms_alloc_pinned", "mms_free_pinned", "mms_version", "mms_mmpld_open", "mms_mmpld_close",
            "mms_mmpld_last_error", "mms_mmpld_info", "mms_mmpld_prefetch", "mms_mmpld_read_frame"]
 
@@ -139,6 +139,9 @@ def load_library():
     L.mms_share_close.argtypes = [C.c_int32, vp, sp]
     L.mms_get_mesh.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     L.mms_get_mesh_device.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    L.mms_set_mesh_indexed.argtypes = [vp, C.c_int32]
+    L.mms_get_mesh_indexed.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    L.mms_get_mesh_indexed_device.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     L.mms_get_home_voxels.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_uint64)]
     L.mms_get_cell_tricounts.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_uint64)]
     L.mms_get_timings.argtypes = [vp, C.POINTER(MmsTimings)]
@@ -427,6 +430,27 @@ class Surf:
             nrm = nrm.copy() if nrm is not None else None
             col = col.copy() if col is not None else None
         return (pos, nrm, col) if colours else (pos, nrm)
+
+    def set_mesh_indexed(self, on=True):
+        """opt-in indexed mesh (one vertex per crossed grid edge + 3 x uint32 per triangle) instead of the reference's triangle soup"""
+        self._chk(self.L.mms_set_mesh_indexed(self.h, int(bool(on))))
+
+    def get_mesh_indexed(self, copy=True):
+        """-> (pos [nv, 3] f32, nrm [nv, 3] f32, idx [nt, 3] u32); host arrays (views of the library's pinned buffers unless copy)"""
+        nv, nt = C.c_uint64(), C.c_uint64()
+        p, q, r = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self._chk(self.L.mms_get_mesh_indexed(self.h, C.byref(nv), C.byref(nt), C.byref(p), C.byref(q), C.byref(r)))
+        pos = _np_view(p.value, (nv.value, 3), np.float32)
+        nrm = _np_view(q.value, (nv.value, 3), np.float32)
+        idx = _np_view(r.value, (nt.value, 3), np.uint32)
+        return (pos.copy(), nrm.copy(), idx.copy()) if copy else (pos, nrm, idx)
+
+    def mesh_indexed_device(self):
+        """-> (nverts, ntris, pos, nrm, idx) device addresses"""
+        nv, nt = C.c_uint64(), C.c_uint64()
+        p, q, r = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self._chk(self.L.mms_get_mesh_indexed_device(self.h, C.byref(nv), C.byref(nt), C.byref(p), C.byref(q), C.byref(r)))
+        return nv.value, nt.value, p.value, q.value, r.value
 
     def mesh_device(self):
         n = C.c_uint64()

@@ -68,6 +68,7 @@ struct DevState {
     unsigned pad[2];     // [0] error flag of the density kernels, [1] some kept particle lies outside the grid on a periodic axis
     unsigned nBig;       // crowded cells (more than kBigCell records) found by cell_order_kernel ...
     unsigned bigNext;    // ... and the work counter of cell_sort_big_kernel
+    unsigned long long totalVerts; // indexed mesh: crossed grid edges = vertices (mcx_vertex_kernel + scan)
 };
 
 __device__ __forceinline__ unsigned floatKey(float f) {

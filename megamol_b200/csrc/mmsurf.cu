@@ -20,6 +20,7 @@
 #include "density.cuh"
 #include "mc.cuh"
 #include "mc_emit_v4.cuh" // TEMPORARY: A/B check of the new emit kernel (MMS_EMIT_V4=1)
+#include "mc_indexed.cuh"
 #include "mt.cuh"
 #include "route.cuh"
 
@@ -279,7 +280,10 @@ struct mms_ctx {
     unsigned haloFrame = 0;       // parity selects the counter word of the current frame
     PinBuf hRoute;
     DevBuf cellCount, cellStart, cursor, tileSums, recsA, recsB, auxA, auxB, vol, rgb, segCount, segOffset, meshPos, meshNrm,
-        meshCol, triCount, home, dstate, dirVol, rmaxBuf, bigCells, s3Tables;
+        meshCol, triCount, home, dstate, dirVol, rmaxBuf, bigCells, s3Tables, vertCount, vertOffset, meshIdx;
+    PinBuf hIdx;
+    bool meshIndexed = false, countIndexed = false; // mms_set_mesh_indexed: the mode in force / the mode the last count ran in
+    unsigned long long nverts = 0;                  // indexed mesh: vertices of the last count
     Geo s3Geo{};          // density_splat3_kernel: the geometry its cell tables (s3Tables) were built for
     int s3Reach = -1;
     std::vector<unsigned char> s3Host;
@@ -386,6 +390,7 @@ __global__ void init_state_kernel(DevState* st) {
     st->pad[1] = 0u;
     st->nBig = 0u;
     st->bigNext = 0u;
+    st->totalVerts = 0ull;
 }
 
 /** The state block goes to the host by a store into mapped pinned memory, not by a copy-engine transfer: a cudaMemcpyAsync would queue
@@ -564,9 +569,9 @@ int mms_destroy(mms_ctx* c) {
         DeviceGuard guard(c->device);
         mms_clear_particles(c);
         for (DevBuf* b : {&c->cellCount, &c->cellStart, &c->cursor, &c->tileSums, &c->recsA, &c->recsB, &c->auxA, &c->auxB, &c->vol,
-                 &c->rgb, &c->segCount, &c->segOffset, &c->meshPos, &c->meshNrm, &c->meshCol, &c->triCount, &c->home, &c->dstate, &c->routeCounts, &c->routeOffsets, &c->routeTile, &c->rangeBuf, &c->dirVol, &c->rmaxBuf, &c->bigCells, &c->haloBuf, &c->haloCounters, &c->s3Tables})
+                 &c->rgb, &c->segCount, &c->segOffset, &c->meshPos, &c->meshNrm, &c->meshCol, &c->triCount, &c->home, &c->dstate, &c->routeCounts, &c->routeOffsets, &c->routeTile, &c->rangeBuf, &c->dirVol, &c->rmaxBuf, &c->bigCells, &c->haloBuf, &c->haloCounters, &c->s3Tables, &c->vertCount, &c->vertOffset, &c->meshIdx})
             b->release();
-        for (PinBuf* b : {&c->hState, &c->hVol, &c->hRgb, &c->hPos, &c->hNrm, &c->hCol, &c->hHome, &c->hTri, &c->hRoute, &c->hDir}) b->release();
+        for (PinBuf* b : {&c->hState, &c->hVol, &c->hRgb, &c->hPos, &c->hNrm, &c->hCol, &c->hHome, &c->hTri, &c->hRoute, &c->hDir, &c->hIdx}) b->release();
         cudaStreamSynchronize(c->stream);
         cudaStreamSynchronize(c->copyStream);
         for (auto& a : c->arena) {
@@ -1254,6 +1259,25 @@ static int countLaunch(mms_ctx* c, float iso) {
     DevState* ds = c->dstate.as<DevState>();
     exclusiveScan(c->segCount.as<unsigned>(), c->segOffset.as<unsigned>(), nullptr, c->tileSums.as<unsigned>(), static_cast<unsigned>(nseg),
         &ds->totalTris, st, c->launches);
+    c->countIndexed = false;
+    if (c->meshIndexed) {
+        // indexed mesh: one vertex per crossed grid edge, numbered by node segment (mc_indexed.cuh)
+        if (c->isoMode != MMS_ISO_MARCHING_CUBES) return c->fail(MMS_ERR_UNSUPPORTED, "the indexed mesh is a marching-cubes output");
+        if (c->haveColour) return c->fail(MMS_ERR_UNSUPPORTED, "the indexed mesh has no colour output yet");
+        if (c->z0 != 0 || c->nz != c->grid.res[2] || m.cz0 != 0 || m.cnz != c->grid.res[2] - 1)
+            return c->fail(MMS_ERR_UNSUPPORTED, "the indexed mesh needs the whole volume in one context (vertex ids cross z-slab borders)");
+        const size_t nvs = static_cast<size_t>((m.sx + 31) / 32) * m.sy * m.szGlobal;
+        if (nvs >= (1ull << 32) - 1) return c->fail(MMS_ERR_UNSUPPORTED, "too many node segments");
+        const unsigned vtiles = static_cast<unsigned>((nvs + kScanTile - 1) / kScanTile);
+        if (!c->vertCount.ensure(nvs * 4) || !c->vertOffset.ensure((nvs + 1) * 4) || !c->tileSums.ensure(std::max<size_t>(std::max(ntiles, vtiles), 1) * 4))
+            return c->fail(MMS_ERR_NOMEM, "device allocation failed (vertex segments)");
+        dim3 gv((m.sx + 31) / 32, (m.sy + MCX_WARPS - 1) / MCX_WARPS, m.szGlobal);
+        mcx_vertex_kernel<false><<<gv, MCX_THREADS, 0, st>>>(m, c->isoVol(), c->vertCount.as<unsigned>(), nullptr, nullptr, nullptr);
+        ++c->launches;
+        exclusiveScan(c->vertCount.as<unsigned>(), c->vertOffset.as<unsigned>(), nullptr, c->tileSums.as<unsigned>(), static_cast<unsigned>(nvs),
+            &ds->totalVerts, st, c->launches);
+        c->countIndexed = true;
+    }
     publish_state_kernel<<<1, 1, 0, st>>>(c->dstate.as<DevState>(), c->hState.as<DevState>());
     ++c->launches;
     MMS_CUDA(c, cudaGetLastError());
@@ -1271,6 +1295,8 @@ static int countFinish(mms_ctx* c, uint64_t* ntris) {
     // the state block also carries the density kernels' error flag: a truncated volume must not become a mesh
     if (int rc = deviceErrorFromState(c)) return rc;
     c->ntris = c->hState.as<DevState>()->totalTris;
+    c->nverts = c->countIndexed ? c->hState.as<DevState>()->totalVerts : 0;
+    if (c->countIndexed && c->nverts >= (1ull << 32)) return c->fail(MMS_ERR_UNSUPPORTED, "more than 2^32 vertices do not fit 32-bit indices");
     c->haveCount = true;
     if (ntris) *ntris = c->ntris;
     return MMS_OK;
@@ -1289,6 +1315,28 @@ int mms_emit_isosurface(mms_ctx* c, float* pos, float* nrm, float* col, uint64_t
     const McGeo& m = c->mcGeo;
     cudaStream_t st = c->stream;
     const bool own = pos == nullptr;
+    if (c->countIndexed) {
+        if (!own) return c->fail(MMS_ERR_UNSUPPORTED, "the indexed mesh is emitted into the library's own buffers (mms_get_mesh_indexed*)");
+        if (c->ntris > 0) {
+            const size_t vbytes = static_cast<size_t>(c->nverts) * 12, ibytes = static_cast<size_t>(c->ntris) * 12;
+            auto grow = [&](DevBuf& b, size_t bytes) { return b.cap >= bytes || b.ensure(bytes + bytes / 8) || b.ensure(bytes); };
+            if (!grow(c->meshPos, vbytes) || !grow(c->meshNrm, vbytes) || !grow(c->meshIdx, ibytes))
+                return c->fail(MMS_ERR_NOMEM, "device allocation of the indexed mesh (%llu vertices, %llu triangles) failed", c->nverts, c->ntris);
+            c->rec(EV_EMIT0);
+            dim3 gv((m.sx + 31) / 32, (m.sy + MCX_WARPS - 1) / MCX_WARPS, m.szGlobal);
+            mcx_vertex_kernel<true><<<gv, MCX_THREADS, 0, st>>>(m, c->isoVol(), nullptr, c->vertOffset.as<unsigned>(), c->meshPos.as<float>(),
+                c->meshNrm.as<float>());
+            dim3 gi(m.nsegx, (m.cy + MCX_WARPS - 1) / MCX_WARPS, m.cnz);
+            mcx_index_kernel<<<gi, MCX_THREADS, 0, st>>>(m, c->isoVol(), c->segOffset.as<unsigned>(), c->vertOffset.as<unsigned>(),
+                c->meshIdx.as<unsigned>());
+            c->launches += 2;
+        }
+        c->rec(EV_MC1);
+        MMS_CUDA(c, cudaGetLastError());
+        c->haveMesh = true;
+        c->meshExternal = false;
+        return MMS_OK;
+    }
     if (c->ntris > 0) {
         float *P = pos, *N = nrm, *C = col;
         if (own) {
@@ -1360,9 +1408,53 @@ int mms_extract_isosurface(mms_ctx* c, float iso) {
     return mms_emit_isosurface(c, nullptr, nullptr, nullptr, 0);
 }
 
+int mms_set_mesh_indexed(mms_ctx* c, int32_t on) {
+    if (!c) return MMS_ERR_INVALID;
+    c->meshIndexed = on != 0;
+    c->haveMesh = c->haveCount = false; // a count made for the other format must not be emitted
+    return MMS_OK;
+}
+
+int mms_get_mesh_indexed_device(mms_ctx* c, uint64_t* nverts, uint64_t* ntris, const float** pos, const float** nrm, const uint32_t** idx) {
+    if (!c || !nverts || !ntris) return MMS_ERR_INVALID;
+    if (!c->haveMesh || !c->countIndexed) return c->fail(MMS_ERR_INVALID, "no indexed isosurface has been extracted (mms_set_mesh_indexed)");
+    *nverts = c->ntris ? c->nverts : 0, *ntris = c->ntris;
+    if (pos) *pos = c->ntris ? c->meshPos.as<float>() : nullptr;
+    if (nrm) *nrm = c->ntris ? c->meshNrm.as<float>() : nullptr;
+    if (idx) *idx = c->ntris ? c->meshIdx.as<uint32_t>() : nullptr;
+    return MMS_OK;
+}
+
+int mms_get_mesh_indexed(mms_ctx* c, uint64_t* nverts, uint64_t* ntris, const float** pos, const float** nrm, const uint32_t** idx) {
+    if (!c || !nverts || !ntris) return MMS_ERR_INVALID;
+    if (!c->haveMesh || !c->countIndexed) return c->fail(MMS_ERR_INVALID, "no indexed isosurface has been extracted (mms_set_mesh_indexed)");
+    DeviceGuard guard(c->device);
+    *nverts = c->ntris ? c->nverts : 0, *ntris = c->ntris;
+    if (pos) *pos = nullptr;
+    if (nrm) *nrm = nullptr;
+    if (idx) *idx = nullptr;
+    const size_t vbytes = static_cast<size_t>(*nverts) * 12, ibytes = static_cast<size_t>(c->ntris) * 12;
+    if (ibytes) {
+        auto growPin = [&](PinBuf& b, size_t bytes) { return b.cap >= bytes || b.ensure(bytes + bytes / 8) || b.ensure(bytes); };
+        if ((pos && !growPin(c->hPos, vbytes)) || (nrm && !growPin(c->hNrm, vbytes)) || (idx && !growPin(c->hIdx, ibytes)))
+            return c->fail(MMS_ERR_NOMEM, "pinned allocation of %zu bytes failed", vbytes + vbytes + ibytes);
+        c->rec(EV_DM0);
+        if (pos) MMS_CUDA(c, cudaMemcpyAsync(c->hPos.p, c->meshPos.p, vbytes, cudaMemcpyDeviceToHost, c->stream));
+        if (nrm) MMS_CUDA(c, cudaMemcpyAsync(c->hNrm.p, c->meshNrm.p, vbytes, cudaMemcpyDeviceToHost, c->stream));
+        if (idx) MMS_CUDA(c, cudaMemcpyAsync(c->hIdx.p, c->meshIdx.p, ibytes, cudaMemcpyDeviceToHost, c->stream));
+        c->rec(EV_DM1);
+        MMS_CUDA(c, cudaStreamSynchronize(c->stream));
+        if (pos) *pos = c->hPos.as<float>();
+        if (nrm) *nrm = c->hNrm.as<float>();
+        if (idx) *idx = c->hIdx.as<uint32_t>();
+    }
+    return MMS_OK;
+}
+
 int mms_get_mesh_device(mms_ctx* c, uint64_t* nverts, const float** pos, const float** nrm, const float** col) {
     if (!c || !nverts) return MMS_ERR_INVALID;
     if (!c->haveMesh) return c->fail(MMS_ERR_INVALID, "no isosurface has been extracted");
+    if (c->countIndexed) return c->fail(MMS_ERR_INVALID, "the mesh is indexed: use mms_get_mesh_indexed_device");
     if (c->meshExternal) return c->fail(MMS_ERR_INVALID, "the mesh was emitted into caller-supplied memory");
     *nverts = c->ntris * 3;
     if (pos) *pos = c->ntris ? c->meshPos.as<float>() : nullptr;
@@ -1374,6 +1466,7 @@ int mms_get_mesh_device(mms_ctx* c, uint64_t* nverts, const float** pos, const f
 int mms_get_mesh(mms_ctx* c, uint64_t* nverts, const float** pos, const float** nrm, const float** col) {
     if (!c || !nverts) return MMS_ERR_INVALID;
     if (!c->haveMesh) return c->fail(MMS_ERR_INVALID, "no isosurface has been extracted");
+    if (c->countIndexed) return c->fail(MMS_ERR_INVALID, "the mesh is indexed: use mms_get_mesh_indexed");
     if (c->meshExternal) return c->fail(MMS_ERR_INVALID, "the mesh was emitted into caller-supplied memory");
     DeviceGuard guard(c->device);
     const size_t bytes = static_cast<size_t>(c->ntris) * 36;
@@ -1692,6 +1785,7 @@ int mms_share_density(mms_ctx* c, mms_share* vol, mms_share* rgb) {
 int mms_share_mesh(mms_ctx* c, uint64_t* nverts, mms_share* pos, mms_share* nrm, mms_share* col) {
     if (!c || !nverts) return MMS_ERR_INVALID;
     if (!c->haveMesh || c->meshExternal) return c->fail(MMS_ERR_INVALID, "no isosurface has been extracted into library memory");
+    if (c->countIndexed) return c->fail(MMS_ERR_UNSUPPORTED, "mms_share_mesh shares the triangle soup; the indexed mesh is read with mms_get_mesh_indexed_device");
     DeviceGuard guard(c->device);
     MMS_CUDA(c, cudaStreamSynchronize(c->stream));
     *nverts = c->ntris * 3;

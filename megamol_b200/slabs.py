@@ -157,6 +157,9 @@ class SlabJob:
             self.origin = tuple(float(v) for v in org)
             pad_ext = ext + 1.0
             self.box = tuple(float(v) for v in pad_ext)
+            # useful (voxel, atom) pairs, SURVEY 8d: sum over the atoms of (4/3) pi (cut-off / voxel size)^3, cut-off = gausslim * radscale * r
+            h = np.asarray(pad_ext, np.float64) / (np.asarray(res, np.float64) - 1.0)
+            self.gauss_pairs = float(np.sum((4.0 / 3.0) * np.pi * (3.0 * data[:, 3].astype(np.float64)) ** 3) / float(np.prod(h)))
         elif w["kind"] == "lj" and w.get("fixed_total"):
             # strong-scaling configuration (BASELINE configs[3]): the frame is fixed, the ranks share it
             Lc = int(w["lattice"])
@@ -538,6 +541,21 @@ class SlabJob:
                         self._hwin[:n].copy_(flat[o:o + n], non_blocking=True)
             torch.cuda.current_stream().synchronize()
 
+    def step_e2e_indexed(self):
+        """single GPU, host buffers, the opt-in INDEXED mesh (one vertex per crossed edge + 3 x uint32 per triangle): pinned H2D of the
+        particles, D2H of the volume and of the indexed mesh.  Returns the D2H bytes of the step."""
+        assert self.world == 1 and not self.protein
+        s = self.surf
+        s.set_mesh_indexed(True)
+        try:
+            self._compute(self.h_xyz.data_ptr(), self.n_local, prefetch=True)
+            s.get_density(copy=False)
+            vpos, _, idx = s.get_mesh_indexed(copy=False)
+        finally:
+            s.set_mesh_indexed(False)
+        self.last["indexed"] = (int(vpos.shape[0]), int(idx.shape[0]))
+        return self.res[0] * self.res[1] * self.res[2] * 4 + vpos.shape[0] * 24 + idx.shape[0] * 12
+
     # ---- accounting -------------------------------------------------------------------------------------------
     def launches(self):
         return self.surf.launch_count()
@@ -583,7 +601,7 @@ class SlabJob:
     def roofline(self, stage, peak):
         """Roofline of the dominant KERNEL: algorithmic bytes of one launch / its CUDA-event time (library stream)."""
         b = self._local_alg_bytes()
-        dens = "density_gather_kernel" if self.protein else "density_splat_kernel"
+        dens = "density_gauss_kernel" if self.protein else "density_splat_kernel"
         # mc_emit: reads the density once more, writes the mesh; mc_count reads the density once
         emit_bytes = b["mc"]
         cand = {dens: (stage["density"], b["density"]), "mc_emit_kernel": (stage.get("mc_emit", 0.0), emit_bytes)}
@@ -603,9 +621,22 @@ class SlabJob:
             pass
         stages = {"bin (count+scan+scatter+order)": (stage["bin"], b["bin"]), dens: (stage["density"], b["density"]),
                   "marching cubes (count+scan+emit)": (stage["mc"], b["mc"] + b["v"] * 4)}
+        per_stage = {k: (v[1] / (v[0] * 1e-3) / 1e9 / peak if v[0] > 0 else None) for k, v in stages.items()}
+        if self.protein and name == dens:
+            # The Gaussian density kernel is arithmetic-bound, not HBM-bound: per useful (voxel, atom) pair 3 sub + 3 FMA-class
+            # for d^2, 1 compare, 1 mul + 1 ex2, 1 add, 3 FMA with colour = 13 FP32-pipe operations (19 flops, FMA = 2) and ONE SFU operation.
+            # Peaks are nominal: 148 SMs x 128 FP32 lanes (x 2 flops per FMA) and 148 x 16 SFU lanes at the 1.965 GHz the bench runs at.
+            pairs = getattr(self, "gauss_pairs", 0.0)
+            fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12
+            tf = pairs * 19 / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
+            sfu = pairs / (ms * 1e-3) / (148 * 16 * 1.965e9) if ms > 0 else 0.0
+            return {"bound": "fp32", "kernel": name, "achieved": tf, "peak": fp32_peak, "unit": "TFLOP/s", "frac": tf / fp32_peak, "traffic": None,
+                    "peak_source": "nominal FP32 FMA peak (148 SMs x 128 lanes x 2 x 1.965 GHz); MEASURED_PEAKS.json holds no FP32 figure",
+                    "algorithmic_flops": pairs * 19, "useful_pairs": pairs, "fp32_ops_per_pair": 13, "flops_per_pair": 19,
+                    "issue_slot_frac": pairs * 13 / (ms * 1e-3) / (148 * 128 * 1.965e9) if ms > 0 else 0.0,
+                    "sfu_frac": sfu, "hbm_frac": ach / peak, "algorithmic_bytes": by, "ms": ms, "per_stage_frac": per_stage}
         return {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
-                "algorithmic_bytes": by, "ms": ms,
-                "per_stage_frac": {k: (v[1] / (v[0] * 1e-3) / 1e9 / peak if v[0] > 0 else None) for k, v in stages.items()}}
+                "algorithmic_bytes": by, "ms": ms, "per_stage_frac": per_stage}
 
     def h2d_bytes(self):
         return self.n_local * (32 if self.protein else 12) * self.world
