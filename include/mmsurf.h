@@ -202,7 +202,7 @@ int mms_get_mesh(mms_ctx* ctx, uint64_t* nverts, const float** pos, const float*
 int mms_get_mesh_device(mms_ctx* ctx, uint64_t* nverts, const float** pos, const float** nrm, const float** col);
 /* Opt-in INDEXED mesh (the default stays the reference's unindexed soup): one vertex per crossed grid edge + three 32-bit indices
  * per triangle, what CallTriMeshData::Mesh::SetVertexData + SetTriangleData(cnt, unsigned int*) carry
- * (plugins/geometry_calls/include/geometry_calls/CallTriMeshData.h, plugins/mesh_gl/.../CallTriMeshDataGL.h:922-1000) -- about 28 bytes
+ * (plugins/geometry_calls_gl/include/geometry_calls_gl/CallTriMeshDataGL.h:897-1000) -- about 28 bytes
  * per triangle instead of 72.  Same triangles in the same order as the soup, and pos[idx[k]] / nrm[idx[k]] are bit for bit the soup's
  * k-th vertex.  Marching cubes without colours on a whole-volume context (no z-slabs); mms_set_mesh_indexed invalidates a count.
  * pos, nrm: 3 floats per vertex; idx: 3 indices per triangle.  The soup getters (mms_get_mesh*, mms_share_mesh) refuse an indexed mesh. */

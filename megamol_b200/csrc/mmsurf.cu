@@ -280,7 +280,7 @@ struct mms_ctx {
     unsigned haloFrame = 0;       // parity selects the counter word of the current frame
     PinBuf hRoute;
     DevBuf cellCount, cellStart, cursor, tileSums, recsA, recsB, auxA, auxB, vol, rgb, segCount, segOffset, meshPos, meshNrm,
-        meshCol, triCount, home, dstate, dirVol, rmaxBuf, bigCells, s3Tables, vertCount, vertOffset, meshIdx;
+        meshCol, triCount, home, dstate, dirVol, rmaxBuf, bigCells, s3Tables, vertCount, vertOffset, vertRec, meshIdx;
     PinBuf hIdx;
     bool meshIndexed = false, countIndexed = false; // mms_set_mesh_indexed: the mode in force / the mode the last count ran in
     unsigned long long nverts = 0;                  // indexed mesh: vertices of the last count
@@ -569,7 +569,7 @@ int mms_destroy(mms_ctx* c) {
         DeviceGuard guard(c->device);
         mms_clear_particles(c);
         for (DevBuf* b : {&c->cellCount, &c->cellStart, &c->cursor, &c->tileSums, &c->recsA, &c->recsB, &c->auxA, &c->auxB, &c->vol,
-                 &c->rgb, &c->segCount, &c->segOffset, &c->meshPos, &c->meshNrm, &c->meshCol, &c->triCount, &c->home, &c->dstate, &c->routeCounts, &c->routeOffsets, &c->routeTile, &c->rangeBuf, &c->dirVol, &c->rmaxBuf, &c->bigCells, &c->haloBuf, &c->haloCounters, &c->s3Tables, &c->vertCount, &c->vertOffset, &c->meshIdx})
+                 &c->rgb, &c->segCount, &c->segOffset, &c->meshPos, &c->meshNrm, &c->meshCol, &c->triCount, &c->home, &c->dstate, &c->routeCounts, &c->routeOffsets, &c->routeTile, &c->rangeBuf, &c->dirVol, &c->rmaxBuf, &c->bigCells, &c->haloBuf, &c->haloCounters, &c->s3Tables, &c->vertCount, &c->vertOffset, &c->vertRec, &c->meshIdx})
             b->release();
         for (PinBuf* b : {&c->hState, &c->hVol, &c->hRgb, &c->hPos, &c->hNrm, &c->hCol, &c->hHome, &c->hTri, &c->hRoute, &c->hDir, &c->hIdx}) b->release();
         cudaStreamSynchronize(c->stream);
@@ -1269,10 +1269,10 @@ static int countLaunch(mms_ctx* c, float iso) {
         const size_t nvs = static_cast<size_t>((m.sx + 31) / 32) * m.sy * m.szGlobal;
         if (nvs >= (1ull << 32) - 1) return c->fail(MMS_ERR_UNSUPPORTED, "too many node segments");
         const unsigned vtiles = static_cast<unsigned>((nvs + kScanTile - 1) / kScanTile);
-        if (!c->vertCount.ensure(nvs * 4) || !c->vertOffset.ensure((nvs + 1) * 4) || !c->tileSums.ensure(std::max<size_t>(std::max(ntiles, vtiles), 1) * 4))
+        if (!c->vertCount.ensure(nvs * 4) || !c->vertOffset.ensure((nvs + 1) * 4) || !c->vertRec.ensure(nvs * 16) || !c->tileSums.ensure(std::max<size_t>(std::max(ntiles, vtiles), 1) * 4))
             return c->fail(MMS_ERR_NOMEM, "device allocation failed (vertex segments)");
         dim3 gv((m.sx + 31) / 32, (m.sy + MCX_WARPS - 1) / MCX_WARPS, m.szGlobal);
-        mcx_vertex_kernel<false><<<gv, MCX_THREADS, 0, st>>>(m, c->isoVol(), c->vertCount.as<unsigned>(), nullptr, nullptr, nullptr);
+        mcx_mask_kernel<<<gv, MCX_THREADS, 0, st>>>(m, c->isoVol(), c->vertRec.as<uint4>(), c->vertCount.as<unsigned>());
         ++c->launches;
         exclusiveScan(c->vertCount.as<unsigned>(), c->vertOffset.as<unsigned>(), nullptr, c->tileSums.as<unsigned>(), static_cast<unsigned>(nvs),
             &ds->totalVerts, st, c->launches);
@@ -1324,10 +1324,10 @@ int mms_emit_isosurface(mms_ctx* c, float* pos, float* nrm, float* col, uint64_t
                 return c->fail(MMS_ERR_NOMEM, "device allocation of the indexed mesh (%llu vertices, %llu triangles) failed", c->nverts, c->ntris);
             c->rec(EV_EMIT0);
             dim3 gv((m.sx + 31) / 32, (m.sy + MCX_WARPS - 1) / MCX_WARPS, m.szGlobal);
-            mcx_vertex_kernel<true><<<gv, MCX_THREADS, 0, st>>>(m, c->isoVol(), nullptr, c->vertOffset.as<unsigned>(), c->meshPos.as<float>(),
+            mcx_vertex_kernel<<<gv, MCX_THREADS, 0, st>>>(m, c->isoVol(), c->vertRec.as<uint4>(), c->vertOffset.as<unsigned>(), c->meshPos.as<float>(),
                 c->meshNrm.as<float>());
             dim3 gi(m.nsegx, (m.cy + MCX_WARPS - 1) / MCX_WARPS, m.cnz);
-            mcx_index_kernel<<<gi, MCX_THREADS, 0, st>>>(m, c->isoVol(), c->segOffset.as<unsigned>(), c->vertOffset.as<unsigned>(),
+            mcx_index_kernel<<<gi, MCX_THREADS, 0, st>>>(m, c->vertRec.as<uint4>(), c->segOffset.as<unsigned>(), c->vertOffset.as<unsigned>(),
                 c->meshIdx.as<unsigned>());
             c->launches += 2;
         }

@@ -53,6 +53,8 @@ class Harness:
         L.mmh_pull_mesh.argtypes = [C.c_void_p, C.c_uint, C.c_float, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
                                     C.POINTER(C.c_double)]
         L.mmh_copy_mesh.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        if hasattr(L, "mmh_copy_indices"):
+            L.mmh_copy_indices.argtypes = [C.c_void_p, C.c_void_p]
         L.mmh_pull_mesh2.argtypes = L.mmh_pull_mesh.argtypes
         L.mmh_select_mesh.argtypes = [C.c_void_p, C.c_int]
         L.mmh_mc_tables.argtypes = [C.c_void_p] * 5
@@ -244,6 +246,12 @@ class Harness:
             if rc:
                 raise RuntimeError(f"mmh_copy_mesh rc={rc}")
             res.update(pos=pos, nrm=nrm, col=col)
+        if copy and nt.value:  # an indexed mesh (the reference's own IsoSurface hands out 0 triangles: an unindexed soup)
+            idx = np.empty((nt.value, 3), np.uint32)
+            rc = self.lib.mmh_copy_indices(self.h, idx.ctypes.data)
+            if rc:
+                raise RuntimeError(f"mmh_copy_indices rc={rc}")
+            res.update(idx=idx)
         return res
 
     def share_density(self):

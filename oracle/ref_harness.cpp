@@ -546,6 +546,18 @@ int mmh_copy_mesh(void* hv, float* pos, float* nrm, float* col) {
     return 0;
 }
 
+/** Triangle indices of the last pulled mesh (3 x uint32 per triangle; an unindexed soup has 0 triangles, IsoSurface.cpp:171-181). */
+int mmh_copy_indices(void* hv, unsigned* idx) {
+    auto* h = static_cast<Harness*>(hv);
+    if (!h->mesh) return -1;
+    using Mesh = geocalls_gl::CallTriMeshDataGL::Mesh;
+    const size_t n = h->mesh->GetTriCount();
+    if (n == 0) return 0;
+    if (h->mesh->GetTriDataType() != Mesh::DT_UINT32) return -2;
+    std::memcpy(idx, h->mesh->GetTriIndexPointerUInt32(), n * 3 * sizeof(unsigned));
+    return 0;
+}
+
 #ifdef MMH_B200
 /** Device-resident hand-off of the B200 modules: out[0..4] = volume share {fd, alloc_bytes, offset, bytes, MemLoc of the metadata}. */
 int mmh_share_density(void* hv, int64_t out[5]) {

@@ -37,7 +37,9 @@ IsoSurfaceB200::IsoSurfaceB200()
         , deviceSlot("device", "CUDA device ordinal used for volumes that are not already device resident")
         , algorithmSlot("algorithm", "Triangulation: marching cubes (smooth normals, node-centred frame) or the CPU module's marching "
                                      "tetrahedra reproduced triangle for triangle")
-        , deviceMeshSlot("deviceMesh", "Leave the mesh in importable device memory (ShareMesh()); CallTriMeshData then carries no object") {
+        , deviceMeshSlot("deviceMesh", "Leave the mesh in importable device memory (ShareMesh()); CallTriMeshData then carries no object")
+        , indexedMeshSlot("indexedMesh", "Hand out an indexed mesh (one vertex per crossed grid edge + 32-bit triangle indices) instead of the "
+                                         "reference's unindexed triangle soup; marching cubes on a single device only") {
 
     this->inDataSlot.SetCompatibleCall<geocalls::VolumetricDataCallDescription>();
     this->MakeSlotAvailable(&this->inDataSlot);
@@ -63,6 +65,9 @@ IsoSurfaceB200::IsoSurfaceB200()
 
     this->deviceMeshSlot << new core::param::BoolParam(false);
     this->MakeSlotAvailable(&this->deviceMeshSlot);
+
+    this->indexedMeshSlot << new core::param::BoolParam(false);
+    this->MakeSlotAvailable(&this->indexedMeshSlot);
 }
 
 IsoSurfaceB200::~IsoSurfaceB200() {
@@ -117,6 +122,10 @@ bool IsoSurfaceB200::buildMesh(VolumetricDataCall* cvd, float iso) {
         auto* p2d = dynamic_cast<const ParticlesToDensityB200*>(parent.get());
         if (p2d != nullptr && p2d->Group() != nullptr && this->deviceMeshSlot.Param<core::param::BoolParam>()->Value()) {
             Log::DefaultLog.WriteError("IsoSurfaceB200: 'deviceMesh' hands out ONE device allocation; it cannot follow a multi-device producer");
+            return false;
+        }
+        if (p2d != nullptr && p2d->Group() != nullptr && this->indexedMeshSlot.Param<core::param::BoolParam>()->Value()) {
+            Log::DefaultLog.WriteError("IsoSurfaceB200: 'indexedMesh' needs the whole volume on one device (vertex ids cross z-slab borders)");
             return false;
         }
         if (p2d != nullptr && p2d->Group() != nullptr && p2d->VolumeHash() == cvd->DataHash() && algorithm == MMS_ISO_MARCHING_CUBES) {
@@ -203,6 +212,33 @@ bool IsoSurfaceB200::buildMesh(VolumetricDataCall* cvd, float iso) {
     }
     uint64_t nverts = 0;
     const float *pos = nullptr, *nrm = nullptr, *col = nullptr; // col stays NULL unless the volume carries colours (QuickSurf mode)
+    const bool indexed = this->indexedMeshSlot.Param<core::param::BoolParam>()->Value();
+    if (mms_set_mesh_indexed(use, indexed ? 1 : 0) != MMS_OK) {
+        Log::DefaultLog.WriteError("IsoSurfaceB200: %s", mms_last_error(use));
+        return false;
+    }
+    if (indexed) {
+        // opt-in: CallTriMeshData's indexed form (Mesh::SetVertexData + SetTriangleData(cnt, unsigned int*), CallTriMeshDataGL.h:897-1000)
+        uint64_t ntris = 0;
+        const uint32_t* idx = nullptr;
+        if (this->meshOnDevice) {
+            Log::DefaultLog.WriteError("IsoSurfaceB200: 'indexedMesh' and 'deviceMesh' cannot be combined (ShareMesh() shares the triangle soup)");
+            return false;
+        }
+        if (mms_set_isosurface_mode(use, algorithm) != MMS_OK || mms_extract_isosurface(use, iso) != MMS_OK ||
+            mms_get_mesh_indexed(use, &nverts, &ntris, &pos, &nrm, &idx) != MMS_OK) {
+            Log::DefaultLog.WriteError("IsoSurfaceB200: %s", mms_last_error(use));
+            return false;
+        }
+        this->mesh.SetMaterial(nullptr);
+        this->mesh.SetVertexData(static_cast<unsigned int>(nverts), const_cast<float*>(pos), const_cast<float*>(nrm), static_cast<float*>(nullptr),
+            static_cast<float*>(nullptr), false);
+        this->mesh.SetTriangleData(static_cast<unsigned int>(ntris), const_cast<unsigned int*>(idx), false);
+        const std::chrono::duration<float, std::milli> msi = std::chrono::high_resolution_clock::now() - t0;
+        Log::DefaultLog.WriteInfo("IsoSurfaceB200: %llu triangles on %llu vertices (indexed) at iso %f took %f ms.", static_cast<unsigned long long>(ntris),
+            static_cast<unsigned long long>(nverts), iso, msi.count());
+        return true;
+    }
     if (mms_set_isosurface_mode(use, algorithm) != MMS_OK || mms_extract_isosurface(use, iso) != MMS_OK ||
         (!this->meshOnDevice && mms_get_mesh(use, &nverts, &pos, &nrm, &col) != MMS_OK)) {
         Log::DefaultLog.WriteError("IsoSurfaceB200: %s", mms_last_error(use));
@@ -251,6 +287,10 @@ bool IsoSurfaceB200::outDataCallback(core::Call& caller) {
         }
         if (this->deviceMeshSlot.IsDirty()) {
             this->deviceMeshSlot.ResetDirty();
+            recalc = true;
+        }
+        if (this->indexedMeshSlot.IsDirty()) {
+            this->indexedMeshSlot.ResetDirty();
             recalc = true;
         }
         cvd->SetFrameID(tmd->FrameID(), tmd->IsFrameForced());

@@ -2,7 +2,9 @@
  * IsoSurfaceB200.h -- drop-in for trisoup_gl::volumetrics::IsoSurface (plugins/trisoup_gl/src/volumetrics/IsoSurface.h):
  * slots inData (VolumetricDataCall) / outData ("CallTriMeshData": GetData, GetExtent), parameters attr, isoval.
  * Marching cubes with the classic table instead of marching tetrahedra, smooth normals; the mesh contract is the
- * reference's: one Mesh, unindexed triangle soup, float positions + float normals.
+ * reference's: one Mesh, unindexed triangle soup, float positions + float normals.  'indexedMesh' (off by default) switches to the
+ * indexed form the call carries as well (SetVertexData with one vertex per crossed grid edge + SetTriangleData with 32-bit indices):
+ * the same triangles in the same order, 28 instead of 72 bytes per triangle.
  */
 #pragma once
 #include <vector>
@@ -52,7 +54,7 @@ private:
 
     core::CallerSlot inDataSlot;
     core::CalleeSlot outDataSlot;
-    core::param::ParamSlot attributeSlot, isoValueSlot, deviceSlot, algorithmSlot, deviceMeshSlot;
+    core::param::ParamSlot attributeSlot, isoValueSlot, deviceSlot, algorithmSlot, deviceMeshSlot, indexedMeshSlot;
     bool meshOnDevice = false;
 
     mms_ctx* ctx = nullptr; // own context, used when the volume comes from a foreign (host) source

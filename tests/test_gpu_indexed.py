@@ -1,5 +1,5 @@
 """GPU: the opt-in INDEXED marching-cubes mesh (mms_set_mesh_indexed; CallTriMeshData's SetVertexData + SetTriangleData(uint32) form,
-plugins/geometry_calls/include/geometry_calls/CallTriMeshData.h) against the default triangle soup, which is itself pinned to the oracle
+plugins/geometry_calls_gl/include/geometry_calls_gl/CallTriMeshDataGL.h:897-1000) against the default triangle soup, which is itself pinned to the oracle
 (tests/test_gpu_parity.py, test_gpu_fullsize.py):
 
   * expanding the indices reproduces the soup BIT FOR BIT (positions and normals, triangle for triangle)

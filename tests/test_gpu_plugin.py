@@ -105,6 +105,29 @@ def test_mesh_call_contract(ref, plug, oracle):
     assert m3["nverts"] != m["nverts"]
 
 
+def test_indexed_mesh_parameter(plug):
+    """IsoSurfaceB200 'indexedMesh': CallTriMeshData's indexed form (SetVertexData + SetTriangleData with 32-bit indices); expanding the
+    indices gives the module's default soup bit for bit, and switching back restores the reference's contract (0 triangles)."""
+    n, box, res = 6000, 10.0, (40, 28, 24)
+    xyz = synth.uniform_box(n, box, seed=13)
+    lists = [dict(vtx=xyz, vtx_type=rb.VERT_FLOAT_XYZ, count=n, global_radius=0.9)]
+    feed(plug, lists, (0, 0, 0, box, box, box), res, cyclic=(False,) * 3, normalize=True)
+    plug.pull_volume()
+    soup = plug.pull_mesh(0.4)
+    assert soup["ntris"] == 0 and soup["nverts"] > 3000
+    plug.set_param(1, "indexedMesh", 1)
+    try:
+        m = plug.pull_mesh(0.4)
+        assert m["ntris"] * 3 == soup["nverts"] and 0 < m["nverts"] < soup["nverts"] // 3
+        assert int(m["idx"].max()) < m["nverts"]
+        assert np.array_equal(m["pos"][m["idx"].reshape(-1)].view(np.uint32), soup["pos"].view(np.uint32))
+        assert np.array_equal(m["nrm"][m["idx"].reshape(-1)].view(np.uint32), soup["nrm"].view(np.uint32))
+    finally:
+        plug.set_param(1, "indexedMesh", 0)
+    back = plug.pull_mesh(0.4)
+    assert back["ntris"] == 0 and np.array_equal(back["pos"], soup["pos"])
+
+
 def test_two_isosurface_modules_share_one_density_module(plug):
     """Two IsoSurfaceB200 behind one ParticlesToDensityB200 (different iso values): each keeps its mesh in its own context
     (mms_adopt_density takes only the device volume from the producer).  The mesh module 0 handed out stays intact -- its pointers are
