@@ -490,11 +490,16 @@ def main():
                          "no host synchronisation) or nccl (round-1 baseline: routing kernels + count matrix + all-to-all-v)")
     ap.add_argument("--no-c4", action="store_true", help="N > 1: skip the C4 (100 M particles -> 1024^3, strong scaling) figures in the record")
     ap.add_argument("--tmpdir", default="/tmp")
+    ap.add_argument("--radius", type=float, default=None, help="particle radius of the LJ workloads (default 0.5; SURVEY's C2 variant: 1.0, a 5^3 support)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.workload == "c5" and args.impl == "ours":
         return run_c5(args)
     w = workload("c2" if args.workload == "c5" else args.workload)
+    if args.radius is not None:
+        global RADIUS
+        RADIUS = float(args.radius)
+        w = dict(w, name=w["name"] + f" [radius {RADIUS:g}]")
     if args.impl == "reference":
         run_reference(args, w)
     else:

@@ -57,41 +57,37 @@ __global__ void __launch_bounds__(MCX_THREADS) mcx_mask_kernel(McGeo m, const fl
 }
 
 /** The vertex on the crossed edge from node A = (x, y, z) to A + unit(axis).  Operation for operation the V stage of mc_emit_kernel
- *  (mc.cuh): gradient (f(+) - f(-)) * 1/(n*sd) with the samples clamped at the GLOBAL grid border (one-sided there). */
-__device__ __forceinline__ void mcxEdgeVertex(const McGeo& m, const float* __restrict__ pA, size_t plane, int x, int y, int z, int axis,
+ *  (mc.cuh): gradient (f(+) - f(-)) * 1/(n*sd) with the samples clamped at the GLOBAL grid border (one-sided there).  Branch-free: the border only changes offsets and the factor. */
+__device__ __forceinline__ void mcxEdgeVertex(const McGeo& m, const float* __restrict__ pA, int plane, int x, int y, int z, int axis,
     float* __restrict__ pos, float* __restrict__ nrm) {
+    const int sx = m.sx; // (32-bit element offsets: the host admits the indexed mesh only for planes below 2^31 voxels)
     auto gradient = [&](const float* __restrict__ p, int gx_, int gy_, int gz_, float& gx, float& gy, float& gz) {
-        const int xm = gx_ > 0 ? 1 : 0, xp = gx_ < m.sx - 1 ? 1 : 0;
-        const int ym = gy_ > 0 ? 1 : 0, yp = gy_ < m.sy - 1 ? 1 : 0;
-        const int zm = gz_ > 0 ? 1 : 0, zp = gz_ < m.szGlobal - 1 ? 1 : 0;
-        gx = xp + xm ? __fmul_rn(__fsub_rn(__ldg(p + xp), __ldg(p - xm)), m.rinv[0][xp + xm]) : 0.0f;
-        gy = yp + ym ? __fmul_rn(__fsub_rn(__ldg(p + (yp ? m.sx : 0)), __ldg(p - (ym ? m.sx : 0))), m.rinv[1][yp + ym]) : 0.0f;
-        gz = zp + zm ? __fmul_rn(__fsub_rn(__ldg(p + (zp ? plane : 0)), __ldg(p - (zm ? plane : 0))), m.rinv[2][zp + zm]) : 0.0f;
+        const int xm = gx_ > 0, xp = gx_ < m.sx - 1, ym = gy_ > 0, yp = gy_ < m.sy - 1, zm = gz_ > 0, zp = gz_ < m.szGlobal - 1;
+        // (no dynamic index into the parameter struct: one-sided and central factors by select; on an axis of a single node both
+        //  samples are the node itself and the difference is an exact 0)
+        gx = __fmul_rn(__fsub_rn(__ldg(p + xp), __ldg(p - xm)), (xp & xm) ? m.rinv[0][2] : m.rinv[0][1]);
+        gy = __fmul_rn(__fsub_rn(__ldg(p + yp * sx), __ldg(p - ym * sx)), (yp & ym) ? m.rinv[1][2] : m.rinv[1][1]);
+        gz = __fmul_rn(__fsub_rn(__ldg(p + zp * plane), __ldg(p - zm * plane)), (zp & zm) ? m.rinv[2][2] : m.rinv[2][1]);
     };
-    const float* pB = pA + (axis == 0 ? size_t(1) : (axis == 1 ? static_cast<size_t>(m.sx) : plane));
+    const int ax = axis == 0, ay = axis == 1, az = axis == 2;
+    const float* pB = pA + (ax ? 1 : (ay ? sx : plane));
     float gax, gay, gaz, gbx, gby, gbz;
     gradient(pA, x, y, z, gax, gay, gaz);
-    gradient(pB, x + (axis == 0), y + (axis == 1), z + (axis == 2), gbx, gby, gbz);
+    gradient(pB, x + ax, y + ay, z + az, gbx, gby, gbz);
     const float fa = __ldg(pA), fb = __ldg(pB);
     const float tnum = __fsub_rn(m.iso, fa), tden = __fsub_rn(fb, fa);
     const float t01 = fabsf(tden) > 1e-30f ? __fmul_rn(tnum, rcpApproxF(tden)) : __fdiv_rn(tnum, tden);
-    float px = __fadd_rn(__fmul_rn((float)x, m.sd[0]), m.org[0]);
-    float py = __fadd_rn(__fmul_rn((float)y, m.sd[1]), m.org[1]);
-    float pz = __fadd_rn(__fmul_rn((float)z, m.sd[2]), m.org[2]);
-    const int c = axis == 0 ? x : (axis == 1 ? y : z);
-    const float pa = axis == 0 ? px : (axis == 1 ? py : pz);
-    const float sdA = axis == 0 ? m.sd[0] : (axis == 1 ? m.sd[1] : m.sd[2]), orgA = axis == 0 ? m.org[0] : (axis == 1 ? m.org[1] : m.org[2]);
-    const float pb = __fadd_rn(__fmul_rn((float)(c + 1), sdA), orgA);
+    const float px = __fadd_rn(__fmul_rn((float)x, m.sd[0]), m.org[0]), qx = __fadd_rn(__fmul_rn((float)(x + 1), m.sd[0]), m.org[0]);
+    const float py = __fadd_rn(__fmul_rn((float)y, m.sd[1]), m.org[1]), qy = __fadd_rn(__fmul_rn((float)(y + 1), m.sd[1]), m.org[1]);
+    const float pz = __fadd_rn(__fmul_rn((float)z, m.sd[2]), m.org[2]), qz = __fadd_rn(__fmul_rn((float)(z + 1), m.sd[2]), m.org[2]);
+    const float pa = ax ? px : (ay ? py : pz), pb = ax ? qx : (ay ? qy : qz);
     const float pc = __fadd_rn(pa, __fmul_rn(t01, __fsub_rn(pb, pa)));
-    if (axis == 0) px = pc;
-    else if (axis == 1) py = pc;
-    else pz = pc;
     const float gx = __fadd_rn(gax, __fmul_rn(t01, __fsub_rn(gbx, gax)));
     const float gy = __fadd_rn(gay, __fmul_rn(t01, __fsub_rn(gby, gay)));
     const float gz = __fadd_rn(gaz, __fmul_rn(t01, __fsub_rn(gbz, gaz)));
     const float len2 = __fadd_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)), __fmul_rn(gz, gz));
     const float inv = len2 > 0.0f ? -rsqrtApproxF(len2) : 0.0f;
-    pos[0] = px, pos[1] = py, pos[2] = pz;
+    pos[0] = ax ? pc : px, pos[1] = ay ? pc : py, pos[2] = az ? pc : pz;
     nrm[0] = __fmul_rn(gx, inv), nrm[1] = __fmul_rn(gy, inv), nrm[2] = __fmul_rn(gz, inv);
 }
 
@@ -114,9 +110,10 @@ __global__ void __launch_bounds__(MCX_THREADS) mcx_vertex_kernel(McGeo m, const 
     if ((r.z >> lane) & 1u) list[k++] = static_cast<unsigned char>(lane << 2 | 1);
     if ((r.w >> lane) & 1u) list[k] = static_cast<unsigned char>(lane << 2 | 2);
     __syncwarp();
-    const size_t plane = static_cast<size_t>(m.sx) * m.sy;
-    const float* row = vol + xs * 32 + static_cast<size_t>(m.sx) * y + plane * (z - m.zPlane0);
+    const int plane = m.sx * m.sy;
+    const float* row = vol + xs * 32 + static_cast<long long>(m.sx) * y + static_cast<long long>(plane) * (z - m.zPlane0);
     const size_t base = voff[seg];
+#pragma unroll 1
     for (unsigned c = lane; c < n; c += 32) {
         const unsigned code = list[c];
         const int i = code >> 2, axis = code & 3;

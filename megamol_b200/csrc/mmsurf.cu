@@ -1266,6 +1266,7 @@ static int countLaunch(mms_ctx* c, float iso) {
         if (c->haveColour) return c->fail(MMS_ERR_UNSUPPORTED, "the indexed mesh has no colour output yet");
         if (c->z0 != 0 || c->nz != c->grid.res[2] || m.cz0 != 0 || m.cnz != c->grid.res[2] - 1)
             return c->fail(MMS_ERR_UNSUPPORTED, "the indexed mesh needs the whole volume in one context (vertex ids cross z-slab borders)");
+        if (static_cast<long long>(m.sx) * m.sy >= (1ll << 31)) return c->fail(MMS_ERR_UNSUPPORTED, "the indexed mesh needs planes below 2^31 voxels");
         const size_t nvs = static_cast<size_t>((m.sx + 31) / 32) * m.sy * m.szGlobal;
         if (nvs >= (1ull << 32) - 1) return c->fail(MMS_ERR_UNSUPPORTED, "too many node segments");
         const unsigned vtiles = static_cast<unsigned>((nvs + kScanTile - 1) / kScanTile);

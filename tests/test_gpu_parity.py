@@ -50,6 +50,50 @@ def test_home_voxels_and_density(surf, oracle, case):
     assert abs(gmn - mn) <= 1e-5 * max(abs(mn), 1e-5) and abs(gmx - mx) <= 1e-5 * abs(mx)
 
 
+@pytest.mark.parametrize("ctype", ["USHORT_RGBA", "DOUBLE_I", "FLOAT_RGB"])
+def test_intensity_from_the_remaining_colour_types(surf, oracle, ctype):
+    """Aggregator 1 weights every particle with its colour-R accessor as a float (ParticlesToDensity.cpp:483,515;
+    SimpleSphericalParticles.h:123-178): raw unsigned short, double narrowed to float, first float of an RGB triple.
+    Also through QuickSurf's colour conversion (ushort / 255, intensity min-max normalised, QuickSurf.cpp:511-577)."""
+    rng = np.random.default_rng(17)
+    n = 5000
+    xyz = synth.uniform_box(n, 12.0, seed=31)
+    if ctype == "USHORT_RGBA":
+        col = rng.integers(0, 65535, size=(n, 4), dtype=np.uint16)
+        ct, stride = H.COL_USHORT_RGBA, 8
+    elif ctype == "DOUBLE_I":
+        col = (rng.random(n) * 5.0 + 0.25).astype(np.float64)
+        ct, stride = H.COL_DOUBLE_I, 8
+    else:
+        col = rng.random((n, 3)).astype(np.float32)
+        ct, stride = H.COL_FLOAT_RGB, 12
+    col = np.ascontiguousarray(col)
+    lists = [dict(vtx=xyz, vtx_type=H.VERT_FLOAT_XYZ, count=n, global_radius=0.9, col=col, col_type=ct, col_stride=stride)]
+    res = (24, 24, 24)
+    gpu = run_density(surf, lists, (0, 0, 0), (12, 12, 12), res, (True,) * 3, aggregator=1, normalize=False)
+    ref, _ = oracle.density_p2d(lists, (0, 0, 0), (12, 12, 12), res, (True,) * 3, aggregator=1, normalize=False)
+    assert ref.max() > 0
+    err = np.abs(gpu.astype(np.float64) - ref) / np.maximum(np.abs(ref), H.DENSITY_FLOOR * max(1.0, float(ref.max())))
+    assert err.max() < H.DENSITY_RTOL, err.max()
+    # QuickSurf colour conversion of the same list (Gaussian mode, density-weighted RGB volume)
+    data = np.concatenate([xyz, np.full((n, 1), 0.8, np.float32)], axis=1).astype(np.float32)
+    ql = [dict(vtx=data, vtx_type=H.VERT_FLOAT_XYZR, vtx_stride=16, count=n, col=col, col_type=ct, col_stride=stride)]
+    if ct == H.COL_DOUBLE_I:
+        ql[0]["irange"] = (float(np.float32(col.min())), float(np.float32(col.max())))
+    surf.clear_particles()
+    surf.set_grid((0, 0, 0), (12, 12, 12), res, (False,) * 3)
+    surf.set_params(mode=1, aggregator=0, normalize=0, radscale=1.0, gausslim=2.0, colour=1)
+    surf.push_particles(ql)
+    surf.compute_density()
+    vol, rgb = surf.get_density(with_rgb=True)
+    sd = (np.float32(12.0) / np.float32(23.0)) * np.ones(3, np.float32)
+    rvol, rrgb = oracle.density_gauss(ql, (0, 0, 0), sd, res, radscale=1.0, gausslim=2.0, colour=True)
+    scale = float(rvol.max())
+    assert (np.abs(vol.astype(np.float64) - rvol) / np.maximum(np.abs(rvol), 1e-5 * scale)).max() < 2e-5
+    assert (np.abs(rgb.astype(np.float64) - rrgb) / np.maximum(np.abs(rrgb), 1e-5 * scale)).max() < 2e-5
+    surf.set_params(mode=0, colour=0)
+
+
 def test_density_deterministic(surf):
     lists, bmin, bext = H.uniform_case(30000, 24.0, 0.7)
     a = run_density(surf, lists, bmin, bext, (48, 48, 48), (True, True, True))
