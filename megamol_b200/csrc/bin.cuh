@@ -75,7 +75,7 @@ __device__ __forceinline__ Binned binParticle(const Geo& g, const ListDev& l, un
 }
 
 __global__ void __launch_bounds__(256) bin_count_kernel(Geo g, ListDev l, unsigned* __restrict__ cellCount,
-    DevState* __restrict__ st, int* __restrict__ homeOut) {
+    DevState* __restrict__ st, int* __restrict__ homeOut, int* __restrict__ cellOut) {
     const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
     float rmax = 0.0f;
     unsigned kept = 0;
@@ -88,6 +88,7 @@ __global__ void __launch_bounds__(256) bin_count_kernel(Geo g, ListDev l, unsign
             int* h = homeOut + 3 * (l.base + j);
             h[0] = q.X, h[1] = q.Y, h[2] = q.Z;
         }
+        cellOut[l.base + j] = q.cell; // the scatter pass does not repeat the divisions and the culling tests
         if (q.cell >= 0) {
             atomicAdd(&cellCount[q.cell], 1u);
             rmax = fmaxf(rmax, q.p.w);
@@ -106,22 +107,40 @@ __global__ void __launch_bounds__(256) bin_count_kernel(Geo g, ListDev l, unsign
     }
 }
 
-/** aux: 0 floats (plain), 1 float (aggregator 1: intensity) or 4 floats (QuickSurf colour; aggregator 2: direction) per record. */
+/** aux: 0 floats (plain), 1 float (aggregator 1: intensity) or 4 floats (QuickSurf colour; aggregator 2: direction) per record.
+ *  cellIn = the cell ids bin_count_kernel left per particle (-1: culled).  (A per-slot cell id for cell_order_kernel was measured and
+ *  rejected: the extra scattered 4-byte store costs this kernel more -- 95 -> 135 us on C2 -- than the divisions it saves there.) */
 __global__ void __launch_bounds__(256) bin_scatter_kernel(Geo g, ListDev l, unsigned* __restrict__ cursor,
-    float4* __restrict__ recs, float* __restrict__ aux, int auxN) {
+    float4* __restrict__ recs, float* __restrict__ aux, int auxN, const int* __restrict__ cellIn) {
     const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
     const unsigned long long count = listCount(l);
     for (unsigned long long j = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x; j < count; j += stride) {
-        const Binned q = binParticle(g, l, j);
-        if (q.cell < 0) continue;
-        const unsigned slot = atomicAdd(&cursor[q.cell], 1u);
-        recs[slot] = q.p;
+        const int cell = cellIn[l.base + j];
+        if (cell < 0) continue;
+        const unsigned slot = atomicAdd(&cursor[cell], 1u);
+        recs[slot] = fetchParticle(l, j);
         if (auxN == 1) {
             aux[slot] = fetchColourRaw(l, j).x; // iAcc->Get_f (ParticlesToDensity.cpp:483,515)
         } else if (auxN == 4) {
             reinterpret_cast<float4*>(aux)[slot] = g.mode == 0 ? fetchDirection(l, j) : quicksurfColour(l, fetchColourRaw(l, j));
         }
     }
+}
+
+/** Lexicographic order on the records' bit patterns (x, y, z, r as unsigned words, then the aux words) = the order of the 128-bit
+ *  concatenation: two 64-bit compares.  -1: a before b, 0: bit-identical, +1: b before a. */
+__device__ __forceinline__ int recCompare(const float4& a, const float* aa, const float4& b, const float* ab, int auxN) {
+    const unsigned long long a0 = static_cast<unsigned long long>(__float_as_uint(a.x)) << 32 | __float_as_uint(a.y);
+    const unsigned long long a1 = static_cast<unsigned long long>(__float_as_uint(a.z)) << 32 | __float_as_uint(a.w);
+    const unsigned long long b0 = static_cast<unsigned long long>(__float_as_uint(b.x)) << 32 | __float_as_uint(b.y);
+    const unsigned long long b1 = static_cast<unsigned long long>(__float_as_uint(b.z)) << 32 | __float_as_uint(b.w);
+    if (a0 != b0) return a0 < b0 ? -1 : 1;
+    if (a1 != b1) return a1 < b1 ? -1 : 1;
+    for (int i = 0; i < auxN; ++i) {
+        const unsigned x = __float_as_uint(aa[i]), y = __float_as_uint(ab[i]);
+        if (x != y) return x < y ? -1 : 1;
+    }
+    return 0;
 }
 
 __device__ __forceinline__ bool recLess(const float4& a, const float* aa, const float4& b, const float* ab, int auxN) {
@@ -152,24 +171,24 @@ __global__ void __launch_bounds__(256) cell_order_kernel(Geo g, const unsigned* 
     const float4 me = in[i];
     // my cell (records only exist for contributing particles, so the clamped/wrapped home is in range)
     const int X = homeVoxel(me.x, g.mn[0], g.sd[0]), Y = homeVoxel(me.y, g.mn[1], g.sd[1]), Z = homeVoxel(me.z, g.mn[2], g.sd[2]);
-    const int xw = g.cyc[0] ? floorMod(X, g.s[0]) : min(max(X, 0), g.s[0] - 1);
-    const int yw = g.cyc[1] ? floorMod(Y, g.s[1]) : min(max(Y, 0), g.s[1] - 1);
-    const int zw = g.cyc[2] ? floorMod(Z, g.s[2]) : min(max(Z, 0), g.s[2] - 1);
-    const int cell = (xw >> g.cshift) + g.nc[0] * ((yw >> g.cshift) + g.nc[1] * (zw >> g.cshift));
+    const int xw = g.cyc[0] ? wrapIndex(X, g.s[0]) : min(max(X, 0), g.s[0] - 1);
+    const int yw = g.cyc[1] ? wrapIndex(Y, g.s[1]) : min(max(Y, 0), g.s[1] - 1);
+    const int zw = g.cyc[2] ? wrapIndex(Z, g.s[2]) : min(max(Z, 0), g.s[2] - 1);
+    const unsigned cell = static_cast<unsigned>((xw >> g.cshift) + g.nc[0] * ((yw >> g.cshift) + g.nc[1] * (zw >> g.cshift)));
     const unsigned b = cellStart[cell], e = cellStart[cell + 1];
     if (e - b > kBigCell) { // crowded cell: ranking by all pairs would be quadratic; cell_sort_big_kernel sorts it
-        if (i == b) bigCells[atomicAdd(nBig, 1u)] = static_cast<unsigned>(cell);
+        if (i == b) bigCells[atomicAdd(nBig, 1u)] = cell;
         return;
     }
     float myAux[4] = {0, 0, 0, 0};
     for (int k = 0; k < auxN; ++k) myAux[k] = auxIn[static_cast<size_t>(i) * auxN + k];
     unsigned rank = 0;
     for (unsigned k = b; k < e; ++k) {
-        if (k == i) continue;
         const float4 o = in[k];
         float oa[4] = {0, 0, 0, 0};
         for (int q = 0; q < auxN; ++q) oa[q] = auxIn[static_cast<size_t>(k) * auxN + q];
-        if (recLess(o, oa, me, myAux, auxN) || (!recLess(me, myAux, o, oa, auxN) && k < i)) ++rank;
+        const int c = recCompare(o, oa, me, myAux, auxN);
+        rank += (c < 0 || (c == 0 && k < i)) ? 1u : 0u; // (k == i compares equal and is not before itself)
     }
     out[b + rank] = me;
     for (int k = 0; k < auxN; ++k) auxOut[static_cast<size_t>(b + rank) * auxN + k] = myAux[k];

@@ -702,7 +702,10 @@ __global__ void __launch_bounds__(CT_THREADS, 4) density_splat3_kernel(Geo g, Sp
         const int a = lane < 4 ? 0 : (lane < 4 + S3_PRECELLS ? 1 : 2), i = lane < 4 ? lane : (lane < 4 + S3_PRECELLS ? lane - 4 : lane - 4 - S3_PRECELLS);
         const int t0 = a == 0 ? t0x : (a == 1 ? t0y : t0z), t1 = a == 0 ? t1x : (a == 1 ? t1y : t1z);
         const float shift = a == 0 ? sh.runs.runShift[i] : (a == 1 ? AY.shift[i] : AZ.shift[i]);
-        const float2 b = make_float2(fmaf((float)t0, g.sd[a], g.mn[a]) - kc.slack[a] - shift, fmaf((float)t1, g.sd[a], g.mn[a]) + kc.slack[a] - shift);
+        // (selects, not g.sd[a]: a dynamic index would make the compiler keep a local-memory copy of the parameter structs)
+        const float sdA = a == 0 ? g.sd[0] : (a == 1 ? g.sd[1] : g.sd[2]), mnA = a == 0 ? g.mn[0] : (a == 1 ? g.mn[1] : g.mn[2]);
+        const float slackA = a == 0 ? kc.slack[0] : (a == 1 ? kc.slack[1] : kc.slack[2]);
+        const float2 b = make_float2(fmaf((float)t0, sdA, mnA) - slackA - shift, fmaf((float)t1, sdA, mnA) + slackA - shift);
         (a == 0 ? W.bx : (a == 1 ? W.by : W.bz))[i] = b;
     }
     __syncwarp();

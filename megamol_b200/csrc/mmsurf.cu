@@ -280,7 +280,7 @@ struct mms_ctx {
     unsigned haloFrame = 0;       // parity selects the counter word of the current frame
     PinBuf hRoute;
     DevBuf cellCount, cellStart, cursor, tileSums, recsA, recsB, auxA, auxB, vol, rgb, segCount, segOffset, meshPos, meshNrm,
-        meshCol, triCount, home, dstate, dirVol, rmaxBuf, bigCells, s3Tables, vertCount, vertOffset, vertRec, meshIdx;
+        meshCol, triCount, home, dstate, dirVol, rmaxBuf, bigCells, s3Tables, vertCount, vertOffset, vertRec, meshIdx, cellOf;
     PinBuf hIdx;
     bool meshIndexed = false, countIndexed = false; // mms_set_mesh_indexed: the mode in force / the mode the last count ran in
     unsigned long long nverts = 0;                  // indexed mesh: vertices of the last count
@@ -569,7 +569,7 @@ int mms_destroy(mms_ctx* c) {
         DeviceGuard guard(c->device);
         mms_clear_particles(c);
         for (DevBuf* b : {&c->cellCount, &c->cellStart, &c->cursor, &c->tileSums, &c->recsA, &c->recsB, &c->auxA, &c->auxB, &c->vol,
-                 &c->rgb, &c->segCount, &c->segOffset, &c->meshPos, &c->meshNrm, &c->meshCol, &c->triCount, &c->home, &c->dstate, &c->routeCounts, &c->routeOffsets, &c->routeTile, &c->rangeBuf, &c->dirVol, &c->rmaxBuf, &c->bigCells, &c->haloBuf, &c->haloCounters, &c->s3Tables, &c->vertCount, &c->vertOffset, &c->vertRec, &c->meshIdx})
+                 &c->rgb, &c->segCount, &c->segOffset, &c->meshPos, &c->meshNrm, &c->meshCol, &c->triCount, &c->home, &c->dstate, &c->routeCounts, &c->routeOffsets, &c->routeTile, &c->rangeBuf, &c->dirVol, &c->rmaxBuf, &c->bigCells, &c->haloBuf, &c->haloCounters, &c->s3Tables, &c->vertCount, &c->vertOffset, &c->vertRec, &c->meshIdx, &c->cellOf})
             b->release();
         for (PinBuf* b : {&c->hState, &c->hVol, &c->hRgb, &c->hPos, &c->hNrm, &c->hCol, &c->hHome, &c->hTri, &c->hRoute, &c->hDir, &c->hIdx}) b->release();
         cudaStreamSynchronize(c->stream);
@@ -857,7 +857,8 @@ int mms_compute_density(mms_ctx* c) {
     const unsigned ntiles = static_cast<unsigned>((ncells + kScanTile - 1) / kScanTile);
     if (!c->cellCount.ensure(ncells * 4) || !c->cellStart.ensure((ncells + 1) * 4) || !c->cursor.ensure(ncells * 4) ||
         !c->tileSums.ensure(std::max<size_t>(ntiles, 1) * 4) || !c->recsA.ensure(std::max<size_t>(n, 1) * 16) ||
-        !c->recsB.ensure(std::max<size_t>(n, 1) * 16) || !c->vol.ensure(nvox * 4) || !c->bigCells.ensure((n / kBigCell + 2) * 4))
+        !c->recsB.ensure(std::max<size_t>(n, 1) * 16) || !c->vol.ensure(nvox * 4) || !c->bigCells.ensure((n / kBigCell + 2) * 4) ||
+        !c->cellOf.ensure(std::max<size_t>(n, 1) * 4))
         return c->fail(MMS_ERR_NOMEM, "device allocation failed (cells %zu, particles %zu, voxels %zu)", ncells, n, nvox);
     if (auxN && (!c->auxA.ensure(std::max<size_t>(n, 1) * 4 * auxN) || !c->auxB.ensure(std::max<size_t>(n, 1) * 4 * auxN)))
         return c->fail(MMS_ERR_NOMEM, "device allocation failed (aux)");
@@ -869,14 +870,14 @@ int mms_compute_density(mms_ctx* c) {
     MMS_CUDA(c, cudaMemsetAsync(c->cellCount.p, 0, ncells * 4, st));
     const int cap = c->smCount * 16;
     for (const ListDev& l : c->lists) {
-        bin_count_kernel<<<gridFor(l.count, 256, cap), 256, 0, st>>>(g, l, c->cellCount.as<unsigned>(), c->dstate.as<DevState>(), homeOut);
+        bin_count_kernel<<<gridFor(l.count, 256, cap), 256, 0, st>>>(g, l, c->cellCount.as<unsigned>(), c->dstate.as<DevState>(), homeOut, c->cellOf.as<int>());
         ++c->launches;
     }
     exclusiveScan(c->cellCount.as<unsigned>(), c->cellStart.as<unsigned>(), c->cursor.as<unsigned>(), c->tileSums.as<unsigned>(),
         static_cast<unsigned>(ncells), nullptr, st, c->launches);
     for (const ListDev& l : c->lists) {
         bin_scatter_kernel<<<gridFor(l.count, 256, cap), 256, 0, st>>>(g, l, c->cursor.as<unsigned>(), c->recsA.as<float4>(),
-            c->auxA.as<float>(), auxN);
+            c->auxA.as<float>(), auxN, c->cellOf.as<int>());
         ++c->launches;
     }
     // the raw input is not needed any more: its arena may be overwritten by the upload of the frame after next
