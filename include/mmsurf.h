@@ -239,13 +239,18 @@ int mms_route_particles(mms_ctx* ctx, const mms_list* list, int32_t nslabs, cons
  * processes: mms_ipc_export / mms_ipc_open; peer access inside one process) and APPEND what that slab needs from their share of the
  * frame with one kernel (halo_push_kernel: ballot-aggregated system-scope atomics over NVLink).  Per frame and slab:
  *     mms_clear_particles, mms_push_particles(own share)           (as always)
- *     mms_halo_push(...)                                           one kernel per pushed list; nothing to wait for on the host
- *     <every slab's push is complete: a stream-ordered collective (any tiny all-reduce) between processes, events inside one>
+ *     mms_halo_push(...)                                           one kernel per pushed list + one signal kernel; no host wait
+ *     mms_halo_wait(ctx, npeers)                                   stream-ordered: returns at once, the STREAM waits until `npeers` slabs have
+ *                                                                  signalled that their records of this frame have landed (a spinning
+ *                                                                  one-thread kernel on a flag in this GPU's memory: no collective, no host;
+ *                                                                  inside one process CUDA events do the same and the call is not needed)
  *     mms_halo_receive(ctx, radius_bound)                          the received records become one more list; its LENGTH stays on the device
  *     mms_compute_density ...
- * The counters alternate between two words per frame; a slab clears the word of the NEXT frame while it consumes this one's. */
-/* This context's receive buffer (capacity_records x 16 bytes, grow-only; growing invalidates earlier mappings) and its counter block
- * (4 x uint32: counter of even frames, counter of odd frames, 2 spare). */
+ * Counters and buffer halves alternate between two sets per frame: a slab clears the counters of the NEXT frame when it signals this one,
+ * and frame k+1's records never land in memory frame k is still being binned from. */
+/* This context's receive buffer (2 x capacity_records x 16 bytes -- one half per frame parity --, grow-only; growing invalidates earlier
+ * mappings) and its counter block (4 x uint32: record counter of even / odd frames, arrival counter of even / odd frames).  Every slab
+ * passes the SAME capacity_records. */
 int mms_halo_buffers(mms_ctx* ctx, uint64_t capacity_records, void** recv_buf, void** counters);
 /* Routes the lists pushed so far: slab i computes planes [plane_lo[i], plane_hi[i]]; peer_bufs[i] / peer_counters[i] are slab i's receive
  * buffer / counter block as mapped into THIS process (ignored for i == my_slab); capacity_records as given to the peers' mms_halo_buffers. */
@@ -254,6 +259,8 @@ int mms_halo_push(mms_ctx* ctx, int32_t nslabs, int32_t my_slab, const int32_t* 
 /* Adds what the peers have pushed into this context's buffer as a FLOAT_XYZR list (radii <= radius_bound: the largest radius any slab
  * may send -- it sizes the sort cells without a device scan).  Call once every peer's mms_halo_push of this frame has completed. */
 int mms_halo_receive(mms_ctx* ctx, float radius_bound);
+/* Between processes: makes this context's stream wait for the signals of `npeers` pushing slabs (normally nslabs - 1). */
+int mms_halo_wait(mms_ctx* ctx, int32_t npeers);
 
 /* ---- several GPUs behind ONE handle, inside one process (the drop-in modules' `devices` parameter) ---------------------------------
  * The z-slab decomposition of SURVEY 8e driven from C: one context per device, slab g owns cell layers [g(sz-1)/G, (g+1)(sz-1)/G) and

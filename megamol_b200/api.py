@@ -18,7 +18,7 @@ ISO_MARCHING_CUBES, ISO_MARCHING_TETS = 0, 1
 EXPORTS = ["mms_create", "mms_destroy", "mms_last_error", "mms_set_grid", "mms_set_slab", "mms_set_params",
            "mms_clear_particles", "mms_push_particles", "mms_push_particles_dir", "mms_get_vector_field", "mms_get_vector_field_device", "mms_get_max_radius", "mms_compute_density", "mms_get_density_range", "mms_normalize", "mms_density_range_device", "mms_normalize_device", "mms_set_stream",
            "mms_get_density", "mms_prefetch_density", "mms_get_density_device", "mms_set_density", "mms_adopt_density", "mms_extract_isosurface", "mms_set_isosurface_mode", "mms_count_isosurface", "mms_emit_isosurface", "mms_device_alloc",
-           "mms_device_free", "mms_route_particles", "mms_halo_buffers", "mms_halo_push", "mms_halo_receive", "mms_slabs_create", "mms_slabs_destroy", "mms_slabs_last_error", "mms_slabs_count", "mms_slabs_context", "mms_slabs_set_grid", "mms_slabs_set_params", "mms_slabs_clear_particles", "mms_slabs_push_particles", "mms_slabs_compute_density", "mms_slabs_get_density_range", "mms_slabs_get_density", "mms_slabs_adopt_density", "mms_slabs_extract_isosurface", "mms_slabs_get_mesh", "mms_ipc_export", "mms_ipc_open", "mms_ipc_close", "mms_share_enable", "mms_share_density", "mms_share_mesh", "mms_share_open", "mms_share_close", "mms_get_mesh",
+           "mms_device_free", "mms_route_particles", "mms_halo_buffers", "mms_halo_push", "mms_halo_receive", "mms_halo_wait", "mms_slabs_create", "mms_slabs_destroy", "mms_slabs_last_error", "mms_slabs_count", "mms_slabs_context", "mms_slabs_set_grid", "mms_slabs_set_params", "mms_slabs_clear_particles", "mms_slabs_push_particles", "mms_slabs_compute_density", "mms_slabs_get_density_range", "mms_slabs_get_density", "mms_slabs_adopt_density", "mms_slabs_extract_isosurface", "mms_slabs_get_mesh", "mms_ipc_export", "mms_ipc_open", "mms_ipc_close", "mms_share_enable", "mms_share_density", "mms_share_mesh", "mms_share_open", "mms_share_close", "mms_get_mesh",
            "mms_get_mesh_device", "mms_set_mesh_indexed", "mms_get_mesh_indexed", "mms_get_mesh_indexed_device", "mms_get_home_voxels", "mms_get_cell_tricounts", "mms_get_timings", "mms_synchronize",
            "mms_timer_start", "mms_timer_stop", "mms_launch_count", "mms_alloc_pinned", "mms_free_pinned", "mms_version", "mms_mmpld_open", "mms_mmpld_close",
            "mms_mmpld_last_error", "mms_mmpld_info", "mms_mmpld_prefetch", "mms_mmpld_read_frame"]
@@ -399,6 +399,10 @@ class Surf:
         pb = (C.c_void_p * n)(*[C.c_void_p(p) for p in peer_bufs])
         pc = (C.c_void_p * n)(*[C.c_void_p(p) for p in peer_counters])
         self._chk(self.L.mms_halo_push(self.h, n, int(mine), lo, hi, pb, pc, int(capacity)))
+
+    def halo_wait(self, npeers):
+        """stream-ordered: the context's stream waits until `npeers` slabs have signalled that their pushes of this frame have landed"""
+        self._chk(self.L.mms_halo_wait(self.h, int(npeers)))
 
     def halo_receive(self, radius_bound):
         self._chk(self.L.mms_halo_receive(self.h, float(radius_bound)))

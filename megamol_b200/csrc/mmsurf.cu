@@ -984,6 +984,9 @@ int mms_compute_density(mms_ctx* c) {
  *  field read-back, the triangle count).  Purely device-resident sequences (mms_*_device) end in mms_count_isosurface, which checks. */
 static int deviceErrorFromState(mms_ctx* c) {
     const DevState* hs = c->hState.as<DevState>();
+    if (hs->pad[0] == 5)
+        return c->fail(MMS_ERR_UNSUPPORTED, "halo exchange: the receive buffer overflowed (mms_halo_buffers capacity too small) or the other slabs' "
+                                            "records did not arrive in time (mms_halo_wait)");
     if (hs->pad[0] == 2)
         return c->fail(MMS_ERR_UNSUPPORTED, "internal error: the single-image gather kernel ran on a short periodic axis");
     if (hs->pad[0] != 0)
@@ -1613,7 +1616,7 @@ int mms_halo_buffers(mms_ctx* c, uint64_t cap, void** buf, void** counters) {
     if (!c || !buf || !counters || cap == 0) return MMS_ERR_INVALID;
     DeviceGuard guard(c->device);
     const bool fresh = c->haloCounters.p == nullptr;
-    if (!c->haloBuf.ensure(cap * 16) || !c->haloCounters.ensure(16)) return c->fail(MMS_ERR_NOMEM, "allocation of the halo receive buffer (%llu records) failed",
+    if (!c->haloBuf.ensure(cap * 16 * 2) || !c->haloCounters.ensure(16)) return c->fail(MMS_ERR_NOMEM, "allocation of the halo receive buffer (%llu records) failed",
         static_cast<unsigned long long>(cap));
     if (fresh) MMS_CUDA(c, cudaMemset(c->haloCounters.p, 0, 16));
     c->haloCap = cap;
@@ -1641,20 +1644,35 @@ int mms_halo_push(mms_ctx* c, int32_t nslabs, int32_t mine, const int32_t* plane
         r.lo[i] = plane_lo[i], r.hi[i] = plane_hi[i];
         if (i != mine && plane_lo[i] <= plane_hi[i] && peer_bufs[i] && peer_counters[i]) {
             r.enabled |= 1u << i;
-            hp.buf[i] = static_cast<float4*>(peer_bufs[i]);
+            hp.buf[i] = static_cast<float4*>(peer_bufs[i]) + static_cast<size_t>(word) * cap; // frames alternate between the buffer's halves
             hp.counter[i] = static_cast<unsigned*>(peer_counters[i]) + word;
+            hp.arrive[i] = static_cast<unsigned*>(peer_counters[i]) + 2 + word;
         }
     }
     hp.cap = static_cast<unsigned>(std::min<uint64_t>(cap, 0xffffffffull));
     r.sigma = g.sigma, r.radscale = g.radscale, r.gausslim = g.gausslim, r.mode = g.mode;
-    // my own counter of the NEXT frame: nobody pushes into it before this frame's "all pushes complete" point
-    MMS_CUDA(c, cudaMemsetAsync(c->haloCounters.as<unsigned>() + (word ^ 1u), 0, 4, st));
+    if (cap != c->haloCap) return c->fail(MMS_ERR_INVALID, "capacity_records must be the capacity every slab passed to mms_halo_buffers");
     if (r.enabled)
         for (const ListDev& l : c->lists) {
             if (l.countPtr) continue; // a received list is never forwarded
             halo_push_kernel<<<gridFor(l.count, 256, c->smCount * 16), 256, 0, st>>>(r, l, hp);
             ++c->launches;
         }
+    // my own counters of the NEXT frame are cleared (nobody touches them before this frame's signal), then the peers learn that my
+    // records of this frame have landed
+    halo_signal_kernel<<<1, 32, 0, st>>>(hp, r.enabled, c->haloCounters.as<unsigned>() + (word ^ 1u), c->haloCounters.as<unsigned>() + 2 + (word ^ 1u));
+    ++c->launches;
+    MMS_CUDA(c, cudaGetLastError());
+    return MMS_OK;
+}
+
+int mms_halo_wait(mms_ctx* c, int32_t npeers) {
+    if (!c || npeers < 0) return MMS_ERR_INVALID;
+    if (!c->haloCounters.p || !c->haloCap) return c->fail(MMS_ERR_INVALID, "mms_halo_buffers has not been called");
+    DeviceGuard guard(c->device);
+    halo_wait_kernel<<<1, 1, 0, c->stream>>>(c->haloCounters.as<unsigned>() + 2 + (c->haloFrame & 1u), static_cast<unsigned>(npeers),
+        c->haloCounters.as<unsigned>() + (c->haloFrame & 1u));
+    ++c->launches;
     MMS_CUDA(c, cudaGetLastError());
     return MMS_OK;
 }
@@ -1664,7 +1682,7 @@ int mms_halo_receive(mms_ctx* c, float radius_bound) {
     if (!c->haloCounters.p || !c->haloCap) return c->fail(MMS_ERR_INVALID, "mms_halo_buffers has not been called");
     if (c->lists.size() + 1 > static_cast<size_t>(kMaxLists)) return c->fail(MMS_ERR_UNSUPPORTED, "more than %d particle lists", kMaxLists);
     ListDev d{};
-    d.vtx = static_cast<const char*>(c->haloBuf.p);
+    d.vtx = static_cast<const char*>(c->haloBuf.p) + static_cast<size_t>(c->haloFrame & 1u) * c->haloCap * 16; // this frame's half
     d.count = c->haloCap; // the bound; the length is read on the device
     d.countPtr = c->haloCounters.as<unsigned>() + (c->haloFrame & 1u);
     d.base = c->nparticles;

@@ -103,10 +103,35 @@ __global__ void __launch_bounds__(256) route_scatter_kernel(RouteGeo r, ListDev 
 
 /** Receive buffers of the other slabs (peer memory: CUDA IPC mappings or peer access) and their record counters. */
 struct HaloPeers {
-    float4* buf[kMaxSlabs];
-    unsigned* counter[kMaxSlabs];
+    float4* buf[kMaxSlabs];       // this frame's half of the peer's receive buffer
+    unsigned* counter[kMaxSlabs]; // this frame's record counter of the peer
+    unsigned* arrive[kMaxSlabs];  // this frame's arrival counter of the peer: +1 once ALL my pushes of the frame have landed
     unsigned cap;
 };
+
+/** After the push kernels of a frame (same stream): clear MY counters of the next frame, then tell every peer that my records of this
+ *  frame are complete.  The peers' halo_wait_kernel spins on that count -- the "every push has completed" point needs no collective
+ *  and no host.  (The clear comes first: a peer can only push or signal the next frame after it has seen this signal.) */
+__global__ void halo_signal_kernel(HaloPeers hp, unsigned enabled, unsigned* myNextCounter, unsigned* myNextArrive) {
+    if (threadIdx.x == 0) *myNextCounter = 0u, *myNextArrive = 0u;
+    __threadfence_system(); // (the push kernels before this one in the stream have completed: their stores are performed)
+    __syncthreads();
+    if (threadIdx.x < kMaxSlabs && ((enabled >> threadIdx.x) & 1u)) atomicAdd_system(hp.arrive[threadIdx.x], 1u);
+}
+
+/** Stream-ordered wait for `npeers` arrivals (see halo_signal_kernel).  Gives up after ~4 s: the record counter is then poisoned, which
+ *  bin_count_kernel reports like an overflow of the receive buffer (the frame fails at the next host-synchronising call). */
+__global__ void halo_wait_kernel(const unsigned* arrive, unsigned npeers, unsigned* myCounter) {
+    const long long t0 = clock64();
+    while (*reinterpret_cast<const volatile unsigned*>(arrive) < npeers) {
+        if (clock64() - t0 > (8ll << 30)) {
+            atomicExch(myCounter, 0xffffffffu);
+            break;
+        }
+        __nanosleep(200);
+    }
+    __threadfence_system();
+}
 
 /**
  * Halo exchange in ONE kernel, no host round trip, no collective: every record of the list that another slab needs (routeMask; the

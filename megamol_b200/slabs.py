@@ -264,7 +264,7 @@ class SlabJob:
         L = self.surf.L
         # a slab receives at most what its neighbours' halos hold; the frames here are z-ordered, so a rank's own share bounds it amply.
         # (An overflow is detected on the device and reported by the next host-synchronising call.)
-        self._halo_cap = self.n_local + (1 << 20)
+        self._halo_cap = -(-self.n_total // self.world) + 1 + (1 << 20)  # the same on every rank (the buffer halves are addressed with it)
         buf, ctr = self.surf.halo_buffers(self._halo_cap)
         mine = []
         for ptr in (buf, ctr):
@@ -294,13 +294,19 @@ class SlabJob:
             self._peer_ctrs.append(ptrs[1])
         self._peer_cap = min(caps)
         self._tick = self.torch.zeros(1, device=self.dev, dtype=self.torch.float32)
+        import os
+        self._halo_allreduce = bool(os.environ.get("MMS_HALO_ALLREDUCE"))
 
     def _halo(self):
-        """Fused halo exchange of the lists pushed so far: one push kernel, a one-word all-reduce as the stream-ordered "all pushes are
-        complete" point, then the received records join the frame as one more list (its length stays on the device)."""
-        import torch.distributed as dist
+        """Fused halo exchange of the lists pushed so far: one push kernel per list and a signal kernel; the stream then waits on a flag
+        in this GPU's memory until every other rank's records have landed (no collective, no host round trip); the received records join the
+        frame as one more list (its length stays on the device).  MMS_HALO_ALLREDUCE=1: the earlier one-word all-reduce as that point."""
         self.surf.halo_push(self.slabs, self.rank, self._peer_bufs, self._peer_ctrs, self._peer_cap)
-        dist.all_reduce(self._tick)
+        if self._halo_allreduce:
+            import torch.distributed as dist
+            dist.all_reduce(self._tick)
+        else:
+            self.surf.halo_wait(self.world - 1)
         self.surf.halo_receive(self.radius)
 
     def _exchange(self, xyz_dev):
@@ -350,18 +356,32 @@ class SlabJob:
         self.last["tri_counts"] = [c // 3 for c in counts]
         self.last["gathered_verts"] = sum(counts)
 
-    def _allgather_counts(self):
+    def _allgather_counts(self, ntris=None):
         """mesh stays sharded: all-gather of the per-slab triangle counts -> every rank knows its offset in the frame's mesh.
-        The collective is only enqueued here; the host reads the counts when somebody asks for them (tri_counts())."""
+        The collective is only enqueued here; the host reads the counts when somebody asks for them (tri_counts()).
+        ntris given (the count is known, the emit kernel not yet launched): the collective goes to a side stream and runs UNDER the
+        emit kernel; _join_counts() makes the main stream wait for it."""
         torch = self.torch
         import torch.distributed as dist
-        nverts, _, _ = self.surf.mesh_device()
-        cnt = torch.tensor([nverts // 3], device=self.dev, dtype=torch.int64)
         if getattr(self, "_tcounts", None) is None:
             self._tcounts = torch.empty((self.world,), device=self.dev, dtype=torch.int64)
-        dist.all_gather_into_tensor(self._tcounts, cnt)
+            self._side = torch.cuda.Stream(device=self.dev)
         self.last.pop("tri_counts", None)
         self.last["gathered_verts"] = 0
+        if ntris is None:
+            nverts, _, _ = self.surf.mesh_device()
+            cnt = torch.tensor([nverts // 3], device=self.dev, dtype=torch.int64)
+            dist.all_gather_into_tensor(self._tcounts, cnt)
+            return
+        with torch.cuda.stream(self._side):
+            cnt = torch.tensor([int(ntris)], device=self.dev, dtype=torch.int64)
+            dist.all_gather_into_tensor(self._tcounts, cnt)
+        self._counts_pending = True
+
+    def _join_counts(self):
+        if getattr(self, "_counts_pending", False):
+            self.torch.cuda.current_stream().wait_stream(self._side)
+            self._counts_pending = False
 
     def tri_counts(self):
         """per-slab triangle counts of the last step (host list; synchronises if they are still on the device)"""
@@ -464,7 +484,15 @@ class SlabJob:
         if prefetch:
             s.prefetch_density()
         if extract:
-            s.extract_isosurface(self.iso)
+            if self.world > 1 and self.gather == "host" and not self.protein:
+                # the triangle count is on the host after the count half: the emit kernel is launched first, then the count's all-gather
+                # goes to a side stream and runs under it (the side stream has nothing to wait for: the count comes from the host, and the
+                # previous frame's readers of the gathered counts have been joined)
+                ntris = s.count_isosurface(self.iso)
+                s.emit_isosurface()
+                self._allgather_counts(ntris)
+            else:
+                s.extract_isosurface(self.iso)
 
     def step_device(self):
         """inputs resident in HBM: (exchange) -> bin -> density -> (range all-reduce, normalise) -> MC -> (mesh gather)"""
@@ -487,7 +515,7 @@ class SlabJob:
             elif self.gather == "nccl":
                 self._gather_mesh()
             else:
-                self._allgather_counts()
+                self._join_counts()
             ev[3].record()
             torch.cuda.current_stream().synchronize()
             self.last["exchange_ms"] = ev[0].elapsed_time(ev[1]) if self.exchange != "fused" else self._halo_events[0].elapsed_time(self._halo_events[1])
@@ -511,7 +539,7 @@ class SlabJob:
             self._keep = [d]
             self._compute(d.data_ptr(), self.n_local, more=more, prefetch=True)
             self.surf.get_density(copy=False)
-            self._allgather_counts()
+            self._join_counts()
             torch.cuda.current_stream().synchronize()
         else:
             d = self.h_xyz.to(self.dev, non_blocking=True)
@@ -525,7 +553,7 @@ class SlabJob:
             elif self.gather == "nccl":
                 self._gather_mesh()
             else:
-                self._allgather_counts()
+                self._join_counts()
                 self.surf.get_mesh(copy=False)   # this rank's slab over this GPU's own PCIe link
             if self.rank == 0 and self.gather != "host":
                 # D2H of the gathered mesh through a fixed 1 GiB pinned window (a consumer would map its own buffer; pinning
