@@ -1121,7 +1121,7 @@ __global__ void __launch_bounds__(GT_THREADS, 2) density_gather_kernel(Geo g, De
 // ---------------------------------------------------------------------------------------------------------------
 // density_gauss_kernel: QuickSurf-Gaussian mode with the radial cut-off on a non-periodic grid (C3)
 // ---------------------------------------------------------------------------------------------------------------
-// A WARP owns an 8x4x8-voxel patch (a thread: a column of eight voxels in registers; eight patches make the 32x8x8 tile of a block, but
+// A WARP owns an 8x4x8-voxel patch (a thread: a column of eight voxels in registers; four patches make the 32x4x8 strip of a block, but
 // the warps never talk to each other: no block barrier, no shared candidate stage).  The warp streams, in ascending (cell z, cell y,
 // cell x) and canonical in-cell order, the records of every cell row its patch's neighbourhood touches -- the x cells of a row are one
 // contiguous record range --, 32 records per round: each lane turns its record into a candidate (cut-off^2, exponent scale, colour),
@@ -1137,19 +1137,21 @@ struct GaussCand {          // 64 bytes
     float dz2[GT_Z];        // (z_k - z)^2 of the patch's eight planes: the same for every lane, computed once by the lane that stages the atom
 };
 constexpr int GP_X = 8, GP_Y = 4; // voxel columns of a warp's patch
+constexpr int GQ_WARPS = 4;       // independent warps per block: a 32x4x8 strip of four patches (20 warps per SM at <= 102 registers)
+constexpr int GQ_THREADS = GQ_WARPS * 32;
 struct GaussShared {
-    GaussCand cand[GT_THREADS / 32][32];
+    GaussCand cand[GQ_WARPS][32];
 };
 
 template<bool COLOUR>
-__global__ void __launch_bounds__(GT_THREADS, 2) density_gauss_kernel(Geo g, DevState* st, const float4* __restrict__ recs,
+__global__ void __launch_bounds__(GQ_THREADS, 5) density_gauss_kernel(Geo g, DevState* st, const float4* __restrict__ recs,
     const float* __restrict__ aux, int auxN, const unsigned* __restrict__ cellStart, float* __restrict__ vol, float* __restrict__ rgb,
     int reach) {
     __shared__ GaussShared sh;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int t0x = (int)blockIdx.x * GT_X, t0y = (int)blockIdx.y * GT_Y, t0z = g.z0 + (int)blockIdx.z * GT_Z;
-    const int t1x = min(t0x + GT_X, g.s[0]) - 1, t1y = min(t0y + GT_Y, g.s[1]) - 1, t1z = min(t0z + GT_Z, g.z0 + g.nz) - 1;
-    const int p0x = t0x + (warp & 3) * GP_X, p0y = t0y + (warp >> 2) * GP_Y;
+    const int t0x = (int)blockIdx.x * GT_X, t0y = (int)blockIdx.y * GP_Y, t0z = g.z0 + (int)blockIdx.z * GT_Z;
+    const int t1x = min(t0x + GT_X, g.s[0]) - 1, t1y = min(t0y + GP_Y, g.s[1]) - 1, t1z = min(t0z + GT_Z, g.z0 + g.nz) - 1;
+    const int p0x = t0x + warp * GP_X, p0y = t0y;
     const int p1x = min(p0x + GP_X - 1, t1x), p1y = min(p0y + GP_Y - 1, t1y);
     if (p0x > t1x || p0y > t1y) return; // patch beyond the grid
     GaussCand* stage = sh.cand[warp];
@@ -1240,11 +1242,13 @@ __global__ void __launch_bounds__(GT_THREADS, 2) density_gauss_kernel(Geo g, Dev
 #pragma unroll
                 for (int k = 0; k < GT_Z; ++k) {
                     const float d2 = __fadd_rn(dxy2, dz2[k]);
-                    // branch-free: outside the cut-off the weight is an exact 0, and x + 0 == x -- the same bits as skipping
-                    const float e = ex2Approx(__fmul_rn(d2, A.w));
-                    const float w = d2 < B.x ? e : 0.0f;
-                    acc[k] = __fadd_rn(acc[k], w);
-                    if (COLOUR) accR[k] = fmaf(w, B.y, accR[k]), accG[k] = fmaf(w, B.z, accG[k]), accB[k] = fmaf(w, B.w, accB[k]);
+                    // outside the cut-off nothing is added (predicated accumulation: one compare, no select; the exponential is evaluated
+                    // regardless so that the eight chains stay independent)
+                    const float w = ex2Approx(__fmul_rn(d2, A.w));
+                    if (d2 < B.x) {
+                        acc[k] = __fadd_rn(acc[k], w);
+                        if (COLOUR) accR[k] = fmaf(w, B.y, accR[k]), accG[k] = fmaf(w, B.z, accG[k]), accB[k] = fmaf(w, B.w, accB[k]);
+                    }
                 }
             }
             __syncwarp(); // the stage is rewritten in the next round

@@ -912,8 +912,9 @@ int mms_compute_density(mms_ctx* c) {
                  : density_gather_kernel<M, COL, false><<<grid, GT_THREADS, 0, st>>>(g, DS, R, A, auxN, CS, V, out, c->reach))
         // Gaussian mode, radial cut-off, no periodic axis (QuickSurf's own case): the warp-patch kernel
         const bool gauss = g.mode == 1 && !general && !g.cyc[0] && !g.cyc[1] && !g.cyc[2] && !getenv("MMS_GATHER_GENERIC");
-        if (gauss && colour) density_gauss_kernel<true><<<grid, GT_THREADS, 0, st>>>(g, DS, R, A, auxN, CS, V, C3, c->reach);
-        else if (gauss) density_gauss_kernel<false><<<grid, GT_THREADS, 0, st>>>(g, DS, R, A, auxN, CS, V, nullptr, c->reach);
+        const dim3 gridQ((g.s[0] + GT_X - 1) / GT_X, (g.s[1] + GP_Y - 1) / GP_Y, (g.nz + GT_Z - 1) / GT_Z);
+        if (gauss && colour) density_gauss_kernel<true><<<gridQ, GQ_THREADS, 0, st>>>(g, DS, R, A, auxN, CS, V, C3, c->reach);
+        else if (gauss) density_gauss_kernel<false><<<gridQ, GQ_THREADS, 0, st>>>(g, DS, R, A, auxN, CS, V, nullptr, c->reach);
         else if (vector) MMS_GATHER(0, true, C3);
         else if (g.mode == 0) MMS_GATHER(0, false, nullptr);
         else if (colour) MMS_GATHER(1, true, C3);
