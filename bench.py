@@ -442,17 +442,24 @@ def run_c5(args):
     s = mm.Surf(0)
     s.set_grid((0, 0, 0), (L, L, L), res, (True, True, True))
     s.set_params(mode=0, aggregator=0, normalize=1, sigma=1.0)
-    stream.stream_frames(s, rd, min(3, F), ISO)            # warm-up: allocations, page cache
+    if args.indexed:
+        s.set_mesh_indexed(True)
+    stream.stream_frames(s, rd, min(3, F), ISO, indexed=args.indexed)            # warm-up: allocations, page cache
     sampler = ClockSampler(0)
     sampler.start()
     l0 = s.launch_count()
     t0 = time.perf_counter()
-    lat = stream.stream_frames(s, rd, F, ISO)
+    lat = stream.stream_frames(s, rd, F, ISO, indexed=args.indexed)
     s.synchronize()
     dt = time.perf_counter() - t0
     sampler.stop_flag.set()
     sampler.join(timeout=3)
-    ntri = s.mesh_device()[0] // 3
+    if args.indexed:
+        nvert, ntri = s.mesh_indexed_device()[:2]
+        mesh_bytes = nvert * 24 + ntri * 12
+    else:
+        ntri = s.mesh_device()[0] // 3
+        mesh_bytes = ntri * 72
     st = s.timings()
     line = {"metric": METRIC, "value": n * F / dt / 1e6, "unit": "Mparticles/s", "n_gpus": 1, "steps": F, "warmup": min(3, F),
             "ms_per_step": dt / F * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -462,7 +469,8 @@ def run_c5(args):
                        "frames": F, "file_bytes": os.path.getsize(path), "file_write_s": t_write, "triangles_last_frame": ntri,
                        "latency_ms": {"median": float(np.median(lat)), "max": float(np.max(lat))}},
             "stages_ms": {k: round(v, 4) for k, v in st.items()},
-            "e2e": {"value": n * F / dt / 1e6, "unit": "Mparticles/s", "h2d_bytes_per_step": n * 12, "d2h_bytes_per_step": res[0] * res[1] * res[2] * 4 + ntri * 72},
+            "e2e": {"value": n * F / dt / 1e6, "unit": "Mparticles/s", "h2d_bytes_per_step": n * 12, "d2h_bytes_per_step": res[0] * res[1] * res[2] * 4 + mesh_bytes},
+            "mesh": "indexed (opt-in: one vertex per crossed grid edge + 32-bit indices)" if args.indexed else "triangle soup (the reference's contract)",
             "gpu_launches": s.launch_count() - l0, "clocks": sampler.summary()}
     print(json.dumps(line))
     s.close()
@@ -490,6 +498,7 @@ def main():
                          "no host synchronisation) or nccl (round-1 baseline: routing kernels + count matrix + all-to-all-v)")
     ap.add_argument("--no-c4", action="store_true", help="N > 1: skip the C4 (100 M particles -> 1024^3, strong scaling) figures in the record")
     ap.add_argument("--tmpdir", default="/tmp")
+    ap.add_argument("--indexed", action="store_true", help="C5: read the opt-in indexed mesh back instead of the triangle soup")
     ap.add_argument("--radius", type=float, default=None, help="particle radius of the LJ workloads (default 0.5; SURVEY's C2 variant: 1.0, a 5^3 support)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

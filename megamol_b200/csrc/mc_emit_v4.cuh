@@ -1,4 +1,5 @@
-// TEMPORARY (development A/B only): the round-1 emit kernel, kept to check the new kernel bit for bit.
+// The round-1 emit kernel (two cell layers per step, four block barriers per step), kept as an independent implementation that
+// tests/test_gpu_variants.py runs against mc_emit_kernel bit for bit (MMS_EMIT_V4=1; a debug knob, not part of the C ABI).
 #pragma once
 #include "mc.cuh"
 namespace mms {

@@ -19,7 +19,7 @@
 #include "bin.cuh"
 #include "density.cuh"
 #include "mc.cuh"
-#include "mc_emit_v4.cuh" // TEMPORARY: A/B check of the new emit kernel (MMS_EMIT_V4=1)
+#include "mc_emit_v4.cuh" // independent cross-check of mc_emit_kernel (MMS_EMIT_V4=1, tests/test_gpu_variants.py)
 #include "mc_indexed.cuh"
 #include "mt.cuh"
 #include "route.cuh"

@@ -19,5 +19,5 @@ for WL in c1 c3; do python bench.py --steps 10 --warmup 3 --no-cpu --workload $W
 python bench.py --steps 5 --warmup 3 --no-cpu --radius 1.0 2>/dev/null | tail -1 > gpurun_out/${T}_bench_c2_radius1.json; cut -c1-300 gpurun_out/${T}_bench_c2_radius1.json
 python bench.py --steps 3 --warmup 3 --no-cpu --algorithm mt 2>/dev/null | tail -1 > gpurun_out/${T}_bench_c2_marching_tets.json; cut -c1-300 gpurun_out/${T}_bench_c2_marching_tets.json
 python bench.py --workload c5 --frames 100 2>gpurun_out/c5.err | tail -1 > gpurun_out/${T}_bench_c5_100frames.json; cut -c1-400 gpurun_out/${T}_bench_c5_100frames.json
-cuobjdump -sass -fun 'mc_emit_kernel' megamol_b200/libmmsurf.so 2>/dev/null | grep -E "UTMALDG|UTMASTG|SYNCS|STG|LDS|BAR" | sed 's/^ *\/\*[0-9a-f]*\*\/ *//' | awk '{print $1}' | sort | uniq -c | sort -rn > gpurun_out/${T}_sass_mc_emit_opcodes.txt
+python bench.py --workload c5 --frames 100 --indexed 2>gpurun_out/c5i.err | tail -1 > gpurun_out/${T}_bench_c5_100frames_indexed.json; cut -c1-400 gpurun_out/${T}_bench_c5_100frames_indexed.json
 ls -la gpurun_out | tail -20
