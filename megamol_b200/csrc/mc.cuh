@@ -59,6 +59,8 @@ struct McGeo {
     float org[3], sd[3];
     float rinv[3][3];  // rinv[a][n] = 1/(n*sd[a]), n = 1, 2 (gradient: one-sided / central)
     float iso;
+    unsigned maxTris;  // mc_emit_kernel: cell rows whose triangles end beyond this many are skipped (speculative launch before the count is
+                       // known on the host: the destination's capacity; 0xffffffff otherwise)
 };
 
 constexpr int MC_THREADS = 256;
@@ -276,6 +278,7 @@ __global__ void __launch_bounds__(MC_THREADS, COLOUR ? 2 : 4) mc_emit_kernel(McG
             const size_t seg = blockIdx.x + static_cast<size_t>(m.nsegx) * (cyi + static_cast<size_t>(m.cy) * (zcBeg + k - m.cz0));
             off = segOffset[seg];
             cnt = segOffset[seg + 1] - off;
+            if (off + cnt > m.maxTris) cnt = 0; // beyond the destination's capacity (the host re-emits after growing the buffers)
         }
         sh.segOff[tid + h * MC_THREADS] = off;
         sh.segCnt[tid + h * MC_THREADS] = static_cast<unsigned char>(cnt);

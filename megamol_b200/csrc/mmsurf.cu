@@ -250,6 +250,7 @@ struct mms_ctx {
     int arenaCur = 0;
     cudaStream_t copyStream = nullptr;
     cudaEvent_t uploadDone = nullptr;
+    cudaEvent_t countReady = nullptr; // recorded behind the count's publish kernel: the host waits for THIS, not for the whole stream
     cudaEvent_t volReady = nullptr, volCopied = nullptr; // mms_prefetch_density: volume final on the compute stream / host copy complete
     bool volPrefetched = false;
     bool uploadPending = false;
@@ -579,6 +580,7 @@ int mms_destroy(mms_ctx* c) {
             cudaEventDestroy(a.consumed);
         }
         cudaEventDestroy(c->uploadDone);
+        if (c->countReady) cudaEventDestroy(c->countReady);
         cudaEventDestroy(c->volReady);
         cudaEventDestroy(c->volCopied);
         cudaEventDestroy(c->adoptReady);
@@ -1218,6 +1220,7 @@ static int countLaunch(mms_ctx* c, float iso) {
         m.rinv[a][0] = 0.0f;
     }
     m.iso = iso;
+    m.maxTris = 0xffffffffu;
     c->mcGeo = m;
     c->ntris = 0;
     c->haveCount = false; // set once the count has run and the device reported no error
@@ -1287,6 +1290,8 @@ static int countLaunch(mms_ctx* c, float iso) {
     publish_state_kernel<<<1, 1, 0, st>>>(c->dstate.as<DevState>(), c->hState.as<DevState>());
     ++c->launches;
     MMS_CUDA(c, cudaGetLastError());
+    if (!c->countReady) MMS_CUDA(c, cudaEventCreateWithFlags(&c->countReady, cudaEventDisableTiming));
+    MMS_CUDA(c, cudaEventRecord(c->countReady, st));
     c->countPending = true;
     return MMS_OK;
 }
@@ -1297,7 +1302,7 @@ static int countFinish(mms_ctx* c, uint64_t* ntris) {
     if (!c->countPending) return MMS_OK; // empty slab
     DeviceGuard guard(c->device);
     c->countPending = false;
-    MMS_CUDA(c, cudaStreamSynchronize(c->stream));
+    MMS_CUDA(c, cudaEventSynchronize(c->countReady)); // (not the stream: a speculative emit kernel may already be running behind the count)
     // the state block also carries the density kernels' error flag: a truncated volume must not become a mesh
     if (int rc = deviceErrorFromState(c)) return rc;
     c->ntris = c->hState.as<DevState>()->totalTris;
@@ -1312,6 +1317,27 @@ int mms_count_isosurface(mms_ctx* c, float iso, uint64_t* ntris) {
     if (ntris) *ntris = 0;
     if (int rc = countLaunch(c, iso)) return rc;
     return countFinish(c, ntris);
+}
+
+/** mc_emit_kernel into P / N / C (the default marching-cubes emission); maxTris: see McGeo. */
+static void launchMcEmit(mms_ctx* c, float* P, float* N, float* C, unsigned maxTris) {
+    McGeo m = c->mcGeo;
+    m.maxTris = maxTris;
+    cudaStream_t st = c->stream;
+    const dim3 gridE(m.nsegx, (m.cy + EY - 1) / EY, (m.cnz + EM_LAYERS - 1) / EM_LAYERS);
+    CUtensorMap map{};
+    const bool tma = makeVolumeTensorMap(&map, c->isoVol(), m.sx, m.sy, m.nzPlanes);
+    const float* V = c->isoVol();
+    const float* RGB = c->isoRgb();
+    const unsigned* S = c->segOffset.as<unsigned>();
+    if (c->haveColour) {
+        if (tma) mc_emit_kernel<true, true><<<gridE, MC_THREADS, emitSmemBytes(true), st>>>(m, map, V, RGB, S, P, N, C);
+        else mc_emit_kernel<true, false><<<gridE, MC_THREADS, emitSmemBytes(true), st>>>(m, map, V, RGB, S, P, N, C);
+    } else {
+        if (tma) mc_emit_kernel<false, true><<<gridE, MC_THREADS, emitSmemBytes(false), st>>>(m, map, V, nullptr, S, P, N, nullptr);
+        else mc_emit_kernel<false, false><<<gridE, MC_THREADS, emitSmemBytes(false), st>>>(m, map, V, nullptr, S, P, N, nullptr);
+    }
+    ++c->launches;
 }
 
 int mms_emit_isosurface(mms_ctx* c, float* pos, float* nrm, float* col, uint64_t first_triangle) {
@@ -1384,14 +1410,10 @@ int mms_emit_isosurface(mms_ctx* c, float* pos, float* nrm, float* col, uint64_t
                 if (tma) v4::mc_emit_v4_kernel<false, true><<<g4, MC_THREADS, emitV4SmemBytes(false), st>>>(m, map, V, nullptr, S, P, N, nullptr);
                 else v4::mc_emit_v4_kernel<false, false><<<g4, MC_THREADS, emitV4SmemBytes(false), st>>>(m, map, V, nullptr, S, P, N, nullptr);
             }
-        } else if (c->haveColour) {
-            if (tma) mc_emit_kernel<true, true><<<gridE, MC_THREADS, emitSmemBytes(true), st>>>(m, map, V, RGB, S, P, N, C);
-            else mc_emit_kernel<true, false><<<gridE, MC_THREADS, emitSmemBytes(true), st>>>(m, map, V, RGB, S, P, N, C);
+            ++c->launches;
         } else {
-            if (tma) mc_emit_kernel<false, true><<<gridE, MC_THREADS, emitSmemBytes(false), st>>>(m, map, V, nullptr, S, P, N, nullptr);
-            else mc_emit_kernel<false, false><<<gridE, MC_THREADS, emitSmemBytes(false), st>>>(m, map, V, nullptr, S, P, N, nullptr);
+            launchMcEmit(c, P, N, C, 0xffffffffu);
         }
-        ++c->launches;
     }
     c->rec(EV_MC1);
     MMS_CUDA(c, cudaGetLastError());
@@ -1410,7 +1432,34 @@ int mms_set_isosurface_mode(mms_ctx* c, int32_t mode) {
 }
 
 int mms_extract_isosurface(mms_ctx* c, float iso) {
-    if (int rc = mms_count_isosurface(c, iso, nullptr)) return rc;
+    if (!c) return MMS_ERR_INVALID;
+    if (int rc = countLaunch(c, iso)) return rc;
+    // Speculative emission: the only thing the host needs the triangle count for is the SIZE of the mesh buffers.  Where buffers of an
+    // earlier frame exist (steady state of a time series; they keep 1/8 headroom), the emit kernel is launched right behind the count
+    // and the scan, with the buffers' capacity as its limit, and the host round trip leaves the GPU's critical path; only a frame that
+    // outgrows the buffers is emitted again after growing them.
+    uint64_t capTris = std::min(c->meshPos.cap, c->meshNrm.cap) / 36;
+    if (c->haveColour) capTris = std::min<uint64_t>(capTris, c->meshCol.cap / 36);
+    const bool speculate = c->countPending && !c->countIndexed && c->countMode == MMS_ISO_MARCHING_CUBES && capTris > 0 && !getenv("MMS_EMIT_V4") &&
+                           !getenv("MMS_NO_SPECULATION");
+    if (speculate) {
+        DeviceGuard guard(c->device);
+        c->rec(EV_EMIT0);
+        launchMcEmit(c, c->meshPos.as<float>(), c->meshNrm.as<float>(), c->haveColour ? c->meshCol.as<float>() : nullptr,
+            static_cast<unsigned>(std::min<uint64_t>(capTris, 0xffffffffull)));
+        c->rec(EV_MC1);
+    }
+    if (int rc = countFinish(c, nullptr)) return rc;
+    if (speculate && c->ntris <= capTris) {
+        MMS_CUDA(c, cudaGetLastError());
+        c->haveMesh = true;
+        c->meshExternal = false;
+        return MMS_OK;
+    }
+    if (speculate) { // the frame outgrew the buffers: the truncated emission must have left them before they are re-allocated
+        DeviceGuard guard(c->device);
+        MMS_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
     return mms_emit_isosurface(c, nullptr, nullptr, nullptr, 0);
 }
 

@@ -485,12 +485,11 @@ class SlabJob:
             s.prefetch_density()
         if extract:
             if self.world > 1 and self.gather == "host" and not self.protein:
-                # the triangle count is on the host after the count half: the emit kernel is launched first, then the count's all-gather
+                # the library launches the emit kernel speculatively right behind the count (mms_extract_isosurface); the count's all-gather
                 # goes to a side stream and runs under it (the side stream has nothing to wait for: the count comes from the host, and the
                 # previous frame's readers of the gathered counts have been joined)
-                ntris = s.count_isosurface(self.iso)
-                s.emit_isosurface()
-                self._allgather_counts(ntris)
+                s.extract_isosurface(self.iso)  # (returns once the count is on the host; the emit kernel is already running behind it)
+                self._allgather_counts(s.mesh_device()[0] // 3)
             else:
                 s.extract_isosurface(self.iso)
 
