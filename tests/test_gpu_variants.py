@@ -86,3 +86,42 @@ def test_prefetched_volume_copy_equals_plain_copy():
         s.close()
     assert np.array_equal(out[0][0].view(np.uint32), out[1][0].view(np.uint32)) and np.array_equal(out[0][1], out[1][1])
     assert out[0][0].max() == 1.0 and out[0][1].shape[0] > 1000
+
+
+def test_speculative_emit_regrows_and_matches_the_plain_path():
+    """mms_extract_isosurface launches the emit kernel behind the count with the EXISTING mesh buffers' capacity as its limit; a frame
+    whose mesh outgrows them is emitted again after growing them.  Sequence small -> large -> small -> large on one context, every mesh
+    bit-identical to the one a fresh context produces without speculation (MMS_NO_SPECULATION, a debug knob)."""
+    n, res = 150_000, (96, 80, 64)
+    box = tuple(float(np.float32(r - 1) * np.float32(0.4563)) for r in res)
+    xyz = synth.uniform_box(n, 1.0) * np.asarray(box, np.float32)
+
+    def fresh(iso):
+        os.environ["MMS_NO_SPECULATION"] = "1"
+        try:
+            s = mm.Surf(0)
+            s.set_grid((0, 0, 0), box, res, (True, True, True))
+            s.set_params(mode=0, aggregator=0, normalize=1, sigma=1.0)
+            s.push_particles([dict(vtx=xyz, vtx_type=1, count=n, global_radius=0.5)])
+            s.compute_density()
+            s.extract_isosurface(iso)
+            pos, nrm = s.get_mesh()
+            s.close()
+            return pos.copy(), nrm.copy()
+        finally:
+            os.environ.pop("MMS_NO_SPECULATION", None)
+
+    isos = (0.9, 0.3, 0.95, 0.2, 0.2)   # few triangles, many (outgrows the buffers), few (fits easily), more again, same again
+    want = {iso: fresh(iso) for iso in set(isos)}
+    assert want[0.2][0].shape[0] > 1.5 * want[0.3][0].shape[0] > 3 * want[0.9][0].shape[0] > 0
+    s = mm.Surf(0)
+    s.set_grid((0, 0, 0), box, res, (True, True, True))
+    s.set_params(mode=0, aggregator=0, normalize=1, sigma=1.0)
+    s.push_particles([dict(vtx=xyz, vtx_type=1, count=n, global_radius=0.5)])
+    s.compute_density()
+    for iso in isos:
+        s.extract_isosurface(iso)
+        pos, nrm = s.get_mesh()
+        assert pos.shape == want[iso][0].shape, iso
+        assert np.array_equal(pos, want[iso][0]) and np.array_equal(nrm, want[iso][1]), iso
+    s.close()
