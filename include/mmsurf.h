@@ -240,10 +240,12 @@ int mms_route_particles(mms_ctx* ctx, const mms_list* list, int32_t nslabs, cons
  * frame with one kernel (halo_push_kernel: ballot-aggregated system-scope atomics over NVLink).  Per frame and slab:
  *     mms_clear_particles, mms_push_particles(own share)           (as always)
  *     mms_halo_push(...)                                           one kernel per pushed list + one signal kernel; no host wait
- *     mms_halo_wait(ctx, npeers)                                   stream-ordered: returns at once, the STREAM waits until `npeers` slabs have
- *                                                                  signalled that their records of this frame have landed (a spinning
- *                                                                  one-thread kernel on a flag in this GPU's memory: no collective, no host;
- *                                                                  inside one process CUDA events do the same and the call is not needed)
+ *     mms_halo_wait(ctx, npeers)                                   stream-ordered: returns at once; before mms_compute_density reads the
+ *                                                                  received list, the STREAM waits until `npeers` slabs have signalled that
+ *                                                                  their records of this frame have landed (a spinning one-thread kernel
+ *                                                                  on a flag in this GPU's memory, placed behind the binning of the
+ *                                                                  context's own lists: no collective, no host; inside one process CUDA
+ *                                                                  events do the same and the call is not needed)
  *     mms_halo_receive(ctx, radius_bound)                          the received records become one more list; its LENGTH stays on the device
  *     mms_compute_density ...
  * Counters and buffer halves alternate between two sets per frame: a slab clears the counters of the NEXT frame when it signals this one,

@@ -279,6 +279,7 @@ struct mms_ctx {
     DevBuf haloBuf, haloCounters; // mms_halo_*: receive buffer (float4 records) and counter block of this slab
     uint64_t haloCap = 0;
     unsigned haloFrame = 0;       // parity selects the counter word of the current frame
+    int haloWaitPeers = -1;       // mms_halo_wait: arrivals the stream has to see before the received list is read (-1: nothing pending)
     PinBuf hRoute;
     DevBuf cellCount, cellStart, cursor, tileSums, recsA, recsB, auxA, auxB, vol, rgb, segCount, segOffset, meshPos, meshNrm,
         meshCol, triCount, home, dstate, dirVol, rmaxBuf, bigCells, s3Tables, vertCount, vertOffset, vertRec, meshIdx, cellOf;
@@ -872,6 +873,12 @@ int mms_compute_density(mms_ctx* c) {
     MMS_CUDA(c, cudaMemsetAsync(c->cellCount.p, 0, ncells * 4, st));
     const int cap = c->smCount * 16;
     for (const ListDev& l : c->lists) {
+        if (l.countPtr && c->haloWaitPeers >= 0) { // the received halo list: its records and its length must have arrived (mms_halo_wait)
+            halo_wait_kernel<<<1, 1, 0, st>>>(c->haloCounters.as<unsigned>() + 2 + (c->haloFrame & 1u), static_cast<unsigned>(c->haloWaitPeers),
+                c->haloCounters.as<unsigned>() + (c->haloFrame & 1u));
+            ++c->launches;
+            c->haloWaitPeers = -1;
+        }
         bin_count_kernel<<<gridFor(l.count, 256, cap), 256, 0, st>>>(g, l, c->cellCount.as<unsigned>(), c->dstate.as<DevState>(), homeOut, c->cellOf.as<int>());
         ++c->launches;
     }
@@ -1719,11 +1726,9 @@ int mms_halo_push(mms_ctx* c, int32_t nslabs, int32_t mine, const int32_t* plane
 int mms_halo_wait(mms_ctx* c, int32_t npeers) {
     if (!c || npeers < 0) return MMS_ERR_INVALID;
     if (!c->haloCounters.p || !c->haloCap) return c->fail(MMS_ERR_INVALID, "mms_halo_buffers has not been called");
-    DeviceGuard guard(c->device);
-    halo_wait_kernel<<<1, 1, 0, c->stream>>>(c->haloCounters.as<unsigned>() + 2 + (c->haloFrame & 1u), static_cast<unsigned>(npeers),
-        c->haloCounters.as<unsigned>() + (c->haloFrame & 1u));
-    ++c->launches;
-    MMS_CUDA(c, cudaGetLastError());
+    // deferred: the wait kernel goes into the stream right before the first kernel that READS the received list (mms_compute_density
+    // bins the context's own lists first), so the wait for the slowest neighbour hides behind work that does not need its records
+    c->haloWaitPeers = npeers;
     return MMS_OK;
 }
 
