@@ -59,6 +59,7 @@ struct McGeo {
     float org[3], sd[3];
     float rinv[3][3];  // rinv[a][n] = 1/(n*sd[a]), n = 1, 2 (gradient: one-sided / central)
     float iso;
+    int layersPerBlock; // mc_emit_kernel: cell layers a block marches (<= EM_LAYERS; fewer on small volumes, so that the grid fills the machine)
     unsigned maxTris;  // mc_emit_kernel: cell rows whose triangles end beyond this many are skipped (speculative launch before the count is
                        // known on the host: the destination's capacity; 0xffffffff otherwise)
 };
@@ -75,7 +76,7 @@ constexpr int CN_WORDS = CN_SEGS + 1;       // mask words per node row: 16 segme
 constexpr int CN_NROWS = CN_ROWS + 1;       // node rows per plane
 
 __global__ void __launch_bounds__(MC_THREADS) mc_count_kernel(McGeo m, const float* __restrict__ vol, unsigned* __restrict__ segCount,
-    unsigned char* __restrict__ triCount) {
+    unsigned char* __restrict__ triCount, uint4* __restrict__ vrec, unsigned* __restrict__ vcount) {
     __shared__ unsigned sMask[3][CN_NROWS][CN_WORDS];
     __shared__ unsigned char sCount[256];
     sCount[threadIdx.x] = static_cast<unsigned char>(kCasePerm.w[threadIdx.x] & 15ull);
@@ -145,6 +146,17 @@ __global__ void __launch_bounds__(MC_THREADS) mc_count_kernel(McGeo m, const flo
                 if (tc) tc[b] = static_cast<unsigned char>(k);
             }
             segCount[xseg + static_cast<size_t>(m.nsegx) * (y + static_cast<size_t>(m.cy) * (cz - m.cz0))] = n;
+            if (vrec) {
+                // indexed mesh (mc_indexed.cuh): the mask record of node row (y, cz), segment xseg -- the bits are all here already.
+                // Nodes beyond the grid are clamped copies, so an x-edge that leaves the grid is never crossed; y- and z-edges of
+                // such copies are masked.  (The last node row / plane / a lone last node segment have no cell row: mcx_mask_kernel.)
+                const int nvx = m.sx - xseg * 32;
+                const unsigned nodeValid = nvx >= 32 ? 0xffffffffu : (1u << nvx) - 1u;
+                const unsigned mx = a0 ^ a0s, my = (a0 ^ b0) & nodeValid, mz = (a0 ^ c0) & nodeValid;
+                const size_t sv = xseg + static_cast<size_t>((m.sx + 31) >> 5) * (y + static_cast<size_t>(m.sy) * cz);
+                vrec[sv] = make_uint4(a0, mx, my, mz);
+                vcount[sv] = __popc(mx) + __popc(my) + __popc(mz);
+            }
         }
     }
 }
@@ -263,8 +275,8 @@ __global__ void __launch_bounds__(MC_THREADS, COLOUR ? 2 : 4) mc_emit_kernel(McG
     McEmitShared& sh = *reinterpret_cast<McEmitShared*>(smemAligned);
     float4* recCol = reinterpret_cast<float4*>(smemAligned + sizeof(McEmitShared)); // COLOUR only
     const int x0 = blockIdx.x * EX, y0 = blockIdx.y * EY;
-    const int zcBeg = m.cz0 + blockIdx.z * EM_LAYERS;                      // first global cell layer (= node plane) of this block
-    const int nLayers = min(EM_LAYERS, m.cz0 + m.cnz - zcBeg);
+    const int zcBeg = m.cz0 + blockIdx.z * m.layersPerBlock;               // first global cell layer (= node plane) of this block
+    const int nLayers = min(m.layersPerBlock, m.cz0 + m.cnz - zcBeg);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     // ---- the block's cell rows: first triangle, triangle count, which layers have any (one global read per row) ---------

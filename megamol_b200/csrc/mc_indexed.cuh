@@ -11,8 +11,10 @@
 //                                                            + (a >= 1 ? mx_i : 0) + (a == 2 ? my_i : 0)
 //                      with mx/my/mz the segment's crossing masks -- any kernel that knows the "below iso" bits around a cell can name
 //                      the vertex of each of its edges without a search or a hash.
-//   mcx_mask_kernel    a warp per node segment: "below iso" bits and the three crossing masks (one 16-byte record per segment: the later
-//                      kernels never touch the volume again to classify) and the segment's crossing count (-> exclusive scan = vertOffset)
+//   mask records       per node segment the "below iso" bits and the three crossing masks (one 16-byte record: the later kernels never touch
+//                      the volume again to classify) and the segment's crossing count (-> exclusive scan = vertOffset).  mc_count_kernel
+//                      has all these bits in its registers and writes the records as a by-product; mcx_mask_kernel (a warp per node
+//                      segment) only serves the node rows without a cell row: the last row, the last plane, a lone last segment
 //   mcx_vertex_kernel  a warp per node segment: its crossings, compacted in vertex order, are evaluated by full lanes with exactly the
 //                      arithmetic of mc_emit_kernel's V stage (gradient normal by central differences clamped at the global border,
 //                      SFU reciprocal for the interpolation parameter): position and normal are BIT-IDENTICAL to the soup's corners;
@@ -30,12 +32,17 @@ constexpr int MCX_WARPS = MCX_THREADS / 32;
 
 /** Node segments: nsv = ceil(sx / 32) per node row, sy rows, sz planes.  rec[s] = {below, mx, my, mz}: bit i <=> node 32 xs + i is below
  *  the iso value / its x-, y-, z-edge (towards the next node) is crossed; vcount[s] = crossed edges owned by the segment's nodes. */
-__global__ void __launch_bounds__(MCX_THREADS) mcx_mask_kernel(McGeo m, const float* __restrict__ vol, uint4* __restrict__ rec,
+struct McxRange { // node segments [xs0, xs0 + gridDim.x), node rows [y0, y1), planes [z0, z0 + gridDim.z)
+    int xs0, y0, y1, z0;
+};
+/** mc_count_kernel writes the records of every node row that is the low row of a cell row (y < sy-1, z < sz-1, segments that hold a
+ *  cell); this kernel serves the rest: the last node row, the last plane and a lone last node segment (sx = 32 k + 1). */
+__global__ void __launch_bounds__(MCX_THREADS) mcx_mask_kernel(McGeo m, McxRange rg, const float* __restrict__ vol, uint4* __restrict__ rec,
     unsigned* __restrict__ vcount) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nsv = (m.sx + 31) >> 5;
-    const int xs = blockIdx.x, y = blockIdx.y * MCX_WARPS + warp, z = blockIdx.z;
-    if (y >= m.sy) return;
+    const int xs = rg.xs0 + blockIdx.x, y = rg.y0 + blockIdx.y * MCX_WARPS + warp, z = rg.z0 + blockIdx.z;
+    if (y >= rg.y1) return;
     const int x = xs * 32 + lane;
     const bool valid = x < m.sx;
     const int xc = min(x, m.sx - 1);

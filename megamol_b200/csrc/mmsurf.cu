@@ -1228,6 +1228,7 @@ static int countLaunch(mms_ctx* c, float iso) {
     }
     m.iso = iso;
     m.maxTris = 0xffffffffu;
+    m.layersPerBlock = EM_LAYERS;
     c->mcGeo = m;
     c->ntris = 0;
     c->haveCount = false; // set once the count has run and the device reported no error
@@ -1268,7 +1269,14 @@ static int countLaunch(mms_ctx* c, float iso) {
     } else {
         if (tri) MMS_CUDA(c, cudaMemsetAsync(tri, 0, static_cast<size_t>(m.cx) * m.cy * m.cnz, st)); // the kernel writes the non-empty cells only
         dim3 grid((m.nsegx + CN_SEGS - 1) / CN_SEGS, (m.cy + CN_ROWS - 1) / CN_ROWS, (m.cnz + CN_LAYERS - 1) / CN_LAYERS);
-        mc_count_kernel<<<grid, MC_THREADS, 0, st>>>(m, c->isoVol(), c->segCount.as<unsigned>(), tri);
+        // indexed mesh: the count kernel writes the node segments' mask records as a by-product (validated and allocated below)
+        const bool ix = c->meshIndexed && !c->haveColour && c->z0 == 0 && c->nz == c->grid.res[2] && m.cz0 == 0 && m.cnz == c->grid.res[2] - 1 &&
+                        static_cast<long long>(m.sx) * m.sy < (1ll << 31);
+        const size_t nvs = static_cast<size_t>((m.sx + 31) / 32) * m.sy * m.szGlobal;
+        if (ix && (nvs >= (1ull << 32) - 1 || !c->vertCount.ensure(nvs * 4) || !c->vertOffset.ensure((nvs + 1) * 4) || !c->vertRec.ensure(nvs * 16)))
+            return c->fail(MMS_ERR_NOMEM, "device allocation failed (vertex segments)");
+        mc_count_kernel<<<grid, MC_THREADS, 0, st>>>(m, c->isoVol(), c->segCount.as<unsigned>(), tri, ix ? c->vertRec.as<uint4>() : nullptr,
+            ix ? c->vertCount.as<unsigned>() : nullptr);
     }
     ++c->launches;
     DevState* ds = c->dstate.as<DevState>();
@@ -1287,9 +1295,25 @@ static int countLaunch(mms_ctx* c, float iso) {
         const unsigned vtiles = static_cast<unsigned>((nvs + kScanTile - 1) / kScanTile);
         if (!c->vertCount.ensure(nvs * 4) || !c->vertOffset.ensure((nvs + 1) * 4) || !c->vertRec.ensure(nvs * 16) || !c->tileSums.ensure(std::max<size_t>(std::max(ntiles, vtiles), 1) * 4))
             return c->fail(MMS_ERR_NOMEM, "device allocation failed (vertex segments)");
-        dim3 gv((m.sx + 31) / 32, (m.sy + MCX_WARPS - 1) / MCX_WARPS, m.szGlobal);
-        mcx_mask_kernel<<<gv, MCX_THREADS, 0, st>>>(m, c->isoVol(), c->vertRec.as<uint4>(), c->vertCount.as<unsigned>());
-        ++c->launches;
+        // the node rows without a cell row (mc_count_kernel has written all the others): last row, last plane, a lone last segment
+        const int nsvI = (m.sx + 31) / 32;
+        {
+            const McxRange lastRow{0, m.sy - 1, m.sy, 0};
+            mcx_mask_kernel<<<dim3(nsvI, 1, m.szGlobal), MCX_THREADS, 0, st>>>(m, lastRow, c->isoVol(), c->vertRec.as<uint4>(), c->vertCount.as<unsigned>());
+            ++c->launches;
+            if (m.sy > 1) {
+                const McxRange lastPlane{0, 0, m.sy - 1, m.szGlobal - 1};
+                mcx_mask_kernel<<<dim3(nsvI, (m.sy - 1 + MCX_WARPS - 1) / MCX_WARPS, 1), MCX_THREADS, 0, st>>>(m, lastPlane, c->isoVol(), c->vertRec.as<uint4>(),
+                    c->vertCount.as<unsigned>());
+                ++c->launches;
+            }
+            if (nsvI > m.nsegx && m.sy > 1 && m.szGlobal > 1) {
+                const McxRange lastSeg{nsvI - 1, 0, m.sy - 1, 0};
+                mcx_mask_kernel<<<dim3(1, (m.sy - 1 + MCX_WARPS - 1) / MCX_WARPS, m.szGlobal - 1), MCX_THREADS, 0, st>>>(m, lastSeg, c->isoVol(),
+                    c->vertRec.as<uint4>(), c->vertCount.as<unsigned>());
+                ++c->launches;
+            }
+        }
         exclusiveScan(c->vertCount.as<unsigned>(), c->vertOffset.as<unsigned>(), nullptr, c->tileSums.as<unsigned>(), static_cast<unsigned>(nvs),
             &ds->totalVerts, st, c->launches);
         c->countIndexed = true;
@@ -1331,7 +1355,12 @@ static void launchMcEmit(mms_ctx* c, float* P, float* N, float* C, unsigned maxT
     McGeo m = c->mcGeo;
     m.maxTris = maxTris;
     cudaStream_t st = c->stream;
-    const dim3 gridE(m.nsegx, (m.cy + EY - 1) / EY, (m.cnz + EM_LAYERS - 1) / EM_LAYERS);
+    // a block marches up to EM_LAYERS cell layers; on small volumes fewer, until the grid holds two waves of blocks (4 per SM)
+    int L = EM_LAYERS;
+    const long long columns = static_cast<long long>(m.nsegx) * ((m.cy + EY - 1) / EY);
+    while (L > 8 && columns * ((m.cnz + L - 1) / L) < 8ll * c->smCount) L /= 2;
+    m.layersPerBlock = L;
+    const dim3 gridE(m.nsegx, (m.cy + EY - 1) / EY, (m.cnz + L - 1) / L);
     CUtensorMap map{};
     const bool tma = makeVolumeTensorMap(&map, c->isoVol(), m.sx, m.sy, m.nzPlanes);
     const float* V = c->isoVol();
@@ -1391,7 +1420,6 @@ int mms_emit_isosurface(mms_ctx* c, float* pos, float* nrm, float* col, uint64_t
             P += first_triangle * 9, N += first_triangle * 9;
             if (C) C += first_triangle * 9;
         }
-        dim3 gridE(m.nsegx, (m.cy + EY - 1) / EY, (m.cnz + EM_LAYERS - 1) / EM_LAYERS);
         c->rec(EV_EMIT0);
         if (c->countMode == MMS_ISO_MARCHING_TETS) {
             dim3 grid(m.nsegx, (m.cy + MT_THREADS / 32 - 1) / (MT_THREADS / 32), m.cnz);
