@@ -642,8 +642,12 @@ class SlabJob:
             import json, os
             with open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "traffic.json")) as f:
                 t = json.load(f)
-            if self.w.get("kind") == "lj" and self.world == 1:
-                traffic = t["c2"].get(name)
+            # (the committed captures are of the C2 frame per GPU -- the weak-scaled slabs run the same kernels on the same amount of
+            #  work -- and of C3; the C2 frame uses the warp-tile splat kernel)
+            if self.w.get("kind") == "lj" and not self.w.get("fixed_total") and abs(self.radius - 0.5) < 1e-6:
+                traffic = t["c2"].get(name) or t["c2"].get(name.replace("density_splat_kernel", "density_splat3_kernel"))
+            elif self.protein:
+                traffic = t["c3"].get(name)
         except Exception:
             pass
         stages = {"bin (count+scan+scatter+order)": (stage["bin"], b["bin"]), dens: (stage["density"], b["density"]),
@@ -657,7 +661,7 @@ class SlabJob:
             fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12
             tf = pairs * 19 / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
             sfu = pairs / (ms * 1e-3) / (148 * 16 * 1.965e9) if ms > 0 else 0.0
-            return {"bound": "fp32", "kernel": name, "achieved": tf, "peak": fp32_peak, "unit": "TFLOP/s", "frac": tf / fp32_peak, "traffic": None,
+            return {"bound": "fp32", "kernel": name, "achieved": tf, "peak": fp32_peak, "unit": "TFLOP/s", "frac": tf / fp32_peak, "traffic": traffic,
                     "peak_source": "nominal FP32 FMA peak (148 SMs x 128 lanes x 2 x 1.965 GHz); MEASURED_PEAKS.json holds no FP32 figure",
                     "algorithmic_flops": pairs * 19, "useful_pairs": pairs, "fp32_ops_per_pair": 13, "flops_per_pair": 19,
                     "issue_slot_frac": pairs * 13 / (ms * 1e-3) / (148 * 128 * 1.965e9) if ms > 0 else 0.0,
