@@ -143,6 +143,24 @@ class Harness:
         if rc:
             raise RuntimeError(f"mmh_set_molecule rc={rc}")
 
+    def set_molecule_structure(self, bfactor=None, atoms_per_residue=0, residues_per_molecule=0, molecules_per_chain=0):
+        """optional B-factors [n] and a synthetic structure of equal-sized residues / molecules / chains (after set_molecule)"""
+        bf = None if bfactor is None else np.ascontiguousarray(bfactor, np.float32)
+        self.lib.mmh_set_molecule_structure.argtypes = [C.c_void_p, C.c_void_p, C.c_uint, C.c_uint, C.c_uint]
+        if self.lib.mmh_set_molecule_structure(self.h, None if bf is None else bf.ctypes.data, int(atoms_per_residue), int(residues_per_molecule),
+                                               int(molecules_per_chain)):
+            raise RuntimeError("mmh_set_molecule_structure failed")
+
+    def molecule_colour_table(self, natoms, mode0, mode1, weight, grad):
+        """the unmodified reference's ProteinColor::MakeWeightedColorTable for the molecule source's atoms -> [n, 3] float32"""
+        g = np.ascontiguousarray(grad, np.float32).reshape(9)
+        out = np.empty((natoms, 3), np.float32)
+        self.lib.mmh_molecule_colour_table.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p]
+        n = self.lib.mmh_molecule_colour_table(self.h, int(mode0), int(mode1), float(weight), g.ctypes.data, out.ctypes.data)
+        if n != natoms:
+            raise RuntimeError(f"mmh_molecule_colour_table returned {n} atoms")
+        return out
+
     def set_p2d_params(self, res, cyclic=(True, True, True), normalize=True, sigma=1.0, aggregator=0,
                        for_surface=False):
         self.res = tuple(int(r) for r in res)

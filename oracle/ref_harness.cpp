@@ -40,6 +40,7 @@
 #include "mmcore/param/ParamSlot.h"
 #include "mmcore/utility/log/Log.h"
 #include "protein_calls/MolecularDataCall.h"
+#include "protein_calls/ProteinColor.h"
 #include "trisoup/volumetrics/MarchingCubeTables.h"
 
 #ifdef MMH_B200
@@ -148,8 +149,28 @@ public:
     std::vector<float> pos;
     std::vector<unsigned> typeIdx;
     std::vector<protein_calls::MolecularDataCall::AtomType> types;
+    std::vector<float> bfactor; // optional (B-factor colouring)
+    // optional synthetic structure (chain / molecule / residue colouring): equal-sized residues, molecules, chains
+    std::vector<protein_calls::MolecularDataCall::Residue> residues;
+    std::vector<const protein_calls::MolecularDataCall::Residue*> residuePtrs;
+    std::vector<protein_calls::MolecularDataCall::Molecule> molecules;
+    std::vector<protein_calls::MolecularDataCall::Chain> chains;
+    std::vector<vislib::StringA> residueTypeNames;
     float bbox[6] = {0, 0, 0, 1, 1, 1};
     size_t hash = 1;
+
+    /** What getData puts into a call (also used to fill a local call for the expected colour table). */
+    void fill(protein_calls::MolecularDataCall& m) {
+        m.SetAtoms(static_cast<unsigned>(typeIdx.size()), static_cast<unsigned>(types.size()), typeIdx.data(), pos.data(), types.data(),
+            nullptr, bfactor.empty() ? nullptr : bfactor.data(), nullptr, nullptr);
+        if (!bfactor.empty()) m.SetBFactorRange(*std::min_element(bfactor.begin(), bfactor.end()), *std::max_element(bfactor.begin(), bfactor.end()));
+        if (!chains.empty()) {
+            m.SetResidueTypeNames(static_cast<unsigned>(residueTypeNames.size()), residueTypeNames.data());
+            m.SetResidues(static_cast<unsigned>(residuePtrs.size()), residuePtrs.data());
+            m.SetMolecules(static_cast<unsigned>(molecules.size()), molecules.data());
+            m.SetChains(static_cast<unsigned>(chains.size()), chains.data());
+        }
+    }
 
 protected:
     bool create() override { return true; }
@@ -171,8 +192,7 @@ private:
         auto* m = dynamic_cast<protein_calls::MolecularDataCall*>(&c);
         if (!m) return false;
         m->SetDataHash(hash);
-        m->SetAtoms(static_cast<unsigned>(typeIdx.size()), static_cast<unsigned>(types.size()), typeIdx.data(), pos.data(), types.data(),
-            nullptr, nullptr, nullptr, nullptr);
+        fill(*m);
         m->SetUnlocker(nullptr);
         return true;
     }
@@ -331,6 +351,58 @@ int mmh_set_molecule(void* hv, unsigned natoms, const float* pos, const unsigned
     std::memcpy(m.bbox, bbox, sizeof(float) * 6);
     ++m.hash;
     return 0;
+}
+
+/** Optional extras of the molecule source: B-factors (NULL: none) and a synthetic structure of equal-sized residues / molecules / chains
+ *  (atoms_per_residue == 0: none).  Call after mmh_set_molecule. */
+int mmh_set_molecule_structure(void* hv, const float* bfactor, unsigned atoms_per_residue, unsigned residues_per_molecule, unsigned molecules_per_chain) {
+    auto* h = static_cast<Harness*>(hv);
+    auto& m = *h->mol;
+    using MDC = protein_calls::MolecularDataCall;
+    const unsigned n = static_cast<unsigned>(m.typeIdx.size());
+    m.bfactor.clear();
+    if (bfactor) m.bfactor.assign(bfactor, bfactor + n);
+    m.residues.clear(), m.residuePtrs.clear(), m.molecules.clear(), m.chains.clear();
+    m.residueTypeNames = {vislib::StringA("ALA"), vislib::StringA("GLY"), vislib::StringA("SOL"), vislib::StringA("LYS"), vislib::StringA("TOL")};
+    if (atoms_per_residue && residues_per_molecule && molecules_per_chain && n) {
+        const unsigned nres = (n + atoms_per_residue - 1) / atoms_per_residue;
+        const unsigned nmol = (nres + residues_per_molecule - 1) / residues_per_molecule;
+        const unsigned nchain = (nmol + molecules_per_chain - 1) / molecules_per_chain;
+        m.residues.reserve(nres);
+        for (unsigned r = 0; r < nres; ++r) {
+            const unsigned first = r * atoms_per_residue, cnt = std::min(atoms_per_residue, n - first);
+            m.residues.emplace_back(first, cnt, vislib::math::Cuboid<float>(0, 0, 0, 1, 1, 1), r % 5u, static_cast<int>(r / residues_per_molecule), r);
+        }
+        for (auto& r : m.residues) m.residuePtrs.push_back(&r);
+        for (unsigned k = 0; k < nmol; ++k) {
+            const unsigned first = k * residues_per_molecule, cnt = std::min(residues_per_molecule, nres - first);
+            m.molecules.emplace_back(first, cnt, static_cast<int>(k / molecules_per_chain));
+        }
+        for (unsigned c = 0; c < nchain; ++c) {
+            const unsigned first = c * molecules_per_chain, cnt = std::min(molecules_per_chain, nmol - first);
+            m.chains.emplace_back(first, cnt, static_cast<char>('A' + c % 26));
+        }
+    }
+    ++m.hash;
+    return 0;
+}
+
+/** The colour table the UNMODIFIED reference code (protein_calls::ProteinColor::MakeWeightedColorTable, what QuickSurf.cpp:596-616 calls)
+ *  makes for the molecule source's atoms: the expectation the drop-in module's colours are checked against.  grad = min, mid, max gradient
+ *  colours (3 x RGB); out = 3 floats per atom. */
+int mmh_molecule_colour_table(void* hv, int mode0, int mode1, float weight, const float grad[9], float* out) {
+    auto* h = static_cast<Harness*>(hv);
+    using protein_calls::ProteinColor;
+    protein_calls::MolecularDataCall call;
+    h->mol->fill(call);
+    std::vector<glm::vec3> table, fileTable, rainbow;
+    ProteinColor::ReadColorTableFromFile(std::string("colors.txt"), fileTable);
+    ProteinColor::MakeRainbowColorTable(100, rainbow);
+    const std::vector<glm::vec3> lookup = {glm::make_vec3(grad), glm::make_vec3(grad + 3), glm::make_vec3(grad + 6)};
+    ProteinColor::MakeWeightedColorTable(call, static_cast<ProteinColor::ColoringMode>(mode0), static_cast<ProteinColor::ColoringMode>(mode1), weight,
+        1.0 - weight, table, lookup, fileTable, rainbow, nullptr, nullptr, true);
+    for (size_t i = 0; i < table.size(); ++i) out[3 * i] = table[i].r, out[3 * i + 1] = table[i].g, out[3 * i + 2] = table[i].b;
+    return static_cast<int>(table.size());
 }
 
 /** Replaces the source's particle lists; bumps the data hash so that consumers recompute. */

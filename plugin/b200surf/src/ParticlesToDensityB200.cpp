@@ -16,6 +16,8 @@
 
 #include "datatools/table/TableDataCall.h"
 #include "mmcore/param/BoolParam.h"
+#include "mmcore/param/ColorParam.h"
+#include "mmcore/param/FilePathParam.h"
 #include "mmcore/param/EnumParam.h"
 #include "mmcore/param/FloatParam.h"
 #include "mmcore/param/IntParam.h"
@@ -57,6 +59,13 @@ ParticlesToDensityB200::ParticlesToDensityB200()
         , qsQualitySlot("quicksurf::quality", "Quality: 0 low .. 3 ultra (Gaussian cut-off 2.0/2.5/3.0/4.0 sigma)")
         , qsRadScaleSlot("quicksurf::radiusScale", "Radius scale")
         , qsColourSlot("quicksurf::colour", "Also build the density-weighted colour volume (coloured isosurface)")
+        , colorTableFileSlot("color::colorTableFilename", "Path to the file containing a custom color table")
+        , coloringMode0Slot("color::coloringMode0", "The first coloring mode")
+        , coloringMode1Slot("color::coloringMode1", "The second coloring mode")
+        , coloringModeWeightSlot("color::colorWeighting", "Weighting factor between the two coloring modes")
+        , minGradColorSlot("color::minGradColor", "The color for the minimum value for gradient coloring")
+        , midGradColorSlot("color::midGradColor", "The color for the middle value for gradient coloring")
+        , maxGradColorSlot("color::maxGradColor", "The color for the maximum value for gradient coloring")
         , qsRefCellsSlot("quicksurf::referenceCandidates",
               "Sum over the candidate set of protein_cuda's QuickSurf (all atoms of the acceleration cells around a voxel's 8^3 block, no radial "
               "cut-off): the reference's density up to fp32 summation order, at ~15x the cost of the radial cut-off")
@@ -135,6 +144,34 @@ ParticlesToDensityB200::ParticlesToDensityB200()
     this->MakeSlotAvailable(&this->qsRadScaleSlot);
     this->qsColourSlot << new core::param::BoolParam(false);
     this->MakeSlotAvailable(&this->qsColourSlot);
+
+    // colouring of a molecule input: names, types and defaults of the reference QuickSurf module (QuickSurf.cpp:62-109)
+    using protein_calls::ProteinColor;
+    std::string filename("colors.txt");
+    ProteinColor::ReadColorTableFromFile(filename, this->fileColorTable); // (no such file: the built-in table, ProteinColor.cpp:64-75)
+    this->colorTableFileSlot.SetParameter(
+        new core::param::FilePathParam(filename, core::param::FilePathParam::FilePathFlags_::Flag_File_ToBeCreated));
+    this->MakeSlotAvailable(&this->colorTableFileSlot);
+    auto* cm0 = new core::param::EnumParam(static_cast<int>(ProteinColor::ColoringMode::CHAIN));
+    auto* cm1 = new core::param::EnumParam(static_cast<int>(ProteinColor::ColoringMode::ELEMENT));
+    for (int cCnt = 0; cCnt < static_cast<int>(ProteinColor::ColoringMode::MODE_COUNT); ++cCnt) {
+        const auto name = ProteinColor::GetName(static_cast<ProteinColor::ColoringMode>(cCnt));
+        cm0->SetTypePair(cCnt, name.c_str());
+        cm1->SetTypePair(cCnt, name.c_str());
+    }
+    this->coloringMode0Slot << cm0;
+    this->coloringMode1Slot << cm1;
+    this->MakeSlotAvailable(&this->coloringMode0Slot);
+    this->MakeSlotAvailable(&this->coloringMode1Slot);
+    this->coloringModeWeightSlot.SetParameter(new core::param::FloatParam(0.5f, 0.0f, 1.0f));
+    this->MakeSlotAvailable(&this->coloringModeWeightSlot);
+    this->minGradColorSlot.SetParameter(new core::param::ColorParam("#146496"));
+    this->MakeSlotAvailable(&this->minGradColorSlot);
+    this->midGradColorSlot.SetParameter(new core::param::ColorParam("#f0f0f0"));
+    this->MakeSlotAvailable(&this->midGradColorSlot);
+    this->maxGradColorSlot.SetParameter(new core::param::ColorParam("#ae3b32"));
+    this->MakeSlotAvailable(&this->maxGradColorSlot);
+    ProteinColor::MakeRainbowColorTable(100, this->rainbowColorTable);
     this->qsRefCellsSlot << new core::param::BoolParam(false);
     this->MakeSlotAvailable(&this->qsRefCellsSlot);
     this->qsGridSpacingSlot << new core::param::FloatParam(0.0f, 0.0f);
@@ -177,13 +214,16 @@ bool ParticlesToDensityB200::anythingDirty() const {
     return this->aggregatorSlot.IsDirty() || this->xResSlot.IsDirty() || this->yResSlot.IsDirty() || this->zResSlot.IsDirty() ||
            this->cyclXSlot.IsDirty() || this->cyclYSlot.IsDirty() || this->cyclZSlot.IsDirty() || this->normalizeSlot.IsDirty() ||
            this->sigmaSlot.IsDirty() || this->deviceSlot.IsDirty() || this->devicesSlot.IsDirty() || this->memLocSlot.IsDirty() || this->modeSlot.IsDirty() || this->qsQualitySlot.IsDirty() ||
-           this->qsRadScaleSlot.IsDirty() || this->qsColourSlot.IsDirty() || this->qsGridSpacingSlot.IsDirty() ||
+           this->qsRadScaleSlot.IsDirty() || this->qsColourSlot.IsDirty() || this->qsGridSpacingSlot.IsDirty() || this->colorTableFileSlot.IsDirty() ||
+           this->coloringMode0Slot.IsDirty() || this->coloringMode1Slot.IsDirty() || this->coloringModeWeightSlot.IsDirty() ||
+           this->minGradColorSlot.IsDirty() || this->midGradColorSlot.IsDirty() || this->maxGradColorSlot.IsDirty() ||
            this->qsRefCellsSlot.IsDirty();
 }
 
 void ParticlesToDensityB200::resetDirty() {
     for (auto* s : {&aggregatorSlot, &xResSlot, &yResSlot, &zResSlot, &cyclXSlot, &cyclYSlot, &cyclZSlot, &normalizeSlot, &sigmaSlot, &deviceSlot, &devicesSlot, &memLocSlot, &modeSlot,
-             &qsQualitySlot, &qsRadScaleSlot, &qsColourSlot, &qsGridSpacingSlot, &qsRefCellsSlot})
+             &qsQualitySlot, &qsRadScaleSlot, &qsColourSlot, &qsGridSpacingSlot, &qsRefCellsSlot, &coloringMode0Slot, &coloringMode1Slot,
+             &coloringModeWeightSlot, &minGradColorSlot, &midGradColorSlot, &maxGradColorSlot})
         s->ResetDirty();
 }
 
@@ -363,19 +403,55 @@ bool ParticlesToDensityB200::computeVolume(core::AbstractGetData3DCall* in) {
     auto* mpdc = dynamic_cast<MultiParticleDataCall*>(in);
     if (auto* mol = dynamic_cast<protein_calls::MolecularDataCall*>(in)) {
         // one FLOAT_XYZR list with interleaved FLOAT_RGBA colours, what QuickSurf::calculateSurface(MolecularDataCall&) assembles
-        // (QuickSurf.cpp:369-386); colour = the atom type's colour (MolecularDataCall.h:958), bytes / 255
+        // (QuickSurf.cpp:369-386)
         const size_t n = mol->AtomCount();
         if (n > 0 && (mol->AtomTypeCount() == 0 || mol->AtomPositions() == nullptr || mol->AtomTypeIndices() == nullptr)) {
             Log::DefaultLog.WriteError("ParticlesToDensityB200: MolecularDataCall without atom types or positions");
             return false;
         }
+        // the atoms' colours: the reference module's colour table (QuickSurf.cpp:596-616 -> ProteinColor::MakeWeightedColorTable, the
+        // UNMODIFIED protein_calls code): two colouring modes blended by color::colorWeighting.  A mode that walks the molecule's
+        // structure (chains / molecules / residues) on a call that carries none would index empty arrays in the reference; here it falls
+        // back to the element colours.
+        using protein_calls::ProteinColor;
+        if (this->colorTableFileSlot.IsDirty()) {
+            ProteinColor::ReadColorTableFromFile(this->colorTableFileSlot.Param<core::param::FilePathParam>()->Value(), this->fileColorTable);
+            this->colorTableFileSlot.ResetDirty();
+        }
+        const bool hasStructure = mol->ResidueCount() > 0 && mol->MoleculeCount() > 0 && mol->ChainCount() > 0 && mol->Residues() != nullptr &&
+                                  mol->ResidueTypeNameCount() > 0;
+        auto usable = [&](int m) {
+            const auto mode = static_cast<ProteinColor::ColoringMode>(m);
+            switch (mode) {
+            case ProteinColor::ColoringMode::ELEMENT:
+            case ProteinColor::ColoringMode::RAINBOW:
+            case ProteinColor::ColoringMode::HEIGHTMAP_COLOR:
+            case ProteinColor::ColoringMode::HEIGHTMAP_VALUE: return mode;
+            case ProteinColor::ColoringMode::BFACTOR: return mol->AtomBFactors() ? mode : ProteinColor::ColoringMode::ELEMENT;
+            case ProteinColor::ColoringMode::CHARGE: return mol->AtomCharges() ? mode : ProteinColor::ColoringMode::ELEMENT;
+            case ProteinColor::ColoringMode::OCCUPANCY: return mol->AtomOccupancies() ? mode : ProteinColor::ColoringMode::ELEMENT;
+            case ProteinColor::ColoringMode::BINDINGSITE:
+            case ProteinColor::ColoringMode::PER_ATOM_FLOAT: return ProteinColor::ColoringMode::ELEMENT; // need calls this module does not have
+            default: return hasStructure ? mode : ProteinColor::ColoringMode::ELEMENT;
+            }
+        };
+        const auto mode0 = usable(this->coloringMode0Slot.Param<core::param::EnumParam>()->Value());
+        const auto mode1 = usable(this->coloringMode1Slot.Param<core::param::EnumParam>()->Value());
+        const std::vector<glm::vec3> smallColorTable = {glm::make_vec3(this->minGradColorSlot.Param<core::param::ColorParam>()->Value().data()),
+            glm::make_vec3(this->midGradColorSlot.Param<core::param::ColorParam>()->Value().data()),
+            glm::make_vec3(this->maxGradColorSlot.Param<core::param::ColorParam>()->Value().data())};
+        const float weight = this->coloringModeWeightSlot.Param<core::param::FloatParam>()->Value();
+        if (n > 0)
+            ProteinColor::MakeWeightedColorTable(*mol, mode0, mode1, weight, 1.0 - weight, this->atomColorTable, smallColorTable, this->fileColorTable,
+                this->rainbowColorTable, nullptr, nullptr, true);
         this->atoms.resize(8 * n);
         for (size_t i = 0; i < n; ++i) {
             const auto& type = mol->AtomTypes()[mol->AtomTypeIndices()[i]];
             float* a = &this->atoms[8 * i];
             a[0] = mol->AtomPositions()[3 * i + 0], a[1] = mol->AtomPositions()[3 * i + 1], a[2] = mol->AtomPositions()[3 * i + 2];
             a[3] = type.Radius();
-            a[4] = type.Colour()[0] / 255.0f, a[5] = type.Colour()[1] / 255.0f, a[6] = type.Colour()[2] / 255.0f, a[7] = 1.0f;
+            const glm::vec3 col = this->atomColorTable[i];
+            a[4] = col.r, a[5] = col.g, a[6] = col.b, a[7] = 1.0f;
         }
         if (n > 0) {
             mms_list l{};

@@ -21,6 +21,7 @@
 #include "mmcore/CallerSlot.h"
 #include "mmcore/Module.h"
 #include "mmcore/param/ParamSlot.h"
+#include "protein_calls/ProteinColor.h"
 #include "mmstd/data/AbstractGetData3DCall.h"
 #include "protein_calls/MolecularDataCall.h"
 
@@ -93,6 +94,11 @@ private:
     core::param::ParamSlot deviceSlot; // extra: CUDA device ordinal
     // extra: QuickSurf semantics as a kernel mode (names and defaults of protein_cuda::QuickSurf, QuickSurf.cpp:18-31,62-72)
     core::param::ParamSlot modeSlot, qsQualitySlot, qsRadScaleSlot, qsColourSlot, qsGridSpacingSlot, qsRefCellsSlot;
+    // the reference QuickSurf module's colouring of a MolecularDataCall (plugins/protein_cuda/src/QuickSurf.cpp:25-28, 62-91, 281-320,
+    // 596-616): two protein_calls::ProteinColor colouring modes blended by a weight, gradient colours, colour table file
+    core::param::ParamSlot colorTableFileSlot, coloringMode0Slot, coloringMode1Slot, coloringModeWeightSlot, minGradColorSlot, midGradColorSlot,
+        maxGradColorSlot;
+    std::vector<glm::vec3> atomColorTable, fileColorTable, rainbowColorTable;
     core::CalleeSlot outDataSlot, outParticlesSlot, outInfoSlot;
     core::CallerSlot inDataSlot;
 

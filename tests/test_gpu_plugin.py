@@ -297,6 +297,62 @@ def test_marching_tetrahedra_algorithm_matches_the_reference_module(ref, plug, o
         plug.set_param(1, "algorithm", 0)
 
 
+def test_molecule_colouring_modes_of_the_reference_quicksurf(plug):
+    """The reference QuickSurf module colours a MolecularDataCall with two protein_calls::ProteinColor modes blended by a weight
+    (plugins/protein_cuda/src/QuickSurf.cpp:62-109, 281-320, 596-616; parameters color::coloringMode0/1, color::colorWeighting,
+    color::min/mid/maxGradColor).  ParticlesToDensityB200 has the same parameters and calls the same (unmodified) ProteinColor code: for
+    several mode pairs the density-weighted colour volume equals, bit for bit, the one of the equivalent FLOAT_XYZR + FLOAT_RGBA particle
+    list whose colours are the reference's table for that pair."""
+    n = 3000
+    data, _, _ = synth.protein_like(n, seed=9, nballs=5, extent=36.0)
+    radii = np.array([1.2, 1.52, 1.55, 1.7, 1.8], np.float32)
+    rgb = np.array([[255, 255, 255], [255, 13, 13], [48, 80, 248], [144, 144, 144], [255, 255, 48]], np.uint8)
+    tidx = (np.arange(n) * 7 % 5).astype(np.uint32)
+    pos = np.ascontiguousarray(data[:, :3])
+    bfac = (np.random.default_rng(3).random(n) * 80.0 + 5.0).astype(np.float32)
+    bbox, res = (0, 0, 0, 36, 36, 36), (40, 40, 40)
+    ELEMENT, RAINBOW, BFACTOR, CHAIN, MOLECULE, RESIDUE = 0, 2, 3, 6, 7, 8   # protein_calls::ProteinColor::ColoringMode
+    grad = np.array([[0x14, 0x64, 0x96], [0xf0, 0xf0, 0xf0], [0xae, 0x3b, 0x32]], np.float32) / np.float32(255.0)  # the parameters' defaults
+
+    mol = rb.Harness(rb.PLUG_LIB, molecule=True)
+    mol.set_molecule(pos, tidx, radii, rgb, bbox)
+    mol.set_molecule_structure(bfac, atoms_per_residue=9, residues_per_molecule=25, molecules_per_chain=3)
+
+    def setup(h):
+        h.set_p2d_params(res, cyclic=(False,) * 3, normalize=False)
+        h.set_param(0, "mode", 1)
+        h.set_param(0, "quicksurf::quality", 1)
+        h.set_param(0, "quicksurf::colour", 1)
+
+    seen = []
+    try:
+        for m0, m1, w in ((CHAIN, ELEMENT, 0.5), (ELEMENT, ELEMENT, 0.5), (BFACTOR, RAINBOW, 0.25), (MOLECULE, RESIDUE, 0.7), (RAINBOW, CHAIN, 1.0)):
+            setup(mol)
+            mol.set_param(0, "color::coloringMode0", m0)
+            mol.set_param(0, "color::coloringMode1", m1)
+            mol.set_param(0, "color::colorWeighting", float(w))
+            mvol, _ = mol.pull_volume()
+            table = mol.molecule_colour_table(n, m0, m1, w, grad)
+            assert table.min() >= 0.0 and table.max() <= 1.0 + 1e-6
+            seen.append(table)
+            buf = np.zeros((n, 8), np.float32)
+            buf[:, :3], buf[:, 3], buf[:, 4:7], buf[:, 7] = pos, radii[tidx], table, 1.0
+            lists = [dict(vtx=buf, vtx_type=rb.VERT_FLOAT_XYZR, vtx_stride=32, count=n, col=buf.ctypes.data + 16, col_type=rb.COL_FLOAT_RGBA, col_stride=32)]
+            plug.set_particles(lists, bbox)
+            setup(plug)
+            pvol, _ = plug.pull_volume()
+            assert np.array_equal(mvol, pvol) and mvol.max() > 0.5
+            mm_, pm = mol.pull_mesh(0.5, colours=True), plug.pull_mesh(0.5, colours=True)
+            assert mm_["nverts"] == pm["nverts"] > 1000
+            assert np.array_equal(mm_["col"], pm["col"]), (m0, m1, w)   # the coloured mesh carries the colour volume
+    finally:
+        plug.set_param(0, "mode", 0)
+        plug.set_param(0, "quicksurf::colour", 0)
+        mol.close()
+    # the modes really differ (chain / b-factor / rainbow tables are not the element colours)
+    assert not np.allclose(seen[0], seen[1]) and not np.allclose(seen[2], seen[1]) and not np.allclose(seen[3], seen[4])
+
+
 @pytest.mark.parametrize("cyc,norm", [(True, True), (False, False)])
 def test_vector_aggregator_matches_the_reference_module(ref, plug, oracle, cyc, norm):
     """aggregator = IVecToSingleCell_Volume: the 3-component VolumetricDataCall, the grid particles on "outParticles" and the table on
