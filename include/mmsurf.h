@@ -270,6 +270,8 @@ int mms_halo_wait(mms_ctx* ctx, int32_t npeers);
  * PCIe link, the halo particles go through mms_halo_push / mms_halo_receive with peer access (ordered by CUDA events, no host
  * synchronisation), the global density range is combined by a kernel reading the peers' ranges (instead of the reference's
  * volume-sized MPI_Allreduce, plugins/datatools/src/MPIVolumeAggregator.cpp:94-152).  Results are bit-identical to one GPU.
+ * A device may be named several times: z-chunks on ONE GPU, which is how a volume of 2^32 voxels or more (more than one context's 32-bit
+ * voxel indices reach) is computed on a single device (the reference chunks in z as well, CUDAQuickSurf.cu:1050-1126, 1406-1447).
  * Scalar ParticlesToDensity modes (aggregators 0 / 1 need no per-particle extras beyond x y z r: aggregator 0 only for G > 1). */
 typedef struct mms_slabs mms_slabs;
 int mms_slabs_create(mms_slabs** out, const int32_t* devices, int32_t ndevices);

@@ -509,6 +509,17 @@ bool ParticlesToDensityB200::computeVolume(core::AbstractGetData3DCall* in) {
             pos = end + 1;
         }
     }
+    // A volume of 2^32 voxels or more does not fit one context's 32-bit voxel indices: it is computed in z-chunks on the one device -- a
+    // slab group that names the device several times (the reference's QuickSurf chunks its volume in z as well,
+    // CUDAQuickSurf.cu:1050-1126, 1406-1447)
+    if (devs.size() <= 1) {
+        const unsigned long long nvox = static_cast<unsigned long long>(grid.res[0]) * grid.res[1] * grid.res[2];
+        if (nvox >= (1ull << 32) - 1) {
+            const int dev = devs.empty() ? this->deviceSlot.Param<core::param::IntParam>()->Value() : devs[0];
+            const unsigned long long chunks = std::min<unsigned long long>((nvox >> 31) + 1, 16ull);
+            devs.assign(static_cast<size_t>(chunks), dev);
+        }
+    }
     this->groupActive = false;
     if (devs.size() > 1) {
         if (this->volumeOnDevice) {

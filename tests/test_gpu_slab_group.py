@@ -1,5 +1,8 @@
-"""GPU suite, needs >= 2 GPUs (skipped on a single-GPU box): the single-process slab group of the C ABI (mms_slabs_*: one context per
-device, fused halo push over peer memory, range combined by peer reads) against one GPU -- volume and mesh bit for bit."""
+"""GPU suite: the single-process slab group of the C ABI (mms_slabs_*: one context per device, fused halo push over peer memory, range
+combined by peer reads) against one GPU -- volume and mesh bit for bit.  The multi-device cases need >= 2 GPUs (skipped on a single-GPU
+box); a group may also name ONE device several times: z-chunks on a single GPU, the way a volume of 2^32 voxels or more (more than one
+context indexes) is computed on one device -- the reference's QuickSurf chunks its volume in z for the same reason
+(CUDAQuickSurf.cu:1050-1126, 1406-1447)."""
 import numpy as np
 import pytest
 
@@ -42,6 +45,39 @@ def test_slab_group_equals_one_gpu(ndev, cyclic):
             pos, nrm = g.get_mesh()
             assert np.array_equal(vol.view(np.uint32), ref.view(np.uint32)), "volume differs from one GPU"
             assert pos.shape == rpos.shape and np.array_equal(pos, rpos) and np.array_equal(nrm, rnrm), "mesh differs from one GPU"
+        assert rpos.shape[0] > 10000
+    finally:
+        g.close()
+
+
+@pytest.mark.parametrize("nchunks", [2, 3])
+def test_z_chunks_on_one_device_equal_one_context(nchunks):
+    n, res, box, radius, iso = 300_000, (96, 80, 75), (40.0, 33.0, 31.0), 0.6, 0.35
+    xyz = synth.uniform_box(n, 1.0, seed=77) * np.asarray(box, np.float32)
+    lists = [dict(vtx=xyz, vtx_type=1, count=n, global_radius=radius)]
+    one = mm.Surf(0)
+    one.set_grid((0, 0, 0), box, res, (True, True, True))
+    one.set_params(mode=0, aggregator=0, normalize=1, sigma=1.0)
+    one.push_particles(lists)
+    one.compute_density()
+    ref = one.get_density().copy()
+    one.extract_isosurface(iso)
+    rpos, rnrm = one.get_mesh()
+    rpos, rnrm = rpos.copy(), rnrm.copy()
+    one.close()
+    g = mm.SurfGroup([0] * nchunks)
+    try:
+        g.set_grid((0, 0, 0), box, res, (True, True, True))
+        g.set_params(mode=0, aggregator=0, normalize=1, sigma=1.0)
+        for _ in range(2):
+            g.clear_particles()
+            g.push_particles(lists)
+            g.compute_density()
+            vol = g.get_density()
+            g.extract_isosurface(iso)
+            pos, nrm = g.get_mesh()
+            assert np.array_equal(vol.view(np.uint32), ref.view(np.uint32)), "volume differs from one context"
+            assert pos.shape == rpos.shape and np.array_equal(pos, rpos) and np.array_equal(nrm, rnrm), "mesh differs from one context"
         assert rpos.shape[0] > 10000
     finally:
         g.close()
