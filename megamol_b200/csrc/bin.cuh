@@ -70,7 +70,9 @@ __device__ __forceinline__ Binned binParticle(const Geo& g, const ListDev& l, un
     const int xw = g.cyc[0] ? wrapIndex(q.X, g.s[0]) : min(max(q.X, 0), g.s[0] - 1);
     const int yw = g.cyc[1] ? wrapIndex(q.Y, g.s[1]) : min(max(q.Y, 0), g.s[1] - 1);
     const int zw = g.cyc[2] ? wrapIndex(q.Z, g.s[2]) : min(max(q.Z, 0), g.s[2] - 1);
-    q.cell = (xw >> g.cshift) + g.nc[0] * ((yw >> g.cshift) + g.nc[1] * (zw >> g.cshift));
+    const int lz = cellZLocal(g, zw >> g.cshift);
+    if (lz >= g.czCount) return q; // (cannot happen: the host sizes the slab's cell range from the largest filter size)
+    q.cell = (xw >> g.cshift) + g.nc[0] * ((yw >> g.cshift) + g.nc[1] * lz);
     return q;
 }
 
@@ -174,7 +176,7 @@ __global__ void __launch_bounds__(256) cell_order_kernel(Geo g, const unsigned* 
     const int xw = g.cyc[0] ? wrapIndex(X, g.s[0]) : min(max(X, 0), g.s[0] - 1);
     const int yw = g.cyc[1] ? wrapIndex(Y, g.s[1]) : min(max(Y, 0), g.s[1] - 1);
     const int zw = g.cyc[2] ? wrapIndex(Z, g.s[2]) : min(max(Z, 0), g.s[2] - 1);
-    const unsigned cell = static_cast<unsigned>((xw >> g.cshift) + g.nc[0] * ((yw >> g.cshift) + g.nc[1] * (zw >> g.cshift)));
+    const unsigned cell = static_cast<unsigned>((xw >> g.cshift) + g.nc[0] * ((yw >> g.cshift) + g.nc[1] * cellZLocal(g, zw >> g.cshift)));
     const unsigned b = cellStart[cell], e = cellStart[cell + 1];
     if (e - b > kBigCell) { // crowded cell: ranking by all pairs would be quadratic; cell_sort_big_kernel sorts it
         if (i == b) bigCells[atomicAdd(nBig, 1u)] = cell;

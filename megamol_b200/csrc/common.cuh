@@ -17,6 +17,9 @@ struct Geo {
     int z0, nz;   // slab: voxel planes [z0, z0+nz)
     int cshift;   // log2(cell edge in voxels)
     int nc[3];    // cell grid = ceil(s / cell)
+    // A z-slab only bins what reaches it: its cell arrays cover czCount cell layers from global layer czBase on (wrapping on a periodic
+    // axis) instead of all nc[2] -- per-GPU work must not grow with the number of slabs.  Local layer = cellZLocal(g, global layer).
+    int czBase, czCount;
     float sigma;
     int agg;      // 0 position, 1 intensity-weighted, 2 direction-weighted (vector field)
     int mode;     // 0 P2D bump, 1 QuickSurf Gaussian
@@ -70,6 +73,12 @@ struct DevState {
     unsigned bigNext;    // ... and the work counter of cell_sort_big_kernel
     unsigned long long totalVerts; // indexed mesh: crossed grid edges = vertices (mcx_vertex_kernel + scan)
 };
+
+/** Local index (into the context's cell arrays) of global cell layer cz in [0, nc[2]); >= czCount: a layer this slab does not hold. */
+__host__ __device__ __forceinline__ int cellZLocal(const Geo& g, int cz) {
+    int l = cz - g.czBase;
+    return l < 0 ? l + g.nc[2] : l;
+}
 
 __device__ __forceinline__ unsigned floatKey(float f) {
     const unsigned b = __float_as_uint(f);

@@ -181,8 +181,9 @@ __global__ void __launch_bounds__(CT_THREADS, 4) density_splat_kernel(Geo g, Dev
     for (int i = tid; i < nneigh; i += CT_THREADS) {
         const int kx = i % nax, ky = (i / nax) % nay, kz = i / (nax * nay);
         const int cxg = sh.axisCells[0][kx], cyg = sh.axisCells[1][ky], czg = sh.axisCells[2][kz];
-        const size_t cell = cxg + static_cast<size_t>(g.nc[0]) * (cyg + static_cast<size_t>(g.nc[1]) * czg);
-        const unsigned b = cellStart[cell], e = cellStart[cell + 1];
+        const int czl = cellZLocal(g, czg);
+        const size_t cell = cxg + static_cast<size_t>(g.nc[0]) * (cyg + static_cast<size_t>(g.nc[1]) * czl);
+        const unsigned b = czl < g.czCount ? cellStart[cell] : 0u, e = czl < g.czCount ? cellStart[cell + 1] : 0u;
         sh.cellB[i] = b;
         sh.cellN[i] = e - b;
         if (e > b) {
@@ -718,8 +719,9 @@ __global__ void __launch_bounds__(CT_THREADS, 4) density_splat3_kernel(Geo g, Sp
         if (row0 + lane < nrows) {
             const int i = row0 + lane;
             const int kr = i % nruns, t = i / nruns, ky = t % nay, kz = t / nay;
-            const size_t rowBase = (static_cast<size_t>(AZ.cell[kz]) * g.nc[1] + AY.cell[ky]) * g.nc[0];
-            myB = cellStart[rowBase + sh.runs.runA[kr]], myE = cellStart[rowBase + sh.runs.runB[kr] + 1];
+            const int czl = cellZLocal(g, AZ.cell[kz]);
+            const size_t rowBase = (static_cast<size_t>(czl) * g.nc[1] + AY.cell[ky]) * g.nc[0];
+            if (czl < g.czCount) myB = cellStart[rowBase + sh.runs.runA[kr]], myE = cellStart[rowBase + sh.runs.runB[kr] + 1];
             myCode = kz | ky << 4 | kr << 8;
         }
         const unsigned nonEmpty = __ballot_sync(0xffffffffu, myE > myB);
@@ -896,9 +898,10 @@ __global__ void __launch_bounds__(GT_THREADS, 2) density_gather_kernel(Geo g, De
                 const int gs = segBase + sI;
                 const int row = gs / nruns, run = gs - row * nruns;
                 const int cz = sh.axisCells[2][row / ncy], cy = sh.axisCells[1][row % ncy];
-                const size_t rowBase = (static_cast<size_t>(cz) * g.nc[1] + cy) * g.nc[0];
-                const unsigned beg = cellStart[rowBase + runStart[run]];
-                len = cellStart[rowBase + runEnd[run] + 1] - beg;
+                const int czl = cellZLocal(g, cz);
+                const size_t rowBase = (static_cast<size_t>(czl) * g.nc[1] + cy) * g.nc[0];
+                const unsigned beg = czl < g.czCount ? cellStart[rowBase + runStart[run]] : 0u;
+                len = czl < g.czCount ? cellStart[rowBase + runEnd[run] + 1] - beg : 0u;
                 sh.segBegin[sI] = beg;
             }
             unsigned total;
@@ -1180,8 +1183,9 @@ __global__ void __launch_bounds__(GQ_THREADS, 5) density_gauss_kernel(Geo g, Dev
         unsigned myB = 0, myE = 0;
         if (row0 + lane < nrows) {
             const int i = row0 + lane, cz = cz0 + i / nyc, cy = cy0 + i % nyc;
-            const size_t rowBase = (static_cast<size_t>(cz) * g.nc[1] + cy) * g.nc[0];
-            myB = cellStart[rowBase + cx0], myE = cellStart[rowBase + cx1 + 1];
+            const int czl = cellZLocal(g, cz);
+            const size_t rowBase = (static_cast<size_t>(czl) * g.nc[1] + cy) * g.nc[0];
+            if (czl < g.czCount) myB = cellStart[rowBase + cx0], myE = cellStart[rowBase + cx1 + 1];
         }
         unsigned rest = __ballot_sync(0xffffffffu, myE > myB);
         unsigned base = 0, end = 0;

@@ -259,6 +259,7 @@ struct mms_ctx {
     unsigned long long ntris = 0;
     unsigned long long launches = 0;
     int cshift = 2, reach = 2;
+    int czBase = 0, czCount = 0; // cell layers this slab's cell arrays cover (czCount == 0: all), see Geo
     bool useGather = false, haveColour = false, splatV2ok = false;
     bool haveVector = false; // aggregator 2: rgb = vector volume, vol = |v|, dirVol = unit directions
     McGeo mcGeo{};
@@ -365,6 +366,7 @@ Geo makeGeo(const mms_ctx* c) {
     g.z0 = c->z0, g.nz = c->nz;
     g.cshift = c->cshift;
     for (int a = 0; a < 3; ++a) g.nc[a] = (g.s[a] + (1 << g.cshift) - 1) >> g.cshift;
+    g.czBase = c->czCount > 0 ? c->czBase : 0, g.czCount = c->czCount > 0 ? c->czCount : g.nc[2];
     g.sigma = c->params.sigma;
     g.agg = c->params.aggregator;
     g.mode = c->params.mode == MMS_MODE_P2D_BUMP ? 0 : 1; // both Gaussian modes are mode 1 on the device; qsAc > 0 selects the reference cells
@@ -833,6 +835,32 @@ int mms_compute_density(mms_ctx* c) {
         else if (need <= 4) c->cshift = 3;
         else c->cshift = 4;
         c->reach = need;
+        // ---- the cell layers this slab has to hold: everything within the largest filter size (what the binning keeps) or reach (what the
+        //      density kernels ask for) of its planes, + a voxel of margin; wrapped on a periodic axis -----------------------------------
+        {
+            float radEff = c->params.mode == MMS_MODE_P2D_BUMP ? rmax : c->params.gausslim * c->params.radscale * rmax;
+            if (c->qsAc > 0.0f) radEff = 2.0f * c->qsAc;
+            const int fz = static_cast<int>(std::ceil(radEff / g0.sd[2])) + 2;
+            const int zr = std::max(fz, need + 1);
+            const int s = c->grid.res[2], nc2 = (s + (1 << c->cshift) - 1) >> c->cshift, cs = c->cshift;
+            int a = c->z0 - zr, b = c->z0 + c->nz - 1 + zr;
+            if (!c->grid.cyclic[2]) {
+                a = std::max(a, 0), b = std::min(b, s - 1);
+                c->czBase = a >> cs, c->czCount = (b >> cs) - c->czBase + 1;
+            } else if (b - a + 1 >= s) {
+                c->czBase = 0, c->czCount = nc2;
+            } else {
+                // the planes a..b wrap around the axis; a range that comes back to the layer it started in has visited every layer
+                const int first = (a < 0 ? a + s : a) >> cs;
+                int layers = 1, prev = first;
+                for (int v = a + 1; v <= b && layers < nc2; ++v) {
+                    const int cz = (v < 0 ? v + s : v >= s ? v - s : v) >> cs;
+                    if (cz != prev) ++layers, prev = cz;
+                }
+                c->czBase = first, c->czCount = layers;
+            }
+            if (c->czCount >= nc2 || c->czCount <= 0) c->czBase = 0, c->czCount = nc2;
+        }
         // tight support box = the integers of an interval of length 2 eps / sliceDist (+ rounding slop): at most 3 per axis?
         c->splatV2ok = true;
         for (int a = 0; a < 3; ++a)
@@ -846,7 +874,7 @@ int mms_compute_density(mms_ctx* c) {
             l.gf[a] = static_cast<int>(std::ceil(q)) + (g.mode == 0 ? 0 : 1);
         }
     }
-    const size_t ncells = static_cast<size_t>(g.nc[0]) * g.nc[1] * g.nc[2];
+    const size_t ncells = static_cast<size_t>(g.nc[0]) * g.nc[1] * g.czCount; // (a slab: only the cell layers that can reach it)
     const size_t nvox = static_cast<size_t>(g.s[0]) * g.s[1] * g.nz;
     const bool colour = g.mode == 1 && c->params.colour != 0;
     if (g.qsAc > 0.0f)
