@@ -59,6 +59,7 @@ struct McGeo {
     float org[3], sd[3];
     float rinv[3][3];  // rinv[a][n] = 1/(n*sd[a]), n = 1, 2 (gradient: one-sided / central)
     float iso;
+    int countLayers;    // mc_count_kernel: cell layers a block marches (the host picks it so that the grid fills whole waves of resident blocks)
     int layersPerBlock; // mc_emit_kernel: cell layers a block marches (<= EM_LAYERS; fewer on small volumes, so that the grid fills the machine)
     unsigned maxTris;  // mc_emit_kernel: cell rows whose triangles end beyond this many are skipped (speculative launch before the count is
                        // known on the host: the destination's capacity; 0xffffffff otherwise)
@@ -71,7 +72,7 @@ constexpr int MC_THREADS = 256;
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int CN_SEGS = 16;                 // x-segments (32 cells each) per block
 constexpr int CN_ROWS = 16;                 // cell rows (y) per block
-constexpr int CN_LAYERS = 16;               // cell layers (z) a block marches through
+constexpr int CN_LAYERS = 16;               // cell layers (z) a block marches through (default; McGeo::countLayers)
 constexpr int CN_WORDS = CN_SEGS + 1;       // mask words per node row: 16 segments + the first node of the next segment
 constexpr int CN_NROWS = CN_ROWS + 1;       // node rows per plane
 
@@ -82,7 +83,7 @@ __global__ void __launch_bounds__(MC_THREADS) mc_count_kernel(McGeo m, const flo
     sCount[threadIdx.x] = static_cast<unsigned char>(kCasePerm.w[threadIdx.x] & 15ull);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int seg0 = blockIdx.x * CN_SEGS, yBeg = blockIdx.y * CN_ROWS;
-    const int czBeg = m.cz0 + blockIdx.z * CN_LAYERS, czEnd = min(czBeg + CN_LAYERS, m.cz0 + m.cnz);
+    const int czBeg = m.cz0 + blockIdx.z * m.countLayers, czEnd = min(czBeg + m.countLayers, m.cz0 + m.cnz);
     if (czBeg >= czEnd) return;
     const size_t plane = static_cast<size_t>(m.sx) * m.sy;
     const int nsegHere = min(CN_SEGS, m.nsegx - seg0);
@@ -555,13 +556,25 @@ __global__ void __launch_bounds__(MC_THREADS, COLOUR ? 2 : 4) mc_emit_kernel(McG
                 __syncwarp();
                 const unsigned ncorn = segTris * 3;
                 const size_t gbase = static_cast<size_t>(segOff) * 9;
+#ifndef EMIT_PTR32
                 float* op = outPos + gbase + lane * 3; // this lane's corner of the current round; 32 corners = 96 floats per round
                 float* on = outNrm + gbase + lane * 3;
+#endif
                 float* oc = COLOUR ? outCol + gbase + lane * 3 : nullptr;
                 const float tz0 = pzM2, tz1 = pzM1;
                 const unsigned* etab = sh.etab[warp];
-#pragma unroll 2 // two independent gather chains in flight
+#ifndef EMIT_UNROLL
+#define EMIT_UNROLL 1 // a row has 2.6 rounds on average: unrolling by two costs more in the remainder logic than the second gather chain gains
+#endif                // (C2: 2.635 -> 2.522 ms; by three: 2.68 ms)
+                constexpr int kEmitUnroll = EMIT_UNROLL;
+#pragma unroll(kEmitUnroll)
+#ifdef EMIT_PTR32
+                for (unsigned jc = lane; jc < ncorn; jc += 32) {
+                    float* const op = outPos + gbase + jc * 3u;
+                    float* const on = outNrm + gbase + jc * 3u;
+#else
                 for (unsigned jc = lane; jc < ncorn; jc += 32, op += 96, on += 96) {
+#endif
                     const unsigned t = jc / 3;
                     const unsigned ok = owner[t];
                     const unsigned L = (ok >> 12) + (t >= tHalf ? 16u : 0u);

@@ -294,6 +294,7 @@ struct mms_ctx {
     cudaEvent_t ev[EV_COUNT]{};
     bool evSet[EV_COUNT]{};
     int smCount = 148;
+    int countSlots = 0; // resident mc_count_kernel blocks of the device (occupancy query, once)
 
     int fail(int code, const char* fmt, ...) {
         char buf[512];
@@ -1257,6 +1258,7 @@ static int countLaunch(mms_ctx* c, float iso) {
     m.iso = iso;
     m.maxTris = 0xffffffffu;
     m.layersPerBlock = EM_LAYERS;
+    m.countLayers = CN_LAYERS;
     c->mcGeo = m;
     c->ntris = 0;
     c->haveCount = false; // set once the count has run and the device reported no error
@@ -1296,7 +1298,27 @@ static int countLaunch(mms_ctx* c, float iso) {
         mt_count_kernel<<<grid, MT_THREADS, 0, st>>>(t, c->isoVol(), c->segCount.as<unsigned>(), tri);
     } else {
         if (tri) MMS_CUDA(c, cudaMemsetAsync(tri, 0, static_cast<size_t>(m.cx) * m.cy * m.cnz, st)); // the kernel writes the non-empty cells only
-        dim3 grid((m.nsegx + CN_SEGS - 1) / CN_SEGS, (m.cy + CN_ROWS - 1) / CN_ROWS, (m.cnz + CN_LAYERS - 1) / CN_LAYERS);
+        // Layers per block: the smallest count >= CN_LAYERS for which the grid is a whole number of waves of resident blocks or just under
+        // it (C2: 1024 blocks of 16 layers on 888 slots ran a second wave that was 15 % full), large grids keep the default.
+        {
+            if (c->countSlots == 0) {
+                int perSm = 0;
+                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, mc_count_kernel, MC_THREADS, 0) != cudaSuccess || perSm < 1) perSm = 4;
+                c->countSlots = perSm * c->smCount;
+            }
+            const long long cols = static_cast<long long>((m.nsegx + CN_SEGS - 1) / CN_SEGS) * ((m.cy + CN_ROWS - 1) / CN_ROWS);
+            int L = CN_LAYERS;
+            const long long blocks0 = cols * ((m.cnz + L - 1) / L);
+            if (blocks0 > c->countSlots && blocks0 < 4ll * c->countSlots) {
+                const long long waves = (blocks0 + c->countSlots - 1) / c->countSlots;
+                // fewest layers per block that bring the grid down to (waves - 1) full waves
+                const long long zBlocks = std::max(1ll, (waves - 1) * c->countSlots / cols);
+                const int L2 = static_cast<int>((m.cnz + zBlocks - 1) / zBlocks);
+                if (L2 <= 2 * CN_LAYERS && static_cast<double>(blocks0) / (waves * c->countSlots) < 0.8) L = L2; // (a nearly full last wave stays)
+            }
+            c->mcGeo.countLayers = m.countLayers = L;
+        }
+        dim3 grid((m.nsegx + CN_SEGS - 1) / CN_SEGS, (m.cy + CN_ROWS - 1) / CN_ROWS, (m.cnz + m.countLayers - 1) / m.countLayers);
         // indexed mesh: the count kernel writes the node segments' mask records as a by-product (validated and allocated below)
         const bool ix = c->meshIndexed && !c->haveColour && c->z0 == 0 && c->nz == c->grid.res[2] && m.cz0 == 0 && m.cnz == c->grid.res[2] - 1 &&
                         static_cast<long long>(m.sx) * m.sy < (1ll << 31);
