@@ -556,10 +556,8 @@ __global__ void __launch_bounds__(MC_THREADS, COLOUR ? 2 : 4) mc_emit_kernel(McG
                 __syncwarp();
                 const unsigned ncorn = segTris * 3;
                 const size_t gbase = static_cast<size_t>(segOff) * 9;
-#ifndef EMIT_PTR32
                 float* op = outPos + gbase + lane * 3; // this lane's corner of the current round; 32 corners = 96 floats per round
                 float* on = outNrm + gbase + lane * 3;
-#endif
                 float* oc = COLOUR ? outCol + gbase + lane * 3 : nullptr;
                 const float tz0 = pzM2, tz1 = pzM1;
                 const unsigned* etab = sh.etab[warp];
@@ -568,13 +566,7 @@ __global__ void __launch_bounds__(MC_THREADS, COLOUR ? 2 : 4) mc_emit_kernel(McG
 #endif                // (C2: 2.635 -> 2.522 ms; by three: 2.68 ms)
                 constexpr int kEmitUnroll = EMIT_UNROLL;
 #pragma unroll(kEmitUnroll)
-#ifdef EMIT_PTR32
-                for (unsigned jc = lane; jc < ncorn; jc += 32) {
-                    float* const op = outPos + gbase + jc * 3u;
-                    float* const on = outNrm + gbase + jc * 3u;
-#else
                 for (unsigned jc = lane; jc < ncorn; jc += 32, op += 96, on += 96) {
-#endif
                     const unsigned t = jc / 3;
                     const unsigned ok = owner[t];
                     const unsigned L = (ok >> 12) + (t >= tHalf ? 16u : 0u);
