@@ -103,3 +103,26 @@ def test_c2_full_size_is_reproducible(c2):
         assert sums[0] == sums[1]
     finally:
         s.close()
+
+
+def test_count_kernel_with_rebalanced_layers(oracle):
+    """mc_count_kernel picks the number of cell layers a block marches so that the grid fills whole waves of resident blocks
+    (McGeo::countLayers).  A 1024 x 1024 x 161 volume has 128 block columns x 10 default z-blocks = 1280 blocks for 1184 resident
+    ones on a B200, so the kernel runs with 18 instead of 16 layers per block: every per-cell triangle count equals the oracle's."""
+    res = (1024, 1024, 161)
+    z, y, x = np.ogrid[0:res[2], 0:res[1], 0:res[0]]
+    vol = (np.sin(0.05 * x) + np.sin(0.043 * y) + np.sin(0.061 * z)).astype(np.float32)
+    vol += (synth.uniform(4242, 0, 4096, 0).astype(np.float32) * np.float32(0.02))[(x * 7 + y * 13 + z * 29) % 4096]
+    s = mm.Surf(0)
+    try:
+        s.set_grid((0, 0, 0), tuple(float(r - 1) for r in res), res, (False,) * 3)
+        s.set_params(want_cell_tricounts=1)
+        s.set_density(vol)
+        s.extract_isosurface(1.1)
+        counts = s.cell_tricounts()
+        total = s.count_isosurface(1.1)
+        ref_total, ref_counts, _ = oracle.mc_count(vol, 1.1)
+        assert total == ref_total and total > 1_000_000
+        assert np.array_equal(counts, ref_counts)
+    finally:
+        s.close()
