@@ -272,7 +272,8 @@ int mms_halo_wait(mms_ctx* ctx, int32_t npeers);
  * volume-sized MPI_Allreduce, plugins/datatools/src/MPIVolumeAggregator.cpp:94-152).  Results are bit-identical to one GPU.
  * A device may be named several times: z-chunks on ONE GPU, which is how a volume of 2^32 voxels or more (more than one context's 32-bit
  * voxel indices reach) is computed on a single device (the reference chunks in z as well, CUDAQuickSurf.cu:1050-1126, 1406-1447).
- * Scalar ParticlesToDensity modes (aggregators 0 / 1 need no per-particle extras beyond x y z r: aggregator 0 only for G > 1). */
+ * For G > 1 the halo records travel as x y z r, i.e. scalar volumes: ParticlesToDensity aggregator 0, or the QuickSurf Gaussian with the
+ * radial cut-off (MMS_MODE_QS_GAUSS) without its colour volume -- the reference chunks exactly this volume in z (CUDAQuickSurf.cu:1050-1126). */
 typedef struct mms_slabs mms_slabs;
 int mms_slabs_create(mms_slabs** out, const int32_t* devices, int32_t ndevices);
 int mms_slabs_destroy(mms_slabs* s);

@@ -2120,8 +2120,11 @@ int mms_slabs_set_grid(mms_slabs* s, const mms_grid* grid) {
 int mms_slabs_set_params(mms_slabs* s, const mms_params* p) {
     if (!s || !p) return MMS_ERR_INVALID;
     const int G = static_cast<int>(s->ctx.size());
-    if (G > 1 && (p->mode != MMS_MODE_P2D_BUMP || p->aggregator != 0))
-        return s->fail(MMS_ERR_UNSUPPORTED, "a slab group of several devices computes the scalar ParticlesToDensity volume (aggregator 0)");
+    // halo records travel as xyzr: scalar volumes only -- the P2D bump with aggregator 0, or the QuickSurf Gaussian (radial cut-off) without
+    // its colour volume
+    if (G > 1 && !((p->mode == MMS_MODE_P2D_BUMP && p->aggregator == 0) || (p->mode == MMS_MODE_QS_GAUSS && p->colour == 0)))
+        return s->fail(MMS_ERR_UNSUPPORTED, "a slab group of several devices computes a scalar volume (ParticlesToDensity aggregator 0, or the "
+                                            "QuickSurf Gaussian without colours)");
     mms_params q = *p;
     if (G > 1) q.defer_normalize = 1; // the range is global: normalised after the slabs' ranges have been combined
     for (mms_ctx* c : s->ctx)
