@@ -272,8 +272,9 @@ int mms_halo_wait(mms_ctx* ctx, int32_t npeers);
  * volume-sized MPI_Allreduce, plugins/datatools/src/MPIVolumeAggregator.cpp:94-152).  Results are bit-identical to one GPU.
  * A device may be named several times: z-chunks on ONE GPU, which is how a volume of 2^32 voxels or more (more than one context's 32-bit
  * voxel indices reach) is computed on a single device (the reference chunks in z as well, CUDAQuickSurf.cu:1050-1126, 1406-1447).
- * For G > 1 the halo records travel as x y z r, i.e. scalar volumes: ParticlesToDensity aggregator 0, or the QuickSurf Gaussian with the
- * radial cut-off (MMS_MODE_QS_GAUSS) without its colour volume -- the reference chunks exactly this volume in z (CUDAQuickSurf.cu:1050-1126). */
+ * For G > 1 the halo records travel as x y z r (+ RGBA where the QuickSurf colour volume is on): ParticlesToDensity aggregator 0, or the
+ * QuickSurf Gaussian with the radial cut-off (MMS_MODE_QS_GAUSS) -- the reference chunks exactly these volumes in z
+ * (CUDAQuickSurf.cu:1050-1126). */
 typedef struct mms_slabs mms_slabs;
 int mms_slabs_create(mms_slabs** out, const int32_t* devices, int32_t ndevices);
 int mms_slabs_destroy(mms_slabs* s);
@@ -292,6 +293,11 @@ int mms_slabs_adopt_density(mms_slabs* s, mms_slabs* producer);
 int mms_slabs_extract_isosurface(mms_slabs* s, float isovalue);
 /* The whole mesh in cell-linear order (= the single-GPU order), library-owned pinned memory; every slab is copied over its own link. */
 int mms_slabs_get_mesh(mms_slabs* s, uint64_t* nverts, const float** positions, const float** normals);
+/* QuickSurf colour outputs of the group (MMS_MODE_QS_GAUSS with params.colour; the halo records then carry their RGBA as well): the
+ * density-weighted RGB volume (3 floats per voxel, whole volume) and the per-vertex colours in the order of mms_slabs_get_mesh
+ * (QuickSurf.cpp:596-616 is what the reference feeds its colour volume with).  NULL where the mode has no colours. */
+int mms_slabs_get_colour_volume(mms_slabs* s, const float** host_rgb);
+int mms_slabs_get_mesh_colours(mms_slabs* s, const float** colours);
 
 /* Device buffers that can be shared between the per-GPU processes of one node (CUDA IPC over NVLink / PCIe P2P). */
 int mms_device_alloc(int32_t device, size_t bytes, void** ptr);

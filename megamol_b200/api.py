@@ -18,7 +18,7 @@ ISO_MARCHING_CUBES, ISO_MARCHING_TETS = 0, 1
 EXPORTS = ["mms_create", "mms_destroy", "mms_last_error", "mms_set_grid", "mms_set_slab", "mms_set_params",
            "mms_clear_particles", "mms_push_particles", "mms_push_particles_dir", "mms_get_vector_field", "mms_get_vector_field_device", "mms_get_max_radius", "mms_compute_density", "mms_get_density_range", "mms_normalize", "mms_density_range_device", "mms_normalize_device", "mms_set_stream",
            "mms_get_density", "mms_prefetch_density", "mms_get_density_device", "mms_set_density", "mms_adopt_density", "mms_extract_isosurface", "mms_set_isosurface_mode", "mms_count_isosurface", "mms_emit_isosurface", "mms_device_alloc",
-           "mms_device_free", "mms_route_particles", "mms_halo_buffers", "mms_halo_push", "mms_halo_receive", "mms_halo_wait", "mms_slabs_create", "mms_slabs_destroy", "mms_slabs_last_error", "mms_slabs_count", "mms_slabs_context", "mms_slabs_set_grid", "mms_slabs_set_params", "mms_slabs_clear_particles", "mms_slabs_push_particles", "mms_slabs_compute_density", "mms_slabs_get_density_range", "mms_slabs_get_density", "mms_slabs_adopt_density", "mms_slabs_extract_isosurface", "mms_slabs_get_mesh", "mms_ipc_export", "mms_ipc_open", "mms_ipc_close", "mms_share_enable", "mms_share_density", "mms_share_mesh", "mms_share_open", "mms_share_close", "mms_get_mesh",
+           "mms_device_free", "mms_route_particles", "mms_halo_buffers", "mms_halo_push", "mms_halo_receive", "mms_halo_wait", "mms_slabs_create", "mms_slabs_destroy", "mms_slabs_last_error", "mms_slabs_count", "mms_slabs_context", "mms_slabs_set_grid", "mms_slabs_set_params", "mms_slabs_clear_particles", "mms_slabs_push_particles", "mms_slabs_compute_density", "mms_slabs_get_density_range", "mms_slabs_get_density", "mms_slabs_adopt_density", "mms_slabs_extract_isosurface", "mms_slabs_get_mesh", "mms_slabs_get_colour_volume", "mms_slabs_get_mesh_colours", "mms_ipc_export", "mms_ipc_open", "mms_ipc_close", "mms_share_enable", "mms_share_density", "mms_share_mesh", "mms_share_open", "mms_share_close", "mms_get_mesh",
            "mms_get_mesh_device", "mms_set_mesh_indexed", "mms_get_mesh_indexed", "mms_get_mesh_indexed_device", "mms_get_home_voxels", "mms_get_cell_tricounts", "mms_get_timings", "mms_synchronize",
            "mms_timer_start", "mms_timer_stop", "mms_launch_count", "mms_alloc_pinned", "mms_free_pinned", "mms_version", "mms_mmpld_open", "mms_mmpld_close",
            "mms_mmpld_last_error", "mms_mmpld_info", "mms_mmpld_prefetch", "mms_mmpld_read_frame"]
@@ -128,6 +128,8 @@ def load_library():
     L.mms_slabs_adopt_density.argtypes = [vp, vp]
     L.mms_slabs_extract_isosurface.argtypes = [vp, C.c_float]
     L.mms_slabs_get_mesh.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(vp), C.POINTER(vp)]
+    L.mms_slabs_get_colour_volume.argtypes = [vp, C.POINTER(vp)]
+    L.mms_slabs_get_mesh_colours.argtypes = [vp, C.POINTER(vp)]
     L.mms_ipc_export.argtypes = [C.c_int32, vp, C.POINTER(C.c_ubyte)]
     L.mms_ipc_open.argtypes = [C.c_int32, C.POINTER(C.c_ubyte), C.POINTER(vp)]
     L.mms_ipc_close.argtypes = [C.c_int32, vp]
@@ -541,6 +543,18 @@ class SurfGroup:
             self._keep.append(v)
             arr[i].vtx, arr[i].vtx_type, arr[i].vtx_stride, arr[i].count = v.ctypes.data, l["vtx_type"], l.get("vtx_stride", 0), l["count"]
             arr[i].global_radius = l.get("global_radius", 0.5)
+            col = l.get("col")
+            if col is not None:  # ndarray or the address of colour data interleaved with the (kept) vertex array
+                if isinstance(col, np.ndarray):
+                    col = np.ascontiguousarray(col)
+                    self._keep.append(col)
+                    col = col.ctypes.data
+                arr[i].col, arr[i].col_type, arr[i].col_stride = int(col), l.get("col_type", COL_NONE), l.get("col_stride", 0)
+            rgba = l.get("global_rgba", (255, 255, 255, 255))
+            for k in range(4):
+                arr[i].global_rgba[k] = rgba[k]
+            ir = l.get("irange", (0.0, 1.0))
+            arr[i].irange[0], arr[i].irange[1] = ir
         self._chk(self.L.mms_slabs_push_particles(self.h, len(lists), arr))
 
     def compute_density(self):
@@ -555,6 +569,21 @@ class SurfGroup:
         p = C.c_void_p()
         self._chk(self.L.mms_slabs_get_density(self.h, C.byref(p)))
         return _np_view(p.value, (self.res[2], self.res[1], self.res[0]), np.float32).copy()
+
+    def get_colour_volume(self):
+        """QuickSurf colour mode: the density-weighted RGB volume (sz, sy, sx, 3), or None"""
+        p = C.c_void_p()
+        self._chk(self.L.mms_slabs_get_colour_volume(self.h, C.byref(p)))
+        if not p.value:
+            return None
+        return _np_view(p.value, (self.res[2], self.res[1], self.res[0], 3), np.float32).copy()
+
+    def get_mesh_colours(self, nverts):
+        p = C.c_void_p()
+        self._chk(self.L.mms_slabs_get_mesh_colours(self.h, C.byref(p)))
+        if not p.value:
+            return None
+        return _np_view(p.value, (nverts // 3, 3, 3), np.float32).copy()
 
     def extract_isosurface(self, iso):
         self._chk(self.L.mms_slabs_extract_isosurface(self.h, float(iso)))

@@ -279,6 +279,7 @@ struct mms_ctx {
     DevBuf routeCounts, routeOffsets, routeTile;
     DevBuf haloBuf, haloCounters; // mms_halo_*: receive buffer (float4 records) and counter block of this slab
     uint64_t haloCap = 0;
+    bool haloColour = false;      // the halves carry cap colours behind their cap records (set by mms_halo_buffers from the parameters)
     unsigned haloFrame = 0;       // parity selects the counter word of the current frame
     int haloWaitPeers = -1;       // mms_halo_wait: arrivals the stream has to see before the received list is read (-1: nothing pending)
     PinBuf hRoute;
@@ -1751,7 +1752,9 @@ int mms_halo_buffers(mms_ctx* c, uint64_t cap, void** buf, void** counters) {
     if (!c || !buf || !counters || cap == 0) return MMS_ERR_INVALID;
     DeviceGuard guard(c->device);
     const bool fresh = c->haloCounters.p == nullptr;
-    if (!c->haloBuf.ensure(cap * 16 * 2) || !c->haloCounters.ensure(16)) return c->fail(MMS_ERR_NOMEM, "allocation of the halo receive buffer (%llu records) failed",
+    // per frame half: cap x y z r records, followed by their cap RGBA colours where the QuickSurf colour volume is on
+    c->haloColour = c->params.mode != MMS_MODE_P2D_BUMP && c->params.colour != 0;
+    if (!c->haloBuf.ensure(cap * 16 * 2 * (c->haloColour ? 2 : 1)) || !c->haloCounters.ensure(16)) return c->fail(MMS_ERR_NOMEM, "allocation of the halo receive buffer (%llu records) failed",
         static_cast<unsigned long long>(cap));
     if (fresh) MMS_CUDA(c, cudaMemset(c->haloCounters.p, 0, 16));
     c->haloCap = cap;
@@ -1779,12 +1782,13 @@ int mms_halo_push(mms_ctx* c, int32_t nslabs, int32_t mine, const int32_t* plane
         r.lo[i] = plane_lo[i], r.hi[i] = plane_hi[i];
         if (i != mine && plane_lo[i] <= plane_hi[i] && peer_bufs[i] && peer_counters[i]) {
             r.enabled |= 1u << i;
-            hp.buf[i] = static_cast<float4*>(peer_bufs[i]) + static_cast<size_t>(word) * cap; // frames alternate between the buffer's halves
+            hp.buf[i] = static_cast<float4*>(peer_bufs[i]) + static_cast<size_t>(word) * cap * (c->haloColour ? 2 : 1); // frames alternate between the buffer's halves
             hp.counter[i] = static_cast<unsigned*>(peer_counters[i]) + word;
             hp.arrive[i] = static_cast<unsigned*>(peer_counters[i]) + 2 + word;
         }
     }
     hp.cap = static_cast<unsigned>(std::min<uint64_t>(cap, 0xffffffffull));
+    hp.colour = c->haloColour ? 1 : 0;
     r.sigma = g.sigma, r.radscale = g.radscale, r.gausslim = g.gausslim, r.mode = g.mode;
     if (cap != c->haloCap) return c->fail(MMS_ERR_INVALID, "capacity_records must be the capacity every slab passed to mms_halo_buffers");
     if (r.enabled)
@@ -1815,14 +1819,19 @@ int mms_halo_receive(mms_ctx* c, float radius_bound) {
     if (!c->haloCounters.p || !c->haloCap) return c->fail(MMS_ERR_INVALID, "mms_halo_buffers has not been called");
     if (c->lists.size() + 1 > static_cast<size_t>(kMaxLists)) return c->fail(MMS_ERR_UNSUPPORTED, "more than %d particle lists", kMaxLists);
     ListDev d{};
-    d.vtx = static_cast<const char*>(c->haloBuf.p) + static_cast<size_t>(c->haloFrame & 1u) * c->haloCap * 16; // this frame's half
+    d.vtx = static_cast<const char*>(c->haloBuf.p) + static_cast<size_t>(c->haloFrame & 1u) * c->haloCap * 16 * (c->haloColour ? 2 : 1); // this frame's half
+    if (c->haloColour) { // converted colours behind the records: FLOAT_RGBA, for which quicksurfColour is the identity
+        d.col = d.vtx + c->haloCap * 16;
+        d.ctype = MMS_COL_FLOAT_RGBA;
+        d.cstride = 16;
+    }
     d.count = c->haloCap; // the bound; the length is read on the device
     d.countPtr = c->haloCounters.as<unsigned>() + (c->haloFrame & 1u);
     d.base = c->nparticles;
     d.vtype = MMS_VERT_FLOAT_XYZR;
     d.vstride = 16;
     d.valign = 16;
-    d.calign = 4;
+    d.calign = c->haloColour ? 16 : 4;
     d.grad = radius_bound;
     d.radiusBound = 1;
     c->lists.push_back(d);
@@ -2005,7 +2014,7 @@ struct mms_slabs {
     uint64_t haloCap = 0, nparticles = 0;
     float radiusBound = 0.0f;
     bool perParticleRadii = false;
-    PinBuf hVol, hPos, hNrm;
+    PinBuf hVol, hPos, hNrm, hRgb, hCol;
     uint64_t ntris = 0;
     int fail(int code, const char* fmt, ...) {
         char buf[512];
@@ -2037,7 +2046,7 @@ int mms_slabs_destroy(mms_slabs* s) {
         if (g < s->combined.size()) s->combined[g].release();
     }
     for (mms_ctx* c : s->ctx) mms_destroy(c);
-    s->hVol.release(), s->hPos.release(), s->hNrm.release();
+    s->hVol.release(), s->hPos.release(), s->hNrm.release(), s->hRgb.release(), s->hCol.release();
     delete s;
     return MMS_OK;
 }
@@ -2120,11 +2129,11 @@ int mms_slabs_set_grid(mms_slabs* s, const mms_grid* grid) {
 int mms_slabs_set_params(mms_slabs* s, const mms_params* p) {
     if (!s || !p) return MMS_ERR_INVALID;
     const int G = static_cast<int>(s->ctx.size());
-    // halo records travel as xyzr: scalar volumes only -- the P2D bump with aggregator 0, or the QuickSurf Gaussian (radial cut-off) without
-    // its colour volume
-    if (G > 1 && !((p->mode == MMS_MODE_P2D_BUMP && p->aggregator == 0) || (p->mode == MMS_MODE_QS_GAUSS && p->colour == 0)))
-        return s->fail(MMS_ERR_UNSUPPORTED, "a slab group of several devices computes a scalar volume (ParticlesToDensity aggregator 0, or the "
-                                            "QuickSurf Gaussian without colours)");
+    // halo records travel as x y z r (+ RGBA where the QuickSurf colour volume is on): the P2D bump with aggregator 0, or the QuickSurf
+    // Gaussian with the radial cut-off
+    if (G > 1 && !((p->mode == MMS_MODE_P2D_BUMP && p->aggregator == 0) || p->mode == MMS_MODE_QS_GAUSS))
+        return s->fail(MMS_ERR_UNSUPPORTED, "a slab group of several devices computes ParticlesToDensity with aggregator 0 or the QuickSurf "
+                                            "Gaussian with the radial cut-off");
     mms_params q = *p;
     if (G > 1) q.defer_normalize = 1; // the range is global: normalised after the slabs' ranges have been combined
     for (mms_ctx* c : s->ctx)
@@ -2330,6 +2339,63 @@ int mms_slabs_get_mesh(mms_slabs* s, uint64_t* nverts, const float** pos, const 
     }
     if (pos) *pos = s->hPos.as<float>();
     if (nrm) *nrm = s->hNrm.as<float>();
+    return MMS_OK;
+}
+
+int mms_slabs_get_colour_volume(mms_slabs* s, const float** hrgb) {
+    if (!s || !hrgb) return MMS_ERR_INVALID;
+    *hrgb = nullptr;
+    if (!s->haveDensity) return s->fail(MMS_ERR_INVALID, "no density has been computed");
+    const int G = static_cast<int>(s->ctx.size());
+    if (G == 1) {
+        const float* v = nullptr;
+        if (int rc = mms_get_density(s->ctx[0], &v, hrgb)) return s->failFrom(rc, s->ctx[0]);
+        return MMS_OK;
+    }
+    if (!s->ctx[0]->haveColour) return MMS_OK; // no colour volume in this mode: NULL, like mms_get_density
+    const size_t plane = static_cast<size_t>(s->grid.res[0]) * s->grid.res[1] * 3;
+    if (!s->hRgb.ensure(plane * s->grid.res[2] * 4)) return s->fail(MMS_ERR_NOMEM, "pinned allocation of the colour volume failed");
+    for (int g = 0; g < G; ++g) { // the planes of the slab's own cell layers, as in mms_slabs_get_density
+        mms_ctx* c = s->ctx[g];
+        const int p0 = s->plan[g].cellZ0, p1 = g == G - 1 ? s->grid.res[2] : s->plan[g].cellZ0 + s->plan[g].cellNz;
+        if (p1 <= p0) continue;
+        DeviceGuard guard(s->dev[g]);
+        MMS_CUDA(c, cudaMemcpyAsync(s->hRgb.as<float>() + plane * p0, c->isoRgb() + plane * (p0 - s->plan[g].z0), plane * (p1 - p0) * 4,
+            cudaMemcpyDeviceToHost, c->stream));
+    }
+    for (mms_ctx* c : s->ctx)
+        if (int rc = checkDeviceError(c)) return s->failFrom(rc, c);
+    *hrgb = s->hRgb.as<float>();
+    return MMS_OK;
+}
+
+int mms_slabs_get_mesh_colours(mms_slabs* s, const float** col) {
+    if (!s || !col) return MMS_ERR_INVALID;
+    *col = nullptr;
+    if (!s->haveMesh) return s->fail(MMS_ERR_INVALID, "no isosurface has been extracted");
+    if (s->ctx.size() == 1) {
+        uint64_t n = 0;
+        if (int rc = mms_get_mesh(s->ctx[0], &n, nullptr, nullptr, col)) return s->failFrom(rc, s->ctx[0]);
+        return MMS_OK;
+    }
+    const size_t bytes = static_cast<size_t>(s->ntris) * 36;
+    if (!bytes || !s->ctx[0]->haveColour) return MMS_OK;
+    if (!s->hCol.ensure(bytes)) return s->fail(MMS_ERR_NOMEM, "pinned allocation of the mesh colours (%zu bytes) failed", bytes);
+    size_t off = 0;
+    for (size_t g = 0; g < s->ctx.size(); ++g) {
+        mms_ctx* c = s->ctx[g];
+        const size_t b = static_cast<size_t>(c->ntris) * 36;
+        if (b) {
+            DeviceGuard guard(s->dev[g]);
+            MMS_CUDA(c, cudaMemcpyAsync(s->hCol.as<char>() + off, c->meshCol.p, b, cudaMemcpyDeviceToHost, c->stream));
+        }
+        off += b;
+    }
+    for (size_t g = 0; g < s->ctx.size(); ++g) {
+        DeviceGuard guard(s->dev[g]);
+        MMS_CUDA(s->ctx[g], cudaStreamSynchronize(s->ctx[g]->stream));
+    }
+    *col = s->hCol.as<float>();
     return MMS_OK;
 }
 

@@ -107,6 +107,7 @@ struct HaloPeers {
     unsigned* counter[kMaxSlabs]; // this frame's record counter of the peer
     unsigned* arrive[kMaxSlabs];  // this frame's arrival counter of the peer: +1 once ALL my pushes of the frame have landed
     unsigned cap;
+    int colour;                   // QuickSurf colour volume: the record's converted RGBA goes to slot cap + i of the same half
 };
 
 /** After the push kernels of a frame (same stream): clear MY counters of the next frame, then tell every peer that my records of this
@@ -135,7 +136,7 @@ __global__ void halo_wait_kernel(const unsigned* arrive, unsigned npeers, unsign
 
 /**
  * Halo exchange in ONE kernel, no host round trip, no collective: every record of the list that another slab needs (routeMask; the
- * caller switches its own slab off) is appended, as an x y z r record, straight to that slab's receive buffer in peer memory.  A warp
+ * caller switches its own slab off) is appended, as an x y z r record (plus its RGBA colour where the QuickSurf colour volume is on), straight to that slab's receive buffer in peer memory.  A warp
  * claims its slots with one system-scope atomicAdd per destination (ballot-aggregated), so the NVLink atomics stay few.  The order of
  * arrival is arbitrary -- the canonical in-cell order of the binning makes the density independent of it.
  */
@@ -148,6 +149,9 @@ __global__ void __launch_bounds__(256) halo_push_kernel(RouteGeo r, ListDev l, H
         unsigned all = __reduce_or_sync(0xffffffffu, m);
         if (!all) continue;
         const float4 p = m ? fetchParticle(l, j) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        // the colour the binning of a single context would attach to this record (bin_scatter_kernel); the receiver's list is FLOAT_RGBA,
+        // for which the conversion is the identity
+        const float4 col = (m && hp.colour) ? quicksurfColour(l, fetchColourRaw(l, j)) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         for (; all; all &= all - 1) {
             const int d = __ffs(all) - 1;
             const unsigned b = __ballot_sync(0xffffffffu, (m >> d) & 1u);
@@ -156,7 +160,10 @@ __global__ void __launch_bounds__(256) halo_push_kernel(RouteGeo r, ListDev l, H
             base = __shfl_sync(0xffffffffu, base, __ffs(b) - 1);
             if ((m >> d) & 1u) {
                 const unsigned slot = base + __popc(b & lt);
-                if (slot < hp.cap) hp.buf[d][slot] = p; // (an overflow shows in the counter: the receiver reports it)
+                if (slot < hp.cap) { // (an overflow shows in the counter: the receiver reports it)
+                    hp.buf[d][slot] = p;
+                    if (hp.colour) hp.buf[d][hp.cap + slot] = col;
+                }
             }
         }
     }

@@ -83,44 +83,55 @@ def test_z_chunks_on_one_device_equal_one_context(nchunks):
         g.close()
 
 
+@pytest.mark.parametrize("colour", [False, True], ids=["density", "colour"])
 @pytest.mark.parametrize("nchunks", [2, 3])
-def test_gaussian_mode_on_z_chunks_equals_one_context(nchunks):
+def test_gaussian_mode_on_z_chunks_equals_one_context(nchunks, colour):
     """The QuickSurf-Gaussian mode (per-atom radii, non-periodic grid, wide supports: density_gauss_kernel) through the slab group:
-    the halo bound comes from gausslim * radscale * max radius, each chunk bins only the cell layers that reach it -- volume and
-    mesh bit-identical to one context."""
+    the halo bound comes from gausslim * radscale * max radius, each chunk bins only the cell layers that reach it, and with the
+    colour volume on the halo records carry their RGBA -- density, colour volume and (coloured) mesh bit-identical to one context."""
     from megamol_b200 import quicksurf
     from tests import helpers as H
     n = 6000
     data, _, _ = synth.protein_like(n, seed=9, nballs=6, extent=40.0)
-    data = np.ascontiguousarray(data)
-    xyzr = np.ascontiguousarray(data[:, :4])
-    lists = [dict(vtx=xyzr, vtx_type=H.VERT_FLOAT_XYZR, count=n)]
+    data = np.ascontiguousarray(data)  # x y z r | R G B A, stride 32
+    lists = [dict(vtx=data, vtx_type=H.VERT_FLOAT_XYZR, vtx_stride=32, count=n, col=data.ctypes.data + 16, col_type=H.COL_FLOAT_RGBA,
+                  col_stride=32)]
     radscale, spacing, iso = 1.0, 0.8, 0.5
     org, ext, res = quicksurf.grid_from_particles(data[:, :3], data[:, 3], radscale, spacing)
     gl = quicksurf.GAUSSLIM[1]
     one = mm.Surf(0)
     one.set_grid(org, ext, res, (False,) * 3)
-    one.set_params(mode=1, aggregator=0, normalize=0, radscale=radscale, gausslim=gl, colour=0)
+    one.set_params(mode=1, aggregator=0, normalize=0, radscale=radscale, gausslim=gl, colour=int(colour))
     one.push_particles(lists)
     one.compute_density()
-    ref = one.get_density().copy()
+    ref, refrgb = one.get_density(with_rgb=True)
     one.extract_isosurface(iso)
-    rpos, rnrm = one.get_mesh()
-    rpos, rnrm = rpos.copy(), rnrm.copy()
+    if colour:
+        rpos, rnrm, rcol = (a.copy() for a in one.get_mesh(colours=True))
+    else:
+        rpos, rnrm = (a.copy() for a in one.get_mesh())
+        rcol = None
     one.close()
-    assert float(ref.max()) > 1.0 and rpos.shape[0] > 1000
+    assert float(ref.max()) > 1.0 and rpos.shape[0] > 1000 and (refrgb is not None) == colour
     g = mm.SurfGroup([0] * nchunks)
     try:
         g.set_grid(org, ext, res, (False,) * 3)
-        g.set_params(mode=1, aggregator=0, normalize=0, radscale=radscale, gausslim=gl, colour=0)
+        g.set_params(mode=1, aggregator=0, normalize=0, radscale=radscale, gausslim=gl, colour=int(colour))
         for _ in range(2):
             g.clear_particles()
             g.push_particles(lists)
             g.compute_density()
             vol = g.get_density()
+            rgb = g.get_colour_volume()
             g.extract_isosurface(iso)
             pos, nrm = g.get_mesh()
+            col = g.get_mesh_colours(pos.shape[0] * 3)
             assert np.array_equal(vol.view(np.uint32), ref.view(np.uint32)), "volume differs from one context"
             assert pos.shape == rpos.shape and np.array_equal(pos, rpos) and np.array_equal(nrm, rnrm), "mesh differs from one context"
+            if colour:
+                assert np.array_equal(rgb.view(np.uint32), refrgb.view(np.uint32)), "colour volume differs from one context"
+                assert np.array_equal(col.reshape(-1), rcol.reshape(-1)), "mesh colours differ from one context"
+            else:
+                assert rgb is None and col is None
     finally:
         g.close()
