@@ -141,14 +141,14 @@ bool IsoSurfaceB200::buildMesh(VolumetricDataCall* cvd, float iso) {
                 }
             }
             uint64_t nv = 0;
-            const float *gp = nullptr, *gn = nullptr;
+            const float *gp = nullptr, *gn = nullptr, *gc = nullptr; // gc stays NULL unless the slabs carry a QuickSurf colour volume
             if (mms_slabs_adopt_density(this->group, p2d->Group()) != MMS_OK || mms_slabs_extract_isosurface(this->group, iso) != MMS_OK ||
-                mms_slabs_get_mesh(this->group, &nv, &gp, &gn) != MMS_OK) {
+                mms_slabs_get_mesh(this->group, &nv, &gp, &gn) != MMS_OK || mms_slabs_get_mesh_colours(this->group, &gc) != MMS_OK) {
                 Log::DefaultLog.WriteError("IsoSurfaceB200: %s", mms_slabs_last_error(this->group));
                 return false;
             }
             this->mesh.SetMaterial(nullptr);
-            this->mesh.SetVertexData(static_cast<unsigned int>(nv), const_cast<float*>(gp), const_cast<float*>(gn), static_cast<float*>(nullptr),
+            this->mesh.SetVertexData(static_cast<unsigned int>(nv), const_cast<float*>(gp), const_cast<float*>(gn), const_cast<float*>(gc),
                 static_cast<float*>(nullptr), false);
             this->mesh.SetTriangleData(0, static_cast<unsigned int*>(nullptr), false);
             const std::chrono::duration<float, std::milli> msg = std::chrono::high_resolution_clock::now() - t0;

@@ -526,8 +526,8 @@ bool ParticlesToDensityB200::computeVolume(core::AbstractGetData3DCall* in) {
             Log::DefaultLog.WriteError("ParticlesToDensityB200: 'memoryLocation' = VRAM hands out ONE device allocation; it cannot be combined with 'devices'");
             return false;
         }
-        if (p.mode != MMS_MODE_P2D_BUMP || p.aggregator != 0) {
-            Log::DefaultLog.WriteError("ParticlesToDensityB200: 'devices' computes the position aggregator of the bump mode; use 'device' for the other modes");
+        if (!((p.mode == MMS_MODE_P2D_BUMP && p.aggregator == 0) || p.mode == MMS_MODE_QS_GAUSS)) {
+            Log::DefaultLog.WriteError("ParticlesToDensityB200: 'devices' computes the position aggregator of the bump mode or the QuickSurf Gaussian; use 'device' for the other modes");
             return false;
         }
         if (this->group == nullptr || devs != this->groupDevices) {

@@ -270,6 +270,37 @@ def test_quicksurf_mode_through_the_modules(plug, oracle):
         plug.set_param(0, "quicksurf::colour", 0)
 
 
+def test_quicksurf_mode_on_z_chunks_through_the_modules(plug):
+    """`devices` with the QuickSurf mode: the slab group (here the one device named twice = two z-chunks, which runs on a single-GPU box)
+    computes the Gaussian density and its colour volume with coloured halo records, IsoSurfaceB200 adopts the slabs and hands out the
+    coloured mesh -- volume, positions, normals and colours equal the single-context modules' bit for bit."""
+    n = 3000
+    data, _, _ = synth.protein_like(n, seed=3, nballs=5, extent=36.0)
+    data = np.ascontiguousarray(data)
+    lists = [dict(vtx=data, vtx_type=rb.VERT_FLOAT_XYZR, vtx_stride=32, count=n, col=data.ctypes.data + 16, col_type=rb.COL_FLOAT_RGBA,
+                  col_stride=32)]
+    res = (46, 46, 46)
+    plug.set_param(0, "mode", 1)
+    plug.set_param(0, "quicksurf::quality", 1)
+    plug.set_param(0, "quicksurf::colour", 1)
+    outs = []
+    try:
+        for devices in ("", "0,0"):
+            plug.set_param(0, "devices", devices)
+            feed(plug, lists, (0, 0, 0, 36, 36, 36), res, cyclic=(False,) * 3, normalize=False)
+            vol, _ = plug.pull_volume()
+            m = plug.pull_mesh(0.5, colours=True)
+            outs.append((vol.copy(), {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in m.items()}))
+    finally:
+        plug.set_param(0, "devices", "")
+        plug.set_param(0, "mode", 0)
+        plug.set_param(0, "quicksurf::colour", 0)
+    (v1, s1), (v2, s2) = outs
+    assert np.array_equal(v1.view(np.uint32), v2.view(np.uint32))
+    assert s1["nverts"] == s2["nverts"] > 1000 and s1["col"] is not None and s2["col"] is not None
+    assert np.array_equal(s1["pos"], s2["pos"]) and np.array_equal(s1["nrm"], s2["nrm"]) and np.array_equal(s1["col"], s2["col"])
+
+
 def test_marching_tetrahedra_algorithm_matches_the_reference_module(ref, plug, oracle):
     """IsoSurfaceB200 with algorithm = MarchingTetrahedra: on the volume its VolumetricDataCall delivers, the mesh equals the oracle's
     restatement of the reference IsoSurface bit for bit (which itself equals the unmodified module bit for bit: tests/test_oracle_golden.py,
