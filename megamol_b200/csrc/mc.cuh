@@ -561,11 +561,9 @@ __global__ void __launch_bounds__(MC_THREADS, COLOUR ? 2 : 4) mc_emit_kernel(McG
                 float* oc = COLOUR ? outCol + gbase + lane * 3 : nullptr;
                 const float tz0 = pzM2, tz1 = pzM1;
                 const unsigned* etab = sh.etab[warp];
-#ifndef EMIT_UNROLL
-#define EMIT_UNROLL 1 // a row has 2.6 rounds on average: unrolling by two costs more in the remainder logic than the second gather chain gains
-#endif                // (C2: 2.635 -> 2.522 ms; by three: 2.68 ms)
-                constexpr int kEmitUnroll = EMIT_UNROLL;
-#pragma unroll(kEmitUnroll)
+                // not unrolled: a row has 2.6 rounds on average, and unrolling by two costs more in the remainder logic than the second
+                // gather chain gains (C2: 2.635 -> 2.522 ms; by three: 2.68 ms; profiles/rejected/r2_emit_micro_variants.md)
+#pragma unroll 1
                 for (unsigned jc = lane; jc < ncorn; jc += 32, op += 96, on += 96) {
                     const unsigned t = jc / 3;
                     const unsigned ok = owner[t];
