@@ -6,7 +6,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <string>
+#include <thread>
 #include <type_traits>
 #include <vector>
 
@@ -237,6 +239,95 @@ enum Ev { EV_H2D0, EV_H2D1, EV_BIN0, EV_BIN1, EV_DEN1, EV_NRM0, EV_NRM1, EV_MC0,
 
 } // namespace
 
+/** Host -> device copies of PAGEABLE memory (what a MegaMol data source hands out: std::vector / RawStorage): the driver stages those
+ *  through one bounce buffer on the calling thread (~10 GB/s).  Large ones are instead cut into chunks that a few host threads copy
+ *  into pinned slots of their own and send on streams of their own: the memcpy of one chunk overlaps the DMA of another.  Pinned or
+ *  registered sources and small copies take the plain cudaMemcpyAsync. */
+struct HostStager {
+    static constexpr int T = 4;                      // host threads
+    static constexpr size_t CH = 4u << 20;           // chunk size
+    static constexpr size_t kMinBytes = 16u << 20;   // smaller copies: not worth the threads
+    cudaStream_t st[T] = {};
+    void* pin[T][2] = {};
+    cudaEvent_t slotFree[T][2] = {};
+    bool slotUsed[T][2] = {};
+    cudaEvent_t start = nullptr, done[T] = {};
+    bool ready = false, broken = false;
+    bool init() {
+        if (ready || broken) return ready;
+        bool ok = cudaEventCreateWithFlags(&start, cudaEventDisableTiming) == cudaSuccess;
+        for (int t = 0; t < T && ok; ++t) {
+            ok = cudaStreamCreateWithFlags(&st[t], cudaStreamNonBlocking) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&done[t], cudaEventDisableTiming) == cudaSuccess;
+            for (int k = 0; k < 2 && ok; ++k)
+                ok = cudaMallocHost(&pin[t][k], CH) == cudaSuccess && cudaEventCreateWithFlags(&slotFree[t][k], cudaEventDisableTiming) == cudaSuccess;
+        }
+        if (!ok) {
+            cudaGetLastError();
+            release();
+            broken = true;
+            return false;
+        }
+        return ready = true;
+    }
+    void release() {
+        for (int t = 0; t < T; ++t) {
+            if (st[t]) cudaStreamSynchronize(st[t]);
+            for (int k = 0; k < 2; ++k) {
+                if (pin[t][k]) cudaFreeHost(pin[t][k]);
+                if (slotFree[t][k]) cudaEventDestroy(slotFree[t][k]);
+                pin[t][k] = nullptr, slotFree[t][k] = nullptr, slotUsed[t][k] = false;
+            }
+            if (done[t]) cudaEventDestroy(done[t]);
+            if (st[t]) cudaStreamDestroy(st[t]);
+            done[t] = nullptr, st[t] = nullptr;
+        }
+        if (start) cudaEventDestroy(start);
+        start = nullptr;
+        ready = false;
+    }
+    /** dst[0, bytes) <- src[0, bytes), ordered like a copy enqueued on `order` (it starts after what is in `order` now; work enqueued on
+     *  `order` afterwards waits for it).  The source has been read completely when this returns. */
+    cudaError_t copy(int device, char* dst, const char* src, size_t bytes, cudaStream_t order) {
+        cudaError_t e = cudaEventRecord(start, order);
+        if (e != cudaSuccess) return e;
+        std::atomic<int> err{static_cast<int>(cudaSuccess)};
+        const size_t nchunks = (bytes + CH - 1) / CH;
+        auto work = [&](int t) {
+            if (cudaSetDevice(device) != cudaSuccess || cudaStreamWaitEvent(st[t], start, 0) != cudaSuccess) {
+                err = static_cast<int>(cudaErrorUnknown);
+                return;
+            }
+            size_t round = 0;
+            for (size_t c = static_cast<size_t>(t); c < nchunks; c += T, ++round) {
+                const int k = static_cast<int>(round & 1u);
+                const size_t off = c * CH, n = std::min(CH, bytes - off);
+                cudaError_t r = slotUsed[t][k] ? cudaEventSynchronize(slotFree[t][k]) : cudaSuccess; // the slot's previous chunk has left
+                if (r == cudaSuccess) {
+                    std::memcpy(pin[t][k], src + off, n);
+                    r = cudaMemcpyAsync(dst + off, pin[t][k], n, cudaMemcpyHostToDevice, st[t]);
+                }
+                if (r == cudaSuccess) r = cudaEventRecord(slotFree[t][k], st[t]);
+                if (r != cudaSuccess) {
+                    err = static_cast<int>(r);
+                    return;
+                }
+                slotUsed[t][k] = true;
+            }
+            const cudaError_t r = cudaEventRecord(done[t], st[t]);
+            if (r != cudaSuccess) err = static_cast<int>(r);
+        };
+        std::thread th[T];
+        for (int t = 1; t < T; ++t) th[t] = std::thread(work, t);
+        work(0);
+        for (int t = 1; t < T; ++t) th[t].join();
+        if (err.load() != static_cast<int>(cudaSuccess)) return static_cast<cudaError_t>(err.load());
+        for (int t = 0; t < T; ++t)
+            if ((e = cudaStreamWaitEvent(order, done[t], 0)) != cudaSuccess) return e;
+        return cudaSuccess;
+    }
+};
+
 struct mms_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -249,6 +340,7 @@ struct mms_ctx {
     Arena arena[2];
     int arenaCur = 0;
     cudaStream_t copyStream = nullptr;
+    HostStager stager;
     cudaEvent_t uploadDone = nullptr;
     cudaEvent_t countReady = nullptr; // recorded behind the count's publish kernel: the host waits for THIS, not for the whole stream
     cudaEvent_t volReady = nullptr, volCopied = nullptr; // mms_prefetch_density: volume final on the compute stream / host copy complete
@@ -343,6 +435,18 @@ bool isDevicePointer(const void* p) {
         return false;
     }
     return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+/** Host -> device upload on the context's copy stream; pageable sources of 16 MB and more go through the HostStager. */
+cudaError_t uploadHost(mms_ctx* c, char* dst, const char* src, size_t bytes) {
+    if (bytes >= HostStager::kMinBytes && !getenv("MMS_NO_STAGER")) {
+        cudaPointerAttributes a{};
+        bool pageable = false;
+        if (cudaPointerGetAttributes(&a, src) != cudaSuccess) cudaGetLastError(), pageable = true; // (older drivers: an error for plain host memory)
+        else pageable = a.type == cudaMemoryTypeUnregistered;
+        if (pageable && c->stager.init()) return c->stager.copy(c->device, dst, src, bytes, c->copyStream);
+    }
+    return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->copyStream);
 }
 
 int alignOf(const void* p, unsigned stride, int want) {
@@ -580,6 +684,7 @@ int mms_destroy(mms_ctx* c) {
         for (PinBuf* b : {&c->hState, &c->hVol, &c->hRgb, &c->hPos, &c->hNrm, &c->hCol, &c->hHome, &c->hTri, &c->hRoute, &c->hDir, &c->hIdx}) b->release();
         cudaStreamSynchronize(c->stream);
         cudaStreamSynchronize(c->copyStream);
+        c->stager.release();
         for (auto& a : c->arena) {
             a.release();
             cudaEventDestroy(a.consumed);
@@ -683,7 +788,7 @@ static int pushLists(mms_ctx* c, int32_t nlists, const mms_list* lists, const vo
             }
             char* dbase = arena.alloc(static_cast<size_t>(hi - lo), mis);
             if (!dbase) return c->fail(MMS_ERR_NOMEM, "device allocation of %zu bytes for list %d failed", static_cast<size_t>(hi - lo), i);
-            MMS_CUDA(c, cudaMemcpyAsync(dbase, lo, static_cast<size_t>(hi - lo), cudaMemcpyHostToDevice, c->copyStream));
+            MMS_CUDA(c, uploadHost(c, dbase, lo, static_cast<size_t>(hi - lo)));
             d.vtx = dbase + (hv - lo);
             if (d.ctype) {
                 if (interleaved) {
@@ -691,7 +796,7 @@ static int pushLists(mms_ctx* c, int32_t nlists, const mms_list* lists, const vo
                 } else {
                     char* dc = arena.alloc(cbytes, reinterpret_cast<uintptr_t>(hc) & 15u);
                     if (!dc) return c->fail(MMS_ERR_NOMEM, "device allocation of %zu bytes for colours of list %d failed", cbytes, i);
-                    MMS_CUDA(c, cudaMemcpyAsync(dc, hc, cbytes, cudaMemcpyHostToDevice, c->copyStream));
+                    MMS_CUDA(c, uploadHost(c, dc, hc, cbytes));
                     d.col = dc;
                 }
             }
@@ -710,7 +815,7 @@ static int pushLists(mms_ctx* c, int32_t nlists, const mms_list* lists, const vo
                 }
                 char* dd = arena.alloc(dbytes, reinterpret_cast<uintptr_t>(hd) & 15u);
                 if (!dd) return c->fail(MMS_ERR_NOMEM, "device allocation of %zu bytes for directions of list %d failed", dbytes, i);
-                MMS_CUDA(c, cudaMemcpyAsync(dd, hd, dbytes, cudaMemcpyHostToDevice, c->copyStream));
+                MMS_CUDA(c, uploadHost(c, dd, hd, dbytes));
                 d.dir = dd;
                 c->uploadPending = true;
             }
